@@ -1,0 +1,199 @@
+/*
+ * om_b200.h -- C ABI of the B200-native env-step hot path for olympics-mujoco.
+ *
+ * The reference (pigBond/olympics-mujoco) is pure Python; its "FFI" for this path is the set of Python
+ * calls into MuJoCo / mushroom_rl / NumPy listed beside each entry point below (paths relative to the
+ * reference root).  A maintainer binds these symbols with ctypes.
+ *
+ * Conventions
+ *  - Every `float* / uint8_t* / int32_t*` argument is a DEVICE pointer unless its name ends in `_host`.
+ *  - Per-env arrays are structure-of-arrays with the env index fastest: element (c, env) of an array
+ *    with C components lives at  a[c*ld + env],  ld >= n (number of envs).  A MuJoCo field that is
+ *    [nbody,3] per env therefore has C = nbody*3 components, component index body*3+axis.
+ *    Rollout buffers are time-major: (t, c, env) at a[(t*C + c)*ld + env].
+ *  - Quaternions are [w,x,y,z]; spatial velocities are [rot(3); lin(3)] (MuJoCo conventions).
+ *  - `stream` is a cudaStream_t passed as void*; every call only ENQUEUES work on it (no host sync)
+ *    unless documented otherwise.  Inputs are not retained after the call returns (tables are copied).
+ *  - Return value: 0 on success, non-zero on error; om_last_error() returns a thread-local message.
+ *    There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef OM_B200_H
+#define OM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OM_ABI_VERSION 1
+
+/* mjtJoint values (mujoco==2.3.6) */
+#define OM_JNT_FREE 0
+#define OM_JNT_BALL 1
+#define OM_JNT_SLIDE 2
+#define OM_JNT_HINGE 3
+
+#define OM_MAX_BODY 48
+#define OM_MAX_JNT 48
+#define OM_MAX_SITE 8
+
+const char* om_last_error(void);
+int om_abi_version(void);
+/* number of kernels launched by this library since load / since om_reset_launch_count() */
+long long om_launch_count(void);
+void om_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Model constants.  Replaces the mjModel produced by MuJoCo's MJCF compiler
+ * (loco_env_base.py:143-155 MultiMuJoCo.__init__; UnitreeH1.py:70-111).  All pointers are HOST.
+ * Doubles are converted to float on upload. */
+typedef struct OmModelDesc {
+  const char* name;            /* "UnitreeH1" / "StickFigureA3" select a specialised kernel when the
+                                  tables match the ones it was generated from; anything else runs the
+                                  table-driven kernel */
+  int nbody, njnt, nsite, nq, nv;
+  const int32_t* body_parentid;  /* [nbody] */
+  const int32_t* body_rootid;    /* [nbody] */
+  const int32_t* body_jntadr;    /* [nbody], -1 if none */
+  const int32_t* body_jntnum;    /* [nbody] */
+  const double* body_pos;        /* [nbody,3] */
+  const double* body_quat;       /* [nbody,4] normalised */
+  const double* body_ipos;       /* [nbody,3] */
+  const double* body_mass;       /* [nbody] */
+  const int32_t* jnt_type;       /* [njnt] */
+  const int32_t* jnt_qposadr;    /* [njnt] */
+  const int32_t* jnt_dofadr;     /* [njnt] */
+  const double* jnt_axis;        /* [njnt,3] */
+  const double* jnt_pos;         /* [njnt,3] */
+  const double* qpos0;           /* [nq] */
+  const int32_t* site_bodyid;    /* [nsite] */
+  const double* site_pos;        /* [nsite,3] */
+  const double* site_quat;       /* [nsite,4] */
+} OmModelDesc;
+
+typedef struct OmModel OmModel;
+int om_model_create(const OmModelDesc* desc, OmModel** out);
+void om_model_destroy(OmModel* m);
+/* 1 when the model is served by a generated (topology-specialised) kernel, 0 for the table-driven one */
+int om_model_is_specialised(const OmModel* m);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1: forward kinematics + COM + COM velocity = the subset of mujoco.mj_forward the path consumes
+ * (mj_kinematics + mj_comPos + mj_comVel; call sites loco_env_base.py:410,525,1160 and
+ * mujoco_robot_interface.py:468).  Any output pointer may be NULL.
+ *   qpos [nq][ld], qvel [nv][ld] -> xpos [nbody*3][ld], xquat [nbody*4][ld], site_xpos [nsite*3][ld],
+ *   site_xmat [nsite*9][ld], cvel [nbody*6][ld], subtree_com [3][ld] (COM of the tree of body 1).
+ * force_generic != 0 runs the table-driven kernel even when a specialised one exists. */
+int om_fk(const OmModel* m, const float* qpos, const float* qvel, int n, int ld,
+          float* xpos, float* xquat, float* site_xpos, float* site_xmat, float* cvel, float* subtree_com,
+          int force_generic, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2 (H1 flavour): the tail of mushroom_rl MuJoCo.step for UnitreeH1 after the physics:
+ *   ObservationHelper._build_obs + LocoEnvBase._create_observation (loco_env_base.py:737-767),
+ *   UnitreeH1._has_fallen (UnitreeH1.py:162-203) through is_absorbing (base_humanoid_robot.py:246-260),
+ *   TargetVelocityReward on the PREVIOUS observation (utils/reward.py:66-74), fused with K1.
+ * obs_perm[k] (HOST, length n_obs_q) = qpos/qvel address of observation-spec entry k; the emitted
+ * observation drops the first two position entries: obs has 2*n_obs_q-2 components.
+ * prev_x_vel [ld] = row x_vel_idx of the previous observation.  FK outputs may be NULL. */
+typedef struct OmH1Spec {
+  int n_obs_q;                 /* 17 */
+  int32_t obs_perm[32];
+  int x_vel_idx;               /* index of dq_pelvis_tx in the emitted observation (15) */
+  float target_velocity;       /* 1.25 walk / 2.5 run (base_humanoid_robot.py:149-154) */
+  int use_absorbing_states;    /* base_humanoid_robot.py:260 */
+} OmH1Spec;
+
+int om_h1_step(const OmModel* m, const OmH1Spec* spec, const float* qpos, const float* qvel,
+               const float* prev_x_vel, int n, int ld,
+               float* xpos, float* xquat, float* site_xpos, float* cvel,
+               float* obs, float* reward, uint8_t* absorbing, void* stream);
+
+/* has_fallen over a batch of observations (create_dataset check, loco_env_base.py:950-957) */
+int om_h1_has_fallen(const float* obs, int n, int ld, uint8_t* fallen, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3: reference-trajectory table and per-env integer state.  Replaces utils/trajectory.py
+ * reset_trajectory :289-323, get_current_sample :381-387, get_next_sample :389-401 and the wrap ->
+ * reset policy of loco_env_base.py:534-537, :639-657.
+ * table_host: float64 [K][n_traj][T] (the layout of Trajectory.trajectories after resampling).
+ * Channels 0 and 1 (root x, y) are kept in float64 on the device because every reset re-centres them. */
+typedef struct OmTraj OmTraj;
+int om_traj_create(const double* table_host, int K, int n_traj, int T, OmTraj** out);
+void om_traj_destroy(OmTraj* t);
+
+/* Reset envs.  mask (may be NULL = all): reset env i iff mask[i] != 0.  forced_traj / forced_step (may be
+ * NULL) >= 0 override the random draw (reset_trajectory(substep_no, traj_no)).  Random draws follow the
+ * Philox contract (oracle/philox.py): key = seed, counter = (env_id0 + i, reset_count[i], 0, 0).
+ * State: traj_no, step_no [n] int32, reset_count [n] uint32 (incremented), xy_off [2][ld] float64.
+ * sample (may be NULL) [K][ld] = the current sample after the reset. */
+int om_traj_reset(const OmTraj* t, uint64_t seed, uint32_t env_id0, const uint8_t* mask,
+                  const int32_t* forced_traj, const int32_t* forced_step,
+                  int32_t* traj_no, int32_t* step_no, uint32_t* reset_count, double* xy_off,
+                  float* sample, int n, int ld, void* stream);
+/* get_current_sample for every env */
+int om_traj_current(const OmTraj* t, const int32_t* traj_no, const int32_t* step_no, const double* xy_off,
+                    float* sample, int n, int ld, void* stream);
+/* get_next_sample; an env that reaches the end of its trajectory is reset (wrapped[i] = 1) exactly as
+ * loco_env_base.py:534-537 does */
+int om_traj_next(const OmTraj* t, uint64_t seed, uint32_t env_id0,
+                 int32_t* traj_no, int32_t* step_no, uint32_t* reset_count, double* xy_off,
+                 float* sample, uint8_t* wrapped, int n, int ld, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused playback: LocoEnvBase.play_trajectory_from_velocity (loco_env_base.py:444-560) for n envs,
+ * one episode of n_steps steps per call (call once per episode; the end-of-episode reset :555-557 is
+ * performed when end_episode_reset != 0).  Per step: Euler step of the 17 coordinates (:515-519),
+ * set_sim_state (:659-684), K1, next sample / wrap reset (:532-537), observation from the next sample
+ * (:539), has_fallen (:541), TargetVelocityReward on the previous observation.
+ * State in/out: traj_no, step_no, reset_count, xy_off, curr_qpos [n_obs_q][ld] (spec order, float64),
+ * pending [K][ld] (the `sample` variable of the loop), prev_x_vel [ld].
+ * Outputs (any may be NULL), time-major [n_steps][C][ld]: xpos, xquat, site_xpos, cvel, obs, reward,
+ * fallen (uint8), traj_no_t / step_no_t (int32 state after each step). */
+typedef struct OmPlayState {
+  int32_t* traj_no; int32_t* step_no; uint32_t* reset_count; double* xy_off;
+  double* curr_qpos; float* pending; float* prev_x_vel;
+} OmPlayState;
+typedef struct OmPlayOut {
+  float* xpos; float* xquat; float* site_xpos; float* cvel; float* obs; float* reward;
+  uint8_t* fallen; int32_t* traj_no_t; int32_t* step_no_t;
+} OmPlayOut;
+int om_h1_play_from_velocity(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, uint64_t seed,
+                             uint32_t env_id0, float dt, int n_steps, int end_episode_reset,
+                             const OmPlayState* state, const OmPlayOut* out, int n, int ld, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5: returns / advantages over a time-major rollout buffer [T][ld].
+ * om_ppo_returns: PPOBuffer.finish_path (rl/algos/ppo.py:68-84) with the bootstrap of :195-196.
+ *   path_end[t][i] (may be NULL): 0 = the path continues, 1 = it terminated at step t (bootstrap 0),
+ *   2 = it was truncated at step t (max_traj_len, ppo.py:180) and bootstraps with v_next[t][i].
+ *   The buffer end (t == T-1) always closes the path: bootstrap 0 if path_end == 1, else v_next (flag 2)
+ *   or v_last[i] (= (not done) * V(s_T)).  ret = discounted return, adv = ret - values (:335).
+ * om_gae: mushroom_rl.utils.value_functions.compute_gae (called gail_TRPO.py:126): per env,
+ *   adv_t = r_t + gamma*v_next_t*(1-absorbing_t) - v_t            if last_t or t == T-1
+ *         = r_t + gamma*v_next_t - v_t + gamma*lam*adv_{t+1}      otherwise;  v_target = adv + v. */
+int om_ppo_returns(const float* rewards, const float* values, const uint8_t* path_end, const float* v_next,
+                   const float* v_last, float gamma, int T, int n, int ld, float* ret, float* adv, void* stream);
+int om_gae(const float* rewards, const float* v, const float* v_next, const uint8_t* absorbing,
+           const uint8_t* last, float gamma, float lam, int T, int n, int ld,
+           float* adv, float* v_target, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K6: moment partial sums (Standardizer.update_mean_std networks.py:76-81; get_normalization_params
+ * rl/envs/normalize.py:48; advantage mean/std ppo.py:336, gail_TRPO.py:128).
+ * x is [rows][C][ld] (rows = T or 1); sums over rows and envs.  out [2*C+1] float64 on the DEVICE:
+ * sum[C], sumsq[C], count -- ADDED to the existing contents (zero it first), so that a multi-GPU caller
+ * can all-reduce the same buffer with ncclAllReduce(sum). */
+int om_moments(const float* x, int rows, int C, int n, int ld, double* out, void* stream);
+/* stats[0] = mean, stats[1] = std + eps from a one-component moment buffer [sum, sumsq, count] (device);
+ * unbiased != 0 -> torch.std (ppo.py:336, eps 1e-5), 0 -> np.std (gail_TRPO.py:128, eps 1e-8). */
+int om_adv_stats(const double* moments, int unbiased, double eps, double* stats, void* stream);
+/* y = (x - mean) / denom element-wise for a [rows][ld] array with device scalars stats[0]=mean,
+ * stats[1]=denom (advantage normalisation); in place allowed. */
+int om_normalize(const float* x, const double* stats, int rows, int n, int ld, float* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OM_B200_H */

@@ -1,0 +1,105 @@
+"""ctypes binding of libom_b200.so (the C ABI declared in include/om_b200.h).
+
+There is no CPU implementation behind these calls: if the shared library is missing, or no CUDA device
+is present, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libom_b200.so"
+
+c_f32p = C.c_void_p      # device pointers travel as integers
+_lib = None
+
+
+class OmModelDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p),
+                ("nbody", C.c_int), ("njnt", C.c_int), ("nsite", C.c_int), ("nq", C.c_int), ("nv", C.c_int),
+                ("body_parentid", C.c_void_p), ("body_rootid", C.c_void_p), ("body_jntadr", C.c_void_p),
+                ("body_jntnum", C.c_void_p), ("body_pos", C.c_void_p), ("body_quat", C.c_void_p),
+                ("body_ipos", C.c_void_p), ("body_mass", C.c_void_p), ("jnt_type", C.c_void_p),
+                ("jnt_qposadr", C.c_void_p), ("jnt_dofadr", C.c_void_p), ("jnt_axis", C.c_void_p),
+                ("jnt_pos", C.c_void_p), ("qpos0", C.c_void_p), ("site_bodyid", C.c_void_p),
+                ("site_pos", C.c_void_p), ("site_quat", C.c_void_p)]
+
+
+class OmH1Spec(C.Structure):
+    _fields_ = [("n_obs_q", C.c_int), ("obs_perm", C.c_int32 * 32), ("x_vel_idx", C.c_int),
+                ("target_velocity", C.c_float), ("use_absorbing_states", C.c_int)]
+
+
+class OmPlayState(C.Structure):
+    _fields_ = [("traj_no", C.c_void_p), ("step_no", C.c_void_p), ("reset_count", C.c_void_p),
+                ("xy_off", C.c_void_p), ("curr_qpos", C.c_void_p), ("pending", C.c_void_p),
+                ("prev_x_vel", C.c_void_p)]
+
+
+class OmPlayOut(C.Structure):
+    _fields_ = [("xpos", C.c_void_p), ("xquat", C.c_void_p), ("site_xpos", C.c_void_p), ("cvel", C.c_void_p),
+                ("obs", C.c_void_p), ("reward", C.c_void_p), ("fallen", C.c_void_p), ("traj_no_t", C.c_void_p),
+                ("step_no_t", C.c_void_p)]
+
+
+_P, _I, _F, _D = C.c_void_p, C.c_int, C.c_float, C.c_double
+_U64, _U32 = C.c_uint64, C.c_uint32
+
+# name -> (restype, argtypes); kept in the order of include/om_b200.h
+PROTOTYPES = {
+    "om_last_error": (C.c_char_p, []),
+    "om_abi_version": (_I, []),
+    "om_launch_count": (C.c_longlong, []),
+    "om_reset_launch_count": (None, []),
+    "om_model_create": (_I, [C.POINTER(OmModelDesc), C.POINTER(_P)]),
+    "om_model_destroy": (None, [_P]),
+    "om_model_is_specialised": (_I, [_P]),
+    "om_fk": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "om_h1_step": (_I, [_P, C.POINTER(OmH1Spec), _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "om_h1_has_fallen": (_I, [_P, _I, _I, _P, _P]),
+    "om_traj_create": (_I, [_P, _I, _I, _I, C.POINTER(_P)]),
+    "om_traj_destroy": (None, [_P]),
+    "om_traj_reset": (_I, [_P, _U64, _U32, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "om_traj_current": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
+    "om_traj_next": (_I, [_P, _U64, _U32, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "om_h1_play_from_velocity": (_I, [_P, C.POINTER(OmH1Spec), _P, _U64, _U32, _F, _I, _I,
+                                      C.POINTER(OmPlayState), C.POINTER(OmPlayOut), _I, _I, _P]),
+    "om_ppo_returns": (_I, [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P]),
+    "om_gae": (_I, [_P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P, _P]),
+    "om_moments": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "om_adv_stats": (_I, [_P, _I, _D, _P, _P]),
+    "om_normalize": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+}
+
+
+class OmError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and declare every prototype.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise OmError(f"{LIB_PATH} is missing: run `python -m olympics_mujoco_b200.build` "
+                      "(nvcc, sm_100a).  This package has no CPU fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise OmError(load().om_last_error().decode())
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise OmError("no CUDA device: olympics_mujoco_b200 computes only on the GPU (no CPU fallback)")

@@ -1,0 +1,186 @@
+// K1 entry point (om_fk) and K2/H1 (om_h1_step, om_h1_has_fallen).
+#include "om_common.cuh"
+#include "om_fk_generic.cuh"
+#include "om_sinks.cuh"
+#include "gen/fk_unitree_h1.cuh"
+#include "gen/fk_stick_figure_a3.cuh"
+
+namespace om {
+
+// ---------------------------------------------------------------- specialised FK kernels
+template <int MODEL> struct FkSpec;
+template <> struct FkSpec<SPEC_H1> {
+  static constexpr int NQ = 17, NV = 17;
+  template <class S> static OM_HD void run(const float (&q)[17], const float (&qd)[17], S& s) { om_fk_unitree_h1(q, qd, s); }
+};
+template <> struct FkSpec<SPEC_A3> {
+  static constexpr int NQ = 25, NV = 24;
+  template <class S> static OM_HD void run(const float (&q)[25], const float (&qd)[24], S& s) { om_fk_stick_figure_a3(q, qd, s); }
+};
+
+template <int MODEL, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) fk_spec_kernel(const float* __restrict__ qpos, const float* __restrict__ qvel,
+                                                        int n, int ld, FkOut o) {
+  using M = FkSpec<MODEL>;
+  const int env = blockIdx.x * BLOCK + threadIdx.x;
+  if (env >= n) return;
+  float q[M::NQ], qd[M::NV];
+#pragma unroll
+  for (int k = 0; k < M::NQ; ++k) q[k] = qpos[(size_t)k * ld + env];
+#pragma unroll
+  for (int k = 0; k < M::NV; ++k) qd[k] = qvel ? qvel[(size_t)k * ld + env] : 0.f;
+  SoaSink<true> S{o.xpos, o.xquat, o.site_xpos, o.site_xmat, o.cvel, o.com, (size_t)ld, (size_t)env};
+  M::run(q, qd, S);
+}
+
+// ---------------------------------------------------------------- H1 observation / reward / absorbing
+// has_fallen thresholds are float64 in the reference (UnitreeH1.py:176-179); comparing the fp32 value in
+// double keeps the flag bit-exact with the float64 oracle on fp32-representable inputs.
+OM_HD bool h1_has_fallen(float y, float tilt, float lst, float rot) {
+  const double PI = 3.141592653589793;
+  const double dy = y, dt = tilt, dl = lst, dr = rot;
+  const bool cy = (dy < -0.3) || (dy > 0.1);
+  const bool ct = (dt < (-PI / 4.5)) || (dt > (PI / 12));
+  const bool cl = (dl < -PI / 12) || (dl > PI / 8);
+  const bool cr = (dr < (-PI / 8)) || (dr > (PI / 8));
+  return cy || ct || cl || cr;
+}
+
+struct H1SpecDev {
+  int n_obs_q, x_vel_idx, use_absorbing;
+  float target;
+  int perm[32];
+};
+
+// obs / reward / absorbing from qpos/qvel (SoA pass; one thread per env, every access coalesced)
+__device__ __forceinline__ void h1_obs_reward(const H1SpecDev& sp, const float* __restrict__ qpos,
+                                              const float* __restrict__ qvel, const float* __restrict__ prev_x_vel,
+                                              int ld, int env, float* __restrict__ obs, float* __restrict__ reward,
+                                              uint8_t* __restrict__ absorbing) {
+  const int nq = sp.n_obs_q;
+  float head[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = 2; k < nq; ++k) {
+    const float v = qpos[(size_t)sp.perm[k] * ld + env];
+    if (k < 6) head[k - 2] = v;
+    if (obs) obs[(size_t)(k - 2) * ld + env] = v;
+  }
+  if (obs)
+    for (int k = 0; k < nq; ++k) obs[(size_t)(nq - 2 + k) * ld + env] = qvel[(size_t)sp.perm[k] * ld + env];
+  if (absorbing) absorbing[env] = (sp.use_absorbing && h1_has_fallen(head[0], head[1], head[2], head[3])) ? 1 : 0;
+  if (reward) {
+    const float d = prev_x_vel[env] - sp.target;
+    reward[env] = expf(-(d * d));
+  }
+}
+
+template <int BLOCK, bool WRITE_FK>
+__global__ void __launch_bounds__(BLOCK) h1_step_kernel(H1SpecDev sp, const float* __restrict__ qpos,
+                                                        const float* __restrict__ qvel,
+                                                        const float* __restrict__ prev_x_vel, int n, int ld, FkOut o,
+                                                        float* __restrict__ obs, float* __restrict__ reward,
+                                                        uint8_t* __restrict__ absorbing) {
+  const int env = blockIdx.x * BLOCK + threadIdx.x;
+  if (env >= n) return;
+  h1_obs_reward(sp, qpos, qvel, prev_x_vel, ld, env, obs, reward, absorbing);
+  if (WRITE_FK) {
+    float q[17], qd[17];
+#pragma unroll
+    for (int k = 0; k < 17; ++k) q[k] = qpos[(size_t)k * ld + env];
+#pragma unroll
+    for (int k = 0; k < 17; ++k) qd[k] = qvel[(size_t)k * ld + env];
+    SoaSink<false> S{o.xpos, o.xquat, o.site_xpos, nullptr, o.cvel, o.com, (size_t)ld, (size_t)env};
+    om_fk_unitree_h1(q, qd, S);
+  }
+}
+
+__global__ void __launch_bounds__(128) h1_obs_kernel(H1SpecDev sp, const float* __restrict__ qpos,
+                                                     const float* __restrict__ qvel, const float* __restrict__ prev_x_vel,
+                                                     int n, int ld, float* __restrict__ obs, float* __restrict__ reward,
+                                                     uint8_t* __restrict__ absorbing) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  h1_obs_reward(sp, qpos, qvel, prev_x_vel, ld, env, obs, reward, absorbing);
+}
+
+__global__ void __launch_bounds__(256) h1_fallen_kernel(const float* __restrict__ obs, int n, int ld,
+                                                        uint8_t* __restrict__ fallen) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  fallen[env] = h1_has_fallen(obs[env], obs[(size_t)ld + env], obs[(size_t)2 * ld + env], obs[(size_t)3 * ld + env]) ? 1 : 0;
+}
+
+int make_spec(const OmH1Spec* spec, const OmModel* m, H1SpecDev* out) {
+  OM_REQUIRE(spec->n_obs_q >= 6 && spec->n_obs_q <= 32, "OmH1Spec.n_obs_q %d outside [6,32]", spec->n_obs_q);
+  OM_REQUIRE(spec->n_obs_q <= m->host.nq && spec->n_obs_q <= m->host.nv, "OmH1Spec.n_obs_q exceeds nq/nv");
+  out->n_obs_q = spec->n_obs_q;
+  out->x_vel_idx = spec->x_vel_idx;
+  out->use_absorbing = spec->use_absorbing_states;
+  out->target = spec->target_velocity;
+  for (int k = 0; k < 32; ++k) {
+    out->perm[k] = k < spec->n_obs_q ? spec->obs_perm[k] : 0;
+    OM_REQUIRE(out->perm[k] >= 0 && out->perm[k] < m->host.nq, "OmH1Spec.obs_perm[%d] out of range", k);
+  }
+  return 0;
+}
+
+}  // namespace om
+
+using namespace om;
+
+extern "C" int om_fk(const OmModel* m, const float* qpos, const float* qvel, int n, int ld, float* xpos, float* xquat,
+                     float* site_xpos, float* site_xmat, float* cvel, float* subtree_com, int force_generic,
+                     void* stream) {
+  OM_REQUIRE(m && qpos, "om_fk: null model or qpos");
+  OM_REQUIRE(n >= 0 && ld >= n, "om_fk: need 0 <= n <= ld (n=%d ld=%d)", n, ld);
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  FkOut o{xpos, xquat, site_xpos, site_xmat, cvel, subtree_com};
+  constexpr int BLOCK = 128;
+  const int grid = ceil_div(n, BLOCK);
+  if (!force_generic && m->specialised == SPEC_H1)
+    fk_spec_kernel<SPEC_H1, BLOCK><<<grid, BLOCK, 0, st>>>(qpos, qvel, n, ld, o);
+  else if (!force_generic && m->specialised == SPEC_A3)
+    fk_spec_kernel<SPEC_A3, BLOCK><<<grid, BLOCK, 0, st>>>(qpos, qvel, n, ld, o);
+  else
+    fk_generic_kernel<<<grid, BLOCK, 0, st>>>(m->dev, qpos, qvel, n, ld, o);
+  OM_LAUNCHED();
+  return 0;
+}
+
+extern "C" int om_h1_step(const OmModel* m, const OmH1Spec* spec, const float* qpos, const float* qvel,
+                          const float* prev_x_vel, int n, int ld, float* xpos, float* xquat, float* site_xpos,
+                          float* cvel, float* obs, float* reward, uint8_t* absorbing, void* stream) {
+  OM_REQUIRE(m && spec && qpos && qvel, "om_h1_step: null argument");
+  OM_REQUIRE(n >= 0 && ld >= n, "om_h1_step: need 0 <= n <= ld (n=%d ld=%d)", n, ld);
+  OM_REQUIRE(!reward || prev_x_vel, "om_h1_step: reward requested without prev_x_vel");
+  if (n == 0) return 0;
+  H1SpecDev sp;
+  if (make_spec(spec, m, &sp)) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  FkOut o{xpos, xquat, site_xpos, nullptr, cvel, nullptr};
+  const bool want_fk = xpos || xquat || site_xpos || cvel;
+  constexpr int BLOCK = 128;
+  const int grid = ceil_div(n, BLOCK);
+  if (m->specialised == SPEC_H1) {
+    if (want_fk) h1_step_kernel<BLOCK, true><<<grid, BLOCK, 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);
+    else h1_step_kernel<BLOCK, false><<<grid, BLOCK, 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);
+    OM_LAUNCHED();
+  } else {
+    if (want_fk) {
+      fk_generic_kernel<<<grid, BLOCK, 0, st>>>(m->dev, qpos, qvel, n, ld, o);
+      OM_LAUNCHED();
+    }
+    h1_obs_kernel<<<grid, BLOCK, 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, obs, reward, absorbing);
+    OM_LAUNCHED();
+  }
+  return 0;
+}
+
+extern "C" int om_h1_has_fallen(const float* obs, int n, int ld, uint8_t* fallen, void* stream) {
+  OM_REQUIRE(obs && fallen, "om_h1_has_fallen: null argument");
+  OM_REQUIRE(n >= 0 && ld >= n, "om_h1_has_fallen: need 0 <= n <= ld");
+  if (n == 0) return 0;
+  h1_fallen_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(obs, n, ld, fallen);
+  OM_LAUNCHED();
+  return 0;
+}

@@ -1,0 +1,292 @@
+// K3: reference-trajectory table + per-env integer state, and the fused H1 playback kernel.
+#include <vector>
+
+#include "om_common.cuh"
+#include "om_sinks.cuh"
+#include "om_traj.cuh"
+#include "gen/fk_unitree_h1.cuh"
+#include "gen/h1_perm.h"
+
+namespace om {
+
+// ---------------------------------------------------------------- per-step API kernels
+__global__ void __launch_bounds__(128) traj_reset_kernel(TrajDev t, uint64_t seed, uint32_t env_id0,
+                                                         const uint8_t* __restrict__ mask,
+                                                         const int32_t* __restrict__ forced_traj,
+                                                         const int32_t* __restrict__ forced_step,
+                                                         int32_t* traj_no, int32_t* step_no, uint32_t* reset_count,
+                                                         double* xy_off, float* sample, int n, int ld) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  if (mask && !mask[env]) return;
+  int tr, st;
+  uint32_t rc = reset_count[env];
+  traj_draw(t, seed, env_id0 + env, rc, tr, st);
+  if (forced_traj && forced_traj[env] >= 0) tr = min(forced_traj[env], t.n_traj - 1);
+  if (forced_step && forced_step[env] >= 0) st = min(forced_step[env], t.T - 1);
+  reset_count[env] = rc + 1;
+  traj_no[env] = tr;
+  step_no[env] = st;
+  const double ox = t.xy[((size_t)tr * t.T + st) * 2], oy = t.xy[((size_t)tr * t.T + st) * 2 + 1];
+  xy_off[env] = ox;
+  xy_off[(size_t)ld + env] = oy;
+  if (sample) traj_write_sample(t, tr, st, ox, oy, sample, ld, env);
+}
+
+__global__ void __launch_bounds__(128) traj_current_kernel(TrajDev t, const int32_t* __restrict__ traj_no,
+                                                           const int32_t* __restrict__ step_no,
+                                                           const double* __restrict__ xy_off, float* sample, int n,
+                                                           int ld) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  traj_write_sample(t, traj_no[env], step_no[env], xy_off[env], xy_off[(size_t)ld + env], sample, ld, env);
+}
+
+__global__ void __launch_bounds__(128) traj_next_kernel(TrajDev t, uint64_t seed, uint32_t env_id0, int32_t* traj_no,
+                                                        int32_t* step_no, uint32_t* reset_count, double* xy_off,
+                                                        float* sample, uint8_t* wrapped, int n, int ld) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  int tr = traj_no[env], st = step_no[env] + 1;
+  double ox = xy_off[env], oy = xy_off[(size_t)ld + env];
+  const bool wrap = st >= t.T;
+  if (wrap) {
+    uint32_t rc = reset_count[env];
+    traj_draw(t, seed, env_id0 + env, rc, tr, st);
+    reset_count[env] = rc + 1;
+    ox = t.xy[((size_t)tr * t.T + st) * 2];
+    oy = t.xy[((size_t)tr * t.T + st) * 2 + 1];
+    xy_off[env] = ox;
+    xy_off[(size_t)ld + env] = oy;
+    traj_no[env] = tr;
+  }
+  step_no[env] = st;
+  if (wrapped) wrapped[env] = wrap ? 1 : 0;
+  if (sample) traj_write_sample(t, tr, st, ox, oy, sample, ld, env);
+}
+
+// ---------------------------------------------------------------- fused playback (sequential in time)
+// One thread per env walks its episode step by step (loco_env_base.py:511-552).  Used when the episode is
+// short or the caller asks for it; the time-parallel kernel below is the throughput path.
+struct PlayArgs {
+  TrajDev t;
+  uint64_t seed;
+  uint32_t env_id0;
+  float dt, target;
+  int use_absorbing, n_steps, end_reset, n, ld;
+  OmPlayState s;
+  OmPlayOut o;
+};
+
+OM_HD bool h1_fallen_f(float y, float tilt, float lst, float rot) {
+  const double PI = 3.141592653589793;
+  const double dy = y, dt = tilt, dl = lst, dr = rot;
+  return (dy < -0.3) || (dy > 0.1) || (dt < (-PI / 4.5)) || (dt > (PI / 12)) || (dl < -PI / 12) || (dl > PI / 8) ||
+         (dr < (-PI / 8)) || (dr > (PI / 8));
+}
+
+// One playback step given the sim state; shared by both playback kernels.
+//   qs[17] (spec order, double) , dq[17] (spec order) -> FK outputs at time slot `slot`
+OM_HD void play_fk(const double (&qs)[17], const float (&dq)[17], const OmPlayOut& o, size_t slot, size_t ld, size_t env) {
+  float q[17], qd[17];
+#pragma unroll
+  for (int k = 0; k < 17; ++k) {
+    q[OM_H1_PERM[k]] = (float)qs[k];
+    qd[OM_H1_PERM[k]] = dq[k];
+  }
+  SoaSink<false> S{o.xpos ? o.xpos + slot * 63 * ld : nullptr, o.xquat ? o.xquat + slot * 84 * ld : nullptr,
+                   o.site_xpos ? o.site_xpos + slot * 3 * ld : nullptr, nullptr,
+                   o.cvel ? o.cvel + slot * 126 * ld : nullptr, nullptr, ld, env};
+  om_fk_unitree_h1(q, qd, S);
+}
+
+// obs / fallen / reward / integer state of one step from the freshly gathered sample row
+OM_HD void play_emit(const float (&samp)[36], float prev_x_vel, const PlayArgs& a, size_t slot, size_t env, int tr, int st) {
+  const size_t ld = a.ld;
+  if (a.o.obs) {
+    float* ob = a.o.obs + slot * 32 * ld + env;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) ob[k * ld] = samp[k + 2];
+  }
+  if (a.o.fallen) a.o.fallen[slot * ld + env] = h1_fallen_f(samp[2], samp[3], samp[4], samp[5]) ? 1 : 0;
+  if (a.o.reward) {
+    const float d = prev_x_vel - a.target;
+    a.o.reward[slot * ld + env] = expf(-(d * d));
+  }
+  if (a.o.traj_no_t) a.o.traj_no_t[slot * ld + env] = tr;
+  if (a.o.step_no_t) a.o.step_no_t[slot * ld + env] = st;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) play_h1_seq_kernel(PlayArgs a) {
+  const int env = blockIdx.x * BLOCK + threadIdx.x;
+  if (env >= a.n) return;
+  const size_t ld = a.ld, e = env;
+  int tr = a.s.traj_no[e], st = a.s.step_no[e];
+  uint32_t rc = a.s.reset_count[e];
+  double ox = a.s.xy_off[e], oy = a.s.xy_off[ld + e];
+  double cq[17];
+  float dq[17];
+#pragma unroll
+  for (int k = 0; k < 17; ++k) {
+    cq[k] = a.s.curr_qpos[k * ld + e];
+    dq[k] = a.s.pending[(17 + k) * ld + e];
+  }
+  float pxv = a.s.prev_x_vel[e];
+  float samp[36];
+  bool have_samp = false;
+  for (int s = 0; s < a.n_steps; ++s) {
+#pragma unroll
+    for (int k = 0; k < 17; ++k) cq[k] = fma((double)a.dt, (double)dq[k], cq[k]);   // :515-519
+    play_fk(cq, dq, a.o, (size_t)s, ld, e);                                          // :521-525
+    ++st;                                                                            // :532
+    const bool wrap = st >= a.t.T;
+    if (wrap) {                                                                      // :534-537
+      traj_draw(a.t, a.seed, a.env_id0 + env, rc, tr, st);
+      ++rc;
+      ox = a.t.xy[((size_t)tr * a.t.T + st) * 2];
+      oy = a.t.xy[((size_t)tr * a.t.T + st) * 2 + 1];
+    }
+    traj_load_row(a.t, tr, st, samp);
+    have_samp = true;
+    if (wrap) {
+      cq[0] = 0.0; cq[1] = 0.0;       // x - x_off and y - y_off are exactly zero at the reset sample
+#pragma unroll
+      for (int k = 2; k < 17; ++k) cq[k] = samp[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 17; ++k) dq[k] = samp[17 + k];
+    play_emit(samp, pxv, a, (size_t)s, e, tr, st);                                   // :539-541
+    pxv = samp[17];
+  }
+  // write the loop's `sample` variable back (x, y re-centred) before the end-of-episode reset
+  if (have_samp) {
+    a.s.pending[e] = (float)(a.t.xy[((size_t)tr * a.t.T + st) * 2] - ox);
+    a.s.pending[ld + e] = (float)(a.t.xy[((size_t)tr * a.t.T + st) * 2 + 1] - oy);
+#pragma unroll
+    for (int k = 2; k < 34; ++k) a.s.pending[k * ld + e] = samp[k];
+  }
+  if (a.end_reset) {                                                                 // :555-557
+    traj_draw(a.t, a.seed, a.env_id0 + env, rc, tr, st);
+    ++rc;
+    ox = a.t.xy[((size_t)tr * a.t.T + st) * 2];
+    oy = a.t.xy[((size_t)tr * a.t.T + st) * 2 + 1];
+    traj_load_row(a.t, tr, st, samp);
+    cq[0] = 0.0; cq[1] = 0.0;
+#pragma unroll
+    for (int k = 2; k < 17; ++k) cq[k] = samp[k];
+    pxv = samp[17];
+  }
+  a.s.traj_no[e] = tr;
+  a.s.step_no[e] = st;
+  a.s.reset_count[e] = rc;
+  a.s.xy_off[e] = ox;
+  a.s.xy_off[ld + e] = oy;
+#pragma unroll
+  for (int k = 0; k < 17; ++k) a.s.curr_qpos[k * ld + e] = cq[k];
+  a.s.prev_x_vel[e] = pxv;
+}
+
+}  // namespace om
+
+using namespace om;
+
+struct OmTraj {
+  TrajDev d;
+};
+
+extern "C" int om_traj_create(const double* table, int K, int n_traj, int T, OmTraj** out) {
+  OM_REQUIRE(table && out, "om_traj_create: null argument");
+  OM_REQUIRE(K >= 2 && K <= 64 && n_traj >= 1 && T >= 1, "om_traj_create: bad shape K=%d n_traj=%d T=%d", K, n_traj, T);
+  const int kpad = (K + 3) / 4 * 4;
+  std::vector<float> rows((size_t)n_traj * T * kpad, 0.f);
+  std::vector<double> xy((size_t)n_traj * T * 2);
+  for (int k = 0; k < K; ++k)
+    for (int tr = 0; tr < n_traj; ++tr)
+      for (int s = 0; s < T; ++s) {
+        const double v = table[((size_t)k * n_traj + tr) * T + s];
+        rows[((size_t)tr * T + s) * kpad + k] = (float)v;
+        if (k < 2) xy[((size_t)tr * T + s) * 2 + k] = v;
+      }
+  OmTraj* t = new OmTraj();
+  t->d.K = K; t->d.kpad = kpad; t->d.n_traj = n_traj; t->d.T = T;
+  float* drows = nullptr;
+  double* dxy = nullptr;
+  cudaError_t e = cudaMalloc(&drows, rows.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&dxy, xy.size() * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(drows, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dxy, xy.data(), xy.size() * sizeof(double), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (drows) cudaFree(drows);
+    if (dxy) cudaFree(dxy);
+    delete t;
+    return fail("om_traj_create: device upload failed: %s (no CPU path)", cudaGetErrorString(e));
+  }
+  t->d.rows = drows;
+  t->d.xy = dxy;
+  *out = t;
+  return 0;
+}
+
+extern "C" void om_traj_destroy(OmTraj* t) {
+  if (!t) return;
+  cudaFree((void*)t->d.rows);
+  cudaFree((void*)t->d.xy);
+  delete t;
+}
+
+extern "C" int om_traj_reset(const OmTraj* t, uint64_t seed, uint32_t env_id0, const uint8_t* mask,
+                             const int32_t* forced_traj, const int32_t* forced_step, int32_t* traj_no, int32_t* step_no,
+                             uint32_t* reset_count, double* xy_off, float* sample, int n, int ld, void* stream) {
+  OM_REQUIRE(t && traj_no && step_no && reset_count && xy_off, "om_traj_reset: null argument");
+  OM_REQUIRE(n >= 0 && ld >= n, "om_traj_reset: need 0 <= n <= ld");
+  if (n == 0) return 0;
+  traj_reset_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(t->d, seed, env_id0, mask, forced_traj, forced_step,
+                                                                         traj_no, step_no, reset_count, xy_off, sample, n, ld);
+  OM_LAUNCHED();
+  return 0;
+}
+
+extern "C" int om_traj_current(const OmTraj* t, const int32_t* traj_no, const int32_t* step_no, const double* xy_off,
+                               float* sample, int n, int ld, void* stream) {
+  OM_REQUIRE(t && traj_no && step_no && xy_off && sample, "om_traj_current: null argument");
+  OM_REQUIRE(n >= 0 && ld >= n, "om_traj_current: need 0 <= n <= ld");
+  if (n == 0) return 0;
+  traj_current_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(t->d, traj_no, step_no, xy_off, sample, n, ld);
+  OM_LAUNCHED();
+  return 0;
+}
+
+extern "C" int om_traj_next(const OmTraj* t, uint64_t seed, uint32_t env_id0, int32_t* traj_no, int32_t* step_no,
+                            uint32_t* reset_count, double* xy_off, float* sample, uint8_t* wrapped, int n, int ld,
+                            void* stream) {
+  OM_REQUIRE(t && traj_no && step_no && reset_count && xy_off, "om_traj_next: null argument");
+  OM_REQUIRE(n >= 0 && ld >= n, "om_traj_next: need 0 <= n <= ld");
+  if (n == 0) return 0;
+  traj_next_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(t->d, seed, env_id0, traj_no, step_no, reset_count,
+                                                                        xy_off, sample, wrapped, n, ld);
+  OM_LAUNCHED();
+  return 0;
+}
+
+extern "C" int om_h1_play_from_velocity(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, uint64_t seed,
+                                        uint32_t env_id0, float dt, int n_steps, int end_episode_reset,
+                                        const OmPlayState* state, const OmPlayOut* out, int n, int ld, void* stream) {
+  OM_REQUIRE(m && spec && t && state && out, "om_h1_play_from_velocity: null argument");
+  OM_REQUIRE(n >= 0 && ld >= n && n_steps >= 0, "om_h1_play_from_velocity: bad sizes");
+  OM_REQUIRE(m->specialised == SPEC_H1, "om_h1_play_from_velocity: model is not the UnitreeH1 (arms disabled) model");
+  OM_REQUIRE(spec->n_obs_q == 17 && t->d.K == 34, "om_h1_play_from_velocity: expects the 34-key H1 trajectory");
+  for (int k = 0; k < 17; ++k)
+    OM_REQUIRE(spec->obs_perm[k] == OM_H1_PERM_HOST[k], "om_h1_play_from_velocity: observation spec differs from UnitreeH1's");
+  OM_REQUIRE(state->traj_no && state->step_no && state->reset_count && state->xy_off && state->curr_qpos &&
+                 state->pending && state->prev_x_vel, "om_h1_play_from_velocity: incomplete state");
+  if (n == 0) return 0;
+  PlayArgs a;
+  a.t = t->d; a.seed = seed; a.env_id0 = env_id0; a.dt = dt; a.target = spec->target_velocity;
+  a.use_absorbing = spec->use_absorbing_states; a.n_steps = n_steps; a.end_reset = end_episode_reset;
+  a.n = n; a.ld = ld; a.s = *state; a.o = *out;
+  constexpr int BLOCK = 128;
+  play_h1_seq_kernel<BLOCK><<<ceil_div(n, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(a);
+  OM_LAUNCHED();
+  return 0;
+}

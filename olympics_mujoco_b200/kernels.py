@@ -1,0 +1,281 @@
+"""Torch-level wrappers over the C ABI: torch provides device memory and streams, nothing else.
+
+Layout contract (include/om_b200.h): every per-env array is a 2-D ``[C, n]`` tensor (component-major,
+env index contiguous); rollout buffers are ``[T, C, n]``.  ``env_major`` gives the reference's logical
+shapes (``[n, nbody, 3]`` ...) as zero-copy permuted views.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import OmH1Spec, OmModelDesc, OmPlayOut, OmPlayState, check
+from .mjcf import KinematicModel
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, dtype=None, rows=None):
+    """Device pointer of a tensor laid out [.., C, ld] with unit stride on the last axis."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.OmError("expected a CUDA tensor (this package has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    if t.dim() >= 1 and t.stride(-1) != 1 and t.shape[-1] > 1:
+        raise ValueError("last axis (envs) must be contiguous")
+    if t.dim() >= 2 and not t.is_contiguous():
+        raise ValueError("SoA arrays must be contiguous [.., C, n] tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def soa(c, n, dtype=torch.float32, device="cuda", t=None):
+    shape = (c, n) if t is None else (t, c, n)
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
+def env_major(x, *comp_shape):
+    """[C, n] -> [n, *comp_shape] view (or [T, C, n] -> [T, n, *comp_shape])."""
+    if x.dim() == 2:
+        return x.view(*comp_shape, x.shape[-1]).permute(len(comp_shape), *range(len(comp_shape)))
+    t = x.shape[0]
+    v = x.view(t, *comp_shape, x.shape[-1])
+    return v.permute(0, len(comp_shape) + 1, *range(1, len(comp_shape) + 1))
+
+
+def to_soa(x):
+    """[n, C] (any float dtype, host or device) -> contiguous float32 [C, n] CUDA tensor."""
+    x = torch.as_tensor(x)
+    return x.to(device="cuda", dtype=torch.float32).t().contiguous()
+
+
+# ------------------------------------------------------------------------------------------- model
+class DeviceModel:
+    """OmModel handle for a KinematicModel."""
+
+    def __init__(self, km: KinematicModel):
+        _lib.require_cuda()
+        lib = _lib.load()
+        self.km = km
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        keep = dict(body_parentid=i32(km.body_parentid), body_rootid=i32(km.body_rootid),
+                    body_jntadr=i32(km.body_jntadr), body_jntnum=i32(km.body_jntnum), body_pos=f64(km.body_pos),
+                    body_quat=f64(km.body_quat), body_ipos=f64(km.body_ipos), body_mass=f64(km.body_mass),
+                    jnt_type=i32(km.jnt_type), jnt_qposadr=i32(km.jnt_qposadr), jnt_dofadr=i32(km.jnt_dofadr),
+                    jnt_axis=f64(km.jnt_axis), jnt_pos=f64(km.jnt_pos), qpos0=f64(km.qpos0),
+                    site_bodyid=i32(km.site_bodyid), site_pos=f64(km.site_pos), site_quat=f64(km.site_quat))
+        desc = OmModelDesc(name=km.name.encode(), nbody=km.nbody, njnt=km.njnt, nsite=km.nsite, nq=km.nq, nv=km.nv,
+                           **{k: v.ctypes.data for k, v in keep.items()})
+        h = C.c_void_p()
+        check(lib.om_model_create(C.byref(desc), C.byref(h)))
+        self.handle = h
+        self.specialised = bool(lib.om_model_is_specialised(h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().om_model_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def fk(dm: DeviceModel, qpos, qvel=None, want=("xpos", "xquat", "site_xpos", "site_xmat", "cvel", "subtree_com"),
+       force_generic=False, out=None):
+    """K1.  qpos [nq,n], qvel [nv,n] -> dict of SoA tensors."""
+    km = dm.km
+    n = qpos.shape[-1]
+    assert qpos.shape[0] == km.nq and (qvel is None or qvel.shape == (km.nv, n))
+    sizes = dict(xpos=km.nbody * 3, xquat=km.nbody * 4, site_xpos=km.nsite * 3, site_xmat=km.nsite * 9,
+                 cvel=km.nbody * 6, subtree_com=3)
+    out = dict(out or {})
+    for k in want:
+        if k not in out:
+            out[k] = soa(sizes[k], n, device=qpos.device)
+    g = lambda k: _p(out.get(k), torch.float32)
+    check(_lib.load().om_fk(dm.handle, _p(qpos, torch.float32), _p(qvel, torch.float32), n, qpos.stride(0) if n > 1 else max(n, 1),
+                            g("xpos"), g("xquat"), g("site_xpos"), g("site_xmat"), g("cvel"), g("subtree_com"),
+                            int(force_generic), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------- H1
+def make_h1_spec(perm, x_vel_idx, target_velocity=1.25, use_absorbing_states=True):
+    s = OmH1Spec()
+    s.n_obs_q = len(perm)
+    for k, v in enumerate(perm):
+        s.obs_perm[k] = int(v)
+    s.x_vel_idx = int(x_vel_idx)
+    s.target_velocity = float(target_velocity)
+    s.use_absorbing_states = int(bool(use_absorbing_states))
+    return s
+
+
+def h1_step(dm, spec, qpos, qvel, prev_x_vel, want_fk=True, out=None):
+    """K1+K2 fused: FK + observation + absorbing + reward for n envs."""
+    km = dm.km
+    n = qpos.shape[-1]
+    nobs = 2 * spec.n_obs_q - 2
+    out = dict(out or {})
+    dev = qpos.device
+    if want_fk:
+        for k, c in (("xpos", km.nbody * 3), ("xquat", km.nbody * 4), ("site_xpos", km.nsite * 3), ("cvel", km.nbody * 6)):
+            out.setdefault(k, soa(c, n, device=dev))
+    out.setdefault("obs", soa(nobs, n, device=dev))
+    out.setdefault("reward", torch.empty(n, device=dev))
+    out.setdefault("absorbing", torch.empty(n, dtype=torch.uint8, device=dev))
+    g = lambda k: _p(out.get(k), torch.float32)
+    check(_lib.load().om_h1_step(dm.handle, C.byref(spec), _p(qpos, torch.float32), _p(qvel, torch.float32),
+                                 _p(prev_x_vel, torch.float32), n, max(n, 1), g("xpos"), g("xquat"), g("site_xpos"),
+                                 g("cvel"), g("obs"), g("reward"), _p(out["absorbing"], torch.uint8), _stream()))
+    return out
+
+
+def h1_has_fallen(obs):
+    n = obs.shape[-1]
+    fallen = torch.empty(n, dtype=torch.uint8, device=obs.device)
+    check(_lib.load().om_h1_has_fallen(_p(obs, torch.float32), n, max(n, 1), _p(fallen), _stream()))
+    return fallen
+
+
+# ------------------------------------------------------------------------------------------- trajectory
+class DeviceTrajectory:
+    """OmTraj handle + per-env integer state for n envs (K3)."""
+
+    def __init__(self, table, n_env, seed=0, env_id0=0, device="cuda"):
+        _lib.require_cuda()
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        assert table.ndim == 3, "table must be [K, n_traj, T]"
+        self.K, self.n_traj, self.T = table.shape
+        h = C.c_void_p()
+        check(_lib.load().om_traj_create(table.ctypes.data, self.K, self.n_traj, self.T, C.byref(h)))
+        self.handle = h
+        self.n, self.seed, self.env_id0 = int(n_env), int(seed), int(env_id0)
+        self.traj_no = torch.zeros(n_env, dtype=torch.int32, device=device)
+        self.step_no = torch.zeros(n_env, dtype=torch.int32, device=device)
+        self.reset_count = torch.zeros(n_env, dtype=torch.int32, device=device)   # bits of a uint32
+        self.xy_off = torch.zeros((2, n_env), dtype=torch.float64, device=device)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().om_traj_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def reset(self, mask=None, traj_no=None, substep_no=None, sample=None):
+        if sample is None:
+            sample = soa(self.K, self.n, device=self.traj_no.device)
+        check(_lib.load().om_traj_reset(self.handle, self.seed, self.env_id0, _p(mask, torch.uint8),
+                                        _p(traj_no, torch.int32), _p(substep_no, torch.int32), _p(self.traj_no),
+                                        _p(self.step_no), _p(self.reset_count), _p(self.xy_off), _p(sample, torch.float32),
+                                        self.n, max(self.n, 1), _stream()))
+        return sample
+
+    def current(self, sample=None):
+        if sample is None:
+            sample = soa(self.K, self.n, device=self.traj_no.device)
+        check(_lib.load().om_traj_current(self.handle, _p(self.traj_no), _p(self.step_no), _p(self.xy_off),
+                                          _p(sample, torch.float32), self.n, max(self.n, 1), _stream()))
+        return sample
+
+    def next(self, sample=None, wrapped=None):
+        if sample is None:
+            sample = soa(self.K, self.n, device=self.traj_no.device)
+        check(_lib.load().om_traj_next(self.handle, self.seed, self.env_id0, _p(self.traj_no), _p(self.step_no),
+                                       _p(self.reset_count), _p(self.xy_off), _p(sample, torch.float32),
+                                       _p(wrapped, torch.uint8), self.n, max(self.n, 1), _stream()))
+        return sample
+
+
+def h1_play_from_velocity(dm, spec, traj: DeviceTrajectory, state, n_steps, dt=0.01, end_episode_reset=True,
+                          want=("xpos", "xquat", "site_xpos", "cvel", "obs", "reward", "fallen", "traj_no_t", "step_no_t"),
+                          out=None):
+    """Fused playback of one episode (loco_env_base.py:511-557).  ``state``: dict with curr_qpos [17,n] f64,
+    pending [34,n] f32, prev_x_vel [n] f32 (the trajectory indices live in ``traj``)."""
+    km, n = dm.km, traj.n
+    dev = traj.traj_no.device
+    sizes = dict(xpos=(km.nbody * 3, torch.float32), xquat=(km.nbody * 4, torch.float32),
+                 site_xpos=(km.nsite * 3, torch.float32), cvel=(km.nbody * 6, torch.float32),
+                 obs=(32, torch.float32), reward=(None, torch.float32), fallen=(None, torch.uint8),
+                 traj_no_t=(None, torch.int32), step_no_t=(None, torch.int32))
+    out = dict(out or {})
+    for k in want:
+        if k not in out:
+            c, dt_ = sizes[k]
+            out[k] = torch.empty((n_steps, n) if c is None else (n_steps, c, n), dtype=dt_, device=dev)
+    ps = OmPlayState(traj_no=traj.traj_no.data_ptr(), step_no=traj.step_no.data_ptr(),
+                     reset_count=traj.reset_count.data_ptr(), xy_off=traj.xy_off.data_ptr(),
+                     curr_qpos=_p(state["curr_qpos"], torch.float64).value, pending=_p(state["pending"], torch.float32).value,
+                     prev_x_vel=_p(state["prev_x_vel"], torch.float32).value)
+    po = OmPlayOut(**{k: (out[k].data_ptr() if k in out else None) for k in sizes})
+    check(_lib.load().om_h1_play_from_velocity(dm.handle, C.byref(spec), traj.handle, traj.seed, traj.env_id0, float(dt),
+                                               int(n_steps), int(bool(end_episode_reset)), C.byref(ps), C.byref(po),
+                                               n, max(n, 1), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------- learner side
+def ppo_returns(rewards, values, gamma, path_end=None, v_next=None, v_last=None):
+    """K5a over a [T, n] buffer -> (returns, advantages)."""
+    T, n = rewards.shape
+    ret, adv = torch.empty_like(rewards), torch.empty_like(rewards)
+    check(_lib.load().om_ppo_returns(_p(rewards, torch.float32), _p(values, torch.float32), _p(path_end, torch.uint8),
+                                     _p(v_next, torch.float32), _p(v_last, torch.float32), float(gamma), T, n, max(n, 1),
+                                     _p(ret), _p(adv), _stream()))
+    return ret, adv
+
+
+def gae(rewards, v, v_next, absorbing, last, gamma, lam):
+    """K5b over a [T, n] buffer -> (v_target, adv) (the order compute_gae returns)."""
+    T, n = rewards.shape
+    adv, vt = torch.empty_like(rewards), torch.empty_like(rewards)
+    check(_lib.load().om_gae(_p(rewards, torch.float32), _p(v, torch.float32), _p(v_next, torch.float32),
+                             _p(absorbing, torch.uint8), _p(last, torch.uint8), float(gamma), float(lam), T, n, max(n, 1),
+                             _p(adv), _p(vt), _stream()))
+    return vt, adv
+
+
+def moments(x, out=None):
+    """K6.  x [C, n] or [rows, C, n] -> float64 [2C+1] = (sum[C], sumsq[C], count), accumulated into ``out``."""
+    if x.dim() == 1:
+        x = x.view(1, 1, -1)
+    elif x.dim() == 2:
+        x = x.view(1, *x.shape)
+    rows, c, n = x.shape
+    if out is None:
+        out = torch.zeros(2 * c + 1, dtype=torch.float64, device=x.device)
+    check(_lib.load().om_moments(_p(x, torch.float32), rows, c, n, max(n, 1), _p(out, torch.float64), _stream()))
+    return out
+
+
+def adv_stats(mom, unbiased, eps):
+    stats = torch.empty(2, dtype=torch.float64, device=mom.device)
+    check(_lib.load().om_adv_stats(_p(mom, torch.float64), int(bool(unbiased)), float(eps), _p(stats), _stream()))
+    return stats
+
+
+def normalize(x, stats, out=None):
+    """(x - stats[0]) / stats[1] over a [rows, n] buffer."""
+    x2 = x.view(1, -1) if x.dim() == 1 else x
+    rows, n = x2.shape
+    out = torch.empty_like(x) if out is None else out
+    check(_lib.load().om_normalize(_p(x2, torch.float32), _p(stats, torch.float64), rows, n, max(n, 1),
+                                   _p(out, torch.float32), _stream()))
+    return out
+
+
+def launch_count():
+    return int(_lib.load().om_launch_count())
+
+
+def reset_launch_count():
+    _lib.load().om_reset_launch_count()

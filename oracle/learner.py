@@ -1,0 +1,168 @@
+"""Oracle: learner-side pieces of the hot path in float64 NumPy (TEST INFRASTRUCTURE).
+
+* ``ppo_returns``          restates ``PPOBuffer.finish_path`` (reference ``rl/algos/ppo.py:68-84``) with
+  the bootstrap ``(not done) * V(s_T)`` of ``:195-196`` and the advantage normalisation of ``:334-336``
+  (``torch.std`` -> unbiased, ``eps=1e-5``).  Pinned: reference class imported by ``tools/gen_golden.py``.
+* ``compute_gae``          restates ``mushroom_rl.utils.value_functions.compute_gae`` (mushroom-rl>=1.10,
+  not in tree), called at ``imitation_lib/imitation/gail_TRPO.py:126-128``
+  followed by ``(adv-mean)/(np.std(adv)+1e-8)``.  PARITY UNPINNED by the reference (third party).
+* ``Standardizer``         restates ``imitation_lib/utils/networks.py:48-81``.
+* ``RunningMeanStd`` / ``normalization_params``  restate ``rl/envs/normalize.py:190-208`` and ``:48``.
+* ``vail_forward`` / ``gail_forward`` / ``discrim_reward``  restate ``networks.py:258-284``,
+  ``:208-234`` and ``gail_TRPO.py:320-327`` for the shapes fixed by
+  ``examples/imitation_learning/utils.py:151-179`` + ``confs.yaml:113-130``.
+"""
+import numpy as np
+
+
+# ------------------------------------------------------------------ PPO returns (G1)
+def ppo_returns(rewards, values, done_last, v_boot, gamma):
+    """One path per env of fixed length T.  rewards/values [T,N]; done_last [N] bool (episode ended by
+    termination at the last step); v_boot [N] = V(s_T).  Returns (returns [T,N], advantages [T,N])."""
+    rewards = np.asarray(rewards, np.float64)
+    T = rewards.shape[0]
+    R = np.where(done_last, 0.0, 1.0) * np.asarray(v_boot, np.float64)      # ppo.py:196
+    ret = np.empty_like(rewards)
+    for t in range(T - 1, -1, -1):                                          # ppo.py:75-77
+        R = gamma * R + rewards[t]
+        ret[t] = R
+    return ret, ret - np.asarray(values, np.float64)                        # ppo.py:335
+
+
+def ppo_returns_segmented(rewards, values, done, v_next, gamma):
+    """Fixed-horizon rollout buffer with episode ends inside it (``sample`` loop ppo.py:166-196):
+    ``done[t]`` marks the last step of a path that terminated (bootstrap 0); a path cut by the end of
+    the buffer bootstraps with ``v_next[T-1]`` (= V of the state after the last step)."""
+    rewards = np.asarray(rewards, np.float64)
+    T = rewards.shape[0]
+    ret = np.empty_like(rewards)
+    R = np.where(done[T - 1], 0.0, np.asarray(v_next, np.float64)[T - 1])
+    for t in range(T - 1, -1, -1):
+        if t < T - 1:
+            R = np.where(done[t], 0.0, R)
+        R = gamma * R + rewards[t]
+        ret[t] = R
+    return ret, ret - np.asarray(values, np.float64)
+
+
+def normalize_advantage_ppo(adv, eps=1e-5):
+    """ppo.py:336: torch.std is the unbiased estimator."""
+    adv = np.asarray(adv, np.float64)
+    return (adv - adv.mean()) / (adv.std(ddof=1) + eps)
+
+
+# ------------------------------------------------------------------ GAE (G2)
+def compute_gae(v, v_next, r, absorbing, last, gamma, lam):
+    """mushroom_rl compute_gae over a flat dataset of n transitions (loop from n-1 down)."""
+    v = np.asarray(v, np.float64)
+    v_next = np.asarray(v_next, np.float64)
+    r = np.asarray(r, np.float64)
+    n = len(r)
+    adv = np.empty(n)
+    for k in range(n - 1, -1, -1):
+        if last[k] or k == n - 1:
+            adv[k] = r[k] - v[k]
+            if not absorbing[k]:
+                adv[k] += gamma * v_next[k]
+        else:
+            adv[k] = r[k] + gamma * v_next[k] - v[k] + gamma * lam * adv[k + 1]
+    return adv + v, adv
+
+
+def compute_gae_batched(v, v_next, r, absorbing, last, gamma, lam):
+    """Same recurrence for a time-major rollout buffer [T,N] of N independent envs; the buffer end
+    (t == T-1) acts as the ``k == n-1`` case for every env."""
+    v, v_next, r = (np.asarray(a, np.float64) for a in (v, v_next, r))
+    T = r.shape[0]
+    adv = np.empty_like(r)
+    for t in range(T - 1, -1, -1):
+        term = last[t] if t < T - 1 else np.ones_like(last[t], dtype=bool)
+        boot = np.where(absorbing[t], 0.0, gamma * v_next[t])
+        tail = r[t] - v[t] + boot
+        if t < T - 1:
+            cont = r[t] + gamma * v_next[t] - v[t] + gamma * lam * adv[t + 1]
+            adv[t] = np.where(term, tail, cont)
+        else:
+            adv[t] = tail
+    return adv + v, adv
+
+
+def normalize_advantage_gail(adv):
+    """gail_TRPO.py:128: np.std is the population estimator."""
+    adv = np.asarray(adv, np.float64)
+    return (adv - adv.mean()) / (adv.std() + 1e-8)
+
+
+# ------------------------------------------------------------------ statistics (S1)
+class Standardizer:
+    """networks.py:48-81 (running sums start at 0, 1e-2, 1e-2; std floor sqrt(1e-2))."""
+
+    def __init__(self):
+        self._sum, self._sumsq, self._count = 0.0, 1e-2, 1e-2
+        self.mean, self.std = 0.0, 1.0
+
+    def update_mean_std(self, x):
+        x = np.asarray(x, np.float64)
+        self._sum = self._sum + x.sum(axis=0).ravel()
+        self._sumsq = self._sumsq + np.square(x).sum(axis=0).ravel()
+        self._count = self._count + np.array([len(x)])
+        self.mean = self._sum / self._count
+        self.std = np.sqrt(np.maximum(self._sumsq / self._count - np.square(self.mean), 1e-2))
+
+    def forward(self, x):
+        self.update_mean_std(x)
+        return (np.asarray(x, np.float64) - self.mean) / self.std
+
+
+class RunningMeanStd:
+    """rl/envs/normalize.py:190-208 (parallel-variance merge)."""
+
+    def __init__(self, epsilon=1e-4, shape=()):
+        self.mean = np.zeros(shape, "float64")
+        self.var = np.zeros(shape, "float64")
+        self.count = epsilon
+
+    def update(self, x):
+        bm, bv, bc = np.mean(x, axis=0), np.var(x, axis=0), x.shape[0]
+        delta = bm - self.mean
+        tot = self.count + bc
+        new_mean = self.mean + delta * bc / tot
+        M2 = self.var * self.count + bv * bc + np.square(delta) * self.count * bc / tot
+        self.mean, self.var, self.count = new_mean, M2 / tot, tot
+
+
+def normalization_params(states):
+    """rl/envs/normalize.py:48."""
+    return np.mean(states, axis=0), np.sqrt(np.var(states, axis=0) + 1e-8)
+
+
+# ------------------------------------------------------------------ discriminator reward (D1)
+def _linear(x, w, b):
+    return x @ np.asarray(w, np.float64).T + np.asarray(b, np.float64)
+
+
+def vail_forward(p, s, eps, mean, std):
+    """VariationalNet.forward (networks.py:258-284) for the H1 VAIL shapes, states only.
+    p: dict w1[256,32] b1 w2[128,256] b2 wmu[128,128] bmu wlv[128,128] blv wd[1,128] bd."""
+    x = (np.asarray(s, np.float64) - mean) / std                       # Standardizer.forward :73-74
+    h = np.maximum(_linear(x, p["w1"], p["b1"]), 0.0)                  # encoder relu
+    h = np.maximum(_linear(h, p["w2"], p["b2"]), 0.0)                  # encoder output relu
+    mu = _linear(h, p["wmu"], p["bmu"])
+    logvar = _linear(h, p["wlv"], p["blv"])
+    z = mu + np.exp(logvar / 2) * np.asarray(eps, np.float64)          # reparameterize :21-24
+    d = _linear(z, p["wd"], p["bd"])                                   # decoder, identity
+    return d[..., 0], mu, logvar
+
+
+def gail_forward(p, s, mean, std):
+    """DiscriminatorNetwork.forward (networks.py:208-234), tanh-tanh-identity, 32-512-256-1."""
+    x = (np.asarray(s, np.float64) - mean) / std
+    h = np.tanh(_linear(x, p["w1"], p["b1"]))
+    h = np.tanh(_linear(h, p["w2"], p["b2"]))
+    return _linear(h, p["w3"], p["b3"])[..., 0]
+
+
+def discrim_reward(d):
+    """gail_TRPO.py:326-327."""
+    plcy_prob = 1.0 / (1.0 + np.exp(-np.asarray(d, np.float64)))
+    return (-np.log(1.0 - plcy_prob + 1e-8)).astype(np.float32)

@@ -1,0 +1,41 @@
+// TEST INFRASTRUCTURE: compiles the GENERATED fk device functions as plain host C++ so that the code
+// generator can be checked against the float64 oracle in a container without a GPU.  Never shipped,
+// never used by the product (which has no CPU path).
+#include <cmath>
+#include <cstring>
+#define OM_HD inline
+static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+#include "fk_unitree_h1.cuh"
+#include "fk_stick_figure_a3.cuh"
+
+struct HostSink {
+  static constexpr bool want_site_xmat = true;
+  float *xp, *xq, *sp, *sm, *cv, *cm;
+  void xpos(int b, float x, float y, float z) { xp[b*3]=x; xp[b*3+1]=y; xp[b*3+2]=z; }
+  void xquat(int b, float w, float x, float y, float z) { xq[b*4]=w; xq[b*4+1]=x; xq[b*4+2]=y; xq[b*4+3]=z; }
+  void site_xpos(int s, float x, float y, float z) { sp[s*3]=x; sp[s*3+1]=y; sp[s*3+2]=z; }
+  void site_xmat(int s, float a, float b, float c, float d, float e, float f, float g, float h, float i) {
+    float m[9] = {a,b,c,d,e,f,g,h,i}; std::memcpy(sm + 9*s, m, sizeof m); }
+  void cvel(int b, float wx, float wy, float wz, float vx, float vy, float vz) {
+    float v[6] = {wx,wy,wz,vx,vy,vz}; std::memcpy(cv + 6*b, v, sizeof v); }
+  void com(float x, float y, float z) { cm[0]=x; cm[1]=y; cm[2]=z; }
+};
+
+extern "C" void host_fk_h1(const float* q, const float* qd, int n, float* xp, float* xq, float* sp, float* sm,
+                           float* cv, float* cm) {
+  for (int e = 0; e < n; ++e) {
+    float qq[17], dd[17];
+    std::memcpy(qq, q + 17*e, sizeof qq); std::memcpy(dd, qd + 17*e, sizeof dd);
+    HostSink S{xp + 63*e, xq + 84*e, sp + 3*e, sm + 9*e, cv + 126*e, cm + 3*e};
+    om_fk_unitree_h1(qq, dd, S);
+  }
+}
+extern "C" void host_fk_a3(const float* q, const float* qd, int n, float* xp, float* xq, float* sp, float* sm,
+                           float* cv, float* cm) {
+  for (int e = 0; e < n; ++e) {
+    float qq[25], dd[24];
+    std::memcpy(qq, q + 25*e, sizeof qq); std::memcpy(dd, qd + 24*e, sizeof dd);
+    HostSink S{xp + 51*e, xq + 68*e, sp + 6*e, sm + 18*e, cv + 102*e, cm + 3*e};
+    om_fk_stick_figure_a3(qq, dd, S);
+  }
+}

@@ -1,0 +1,158 @@
+"""GPU parity: H1 step tail (K1+K2), trajectory state machine (K3) and the fused playback kernel vs
+the oracle (oracle/h1.py, oracle/trajectory.py) through the C ABI."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _table():
+    """Reference-resampled table [34, 3, 50] from the golden fixture; channels >= 2 rounded to fp32 (what
+    the device stores), channels 0,1 (x, y) stay float64 on both sides."""
+    tab = np.load(GOLDEN / "trajectory_ref.npz")["table"].copy()
+    tab[2:] = tab[2:].astype(np.float32).astype(np.float64)
+    return tab
+
+
+def _spec(model, **kw):
+    from olympics_mujoco_b200 import kernels as Kn
+    from oracle import h1 as OH
+    return Kn.make_h1_spec(OH.perm(model), OH.x_vel_idx(model), **kw)
+
+
+def test_h1_step_parity(h1_model, h1_states):
+    import torch
+    from olympics_mujoco_b200 import kernels as Kn
+    from oracle import h1 as OH
+    qpos, qvel = h1_states
+    n = qpos.shape[0]
+    rng = np.random.default_rng(0)
+    # push a third of the states over the has_fallen thresholds, including exact threshold values
+    qpos = qpos.copy()
+    idx = rng.choice(n, n // 3, replace=False)
+    qpos[idx, 3] += rng.uniform(-1.0, 1.0, idx.size)
+    qpos[idx[:10], 2] = np.float32(0.1)
+    qpos[idx[10:20], 2] = np.float32(-0.3)
+    qpos[idx[20:30], 5] = np.float32(np.pi / 8)
+    qpos = qpos.astype(np.float32).astype(np.float64)
+    prev_obs = rng.normal(1.2, 0.3, (n, 32)).astype(np.float32).astype(np.float64)
+    ref = OH.step(h1_model, qpos, qvel, prev_obs)
+    dm = Kn.DeviceModel(h1_model)
+    out = Kn.h1_step(dm, _spec(h1_model), Kn.to_soa(qpos), Kn.to_soa(qvel),
+                     torch.tensor(prev_obs[:, 15], dtype=torch.float32, device="cuda"))
+    torch.cuda.synchronize()
+    o = {k: v.cpu().numpy() for k, v in out.items()}
+    assert np.array_equal(o["absorbing"].astype(bool), ref["absorbing"]), "absorbing flags must be bit-exact"
+    assert ref["absorbing"].sum() > 20 and (~ref["absorbing"]).sum() > 20
+    assert np.array_equal(o["obs"].T, ref["obs"].astype(np.float32)), "obs is a pure gather: exact"
+    assert_close(o["reward"], ref["reward"], "reward")
+    assert_close(o["xpos"].T.reshape(n, 21, 3), ref["xpos"], "xpos")
+    assert_close(o["xquat"].T.reshape(n, 21, 4), ref["xquat"], "xquat")
+    assert_close(o["site_xpos"].T.reshape(n, 1, 3), ref["site_xpos"], "site_xpos")
+    assert_close(o["cvel"].T.reshape(n, 21, 6), ref["cvel"], "cvel")
+
+
+def test_h1_step_absorbing_disabled(h1_model, h1_states):
+    import torch
+    from olympics_mujoco_b200 import kernels as Kn
+    qpos, qvel = h1_states
+    qpos = qpos.copy()
+    qpos[:, 2] = 5.0                                   # every env "fallen"
+    dm = Kn.DeviceModel(h1_model)
+    pv = torch.zeros(qpos.shape[0], device="cuda")
+    on = Kn.h1_step(dm, _spec(h1_model), Kn.to_soa(qpos), Kn.to_soa(qvel), pv, want_fk=False)
+    off = Kn.h1_step(dm, _spec(h1_model, use_absorbing_states=False), Kn.to_soa(qpos), Kn.to_soa(qvel), pv, want_fk=False)
+    assert bool(on["absorbing"].all()) and not bool(off["absorbing"].any())
+
+
+def test_has_fallen_golden_rollouts(h1_model):
+    """The reference's recorded H1 rollouts (saved_npz) are non-terminal on every sample."""
+    from olympics_mujoco_b200 import kernels as Kn
+    from oracle import h1 as OH
+    z = np.load(GOLDEN / "saved_rollouts_ref.npz")
+    for name in ("vail_unprocessed_0", "gail_unprocessed_0", "vail_processed_0", "gail_processed_0"):
+        obs = z[name][:, 2:]
+        fallen = Kn.h1_has_fallen(Kn.to_soa(obs)).cpu().numpy().astype(bool)
+        assert not fallen.any()
+        assert np.array_equal(fallen, OH.has_fallen(obs.astype(np.float32).astype(np.float64)))
+
+
+def test_trajectory_state_machine():
+    """reset / current / next with wrap -> reset against the oracle, integers bit-exact."""
+    import torch
+    from olympics_mujoco_b200 import kernels as Kn
+    from oracle.trajectory import TrajectoryState
+    tab = _table()
+    n, seed, env0 = 67, 1234567891011, 5
+    dt = Kn.DeviceTrajectory(tab, n, seed=seed, env_id0=env0)
+    oracles = [TrajectoryState(tab, seed=seed, env_id=env0 + i) for i in range(n)]
+    s = dt.reset().cpu().numpy().T
+    ref = np.stack([o.reset_trajectory() for o in oracles])
+    assert np.array_equal(dt.traj_no.cpu().numpy(), [o.traj_no for o in oracles])
+    assert np.array_equal(dt.step_no.cpu().numpy(), [o.step_no for o in oracles])
+    assert_close(s, ref, "reset sample", rtol=1e-6, atol=1e-6)
+    assert np.all(s[:, :2] == 0.0)
+    wrapped = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    n_wraps = 0
+    for _ in range(130):                                 # > 2 * T: every env wraps at least once
+        s = dt.next(wrapped=wrapped).cpu().numpy().T
+        ref = []
+        for o in oracles:
+            r = o.get_next_sample()
+            if r is None:                                # loco_env_base.py:534-537
+                r = o.reset_trajectory()
+            ref.append(r)
+        assert np.array_equal(dt.traj_no.cpu().numpy(), [o.traj_no for o in oracles])
+        assert np.array_equal(dt.step_no.cpu().numpy(), [o.step_no for o in oracles])
+        assert np.array_equal(dt.reset_count.cpu().numpy(), [o.reset_count for o in oracles])
+        assert_close(s, np.stack(ref), "next sample", rtol=1e-6, atol=1e-6)
+        n_wraps += int(wrapped.sum())
+    assert n_wraps >= n
+    assert_close(dt.current().cpu().numpy().T, np.stack([o.get_current_sample() for o in oracles]), "current",
+                 rtol=1e-6, atol=1e-6)
+    # forced reset (reset_trajectory(substep_no, traj_no)) on a masked subset
+    mask = torch.zeros(n, dtype=torch.uint8, device="cuda"); mask[::3] = 1
+    ft = torch.full((n,), 2, dtype=torch.int32, device="cuda")
+    fs = torch.full((n,), 17, dtype=torch.int32, device="cuda")
+    before = dt.step_no.clone()
+    dt.reset(mask=mask, traj_no=ft, substep_no=fs)
+    st = dt.step_no.cpu().numpy()
+    assert np.all(st[::3] == 17) and np.array_equal(st[1::3], before.cpu().numpy()[1::3])
+
+
+@pytest.mark.parametrize("n_episodes,n_steps", [(1, 120), (3, 37)])
+def test_play_trajectory_from_velocity_parity(h1_model, n_episodes, n_steps):
+    import torch
+    from olympics_mujoco_b200 import kernels as Kn
+    from oracle import h1 as OH
+    tab = _table()
+    n, seed = 24, 99
+    dm = Kn.DeviceModel(h1_model)
+    spec = _spec(h1_model)
+    dt = Kn.DeviceTrajectory(tab, n, seed=seed)
+    sample = dt.reset()                                                    # :481-485
+    state = dict(curr_qpos=sample[:17].double().contiguous(), pending=sample.clone(),
+                 prev_x_vel=sample[17].clone())
+    outs = []
+    for _ in range(n_episodes):
+        o = Kn.h1_play_from_velocity(dm, spec, dt, state, n_steps, dt=0.01, end_episode_reset=True)
+        torch.cuda.synchronize()
+        outs.append({k: v.cpu().numpy() for k, v in o.items()})
+    cat = {k: np.concatenate([o[k] for o in outs], axis=0) for k in outs[0]}
+    for e in range(n):
+        ref = OH.play_trajectory_from_velocity(h1_model, tab, n_episodes, n_steps, seed=seed, env_id=e)
+        assert np.array_equal(cat["traj_no_t"][:, e], ref["traj_no"]), "trajectory number must be bit-exact"
+        assert np.array_equal(cat["step_no_t"][:, e], ref["step_no"]), "trajectory index must be bit-exact"
+        assert np.array_equal(cat["fallen"][:, e].astype(bool), ref["fallen"])
+        assert np.array_equal(cat["obs"][:, :, e], ref["obs"].astype(np.float32))
+        assert_close(cat["reward"][:, e], ref["reward"], "reward")
+        assert_close(cat["xpos"][:, :, e], ref["xpos"].reshape(-1, 63), "xpos")
+        assert_close(cat["xquat"][:, :, e], ref["xquat"].reshape(-1, 84), "xquat")
+        assert_close(cat["site_xpos"][:, :, e], ref["site_xpos"].reshape(-1, 3), "site_xpos")
+        assert_close(cat["cvel"][:, :, e], ref["cvel"].reshape(-1, 126), "cvel")
+        fin = ref["final"]
+        assert int(dt.traj_no[e]) == fin["traj_no"] and int(dt.step_no[e]) == fin["step_no"]
+        assert int(dt.reset_count[e]) == fin["reset_count"]
+        assert_close(state["curr_qpos"][:, e].cpu().numpy(), fin["curr_qpos"], "curr_qpos", rtol=1e-6, atol=1e-6)
