@@ -1,0 +1,249 @@
+"""Headline benchmark: env-steps/sec of the H1 hot path (FK + obs + reward + GAE), BASELINE.json configs[1].
+
+One "step" = one pass of the hot path over one batch: a 4096-env x 500-step
+``play_trajectory_from_velocity`` rollout per GPU (Euler step, set_sim_state, FK, next sample / wrap reset,
+observation, has_fallen, TargetVelocityReward) followed by GAE(lambda) + advantage normalisation over the
+[500, 4096] rollout buffer.  Every rank owns its own 4096 envs (weak scaling); the only exchange is one
+NCCL all-reduce of the float64 moment sums (advantage + observation statistics) per rollout.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference ...                     # CPU oracle port on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+BYTES_PER_ENV_STEP = 1517          # SURVEY.md section 8(d), config 2 (algorithmic HBM bytes of the playback step)
+N_ENVS = 4096
+HORIZON = 500
+GAMMA, LAM = 0.99, 0.97
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_table():
+    """Dataset-shaped synthetic trajectory -> the reference's resampled table [34, 4, 500] (100 Hz)."""
+    from olympics_mujoco_b200 import mjcf, synthetic
+    from olympics_mujoco_b200.utils.trajectory import resample_table
+    model = mjcf.load_builtin("unitree_h1")
+    data = synthetic.h1_walk_dataset(n_traj=4, t_raw=2500, seed=0, model=model)
+    return model, resample_table(data, model)
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's CPU path for the same workload, restated (oracle port; the reference's own MuJoCo /
+    mushroom_rl stack cannot be installed here).  Rank 0 only; bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_baseline
+    model, table = build_table()
+    res = cpu_baseline.run(model, table, steps=args.steps, warmup=args.warmup, horizon=HORIZON)
+    line = {"impl": "reference", "metric": "env-steps/sec (FK+obs+reward+GAE)", "value": res["value"],
+            "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "UnitreeH1 walk playback rollout 4096 envs x 500 steps + GAE (configs[1])",
+                       "sample": res["sample"]},
+            "cpu_baseline": {"value": res["value"], "unit": "env-steps/s", "cores": res["cores"], "kind": res["kind"],
+                             "sample": res["sample"]},
+            "e2e": {"value": res["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from olympics_mujoco_b200 import kernels as Kn
+    from olympics_mujoco_b200.environments import LocoEnvBase
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, T = args.envs, args.horizon
+
+    model, table = build_table()
+    env = LocoEnvBase.make("UnitreeH1.walk.real", n_envs=n, traj_params=dict(table=table), seed=1234,
+                           env_id0=rank * n, device=f"cuda:{local}")
+    roll = env.make_rollout_buffers(T)                         # device-resident [T, C, n] outputs
+    g = torch.Generator(device="cuda").manual_seed(7 + rank)
+    values = torch.randn((T + 1, n), device="cuda", generator=g)
+    values_host = values.cpu().pin_memory()
+    last = torch.zeros((T, n), dtype=torch.uint8, device="cuda")
+    mom = torch.zeros(3 + 65, dtype=torch.float64, device="cuda")    # advantage [3] + observation [2*32+1]
+    host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in
+            dict(obs=roll["obs"], reward=roll["reward"], fallen=roll["fallen"]).items()}
+    host["adv"] = torch.empty((T, n)).pin_memory()
+    host["v_target"] = torch.empty((T, n)).pin_memory()
+    ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+
+    def hot_step(i=None, vals=values):
+        if i is not None:
+            ev_k0[i].record()
+        out = env.play_trajectory_from_velocity(n_episodes=1, n_steps_per_episode=T, render=False, out=roll)
+        if i is not None:
+            ev_k1[i].record()
+        vt, adv = Kn.gae(out["reward"], vals[:-1], vals[1:], out["fallen"], last, GAMMA, LAM)
+        mom.zero_()
+        Kn.moments(adv, out=mom[:3])
+        Kn.moments(out["obs"], out=mom[3:])
+        if world > 1:
+            dist.all_reduce(mom)                               # the path's only exchange (520 B + 24 B, float64)
+        stats = Kn.adv_stats(mom[:3], unbiased=False, eps=1e-8)
+        Kn.normalize(adv, stats, out=adv)
+        return out, vt, adv
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value")
+    for _ in range(args.warmup):
+        hot_step()
+    sync_all()
+    Kn.reset_launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        hot_step(i)
+    t1.record()
+    sync_all()
+    clocks = sampler.stop()
+    launches = Kn.launch_count()
+    ms = torch.tensor([t0.elapsed_time(t1)], device="cuda", dtype=torch.float64)
+    kms = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)) / args.steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms) / args.steps
+    value = world * n * T / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API with host buffers
+    def e2e_step():
+        vals = values_host.to("cuda", non_blocking=True)
+        out, vt, adv = hot_step(vals=vals)
+        host["obs"].copy_(out["obs"], non_blocking=True)
+        host["reward"].copy_(out["reward"], non_blocking=True)
+        host["fallen"].copy_(out["fallen"], non_blocking=True)
+        host["adv"].copy_(adv, non_blocking=True)
+        host["v_target"].copy_(vt, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    sync_all()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    sync_all()
+    e2e_ms = torch.tensor([(time.perf_counter() - w0) * 1e3 / e2e_steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    h2d = values_host.numel() * 4
+    d2h = sum(v.numel() * v.element_size() for v in host.values())
+
+    if rank == 0:
+        peaks, which = measured_peaks()
+        kernel_ms = float(kms)
+        achieved = BYTES_PER_ENV_STEP * n * T / (kernel_ms * 1e-3) / 1e9
+        line = {"metric": "env-steps/sec (FK+obs+reward+GAE)", "value": value, "unit": "env-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"UnitreeH1 walk playback rollout {n} envs x {T} steps per GPU + GAE (configs[1])",
+                           "envs_per_gpu": n, "horizon": T, "l2": "rollout outputs (2.5 GB/step) exceed the 126 MB L2",
+                           "gamma": GAMMA, "lam": LAM},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": world * n * T / (float(e2e_ms) * 1e-3), "unit": "env-steps/s",
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "roofline": {"bound": "hbm", "kernel": "play_h1_kernel (one episode, incl. end-of-episode reset)", "achieved": achieved,
+                             "peak": peaks["hbm_gbs"], "peak_source": which, "unit": "GB/s",
+                             "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                             "bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": kernel_ms}}
+        if not args.no_cpu_baseline:
+            from oracle import cpu_baseline
+            res = cpu_baseline.run(model, table, steps=1, warmup=0, horizon=T, budget_s=args.cpu_budget)
+            line["cpu_baseline"] = {"value": res["value"], "unit": "env-steps/s", "cores": res["cores"],
+                                    "kind": res["kind"], "sample": res["sample"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=N_ENVS)
+    ap.add_argument("--horizon", type=int, default=HORIZON)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -135,9 +135,10 @@ int om_traj_reset(const OmTraj* t, uint64_t seed, uint32_t env_id0, const uint8_
 /* get_current_sample for every env */
 int om_traj_current(const OmTraj* t, const int32_t* traj_no, const int32_t* step_no, const double* xy_off,
                     float* sample, int n, int ld, void* stream);
-/* get_next_sample; an env that reaches the end of its trajectory is reset (wrapped[i] = 1) exactly as
- * loco_env_base.py:534-537 does */
-int om_traj_next(const OmTraj* t, uint64_t seed, uint32_t env_id0,
+/* get_next_sample.  auto_reset != 0: an env that reaches the end of its trajectory is reset
+ * (wrapped[i] = 1) exactly as loco_env_base.py:534-537 does.  auto_reset == 0: such an env keeps
+ * step_no == T and its sample row is left untouched (the reference returns None), wrapped[i] = 1. */
+int om_traj_next(const OmTraj* t, uint64_t seed, uint32_t env_id0, int auto_reset,
                  int32_t* traj_no, int32_t* step_no, uint32_t* reset_count, double* xy_off,
                  float* sample, uint8_t* wrapped, int n, int ld, void* stream);
 

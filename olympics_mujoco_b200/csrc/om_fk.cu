@@ -130,9 +130,10 @@ using namespace om;
 extern "C" int om_fk(const OmModel* m, const float* qpos, const float* qvel, int n, int ld, float* xpos, float* xquat,
                      float* site_xpos, float* site_xmat, float* cvel, float* subtree_com, int force_generic,
                      void* stream) {
-  OM_REQUIRE(m && qpos, "om_fk: null model or qpos");
+  OM_REQUIRE(m, "om_fk: null model");
   OM_REQUIRE(n >= 0 && ld >= n, "om_fk: need 0 <= n <= ld (n=%d ld=%d)", n, ld);
-  if (n == 0) return 0;
+  if (n == 0) return 0;            // empty batch: nothing to enqueue (pointers may be null)
+  OM_REQUIRE(qpos, "om_fk: null qpos");
   cudaStream_t st = (cudaStream_t)stream;
   FkOut o{xpos, xquat, site_xpos, site_xmat, cvel, subtree_com};
   constexpr int BLOCK = 128;
@@ -150,10 +151,11 @@ extern "C" int om_fk(const OmModel* m, const float* qpos, const float* qvel, int
 extern "C" int om_h1_step(const OmModel* m, const OmH1Spec* spec, const float* qpos, const float* qvel,
                           const float* prev_x_vel, int n, int ld, float* xpos, float* xquat, float* site_xpos,
                           float* cvel, float* obs, float* reward, uint8_t* absorbing, void* stream) {
-  OM_REQUIRE(m && spec && qpos && qvel, "om_h1_step: null argument");
+  OM_REQUIRE(m && spec, "om_h1_step: null model or spec");
   OM_REQUIRE(n >= 0 && ld >= n, "om_h1_step: need 0 <= n <= ld (n=%d ld=%d)", n, ld);
-  OM_REQUIRE(!reward || prev_x_vel, "om_h1_step: reward requested without prev_x_vel");
   if (n == 0) return 0;
+  OM_REQUIRE(qpos && qvel, "om_h1_step: null qpos/qvel");
+  OM_REQUIRE(!reward || prev_x_vel, "om_h1_step: reward requested without prev_x_vel");
   H1SpecDev sp;
   if (make_spec(spec, m, &sp)) return 1;
   cudaStream_t st = (cudaStream_t)stream;
@@ -177,9 +179,9 @@ extern "C" int om_h1_step(const OmModel* m, const OmH1Spec* spec, const float* q
 }
 
 extern "C" int om_h1_has_fallen(const float* obs, int n, int ld, uint8_t* fallen, void* stream) {
-  OM_REQUIRE(obs && fallen, "om_h1_has_fallen: null argument");
   OM_REQUIRE(n >= 0 && ld >= n, "om_h1_has_fallen: need 0 <= n <= ld");
   if (n == 0) return 0;
+  OM_REQUIRE(obs && fallen, "om_h1_has_fallen: null argument");
   h1_fallen_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(obs, n, ld, fallen);
   OM_LAUNCHED();
   return 0;

@@ -141,10 +141,10 @@ using namespace om;
 extern "C" int om_ppo_returns(const float* rewards, const float* values, const uint8_t* path_end, const float* v_next,
                               const float* v_last, float gamma, int T, int n, int ld, float* ret, float* adv,
                               void* stream) {
-  OM_REQUIRE(rewards && (ret || adv), "om_ppo_returns: null argument");
-  OM_REQUIRE(!adv || values, "om_ppo_returns: advantages need values");
   OM_REQUIRE(T >= 0 && n >= 0 && ld >= n, "om_ppo_returns: bad sizes");
   if (T == 0 || n == 0) return 0;
+  OM_REQUIRE(rewards && (ret || adv), "om_ppo_returns: null argument");
+  OM_REQUIRE(!adv || values, "om_ppo_returns: advantages need values");
   ppo_returns_kernel<8><<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(rewards, values, path_end, v_next, v_last, gamma,
                                                                              T, n, ld, ret, adv);
   OM_LAUNCHED();
@@ -154,9 +154,9 @@ extern "C" int om_ppo_returns(const float* rewards, const float* values, const u
 extern "C" int om_gae(const float* rewards, const float* v, const float* v_next, const uint8_t* absorbing,
                       const uint8_t* last, float gamma, float lam, int T, int n, int ld, float* adv, float* v_target,
                       void* stream) {
-  OM_REQUIRE(rewards && v && v_next && (adv || v_target), "om_gae: null argument");
   OM_REQUIRE(T >= 0 && n >= 0 && ld >= n, "om_gae: bad sizes");
   if (T == 0 || n == 0) return 0;
+  OM_REQUIRE(rewards && v && v_next && (adv || v_target), "om_gae: null argument");
   gae_kernel<8><<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(rewards, v, v_next, absorbing, last, gamma, lam, T, n, ld,
                                                                      adv, v_target);
   OM_LAUNCHED();
@@ -164,9 +164,9 @@ extern "C" int om_gae(const float* rewards, const float* v, const float* v_next,
 }
 
 extern "C" int om_moments(const float* x, int rows, int C, int n, int ld, double* out, void* stream) {
-  OM_REQUIRE(x && out, "om_moments: null argument");
   OM_REQUIRE(rows >= 0 && C >= 1 && n >= 0 && ld >= n, "om_moments: bad sizes");
   if (rows == 0 || n == 0) return 0;
+  OM_REQUIRE(x && out, "om_moments: null argument");
   int gx = ceil_div(n, 256 * 4);
   if (gx < 1) gx = 1;
   if (gx > 1184) gx = 1184;
@@ -184,9 +184,9 @@ extern "C" int om_adv_stats(const double* moments, int unbiased, double eps, dou
 }
 
 extern "C" int om_normalize(const float* x, const double* stats, int rows, int n, int ld, float* y, void* stream) {
-  OM_REQUIRE(x && stats && y, "om_normalize: null argument");
   OM_REQUIRE(rows >= 0 && n >= 0 && ld >= n, "om_normalize: bad sizes");
   if (rows == 0 || n == 0) return 0;
+  OM_REQUIRE(x && stats && y, "om_normalize: null argument");
   int gx = ceil_div(n, 256);
   if (gx > 592) gx = 592;
   dim3 grid(gx, rows);

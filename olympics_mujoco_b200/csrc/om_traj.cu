@@ -42,14 +42,19 @@ __global__ void __launch_bounds__(128) traj_current_kernel(TrajDev t, const int3
   traj_write_sample(t, traj_no[env], step_no[env], xy_off[env], xy_off[(size_t)ld + env], sample, ld, env);
 }
 
-__global__ void __launch_bounds__(128) traj_next_kernel(TrajDev t, uint64_t seed, uint32_t env_id0, int32_t* traj_no,
-                                                        int32_t* step_no, uint32_t* reset_count, double* xy_off,
-                                                        float* sample, uint8_t* wrapped, int n, int ld) {
+__global__ void __launch_bounds__(128) traj_next_kernel(TrajDev t, uint64_t seed, uint32_t env_id0, int auto_reset,
+                                                        int32_t* traj_no, int32_t* step_no, uint32_t* reset_count,
+                                                        double* xy_off, float* sample, uint8_t* wrapped, int n, int ld) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= n) return;
   int tr = traj_no[env], st = step_no[env] + 1;
   double ox = xy_off[env], oy = xy_off[(size_t)ld + env];
   const bool wrap = st >= t.T;
+  if (wrap && !auto_reset) {            // get_next_sample returns None: the index parks at T, sample untouched
+    step_no[env] = t.T;
+    if (wrapped) wrapped[env] = 1;
+    return;
+  }
   if (wrap) {
     uint32_t rc = reset_count[env];
     traj_draw(t, seed, env_id0 + env, rc, tr, st);
@@ -238,9 +243,10 @@ extern "C" void om_traj_destroy(OmTraj* t) {
 extern "C" int om_traj_reset(const OmTraj* t, uint64_t seed, uint32_t env_id0, const uint8_t* mask,
                              const int32_t* forced_traj, const int32_t* forced_step, int32_t* traj_no, int32_t* step_no,
                              uint32_t* reset_count, double* xy_off, float* sample, int n, int ld, void* stream) {
-  OM_REQUIRE(t && traj_no && step_no && reset_count && xy_off, "om_traj_reset: null argument");
+  OM_REQUIRE(t, "om_traj_reset: null table");
   OM_REQUIRE(n >= 0 && ld >= n, "om_traj_reset: need 0 <= n <= ld");
   if (n == 0) return 0;
+  OM_REQUIRE(traj_no && step_no && reset_count && xy_off, "om_traj_reset: null state");
   traj_reset_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(t->d, seed, env_id0, mask, forced_traj, forced_step,
                                                                          traj_no, step_no, reset_count, xy_off, sample, n, ld);
   OM_LAUNCHED();
@@ -249,21 +255,23 @@ extern "C" int om_traj_reset(const OmTraj* t, uint64_t seed, uint32_t env_id0, c
 
 extern "C" int om_traj_current(const OmTraj* t, const int32_t* traj_no, const int32_t* step_no, const double* xy_off,
                                float* sample, int n, int ld, void* stream) {
-  OM_REQUIRE(t && traj_no && step_no && xy_off && sample, "om_traj_current: null argument");
+  OM_REQUIRE(t, "om_traj_current: null table");
   OM_REQUIRE(n >= 0 && ld >= n, "om_traj_current: need 0 <= n <= ld");
   if (n == 0) return 0;
+  OM_REQUIRE(traj_no && step_no && xy_off && sample, "om_traj_current: null argument");
   traj_current_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(t->d, traj_no, step_no, xy_off, sample, n, ld);
   OM_LAUNCHED();
   return 0;
 }
 
-extern "C" int om_traj_next(const OmTraj* t, uint64_t seed, uint32_t env_id0, int32_t* traj_no, int32_t* step_no,
-                            uint32_t* reset_count, double* xy_off, float* sample, uint8_t* wrapped, int n, int ld,
-                            void* stream) {
-  OM_REQUIRE(t && traj_no && step_no && reset_count && xy_off, "om_traj_next: null argument");
+extern "C" int om_traj_next(const OmTraj* t, uint64_t seed, uint32_t env_id0, int auto_reset, int32_t* traj_no,
+                            int32_t* step_no, uint32_t* reset_count, double* xy_off, float* sample, uint8_t* wrapped,
+                            int n, int ld, void* stream) {
+  OM_REQUIRE(t, "om_traj_next: null table");
   OM_REQUIRE(n >= 0 && ld >= n, "om_traj_next: need 0 <= n <= ld");
   if (n == 0) return 0;
-  traj_next_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(t->d, seed, env_id0, traj_no, step_no, reset_count,
+  OM_REQUIRE(traj_no && step_no && reset_count && xy_off, "om_traj_next: null state");
+  traj_next_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(t->d, seed, env_id0, auto_reset, traj_no, step_no, reset_count,
                                                                         xy_off, sample, wrapped, n, ld);
   OM_LAUNCHED();
   return 0;
@@ -278,9 +286,9 @@ extern "C" int om_h1_play_from_velocity(const OmModel* m, const OmH1Spec* spec, 
   OM_REQUIRE(spec->n_obs_q == 17 && t->d.K == 34, "om_h1_play_from_velocity: expects the 34-key H1 trajectory");
   for (int k = 0; k < 17; ++k)
     OM_REQUIRE(spec->obs_perm[k] == OM_H1_PERM_HOST[k], "om_h1_play_from_velocity: observation spec differs from UnitreeH1's");
+  if (n == 0) return 0;
   OM_REQUIRE(state->traj_no && state->step_no && state->reset_count && state->xy_off && state->curr_qpos &&
                  state->pending && state->prev_x_vel, "om_h1_play_from_velocity: incomplete state");
-  if (n == 0) return 0;
   PlayArgs a;
   a.t = t->d; a.seed = seed; a.env_id0 = env_id0; a.dt = dt; a.target = spec->target_velocity;
   a.use_absorbing = spec->use_absorbing_states; a.n_steps = n_steps; a.end_reset = end_episode_reset;

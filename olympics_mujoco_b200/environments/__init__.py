@@ -1,0 +1,4 @@
+from .loco_env_base import LocoEnvBase, ValidTaskConf  # noqa: F401
+from .unitree_h1 import BaseHumanoidRobot, UnitreeH1  # noqa: F401
+
+UnitreeH1.register()

@@ -1,0 +1,401 @@
+"""Batched ``LocoEnvBase``: the reference's environment API over n parallel environments on one B200.
+
+Mirrors ``olympic_mujoco/environments/loco_env_base.py`` (``make`` via mushroom ``Environment.make``,
+``reset`` :568-604, ``setup`` :606-657, ``set_sim_state`` :659-684, ``play_trajectory`` :338-442,
+``play_trajectory_from_velocity`` :444-560, ``_create_observation`` :737-767, ``reward`` :776-781,
+``_get_reward_function`` :783-825, ``create_dataset`` :926-968, ``get_obs_idx`` :1195-1205,
+``_get_from_obs`` :1207-1232, ``_len_qpos_qvel`` :1261-1273, ``register`` :1337-1350, ``ValidTaskConf``
+:1381-1455) and the pieces of mushroom_rl's ``MuJoCo`` / ``MultiMuJoCo`` it inherits.
+
+What differs by design:
+* every per-env quantity is a CUDA tensor; observations come back as ``[n_envs, D]`` (``[D]`` when the env
+  was made without ``n_envs``, the reference's single-env shape);
+* contact dynamics (``mj_step``) are NOT part of this path: ``step`` gets the post-physics state from an
+  attached dynamics callable (``attach_dynamics``) and runs the fused FK + observation + absorbing + reward
+  kernel on it;
+* resets draw from the Philox contract, not NumPy's global stream;
+* no viewer: ``render=True`` / ``record=True`` raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import warnings
+from copy import deepcopy
+from itertools import product
+
+import numpy as np
+import torch
+
+from .. import kernels as Kn
+from ..observation_helper import BatchedData, ObservationHelper, ObservationType
+from ..utils import CustomReward, NoReward, PosReward, TargetVelocityReward, Trajectory
+
+
+class Box:
+    """mushroom_rl.utils.spaces.Box (low/high/shape only)."""
+
+    def __init__(self, low, high):
+        self.low, self.high = np.array(low, dtype=np.float64), np.array(high, dtype=np.float64)
+
+    @property
+    def shape(self):
+        return self.low.shape
+
+
+class MDPInfo:
+    def __init__(self, observation_space, action_space, gamma, horizon):
+        self.observation_space, self.action_space = observation_space, action_space
+        self.gamma, self.horizon = gamma, horizon
+
+
+class LocoEnvBase:
+    _registered_envs = dict()
+
+    def __init__(self, model, action_spec, observation_spec, collision_groups=None, gamma=0.99, horizon=1000,
+                 n_substeps=10, reward_type=None, reward_params=None, traj_params=None, random_start=True,
+                 init_step_no=None, timestep=0.001, use_foot_forces=False, use_absorbing_states=True,
+                 n_envs=None, device="cuda", seed=0, env_id0=0, **_ignored_viewer_params):
+        if use_foot_forces:
+            raise NotImplementedError("use_foot_forces needs the contact solver, which is outside this path")
+        self._single = n_envs is None
+        self.n_envs = 1 if n_envs is None else int(n_envs)
+        self._device, self._seed, self._env_id0 = device, int(seed), int(env_id0)
+        self._model = model
+        self._timestep, self._n_substeps, self._n_intermediate_steps = timestep, n_substeps, 1
+        self._data = BatchedData(model, self.n_envs, device=device)
+        self._dm = Kn.DeviceModel(model)
+        self.obs_helper = ObservationHelper(observation_spec, model, self._data, max_joint_velocity=None)
+        self._action_spec = list(action_spec) if action_spec else list(model.actuator_names)
+        a_idx = [model.actuator_names.index(a) for a in self._action_spec]
+        low = np.where(model.actuator_ctrllimited[a_idx], model.actuator_ctrlrange[a_idx, 0], -np.inf)
+        high = np.where(model.actuator_ctrllimited[a_idx], model.actuator_ctrlrange[a_idx, 1], np.inf)
+        self.info = MDPInfo(Box(*self.obs_helper.get_obs_limits()), Box(low, high), gamma, horizon)
+        self._use_foot_forces = use_foot_forces
+        self._reward_function = self._get_reward_function(reward_type, reward_params)
+        self.info.observation_space = Box(*self._get_observation_space())
+        self.norm_act_mean = (high + low) / 2.0                                  # :165-175
+        self.norm_act_delta = (high - low) / 2.0
+        self.info.action_space.low[:] = -1.0
+        self.info.action_space.high[:] = 1.0
+        self._dataset = None
+        self.trajectories = None
+        if traj_params:
+            self.load_trajectory(traj_params)
+        self._random_start, self._init_step_no = random_start, init_step_no
+        self._use_absorbing_states = use_absorbing_states
+        self._dynamics = None
+        self._obs = None
+        self._play_state = None
+
+    # ------------------------------------------------------------------ registry / factory
+    @classmethod
+    def register(cls):
+        LocoEnvBase._registered_envs.setdefault(cls.__name__, cls)
+
+    @staticmethod
+    def list_registered_loco_mujoco():
+        return list(LocoEnvBase._registered_envs.keys())
+
+    @staticmethod
+    def make(env_name, *args, **kwargs):
+        """mushroom_rl ``Environment.make``: ``"Env.task.dataset"`` -> ``Env.generate(task, dataset, **kw)``."""
+        if "." in env_name:
+            parts = env_name.split(".")
+            env_name, args = parts[0], parts[1:] + list(args)
+        if env_name not in LocoEnvBase._registered_envs:
+            raise KeyError(f"environment {env_name!r} is not registered "
+                           f"(registered: {LocoEnvBase.list_registered_loco_mujoco()})")
+        env = LocoEnvBase._registered_envs[env_name]
+        if hasattr(env, "generate"):
+            return env.generate(*args, **kwargs)
+        return env(*args, **kwargs)
+
+    @classmethod
+    def get_all_task_names(cls):
+        names = []
+        for e in cls.list_registered_loco_mujoco():
+            env = cls._registered_envs[e]
+            for conf in env.valid_task_confs.get_all_combinations():
+                names.append(".".join([env.__name__] + list(conf.values())))
+        return names
+
+    # ------------------------------------------------------------------ shapes
+    @property
+    def dt(self):
+        return self._timestep * self._n_intermediate_steps * self._n_substeps
+
+    def _out(self, x):
+        """[n, ...] -> the reference's single-env shape when the env was made without n_envs."""
+        return x[0] if self._single else x
+
+    def _batched(self, x):
+        x = torch.as_tensor(x, device=self._device)
+        return x.unsqueeze(0) if (self._single and x.dim() == 1) else x
+
+    # ------------------------------------------------------------------ trajectories
+    def load_trajectory(self, traj_params, warn=True):
+        if self.trajectories is not None:
+            warnings.warn("New trajectories loaded, which overrides the old ones.", RuntimeWarning)
+        self.trajectories = Trajectory(keys=self.get_all_observation_keys(), low=self.info.observation_space.low,
+                                       high=self.info.observation_space.high, joint_pos_idx=self.obs_helper.joint_pos_idx,
+                                       interpolate_map=self._interpolate_map, interpolate_remap=self._interpolate_remap,
+                                       interpolate_map_params=self._get_interpolate_map_params(),
+                                       interpolate_remap_params=self._get_interpolate_remap_params(), warn=warn,
+                                       n_envs=self.n_envs, seed=self._seed, env_id0=self._env_id0, device=self._device,
+                                       **traj_params)
+
+    def get_all_observation_keys(self):
+        return self.obs_helper.get_all_observation_keys()
+
+    # ------------------------------------------------------------------ state
+    def set_sim_state(self, sample):
+        """:659-684: named scatter of spec-ordered samples [n, len(spec)] into qpos/qvel."""
+        sample = self._batched(sample).to(torch.float32)
+        spec = self.obs_helper.observation_spec
+        assert sample.shape[-1] == len(spec)
+        for i, (key, name, ot) in enumerate(spec):
+            if ot == ObservationType.JOINT_POS:
+                self._data.qpos[self._data.joint_rows(name)[0]] = sample[:, i]
+            elif ot == ObservationType.JOINT_VEL:
+                self._data.qvel[self._data.joint_rows(name)[1]] = sample[:, i]
+
+    def set_state(self, qpos, qvel):
+        """:1155-1160: write qpos/qvel ([n, nq], [n, nv]) and run the forward pass (K1)."""
+        qpos, qvel = self._batched(qpos), self._batched(qvel)
+        assert qpos.shape == (self.n_envs, self._model.nq) and qvel.shape == (self.n_envs, self._model.nv)
+        self._data.qpos.copy_(qpos.t())
+        self._data.qvel.copy_(qvel.t())
+        self.forward()
+
+    def forward(self):
+        """The hot-path subset of ``mujoco.mj_forward``: kinematics, COM, COM velocity (K1)."""
+        d = self._data
+        Kn.fk(self._dm, d.qpos, d.qvel, out=dict(xpos=d.xpos, xquat=d.xquat, site_xpos=d.site_xpos,
+                                                 site_xmat=d.site_xmat, cvel=d.cvel, subtree_com=d.subtree_com))
+
+    @property
+    def data(self):
+        return self._data
+
+    def _init_sim_from_obs(self, obs):
+        obs = self._batched(obs)
+        obs = torch.cat([torch.zeros((obs.shape[0], 2), device=obs.device, dtype=obs.dtype), obs], dim=1)   # :697
+        spec = self.obs_helper.observation_spec
+        assert obs.shape[1] >= len(spec)
+        self.set_sim_state(obs[:, :len(spec)])
+
+    def reset(self, obs=None):
+        """:568-604 (imitation-learning branch)."""
+        self._data.qpos[:] = torch.as_tensor(self._model.qpos0, dtype=torch.float32, device=self._device)[:, None]
+        self._data.qvel.zero_()                                                              # mj_resetData
+        self.setup(obs)
+        self._obs = self._create_observation(self.obs_helper._build_obs(self._data))
+        return self._out(self._modify_observation(self._obs))
+
+    def setup(self, obs):
+        """:606-657."""
+        self._reward_function.reset_state()
+        if obs is not None:
+            self._init_sim_from_obs(obs)
+            return
+        if not self.trajectories and self._random_start:
+            raise ValueError("Random start not possible without trajectory data.")
+        elif not self.trajectories and self._init_step_no is not None:
+            raise ValueError("Setting an initial step is not possible without trajectory data.")
+        elif self._init_step_no is not None and self._random_start:
+            raise ValueError("Either use a random start or set an initial step, not both.")
+        if self.trajectories is not None:
+            if self._random_start:
+                sample = self.trajectories.reset_trajectory()
+            elif self._init_step_no:
+                traj_len = self.trajectories.trajectory_length
+                n_traj = self.trajectories.number_of_trajectories
+                assert self._init_step_no <= traj_len * n_traj
+                sample = self.trajectories.reset_trajectory(int(self._init_step_no % traj_len),
+                                                            int(self._init_step_no / traj_len))
+            else:
+                sample = self.trajectories.reset_trajectory(substep_no=0)
+            self.set_sim_state(sample)
+
+    # ------------------------------------------------------------------ observations
+    def _get_observation_space(self):
+        return self.info.observation_space.low[2:], self.info.observation_space.high[2:]
+
+    def _create_observation(self, obs):
+        """:737-767: drop the root x and y entries."""
+        return obs[..., 2:].contiguous()
+
+    def _modify_observation(self, obs):
+        return obs
+
+    def _get_joint_pos(self):
+        return self.obs_helper.get_joint_pos_from_obs(self.obs_helper._build_obs(self._data))
+
+    def _get_joint_vel(self):
+        return self.obs_helper.get_joint_vel_from_obs(self.obs_helper._build_obs(self._data))
+
+    def get_obs_idx(self, key):
+        return [i - 2 for i in self.obs_helper.obs_idx_map[key]]
+
+    def _get_idx(self, keys):
+        if type(keys) != list:
+            assert type(keys) == str
+            keys = [keys]
+        return np.concatenate([self.obs_helper.obs_idx_map[k] for k in keys]) - 2
+
+    def _get_from_obs(self, obs, keys):
+        """:1207-1232."""
+        obs = torch.as_tensor(obs)
+        pad = torch.zeros(obs.shape[:-1] + (2,), dtype=obs.dtype, device=obs.device)
+        obs = torch.cat([pad, obs], dim=-1)
+        if type(keys) != list:
+            assert type(keys) == str
+            keys = [keys]
+        return torch.cat([self.obs_helper.get_from_obs(obs, k) for k in keys], dim=-1)
+
+    def get_kinematic_obs_mask(self):
+        return np.arange(len(self.obs_helper.observation_spec) - 2)
+
+    def _len_qpos_qvel(self):
+        keys = self.get_all_observation_keys()
+        return len([k for k in keys if k.startswith("q_")]), len([k for k in keys if k.startswith("dq_")])
+
+    # ------------------------------------------------------------------ reward / termination
+    def reward(self, state, action, next_state, absorbing):
+        return self._reward_function(state, action, next_state, absorbing)
+
+    def _get_reward_function(self, reward_type, reward_params):
+        """:783-825."""
+        if reward_type == "custom":
+            return CustomReward(**reward_params)
+        elif reward_type == "target_velocity":
+            x_vel_idx = self.get_obs_idx("dq_pelvis_tx")
+            assert len(x_vel_idx) == 1
+            return TargetVelocityReward(x_vel_idx=x_vel_idx[0], **reward_params)
+        elif reward_type == "x_pos":
+            x_idx = self.get_obs_idx("q_pelvis_tx")
+            assert len(x_idx) == 1
+            return PosReward(pos_idx=x_idx[0])
+        elif reward_type is None:
+            return NoReward()
+        raise NotImplementedError("The specified reward has not been implemented: %s" % reward_type)
+
+    def _has_fallen(self, obs, return_err_msg=False):
+        raise NotImplementedError
+
+    def is_absorbing(self, obs):
+        return self._has_fallen(obs) if self._use_absorbing_states else self._out(
+            torch.zeros(self.n_envs, dtype=torch.bool, device=self._device))
+
+    # ------------------------------------------------------------------ actions (N1: the step before the path)
+    def _preprocess_action(self, action):
+        """:1050-1069."""
+        a = torch.as_tensor(action, device=self._device, dtype=torch.float32)
+        return a * torch.as_tensor(self.norm_act_delta, device=self._device, dtype=torch.float32) + \
+            torch.as_tensor(self.norm_act_mean, device=self._device, dtype=torch.float32)
+
+    def attach_dynamics(self, fn):
+        """``fn(env, ctrl [n, nu]) -> (qpos [n, nq], qvel [n, nv])``: the physics between two observations
+        (``mj_step`` x n_substeps in the reference).  Contact dynamics stay outside this package."""
+        self._dynamics = fn
+
+    def step(self, action):
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ dataset
+    def create_dataset(self, ignore_keys=None):
+        """:926-968 (the terminal-state check runs on the GPU)."""
+        if self._dataset is None:
+            if self.trajectories is None:
+                raise ValueError("No trajectory was passed to the environment. "
+                                 "To create a dataset pass a trajectory first.")
+            dataset = self.trajectories.create_dataset(ignore_keys=ignore_keys)
+            fallen, msg = self._has_fallen(torch.as_tensor(dataset["states"], dtype=torch.float32, device=self._device),
+                                           return_err_msg=True, batched=True)
+            if bool(fallen.any()):
+                raise ValueError("Some of the states in the created dataset are terminal states. "
+                                 "This should not happen.\n\nViolations:\n" + msg)
+            self._dataset = deepcopy(dataset)
+            return dataset
+        return deepcopy(self._dataset)
+
+    # ------------------------------------------------------------------ playback
+    def play_trajectory(self, n_episodes=None, n_steps_per_episode=None, render=False, record=False,
+                        recorder_params=None):
+        """:338-442: force the model to the trajectory samples step by step (per-step kernels K3 + K1)."""
+        assert self.trajectories is not None
+        if render or record:
+            raise NotImplementedError("rendering is outside the hot path; call with render=False")
+        assert n_episodes is not None and n_steps_per_episode is not None, "unbounded playback needs a viewer"
+        self.reset()
+        sample = self.trajectories.get_current_sample()
+        self.set_sim_state(sample)
+        dev = self.trajectories.device_state
+        fallen_any = torch.zeros(self.n_envs, dtype=torch.bool, device=self._device)
+        obs = None
+        for _ in range(n_episodes):
+            for _ in range(n_steps_per_episode):
+                self.set_sim_state(sample)
+                self.forward()
+                dev.next(sample=self.trajectories._sample, auto_reset=True)          # :414-418
+                sample = self.trajectories._sample.t()
+                obs = self._create_observation(sample)
+                fallen_any |= self._has_fallen(obs, batched=True)
+            self.reset()
+        return dict(obs=self._out(obs), has_fallen=self._out(fallen_any))
+
+    def play_trajectory_from_velocity(self, n_episodes=None, n_steps_per_episode=None, render=False, record=False,
+                                      recorder_params=None, out=None, want=None):
+        raise NotImplementedError
+
+    def stop(self):
+        pass
+
+    # ------------------------------------------------------------------ interpolation hooks (:1275-1335)
+    @staticmethod
+    def _interpolate_map(traj, **interpolate_map_params):
+        return np.array(traj)
+
+    @staticmethod
+    def _interpolate_remap(traj, **interpolate_remap_params):
+        return [obs for obs in traj]
+
+    def _get_interpolate_map_params(self):
+        pass
+
+    def _get_interpolate_remap_params(self):
+        pass
+
+
+class ValidTaskConf:
+    """:1381-1455."""
+
+    def __init__(self, tasks=None, modes=None, data_types=None, non_combinable=None):
+        self.tasks, self.modes, self.data_types, self.non_combinable = tasks, modes, data_types, non_combinable
+        if non_combinable is not None:
+            for nc in non_combinable:
+                assert len(nc) == 3
+
+    def get_all(self):
+        return deepcopy(self.tasks), deepcopy(self.modes), deepcopy(self.data_types), deepcopy(self.non_combinable)
+
+    def get_all_combinations(self):
+        confs = []
+        tasks = self.tasks if self.tasks is not None else [None]
+        modes = self.modes if self.modes is not None else [None]
+        data_types = self.data_types if self.data_types is not None else [None]
+        for t, m, dt in product(tasks, modes, data_types):
+            conf = dict()
+            if t is not None:
+                conf["task"] = t
+            if m is not None:
+                conf["mode"] = m
+            if dt is not None:
+                conf["data_type"] = dt
+            if self.non_combinable is not None:
+                for bad_t, bad_m, bad_dt in self.non_combinable:
+                    if not ((t == bad_t or bad_t is None) and (m == bad_m or bad_m is None)
+                            and (dt == bad_dt or bad_dt is None)):
+                        confs.append(conf)
+            else:
+                confs.append(conf)
+        return confs

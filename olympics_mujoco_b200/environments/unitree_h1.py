@@ -1,0 +1,226 @@
+"""Batched ``UnitreeH1`` environment (reference ``real_humanoid_robots/UnitreeH1.py`` and
+``base_robot/base_humanoid_robot.py``): same constructor switches, observation/action specs, ``generate``,
+``_has_fallen`` and ``is_absorbing``; ``step`` and ``play_trajectory_from_velocity`` run the fused CUDA kernels.
+"""
+from __future__ import annotations
+
+import warnings
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .. import kernels as Kn
+from .. import mjcf, synthetic
+from ..observation_helper import ObservationType
+from ..utils import check_validity_task_mode_dataset
+from .loco_env_base import LocoEnvBase, ValidTaskConf
+
+
+class BaseHumanoidRobot(LocoEnvBase):
+    """base_robot/base_humanoid_robot.py: dataset defaults, ``generate`` timing logic, ``is_absorbing``."""
+
+    def create_dataset(self, ignore_keys=None):
+        if ignore_keys is None:
+            ignore_keys = ["q_pelvis_tx", "q_pelvis_tz"]                      # base_humanoid_robot.py:33-34
+        return super().create_dataset(ignore_keys)
+
+    @staticmethod
+    def generate(env, path, task="walk", dataset_type="real", debug=False, clip_trajectory_to_joint_ranges=False,
+                 traj_params=None, **kwargs):
+        """base_humanoid_robot.py:124-234.  ``traj_params`` (extension) overrides the dataset lookup: pass
+        ``dict(traj_path=...)``, ``dict(traj_files=...)`` or ``dict(table=...)``.  When the reference's dataset
+        file is absent (they are not redistributable / not available offline) a synthetic dataset-shaped
+        trajectory is used, with the same warning the reference gives before falling back to its mini datasets."""
+        if task == "walk":
+            mdp = env(reward_type="target_velocity", reward_params=dict(target_velocity=1.25), **kwargs)
+        elif task == "run":
+            mdp = env(reward_type="target_velocity", reward_params=dict(target_velocity=2.5), **kwargs)
+        else:
+            raise ValueError(f"unsupported task {task!r}")
+        desired_contr_freq = 1 / mdp.dt
+        if traj_params is None:
+            if dataset_type != "real":
+                raise NotImplementedError("perfect datasets need the reference's dataset files")
+            traj_data_freq = 500
+            full = Path(__file__).resolve().parent.parent / path
+            if full.exists():
+                traj_params = dict(traj_path=str(full))
+            else:
+                warnings.warn("Datasets not found, falling back to a synthetic dataset-shaped trajectory. Please "
+                              "install the datasets to use this environment for imitation learning!")
+                traj_params = dict(traj_files=synthetic.h1_walk_dataset(model=mdp._model,
+                                                                         speed=1.25 if task == "walk" else 2.5))
+            traj_params.update(traj_dt=1 / traj_data_freq, control_dt=1 / desired_contr_freq,
+                               clip_trajectory_to_joint_ranges=clip_trajectory_to_joint_ranges)
+        mdp.load_trajectory(traj_params, warn=False)
+        return mdp
+
+    def is_absorbing(self, obs):
+        """base_humanoid_robot.py:246-260 (imitation-learning branch)."""
+        if self._use_absorbing_states:
+            return self._has_fallen(obs)
+        return self._out(torch.zeros(self.n_envs, dtype=torch.bool, device=self._device))
+
+
+class UnitreeH1(BaseHumanoidRobot):
+    valid_task_confs = ValidTaskConf(tasks=["walk", "run", "carry"], data_types=["real", "perfect"],
+                                     non_combinable=[("carry", None, "perfect")])
+
+    def __init__(self, disable_arms=True, disable_back_joint=False, hold_weight=False, weight_mass=None, xml_path=None,
+                 **kwargs):
+        if hold_weight:
+            raise NotImplementedError("the 'carry' variants add bodies to the MJCF; not built in this round")
+        action_spec = self._get_action_specification()
+        observation_spec = self._get_observation_specification()
+        self._hidable_obs = ("positions", "velocities", "foot_forces", "weight")
+        self._disable_arms, self._disable_back_joint = disable_arms, disable_back_joint
+        joints_to_remove, motors_to_remove, _ = self._get_xml_modifications()
+        obs_to_remove = ["q_" + j for j in joints_to_remove] + ["dq_" + j for j in joints_to_remove]
+        observation_spec = [e for e in observation_spec if e[0] not in obs_to_remove]
+        action_spec = [a for a in action_spec if a not in motors_to_remove]
+        if xml_path is not None:                       # compile the user's MJCF (the reference's h1.xml)
+            model = mjcf.compile_unitree_h1(xml_path, disable_arms=disable_arms, disable_back_joint=disable_back_joint)
+        elif disable_arms and not disable_back_joint:
+            model = mjcf.load_builtin("unitree_h1")
+        elif not disable_arms and not disable_back_joint:
+            model = mjcf.load_builtin("unitree_h1_arms")
+        else:
+            raise ValueError("disable_back_joint=True needs xml_path (no pre-compiled table for that variant)")
+        super().__init__(model, action_spec, observation_spec, **kwargs)
+        js = [e[1] for e in observation_spec if e[2] == ObservationType.JOINT_POS]
+        perm = [int(model.jnt_qposadr[model.jnt_names.index(j)]) for j in js]
+        rf = self._reward_function
+        self._spec = Kn.make_h1_spec(perm, self.get_obs_idx("dq_pelvis_tx")[0],
+                                     target_velocity=getattr(rf, "_target_vel", 0.0),
+                                     use_absorbing_states=kwargs.get("use_absorbing_states", True))
+        self._fused_reward = hasattr(rf, "_target_vel")
+        self._prev_x_vel = torch.zeros(self.n_envs, device=self._device)
+
+    # ------------------------------------------------------------------ specs (UnitreeH1.py:134-160, 293-376)
+    def _get_xml_modifications(self):
+        joints, motors = [], []
+        if self._disable_arms:
+            joints += list(mjcf.H1_ARM_JOINTS)
+            motors += [j + "_actuator" for j in mjcf.H1_ARM_JOINTS]
+        if self._disable_back_joint:
+            joints += ["back_bkz"]
+            motors += ["back_bkz_actuator"]
+        return joints, motors, []
+
+    @staticmethod
+    def _get_observation_specification():
+        joints = synthetic.H1_SPEC_JOINTS
+        return [("q_" + j, j, ObservationType.JOINT_POS) for j in joints] + \
+               [("dq_" + j, j, ObservationType.JOINT_VEL) for j in joints]
+
+    @staticmethod
+    def _get_action_specification():
+        order = ["back_bkz", "l_arm_shy", "l_arm_shx", "l_arm_shz", "left_elbow", "r_arm_shy", "r_arm_shx", "r_arm_shz",
+                 "right_elbow", "hip_flexion_r", "hip_adduction_r", "hip_rotation_r", "knee_angle_r", "ankle_angle_r",
+                 "hip_flexion_l", "hip_adduction_l", "hip_rotation_l", "knee_angle_l", "ankle_angle_l"]
+        return [j + "_actuator" for j in order]
+
+    @staticmethod
+    def _get_grf_size():
+        return 6
+
+    # ------------------------------------------------------------------ termination (UnitreeH1.py:162-203)
+    def _has_fallen(self, obs, return_err_msg=False, batched=False):
+        obs = torch.as_tensor(obs, device=self._device, dtype=torch.float32)
+        single = obs.dim() == 1
+        o = obs.unsqueeze(0) if single else obs
+        fallen = Kn.h1_has_fallen(o[:, :4].t().contiguous()).bool()
+        res = fallen[0] if (single and not batched) else fallen
+        if not return_err_msg:
+            return res
+        msg = ""
+        if bool(fallen.any()):
+            row = o[int(torch.nonzero(fallen)[0])].double().cpu().numpy()
+            if row[0] < -0.3 or row[0] > 0.1:
+                msg += "pelvis_y_condition violated.\n"
+            elif row[1] < -np.pi / 4.5 or row[1] > np.pi / 12:
+                msg += "pelvis_tilt_condition violated.\n"
+            elif row[2] < -np.pi / 12 or row[2] > np.pi / 8:
+                msg += "pelvis_list_condition violated.\n"
+            else:
+                msg += "pelvis_rotation_condition violated.\n"
+        return res, msg
+
+    # ------------------------------------------------------------------ factory (UnitreeH1.py:205-242)
+    @staticmethod
+    def generate(task="walk", dataset_type="real", **kwargs):
+        check_validity_task_mode_dataset(UnitreeH1.__name__, task, None, dataset_type,
+                                         *UnitreeH1.valid_task_confs.get_all())
+        if task == "carry":
+            raise NotImplementedError("the 'carry' variants add bodies to the MJCF; not built in this round")
+        if dataset_type == "real":
+            path = "datasets/humanoids/real/05-run_UnitreeH1.npz" if task == "run" else \
+                "datasets/humanoids/real/02-constspeed_UnitreeH1.npz"
+        else:
+            path = "datasets/humanoids/perfect/unitreeh1_%s/perfect_expert_dataset_det.npz" % ("run" if task == "run" else "walk")
+        return BaseHumanoidRobot.generate(UnitreeH1, path, task, dataset_type, clip_trajectory_to_joint_ranges=True,
+                                          **kwargs)
+
+    # ------------------------------------------------------------------ step (mushroom MuJoCo.step)
+    def reset(self, obs=None):
+        out = super().reset(obs)
+        self._prev_x_vel.copy_(self._obs[:, self._spec.x_vel_idx])
+        self._play_state = None
+        return out
+
+    def step(self, action):
+        """action [n, nu] in [-1, 1] -> (obs, reward, absorbing, info).  The physics between observations comes
+        from the attached dynamics; everything after it is one fused kernel (K1 + K2)."""
+        if self._dynamics is None:
+            raise RuntimeError("step() needs a dynamics backend: env.attach_dynamics(fn).  Contact dynamics "
+                               "(mj_step) are outside this package's hot path.")
+        ctrl = self._preprocess_action(self._batched(action))
+        qpos, qvel = self._dynamics(self, ctrl)
+        d = self._data
+        d.qpos.copy_(torch.as_tensor(qpos, device=self._device, dtype=torch.float32).reshape(self.n_envs, -1).t())
+        d.qvel.copy_(torch.as_tensor(qvel, device=self._device, dtype=torch.float32).reshape(self.n_envs, -1).t())
+        prev_obs = self._obs
+        out = Kn.h1_step(self._dm, self._spec, d.qpos, d.qvel, self._prev_x_vel,
+                         out=dict(xpos=d.xpos, xquat=d.xquat, site_xpos=d.site_xpos, cvel=d.cvel))
+        cur_obs = out["obs"].t()
+        absorbing = out["absorbing"].bool()
+        reward = out["reward"] if self._fused_reward else self.reward(prev_obs, ctrl, cur_obs, absorbing)
+        self._obs = cur_obs
+        self._prev_x_vel.copy_(out["obs"][self._spec.x_vel_idx])
+        return self._out(self._modify_observation(cur_obs)), self._out(reward), self._out(absorbing), {}
+
+    # ------------------------------------------------------------------ fused playback (loco_env_base.py:444-560)
+    def make_rollout_buffers(self, n_steps, want=("xpos", "xquat", "site_xpos", "cvel", "obs", "reward", "fallen",
+                                                  "traj_no_t", "step_no_t")):
+        m, n, dev = self._model, self.n_envs, self._device
+        spec = dict(xpos=(m.nbody * 3, torch.float32), xquat=(m.nbody * 4, torch.float32),
+                    site_xpos=(m.nsite * 3, torch.float32), cvel=(m.nbody * 6, torch.float32), obs=(32, torch.float32),
+                    reward=(None, torch.float32), fallen=(None, torch.uint8), traj_no_t=(None, torch.int32),
+                    step_no_t=(None, torch.int32))
+        return {k: torch.empty((n_steps, n) if spec[k][0] is None else (n_steps, spec[k][0], n), dtype=spec[k][1],
+                               device=dev) for k in want}
+
+    def play_trajectory_from_velocity(self, n_episodes=None, n_steps_per_episode=None, render=False, record=False,
+                                      recorder_params=None, out=None, want=None):
+        """Replays the loaded trajectory by integrating its joint velocities (reference semantics, one fused
+        kernel per episode).  Returns the last episode's time-major rollout buffers ([T, C, n] SoA; use
+        ``kernels.env_major`` for [T, n, ...] views) -- the reference returns nothing and only renders."""
+        assert self.trajectories is not None
+        if render or record:
+            raise NotImplementedError("rendering is outside the hot path; call with render=False")
+        assert n_episodes is not None and n_steps_per_episode is not None, "unbounded playback needs a viewer"
+        if not self._dm.specialised or len(self.obs_helper.observation_spec) != 34:
+            raise NotImplementedError("fused playback is generated for the default UnitreeH1 (arms disabled)")
+        dev = self.trajectories.device_state
+        if self._play_state is None:
+            self.reset()                                                             # :481
+            sample = self.trajectories.get_current_sample().t().contiguous()         # :483
+            self._play_state = dict(curr_qpos=sample[:17].double().contiguous(), pending=sample.clone(),
+                                    prev_x_vel=self._prev_x_vel)
+        res = None
+        for _ in range(n_episodes):
+            kw = {} if want is None else dict(want=want)
+            res = Kn.h1_play_from_velocity(self._dm, self._spec, dev, self._play_state, n_steps_per_episode,
+                                           dt=self.dt, end_episode_reset=True, out=out, **kw)
+        return res

@@ -187,10 +187,10 @@ class DeviceTrajectory:
                                           _p(sample, torch.float32), self.n, max(self.n, 1), _stream()))
         return sample
 
-    def next(self, sample=None, wrapped=None):
+    def next(self, sample=None, wrapped=None, auto_reset=True):
         if sample is None:
             sample = soa(self.K, self.n, device=self.traj_no.device)
-        check(_lib.load().om_traj_next(self.handle, self.seed, self.env_id0, _p(self.traj_no), _p(self.step_no),
+        check(_lib.load().om_traj_next(self.handle, self.seed, self.env_id0, int(bool(auto_reset)), _p(self.traj_no), _p(self.step_no),
                                        _p(self.reset_count), _p(self.xy_off), _p(sample, torch.float32),
                                        _p(wrapped, torch.uint8), self.n, max(self.n, 1), _stream()))
         return sample

@@ -1,0 +1,143 @@
+"""GPU: the reference-facing Python API (LocoEnvBase.make / reset / step / play_trajectory_from_velocity,
+ObservationHelper, Trajectory) on top of the kernels, checked against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _table():
+    tab = np.load(GOLDEN / "trajectory_ref.npz")["table"].copy()
+    tab[2:] = tab[2:].astype(np.float32).astype(np.float64)
+    return tab
+
+
+def _make(n_envs, **kw):
+    import olympics_mujoco_b200 as om
+    return om.LocoEnvBase.make("UnitreeH1.walk.real", n_envs=n_envs, traj_params=dict(table=_table()), seed=77, **kw)
+
+
+def test_make_reset_shapes_and_spaces():
+    from oracle import h1 as OH
+    env = _make(16)
+    assert env.info.observation_space.shape == (32,) and env.info.action_space.shape == (11,)
+    assert env.info.gamma == 0.99 and env.info.horizon == 1000 and abs(env.dt - 0.01) < 1e-12
+    assert env.get_all_observation_keys() == OH.keys(env._model)
+    assert env.get_obs_idx("dq_pelvis_tx") == [15] and env._len_qpos_qvel() == (17, 17)
+    assert list(env.get_kinematic_obs_mask()) == list(range(32))
+    obs = env.reset()
+    assert tuple(obs.shape) == (16, 32)
+    # reset puts every env on its (Philox) trajectory sample, x and y re-centred to 0
+    tr = env.trajectories
+    tab = _table()
+    tn, sn = tr.traj_no.cpu().numpy(), tr.subtraj_step_no.cpu().numpy()
+    ref = np.stack([tab[2:, a, b] for a, b in zip(tn, sn)])
+    assert np.array_equal(obs.cpu().numpy(), ref.astype(np.float32))
+    assert float(env.data.qpos[:2].abs().max()) == 0.0
+    single = _make(None)
+    assert tuple(single.reset().shape) == (32,)
+
+
+def test_step_with_attached_dynamics_matches_oracle():
+    import torch
+    from oracle import h1 as OH
+    env = _make(32)
+    obs0 = env.reset().clone()
+    g = torch.Generator(device="cuda").manual_seed(0)
+
+    def dynamics(e, ctrl):                       # stand-in physics: a deterministic perturbation of the state
+        q = e.data.qpos.t() + 0.01 * torch.randn((e.n_envs, 17), device="cuda", generator=g)
+        v = e.data.qvel.t() + 0.1 * torch.randn((e.n_envs, 17), device="cuda", generator=g)
+        return q, v
+
+    with pytest.raises(RuntimeError, match="dynamics"):
+        env.step(torch.zeros((32, 11), device="cuda"))
+    env.attach_dynamics(dynamics)
+    prev = obs0
+    for _ in range(3):
+        obs, reward, absorbing, info = env.step(torch.zeros((32, 11), device="cuda"))
+        q = env.data.qpos.t().double().cpu().numpy()
+        v = env.data.qvel.t().double().cpu().numpy()
+        ref = OH.step(env._model, q, v, prev.double().cpu().numpy())
+        assert np.array_equal(obs.cpu().numpy(), ref["obs"].astype(np.float32))
+        assert np.array_equal(absorbing.cpu().numpy(), ref["absorbing"])
+        assert_close(reward.cpu().numpy(), ref["reward"], "reward")
+        assert_close(env.data.xpos.t().cpu().numpy().reshape(32, 21, 3), ref["xpos"], "xpos")
+        assert_close(env.data.cvel.t().cpu().numpy().reshape(32, 21, 6), ref["cvel"], "cvel")
+        # reward(state, ...) called by hand agrees with the fused kernel
+        assert_close(env.reward(prev, None, obs, absorbing).cpu().numpy(), ref["reward"], "reward api")
+        assert np.array_equal(env.is_absorbing(obs).cpu().numpy(), ref["absorbing"])
+        prev = obs.clone()
+
+
+def test_play_trajectory_from_velocity_api_matches_oracle():
+    from olympics_mujoco_b200 import kernels as Kn
+    from oracle import h1 as OH
+    n, T = 8, 90
+    env = _make(n)
+    out = env.play_trajectory_from_velocity(n_episodes=2, n_steps_per_episode=T, render=False)
+    xpos = Kn.env_major(out["xpos"], 21, 3).cpu().numpy()           # [T, n, 21, 3] view of the SoA buffer
+    for e in range(n):
+        ref = OH.play_trajectory_from_velocity(env._model, _table(), 2, T, seed=77, env_id=e)
+        assert np.array_equal(out["step_no_t"][:, e].cpu().numpy(), ref["step_no"][T:])
+        assert_close(xpos[:, e], ref["xpos"][T:], "xpos (second episode)")
+        assert np.array_equal(out["obs"][:, :, e].cpu().numpy(), ref["obs"][T:].astype(np.float32))
+    with pytest.raises(NotImplementedError):
+        env.play_trajectory_from_velocity(1, 1, render=True)
+
+
+def test_play_trajectory_and_dataset_and_trajectory_api():
+    import torch
+    from oracle import h1 as OH
+    env = _make(4)
+    res = env.play_trajectory(n_episodes=1, n_steps_per_episode=60, render=False)
+    assert tuple(res["obs"].shape) == (4, 32) and not bool(res["has_fallen"].any())
+    ds = env.create_dataset()
+    z = np.load(GOLDEN / "trajectory_ref.npz")
+    assert ds["states"].shape == (149, 32) and np.array_equal(ds["last"], z["ds_last"])
+    # a dataset with a terminal state is rejected (loco_env_base.py:949-957)
+    env._dataset = None
+    bad = env.trajectories.trajectories[2]
+    bad[0, 10] = 5.0                                               # q_pelvis_ty far above the 0.1 threshold
+    with pytest.raises(ValueError, match="terminal states"):
+        env.create_dataset()
+    # Trajectory object: reset(substep, traj) / current / next / None at the end (single env)
+    single = _make(None)
+    tr = single.trajectories
+    s = tr.reset_trajectory(substep_no=47, traj_no=1)
+    tab = _table()
+    assert_close(s[0, 2:].cpu().numpy(), tab[2:, 1, 47], "forced reset sample", rtol=1e-7, atol=1e-7)
+    assert tr.get_next_sample() is not None and tr.get_next_sample() is not None       # 48, 49
+    assert tr.get_next_sample() is None and int(tr.subtraj_step_no[0]) == 50           # trajectory_length
+
+
+def test_observation_helper_generic_spec():
+    """Upstream ObservationHelper semantics on body/site entries (BODY_POS, BODY_ROT, BODY_VEL, SITE_POS)."""
+    import torch
+    from olympics_mujoco_b200.observation_helper import BatchedData, ObservationHelper, ObservationType
+    from olympics_mujoco_b200 import kernels as Kn, mjcf
+    from oracle import kinematics as K
+    model = mjcf.load_builtin("unitree_h1")
+    n = 6
+    data = BatchedData(model, n)
+    spec = [("q_knee", "knee_angle_l", ObservationType.JOINT_POS), ("torso_pos", "torso_link", ObservationType.BODY_POS),
+            ("torso_rot", "torso_link", ObservationType.BODY_ROT), ("ankle_vel", "left_ankle_link", ObservationType.BODY_VEL),
+            ("imu", "imu", ObservationType.SITE_POS), ("dq_knee", "knee_angle_l", ObservationType.JOINT_VEL)]
+    oh = ObservationHelper(spec, model, data)
+    assert oh.obs_idx_map["torso_rot"] == [4, 5, 6, 7] and oh.joint_pos_idx == [0] and oh.joint_vel_idx == [17]
+    assert oh.obs_low[0] == -0.26 and oh.obs_high[0] == 2.05 and np.isinf(oh.obs_low[1])
+    rng = np.random.default_rng(0)
+    q = rng.normal(0, 0.3, (n, 17)).astype(np.float32); v = rng.normal(0, 1, (n, 17)).astype(np.float32)
+    data.qpos.copy_(Kn.to_soa(q)); data.qvel.copy_(Kn.to_soa(v))
+    dm = Kn.DeviceModel(model)
+    Kn.fk(dm, data.qpos, data.qvel, out=dict(xpos=data.xpos, xquat=data.xquat, cvel=data.cvel, site_xpos=data.site_xpos,
+                                             site_xmat=data.site_xmat, subtree_com=data.subtree_com))
+    obs = oh._build_obs(data).cpu().numpy()
+    ref = K.forward(model, q.astype(np.float64), v.astype(np.float64))
+    t, a = model.body_id("torso_link"), model.body_id("left_ankle_link")
+    exp = np.concatenate([q[:, [9]], ref["xpos"][:, t], ref["xquat"][:, t], ref["cvel"][:, a], ref["site_xpos"][:, 0],
+                          v[:, [9]]], axis=1)
+    assert_close(obs, exp, "generic obs")
+    assert_close(oh.get_from_obs(torch.as_tensor(obs), "imu").numpy(), ref["site_xpos"][:, 0], "get_from_obs")

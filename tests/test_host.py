@@ -1,0 +1,149 @@
+"""CPU: host-side logic -- MJCF compiler, code generator, Trajectory load path, C-ABI surface."""
+import ctypes
+import re
+import subprocess
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, a3_random_states, assert_close
+
+
+def test_library_exports_every_declared_symbol():
+    """The shared library loads and exports every function include/om_b200.h declares (no compute calls)."""
+    from olympics_mujoco_b200 import _lib
+    from olympics_mujoco_b200 import build
+    build.build(verbose=False)
+    header = (ROOT / "include" / "om_b200.h").read_text()
+    declared = set(re.findall(r"\b(om_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, f"declared but not exported: {missing}"
+    assert declared == set(_lib.PROTOTYPES), "ctypes prototypes out of sync with the header"
+    assert _lib.load().om_abi_version() == 1
+
+
+def test_compute_entry_points_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from olympics_mujoco_b200 import _lib, mjcf
+    from olympics_mujoco_b200 import kernels as Kn
+    with pytest.raises(_lib.OmError, match="no CUDA device"):
+        Kn.DeviceModel(mjcf.load_builtin("unitree_h1"))
+    with pytest.raises(_lib.OmError):
+        Kn.DeviceTrajectory(np.zeros((34, 1, 5)), 4)
+    with pytest.raises(_lib.OmError, match="CUDA tensor"):
+        Kn.h1_has_fallen(torch.zeros((4, 3)))
+
+
+def test_generated_fk_matches_oracle_on_host(h1_model, a3_model, h1_states):
+    """The code generator's output, compiled as plain C++ (fp32), agrees with the float64 oracle: checks the
+    generator in a container without a GPU.  The harness is test-only; the product has no CPU path."""
+    from olympics_mujoco_b200 import codegen
+    from oracle import kinematics as K
+    d = Path(tempfile.mkdtemp())
+    (d / "fk_unitree_h1.cuh").write_text(codegen.generate_fk(h1_model, "om_fk_unitree_h1"))
+    (d / "fk_stick_figure_a3.cuh").write_text(codegen.generate_fk(a3_model, "om_fk_stick_figure_a3"))
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-I", str(d), str(ROOT / "tests/host/fk_host_harness.cpp"),
+                           "-o", str(d / "h.so")])
+    lib = ctypes.CDLL(str(d / "h.so"))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for model, fn, (q, v) in ((h1_model, "host_fk_h1", h1_states),
+                              (a3_model, "host_fk_a3", a3_random_states(a3_model, 128, seed=8))):
+        n = q.shape[0]
+        q32, v32 = np.ascontiguousarray(q, np.float32), np.ascontiguousarray(v, np.float32)
+        xp = np.zeros((n, model.nbody, 3), np.float32); xq = np.zeros((n, model.nbody, 4), np.float32)
+        sp = np.zeros((n, model.nsite, 3), np.float32); sm = np.zeros((n, model.nsite, 3, 3), np.float32)
+        cv = np.zeros((n, model.nbody, 6), np.float32); cm = np.zeros((n, 3), np.float32)
+        getattr(lib, fn)(P(q32), P(v32), n, P(xp), P(xq), P(sp), P(sm), P(cv), P(cm))
+        ref = K.forward(model, q32.astype(np.float64), v32.astype(np.float64))
+        assert_close(xp, ref["xpos"], "xpos"); assert_close(xq, ref["xquat"], "xquat")
+        assert_close(sp, ref["site_xpos"], "site_xpos"); assert_close(sm, ref["site_xmat"], "site_xmat")
+        assert_close(cv, ref["cvel"], "cvel"); assert_close(cm, ref["subtree_com"][:, 1], "com")
+
+
+def test_mjcf_compiler_on_a_small_model(tmp_path):
+    from olympics_mujoco_b200 import mjcf
+    xml = """<mujoco model="toy"><compiler angle="radian" autolimits="true"/>
+      <default><default class="c"><joint damping="1"/><geom type="capsule" density="500"/></default></default>
+      <worldbody><body name="a" pos="0 0 1" childclass="c"><freejoint name="root"/>
+        <geom type="sphere" size="0.1"/>
+        <body name="b" pos="0.2 0 0" quat="2 0 0 0"><joint name="j1" axis="0 2 0" range="-1 1" pos="0 0 0.05"/>
+          <geom fromto="0 0 0 0 0 -0.4" size="0.05"/><site name="tip" pos="0 0 -0.4"/>
+          <body name="c" pos="0 0 -0.4"><joint name="j2" type="slide" axis="1 0 0"/><inertial pos="0 0 0.1" mass="2"/></body>
+        </body></body></worldbody>
+      <actuator><motor name="m1" joint="j1" gear="3"/></actuator></mujoco>"""
+    p = tmp_path / "toy.xml"
+    p.write_text(xml)
+    m = mjcf.compile_mjcf(p)
+    assert (m.nbody, m.njnt, m.nq, m.nv, m.nsite, m.nu) == (4, 3, 9, 8, 1, 1)
+    assert list(m.jnt_type) == [mjcf.JNT_FREE, mjcf.JNT_HINGE, mjcf.JNT_SLIDE]
+    assert_close(m.body_quat[2], [1, 0, 0, 0], "quat normalised", rtol=0, atol=1e-15)
+    assert_close(m.jnt_axis[1], [0, 1, 0], "axis normalised", rtol=0, atol=1e-15)
+    assert bool(m.jnt_limited[1]) and not bool(m.jnt_limited[2])
+    r, h = 0.05, 0.2
+    assert_close(m.body_mass[2], 500 * (np.pi * r * r * 2 * h + 4 / 3 * np.pi * r ** 3), "capsule mass", rtol=1e-12, atol=0)
+    assert_close(m.body_ipos[2], [0, 0, -0.2], "capsule com", rtol=0, atol=1e-15)
+    assert_close(m.body_mass[1], 500 * 4 / 3 * np.pi * 1e-3, "sphere mass (class density)", rtol=1e-12, atol=0)
+    assert_close(m.qpos0, [0, 0, 1, 1, 0, 0, 0, 0, 0], "qpos0", rtol=0, atol=0)
+    rt = mjcf.KinematicModel.from_dict(m.to_dict())
+    assert rt.body_names == m.body_names and np.array_equal(rt.jnt_range, m.jnt_range)
+    with pytest.raises(ValueError):
+        mjcf.compile_mjcf(p, remove_joints=["nope"])
+
+
+def test_trajectory_load_path_matches_reference_class():
+    """Range clipping, splitting and cubic re-sampling reproduce the reference's Trajectory bit for bit."""
+    from olympics_mujoco_b200 import mjcf
+    from olympics_mujoco_b200.utils.trajectory import Trajectory, resample_table
+    z = np.load(GOLDEN / "trajectory_ref.npz")
+    data = {k[3:]: z[k] for k in z.files if k.startswith("in_")}
+    model = mjcf.load_builtin("unitree_h1")
+    assert np.array_equal(resample_table(data, model), z["table"])
+    keys = [k for k in data if k != "split_points"]
+    tr = Trajectory(keys=keys, low=z["low"][2:], high=z["high"][2:], joint_pos_idx=np.arange(17), traj_files=dict(data),
+                    traj_dt=1 / 500, control_dt=1 / 100, clip_trajectory_to_joint_ranges=True, warn=False)
+    assert tr.trajectory_length == 50 and tr.number_of_trajectories == 3
+    assert np.array_equal(tr.split_points, z["split_points"])
+    ds = tr.create_dataset(ignore_keys=["q_pelvis_tx", "q_pelvis_tz"])
+    for k in ("states", "next_states", "absorbing", "last"):
+        assert np.array_equal(ds[k], z["ds_" + k])
+    # ragged input is rejected exactly like the reference (trajectory.py:207-224)
+    bad = dict(data)
+    bad["split_points"] = np.array([0, 100, 750])
+    with pytest.raises(AssertionError, match="equal length"):
+        Trajectory(keys=keys, low=z["low"][2:], high=z["high"][2:], joint_pos_idx=np.arange(17), traj_files=bad, warn=False)
+    with pytest.raises(AssertionError):
+        Trajectory(keys=keys, low=None, high=None, joint_pos_idx=np.arange(17))
+
+
+def test_env_name_grammar_and_registry():
+    import olympics_mujoco_b200 as om
+    assert "UnitreeH1" in om.LocoEnvBase.list_registered_loco_mujoco()
+    names = om.LocoEnvBase.get_all_task_names()
+    assert "UnitreeH1.walk.real" in names and "UnitreeH1.carry.perfect" not in names
+    with pytest.raises(ValueError, match="does not exit"):
+        om.LocoEnvBase.make("UnitreeH1.fly.real")
+    with pytest.raises(ValueError, match="does not exit"):
+        om.LocoEnvBase.make("UnitreeH1.walk.imaginary")
+    with pytest.raises(KeyError):
+        om.LocoEnvBase.make("Nope.walk")
+
+
+def test_synthetic_dataset_is_non_terminal(h1_model):
+    from olympics_mujoco_b200 import synthetic
+    from oracle import h1 as OH
+    d = synthetic.h1_walk_dataset(n_traj=2, t_raw=500, seed=11, model=h1_model)
+    keys = OH.keys(h1_model)
+    assert [k for k in d if k != "split_points"] == keys
+    obs = np.stack([d[k] for k in keys], axis=1)[:, 2:]
+    assert not OH.has_fallen(obs).any()
+    for i, j in enumerate(OH.spec_joints(h1_model)):
+        jid = h1_model.jnt_names.index(j)
+        if h1_model.jnt_limited[jid]:
+            lo, hi = h1_model.jnt_range[jid]
+            assert d["q_" + j].min() >= lo and d["q_" + j].max() <= hi
