@@ -142,7 +142,7 @@ def run_ours(args):
             ev_k1[i].record()
         vt, adv = Kn.gae(out["reward"], vals[:-1], vals[1:], out["fallen"], last, GAMMA, LAM)
         mom.zero_()
-        Kn.moments(adv, out=mom[:3])
+        Kn.moments_scalar(adv, out=mom[:3])
         Kn.moments(out["obs"], out=mom[3:])
         if world > 1:
             dist.all_reduce(mom)                               # the path's only exchange (520 B + 24 B, float64)

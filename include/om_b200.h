@@ -161,7 +161,7 @@ typedef struct OmPlayOut {
   uint8_t* fallen; int32_t* traj_no_t; int32_t* step_no_t;
 } OmPlayOut;
 int om_h1_play_from_velocity(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, uint64_t seed,
-                             uint32_t env_id0, float dt, int n_steps, int end_episode_reset,
+                             uint32_t env_id0, double dt, int n_steps, int end_episode_reset,
                              const OmPlayState* state, const OmPlayOut* out, int n, int ld, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -63,7 +63,7 @@ PROTOTYPES = {
     "om_traj_reset": (_I, [_P, _U64, _U32, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "om_traj_current": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "om_traj_next": (_I, [_P, _U64, _U32, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
-    "om_h1_play_from_velocity": (_I, [_P, C.POINTER(OmH1Spec), _P, _U64, _U32, _F, _I, _I,
+    "om_h1_play_from_velocity": (_I, [_P, C.POINTER(OmH1Spec), _P, _U64, _U32, _D, _I, _I,
                                       C.POINTER(OmPlayState), C.POINTER(OmPlayOut), _I, _I, _P]),
     "om_ppo_returns": (_I, [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P]),
     "om_gae": (_I, [_P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P, _P]),

@@ -1,4 +1,6 @@
 // K5 (returns / GAE reverse scans over a time-major rollout buffer) and K6 (moment partial sums).
+#include <cstdlib>
+
 #include "om_common.cuh"
 
 namespace om {
@@ -87,13 +89,97 @@ __global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rewa
   }
 }
 
+// ---------------------------------------------------------------- K5, scan flavour (T <= 32 * L)
+// Both recurrences are affine: X_t = a_t * X_{t+1} + b_t.  One CTA owns 32 envs (lanes) x all T steps: warp w
+// holds time segment [w*L, (w+1)*L) in registers, composes it into (A, B) with X_first = A * X_in + B, the
+// 32 segment summaries are exchanged through shared memory, every warp folds the summaries of the LATER
+// segments into its carry-in and then emits its L outputs.  Every global access is a 128-byte row segment.
+// This is the "warp-scan over the rollout buffer" of the north star, laid out so that lanes stay on the
+// contiguous env axis; it makes a 4096-env x 500-step buffer 131072 threads instead of 4096.
+struct AffineIn {
+  // GAE: rewards, v, v_next, absorbing, last.  Returns: rewards, values, path_end, v_next, v_last.
+  const float* r; const float* v; const float* vn; const uint8_t* f0; const uint8_t* f1; const float* v_last;
+  float gamma, gl;
+  int mode;   // 0 = GAE, 1 = PPO returns
+};
+
+template <int L>
+__global__ void __launch_bounds__(1024) affine_scan_kernel(AffineIn in, int T, int n, int ld, float* __restrict__ out0,
+                                                           float* __restrict__ out1) {
+  __shared__ float sA[32][33], sB[32][33];
+  const int lane = threadIdx.x, w = threadIdx.y;
+  const int env = blockIdx.x * 32 + lane;
+  const bool live = env < n;
+  const int t0 = w * L;
+  float a[L], b[L], vv[L];
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    const int t = t0 + i;
+    a[i] = 1.f; b[i] = 0.f; vv[i] = 0.f;          // identity for t >= T
+    if (live && t < T) {
+      const size_t idx = (size_t)t * ld + env;
+      const float r = in.r[idx];
+      const bool endbuf = t == T - 1;
+      if (in.mode == 0) {
+        const float v = in.v[idx], vn = in.vn[idx];
+        const bool ab = in.f0 && in.f0[idx], la = (in.f1 && in.f1[idx]) || endbuf;
+        const float boot = (la && ab) ? 0.f : in.gamma * vn;
+        a[i] = la ? 0.f : in.gl;
+        b[i] = (r - v) + boot;
+        vv[i] = v;
+      } else {
+        const uint8_t e = in.f0 ? in.f0[idx] : 0;
+        vv[i] = in.v ? in.v[idx] : 0.f;
+        // R_t = gamma * Rin + r, where Rin is the bootstrap when a path ends at t
+        if (endbuf) {
+          const float boot = (e == 1) ? 0.f : ((e == 2 && in.vn) ? in.vn[idx] : (in.v_last ? in.v_last[env] : 0.f));
+          a[i] = 0.f; b[i] = fmaf(in.gamma, boot, r);
+        } else if (e == 1) { a[i] = 0.f; b[i] = r; }
+        else if (e == 2) { a[i] = 0.f; b[i] = fmaf(in.gamma, in.vn ? in.vn[idx] : 0.f, r); }
+        else { a[i] = in.gamma; b[i] = r; }
+      }
+    }
+  }
+  // compose the segment from its last element backwards: X_{t0} = A * X_in + B
+  float A = 1.f, B = 0.f;
+#pragma unroll
+  for (int i = L - 1; i >= 0; --i) { B = fmaf(a[i], B, b[i]); A = a[i] * A; }
+  sA[w][lane] = A; sB[w][lane] = B;
+  __syncthreads();
+  // carry-in of this segment = value at the first step of segment w+1 = fold of segments 31 .. w+1
+  float X = 0.f;
+  for (int s = 31; s > w; --s) X = fmaf(sA[s][lane], X, sB[s][lane]);
+#pragma unroll
+  for (int i = L - 1; i >= 0; --i) {
+    X = fmaf(a[i], X, b[i]);
+    const int t = t0 + i;
+    if (live && t < T) {
+      const size_t idx = (size_t)t * ld + env;
+      if (in.mode == 0) { if (out0) out0[idx] = X; if (out1) out1[idx] = X + vv[i]; }
+      else { if (out0) out0[idx] = X; if (out1) out1[idx] = X - vv[i]; }
+    }
+  }
+}
+
+static int launch_affine_scan(const AffineIn& in, int T, int n, int ld, float* o0, float* o1, cudaStream_t st) {
+  dim3 block(32, 32), grid(ceil_div(n, 32));
+  const int L = ceil_div(T, 32);
+  if (L <= 1) affine_scan_kernel<1><<<grid, block, 0, st>>>(in, T, n, ld, o0, o1);
+  else if (L <= 2) affine_scan_kernel<2><<<grid, block, 0, st>>>(in, T, n, ld, o0, o1);
+  else if (L <= 4) affine_scan_kernel<4><<<grid, block, 0, st>>>(in, T, n, ld, o0, o1);
+  else if (L <= 8) affine_scan_kernel<8><<<grid, block, 0, st>>>(in, T, n, ld, o0, o1);
+  else if (L <= 16) affine_scan_kernel<16><<<grid, block, 0, st>>>(in, T, n, ld, o0, o1);
+  else affine_scan_kernel<32><<<grid, block, 0, st>>>(in, T, n, ld, o0, o1);
+  return 0;
+}
+
 // ---------------------------------------------------------------- K6: moment partial sums
 // grid = (env chunks, C).  float64 accumulation: per-thread -> warp shuffle -> one atomicAdd per warp.
 __global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ x, int rows, int C, int n, int ld,
                                                       double* __restrict__ out) {
   const int c = blockIdx.y;
   double s = 0.0, s2 = 0.0;
-  for (int r = 0; r < rows; ++r) {
+  for (int r = blockIdx.z; r < rows; r += gridDim.z) {
     const float* row = x + ((size_t)r * C + c) * ld;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
       const double v = row[i];
@@ -110,7 +196,7 @@ __global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ 
     atomicAdd(out + c, s);
     atomicAdd(out + C + c, s2);
   }
-  if (c == 0 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(out + 2 * C, (double)rows * (double)n);
+  if (c == 0 && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 0) atomicAdd(out + 2 * C, (double)rows * (double)n);
 }
 
 // mean / (std + eps) of a single-component moment buffer [sum, sumsq, count] -> stats[0..1]
@@ -145,8 +231,13 @@ extern "C" int om_ppo_returns(const float* rewards, const float* values, const u
   if (T == 0 || n == 0) return 0;
   OM_REQUIRE(rewards && (ret || adv), "om_ppo_returns: null argument");
   OM_REQUIRE(!adv || values, "om_ppo_returns: advantages need values");
-  ppo_returns_kernel<8><<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(rewards, values, path_end, v_next, v_last, gamma,
-                                                                             T, n, ld, ret, adv);
+  if (T <= 1024 && T >= 8 && (long long)n < 148LL * 2048 && !getenv("OM_SERIAL_SCAN")) {
+    AffineIn in{rewards, values, v_next, path_end, nullptr, v_last, gamma, 0.f, 1};
+    launch_affine_scan(in, T, n, ld, ret, adv, (cudaStream_t)stream);
+  } else {
+    ppo_returns_kernel<8><<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(rewards, values, path_end, v_next, v_last,
+                                                                               gamma, T, n, ld, ret, adv);
+  }
   OM_LAUNCHED();
   return 0;
 }
@@ -157,8 +248,13 @@ extern "C" int om_gae(const float* rewards, const float* v, const float* v_next,
   OM_REQUIRE(T >= 0 && n >= 0 && ld >= n, "om_gae: bad sizes");
   if (T == 0 || n == 0) return 0;
   OM_REQUIRE(rewards && v && v_next && (adv || v_target), "om_gae: null argument");
-  gae_kernel<8><<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(rewards, v, v_next, absorbing, last, gamma, lam, T, n, ld,
-                                                                     adv, v_target);
+  if (T <= 1024 && T >= 8 && (long long)n < 148LL * 2048 && !getenv("OM_SERIAL_SCAN")) {
+    AffineIn in{rewards, v, v_next, absorbing, last, nullptr, gamma, gamma * lam, 0};
+    launch_affine_scan(in, T, n, ld, adv, v_target, (cudaStream_t)stream);
+  } else {
+    gae_kernel<8><<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(rewards, v, v_next, absorbing, last, gamma, lam, T, n,
+                                                                       ld, adv, v_target);
+  }
   OM_LAUNCHED();
   return 0;
 }
@@ -170,7 +266,12 @@ extern "C" int om_moments(const float* x, int rows, int C, int n, int ld, double
   int gx = ceil_div(n, 256 * 4);
   if (gx < 1) gx = 1;
   if (gx > 1184) gx = 1184;
-  dim3 grid(gx, C);
+  // split the rows over grid.z until the launch has ~8 CTAs per SM
+  int gz = 1184 / (gx * C);
+  if (gz < 1) gz = 1;
+  if (gz > rows) gz = rows;
+  if (gz > 65535) gz = 65535;
+  dim3 grid(gx, C, gz);
   moments_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, C, n, ld, out);
   OM_LAUNCHED();
   return 0;

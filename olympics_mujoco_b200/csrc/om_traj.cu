@@ -1,4 +1,5 @@
 // K3: reference-trajectory table + per-env integer state, and the fused H1 playback kernel.
+#include <cstdlib>
 #include <vector>
 
 #include "om_common.cuh"
@@ -77,9 +78,11 @@ struct PlayArgs {
   TrajDev t;
   uint64_t seed;
   uint32_t env_id0;
-  float dt, target;
+  double dt;
+  float target;
   int use_absorbing, n_steps, end_reset, n, ld;
-  OmPlayState s;
+  OmPlayState s;      // live carried state (written by the thread that runs the last step)
+  OmPlayState snap;   // episode-start snapshot read by every chunk of the time-parallel kernel
   OmPlayOut o;
 };
 
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(BLOCK) play_h1_seq_kernel(PlayArgs a) {
   bool have_samp = false;
   for (int s = 0; s < a.n_steps; ++s) {
 #pragma unroll
-    for (int k = 0; k < 17; ++k) cq[k] = fma((double)a.dt, (double)dq[k], cq[k]);   // :515-519
+    for (int k = 0; k < 17; ++k) cq[k] = fma(a.dt, (double)dq[k], cq[k]);   // :515-519
     play_fk(cq, dq, a.o, (size_t)s, ld, e);                                          // :521-525
     ++st;                                                                            // :532
     const bool wrap = st >= a.t.T;
@@ -192,6 +195,132 @@ __global__ void __launch_bounds__(BLOCK) play_h1_seq_kernel(PlayArgs a) {
   a.s.prev_x_vel[e] = pxv;
 }
 
+// ---------------------------------------------------------------- fused playback, time-parallel
+__global__ void __launch_bounds__(256) play_snapshot_kernel(OmPlayState live, OmPlayState snap, int n, int ld) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  snap.traj_no[e] = live.traj_no[e];
+  snap.step_no[e] = live.step_no[e];
+  snap.reset_count[e] = live.reset_count[e];
+  snap.xy_off[e] = live.xy_off[e];
+  snap.xy_off[(size_t)ld + e] = live.xy_off[(size_t)ld + e];
+  snap.prev_x_vel[e] = live.prev_x_vel[e];
+  for (int k = 0; k < 17; ++k) {
+    snap.curr_qpos[(size_t)k * ld + e] = live.curr_qpos[(size_t)k * ld + e];
+    snap.pending[(size_t)(17 + k) * ld + e] = live.pending[(size_t)(17 + k) * ld + e];
+  }
+}
+
+// The per-env recurrences of the playback loop are (a) the integer trajectory index, which only changes
+// non-trivially at wrap resets whose draws depend on (seed, env, reset_count) alone, and (b) the Euler sum
+// q_j = q_0 + dt * sum(dq), which telescopes through the float64 prefix table cdq.  A thread can therefore
+// reconstruct the loop state in front of ANY step j0 in O(#resets) and then walk `chunk` steps exactly like
+// the sequential kernel.  grid = (env tiles, time chunks): 4096 envs x 500 steps become ~300k threads
+// instead of 4096, which is what lets a 4096-env rollout fill the 148 SMs.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) play_h1_tp_kernel(PlayArgs a, int chunk) {
+  const int env = blockIdx.x * BLOCK + threadIdx.x;
+  if (env >= a.n) return;
+  const int j0 = blockIdx.y * chunk, j1 = min(j0 + chunk, a.n_steps);
+  const size_t ld = a.ld, e = env;
+  const int T = a.t.T;
+  int tr = a.snap.traj_no[e], st = a.snap.step_no[e];
+  uint32_t rc = a.snap.reset_count[e];
+  // ---- replay the wrap resets that happen before step j0
+  int seg_start = 0;
+  bool first = true;
+  while (seg_start + (T - st) <= j0) {
+    seg_start += T - st;
+    traj_draw(a.t, a.seed, a.env_id0 + env, rc, tr, st);
+    ++rc;
+    first = false;
+  }
+  const int m = j0 - seg_start;                  // steps already taken inside this segment
+  double ox, oy;
+  double cq[17];
+  float dq[17];
+  float pxv;
+  float samp[36];
+  const double* c_hi = a.t.cdq + ((size_t)tr * (T + 1) + st + m) * 17;
+  if (first) {
+    ox = a.snap.xy_off[e]; oy = a.snap.xy_off[ld + e];
+    const double* c_lo = a.t.cdq + ((size_t)tr * (T + 1) + st + 1) * 17;
+#pragma unroll
+    for (int k = 0; k < 17; ++k) {
+      const double q0 = a.snap.curr_qpos[k * ld + e];
+      const float p0 = a.snap.pending[(17 + k) * ld + e];
+      cq[k] = (m == 0) ? q0 : fma(a.dt, (double)p0 + (c_hi[k] - c_lo[k]), q0);
+      dq[k] = p0;
+    }
+    pxv = a.snap.prev_x_vel[e];
+  } else {
+    ox = a.t.xy[((size_t)tr * T + st) * 2];
+    oy = a.t.xy[((size_t)tr * T + st) * 2 + 1];
+    traj_load_row(a.t, tr, st, samp);
+    const double* c_lo = a.t.cdq + ((size_t)tr * (T + 1) + st) * 17;
+    cq[0] = fma(a.dt, c_hi[0] - c_lo[0], 0.0);
+    cq[1] = fma(a.dt, c_hi[1] - c_lo[1], 0.0);
+#pragma unroll
+    for (int k = 2; k < 17; ++k) cq[k] = fma(a.dt, c_hi[k] - c_lo[k], (double)samp[k]);
+  }
+  st += m;
+  if (!first || m > 0) {                         // the pending sample is row (tr, st)
+    traj_load_row(a.t, tr, st, samp);
+#pragma unroll
+    for (int k = 0; k < 17; ++k) dq[k] = samp[17 + k];
+    pxv = samp[17];
+  }
+  // ---- walk the chunk (identical to the sequential kernel's loop body)
+  for (int s = j0; s < j1; ++s) {
+#pragma unroll
+    for (int k = 0; k < 17; ++k) cq[k] = fma(a.dt, (double)dq[k], cq[k]);
+    play_fk(cq, dq, a.o, (size_t)s, ld, e);
+    ++st;
+    const bool wrap = st >= T;
+    if (wrap) {
+      traj_draw(a.t, a.seed, a.env_id0 + env, rc, tr, st);
+      ++rc;
+      ox = a.t.xy[((size_t)tr * T + st) * 2];
+      oy = a.t.xy[((size_t)tr * T + st) * 2 + 1];
+    }
+    traj_load_row(a.t, tr, st, samp);
+    if (wrap) {
+      cq[0] = 0.0; cq[1] = 0.0;
+#pragma unroll
+      for (int k = 2; k < 17; ++k) cq[k] = samp[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 17; ++k) dq[k] = samp[17 + k];
+    play_emit(samp, pxv, a, (size_t)s, e, tr, st);
+    pxv = samp[17];
+  }
+  if (j1 != a.n_steps) return;
+  // ---- the thread that ran the last step owns the carried state
+  a.s.pending[e] = (float)(a.t.xy[((size_t)tr * T + st) * 2] - ox);
+  a.s.pending[ld + e] = (float)(a.t.xy[((size_t)tr * T + st) * 2 + 1] - oy);
+#pragma unroll
+  for (int k = 2; k < 34; ++k) a.s.pending[k * ld + e] = samp[k];
+  if (a.end_reset) {
+    traj_draw(a.t, a.seed, a.env_id0 + env, rc, tr, st);
+    ++rc;
+    ox = a.t.xy[((size_t)tr * T + st) * 2];
+    oy = a.t.xy[((size_t)tr * T + st) * 2 + 1];
+    traj_load_row(a.t, tr, st, samp);
+    cq[0] = 0.0; cq[1] = 0.0;
+#pragma unroll
+    for (int k = 2; k < 17; ++k) cq[k] = samp[k];
+    pxv = samp[17];
+  }
+  a.s.traj_no[e] = tr;
+  a.s.step_no[e] = st;
+  a.s.reset_count[e] = rc;
+  a.s.xy_off[e] = ox;
+  a.s.xy_off[ld + e] = oy;
+#pragma unroll
+  for (int k = 0; k < 17; ++k) a.s.curr_qpos[k * ld + e] = cq[k];
+  a.s.prev_x_vel[e] = pxv;
+}
+
 }  // namespace om
 
 using namespace om;
@@ -213,22 +342,35 @@ extern "C" int om_traj_create(const double* table, int K, int n_traj, int T, OmT
         rows[((size_t)tr * T + s) * kpad + k] = (float)v;
         if (k < 2) xy[((size_t)tr * T + s) * 2 + k] = v;
       }
+  // exclusive prefix sums of the (fp32-rounded, as stored) velocity channels, accumulated in float64
+  const int nq = K / 2;
+  std::vector<double> cdq((size_t)n_traj * (T + 1) * nq, 0.0);
+  for (int tr = 0; tr < n_traj; ++tr)
+    for (int s = 0; s < T; ++s)
+      for (int k = 0; k < nq; ++k)
+        cdq[((size_t)tr * (T + 1) + s + 1) * nq + k] =
+            cdq[((size_t)tr * (T + 1) + s) * nq + k] + (double)rows[((size_t)tr * T + s) * kpad + nq + k];
   OmTraj* t = new OmTraj();
   t->d.K = K; t->d.kpad = kpad; t->d.n_traj = n_traj; t->d.T = T;
   float* drows = nullptr;
   double* dxy = nullptr;
+  double* dcdq = nullptr;
   cudaError_t e = cudaMalloc(&drows, rows.size() * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&dxy, xy.size() * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dcdq, cdq.size() * sizeof(double));
   if (e == cudaSuccess) e = cudaMemcpy(drows, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(dxy, xy.data(), xy.size() * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dcdq, cdq.data(), cdq.size() * sizeof(double), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     if (drows) cudaFree(drows);
     if (dxy) cudaFree(dxy);
+    if (dcdq) cudaFree(dcdq);
     delete t;
     return fail("om_traj_create: device upload failed: %s (no CPU path)", cudaGetErrorString(e));
   }
   t->d.rows = drows;
   t->d.xy = dxy;
+  t->d.cdq = dcdq;
   *out = t;
   return 0;
 }
@@ -237,6 +379,7 @@ extern "C" void om_traj_destroy(OmTraj* t) {
   if (!t) return;
   cudaFree((void*)t->d.rows);
   cudaFree((void*)t->d.xy);
+  cudaFree((void*)t->d.cdq);
   delete t;
 }
 
@@ -278,7 +421,7 @@ extern "C" int om_traj_next(const OmTraj* t, uint64_t seed, uint32_t env_id0, in
 }
 
 extern "C" int om_h1_play_from_velocity(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, uint64_t seed,
-                                        uint32_t env_id0, float dt, int n_steps, int end_episode_reset,
+                                        uint32_t env_id0, double dt, int n_steps, int end_episode_reset,
                                         const OmPlayState* state, const OmPlayOut* out, int n, int ld, void* stream) {
   OM_REQUIRE(m && spec && t && state && out, "om_h1_play_from_velocity: null argument");
   OM_REQUIRE(n >= 0 && ld >= n && n_steps >= 0, "om_h1_play_from_velocity: bad sizes");
@@ -292,9 +435,40 @@ extern "C" int om_h1_play_from_velocity(const OmModel* m, const OmH1Spec* spec, 
   PlayArgs a;
   a.t = t->d; a.seed = seed; a.env_id0 = env_id0; a.dt = dt; a.target = spec->target_velocity;
   a.use_absorbing = spec->use_absorbing_states; a.n_steps = n_steps; a.end_reset = end_episode_reset;
-  a.n = n; a.ld = ld; a.s = *state; a.o = *out;
+  a.n = n; a.ld = ld; a.s = *state; a.snap = *state; a.o = *out;
   constexpr int BLOCK = 128;
-  play_h1_seq_kernel<BLOCK><<<ceil_div(n, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(a);
+  // time-parallel when the env count alone cannot fill the machine (148 SMs x 2048 threads)
+  const long long target_threads = 148LL * 2048;
+  const long long chunks_wanted = target_threads / n > 0 ? target_threads / n : 1;
+  int chunk = ceil_div(n_steps, chunks_wanted);
+  if (const char* f = getenv("OM_PLAY_CHUNK")) chunk = atoi(f);     // tuning / test hook
+  if (chunk < 1) chunk = 1;
+  if (chunk >= n_steps || state->curr_qpos == nullptr) {
+    play_h1_seq_kernel<BLOCK><<<ceil_div(n, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(a);
+  } else {
+    // the carried state is read by every chunk and overwritten by the last one: snapshot the episode-start
+    // state (stream-ordered scratch) so that no thread can observe another's end-of-episode write
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t L = (size_t)ld;
+    const size_t bytes = L * (4 + 4 + 4 + 16 + 4 + 17 * 8 + 34 * 4) + 256;
+    char* scratch = nullptr;
+    OM_CUDA_OK(cudaMallocAsync((void**)&scratch, bytes, st));
+    char* p = scratch;
+    a.snap.curr_qpos = (double*)p; p += L * 17 * 8;
+    a.snap.xy_off = (double*)p; p += L * 16;
+    a.snap.pending = (float*)p; p += L * 34 * 4;
+    a.snap.prev_x_vel = (float*)p; p += L * 4;
+    a.snap.traj_no = (int32_t*)p; p += L * 4;
+    a.snap.step_no = (int32_t*)p; p += L * 4;
+    a.snap.reset_count = (uint32_t*)p;
+    play_snapshot_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a.s, a.snap, n, ld);
+    OM_LAUNCHED();
+    dim3 grid(ceil_div(n, BLOCK), ceil_div(n_steps, chunk));
+    play_h1_tp_kernel<BLOCK><<<grid, BLOCK, 0, st>>>(a, chunk);
+    OM_LAUNCHED();
+    OM_CUDA_OK(cudaFreeAsync(scratch, st));
+    return 0;
+  }
   OM_LAUNCHED();
   return 0;
 }

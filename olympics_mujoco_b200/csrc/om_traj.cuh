@@ -7,6 +7,8 @@ namespace om {
 struct TrajDev {
   const float* rows;   // [n_traj][T][kpad] sample-major rows (one 16-byte aligned row per sample)
   const double* xy;    // [n_traj][T][2]   channels 0,1 (root x, y) in float64
+  const double* cdq;   // [n_traj][T+1][K/2] exclusive prefix sums of the velocity channels (float64):
+                       //   cdq[tr][i][k] = sum_{j<i} rows[tr][j][K/2+k]  (time-parallel playback)
   int K, kpad, n_traj, T;
 };
 

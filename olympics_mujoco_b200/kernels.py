@@ -253,8 +253,18 @@ def moments(x, out=None):
     rows, c, n = x.shape
     if out is None:
         out = torch.zeros(2 * c + 1, dtype=torch.float64, device=x.device)
+    if out.numel() != 2 * c + 1:
+        raise ValueError(f"moments of {c} components need a {2 * c + 1}-element output, got {out.numel()}")
     check(_lib.load().om_moments(_p(x, torch.float32), rows, c, n, max(n, 1), _p(out, torch.float64), _stream()))
     return out
+
+
+def moments_scalar(x, out=None):
+    """K6 for a single-component buffer ([n] or [T, n], e.g. advantages) -> float64 [3] = (sum, sumsq, count)."""
+    x3 = x.reshape(1, 1, -1) if x.dim() == 1 else x.unsqueeze(1)
+    if out is not None and out.numel() != 3:
+        raise ValueError("moments_scalar needs a 3-element output")
+    return moments(x3, out=out)
 
 
 def adv_stats(mom, unbiased, eps):

@@ -122,9 +122,11 @@ def test_trajectory_state_machine():
     assert np.all(st[::3] == 17) and np.array_equal(st[1::3], before.cpu().numpy()[1::3])
 
 
+@pytest.mark.parametrize("chunk", ["1", "7", "100000"])      # time-parallel x2, sequential-in-time kernel
 @pytest.mark.parametrize("n_episodes,n_steps", [(1, 120), (3, 37)])
-def test_play_trajectory_from_velocity_parity(h1_model, n_episodes, n_steps):
+def test_play_trajectory_from_velocity_parity(h1_model, n_episodes, n_steps, chunk, monkeypatch):
     import torch
+    monkeypatch.setenv("OM_PLAY_CHUNK", chunk)
     from olympics_mujoco_b200 import kernels as Kn
     from oracle import h1 as OH
     tab = _table()

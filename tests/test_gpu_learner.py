@@ -25,7 +25,7 @@ def test_ppo_returns_vs_reference_buffer():
     ret, adv = Kn.ppo_returns(_cu(r), _cu(v), float(z["gamma"]), v_last=_cu(v_last, torch.float32))
     assert_close(ret.cpu().numpy(), z["returns"], "returns vs PPOBuffer.finish_path")
     # advantage normalisation ppo.py:335-336 (torch.std unbiased, eps 1e-5)
-    mom = Kn.moments(adv)
+    mom = Kn.moments_scalar(adv)
     stats = Kn.adv_stats(mom, unbiased=True, eps=1e-5)
     an = Kn.normalize(adv, stats)
     assert_close(an.cpu().numpy(), z["adv_norm"], "normalised advantages", rtol=2e-5, atol=2e-5)
@@ -35,9 +35,12 @@ def test_ppo_returns_vs_reference_buffer():
     assert_close(kat.cpu().numpy()[:, 0], [15.62329, 14.771, 12.9], "KAT")
 
 
-@pytest.mark.parametrize("T,n", [(64, 1000), (1, 5), (37, 1)])
-def test_ppo_returns_segmented(T, n):
+@pytest.mark.parametrize("serial", [False, True])
+@pytest.mark.parametrize("T,n", [(64, 1000), (1, 5), (37, 1), (500, 45)])
+def test_ppo_returns_segmented(T, n, serial, monkeypatch):
     from olympics_mujoco_b200 import kernels as Kn
+    if serial:
+        monkeypatch.setenv("OM_SERIAL_SCAN", "1")
     from oracle import learner as L
     rng = np.random.default_rng(T + n)
     r = rng.normal(0, 1, (T, n)).astype(np.float32)
@@ -51,9 +54,12 @@ def test_ppo_returns_segmented(T, n):
     assert_close(adv.cpu().numpy(), ref_adv, "advantages")
 
 
-@pytest.mark.parametrize("T,n", [(64, 513), (1000, 3), (1, 1)])
-def test_gae_vs_mushroom_restatement(T, n):
+@pytest.mark.parametrize("serial", [False, True])                 # affine-scan kernel / one-thread-per-env kernel
+@pytest.mark.parametrize("T,n", [(64, 513), (1000, 3), (500, 70), (1, 1), (1500, 33)])
+def test_gae_vs_mushroom_restatement(T, n, serial, monkeypatch):
     from olympics_mujoco_b200 import kernels as Kn
+    if serial:
+        monkeypatch.setenv("OM_SERIAL_SCAN", "1")
     from oracle import learner as L
     rng = np.random.default_rng(T * 7 + n)
     r = rng.normal(0, 1, (T, n)).astype(np.float32)
@@ -62,14 +68,14 @@ def test_gae_vs_mushroom_restatement(T, n):
     last = rng.random((T, n)) < 0.05
     absorbing = last & (rng.random((T, n)) < 0.5)
     vt, adv = Kn.gae(_cu(r), _cu(v), _cu(vn), _cu(absorbing.astype(np.uint8)), _cu(last.astype(np.uint8)), 0.99, 0.97)
-    ref_vt, ref_adv = L.compute_gae_batched(r, v, vn, absorbing, last, 0.99, 0.97)
+    ref_vt, ref_adv = L.compute_gae_batched(v, vn, r, absorbing, last, 0.99, 0.97)
     assert_close(adv.cpu().numpy(), ref_adv, "adv")
     assert_close(vt.cpu().numpy(), ref_vt, "v_target")
     # flat (single-env dataset) form of compute_gae, column 0
     f_vt, f_adv = L.compute_gae(v[:, 0], vn[:, 0], r[:, 0], absorbing[:, 0], last[:, 0], 0.99, 0.97)
     assert_close(adv.cpu().numpy()[:, 0], f_adv, "adv flat")
     # gail_TRPO.py:128 normalisation (np.std population, eps 1e-8)
-    stats = Kn.adv_stats(Kn.moments(adv), unbiased=False, eps=1e-8)
+    stats = Kn.adv_stats(Kn.moments_scalar(adv), unbiased=False, eps=1e-8)
     an = Kn.normalize(adv, stats).cpu().numpy()
     assert_close(an, L.normalize_advantage_gail(adv.cpu().numpy()), "normalised adv", rtol=2e-5, atol=2e-5)
 
