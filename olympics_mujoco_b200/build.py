@@ -51,6 +51,13 @@ def generate():
            f"__device__ constexpr int OM_H1_PERM[17] = {{{', '.join(map(str, perm))}}};\n"
            f"static const int OM_H1_PERM_HOST[17] = {{{', '.join(map(str, perm))}}};\n")
     _write_if_changed(GEN / "h1_perm.h", txt)
+    ids = dict(ROOT=a3.body_id("torso"), HEAD=a3.body_id("head"), LFOOT=a3.body_id("left_foot"),
+               RFOOT=a3.body_id("right_foot"), LSITE=a3.site_id("lf_force"), RSITE=a3.site_id("rf_force"))
+    txt = ("#pragma once\n// GENERATED: body / site ids the WalkingTask reads (StickFigureA3.py:95-103, "
+           "walking_task.py:254-263) and the model's total mass (mj_getTotalmass)\n" +
+           "".join(f"constexpr int OM_A3_{k} = {v};\n" for k, v in ids.items()) +
+           f"constexpr float OM_A3_TOTAL_MASS = {codegen._f(a3.total_mass)};\n")
+    _write_if_changed(GEN / "a3_ids.h", txt)
 
 
 def sources():
