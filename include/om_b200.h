@@ -165,6 +165,53 @@ int om_h1_play_from_velocity(const OmModel* m, const OmH1Spec* spec, const OmTra
                              const OmPlayState* state, const OmPlayOut* out, int n, int ld, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K2 (A3 flavour): the tail of StickFigureA3.step (real_humanoid_robots/StickFigureA3.py:187-202) after
+ * robot.step (= mj_step, which stays the reference's): WalkingTask.step (tasks/walking_task.py:246-293),
+ * calc_reward (:74-110; terms tasks/rewards.py:27-40,65-83,85-102,121-126), done (:298-319) and get_obs
+ * (StickFigureA3.py:144-178), with K1 fused in (the MjData fields are only written when asked for).
+ * What the task reads from the contact solver enters as contact [4][ld]: left-foot GRF, right-foot GRF
+ * (mujoco_robot_interface.py:275-297), min z of the foot-floor contact points (rewards.py:29-31), flags
+ * (float-coded bits: 1 = any foot-floor contact, 2 = check_bad_collisions :393-399). */
+typedef struct OmA3TaskDesc {
+  int period;                    /* floor(2 * total_duration / control_dt) = 88 (walking_task.py:351) */
+  int delay_frames;              /* floor(swing_duration / control_dt) = 30 (:336) */
+  double target_radius;          /* 0.20 (:333) */
+  double goal_height_ref;        /* 0.80 (StickFigureA3.py:110) */
+  double goal_speed_ref;         /* 0 (walking_task.py:30) */
+  double total_mass;             /* mj_getTotalmass */
+  const double* clock_lut_host;  /* [period][4]: right/left foot force and velocity clocks evaluated at the integer
+                                    phases (rewards.py:270-366), columns r_frc, r_vel, l_frc, l_vel */
+  const double* init_qpos_host;  /* [25] nominal pose (environments/robot.py:61-80) */
+} OmA3TaskDesc;
+typedef struct OmA3Task OmA3Task;
+int om_a3_task_create(const OmA3TaskDesc* desc, OmA3Task** out);
+void om_a3_task_destroy(OmA3Task* t);
+
+/* Per-env WalkingTask state.  ints [7][ld]: phase, t1, t2, target_reached_frames, mode (0 STANDING, 1 FORWARD),
+ * len(sequence), target_reached.  sequence [20*4][ld]: footstep plan rows (x, y, z, theta), component
+ * step*4 + c. */
+typedef struct OmA3State { int32_t* ints; float* sequence; } OmA3State;
+/* Outputs (any may be NULL), time-major over the n_steps of the call: obs [41], terms [6] (the weighted reward
+ * terms in the reference's dict order), reward (their sum), done (uint8); MjData fields xpos [17*3],
+ * xquat [17*4], site_xpos [2*3], site_xmat [2*9], cvel [17*6]. */
+typedef struct OmA3Out {
+  float* obs; float* terms; float* reward; uint8_t* done;
+  float* xpos; float* xquat; float* site_xpos; float* site_xmat; float* cvel;
+} OmA3Out;
+/* n_steps == 1: one StickFigureA3.step tail on the post-physics state qpos [25][ld], qvel [24][ld].
+ * n_steps > 1: replay of n_steps recorded post-physics states (qpos [n_steps][25][ld], ...), the task state
+ * carried from step to step in registers. */
+int om_a3_task_step(const OmModel* m, const OmA3Task* task, const float* qpos, const float* qvel, const float* contact,
+                    int n_steps, const OmA3State* state, const OmA3Out* out, int n, int ld, void* stream);
+/* StickFigureA3.reset_model (StickFigureA3.py:205-235) + WalkingTask.reset (walking_task.py:321-397) for the envs
+ * selected by mask (NULL = all).  Draws follow the Philox contract: key = seed, counter = (env_id0 + i,
+ * reset_count[i], 16 + block, 0), 15 blocks = 60 uniforms in the order documented in oracle/a3.py.
+ * Writes qpos, qvel, the task state and (optionally) the first observation; reset_count[i] += 1. */
+int om_a3_reset(const OmModel* m, const OmA3Task* task, uint64_t seed, uint32_t env_id0, const uint8_t* mask,
+                uint32_t* reset_count, double iteration_count, float* qpos, float* qvel, const OmA3State* state,
+                float* obs, int n, int ld, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K5: returns / advantages over a time-major rollout buffer [T][ld].
  * om_ppo_returns: PPOBuffer.finish_path (rl/algos/ppo.py:68-84) with the bootstrap of :195-196.
  *   path_end[t][i] (may be NULL): 0 = the path continues, 1 = it terminated at step t (bootstrap 0),

@@ -9,7 +9,7 @@ __version__ = "0.1.0"
 
 def __getattr__(name):
     # heavy (torch-importing) modules load lazily so that host-only tools (mjcf, codegen, build) stay light
-    if name in ("LocoEnvBase", "UnitreeH1", "ValidTaskConf"):
+    if name in ("LocoEnvBase", "UnitreeH1", "StickFigureA3", "ValidTaskConf"):
         from . import environments
         return getattr(environments, name)
     if name in ("ObservationHelper", "ObservationType"):

@@ -43,6 +43,22 @@ class OmPlayOut(C.Structure):
                 ("step_no_t", C.c_void_p)]
 
 
+class OmA3TaskDesc(C.Structure):
+    _fields_ = [("period", C.c_int), ("delay_frames", C.c_int), ("target_radius", C.c_double),
+                ("goal_height_ref", C.c_double), ("goal_speed_ref", C.c_double), ("total_mass", C.c_double),
+                ("clock_lut_host", C.c_void_p), ("init_qpos_host", C.c_void_p)]
+
+
+class OmA3State(C.Structure):
+    _fields_ = [("ints", C.c_void_p), ("sequence", C.c_void_p)]
+
+
+class OmA3Out(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("terms", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
+                ("xpos", C.c_void_p), ("xquat", C.c_void_p), ("site_xpos", C.c_void_p), ("site_xmat", C.c_void_p),
+                ("cvel", C.c_void_p)]
+
+
 _P, _I, _F, _D = C.c_void_p, C.c_int, C.c_float, C.c_double
 _U64, _U32 = C.c_uint64, C.c_uint32
 
@@ -65,6 +81,10 @@ PROTOTYPES = {
     "om_traj_next": (_I, [_P, _U64, _U32, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "om_h1_play_from_velocity": (_I, [_P, C.POINTER(OmH1Spec), _P, _U64, _U32, _D, _I, _I,
                                       C.POINTER(OmPlayState), C.POINTER(OmPlayOut), _I, _I, _P]),
+    "om_a3_task_create": (_I, [C.POINTER(OmA3TaskDesc), C.POINTER(_P)]),
+    "om_a3_task_destroy": (None, [_P]),
+    "om_a3_task_step": (_I, [_P, _P, _P, _P, _P, _I, C.POINTER(OmA3State), C.POINTER(OmA3Out), _I, _I, _P]),
+    "om_a3_reset": (_I, [_P, _P, _U64, _U32, _P, _P, _D, _P, _P, C.POINTER(OmA3State), _P, _I, _I, _P]),
     "om_ppo_returns": (_I, [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P]),
     "om_gae": (_I, [_P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P, _P]),
     "om_moments": (_I, [_P, _I, _I, _I, _I, _P, _P]),

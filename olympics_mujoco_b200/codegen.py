@@ -206,6 +206,7 @@ def generate_fk(model, fn_name):
     Sink interface (all indices are literals so unused outputs are dead-code eliminated):
       S.xpos(b,x,y,z)  S.xquat(b,w,x,y,z)  S.site_xpos(s,x,y,z)  S.site_xmat(s,m0..m8)
       S.cvel(b,wx,wy,wz,vx,vy,vz)  S.com(x,y,z)
+      S.vel_p(b,wx,wy,wz,vx,vy,vz)   [w; v of the body-fixed point at xpos[rootid]]
     """
     g = Gen()
     nb = model.nbody
@@ -283,6 +284,9 @@ def generate_fk(model, fn_name):
         pos[i], quat[i], wvel[i], lvel[i] = p, qt, w_i, v_i
         g.emit(f"S.xpos({i}, {p[0]}, {p[1]}, {p[2]});")
         g.emit(f"S.xquat({i}, {qt[0]}, {qt[1]}, {qt[2]}, {qt[3]});")
+        # spatial velocity about the tree root's origin P (before the shift to the subtree COM): lets a
+        # consumer that only needs point velocities (mj_objectVelocity) skip the COM pass entirely
+        g.emit(f"S.vel_p({i}, {w_i[0]}, {w_i[1]}, {w_i[2]}, {v_i[0]}, {v_i[1]}, {v_i[2]});")
         m = float(model.body_mass[i])
         if m > 0:
             xi = g.vadd(p, g.qrot(qt, c3(model.body_ipos[i])))

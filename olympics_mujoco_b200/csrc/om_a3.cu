@@ -1,0 +1,232 @@
+// K2 (A3 flavour) kernels and C ABI: StickFigureA3 RL step tail (FK fused, not materialised unless asked for),
+// multi-step replay of recorded sim states, and the randomised reset.  Per-env arithmetic: om_a3_task.cuh.
+#include <cmath>
+#include <vector>
+
+#include "om_common.cuh"
+#include "om_sinks.cuh"
+#include "om_a3_task.cuh"
+
+namespace om {
+
+struct A3Args {
+  A3TaskConst C;
+  const float* qpos;      // [T][25][ld]
+  const float* qvel;      // [T][24][ld]
+  const float* contact;   // [T][4][ld]: l_grf, r_grf, min contact z, flags (1 = foot-floor contact, 2 = bad collision)
+  int32_t* ints;          // [7][ld]
+  float* sequence;        // [80][ld]
+  OmA3Out o;
+  int T, n, ld;
+};
+
+struct SeqGlobal {
+  const float* base; size_t ld;
+  OM_HD float operator()(int t, int c) const { return base[(size_t)(t * 4 + c) * ld]; }
+};
+struct SeqStore {
+  float* base; size_t ld;
+  OM_HD void operator()(int t, int c, float v) const { base[(size_t)(t * 4 + c) * ld] = v; }
+};
+
+// One thread per env walks its T recorded steps; the integer task state lives in registers across steps and the
+// next step's 53 inputs are requested before the current step's FK so that the loads overlap the arithmetic.
+template <int BLOCK, bool WRITE_FK>
+__global__ void __launch_bounds__(BLOCK) a3_task_kernel(A3Args a) {
+  const int env = blockIdx.x * BLOCK + threadIdx.x;
+  if (env >= a.n) return;
+  const size_t ld = a.ld, e = env;
+  A3TaskRegs s{a.ints[A3I_PHASE * ld + e], a.ints[A3I_T1 * ld + e], a.ints[A3I_T2 * ld + e], a.ints[A3I_FRAMES * ld + e],
+               a.ints[A3I_MODE * ld + e], a.ints[A3I_SEQLEN * ld + e], a.ints[A3I_REACHED * ld + e]};
+  const SeqGlobal seq{a.sequence + e, ld};
+  float q[A3_NQ], qd[A3_NV], con[4];
+  auto load = [&](int t, float (&q_)[A3_NQ], float (&qd_)[A3_NV], float (&c_)[4]) {
+    const float* qp = a.qpos + (size_t)t * A3_NQ * ld + e;
+    const float* vp = a.qvel + (size_t)t * A3_NV * ld + e;
+    const float* cp = a.contact + (size_t)t * 4 * ld + e;
+#pragma unroll
+    for (int k = 0; k < A3_NQ; ++k) q_[k] = qp[k * ld];
+#pragma unroll
+    for (int k = 0; k < A3_NV; ++k) qd_[k] = vp[k * ld];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c_[k] = cp[k * ld];
+  };
+  load(0, q, qd, con);
+  for (int t = 0; t < a.T; ++t) {
+    float qn[A3_NQ], qdn[A3_NV], conn[4];
+    if (t + 1 < a.T) load(t + 1, qn, qdn, conn);
+    float obs[A3_NOBS], terms[6], total;
+    bool done;
+    a3_obs_robot(q, qd, obs);
+    if (WRITE_FK) {
+      const size_t slot = (size_t)t;
+      A3Sink<SoaSink<true>> S{{a.o.xpos ? a.o.xpos + slot * 51 * ld : nullptr, a.o.xquat ? a.o.xquat + slot * 68 * ld : nullptr,
+                               a.o.site_xpos ? a.o.site_xpos + slot * 6 * ld : nullptr,
+                               a.o.site_xmat ? a.o.site_xmat + slot * 18 * ld : nullptr,
+                               a.o.cvel ? a.o.cvel + slot * 102 * ld : nullptr, nullptr, ld, e}, {}};
+      om_fk_stick_figure_a3(q, qd, S);
+      const int fl = (int)con[3];
+      a3_task_step(a.C, S.f, s, seq, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, obs, terms, total, done);
+    } else {
+      A3Sink<NullFkSink> S{};
+      om_fk_stick_figure_a3(q, qd, S);
+      const int fl = (int)con[3];
+      a3_task_step(a.C, S.f, s, seq, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, obs, terms, total, done);
+    }
+    if (a.o.obs) {
+      float* ob = a.o.obs + (size_t)t * A3_NOBS * ld + e;
+#pragma unroll
+      for (int k = 0; k < A3_NOBS; ++k) ob[k * ld] = obs[k];
+    }
+    if (a.o.terms) {
+      float* tp = a.o.terms + (size_t)t * 6 * ld + e;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) tp[k * ld] = terms[k];
+    }
+    if (a.o.reward) a.o.reward[(size_t)t * ld + e] = total;
+    if (a.o.done) a.o.done[(size_t)t * ld + e] = done ? 1 : 0;
+    if (t + 1 < a.T) {
+#pragma unroll
+      for (int k = 0; k < A3_NQ; ++k) q[k] = qn[k];
+#pragma unroll
+      for (int k = 0; k < A3_NV; ++k) qd[k] = qdn[k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) con[k] = conn[k];
+    }
+  }
+  a.ints[A3I_PHASE * ld + e] = s.phase; a.ints[A3I_T1 * ld + e] = s.t1; a.ints[A3I_T2 * ld + e] = s.t2;
+  a.ints[A3I_FRAMES * ld + e] = s.frames; a.ints[A3I_REACHED * ld + e] = s.reached;
+}
+
+struct A3ResetArgs {
+  A3TaskConst C;
+  const float* init_qpos;   // device [25]
+  uint64_t seed;
+  uint32_t env_id0;
+  const uint8_t* mask;
+  uint32_t* reset_count;
+  float step_h;
+  float* qpos; float* qvel; int32_t* ints; float* sequence; float* obs;
+  int n, ld;
+};
+
+__global__ void __launch_bounds__(128) a3_reset_kernel(A3ResetArgs a) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= a.n) return;
+  if (a.mask && !a.mask[env]) return;
+  const size_t ld = a.ld, e = env;
+  const uint32_t rc = a.reset_count[e];
+  a.reset_count[e] = rc + 1;
+  float u[A3_NU], q[A3_NQ], qd[A3_NV];
+  a3_reset_uniforms(a.seed, a.env_id0 + env, rc, u);
+  a3_reset_qpos_qvel(a.init_qpos, u, q, qd);
+  A3Sink<NullFkSink> S{};
+  om_fk_stick_figure_a3(q, qd, S);                                     // set_state -> mj_forward
+  A3TaskRegs s;
+  a3_task_reset(a.C, S.f, u, a.step_h, s, SeqStore{a.sequence + e, ld});
+#pragma unroll
+  for (int k = 0; k < A3_NQ; ++k) a.qpos[k * ld + e] = q[k];
+#pragma unroll
+  for (int k = 0; k < A3_NV; ++k) a.qvel[k * ld + e] = qd[k];
+  a.ints[A3I_PHASE * ld + e] = s.phase; a.ints[A3I_T1 * ld + e] = s.t1; a.ints[A3I_T2 * ld + e] = s.t2;
+  a.ints[A3I_FRAMES * ld + e] = s.frames; a.ints[A3I_MODE * ld + e] = s.mode; a.ints[A3I_SEQLEN * ld + e] = s.seq_len;
+  a.ints[A3I_REACHED * ld + e] = s.reached;
+  if (a.obs) {                                                         // get_obs: goal steps are zero after task.reset
+    float obs[A3_NOBS];
+    a3_obs_robot(q, qd, obs);
+    const float* lrow = a.C.lut + (size_t)s.phase * A3_LUT_COLS;
+    obs[31] = lrow[4];
+    obs[32] = lrow[5];
+#pragma unroll
+    for (int k = 33; k < A3_NOBS; ++k) obs[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < A3_NOBS; ++k) a.obs[k * ld + e] = obs[k];
+  }
+}
+
+}  // namespace om
+
+using namespace om;
+
+struct OmA3Task {
+  A3TaskConst C;
+  float* lut = nullptr;        // device [period][6]
+  float* init_qpos = nullptr;  // device [25]
+};
+
+extern "C" int om_a3_task_create(const OmA3TaskDesc* d, OmA3Task** out) {
+  OM_REQUIRE(d && out, "om_a3_task_create: null argument");
+  OM_REQUIRE(d->period >= 2 && d->period <= 4096 && d->period % 2 == 0, "om_a3_task_create: period %d must be even and in [2,4096]", d->period);
+  OM_REQUIRE(d->delay_frames >= 0 && d->total_mass > 0 && d->clock_lut_host && d->init_qpos_host, "om_a3_task_create: bad description");
+  std::vector<float> lut((size_t)d->period * A3_LUT_COLS);
+  for (int p = 0; p < d->period; ++p) {
+    for (int c = 0; c < 4; ++c) lut[(size_t)p * A3_LUT_COLS + c] = (float)d->clock_lut_host[p * 4 + c];
+    lut[(size_t)p * A3_LUT_COLS + 4] = (float)std::sin(2.0 * M_PI * p / d->period);     // StickFigureA3.py:147-148
+    lut[(size_t)p * A3_LUT_COLS + 5] = (float)std::cos(2.0 * M_PI * p / d->period);
+  }
+  float iq[A3_NQ];
+  for (int k = 0; k < A3_NQ; ++k) iq[k] = (float)d->init_qpos_host[k];
+  OmA3Task* t = new OmA3Task();
+  cudaError_t e = cudaMalloc(&t->lut, lut.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&t->init_qpos, sizeof iq);
+  if (e == cudaSuccess) e = cudaMemcpy(t->lut, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(t->init_qpos, iq, sizeof iq, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (t->lut) cudaFree(t->lut);
+    if (t->init_qpos) cudaFree(t->init_qpos);
+    delete t;
+    return fail("om_a3_task_create: device upload failed: %s (no CPU path)", cudaGetErrorString(e));
+  }
+  t->C.period = d->period;
+  t->C.delay_frames = d->delay_frames;
+  t->C.fmax = (float)(d->total_mass * 9.8 * 0.5);
+  t->C.vmax = 0.2f;
+  t->C.target_radius = d->target_radius;
+  t->C.goal_height_ref = d->goal_height_ref;
+  t->C.deadzone = 0.01 + 0.05 * d->goal_speed_ref;
+  t->C.lut = t->lut;
+  *out = t;
+  return 0;
+}
+
+extern "C" void om_a3_task_destroy(OmA3Task* t) {
+  if (!t) return;
+  cudaFree(t->lut);
+  cudaFree(t->init_qpos);
+  delete t;
+}
+
+extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const float* qpos, const float* qvel,
+                               const float* contact, int n_steps, const OmA3State* state, const OmA3Out* out, int n, int ld,
+                               void* stream) {
+  OM_REQUIRE(m && task && state && out, "om_a3_task_step: null argument");
+  OM_REQUIRE(m->specialised == SPEC_A3, "om_a3_task_step: model is not the StickFigureA3 model");
+  OM_REQUIRE(n >= 0 && ld >= n && n_steps >= 0, "om_a3_task_step: bad sizes (n=%d ld=%d n_steps=%d)", n, ld, n_steps);
+  if (n == 0 || n_steps == 0) return 0;
+  OM_REQUIRE(qpos && qvel && contact && state->ints && state->sequence, "om_a3_task_step: null input / state");
+  A3Args a{task->C, qpos, qvel, contact, state->ints, state->sequence, *out, n_steps, n, ld};
+  const bool want_fk = out->xpos || out->xquat || out->site_xpos || out->site_xmat || out->cvel;
+  constexpr int BLOCK = 64;
+  const int grid = ceil_div(n, BLOCK);
+  if (want_fk) a3_task_kernel<BLOCK, true><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
+  else a3_task_kernel<BLOCK, false><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
+  OM_LAUNCHED();
+  return 0;
+}
+
+extern "C" int om_a3_reset(const OmModel* m, const OmA3Task* task, uint64_t seed, uint32_t env_id0, const uint8_t* mask,
+                           uint32_t* reset_count, double iteration_count, float* qpos, float* qvel, const OmA3State* state,
+                           float* obs, int n, int ld, void* stream) {
+  OM_REQUIRE(m && task && state, "om_a3_reset: null argument");
+  OM_REQUIRE(m->specialised == SPEC_A3, "om_a3_reset: model is not the StickFigureA3 model");
+  OM_REQUIRE(n >= 0 && ld >= n, "om_a3_reset: need 0 <= n <= ld");
+  if (n == 0) return 0;
+  OM_REQUIRE(reset_count && qpos && qvel && state->ints && state->sequence, "om_a3_reset: null state");
+  double h = (iteration_count - 3000.0) / 8000.0;                      // walking_task.py:378
+  h = (h < 0.0 ? 0.0 : (h > 1.0 ? 1.0 : h)) * 0.1;
+  A3ResetArgs a{task->C, task->init_qpos, seed, env_id0, mask, reset_count, (float)h, qpos, qvel, state->ints,
+                state->sequence, obs, n, ld};
+  a3_reset_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(a);
+  OM_LAUNCHED();
+  return 0;
+}

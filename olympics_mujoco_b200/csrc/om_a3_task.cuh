@@ -1,0 +1,279 @@
+// K2 (A3 flavour): per-env device functions of the StickFigureA3 RL step tail -- everything
+// StickFigureA3.step does after robot.step() (= mj_step, outside this path):
+//   WalkingTask.step          tasks/walking_task.py:246-293  (+ update_target_steps :228-244, update_goal_steps :184-225)
+//   WalkingTask.calc_reward   :74-110, step_reward :56-72; terms tasks/rewards.py:27-40, :65-83, :85-102, :121-126
+//   WalkingTask.done          :298-319
+//   StickFigureA3.get_obs     real_humanoid_robots/StickFigureA3.py:144-178
+//   reset_model + task.reset  StickFigureA3.py:205-235, walking_task.py:321-397 (:137-182, :113-135)
+// The body/site quantities the task reads through MujocoRobotInterface (interfaces/mujoco_robot_interface.py
+// :299-346) are captured straight out of the generated FK by A3Sink, in registers; nothing the task does not
+// read is computed (the compiler removes the arms and the COM pass: foot velocities are taken about the root
+// origin, v(xpos) = v_P + w x (xpos - P), which is what mj_objectVelocity(mjOBJ_XBODY) evaluates to).
+// Host-compilable (OM_HD pre-defined) so tests/host/a3_host_harness.cpp can check it without a GPU.
+#pragma once
+#include "om_math.cuh"
+#include "gen/a3_ids.h"
+#include "gen/fk_stick_figure_a3.cuh"
+
+namespace om {
+
+constexpr int A3_NQ = 25, A3_NV = 24, A3_NOBS = 41, A3_MAX_STEPS = 20, A3_NINT = 7, A3_LUT_COLS = 6, A3_NU = 60;
+enum { A3I_PHASE = 0, A3I_T1, A3I_T2, A3I_FRAMES, A3I_MODE, A3I_SEQLEN, A3I_REACHED };
+enum { A3_STANDING = 0, A3_FORWARD = 1 };
+constexpr uint32_t A3_RESET_STREAM = 16;      // oracle/philox.py STREAM_A3_RESET
+
+struct A3TaskConst {
+  int period, delay_frames;
+  float fmax, vmax;                   // rewards.py:66 (mass*9.8*0.5), :87 (0.2)
+  double target_radius;               // walking_task.py:333
+  double goal_height_ref, deadzone;   // StickFigureA3.py:110; rewards.py:36 (0.01 + 0.05*goal_speed_ref)
+  const float* lut;                   // [period][6]: r_frc, r_vel, l_frc, l_vel clocks, sin/cos(2 pi phase/period)
+};
+
+struct A3Feat {
+  V3 root_p, head_p, lfoot_p, rfoot_p, lsite, rsite;
+  Q4 root_q;
+  V3 lw, lv, rw, rv;                  // foot body spatial velocity [w; v] about the root origin
+};
+
+struct NullFkSink {
+  static constexpr bool want_site_xmat = false;
+  OM_HD void xpos(int, float, float, float) const {}
+  OM_HD void xquat(int, float, float, float, float) const {}
+  OM_HD void site_xpos(int, float, float, float) const {}
+  OM_HD void site_xmat(int, float, float, float, float, float, float, float, float, float) const {}
+  OM_HD void cvel(int, float, float, float, float, float, float) const {}
+  OM_HD void com(float, float, float) const {}
+  OM_HD void vel_p(int, float, float, float, float, float, float) const {}
+};
+
+// Captures what the task reads; forwards everything to Inner (NullFkSink, or an HBM sink when the caller also
+// wants the MjData fields).  Body / site indices are literals at every call site, so the branches fold.
+template <class Inner>
+struct A3Sink {
+  static constexpr bool want_site_xmat = Inner::want_site_xmat;
+  Inner inner;
+  A3Feat f;
+  OM_HD void xpos(int b, float x, float y, float z) {
+    inner.xpos(b, x, y, z);
+    if (b == OM_A3_ROOT) f.root_p = V3{x, y, z};
+    else if (b == OM_A3_HEAD) f.head_p = V3{x, y, z};
+    else if (b == OM_A3_LFOOT) f.lfoot_p = V3{x, y, z};
+    else if (b == OM_A3_RFOOT) f.rfoot_p = V3{x, y, z};
+  }
+  OM_HD void xquat(int b, float w, float x, float y, float z) {
+    inner.xquat(b, w, x, y, z);
+    if (b == OM_A3_ROOT) f.root_q = Q4{w, x, y, z};
+  }
+  OM_HD void site_xpos(int s, float x, float y, float z) {
+    inner.site_xpos(s, x, y, z);
+    if (s == OM_A3_LSITE) f.lsite = V3{x, y, z};
+    else if (s == OM_A3_RSITE) f.rsite = V3{x, y, z};
+  }
+  OM_HD void site_xmat(int s, float a, float b, float c, float d, float e, float g, float h, float i, float j) {
+    inner.site_xmat(s, a, b, c, d, e, g, h, i, j);
+  }
+  OM_HD void cvel(int b, float wx, float wy, float wz, float vx, float vy, float vz) { inner.cvel(b, wx, wy, wz, vx, vy, vz); }
+  OM_HD void com(float x, float y, float z) { inner.com(x, y, z); }
+  OM_HD void vel_p(int b, float wx, float wy, float wz, float vx, float vy, float vz) {
+    if (b == OM_A3_LFOOT) { f.lw = V3{wx, wy, wz}; f.lv = V3{vx, vy, vz}; }
+    else if (b == OM_A3_RFOOT) { f.rw = V3{wx, wy, wz}; f.rv = V3{vx, vy, vz}; }
+  }
+};
+
+struct A3TaskRegs { int phase, t1, t2, frames, mode, seq_len, reached; };
+
+OM_HD float norm3(V3 a) { return sqrtf(dot(a, a)); }
+
+// transforms3d quaternions.quat2mat (scale-invariant: s = 2/|q|^2), rows 0..2
+OM_HD void tf3_quat2mat(Q4 q, float (&m)[9]) {
+  const float nq = fmaf(q.w, q.w, fmaf(q.x, q.x, fmaf(q.y, q.y, q.z * q.z)));
+  if (nq < 2.220446e-16f) {            // transforms3d: Nq < float64 eps -> identity
+    m[0] = 1.f; m[1] = 0.f; m[2] = 0.f; m[3] = 0.f; m[4] = 1.f; m[5] = 0.f; m[6] = 0.f; m[7] = 0.f; m[8] = 1.f;
+    return;
+  }
+  const float s = 2.0f / nq;
+  const float X = q.x * s, Y = q.y * s, Z = q.z * s;
+  const float wX = q.w * X, wY = q.w * Y, wZ = q.w * Z, xX = q.x * X, xY = q.x * Y, xZ = q.x * Z;
+  const float yY = q.y * Y, yZ = q.y * Z, zZ = q.z * Z;
+  m[0] = 1.0f - (yY + zZ); m[1] = xY - wZ; m[2] = xZ + wY;
+  m[3] = xY + wZ; m[4] = 1.0f - (xX + zZ); m[5] = yZ - wX;
+  m[6] = xZ - wY; m[7] = yZ + wX; m[8] = 1.0f - (xX + yY);
+}
+
+constexpr float A3_EPS4 = 8.8817842e-16f;     // transforms3d euler._EPS4 (4 * float64 eps)
+
+// StickFigureA3.get_obs rows 0..30 (everything that does not depend on the task state)
+OM_HD void a3_obs_robot(const float (&q)[A3_NQ], const float (&qd)[A3_NV], float (&obs)[A3_NOBS]) {
+  float m[9];
+  tf3_quat2mat(Q4{q[3], q[4], q[5], q[6]}, m);                       // quat2euler(qpos[3:7])[0:2], axes 'sxyz'
+  const float cy = sqrtf(fmaf(m[0], m[0], m[3] * m[3]));
+  const float roll = cy > A3_EPS4 ? atan2f(m[7], m[8]) : atan2f(-m[5], m[4]);
+  const float pitch = atan2f(-m[6], cy);
+  float si, ci, sj, cj;
+  sincosf(0.5f * roll, &si, &ci);
+  sincosf(0.5f * pitch, &sj, &cj);
+  obs[0] = cj * ci; obs[1] = cj * si; obs[2] = sj * ci; obs[3] = -(sj * si);   // euler2quat(roll, pitch, 0)
+#pragma unroll
+  for (int k = 0; k < 3; ++k) obs[4 + k] = qd[3 + k];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) obs[7 + k] = q[7 + k];                 // actuator_length / gear, gear = 1
+#pragma unroll
+  for (int k = 0; k < 12; ++k) obs[19 + k] = qd[6 + k];
+}
+
+// WalkingTask.step + calc_reward + done for one env.  Seq: float operator()(int step, int component).
+template <class Seq>
+OM_HD void a3_task_step(const A3TaskConst& C, const A3Feat& f, A3TaskRegs& s, const Seq& seq, float l_grf, float r_grf,
+                        float min_z, bool foot_contact, bool bad_collision, float (&obs)[A3_NOBS], float (&terms)[6],
+                        float& total, bool& done) {
+  s.phase += 1;                                                      // :248-250
+  if (s.phase >= C.period) s.phase = 0;
+  const V3 lvel = f.lv + cross(f.lw, f.lfoot_p - f.root_p);          // mj_objectVelocity(XBODY), linear part
+  const V3 rvel = f.rv + cross(f.rw, f.rfoot_p - f.root_p);
+  V3 tgt{seq(s.t1, 0), seq(s.t1, 1), seq(s.t1, 2)};                  // :266-283
+  float dl = norm3(f.lsite - tgt), dr = norm3(f.rsite - tgt);
+  if ((double)dl < C.target_radius || (double)dr < C.target_radius) {
+    s.reached = 1;
+    s.frames += 1;
+  } else {
+    s.reached = 0;
+    s.frames = 0;
+  }
+  if (s.reached && s.frames >= C.delay_frames) {                     // :286-289, update_target_steps :228-244
+    s.t1 = s.t2;
+    s.t2 += 1;
+    if (s.t2 == s.seq_len) s.t2 = s.seq_len - 1;
+    s.reached = 0;
+    s.frames = 0;
+    tgt = V3{seq(s.t1, 0), seq(s.t1, 1), seq(s.t1, 2)};
+    dl = norm3(f.lsite - tgt);
+    dr = norm3(f.rsite - tgt);
+  }
+  const float th1 = seq(s.t1, 3);
+  const V3 tgt2{seq(s.t2, 0), seq(s.t2, 1), seq(s.t2, 2)};
+  const float th2 = seq(s.t2, 3);
+
+  // ---- update_goal_steps :184-225: inv([R p; 0 1]) [Rz(theta) t; 0 1]
+  float R[9];
+  tf3_quat2mat(f.root_q, R);
+  const float* lrow = C.lut + (size_t)s.phase * A3_LUT_COLS;
+  obs[31] = lrow[4];
+  obs[32] = lrow[5];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const V3 d = (i == 0 ? tgt : tgt2) - f.root_p;
+    float st, ct;
+    sincosf(i == 0 ? th1 : th2, &st, &ct);
+    const float a = fmaf(R[0], ct, R[3] * st), b = fmaf(R[1], ct, R[4] * st);   // column 0 of R^T Rz
+    const float cy = sqrtf(fmaf(a, a, b * b));
+    const bool walk = s.mode != A3_STANDING;
+    obs[33 + i] = walk ? fmaf(R[0], d.x, fmaf(R[3], d.y, R[6] * d.z)) : 0.f;
+    obs[35 + i] = walk ? fmaf(R[1], d.x, fmaf(R[4], d.y, R[7] * d.z)) : 0.f;
+    obs[37 + i] = walk ? fmaf(R[2], d.x, fmaf(R[5], d.y, R[8] * d.z)) : 0.f;
+    obs[39 + i] = (walk && cy > A3_EPS4) ? atan2f(b, a) : 0.f;
+  }
+
+  // ---- calc_reward :74-110
+  float r_frc_c = 1.f, r_vel_c = -1.f, l_frc_c = 1.f, l_vel_c = -1.f;                  // STANDING :83-91
+  if (s.mode != A3_STANDING) { r_frc_c = lrow[0]; r_vel_c = lrow[1]; l_frc_c = lrow[2]; l_vel_c = lrow[3]; }
+  const float PI4 = 0.78539816339744831f;
+  const float nl = fminf(l_grf, C.fmax) / C.fmax * 2.f - 1.f, nr = fminf(r_grf, C.fmax) / C.fmax * 2.f - 1.f;
+  const float frc = (tanf(PI4 * l_frc_c * nl) + tanf(PI4 * r_frc_c * nr)) * 0.5f;      // rewards.py:65-83
+  const float vl = fminf(norm3(lvel), C.vmax) / C.vmax * 2.f - 1.f, vr = fminf(norm3(rvel), C.vmax) / C.vmax * 2.f - 1.f;
+  const float vel = (tanf(PI4 * l_vel_c * vl) + tanf(PI4 * r_vel_c * vr)) * 0.5f;      // rewards.py:85-102
+  float sh, ch;
+  sincosf(0.5f * th1, &sh, &ch);                                                       // euler2quat(0, 0, theta)
+  const float inner = fmaf(ch, f.root_q.w, sh * f.root_q.z);
+  const float orient = expf(-10.f * (1.f - inner * inner));                            // rewards.py:121-126
+  // rewards.py:27-40; the dead-zone test is evaluated in double on the fp32 inputs (root z is qpos[2] itself)
+  double err = fabs((double)f.root_p.z - (foot_contact ? (double)min_z : 0.0) - C.goal_height_ref);
+  if (err < C.deadzone) err = 0.0;
+  const float errf = (float)err;
+  const float height = expf(-40.f * errf * errf);
+  const float fd = fminf(dl, dr);                                                      // :56-72
+  const float hit = s.reached ? expf(-fd / 0.25f) : 0.f;
+  const float mx = (tgt.x + tgt2.x) * 0.5f - f.root_p.x, my = (tgt.y + tgt2.y) * 0.5f - f.root_p.y;
+  const float progress = expf(-sqrtf(fmaf(mx, mx, my * my)) * 0.5f);
+  const float step_r = fmaf(0.8f, hit, 0.2f * progress);
+  const float hx = f.head_p.x - f.root_p.x, hy = f.head_p.y - f.root_p.y;
+  const float upper = expf(-10.f * fmaf(hx, hx, hy * hy));
+  terms[0] = 0.150f * frc; terms[1] = 0.150f * vel; terms[2] = 0.050f * orient;
+  terms[3] = 0.050f * height; terms[4] = 0.450f * step_r; terms[5] = 0.050f * upper;
+  total = ((((terms[0] + terms[1]) + terms[2]) + terms[3]) + terms[4]) + terms[5];      // StickFigureA3.py:192
+  // ---- done :298-319 (difference of the fp32 heights taken in double, threshold in double)
+  done = ((double)f.root_p.z - (double)fminf(f.lsite.z, f.rsite.z) < 0.6) || bad_collision;
+}
+
+// ---------------------------------------------------------------- reset (A13)
+OM_HD void a3_reset_uniforms(uint64_t seed, uint32_t env_id, uint32_t reset_count, float (&u)[A3_NU]) {
+#pragma unroll
+  for (int s = 0; s < A3_NU / 4; ++s) {
+    const U4 w = om_draw(seed, env_id, reset_count, A3_RESET_STREAM + s);
+    u[4 * s] = to_unit(w.x); u[4 * s + 1] = to_unit(w.y); u[4 * s + 2] = to_unit(w.z); u[4 * s + 3] = to_unit(w.w);
+  }
+}
+
+// reset_model (StickFigureA3.py:205-235): draw order documented in oracle/a3.py reset()
+OM_HD void a3_reset_qpos_qvel(const float* init_qpos, const float (&u)[A3_NU], float (&q)[A3_NQ], float (&qd)[A3_NV]) {
+  const float c = 0.02f;
+#pragma unroll
+  for (int k = 0; k < A3_NQ; ++k) q[k] = fmaf(fmaf(u[k], 2.f, -1.f), c, init_qpos[k]);
+#pragma unroll
+  for (int k = 0; k < A3_NV; ++k) qd[k] = fmaf(u[25 + k], 2.f, -1.f) * c;
+  q[0] = fmaf(u[49], 2.f, -1.f);
+  q[1] = fmaf(u[50], 2.f, -1.f);
+  q[2] = 1.34f;
+  const float pitch = fmaf(u[51], 10.f, -5.f) * 0.017453292519943295f;
+  const float yaw = fmaf(u[52], 2.f, -1.f) * 3.14159265358979323846f;
+  float sj, cj, sk, ck;
+  sincosf(0.5f * pitch, &sj, &cj);
+  sincosf(0.5f * yaw, &sk, &ck);
+  q[3] = cj * ck; q[4] = -(sj * sk); q[5] = sj * ck; q[6] = cj * sk;     // euler2quat(0, pitch, yaw)
+}
+
+// WalkingTask.reset (:321-397) after set_state; SeqOut: void operator()(int step, int component, float value)
+template <class SeqOut>
+OM_HD void a3_task_reset(const A3TaskConst& C, const A3Feat& f, const float (&u)[A3_NU], float step_h, A3TaskRegs& s,
+                         const SeqOut& seq_out) {
+  s.phase = (double)u[53] < 0.5 ? 0 : C.period / 2;                   // :354
+  s.mode = (double)u[54] < 0.2 ? A3_STANDING : A3_FORWARD;            // :362-364
+  int num_steps = A3_MAX_STEPS;
+  float step_height = 0.f;
+  if (s.mode == A3_STANDING) num_steps = 1;
+  else step_height = (double)u[55] < 0.5 ? -step_h : step_h;          // :377-379
+  const float first_y = fmaf(0.01f, u[56], 0.095f);                   // generate_step_sequence :137-182
+  const bool half = s.phase == C.period / 2;
+  const int cc = (double)u[57] < 0.5 ? 2 : 3;
+  float R[9];
+  tf3_quat2mat(f.root_q, R);                                          // transform_sequence :113-135
+  const float cyy = sqrtf(fmaf(R[0], R[0], R[3] * R[3]));
+  const float yaw = cyy > A3_EPS4 ? atan2f(R[3], R[0]) : 0.f;
+  float sy, cy;
+  sincosf(yaw, &sy, &cy);
+  const float mx = (f.lfoot_p.x + f.rfoot_p.x) * 0.5f, my = (f.lfoot_p.y + f.rfoot_p.y) * 0.5f;
+  float x = 0.f, z = 0.f, y = half ? -0.15f : 0.15f;
+  for (int i = 0; i < A3_MAX_STEPS; ++i) {
+    float sx, syy, sz;
+    if (i == 0) { sx = 0.f; syy = half ? -first_y : first_y; sz = 0.f; }
+    else {
+      x += 0.3f;
+      y = -y;
+      if (i > cc) z += step_height;
+      sx = x; syy = y; sz = z;
+    }
+    const bool live = i < num_steps;
+    seq_out(i, 0, live ? mx + sx * cy - syy * sy : 0.f);
+    seq_out(i, 1, live ? my + sx * sy + syy * cy : 0.f);
+    seq_out(i, 2, live ? sz : 0.f);
+    seq_out(i, 3, live ? yaw : 0.f);
+  }
+  s.seq_len = num_steps;
+  s.t1 = 0;                                                           // update_target_steps from t1 = t2 = 0
+  s.t2 = 1;
+  if (s.t2 == s.seq_len) s.t2 = s.seq_len - 1;
+  s.frames = 0;
+  s.reached = 0;
+}
+
+}  // namespace om

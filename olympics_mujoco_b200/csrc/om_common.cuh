@@ -69,65 +69,4 @@ struct OmModel {
   int device = 0;
 };
 
-// ---------------------------------------------------------------- device math
-namespace om {
-
-struct V3 { float x, y, z; };
-struct Q4 { float w, x, y, z; };
-
-OM_HD V3 v3(float x, float y, float z) { return V3{x, y, z}; }
-OM_HD V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
-OM_HD V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
-OM_HD V3 operator*(V3 a, float s) { return V3{a.x * s, a.y * s, a.z * s}; }
-OM_HD V3 cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
-OM_HD float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
-OM_HD V3 fma3(V3 a, float s, V3 c) { return V3{fmaf(a.x, s, c.x), fmaf(a.y, s, c.y), fmaf(a.z, s, c.z)}; }
-
-// mju_mulQuat
-OM_HD Q4 qmul(Q4 a, Q4 b) {
-  return Q4{a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
-            a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w};
-}
-// mju_rotVecQuat
-OM_HD V3 qrot(Q4 q, V3 v) {
-  V3 u{q.x, q.y, q.z};
-  V3 t = v * q.w + cross(u, v);
-  V3 c = cross(u, t);
-  return V3{fmaf(2.0f, c.x, v.x), fmaf(2.0f, c.y, v.y), fmaf(2.0f, c.z, v.z)};
-}
-// mju_normalize4
-OM_HD Q4 qnormalize(Q4 q) {
-  float n2 = fmaf(q.w, q.w, fmaf(q.x, q.x, fmaf(q.y, q.y, q.z * q.z)));
-  if (n2 < 1e-30f) return Q4{1.f, 0.f, 0.f, 0.f};
-  float inv = rsqrtf(n2);
-  return Q4{q.w * inv, q.x * inv, q.y * inv, q.z * inv};
-}
-// mju_quat2Mat (row major)
-OM_HD void quat2mat(Q4 q, float* m) {
-  float ww = q.w * q.w, xx = q.x * q.x, yy = q.y * q.y, zz = q.z * q.z;
-  float xy = q.x * q.y, xz = q.x * q.z, yz = q.y * q.z, wx = q.w * q.x, wy = q.w * q.y, wz = q.w * q.z;
-  m[0] = ww + xx - yy - zz; m[1] = 2.f * (xy - wz);   m[2] = 2.f * (xz + wy);
-  m[3] = 2.f * (xy + wz);   m[4] = ww - xx + yy - zz; m[5] = 2.f * (yz - wx);
-  m[6] = 2.f * (xz - wy);   m[7] = 2.f * (yz + wx);   m[8] = ww - xx - yy + zz;
-}
-
-// ---------------------------------------------------------------- Philox4x32-10 (contract: oracle/philox.py)
-struct U4 { uint32_t x, y, z, w; };
-OM_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-    c = U4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  return c;
-}
-OM_HD U4 om_draw(uint64_t seed, uint32_t env, uint32_t count, uint32_t stream) {
-  return philox4x32_10(U4{env, count, stream, 0u}, (uint32_t)seed, (uint32_t)(seed >> 32));
-}
-OM_HD int to_int(uint32_t x, int n) { return (int)__umulhi(x, (uint32_t)n); }
-OM_HD float to_unit(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
-
-}  // namespace om
+#include "om_math.cuh"

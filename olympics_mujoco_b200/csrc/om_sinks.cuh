@@ -36,6 +36,7 @@ struct SoaSink {
   OM_HD void com(float x, float y, float z) const {
     if (cm) { cm[env] = x; cm[ld + env] = y; cm[2 * ld + env] = z; }
   }
+  OM_HD void vel_p(int, float, float, float, float, float, float) const {}
 };
 
 }  // namespace om

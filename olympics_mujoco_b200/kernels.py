@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import OmH1Spec, OmModelDesc, OmPlayOut, OmPlayState, check
+from ._lib import OmA3Out, OmA3State, OmA3TaskDesc, OmH1Spec, OmModelDesc, OmPlayOut, OmPlayState, check
 from .mjcf import KinematicModel
 
 
@@ -221,6 +221,76 @@ def h1_play_from_velocity(dm, spec, traj: DeviceTrajectory, state, n_steps, dt=0
                                                int(n_steps), int(bool(end_episode_reset)), C.byref(ps), C.byref(po),
                                                n, max(n, 1), _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------- A3
+A3_NINT, A3_MAX_STEPS, A3_NOBS = 7, 20, 41
+A3_FK_SIZES = dict(xpos=17 * 3, xquat=17 * 4, site_xpos=2 * 3, site_xmat=2 * 9, cvel=17 * 6)
+
+
+class A3Task:
+    """OmA3Task handle (constants of the WalkingTask) + per-env task state for n envs."""
+
+    def __init__(self, dm: DeviceModel, n_env, clock_lut, init_qpos, period=88, delay_frames=30, target_radius=0.20,
+                 goal_height_ref=0.80, goal_speed_ref=0.0, seed=0, env_id0=0, device="cuda"):
+        _lib.require_cuda()
+        lut = np.ascontiguousarray(clock_lut, dtype=np.float64)
+        iq = np.ascontiguousarray(init_qpos, dtype=np.float64)
+        assert lut.shape == (period, 4) and iq.shape == (dm.km.nq,)
+        desc = OmA3TaskDesc(period=period, delay_frames=delay_frames, target_radius=target_radius,
+                            goal_height_ref=goal_height_ref, goal_speed_ref=goal_speed_ref,
+                            total_mass=float(dm.km.total_mass), clock_lut_host=lut.ctypes.data, init_qpos_host=iq.ctypes.data)
+        h = C.c_void_p()
+        check(_lib.load().om_a3_task_create(C.byref(desc), C.byref(h)))
+        self.handle, self.dm = h, dm
+        self.n, self.seed, self.env_id0 = int(n_env), int(seed), int(env_id0)
+        self.ints = torch.zeros((A3_NINT, n_env), dtype=torch.int32, device=device)
+        self.sequence = torch.zeros((A3_MAX_STEPS * 4, n_env), dtype=torch.float32, device=device)
+        self.reset_count = torch.zeros(n_env, dtype=torch.int32, device=device)          # bits of a uint32
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().om_a3_task_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def _state(self):
+        return OmA3State(ints=self.ints.data_ptr(), sequence=self.sequence.data_ptr())
+
+    def reset(self, qpos, qvel, mask=None, iteration_count=0.0, obs=None):
+        """reset_model + WalkingTask.reset for the masked envs: fills qpos [25,n], qvel [24,n], the task state and obs."""
+        if obs is None:
+            obs = soa(A3_NOBS, self.n, device=self.ints.device)
+        st = self._state()
+        check(_lib.load().om_a3_reset(self.dm.handle, self.handle, self.seed, self.env_id0, _p(mask, torch.uint8),
+                                      _p(self.reset_count), float(iteration_count), _p(qpos, torch.float32),
+                                      _p(qvel, torch.float32), C.byref(st), _p(obs, torch.float32), self.n, max(self.n, 1),
+                                      _stream()))
+        return obs
+
+    def step(self, qpos, qvel, contact, want=("obs", "terms", "reward", "done"), out=None):
+        """The StickFigureA3.step tail on post-physics states.  qpos [25,n] (one step) or [T,25,n] (replay of T
+        recorded steps); qvel / contact ([4,n]: l_grf, r_grf, min contact z, flags) likewise."""
+        T = 1 if qpos.dim() == 2 else qpos.shape[0]
+        n, dev = self.n, qpos.device
+        assert qpos.shape[-2:] == (25, n) and qvel.shape[-2:] == (24, n) and contact.shape[-2:] == (4, n)
+        sizes = dict(obs=(A3_NOBS, torch.float32), terms=(6, torch.float32), reward=(None, torch.float32),
+                     done=(None, torch.uint8), **{k: (c, torch.float32) for k, c in A3_FK_SIZES.items()})
+        out = dict(out or {})
+        for k in want:
+            if k not in out:
+                c, dt_ = sizes[k]
+                shape = ((n,) if c is None else (c, n)) if qpos.dim() == 2 else ((T, n) if c is None else (T, c, n))
+                out[k] = torch.empty(shape, dtype=dt_, device=dev)
+        for k, t in out.items():
+            _p(t, sizes[k][1])
+        po = OmA3Out(**{k: (out[k].data_ptr() if k in out else None) for k in sizes})
+        st = self._state()
+        check(_lib.load().om_a3_task_step(self.dm.handle, self.handle, _p(qpos, torch.float32), _p(qvel, torch.float32),
+                                          _p(contact, torch.float32), T, C.byref(st), C.byref(po), n, max(n, 1), _stream()))
+        return out
 
 
 # ------------------------------------------------------------------------------------------- learner side

@@ -1,0 +1,75 @@
+// TEST INFRASTRUCTURE: compiles the per-env device functions of the A3 step tail (csrc/om_a3_task.cuh, fp32) as
+// plain host C++ so that they can be checked against the reference-generated golden fixture in a container
+// without a GPU.  The loops below mirror a3_task_kernel / a3_reset_kernel in csrc/om_a3.cu for ONE env.
+// Never shipped, never used by the product (which has no CPU path).
+#include <cmath>
+#include <cstring>
+#define OM_HD inline
+static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+#include "om_a3_task.cuh"
+
+using namespace om;
+
+static A3TaskConst make_const(const float* lut6, int period, int delay, double radius, double gh, double dz, float fmax) {
+  A3TaskConst C;
+  C.period = period; C.delay_frames = delay; C.fmax = fmax; C.vmax = 0.2f;
+  C.target_radius = radius; C.goal_height_ref = gh; C.deadzone = dz; C.lut = lut6;
+  return C;
+}
+
+struct SeqHost {
+  const float* s;
+  float operator()(int t, int c) const { return s[t * 4 + c]; }
+};
+struct SeqHostOut {
+  float* s;
+  void operator()(int t, int c, float v) const { s[t * 4 + c] = v; }
+};
+
+extern "C" void host_a3_rollout(const float* lut6, int period, int delay, double radius, double gh, double dz, float fmax,
+                                const float* qpos, const float* qvel, const float* contact, int T, int* ints, float* seq,
+                                float* obs, float* terms, float* reward, unsigned char* done) {
+  const A3TaskConst C = make_const(lut6, period, delay, radius, gh, dz, fmax);
+  A3TaskRegs s{ints[0], ints[1], ints[2], ints[3], ints[4], ints[5], ints[6]};
+  for (int t = 0; t < T; ++t) {
+    float q[A3_NQ], qd[A3_NV], o[A3_NOBS], tr[6], total;
+    bool d;
+    std::memcpy(q, qpos + t * A3_NQ, sizeof q);
+    std::memcpy(qd, qvel + t * A3_NV, sizeof qd);
+    const float* c = contact + t * 4;
+    a3_obs_robot(q, qd, o);
+    A3Sink<NullFkSink> S{};
+    om_fk_stick_figure_a3(q, qd, S);
+    const int fl = (int)c[3];
+    a3_task_step(C, S.f, s, SeqHost{seq}, c[0], c[1], c[2], (fl & 1) != 0, (fl & 2) != 0, o, tr, total, d);
+    std::memcpy(obs + t * A3_NOBS, o, sizeof o);
+    std::memcpy(terms + t * 6, tr, sizeof tr);
+    reward[t] = total;
+    done[t] = d ? 1 : 0;
+  }
+  int out[7] = {s.phase, s.t1, s.t2, s.frames, s.mode, s.seq_len, s.reached};
+  std::memcpy(ints, out, sizeof out);
+}
+
+extern "C" void host_a3_reset(const float* lut6, int period, int delay, double radius, double gh, double dz, float fmax,
+                              const float* init_qpos, unsigned long long seed, unsigned env, unsigned rc, float step_h,
+                              float* qpos, float* qvel, int* ints, float* seq, float* obs) {
+  const A3TaskConst C = make_const(lut6, period, delay, radius, gh, dz, fmax);
+  float u[A3_NU], q[A3_NQ], qd[A3_NV];
+  a3_reset_uniforms(seed, env, rc, u);
+  a3_reset_qpos_qvel(init_qpos, u, q, qd);
+  A3Sink<NullFkSink> S{};
+  om_fk_stick_figure_a3(q, qd, S);
+  A3TaskRegs s;
+  a3_task_reset(C, S.f, u, step_h, s, SeqHostOut{seq});
+  std::memcpy(qpos, q, sizeof q);
+  std::memcpy(qvel, qd, sizeof qd);
+  int out[7] = {s.phase, s.t1, s.t2, s.frames, s.mode, s.seq_len, s.reached};
+  std::memcpy(ints, out, sizeof out);
+  float o[A3_NOBS];
+  a3_obs_robot(q, qd, o);
+  o[31] = lut6[s.phase * A3_LUT_COLS + 4];
+  o[32] = lut6[s.phase * A3_LUT_COLS + 5];
+  for (int k = 33; k < A3_NOBS; ++k) o[k] = 0.f;
+  std::memcpy(obs, o, sizeof o);
+}

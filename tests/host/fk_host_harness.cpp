@@ -19,6 +19,7 @@ struct HostSink {
   void cvel(int b, float wx, float wy, float wz, float vx, float vy, float vz) {
     float v[6] = {wx,wy,wz,vx,vy,vz}; std::memcpy(cv + 6*b, v, sizeof v); }
   void com(float x, float y, float z) { cm[0]=x; cm[1]=y; cm[2]=z; }
+  void vel_p(int, float, float, float, float, float, float) {}
 };
 
 extern "C" void host_fk_h1(const float* q, const float* qd, int n, float* xp, float* xq, float* sp, float* sm,

@@ -1,0 +1,204 @@
+"""GPU parity: StickFigureA3 step tail (K1 fused + K2/A3), its multi-step replay and the randomised reset, through
+the C ABI, against (a) the fixture produced by the reference's own WalkingTask code and (b) the float64 oracle."""
+import numpy as np
+import pytest
+
+import a3_common as A
+from conftest import a3_random_states, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _task(model, n, seed=0, env_id0=0):
+    from olympics_mujoco_b200 import kernels as Kn
+    from olympics_mujoco_b200.tasks.phase_clock import phase_clock_lut
+    from oracle import a3 as OA
+    dm = Kn.DeviceModel(model)
+    return Kn.A3Task(dm, n, phase_clock_lut(), OA.init_qpos(), seed=seed, env_id0=env_id0)
+
+
+def _soa_t(x):
+    """[n, T, C] numpy -> [T, C, n] float32 CUDA."""
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(np.transpose(x, (1, 2, 0)), dtype=np.float32), device="cuda")
+
+
+@pytest.mark.parametrize("multi_step", [False, True])
+def test_a3_step_vs_reference_task_fixture(a3_model, multi_step):
+    import torch
+    gold = A.golden()
+    n, T = gold["step_done"].shape
+    task = _task(a3_model, n)
+    task.ints.copy_(torch.as_tensor(gold["reset_ints"].T.astype(np.int32)))
+    task.sequence.copy_(torch.as_tensor(gold["reset_sequence"].reshape(n, 80).T.astype(np.float32)))
+    qpos, qvel, con = _soa_t(gold["step_qpos"]), _soa_t(gold["step_qvel"]), _soa_t(A.contact4(gold["step_contact"]))
+    if multi_step:
+        out = task.step(qpos, qvel, con)
+        o = {k: v.cpu().numpy() for k, v in out.items()}
+        ints_last = task.ints.cpu().numpy().T
+        np.testing.assert_array_equal(ints_last, gold["step_ints"][:, -1])
+    else:
+        o = dict(obs=np.zeros((T, 41, n), np.float32), terms=np.zeros((T, 6, n), np.float32),
+                 reward=np.zeros((T, n), np.float32), done=np.zeros((T, n), np.uint8))
+        for t in range(T):
+            out = task.step(qpos[t], qvel[t], con[t])
+            for k in o:
+                o[k][t] = out[k].cpu().numpy()
+            np.testing.assert_array_equal(task.ints.cpu().numpy().T, gold["step_ints"][:, t], err_msg=f"step {t}")
+    np.testing.assert_array_equal(o["done"].T.astype(bool), gold["step_done"])
+    assert_close(np.transpose(o["terms"], (2, 0, 1)), gold["step_terms"], "terms")
+    assert_close(o["reward"].T, gold["step_terms"].sum(axis=2), "reward")
+    assert_close(np.transpose(o["obs"], (2, 0, 1))[:, :, 33:], gold["step_goal"], "goal steps")
+    for e in range(2):                                                 # full observation vs the float64 oracle
+        _, ref_obs, _ = A.oracle_obs(a3_model, gold, e, upto=120)
+        assert_close(o["obs"][:120, :, e], ref_obs, "obs")
+
+
+def test_a3_reset_vs_reference_task_fixture(a3_model):
+    import torch
+    gold = A.golden()
+    n = gold["reset_qpos"].shape[0]
+    task = _task(a3_model, n, seed=int(gold["seed"]))
+    qpos, qvel = torch.zeros((25, n), device="cuda"), torch.zeros((24, n), device="cuda")
+    obs = task.reset(qpos, qvel, iteration_count=float(gold["iteration_count"]))
+    np.testing.assert_array_equal(task.ints.cpu().numpy().T, gold["reset_ints"])
+    assert_close(qpos.cpu().numpy().T, gold["reset_qpos"], "qpos")
+    assert_close(qvel.cpu().numpy().T, gold["reset_qvel"], "qvel")
+    assert_close(task.sequence.cpu().numpy().T.reshape(n, 20, 4), gold["reset_sequence"], "sequence")
+    assert_close(obs.cpu().numpy().T, gold["reset_obs"], "obs")
+    assert np.array_equal(task.reset_count.cpu().numpy(), np.ones(n, np.int32))
+    # masked reset: only env 1 and 4 draw again (counter 1), the others keep their state
+    before = task.ints.clone()
+    mask = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    mask[[1, 4]] = 1
+    task.reset(qpos, qvel, mask=mask, iteration_count=float(gold["iteration_count"]))
+    assert np.array_equal(task.reset_count.cpu().numpy(), [1, 2, 1, 1, 2, 1])
+    keep = [0, 2, 3, 5]
+    assert torch.equal(task.ints[:, keep], before[:, keep])
+    from oracle import a3 as OA
+    for e in (1, 4):
+        q, v, ts, ob = OA.reset(a3_model, int(gold["seed"]), e, 1, iteration_count=float(gold["iteration_count"]))
+        assert_close(qpos[:, e].cpu().numpy(), q, "qpos (second reset)")
+        assert list(task.ints[:, e].cpu().numpy()) == [ts.phase, ts.t1, ts.t2, ts.target_reached_frames, ts.mode,
+                                                       ts.seq_len, int(ts.target_reached)]
+
+
+def test_a3_random_states_large_with_fk_outputs(a3_model):
+    """4096 envs: reset on the GPU, then one step on random post-physics states with the MjData fields written;
+    a sample of envs is replayed through the float64 oracle.  Integer / bool outputs must be identical except where
+    the float64 decision value itself lies within 2e-6 of its threshold (fp32 rounding of the FK)."""
+    import torch
+    from oracle import a3 as OA
+    from oracle import kinematics as K
+    from olympics_mujoco_b200.tasks.phase_clock import phase_clock_lut
+    n, seed = 4096, 77
+    task = _task(a3_model, n, seed=seed, env_id0=1000)
+    qpos, qvel = torch.zeros((25, n), device="cuda"), torch.zeros((24, n), device="cuda")
+    task.reset(qpos, qvel, iteration_count=5000.0)
+    ints0 = task.ints.cpu().numpy().T.copy()
+    rng = np.random.default_rng(5)
+    q0 = qpos.cpu().numpy().T.astype(np.float64)
+    q = q0 + rng.normal(0, 0.05, q0.shape)
+    q[:, 2] = rng.uniform(0.5, 1.5, n)                                  # some envs below the done height
+    v = rng.normal(0, 1.0, (n, 24))
+    q, v = q.astype(np.float32), v.astype(np.float32)
+    fmax = a3_model.total_mass * 9.8 * 0.5
+    c5 = np.stack([rng.uniform(0, 2 * fmax, n), rng.uniform(0, 2 * fmax, n), rng.uniform(-0.01, 0.01, n),
+                   rng.random(n) < 0.7, rng.random(n) < 0.05], axis=1).astype(np.float32)
+    want = ("obs", "terms", "reward", "done", "xpos", "xquat", "site_xpos", "site_xmat", "cvel")
+    out = task.step(torch.as_tensor(q.T.copy(), device="cuda"), torch.as_tensor(v.T.copy(), device="cuda"),
+                    torch.as_tensor(A.contact4(c5).T.copy(), device="cuda"), want=want)
+    o = {k: x.cpu().numpy() for k, x in out.items()}
+    ints1 = task.ints.cpu().numpy().T
+    assert set(ints0[:, 4]) == {0, 1} and 0.1 < (ints0[:, 4] == 0).mean() < 0.3          # 20 % STANDING
+    assert o["done"].any() and not o["done"].all()
+    ref = K.forward(a3_model, q.astype(np.float64), v.astype(np.float64))
+    assert_close(o["xpos"].T.reshape(n, 17, 3), ref["xpos"], "xpos")
+    assert_close(o["xquat"].T.reshape(n, 17, 4), ref["xquat"], "xquat")
+    assert_close(o["site_xpos"].T.reshape(n, 2, 3), ref["site_xpos"], "site_xpos")
+    assert_close(o["site_xmat"].T.reshape(n, 2, 3, 3), ref["site_xmat"], "site_xmat")
+    assert_close(o["cvel"].T.reshape(n, 17, 6), ref["cvel"], "cvel")
+    lut = phase_clock_lut()
+    sample = rng.choice(n, 96, replace=False)
+    excused = 0
+    for e in sample:
+        _, _, ts, _ = OA.reset(a3_model, seed, 1000 + int(e), 0, iteration_count=5000.0)
+        assert [ts.phase, ts.t1, ts.t2, ts.target_reached_frames, ts.mode, ts.seq_len, int(ts.target_reached)] == list(ints0[e])
+        c = c5[e].astype(np.float64)
+        con = OA.Contact(l_grf=c[0], r_grf=c[1], min_z=c[2], foot_contact=bool(c[3]), bad_collision=bool(c[4]))
+        seq_t1 = ts.sequence[ts.t1][:3].copy()
+        obs, total, done, terms = OA.step_tail(a3_model, q[e].astype(np.float64), v[e].astype(np.float64), ts, con, lut)
+        lp, rp = ref["site_xpos"][e, 1], ref["site_xpos"][e, 0]
+        margin = min(abs(np.linalg.norm(lp - seq_t1) - 0.2), abs(np.linalg.norm(rp - seq_t1) - 0.2),
+                     abs(ref["xpos"][e, 1, 2] - min(lp[2], rp[2]) - 0.6))
+        if margin < 2e-6:
+            excused += 1
+            continue
+        assert [ts.phase, ts.t1, ts.t2, ts.target_reached_frames, ts.mode, ts.seq_len, int(ts.target_reached)] == list(ints1[e])
+        assert bool(o["done"][e]) == done
+        assert_close(o["obs"][:, e], obs, "obs")
+        assert_close(o["terms"][:, e], terms, "terms")
+        assert_close(o["reward"][e], total, "reward")
+    assert excused <= 2
+
+
+def test_a3_edge_sizes(a3_model):
+    import torch
+    for n in (0, 1, 63, 65):
+        task = _task(a3_model, n)
+        qpos, qvel = torch.zeros((25, n), device="cuda"), torch.zeros((24, n), device="cuda")
+        obs = task.reset(qpos, qvel)
+        out = task.step(qpos, qvel, torch.zeros((4, n), device="cuda"))
+        torch.cuda.synchronize()
+        assert obs.shape == (41, n) and out["obs"].shape == (41, n) and out["done"].shape == (n,)
+        if n:
+            assert torch.isfinite(out["obs"]).all() and torch.isfinite(out["reward"]).all()
+    task = _task(a3_model, 8)
+    out = task.step(torch.zeros((0, 25, 8), device="cuda"), torch.zeros((0, 24, 8), device="cuda"),
+                    torch.zeros((0, 4, 8), device="cuda"))
+    assert out["obs"].shape == (0, 41, 8)
+
+
+def test_stick_figure_a3_env_api(a3_model):
+    """reset / step through the reference-facing class with an attached (scripted) physics callable."""
+    import torch
+    from olympics_mujoco_b200 import StickFigureA3
+    from oracle import a3 as OA
+    from olympics_mujoco_b200.tasks.phase_clock import phase_clock_lut
+    n = 5
+    env = StickFigureA3(n_envs=n, seed=3, algorithm_type="AlgorithmType.REINFORCEMENT_LEARNING")
+    assert env.observation_space.shape == (41,) and env.action_space.shape == (12,)
+    assert len(env.robot.mirrored_obs) == 41 and env.task._period == 88 and env.task.delay_frames == 30
+    with pytest.raises(RuntimeError):
+        env.step(np.zeros((n, 12)))
+    obs0 = env.reset()
+    assert obs0.shape == (n, 41)
+    rng = np.random.default_rng(1)
+    script = []
+
+    def physics(e, target):
+        assert target.shape == (n, 12)
+        q = e.qpos.clone() + torch.as_tensor(rng.normal(0, 0.01, (25, n)), dtype=torch.float32, device="cuda")
+        v = e.qvel.clone() + torch.as_tensor(rng.normal(0, 0.1, (24, n)), dtype=torch.float32, device="cuda")
+        c = torch.as_tensor(np.stack([rng.uniform(0, 300, n), rng.uniform(0, 300, n), rng.uniform(-0.01, 0.01, n),
+                                      rng.integers(0, 2, n).astype(np.float64)]), dtype=torch.float32, device="cuda")
+        script.append((q.cpu().numpy().T.astype(np.float64), v.cpu().numpy().T.astype(np.float64), c.cpu().numpy().T))
+        return q, v, c
+    env.attach_dynamics(physics)
+    lut = phase_clock_lut()
+    states = [OA.reset(a3_model, 3, e, 0, iteration_count=np.inf) for e in range(n)]
+    for e in range(n):
+        assert_close(obs0[e].cpu().numpy(), states[e][3], "reset obs")
+    for _ in range(3):
+        obs, rew, done, rewards = env.step(np.zeros((n, 12), np.float32))
+        assert obs.shape == (n, 41) and rew.shape == (n,) and done.dtype == torch.bool and len(rewards) == 6
+        q, v, c = script[-1]
+        for e in range(n):
+            con = OA.Contact(l_grf=c[e, 0], r_grf=c[e, 1], min_z=c[e, 2], foot_contact=bool(int(c[e, 3]) & 1),
+                             bad_collision=bool(int(c[e, 3]) & 2))
+            ro, rt, rd, rterms = OA.step_tail(a3_model, q[e], v[e], states[e][2], con, lut)
+            assert_close(obs[e].cpu().numpy(), ro, "obs"); assert_close(rew[e].cpu().numpy(), rt, "reward")
+            assert bool(done[e]) == rd
+            assert_close(rewards["step_reward"][e].cpu().numpy(), rterms[4], "step_reward")
+    single = StickFigureA3(seed=3)
+    assert single.reset().shape == (41,)

@@ -147,3 +147,62 @@ def test_synthetic_dataset_is_non_terminal(h1_model):
         if h1_model.jnt_limited[jid]:
             lo, hi = h1_model.jnt_range[jid]
             assert d["q_" + j].min() >= lo and d["q_" + j].max() <= hi
+
+
+def test_a3_task_device_functions_on_host(a3_model):
+    """The A3 step-tail device functions (csrc/om_a3_task.cuh, fp32), compiled as plain C++, against the fixture
+    produced by the reference's own WalkingTask: integer state and done flags bit-exact, observations and
+    reward terms within 1e-5.  Checks the kernel arithmetic in a container without a GPU (test-only harness)."""
+    import a3_common as A
+    from olympics_mujoco_b200 import build
+    from oracle import a3 as OA
+    build.generate()
+    d = Path(tempfile.mkdtemp())
+    csrc = ROOT / "olympics_mujoco_b200" / "csrc"
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-I", str(csrc), str(ROOT / "tests/host/a3_host_harness.cpp"),
+                           "-o", str(d / "a3.so")])
+    lib = ctypes.CDLL(str(d / "a3.so"))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    gold = A.golden()
+    lut = np.ascontiguousarray(A.lut6())
+    consts = (P(lut), OA.PERIOD, OA.DELAY_FRAMES, ctypes.c_double(0.2), ctypes.c_double(0.80), ctypes.c_double(0.01),
+              ctypes.c_float(a3_model.total_mass * 9.8 * 0.5))
+    n_env, T = gold["step_done"].shape
+    it = float(gold["iteration_count"])
+    h = float(np.clip((it - 3000) / 8000, 0, 1) * 0.1)
+    init = OA.init_qpos().astype(np.float32)
+    for e in range(n_env):
+        q, v = np.zeros(25, np.float32), np.zeros(24, np.float32)
+        ints, seq, obs0 = np.zeros(7, np.int32), np.zeros(80, np.float32), np.zeros(41, np.float32)
+        lib.host_a3_reset(*consts, P(init), ctypes.c_ulonglong(int(gold["seed"])), e, 0, ctypes.c_float(h), P(q), P(v),
+                          P(ints), P(seq), P(obs0))
+        assert list(ints) == list(gold["reset_ints"][e])
+        assert_close(q, gold["reset_qpos"][e], "reset qpos"); assert_close(v, gold["reset_qvel"][e], "reset qvel")
+        assert_close(seq.reshape(20, 4), gold["reset_sequence"][e], "sequence")
+        ref_obs0, ref_obs, ref_total = A.oracle_obs(a3_model, gold, e, upto=T if e < 2 else 40)
+        assert_close(obs0, ref_obs0, "reset obs")
+        # step replay from the REFERENCE's reset state (so that the two checks are independent)
+        ints = gold["reset_ints"][e].astype(np.int32)
+        seq = np.ascontiguousarray(gold["reset_sequence"][e].reshape(-1), np.float32)
+        qpos, qvel = np.ascontiguousarray(gold["step_qpos"][e]), np.ascontiguousarray(gold["step_qvel"][e])
+        con = np.ascontiguousarray(A.contact4(gold["step_contact"][e]))
+        obs, terms = np.zeros((T, 41), np.float32), np.zeros((T, 6), np.float32)
+        reward, done = np.zeros(T, np.float32), np.zeros(T, np.uint8)
+        # per-step state trace: run the harness one step at a time
+        trace = []
+        for t in range(T):
+            lib.host_a3_rollout(*consts, P(qpos[t]), P(qvel[t]), P(con[t]), 1, P(ints), P(seq), P(obs[t]), P(terms[t]),
+                                P(reward[t:t + 1]), P(done[t:t + 1]))
+            trace.append(ints.copy())
+        np.testing.assert_array_equal(np.array(trace), gold["step_ints"][e])
+        np.testing.assert_array_equal(done.astype(bool), gold["step_done"][e])
+        assert_close(terms, gold["step_terms"][e], "terms")
+        assert_close(reward, gold["step_terms"][e].sum(axis=1), "reward")
+        assert_close(obs[:, 33:], gold["step_goal"][e], "goal steps")
+        assert_close(obs[:len(ref_obs)], ref_obs, "obs")
+        # the multi-step entry (T steps in one call) gives the same answer as T single steps
+        ints2 = gold["reset_ints"][e].astype(np.int32)
+        obs2, terms2 = np.zeros_like(obs), np.zeros_like(terms)
+        reward2, done2 = np.zeros_like(reward), np.zeros_like(done)
+        lib.host_a3_rollout(*consts, P(qpos), P(qvel), P(con), T, P(ints2), P(seq), P(obs2), P(terms2), P(reward2), P(done2))
+        assert np.array_equal(obs2, obs) and np.array_equal(done2, done) and np.array_equal(ints2, trace[-1])

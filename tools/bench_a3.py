@@ -1,0 +1,92 @@
+"""Timing of BASELINE.json configs[2]: A3 PPO walk rollout (obs / reward / done + discounted returns),
+16384 envs x 64-step horizon on one B200.  Prints one JSON line (a measurement aid; the driver-facing headline
+bench is bench.py)."""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+BYTES_PER_ENV_STEP = 490          # SURVEY.md 8(d) config 3 (FK fused, not materialised)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=16384)
+    ap.add_argument("--horizon", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--per-step", action="store_true", help="launch the step kernel once per env step (the live-rollout pattern)")
+    args = ap.parse_args()
+    from olympics_mujoco_b200 import kernels as Kn
+    from olympics_mujoco_b200 import mjcf
+    from olympics_mujoco_b200.tasks.phase_clock import phase_clock_lut
+    from olympics_mujoco_b200.environments.stick_figure_a3 import HALF_SITTING_DEG
+    model = mjcf.load_builtin("stick_figure_a3")
+    n, T = args.envs, args.horizon
+    dm = Kn.DeviceModel(model)
+    init = np.array([0, 0, 0.81, 1, 0, 0, 0] + [q * np.pi / 180 for q in HALF_SITTING_DEG])
+    task = Kn.A3Task(dm, n, phase_clock_lut(), init, seed=0)
+    qpos0, qvel0 = Kn.soa(25, n), Kn.soa(24, n)
+    task.reset(qpos0, qvel0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    qpos = qpos0[None] + 0.02 * torch.randn((T, 25, n), device="cuda", generator=g).cumsum(0)
+    qvel = torch.randn((T, 24, n), device="cuda", generator=g).clamp_(-10, 10)
+    fmax = model.total_mass * 9.8 * 0.5
+    con = torch.stack([torch.rand((T, n), device="cuda", generator=g) * 2 * fmax, torch.rand((T, n), device="cuda", generator=g) * 2 * fmax,
+                       (torch.rand((T, n), device="cuda", generator=g) - 0.5) * 0.02,
+                       (torch.rand((T, n), device="cuda", generator=g) < 0.7).float()
+                       + 2 * (torch.rand((T, n), device="cuda", generator=g) < 0.01).float()], dim=1).contiguous()
+    values = torch.randn((T + 1, n), device="cuda", generator=g)
+    out = dict(obs=torch.empty((T, 41, n), device="cuda"), terms=torch.empty((T, 6, n), device="cuda"),
+               reward=torch.empty((T, n), device="cuda"), done=torch.empty((T, n), dtype=torch.uint8, device="cuda"))
+    ints0, seq0 = task.ints.clone(), task.sequence.clone()
+    mom = torch.zeros(3, dtype=torch.float64, device="cuda")
+
+    def step(ev=None):
+        task.ints.copy_(ints0)
+        if ev:
+            ev[0].record()
+        if args.per_step:
+            for t in range(T):
+                task.step(qpos[t], qvel[t], con[t], out={k: v[t] for k, v in out.items()})
+        else:
+            task.step(qpos, qvel, con, out=out)
+        if ev:
+            ev[1].record()
+        ret, adv = Kn.ppo_returns(out["reward"], values[:-1], 0.99, path_end=out["done"], v_next=values[1:])
+        mom.zero_()
+        Kn.moments_scalar(adv, out=mom)
+        stats = Kn.adv_stats(mom, unbiased=True, eps=1e-5)
+        Kn.normalize(adv, stats, out=adv)
+        return ret, adv
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    Kn.reset_launch_count()
+    t0.record()
+    for i in range(args.steps):
+        step(evs[i])
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / args.steps
+    kms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {"hbm_gbs": 6650.0}
+    achieved = BYTES_PER_ENV_STEP * n * T / (kms * 1e-3) / 1e9
+    print(json.dumps({"workload": f"A3 PPO walk rollout {n} envs x {T} steps (configs[2])", "per_step_launches": args.per_step,
+                      "value": n * T / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "task_kernel_ms": kms,
+                      "gpu_launches": Kn.launch_count(),
+                      "roofline": {"bound": "hbm", "kernel": "a3_task_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                                   "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "bytes_per_env_step": BYTES_PER_ENV_STEP}}))
+
+
+if __name__ == "__main__":
+    main()

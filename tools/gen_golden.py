@@ -224,6 +224,210 @@ def gen_running_mean_std():
              count=rms.count)
     print("running_mean_std_ref: mean", rms.mean)
 
+# ---------------------------------------------------------------- 7. WalkingTask (tasks/walking_task.py)
+class _FakeRandom:
+    """np.random stand-in for WalkingTask.reset / generate_step_sequence: returns the Philox-contract draws
+    u[53..57] (oracle/a3.py reset) in the order the reference consumes them."""
+
+    def __init__(self, u):
+        self.u = u
+
+    def choice(self, a, p=None):
+        a = list(a)
+        if p is not None:                      # mode: STANDING 0.2 / FORWARD 0.8 (walking_task.py:362-364)
+            return a[0] if self.u[54] < 0.2 else a[3]
+        if len(a) == 2 and a[0] == 0:          # initial phase in {0, period/2} (:354)
+            return a[0] if self.u[53] < 0.5 else a[1]
+        return a[0] if self.u[55] < 0.5 else a[1]          # step-height sign (:379)
+
+    def uniform(self, lo, hi):
+        return lo + (hi - lo) * self.u[56]     # first-step y (:154,158)
+
+    def randint(self, lo, hi):
+        return lo if self.u[57] < 0.5 else lo + 1          # c in {2,3} (:164)
+
+
+class _NpProxy:
+    """`np` as seen by the reference module, with `.random` replaced."""
+
+    def __init__(self, rnd):
+        self.random = rnd
+
+    def __getattr__(self, k):
+        return getattr(np, k)
+
+
+def gen_a3_task():
+    import os
+    from olympics_mujoco_b200 import mjcf
+    from oracle import a3 as OA
+    from oracle import kinematics as K
+    from oracle import tf3 as T3
+    model = mjcf.load_builtin("stick_figure_a3")
+    ids = OA.A3Ids(model)
+    # transforms3d stand-in built on the oracle restatement (oracle/tf3.py): pins the task CONTROL FLOW and
+    # reward arithmetic to the reference's own code; the tf3 formulas themselves stay "parity unpinned".
+    tf = stub("transforms3d")
+    tf.euler = stub("transforms3d.euler", euler2quat=lambda a, b, c: T3.euler2quat(a, b, c),
+                    quat2euler=lambda q: tuple(float(x) for x in T3.quat2euler(np.asarray(q))),
+                    euler2mat=lambda a, b, c: T3.rotz(c),
+                    mat2euler=lambda m: tuple(float(x) for x in T3.mat2euler(np.asarray(m))))
+    tf.quaternions = stub("transforms3d.quaternions", quat2mat=lambda q: T3.quat2mat(np.asarray(q)),
+                          mat2quat=lambda m: T3.mat2quat(m))
+
+    def compose(t, r, z):
+        a = np.eye(4)
+        a[:3, :3] = np.asarray(r) * np.asarray(z)[None, :]
+        a[:3, 3] = t
+        return a
+    tf.affines = stub("transforms3d.affines", compose=compose)
+    rw = load("ref_rewards_a3", "olympic_mujoco/tasks/rewards.py")
+    pkg = stub("olympic_mujoco"); pkg.__path__ = []
+    tasks = stub("olympic_mujoco.tasks", rewards=rw); tasks.__path__ = []
+    sys.modules["olympic_mujoco.tasks.rewards"] = rw
+    cwd = os.getcwd()
+    os.chdir(REF)                                   # WalkingTask.__init__ opens ./footstep_plans.txt
+    try:
+        wt = load("ref_walking_task", "olympic_mujoco/tasks/walking_task.py")
+    finally:
+        os.chdir(cwd)
+
+    class Con:
+        def __init__(self, z):
+            self.pos = np.array([0.0, 0.0, z])
+
+    class Client:
+        """MujocoRobotInterface getters (interfaces/mujoco_robot_interface.py:239-399) over the oracle's FK; the
+        contact-solver outputs are injected per step."""
+
+        def __init__(self):
+            self.model = types.SimpleNamespace(geom=lambda name: types.SimpleNamespace(pos=np.zeros(3)))
+
+        def set(self, qpos, qvel, contact):
+            self.fk = K.forward(model, qpos[None], qvel[None])
+            self.c = contact
+
+        def get_robot_mass(self):
+            return model.total_mass
+
+        def get_object_xpos_by_name(self, name, typ):
+            if typ == "OBJ_BODY":
+                return self.fk["xpos"][0, model.body_id(name)]
+            return self.fk["site_xpos"][0, model.site_id(name)]
+
+        def get_object_xquat_by_name(self, name, typ):
+            if typ == "OBJ_BODY":
+                return self.fk["xquat"][0, model.body_id(name)]
+            return T3.mat2quat(self.fk["site_xmat"][0, model.site_id(name)])
+
+        def _vel(self, b):
+            v = K.mj_objectVelocity_xbody(model, self.fk["xpos"], self.fk["subtree_com"], self.fk["cvel"], b)[0]
+            return [v[3:6], v[0:3]]
+
+        def get_lfoot_body_vel(self):
+            return self._vel(ids.lfoot)
+
+        def get_rfoot_body_vel(self):
+            return self._vel(ids.rfoot)
+
+        def get_lfoot_body_pos(self):
+            return self.fk["xpos"][0, ids.lfoot]
+
+        def get_rfoot_body_pos(self):
+            return self.fk["xpos"][0, ids.rfoot]
+
+        def get_lfoot_grf(self):
+            return self.c.l_grf
+
+        def get_rfoot_grf(self):
+            return self.c.r_grf
+
+        def check_bad_collisions(self):
+            return self.c.bad_collision
+
+        def check_rfoot_floor_collision(self):
+            return self.c.foot_contact
+
+        def check_lfoot_floor_collision(self):
+            return False
+
+        def get_rfoot_floor_contacts(self):
+            return [(0, Con(self.c.min_z)), (1, Con(self.c.min_z + 0.003))] if self.c.foot_contact else []
+
+        def get_lfoot_floor_contacts(self):
+            return []
+
+    seed, n_env, T = 25, 6, 330
+    rng = np.random.default_rng(5)
+    rec = {k: [] for k in ("qpos", "qvel", "contact", "terms", "done", "ints", "goal", "obs")}
+    reset_rec = {k: [] for k in ("qpos", "qvel", "ints", "sequence", "obs", "u")}
+    f32 = lambda a: np.asarray(a, np.float32).astype(np.float64)
+    for e in range(n_env):
+        u = OA.reset_uniforms(seed, e, 0)
+        qpos0, qvel0, ts0, obs0 = OA.reset(model, seed, e, 0, iteration_count=7000)
+        client = Client()
+        client.set(qpos0, qvel0, OA.Contact())
+        os.chdir(REF)
+        try:
+            task = wt.WalkingTask(client=client, dt=0.025, neutral_foot_orient=np.array([1, 0, 0, 0]),
+                                  root_body="torso", lfoot_body="left_foot", rfoot_body="right_foot", head_body="head")
+        finally:
+            os.chdir(cwd)
+        task._goal_height_ref, task._total_duration = 0.80, 1.1          # StickFigureA3.py:110-113
+        task._swing_duration, task._stance_duration = 0.75, 0.35
+        wt.np = _NpProxy(_FakeRandom(u))
+        task.reset(iter_count=7000)
+        wt.np = np
+        seq = np.zeros((OA.MAX_STEPS, 4))
+        seq[:len(task.sequence)] = np.array(task.sequence)
+        mode = OA.STANDING if task.mode == wt.WalkModes.STANDING else OA.FORWARD
+        reset_rec["qpos"].append(qpos0); reset_rec["qvel"].append(qvel0); reset_rec["u"].append(u)
+        reset_rec["ints"].append([task._phase, task.t1, task.t2, task.target_reached_frames, mode,
+                                  len(task.sequence), int(task.target_reached)])
+        reset_rec["sequence"].append(seq); reset_rec["obs"].append(obs0)
+        # a dataset-shaped walk: the root advances along its heading so that feet pass over the targets
+        yaw = T3.quat2euler(qpos0[3:7])[2]
+        speed = rng.uniform(0.1, 0.2) * 0.025
+        q, v = qpos0.copy(), qvel0.copy()
+        for k in ("qpos", "qvel", "contact", "terms", "done", "ints", "goal", "obs"):
+            rec[k].append([])
+        for t in range(T):
+            q = q.copy()
+            q[0] += speed * np.cos(yaw); q[1] += speed * np.sin(yaw)
+            q[2] = 1.34 + 0.02 * np.sin(0.2 * t) - (0.75 if (e == 3 and t > 300) else 0.0)     # env 3 falls
+            q[7:] = np.clip(q[7:] + rng.normal(0, 0.01, 18), OA.init_qpos()[7:] - 0.5, OA.init_qpos()[7:] + 0.5)
+            dq = rng.normal(0, 0.002, 4); dq[3] += 0.002 * np.sin(0.05 * t)
+            q[3:7] = q[3:7] + dq                                           # un-normalised on purpose
+            v = np.clip(v + rng.normal(0, 0.2, 24), -10, 10)
+            if t % 37 == 5:
+                v[6:18] *= 0.01                                            # near-still feet: velocity clock saturates
+            q, v = f32(q), f32(v)
+            fmax = model.total_mass * 9.8 * 0.5
+            con = OA.Contact(l_grf=float(f32(rng.uniform(0, 2 * fmax))), r_grf=float(f32(rng.uniform(0, 2 * fmax))),
+                             min_z=float(f32(rng.uniform(-0.01, 0.01))), foot_contact=bool(rng.random() < 0.7),
+                             bad_collision=bool(rng.random() < 0.02))
+            client.set(q, v, con)
+            task.step()
+            terms = task.calc_reward(None, None, None)
+            done = task.done()
+            rec["qpos"][-1].append(q); rec["qvel"][-1].append(v)
+            rec["contact"][-1].append([con.l_grf, con.r_grf, con.min_z, float(con.foot_contact), float(con.bad_collision)])
+            rec["terms"][-1].append([float(x) for x in terms.values()])
+            rec["done"][-1].append(bool(done))
+            rec["ints"][-1].append([task._phase, task.t1, task.t2, task.target_reached_frames, mode, len(task.sequence),
+                                    int(task.target_reached)])
+            rec["goal"][-1].append(np.concatenate([task._goal_steps_x, task._goal_steps_y, task._goal_steps_z,
+                                                   task._goal_steps_theta]))
+    out = {"step_" + k: np.array(v) for k, v in rec.items() if k != "obs"}
+    for k in ("step_qpos", "step_qvel", "step_contact"):          # fp32-representable by construction
+        assert np.array_equal(out[k], out[k].astype(np.float32).astype(np.float64))
+        out[k] = out[k].astype(np.float32)
+    out.update({"reset_" + k: np.array(v) for k, v in reset_rec.items()})
+    np.savez_compressed(OUT / "a3_task_ref.npz", seed=seed, iteration_count=7000, **out)
+    ints = out["step_ints"]
+    print("a3_task_ref: steps", out["step_terms"].shape, "max t1", ints[..., 1].max(), "done frac",
+          out["step_done"].mean(), "modes", out["reset_ints"][:, 4])
+
 
 if __name__ == "__main__":
     gen_trajectory()
@@ -232,3 +436,4 @@ if __name__ == "__main__":
     gen_networks()
     gen_saved_rollouts()
     gen_running_mean_std()
+    gen_a3_task()
