@@ -212,6 +212,32 @@ int om_a3_reset(const OmModel* m, const OmA3Task* task, uint64_t seed, uint32_t 
                 float* obs, int n, int ld, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K4: discriminator reward  r = -log(1 - sigmoid(D(s)) + 1e-8)  (GAIL.make_discrim_reward,
+ * imitation_lib/imitation/gail_TRPO.py:320-327; VAIL discrim_output vail_TRPO.py:18-21) for the two networks
+ * the reference configures for UnitreeH1 (examples/imitation_learning/utils.py:151-179, confs.yaml:113-130):
+ *   kind 0 VAIL  VariationalNet (networks.py:258-284): 32 -relu-> 256 -relu-> 128 -> mu[128], logvar[128],
+ *                z = mu + exp(logvar/2) * eps (:21-24), d = wd . z + bd
+ *   kind 1 GAIL  DiscriminatorNetwork (:208-234): 32 -tanh-> 512 -tanh-> 256 -> 1
+ * Weights are HOST pointers, row-major [out][in] float32 (torch.nn.Linear.weight), copied at create time.
+ * The contraction runs on tcgen05 tensor cores as 3xTF32 with fp32 accumulation (fp32-level results). */
+typedef struct OmDiscDesc {
+  int kind, n_in, n_h1, n_h2, z_size;
+  const float* w1; const float* b1;      /* [n_h1][n_in], [n_h1] */
+  const float* w2; const float* b2;      /* [n_h2][n_h1], [n_h2] */
+  const float* wmu; const float* bmu;    /* VAIL: [z][n_h2], [z] */
+  const float* wlv; const float* blv;    /* VAIL: [z][n_h2], [z] */
+  const float* wd; const float* bd;      /* VAIL decoder [1][z] / GAIL output layer [1][n_h2]; [1] */
+} OmDiscDesc;
+typedef struct OmDisc OmDisc;
+int om_disc_create(const OmDiscDesc* desc, OmDisc** out);
+void om_disc_destroy(OmDisc* d);
+/* s [n_in][ld] observations (SoA); mean / std [n_in] = the Standardizer snapshot to apply (networks.py:73-74; the
+ * running sums are updated by the caller with om_moments); eps [z][ld] = the reparameterisation noise (VAIL; NULL
+ * means z = mu); reward [ld]; d_out [ld] (may be NULL) = the raw discriminator logit. */
+int om_disc_reward(const OmDisc* d, const float* s, const float* mean, const float* std, const float* eps, int n, int ld,
+                   float* reward, float* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K5: returns / advantages over a time-major rollout buffer [T][ld].
  * om_ppo_returns: PPOBuffer.finish_path (rl/algos/ppo.py:68-84) with the bootstrap of :195-196.
  *   path_end[t][i] (may be NULL): 0 = the path continues, 1 = it terminated at step t (bootstrap 0),

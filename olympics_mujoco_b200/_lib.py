@@ -59,6 +59,11 @@ class OmA3Out(C.Structure):
                 ("cvel", C.c_void_p)]
 
 
+class OmDiscDesc(C.Structure):
+    _fields_ = [("kind", C.c_int), ("n_in", C.c_int), ("n_h1", C.c_int), ("n_h2", C.c_int), ("z_size", C.c_int)] + \
+               [(k, C.c_void_p) for k in ("w1", "b1", "w2", "b2", "wmu", "bmu", "wlv", "blv", "wd", "bd")]
+
+
 _P, _I, _F, _D = C.c_void_p, C.c_int, C.c_float, C.c_double
 _U64, _U32 = C.c_uint64, C.c_uint32
 
@@ -85,6 +90,9 @@ PROTOTYPES = {
     "om_a3_task_destroy": (None, [_P]),
     "om_a3_task_step": (_I, [_P, _P, _P, _P, _P, _I, C.POINTER(OmA3State), C.POINTER(OmA3Out), _I, _I, _P]),
     "om_a3_reset": (_I, [_P, _P, _U64, _U32, _P, _P, _D, _P, _P, C.POINTER(OmA3State), _P, _I, _I, _P]),
+    "om_disc_create": (_I, [C.POINTER(OmDiscDesc), C.POINTER(_P)]),
+    "om_disc_destroy": (None, [_P]),
+    "om_disc_reward": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "om_ppo_returns": (_I, [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P]),
     "om_gae": (_I, [_P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P, _P]),
     "om_moments": (_I, [_P, _I, _I, _I, _I, _P, _P]),

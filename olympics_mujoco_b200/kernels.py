@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import OmA3Out, OmA3State, OmA3TaskDesc, OmH1Spec, OmModelDesc, OmPlayOut, OmPlayState, check
+from ._lib import OmA3Out, OmA3State, OmA3TaskDesc, OmDiscDesc, OmH1Spec, OmModelDesc, OmPlayOut, OmPlayState, check
 from .mjcf import KinematicModel
 
 
@@ -291,6 +291,51 @@ class A3Task:
         check(_lib.load().om_a3_task_step(self.dm.handle, self.handle, _p(qpos, torch.float32), _p(qvel, torch.float32),
                                           _p(contact, torch.float32), T, C.byref(st), C.byref(po), n, max(n, 1), _stream()))
         return out
+
+
+# ------------------------------------------------------------------------------------------- discriminator (K4)
+class Discriminator:
+    """OmDisc handle.  ``params``: dict of float32 arrays in torch.nn.Linear layout ([out, in] weights):
+    VAIL  w1 b1 w2 b2 wmu bmu wlv blv wd bd   (32-256-128-z128-1)
+    GAIL  w1 b1 w2 b2 w3 b3                   (32-512-256-1)"""
+
+    def __init__(self, kind, params):
+        _lib.require_cuda()
+        kind = {"vail": 0, "gail": 1}[kind.lower()] if isinstance(kind, str) else int(kind)
+        f = lambda k: np.ascontiguousarray(params[k], dtype=np.float32)
+        keep = dict(w1=f("w1"), b1=f("b1"), w2=f("w2"), b2=f("b2"))
+        if kind == 0:
+            keep.update(wmu=f("wmu"), bmu=f("bmu"), wlv=f("wlv"), blv=f("blv"), wd=f("wd"), bd=f("bd"))
+        else:
+            keep.update(wd=f("w3"), bd=f("b3"))
+        n_h1, n_in = keep["w1"].shape
+        n_h2 = keep["w2"].shape[0]
+        assert keep["w2"].shape[1] == n_h1
+        z = keep["wmu"].shape[0] if kind == 0 else 0
+        desc = OmDiscDesc(kind=kind, n_in=n_in, n_h1=n_h1, n_h2=n_h2, z_size=z,
+                          **{k: v.ctypes.data for k, v in keep.items()})
+        h = C.c_void_p()
+        check(_lib.load().om_disc_create(C.byref(desc), C.byref(h)))
+        self.handle, self.kind, self.n_in, self.z = h, kind, n_in, z
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().om_disc_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def reward(self, s, mean, std, eps=None, want_d=False):
+        """s [32, n] observations (SoA), mean / std [32] float32 device tensors, eps [z, n] or None -> reward [n]
+        (and the raw logit d [n] when ``want_d``)."""
+        n = s.shape[-1]
+        assert s.shape == (self.n_in, n) and (eps is None or eps.shape == (self.z, n))
+        reward = torch.empty(n, device=s.device)
+        d = torch.empty(n, device=s.device) if want_d else None
+        check(_lib.load().om_disc_reward(self.handle, _p(s, torch.float32), _p(mean, torch.float32), _p(std, torch.float32),
+                                         _p(eps, torch.float32), n, max(n, 1), _p(reward), _p(d), _stream()))
+        return (reward, d) if want_d else reward
 
 
 # ------------------------------------------------------------------------------------------- learner side

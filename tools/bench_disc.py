@@ -1,0 +1,60 @@
+"""Timing of BASELINE.json configs[3]: VAIL / GAIL discriminator-reward rollout, 65536 envs (tcgen05 MLP).
+Prints one JSON line per network (measurement aid; the driver-facing bench is bench.py)."""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+FLOP = {"vail": 2 * (32 * 256 + 256 * 128 + 2 * 128 * 128 + 128), "gail": 2 * (32 * 512 + 512 * 256 + 256)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=65536)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    args = ap.parse_args()
+    from olympics_mujoco_b200 import kernels as Kn
+    g = np.load(ROOT / "tests/golden/discriminator_ref.npz")
+    n = args.envs
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    s = torch.randn((32, n), device="cuda", generator=gen)
+    eps = torch.randn((128, n), device="cuda", generator=gen)
+    mean, std = torch.zeros(32, device="cuda"), torch.ones(32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {"bf16_tflops": 1590.0}
+    for kind in ("vail", "gail"):
+        pref = "v_" if kind == "vail" else "g_"
+        names = ("w1", "b1", "w2", "b2", "wmu", "bmu", "wlv", "blv", "wd", "bd") if kind == "vail" else ("w1", "b1", "w2", "b2", "w3", "b3")
+        disc = Kn.Discriminator(kind, {k: g[pref + k] for k in names})
+        e = eps if kind == "vail" else None
+        for _ in range(args.warmup):
+            disc.reward(s, mean, std, eps=e)
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(args.steps):
+            flush.zero_()                                    # L2 flush between timed launches
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            disc.reward(s, mean, std, eps=e)
+            t1.record()
+            torch.cuda.synchronize()
+            tot += t0.elapsed_time(t1)
+        ms = tot / args.steps
+        useful = FLOP[kind] * n / (ms * 1e-3) / 1e12
+        peak_tf32 = peaks["bf16_tflops"] / 2
+        print(json.dumps({"workload": f"{kind.upper()} discriminator reward, {n} envs (configs[3])", "ms": ms,
+                          "value": n / (ms * 1e-3), "unit": "samples/s",
+                          "roofline": {"bound": "tensor", "achieved": useful, "executed_3xtf32": 3 * useful, "unit": "TFLOP/s",
+                                       "peak": peak_tf32, "peak_note": "measured bf16 burst / 2 (TF32 rate)",
+                                       "frac": useful / peak_tf32, "frac_executed": 3 * useful / peak_tf32,
+                                       "flop_per_sample": FLOP[kind]}}))
+
+
+if __name__ == "__main__":
+    main()
