@@ -24,6 +24,9 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 BYTES_PER_ENV_STEP = 1517          # SURVEY.md section 8(d), config 2 (algorithmic HBM bytes of the playback step)
+# dram__bytes_read.sum + dram__bytes_write.sum of play_h1_tp_kernel at 4096 envs x 500 steps, one `ncu --set full`
+# capture (profiles/r01_play_h1_tp_raw.csv: 11.3 MB read + 2491.0 MB written per launch)
+NCU_TRAFFIC_BYTES_4096x500 = 11.327e6 + 2491.07e6
 N_ENVS = 4096
 HORIZON = 500
 GAMMA, LAM = 0.99, 0.97
@@ -121,20 +124,17 @@ def run_ours(args):
     model, table = build_table()
     env = LocoEnvBase.make("UnitreeH1.walk.real", n_envs=n, traj_params=dict(table=table), seed=1234,
                            env_id0=rank * n, device=f"cuda:{local}")
-    roll = env.make_rollout_buffers(T)                         # device-resident [T, C, n] outputs
+    rolls = [env.make_rollout_buffers(T) for _ in range(2)]    # device-resident [T, C, n] outputs, double-buffered for e2e
+    roll = rolls[0]
     g = torch.Generator(device="cuda").manual_seed(7 + rank)
     values = torch.randn((T + 1, n), device="cuda", generator=g)
     values_host = values.cpu().pin_memory()
     last = torch.zeros((T, n), dtype=torch.uint8, device="cuda")
     mom = torch.zeros(3 + 65, dtype=torch.float64, device="cuda")    # advantage [3] + observation [2*32+1]
-    host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in
-            dict(obs=roll["obs"], reward=roll["reward"], fallen=roll["fallen"]).items()}
-    host["adv"] = torch.empty((T, n)).pin_memory()
-    host["v_target"] = torch.empty((T, n)).pin_memory()
     ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
 
-    def hot_step(i=None, vals=values):
+    def hot_step(i=None, vals=values, roll=roll):
         if i is not None:
             ev_k0[i].record()
         out = env.play_trajectory_from_velocity(n_episodes=1, n_steps_per_episode=T, render=False, out=roll)
@@ -178,26 +178,54 @@ def run_ours(args):
     ms_per_step = float(ms) / args.steps
     value = world * n * T / (ms_per_step * 1e-3)
 
-    # ---- end to end through the public API with host buffers
-    def e2e_step():
+    # ---- end to end through the public API with host buffers: every step copies its inputs from pinned host memory
+    # and its results (observations, rewards, flags, advantages, value targets) back to pinned host memory.  The
+    # device->host copy of step i runs on a copy stream while step i+1 computes (two buffer sets); everything,
+    # including the last copy, is inside the timed region.
+    def host_set():
+        h = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in
+             dict(obs=roll["obs"], reward=roll["reward"], fallen=roll["fallen"]).items()}
+        h["adv"] = torch.empty((T, n)).pin_memory()
+        h["v_target"] = torch.empty((T, n)).pin_memory()
+        return h
+    hosts = [host_set(), host_set()]
+    copy_stream = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    copied = [None, None]
+
+    def e2e_step(i):
+        b = i % 2
+        if copied[b] is not None:
+            main.wait_event(copied[b])                         # buffer set b is free again
         vals = values_host.to("cuda", non_blocking=True)
-        out, vt, adv = hot_step(vals=vals)
-        host["obs"].copy_(out["obs"], non_blocking=True)
-        host["reward"].copy_(out["reward"], non_blocking=True)
-        host["fallen"].copy_(out["fallen"], non_blocking=True)
-        host["adv"].copy_(adv, non_blocking=True)
-        host["v_target"].copy_(vt, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-    e2e_steps = max(2, min(args.steps, 5))
-    e2e_step()
+        out, vt, adv = hot_step(vals=vals, roll=rolls[b])
+        done = torch.cuda.Event()
+        done.record(main)
+        copy_stream.wait_event(done)
+        with torch.cuda.stream(copy_stream):
+            for k, src in (("obs", out["obs"]), ("reward", out["reward"]), ("fallen", out["fallen"]), ("adv", adv),
+                           ("v_target", vt)):
+                hosts[b][k].copy_(src, non_blocking=True)
+                src.record_stream(copy_stream)
+            vals.record_stream(copy_stream)
+            copied[b] = torch.cuda.Event()
+            copied[b].record(copy_stream)
+    e2e_steps = max(4, min(args.steps, 10))
+    for i in range(2):
+        e2e_step(i)
     sync_all()
-    w0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    for i in range(e2e_steps):
+        e2e_step(i)
+    for ev in copied:
+        main.wait_event(ev)                                    # the last device->host copies are inside the region
+    e1.record(main)
     sync_all()
-    e2e_ms = torch.tensor([(time.perf_counter() - w0) * 1e3 / e2e_steps], device="cuda", dtype=torch.float64)
+    e2e_ms = torch.tensor([e0.elapsed_time(e1) / e2e_steps], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    host = hosts[0]
     h2d = values_host.numel() * 4
     d2h = sum(v.numel() * v.element_size() for v in host.values())
 
@@ -216,8 +244,25 @@ def run_ours(args):
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "roofline": {"bound": "hbm", "kernel": "play_h1_kernel (one episode, incl. end-of-episode reset)", "achieved": achieved,
                              "peak": peaks["hbm_gbs"], "peak_source": which, "unit": "GB/s",
-                             "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                             "frac": achieved / peaks["hbm_gbs"],
+                             "traffic": NCU_TRAFFIC_BYTES_4096x500 if (n, T) == (4096, 500) else None,
                              "bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": kernel_ms}}
+        if not args.no_other_configs:
+            # the other BASELINE.json configs on this GPU (parity cases; measured here so that one file carries them)
+            sys.path.insert(0, str(ROOT / "tools"))
+            other = {}
+            try:
+                import bench_a3
+                other["a3_ppo_rollout_16384x64"] = bench_a3.measure(steps=10, warmup=3)
+                other["a3_ppo_rollout_262144x64"] = bench_a3.measure(envs=262144, steps=5, warmup=2)
+            except Exception as e:                              # never lose the headline line to a side measurement
+                other["a3_error"] = repr(e)
+            try:
+                import bench_disc
+                other["disc_reward_65536"] = bench_disc.measure(steps=20, warmup=3)
+            except Exception as e:
+                other["disc_error"] = repr(e)
+            line["other_configs"] = other
         if not args.no_cpu_baseline:
             from oracle import cpu_baseline
             res = cpu_baseline.run(model, table, steps=1, warmup=0, horizon=T, budget_s=args.cpu_budget)
@@ -237,6 +282,7 @@ def main():
     ap.add_argument("--envs", type=int, default=N_ENVS)
     ap.add_argument("--horizon", type=int, default=HORIZON)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -15,14 +15,8 @@ sys.path.insert(0, str(ROOT))
 BYTES_PER_ENV_STEP = 490          # SURVEY.md 8(d) config 3 (FK fused, not materialised)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--envs", type=int, default=16384)
-    ap.add_argument("--horizon", type=int, default=64)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--per-step", action="store_true", help="launch the step kernel once per env step (the live-rollout pattern)")
-    args = ap.parse_args()
+def measure(envs=16384, horizon=64, steps=20, warmup=3, per_step=False):
+    args = argparse.Namespace(envs=envs, horizon=horizon, steps=steps, warmup=warmup, per_step=per_step)
     from olympics_mujoco_b200 import kernels as Kn
     from olympics_mujoco_b200 import mjcf
     from olympics_mujoco_b200.tasks.phase_clock import phase_clock_lut
@@ -81,11 +75,22 @@ def main():
     kms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {"hbm_gbs": 6650.0}
     achieved = BYTES_PER_ENV_STEP * n * T / (kms * 1e-3) / 1e9
-    print(json.dumps({"workload": f"A3 PPO walk rollout {n} envs x {T} steps (configs[2])", "per_step_launches": args.per_step,
-                      "value": n * T / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "task_kernel_ms": kms,
-                      "gpu_launches": Kn.launch_count(),
-                      "roofline": {"bound": "hbm", "kernel": "a3_task_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                                   "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "bytes_per_env_step": BYTES_PER_ENV_STEP}}))
+    return {"workload": f"A3 PPO walk rollout {n} envs x {T} steps (configs[2])", "per_step_launches": args.per_step,
+            "value": n * T / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "task_kernel_ms": kms,
+            "gpu_launches": Kn.launch_count(),
+            "roofline": {"bound": "hbm", "kernel": "a3_task_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "bytes_per_env_step": BYTES_PER_ENV_STEP}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=16384)
+    ap.add_argument("--horizon", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--per-step", action="store_true", help="launch the step kernel once per env step (the live-rollout pattern)")
+    a = ap.parse_args()
+    print(json.dumps(measure(a.envs, a.horizon, a.steps, a.warmup, a.per_step)))
 
 
 if __name__ == "__main__":

@@ -13,12 +13,9 @@ sys.path.insert(0, str(ROOT))
 FLOP = {"vail": 2 * (32 * 256 + 256 * 128 + 2 * 128 * 128 + 128), "gail": 2 * (32 * 512 + 512 * 256 + 256)}
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--envs", type=int, default=65536)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
-    args = ap.parse_args()
+def measure(envs=65536, steps=50, warmup=5):
+    args = argparse.Namespace(envs=envs, steps=steps, warmup=warmup)
+    res = []
     from olympics_mujoco_b200 import kernels as Kn
     g = np.load(ROOT / "tests/golden/discriminator_ref.npz")
     n = args.envs
@@ -48,12 +45,23 @@ def main():
         ms = tot / args.steps
         useful = FLOP[kind] * n / (ms * 1e-3) / 1e12
         peak_tf32 = peaks["bf16_tflops"] / 2
-        print(json.dumps({"workload": f"{kind.upper()} discriminator reward, {n} envs (configs[3])", "ms": ms,
-                          "value": n / (ms * 1e-3), "unit": "samples/s",
-                          "roofline": {"bound": "tensor", "achieved": useful, "executed_3xtf32": 3 * useful, "unit": "TFLOP/s",
-                                       "peak": peak_tf32, "peak_note": "measured bf16 burst / 2 (TF32 rate)",
-                                       "frac": useful / peak_tf32, "frac_executed": 3 * useful / peak_tf32,
-                                       "flop_per_sample": FLOP[kind]}}))
+        res.append({"workload": f"{kind.upper()} discriminator reward, {n} envs (configs[3])", "ms": ms,
+                    "value": n / (ms * 1e-3), "unit": "samples/s",
+                    "roofline": {"bound": "tensor", "achieved": useful, "executed_3xtf32": 3 * useful, "unit": "TFLOP/s",
+                                 "peak": peak_tf32, "peak_note": "measured bf16 burst / 2 (TF32 rate)",
+                                 "frac": useful / peak_tf32, "frac_executed": 3 * useful / peak_tf32,
+                                 "flop_per_sample": FLOP[kind]}})
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=65536)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    a = ap.parse_args()
+    for r in measure(a.envs, a.steps, a.warmup):
+        print(json.dumps(r))
 
 
 if __name__ == "__main__":
