@@ -327,6 +327,11 @@ using namespace om;
 
 struct OmTraj {
   TrajDev d;
+  // Scratch of the time-parallel playback kernel (episode-start snapshot of the carried state), grown on demand
+  // and kept: a stream-ordered allocation per call cost more than the kernel whenever the pool had been trimmed.
+  // One playback call per handle may be in flight at a time.
+  mutable char* scratch = nullptr;
+  mutable size_t scratch_bytes = 0;
 };
 
 extern "C" int om_traj_create(const double* table, int K, int n_traj, int T, OmTraj** out) {
@@ -380,6 +385,7 @@ extern "C" void om_traj_destroy(OmTraj* t) {
   cudaFree((void*)t->d.rows);
   cudaFree((void*)t->d.xy);
   cudaFree((void*)t->d.cdq);
+  if (t->scratch) cudaFree(t->scratch);
   delete t;
 }
 
@@ -451,9 +457,14 @@ extern "C" int om_h1_play_from_velocity(const OmModel* m, const OmH1Spec* spec, 
     cudaStream_t st = (cudaStream_t)stream;
     const size_t L = (size_t)ld;
     const size_t bytes = L * (4 + 4 + 4 + 16 + 4 + 17 * 8 + 34 * 4) + 256;
-    char* scratch = nullptr;
-    OM_CUDA_OK(cudaMallocAsync((void**)&scratch, bytes, st));
-    char* p = scratch;
+    if (t->scratch_bytes < bytes) {
+      if (t->scratch) OM_CUDA_OK(cudaFree(t->scratch));       // synchronises: no earlier call still reads it
+      t->scratch = nullptr;
+      t->scratch_bytes = 0;
+      OM_CUDA_OK(cudaMalloc((void**)&t->scratch, bytes));
+      t->scratch_bytes = bytes;
+    }
+    char* p = t->scratch;
     a.snap.curr_qpos = (double*)p; p += L * 17 * 8;
     a.snap.xy_off = (double*)p; p += L * 16;
     a.snap.pending = (float*)p; p += L * 34 * 4;
@@ -466,7 +477,6 @@ extern "C" int om_h1_play_from_velocity(const OmModel* m, const OmH1Spec* spec, 
     dim3 grid(ceil_div(n, BLOCK), ceil_div(n_steps, chunk));
     play_h1_tp_kernel<BLOCK><<<grid, BLOCK, 0, st>>>(a, chunk);
     OM_LAUNCHED();
-    OM_CUDA_OK(cudaFreeAsync(scratch, st));
     return 0;
   }
   OM_LAUNCHED();
