@@ -319,3 +319,12 @@ int or_num_threads(void) {
   return 1;
 #endif
 }
+
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU baseline is supposed to use the host cores */
+void or_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}

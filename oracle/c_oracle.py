@@ -93,3 +93,11 @@ def gae(r, v, v_next, absorbing, last, gamma, lam):
 
 def num_threads():
     return int(lib().or_num_threads())
+
+
+def use_all_cores():
+    """Undo an inherited OMP_NUM_THREADS=1 (torchrun sets it for every rank): one thread per usable host CPU."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().or_set_num_threads(int(n))
+    return num_threads()

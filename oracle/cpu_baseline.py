@@ -16,7 +16,7 @@ from . import h1 as OH
 def run(model, table, steps=1, warmup=0, horizon=500, budget_s=15.0, n_env=None):
     cm = c_oracle.CModel(model)
     perm = OH.perm(model)
-    cores = c_oracle.num_threads()
+    cores = c_oracle.use_all_cores()
     # size the bounded sample: time a small probe, then pick n_env so one "step" takes ~budget_s
     probe = max(cores, 8)
     t0 = time.perf_counter()
