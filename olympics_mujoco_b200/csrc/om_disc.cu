@@ -4,14 +4,16 @@
 //   :208-234, FullyConnectedNetwork :94-158, Standardizer.forward :68-74; shapes examples/imitation_learning/utils.py:151-179
 //   + confs.yaml:113-130:  VAIL 32 -relu-> 256 -relu-> 128 -> (mu, logvar)[128+128] -> z -> 1 ;  GAIL 32 -tanh-> 512 -tanh-> 256 -> 1.
 //
-// The only dense contraction on the hot path, so the only tcgen05 kernel.  One CTA (128 threads, 1 per SM) owns a
-// tile of 128 samples: TMEM lane = sample, TMEM column = layer output, i.e. thread t of the CTA owns sample t in every
-// epilogue and the final 128->1 / 256->1 head is a per-thread dot product.  Each layer is D[128 x N] += A[128 x K] B[N x K]^T
-// on tcgen05.mma kind::tf32 (M=128, N<=256, K=8), streamed in K-chunks of 32:
-//   * A chunk (activations of the previous layer): tcgen05.ld from TMEM -> bias + activation -> split -> st.shared in the
-//     canonical K-major no-swizzle UMMA layout [k/4][row][4]  (16-byte rows contiguous: conflict-free stores);
-//   * B chunk (weights): a pre-split image in exactly that layout, fetched by ONE cp.async.bulk (TMA, 1-D) per chunk
-//     onto an mbarrier; two stages so that the copy and the next A chunk overlap the MMAs of the current one;
+// The only dense contraction on the hot path, so the only tcgen05 kernel.  One persistent CTA per SM owns 128-sample
+// tiles: TMEM lane = sample, TMEM column = layer output, so producer thread t owns sample t in every epilogue and the
+// final 128->1 / 256->1 head is a per-thread dot product.  Each layer is D[128 x N] += A[128 x K] B[N x K]^T on
+// tcgen05.mma kind::tf32 (M=128, N<=256, K=8), streamed in K-chunks:
+//   * A chunk (32 K-elements of the previous layer's activations): tcgen05.ld from TMEM -> bias + activation -> hi/lo
+//     split -> st.shared in the canonical K-major no-swizzle UMMA layout [k/4][row][4] (16-byte rows contiguous:
+//     conflict-free stores); 2-stage ring;
+//   * B sub-chunk (16 K-elements of the weights): a pre-split image in exactly that layout, fetched by cp.async.bulk
+//     (TMA, 1-D, several 8 KB pieces in flight) onto an mbarrier; 4-stage ring;
+//   * warp-specialised: 4 producer/epilogue warps, one MMA-issuing thread, one copy-issuing thread, mbarriers only;
 //   * fp32 fidelity: every product is evaluated as 3xTF32 (a_hi b_hi + a_lo b_hi + a_hi b_lo, hi = cvt.rna.tf32), fp32
 //     accumulation in TMEM -- the north star's 1e-5 tolerance on rewards rules out plain TF32 (~1e-3).
 #include <cstring>
@@ -25,8 +27,7 @@ constexpr int DISC_IN = 32;        // observation size of the H1 discriminators
 constexpr int KC = 32;             // K-chunk (elements) = 4 MMA k-steps of 8
 constexpr int TILE = 128;          // samples per CTA tile = UMMA_M
 constexpr int STAGE_A_BYTES = TILE * KC * 4 * 2;      // hi + lo
-constexpr int STAGE_B_BYTES = 256 * KC * 4 * 2;       // up to N = 256 rows, hi + lo
-constexpr int DISC_MAX_PAR = 512 + 256 + 256 + 256;   // biases + head weights staged in shared memory
+constexpr int DISC_MAX_PAR = 512 + 256 + 256 + 256 + 64;   // biases + head weights + standardiser, staged in shared memory
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -135,8 +136,20 @@ __device__ __forceinline__ void store_a_chunk(uint8_t* stage, int row, const flo
   }
 }
 
+// Warp roles (192 threads): warps 0-3 = producers / epilogue (thread t owns sample t = TMEM lane t), warp 4 lane 0 =
+// MMA issuer, warp 5 lane 0 = weight-copy (TMA) issuer.  Rings: A 2 stages x 32 K-elements, B 4 stages x 16 K-elements.
+//   a_full[2]  producers -> issuer   (128 arrivals)        a_free[2]  tcgen05.commit -> producers (stage reuse AND
+//   b_full[4]  bulk copy -> issuer   (transaction bytes)              "all MMAs up to this chunk are complete")
+//   b_free[4]  tcgen05.commit -> copy issuer
+// All three roles walk the same static chunk schedule; ga / qb count A chunks / B sub-chunks since kernel start, so
+// stage = counter mod ring and the mbarrier parity = (counter / ring) & 1.
+constexpr int KB = 16;                                 // K elements per B sub-chunk (2 MMA k-steps)
+constexpr int NSB = 4;
+constexpr int STAGE_B2_BYTES = 256 * KB * 4 * 2;       // 32 KB
+constexpr int COPY_PIECE = 8192;                       // several bulk copies in flight per sub-chunk
+
 template <int N1, int N2, bool VAIL>
-__global__ void __launch_bounds__(128, 1) disc_reward_kernel(DiscArgs a) {
+__global__ void __launch_bounds__(192, 1) disc_reward_kernel(DiscArgs a) {
   constexpr int ACT = VAIL ? ACT_RELU : ACT_TANH;
   constexpr int NB1 = N1 / 256;                 // 256-wide column blocks of layer 1
   constexpr int Z = 128;
@@ -145,23 +158,30 @@ __global__ void __launch_bounds__(128, 1) disc_reward_kernel(DiscArgs a) {
   constexpr int HEAD_K = VAIL ? Z : N2;
   static_assert(N1 % 256 == 0 && N2 % 32 == 0 && N2 <= 256, "unsupported discriminator shape");
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* stA[2] = {smem, smem + STAGE_A_BYTES};
-  uint8_t* stB[2] = {smem + 2 * STAGE_A_BYTES, smem + 2 * STAGE_A_BYTES + STAGE_B_BYTES};
-  float* par = reinterpret_cast<float*>(smem + 2 * STAGE_A_BYTES + 2 * STAGE_B_BYTES);
+  uint8_t* stA = smem;                                            // 2 x STAGE_A_BYTES
+  uint8_t* stB = smem + 2 * STAGE_A_BYTES;                        // NSB x STAGE_B2_BYTES
+  float* par = reinterpret_cast<float*>(stB + NSB * STAGE_B2_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(par + DISC_MAX_PAR + 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const float* b1 = par;
   const float* b2 = par + N1;
   const float* b3 = par + N1 + N2;                          // VAIL: bmu | blv
   const float* wd = par + N1 + N2 + (VAIL ? N3 : 0);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t bar_full[2] = {smem_u32(bars), smem_u32(bars + 1)};
-  const uint32_t bar_done[2] = {smem_u32(bars + 2), smem_u32(bars + 3)};
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s_) { return bar0 + 8u * s_; };
+  auto a_free = [&](int s_) { return bar0 + 8u * (2 + s_); };
+  auto b_full = [&](int s_) { return bar0 + 8u * (4 + s_); };
+  auto b_free = [&](int s_) { return bar0 + 8u * (8 + s_); };
 
   constexpr int NPAR = N1 + N2 + (VAIL ? N3 : 0) + HEAD_K + 1;
-  for (int i = tid; i < NPAR; i += 128) par[i] = a.params[i];
+  for (int i = tid; i < NPAR; i += 192) par[i] = a.params[i];
+  float* s_mean = par + DISC_MAX_PAR - 2 * DISC_IN;          // Standardizer snapshot: mean, 1 / std
+  float* s_inv = s_mean + DISC_IN;
+  if (tid < DISC_IN) { s_mean[tid] = a.mean[tid]; s_inv[tid] = 1.0f / a.stdv[tid]; }
   if (tid == 0) {
-    mbar_init(bar_full[0], 1); mbar_init(bar_full[1], 1); mbar_init(bar_done[0], 1); mbar_init(bar_done[1], 1);
+    for (int s_ = 0; s_ < 2; ++s_) { mbar_init(a_full(s_), 128); mbar_init(a_free(s_), 1); }
+    for (int s_ = 0; s_ < NSB; ++s_) { mbar_init(b_full(s_), 1); mbar_init(b_free(s_), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -169,124 +189,178 @@ __global__ void __launch_bounds__(128, 1) disc_reward_kernel(DiscArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);     // this warp's 32 TMEM lanes
-  const float bd = par[NPAR - 1];
-
   const int ntiles = (a.n + TILE - 1) / TILE;
-  int g = 0;                     // global chunk counter of this CTA (stage = g & 1)
-  // commit of global chunk h has completed  <=>  phase (h >> 1) of bar_done[h & 1] has completed
-  auto wait_chunk = [&](int h) {
-    if (h >= 0) {
-      mbar_wait(bar_done[h & 1], (uint32_t)(h >> 1) & 1u);
-      tc_fence_after();
-    }
-  };
 
-  // One K-chunk: (1) the stage is free once chunk g-2 retired; (2) thread 0 starts the weight copy; (3) every thread
-  // writes its row of the A chunk; (4) thread 0 issues 4 k-steps x 3 products and commits.
-  auto run_chunk = [&](const float (&act_in)[32], const float* img, int rows, uint32_t d_col, bool first) {
-    const int st = g & 1;
-    wait_chunk(g - 2);
-    const uint32_t bytes = (uint32_t)rows * KC * 4 * 2;
-    if (tid == 0) {
-      mbar_expect_tx(bar_full[st], bytes);
-      bulk_g2s(smem_u32(stB[st]), img, bytes, bar_full[st]);
-    }
-    store_a_chunk(stA[st], tid, act_in);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      mbar_wait(bar_full[st], (uint32_t)(g >> 1) & 1u);
-      const uint32_t a_hi = smem_u32(stA[st]), a_lo = a_hi + TILE * KC * 4;
-      const uint32_t b_hi = smem_u32(stB[st]), b_lo = b_hi + (uint32_t)rows * KC * 4;
-      const uint32_t a_lbo = TILE * 16, b_lbo = (uint32_t)rows * 16, sbo = 128;
-      const uint32_t idesc = idesc_tf32(TILE, rows);
-#pragma unroll
-      for (int j = 0; j < KC / 8; ++j) {
-        const uint64_t dah = smem_desc(a_hi + j * 2 * a_lbo, a_lbo, sbo), dal = smem_desc(a_lo + j * 2 * a_lbo, a_lbo, sbo);
-        const uint64_t dbh = smem_desc(b_hi + j * 2 * b_lbo, b_lbo, sbo), dbl = smem_desc(b_lo + j * 2 * b_lbo, b_lbo, sbo);
-        umma_tf32(tmem + d_col, dal, dbh, idesc, (first && j == 0) ? 0u : 1u);      // small terms first
-        umma_tf32(tmem + d_col, dah, dbl, idesc, 1u);
-        umma_tf32(tmem + d_col, dah, dbh, idesc, 1u);
-      }
-      umma_commit(bar_done[st]);
-    }
-    ++g;
-  };
-
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int env = tile * TILE + tid;
-    const bool live = env < a.n;
-    const float* img = a.image;
-    // ---- standardised input row (Standardizer.forward networks.py:73-74 with a frozen snapshot)
-    float x[DISC_IN];
-#pragma unroll
-    for (int k = 0; k < DISC_IN; ++k)
-      x[k] = live ? (a.s[(size_t)k * a.ld + env] - __ldg(a.mean + k)) / __ldg(a.stdv + k) : 0.f;
-#pragma unroll 1
-    for (int nb = 0; nb < NB1; ++nb) {
-      run_chunk(x, img, 256, D1_COL, true);                                        // layer 1, column block nb
-      img += 256 * KC * 2;
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {                                                // layer 2, K-chunks fed by this block
-        if (c == 0) wait_chunk(g - 1);                                             // D1 block complete
-        float h[32];
-        tmem_ld32(lane_addr + D1_COL + c * KC, h);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) h[i] = act<ACT>(h[i] + b1[nb * 256 + c * KC + i]);
-        run_chunk(h, img, N2, D2_COL, nb == 0 && c == 0);
-        img += N2 * KC * 2;
+  if (warp == 5) {
+    // ===================================================== weight-copy issuer
+    if (tid == 160) {
+      int qb = 0;
+      auto copy_chunk = [&](const float*& img, int rows) {                 // one A chunk = two B sub-chunks
+        for (int hb = 0; hb < 2; ++hb, ++qb) {
+          const int sb = qb & (NSB - 1);
+          if (qb >= NSB) mbar_wait(b_free(sb), (uint32_t)((qb / NSB) - 1) & 1u);
+          const uint32_t bytes = (uint32_t)rows * KB * 4 * 2;
+          mbar_expect_tx(b_full(sb), bytes);
+          const uint32_t dst = smem_u32(stB + sb * STAGE_B2_BYTES);
+          for (uint32_t off = 0; off < bytes; off += COPY_PIECE)
+            bulk_g2s(dst + off, reinterpret_cast<const uint8_t*>(img) + off, COPY_PIECE, b_full(sb));
+          img += bytes / 4;
+        }
+      };
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const float* img = a.image;
+        for (int nb = 0; nb < NB1; ++nb) {
+          copy_chunk(img, 256);
+          for (int c = 0; c < 8; ++c) copy_chunk(img, N2);
+        }
+        if (VAIL)
+          for (int c = 0; c < N2 / KC; ++c) copy_chunk(img, N3);
       }
     }
-    float dval = 0.f;
-    if (VAIL) {
-#pragma unroll 1
-      for (int c = 0; c < N2 / KC; ++c) {                                          // [mu; logvar] layer
-        if (c == 0) wait_chunk(g - 1);                                             // D2 complete
-        float h[32];
-        tmem_ld32(lane_addr + D2_COL + c * KC, h);
+  } else if (warp == 4) {
+    // ===================================================== MMA issuer
+    if (tid == 128) {
+      int ga = 0, qb = 0;
+      auto mma_chunk = [&](int rows, uint32_t d_col, bool first) {
+        const int sa = ga & 1;
+        mbar_wait(a_full(sa), (uint32_t)(ga >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(stA + sa * STAGE_A_BYTES), a_lo = a_hi + TILE * KC * 4;
+        const uint32_t a_lbo = TILE * 16, b_lbo = (uint32_t)rows * 16, sbo = 128;
+        const uint32_t idesc = idesc_tf32(TILE, rows);
+        for (int hb = 0; hb < 2; ++hb, ++qb) {
+          const int sb = qb & (NSB - 1);
+          mbar_wait(b_full(sb), (uint32_t)(qb / NSB) & 1u);
+          const uint32_t b_hi = smem_u32(stB + sb * STAGE_B2_BYTES), b_lo = b_hi + (uint32_t)rows * KB * 4;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) h[i] = act<ACT>(h[i] + b2[c * KC + i]);
-        run_chunk(h, img, N3, D3_COL, c == 0);
-        img += N3 * KC * 2;
+          for (int j = 0; j < KB / 8; ++j) {
+            const uint32_t ao = (uint32_t)(hb * (KB / 8) + j) * 2 * a_lbo, bo = (uint32_t)j * 2 * b_lbo;
+            const uint64_t dah = smem_desc(a_hi + ao, a_lbo, sbo), dal = smem_desc(a_lo + ao, a_lbo, sbo);
+            const uint64_t dbh = smem_desc(b_hi + bo, b_lbo, sbo), dbl = smem_desc(b_lo + bo, b_lbo, sbo);
+            umma_tf32(tmem + d_col, dal, dbh, idesc, (first && hb == 0 && j == 0) ? 0u : 1u);     // small terms first
+            umma_tf32(tmem + d_col, dah, dbl, idesc, 1u);
+            umma_tf32(tmem + d_col, dah, dbh, idesc, 1u);
+          }
+          umma_commit(b_free(sb));
+        }
+        umma_commit(a_free(sa));
+        ++ga;
+      };
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int nb = 0; nb < NB1; ++nb) {
+          mma_chunk(256, D1_COL, true);
+          for (int c = 0; c < 8; ++c) mma_chunk(N2, D2_COL, nb == 0 && c == 0);
+        }
+        if (VAIL)
+          for (int c = 0; c < N2 / KC; ++c) mma_chunk(N3, D3_COL, c == 0);
       }
-      wait_chunk(g - 1);
-      // z = mu + exp(logvar / 2) * eps (networks.py:21-24), d = wd . z + bd
-#pragma unroll 1
-      for (int c = 0; c < Z / 32; ++c) {
-        float mu[32], lv[32];
-        tmem_ld32(lane_addr + D3_COL + c * 32, mu);
-        tmem_ld32(lane_addr + D3_COL + Z + c * 32, lv);
+    }
+  } else {
+    // ===================================================== producers / epilogue (128 threads)
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);     // this warp's 32 TMEM lanes
+    const float bd = par[NPAR - 1];
+    int ga = 0;
+    // commit of A chunk h has completed  <=>  phase (h >> 1) of a_free[h & 1] has completed
+    auto wait_chunk = [&](int h) {
+      if (h >= 0) {
+        mbar_wait(a_free(h & 1), (uint32_t)(h >> 1) & 1u);
+        tc_fence_after();
+      }
+    };
+    auto put_chunk = [&](const float (&act_in)[32]) {
+      wait_chunk(ga - 2);                                                // the stage is free
+      store_a_chunk(stA + (ga & 1) * STAGE_A_BYTES, tid, act_in);
+      fence_proxy_async();                                               // generic-proxy stores -> async proxy (UMMA)
+      tc_fence_before();                                                 // earlier tcgen05.ld before later MMAs
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_full(ga & 1)) : "memory");
+      ++ga;
+    };
+    // raw observation row of this thread's sample; the NEXT tile's row is requested while the current tile computes
+    auto load_row = [&](int tile_, float (&raw)[DISC_IN]) {
+      const int env_ = tile_ * TILE + tid;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int j = c * 32 + i;
-          const float e = (a.eps && live) ? a.eps[(size_t)j * a.ld + env] : 0.f;
-          const float zz = fmaf(expf(0.5f * (lv[i] + b3[Z + j])), e, mu[i] + b3[j]);
-          dval = fmaf(wd[j], zz, dval);
+      for (int k = 0; k < DISC_IN; ++k) raw[k] = (tile_ < ntiles && env_ < a.n) ? a.s[(size_t)k * a.ld + env_] : 0.f;
+    };
+    float xn[DISC_IN];
+    load_row(blockIdx.x, xn);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int env = tile * TILE + tid;
+      const bool live = env < a.n;
+      // ---- standardised input row (Standardizer.forward networks.py:73-74 with a frozen snapshot)
+      float x[DISC_IN];
+#pragma unroll
+      for (int k = 0; k < DISC_IN; ++k) x[k] = live ? (xn[k] - s_mean[k]) * s_inv[k] : 0.f;
+      load_row(tile + gridDim.x, xn);
+#pragma unroll 1
+      for (int nb = 0; nb < NB1; ++nb) {
+        put_chunk(x);                                                    // layer 1, column block nb
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {                                    // layer 2, K-chunks fed by this block
+          if (c == 0) wait_chunk(ga - 1);                                // D1 block complete
+          float h[32];
+          tmem_ld32(lane_addr + D1_COL + c * KC, h);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) h[i] = act<ACT>(h[i] + b1[nb * 256 + c * KC + i]);
+          put_chunk(h);
         }
       }
-    } else {
-      wait_chunk(g - 1);
+      float dval = 0.f;
+      if (VAIL) {
 #pragma unroll 1
-      for (int c = 0; c < N2 / 32; ++c) {
-        float h[32];
-        tmem_ld32(lane_addr + D2_COL + c * 32, h);
+        for (int c = 0; c < N2 / KC; ++c) {                              // [mu; logvar] layer
+          if (c == 0) wait_chunk(ga - 1);                                // D2 complete
+          float h[32];
+          tmem_ld32(lane_addr + D2_COL + c * KC, h);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) dval = fmaf(wd[c * 32 + i], act<ACT>(h[i] + b2[c * 32 + i]), dval);
+          for (int i = 0; i < 32; ++i) h[i] = act<ACT>(h[i] + b2[c * KC + i]);
+          put_chunk(h);
+        }
+        // z = mu + exp(logvar / 2) * eps (networks.py:21-24), d = wd . z + bd.  The noise rows are requested one block
+        // ahead so that their latency hides behind the last MMAs / the TMEM loads.
+        auto load_eps = [&](int c, float (&e)[32]) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) e[i] = (a.eps && live) ? a.eps[(size_t)(c * 32 + i) * a.ld + env] : 0.f;
+        };
+        auto head_block = [&](int c, const float (&e)[32]) {
+          float mu[32], lv[32];
+          tmem_ld32(lane_addr + D3_COL + c * 32, mu);
+          tmem_ld32(lane_addr + D3_COL + Z + c * 32, lv);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int j = c * 32 + i;
+            const float zz = fmaf(expf(0.5f * (lv[i] + b3[Z + j])), e[i], mu[i] + b3[j]);
+            dval = fmaf(wd[j], zz, dval);
+          }
+        };
+        float e0[32], e1[32];
+        load_eps(0, e0);
+        wait_chunk(ga - 1);
+        static_assert(Z == 128, "head unrolled for z = 128");
+        load_eps(1, e1); head_block(0, e0);
+        load_eps(2, e0); head_block(1, e1);
+        load_eps(3, e1); head_block(2, e0);
+        head_block(3, e1);
+      } else {
+        wait_chunk(ga - 1);
+#pragma unroll 1
+        for (int c = 0; c < N2 / 32; ++c) {
+          float h[32];
+          tmem_ld32(lane_addr + D2_COL + c * 32, h);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dval = fmaf(wd[c * 32 + i], act<ACT>(h[i] + b2[c * 32 + i]), dval);
+        }
       }
+      dval += bd;
+      if (live) {
+        // 1 - sigmoid(d) evaluated as sigmoid(-d): no cancellation for large d (gail_TRPO.py:326-327)
+        const float one_minus_p = 1.f / (1.f + expf(dval));
+        a.reward[env] = -logf(one_minus_p + 1e-8f);
+        if (a.d_out) a.d_out[env] = dval;
+      }
+      // the next tile's layer-1 MMA overwrites the columns read above: put_chunk orders these loads before its arrive
     }
-    dval += bd;
-    if (live) {
-      // 1 - sigmoid(d) evaluated as sigmoid(-d): no cancellation for large d (gail_TRPO.py:326-327)
-      const float one_minus_p = 1.f / (1.f + expf(dval));
-      a.reward[env] = -logf(one_minus_p + 1e-8f);
-      if (a.d_out) a.d_out[env] = dval;
-    }
-    // the next tile's layer-1 MMA overwrites the columns read above: order the TMEM loads before it
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
@@ -309,16 +383,20 @@ static void split_tf32(float x, float* hi, float* lo) {
   *lo = x - *hi;
 }
 
-// one chunk: rows [r0, r0+rows) x columns [k0, k0+32) of a row-major [*, ldw] matrix -> hi image then lo image
+// one A chunk: rows [r0, r0+rows) x columns [k0, k0+32) of a row-major [*, ldw] matrix, as two B sub-chunks of 16
+// columns, each a hi image [4][rows][4] followed by its lo image
 static void append_chunk(std::vector<float>& img, const float* w, int ldw, int r0, int rows, int k0) {
-  const size_t base = img.size();
-  img.resize(base + (size_t)rows * KC * 2);
-  float* hi = img.data() + base;
-  float* lo = hi + (size_t)rows * KC;
-  for (int kc = 0; kc < 8; ++kc)
-    for (int r = 0; r < rows; ++r)
-      for (int e = 0; e < 4; ++e)
-        split_tf32(w[(size_t)(r0 + r) * ldw + k0 + kc * 4 + e], hi + ((size_t)kc * rows + r) * 4 + e, lo + ((size_t)kc * rows + r) * 4 + e);
+  for (int hb = 0; hb < KC / KB; ++hb) {
+    const size_t base = img.size();
+    img.resize(base + (size_t)rows * KB * 2);
+    float* hi = img.data() + base;
+    float* lo = hi + (size_t)rows * KB;
+    for (int kc = 0; kc < KB / 4; ++kc)
+      for (int r = 0; r < rows; ++r)
+        for (int e = 0; e < 4; ++e)
+          split_tf32(w[(size_t)(r0 + r) * ldw + k0 + hb * KB + kc * 4 + e], hi + ((size_t)kc * rows + r) * 4 + e,
+                     lo + ((size_t)kc * rows + r) * 4 + e);
+  }
 }
 
 extern "C" int om_disc_create(const OmDiscDesc* d, OmDisc** out) {
@@ -385,15 +463,15 @@ extern "C" int om_disc_reward(const OmDisc* h, const float* s, const float* mean
   OM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int ntiles = ceil_div(n, TILE);
   const int grid = ntiles < sms ? ntiles : sms;                  // persistent: one CTA per SM
-  const size_t smem = 2 * STAGE_A_BYTES + 2 * STAGE_B_BYTES + (DISC_MAX_PAR + 4) * sizeof(float) + 4 * 8 + 16;
+  const size_t smem = 2 * STAGE_A_BYTES + NSB * STAGE_B2_BYTES + (DISC_MAX_PAR + 4) * sizeof(float) + 12 * 8 + 16;
   DiscArgs a{h->sh, h->image, h->params, s, mean, stdv, eps, reward, d_out, n, ld};
   cudaStream_t st = (cudaStream_t)stream;
   if (h->sh.kind == 0) {
     OM_CUDA_OK(cudaFuncSetAttribute(disc_reward_kernel<256, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    disc_reward_kernel<256, 128, true><<<grid, 128, smem, st>>>(a);
+    disc_reward_kernel<256, 128, true><<<grid, 192, smem, st>>>(a);
   } else {
     OM_CUDA_OK(cudaFuncSetAttribute(disc_reward_kernel<512, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    disc_reward_kernel<512, 256, false><<<grid, 128, smem, st>>>(a);
+    disc_reward_kernel<512, 256, false><<<grid, 192, smem, st>>>(a);
   }
   OM_LAUNCHED();
   return 0;
