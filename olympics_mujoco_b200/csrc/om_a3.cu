@@ -1,6 +1,7 @@
 // K2 (A3 flavour) kernels and C ABI: StickFigureA3 RL step tail (FK fused, not materialised unless asked for),
 // multi-step replay of recorded sim states, and the randomised reset.  Per-env arithmetic: om_a3_task.cuh.
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "om_common.cuh"
@@ -52,12 +53,14 @@ __global__ void __launch_bounds__(BLOCK) a3_task_kernel(A3Args a) {
     for (int k = 0; k < 4; ++k) c_[k] = cp[k * ld];
   };
   load(0, q, qd, con);
+  A3Targets tc = a3_targets_load(s, seq);
   for (int t = 0; t < a.T; ++t) {
     float qn[A3_NQ], qdn[A3_NV], conn[4];
     if (t + 1 < a.T) load(t + 1, qn, qdn, conn);
     float obs[A3_NOBS], terms[6], total;
     bool done;
     a3_obs_robot(q, qd, obs);
+    A3TaskIn in;
     if (WRITE_FK) {
       const size_t slot = (size_t)t;
       A3Sink<SoaSink<true>> S{{a.o.xpos ? a.o.xpos + slot * 51 * ld : nullptr, a.o.xquat ? a.o.xquat + slot * 68 * ld : nullptr,
@@ -65,14 +68,14 @@ __global__ void __launch_bounds__(BLOCK) a3_task_kernel(A3Args a) {
                                a.o.site_xmat ? a.o.site_xmat + slot * 18 * ld : nullptr,
                                a.o.cvel ? a.o.cvel + slot * 102 * ld : nullptr, nullptr, ld, e}, {}};
       om_fk_stick_figure_a3(q, qd, S);
-      const int fl = (int)con[3];
-      a3_task_step(a.C, S.f, s, seq, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, obs, terms, total, done);
+      in = a3_task_in(S.f);
     } else {
       A3Sink<NullFkSink> S{};
       om_fk_stick_figure_a3(q, qd, S);
-      const int fl = (int)con[3];
-      a3_task_step(a.C, S.f, s, seq, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, obs, terms, total, done);
+      in = a3_task_in(S.f);
     }
+    const int fl = (int)con[3];
+    a3_task_step(a.C, in, s, tc, seq, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, obs, terms, total, done);
     if (a.o.obs) {
       float* ob = a.o.obs + (size_t)t * A3_NOBS * ld + e;
 #pragma unroll
@@ -93,6 +96,82 @@ __global__ void __launch_bounds__(BLOCK) a3_task_kernel(A3Args a) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) con[k] = conn[k];
     }
+  }
+  a.ints[A3I_PHASE * ld + e] = s.phase; a.ints[A3I_T1 * ld + e] = s.t1; a.ints[A3I_T2 * ld + e] = s.t2;
+  a.ints[A3I_FRAMES * ld + e] = s.frames; a.ints[A3I_REACHED * ld + e] = s.reached;
+}
+
+// ---------------------------------------------------------------- time-parallel replay (few envs, many steps)
+// The only recurrence over time is the task's integer state; everything expensive (FK, the state-independent 31
+// observation rows) depends on (env, t) alone.  Pass 1 runs one thread per (env, t) -- 16384 envs x 64 steps fill the
+// machine instead of 256 CTAs of 64 threads -- and leaves a 17-float record per env-step; pass 2 walks the T records
+// of an env sequentially (one thread per env, ~250 instructions per step) and emits what depends on the task state.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) a3_feat_kernel(A3Args a, float* __restrict__ feat) {
+  const int env = blockIdx.x * BLOCK + threadIdx.x;
+  const int t = blockIdx.y;
+  if (env >= a.n) return;
+  const size_t ld = a.ld, e = env;
+  float q[A3_NQ], qd[A3_NV];
+  const float* qp = a.qpos + (size_t)t * A3_NQ * ld + e;
+  const float* vp = a.qvel + (size_t)t * A3_NV * ld + e;
+#pragma unroll
+  for (int k = 0; k < A3_NQ; ++k) q[k] = qp[k * ld];
+#pragma unroll
+  for (int k = 0; k < A3_NV; ++k) qd[k] = vp[k * ld];
+  if (a.o.obs) {
+    float obs[A3_NOBS];
+    a3_obs_robot(q, qd, obs);
+    float* ob = a.o.obs + (size_t)t * A3_NOBS * ld + e;
+#pragma unroll
+    for (int k = 0; k < 31; ++k) ob[k * ld] = obs[k];
+  }
+  A3Sink<NullFkSink> S{};
+  om_fk_stick_figure_a3(q, qd, S);
+  a3_task_in_store(a3_task_in(S.f), feat + (size_t)t * A3_NFEAT * ld + e, ld);
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) a3_seq_kernel(A3Args a, const float* __restrict__ feat) {
+  const int env = blockIdx.x * BLOCK + threadIdx.x;
+  if (env >= a.n) return;
+  const size_t ld = a.ld, e = env;
+  A3TaskRegs s{a.ints[A3I_PHASE * ld + e], a.ints[A3I_T1 * ld + e], a.ints[A3I_T2 * ld + e], a.ints[A3I_FRAMES * ld + e],
+               a.ints[A3I_MODE * ld + e], a.ints[A3I_SEQLEN * ld + e], a.ints[A3I_REACHED * ld + e]};
+  const SeqGlobal seq{a.sequence + e, ld};
+  A3Targets tc = a3_targets_load(s, seq);
+  auto load = [&](int t, A3TaskIn& in, float (&c_)[4]) {
+    in = a3_task_in_load(feat + (size_t)t * A3_NFEAT * ld + e, ld);
+    const float* cp = a.contact + (size_t)t * 4 * ld + e;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c_[k] = cp[k * ld];
+  };
+  A3TaskIn in;
+  float con[4];
+  load(0, in, con);
+  for (int t = 0; t < a.T; ++t) {
+    A3TaskIn inn = in;
+    float conn[4] = {0.f, 0.f, 0.f, 0.f};
+    if (t + 1 < a.T) load(t + 1, inn, conn);                   // independent of the task state: overlaps this step
+    float obs[A3_NOBS], terms[6], total;
+    bool done;
+    const int fl = (int)con[3];
+    a3_task_step(a.C, in, s, tc, seq, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, obs, terms, total, done);
+    if (a.o.obs) {
+      float* ob = a.o.obs + (size_t)t * A3_NOBS * ld + e;
+#pragma unroll
+      for (int k = 31; k < A3_NOBS; ++k) ob[k * ld] = obs[k];
+    }
+    if (a.o.terms) {
+      float* tp = a.o.terms + (size_t)t * 6 * ld + e;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) tp[k * ld] = terms[k];
+    }
+    if (a.o.reward) a.o.reward[(size_t)t * ld + e] = total;
+    if (a.o.done) a.o.done[(size_t)t * ld + e] = done ? 1 : 0;
+    in = inn;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) con[k] = conn[k];
   }
   a.ints[A3I_PHASE * ld + e] = s.phase; a.ints[A3I_T1 * ld + e] = s.t1; a.ints[A3I_T2 * ld + e] = s.t2;
   a.ints[A3I_FRAMES * ld + e] = s.frames; a.ints[A3I_REACHED * ld + e] = s.reached;
@@ -152,6 +231,10 @@ struct OmA3Task {
   A3TaskConst C;
   float* lut = nullptr;        // device [period][6]
   float* init_qpos = nullptr;  // device [25]
+  // record buffer of the time-parallel replay ([T][17][ld] floats), grown on demand and kept; one replay call per
+  // handle may be in flight at a time
+  mutable float* feat = nullptr;
+  mutable size_t feat_floats = 0;
 };
 
 extern "C" int om_a3_task_create(const OmA3TaskDesc* d, OmA3Task** out) {
@@ -193,6 +276,7 @@ extern "C" void om_a3_task_destroy(OmA3Task* t) {
   if (!t) return;
   cudaFree(t->lut);
   cudaFree(t->init_qpos);
+  if (t->feat) cudaFree(t->feat);
   delete t;
 }
 
@@ -208,8 +292,29 @@ extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const flo
   const bool want_fk = out->xpos || out->xquat || out->site_xpos || out->site_xmat || out->cvel;
   constexpr int BLOCK = 64;
   const int grid = ceil_div(n, BLOCK);
-  if (want_fk) a3_task_kernel<BLOCK, true><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
-  else a3_task_kernel<BLOCK, false><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
+  cudaStream_t st = (cudaStream_t)stream;
+  // Few envs, several steps: the env axis alone cannot fill 148 SMs x 2048 threads -> time-parallel replay.
+  int split = !want_fk && n_steps >= 4 && (long long)n < 148LL * 1024;
+  if (const char* f = getenv("OM_A3_SPLIT")) split = atoi(f) != 0 && !want_fk;      // tuning / test hook
+  if (split) {
+    const size_t need = (size_t)n_steps * A3_NFEAT * (size_t)ld;
+    if (task->feat_floats < need) {
+      if (task->feat) OM_CUDA_OK(cudaFree(task->feat));        // synchronises: no earlier call still reads it
+      task->feat = nullptr;
+      task->feat_floats = 0;
+      OM_CUDA_OK(cudaMalloc((void**)&task->feat, need * sizeof(float)));
+      task->feat_floats = need;
+    }
+    constexpr int FB = 128;
+    a3_feat_kernel<FB><<<dim3(ceil_div(n, FB), n_steps), FB, 0, st>>>(a, task->feat);
+    OM_LAUNCHED();
+    constexpr int SB = 32;
+    a3_seq_kernel<SB><<<ceil_div(n, SB), SB, 0, st>>>(a, task->feat);
+    OM_LAUNCHED();
+    return 0;
+  }
+  if (want_fk) a3_task_kernel<BLOCK, true><<<grid, BLOCK, 0, st>>>(a);
+  else a3_task_kernel<BLOCK, false><<<grid, BLOCK, 0, st>>>(a);
   OM_LAUNCHED();
   return 0;
 }

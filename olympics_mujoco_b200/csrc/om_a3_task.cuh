@@ -85,6 +85,47 @@ struct A3TaskRegs { int phase, t1, t2, frames, mode, seq_len, reached; };
 
 OM_HD float norm3(V3 a) { return sqrtf(dot(a, a)); }
 
+// What WalkingTask.step / calc_reward / done read per env-step, reduced to 17 floats: this is also the record the
+// time-parallel path writes between its FK pass and its (sequential-in-time) task pass.
+constexpr int A3_NFEAT = 17;
+struct A3TaskIn {
+  V3 root_p; Q4 root_q; float head_x, head_y; V3 lsite, rsite; float lvel_n, rvel_n;
+};
+OM_HD A3TaskIn a3_task_in(const A3Feat& f) {
+  A3TaskIn t;
+  t.root_p = f.root_p; t.root_q = f.root_q; t.head_x = f.head_p.x; t.head_y = f.head_p.y;
+  t.lsite = f.lsite; t.rsite = f.rsite;
+  t.lvel_n = norm3(f.lv + cross(f.lw, f.lfoot_p - f.root_p));     // mj_objectVelocity(XBODY), linear part, at xpos
+  t.rvel_n = norm3(f.rv + cross(f.rw, f.rfoot_p - f.root_p));
+  return t;
+}
+OM_HD void a3_task_in_store(const A3TaskIn& t, float* b, size_t ld) {
+  b[0] = t.root_p.x; b[ld] = t.root_p.y; b[2 * ld] = t.root_p.z;
+  b[3 * ld] = t.root_q.w; b[4 * ld] = t.root_q.x; b[5 * ld] = t.root_q.y; b[6 * ld] = t.root_q.z;
+  b[7 * ld] = t.head_x; b[8 * ld] = t.head_y;
+  b[9 * ld] = t.lsite.x; b[10 * ld] = t.lsite.y; b[11 * ld] = t.lsite.z;
+  b[12 * ld] = t.rsite.x; b[13 * ld] = t.rsite.y; b[14 * ld] = t.rsite.z;
+  b[15 * ld] = t.lvel_n; b[16 * ld] = t.rvel_n;
+}
+OM_HD A3TaskIn a3_task_in_load(const float* b, size_t ld) {
+  A3TaskIn t;
+  t.root_p = V3{b[0], b[ld], b[2 * ld]};
+  t.root_q = Q4{b[3 * ld], b[4 * ld], b[5 * ld], b[6 * ld]};
+  t.head_x = b[7 * ld]; t.head_y = b[8 * ld];
+  t.lsite = V3{b[9 * ld], b[10 * ld], b[11 * ld]};
+  t.rsite = V3{b[12 * ld], b[13 * ld], b[14 * ld]};
+  t.lvel_n = b[15 * ld]; t.rvel_n = b[16 * ld];
+  return t;
+}
+
+// sequence[t1], sequence[t2] kept in registers: they change only when a target is reached
+struct A3Targets { V3 p1; float th1; V3 p2; float th2; };
+template <class Seq>
+OM_HD A3Targets a3_targets_load(const A3TaskRegs& s, const Seq& seq) {
+  return A3Targets{V3{seq(s.t1, 0), seq(s.t1, 1), seq(s.t1, 2)}, seq(s.t1, 3), V3{seq(s.t2, 0), seq(s.t2, 1), seq(s.t2, 2)},
+                   seq(s.t2, 3)};
+}
+
 // transforms3d quaternions.quat2mat (scale-invariant: s = 2/|q|^2), rows 0..2
 OM_HD void tf3_quat2mat(Q4 q, float (&m)[9]) {
   const float nq = fmaf(q.w, q.w, fmaf(q.x, q.x, fmaf(q.y, q.y, q.z * q.z)));
@@ -122,17 +163,15 @@ OM_HD void a3_obs_robot(const float (&q)[A3_NQ], const float (&qd)[A3_NV], float
   for (int k = 0; k < 12; ++k) obs[19 + k] = qd[6 + k];
 }
 
-// WalkingTask.step + calc_reward + done for one env.  Seq: float operator()(int step, int component).
+// WalkingTask.step + calc_reward + done for one env.  Seq: float operator()(int step, int component); `tc` caches
+// sequence[t1] / sequence[t2] across steps.  Fills obs[31..40], the six weighted terms, their sum and done.
 template <class Seq>
-OM_HD void a3_task_step(const A3TaskConst& C, const A3Feat& f, A3TaskRegs& s, const Seq& seq, float l_grf, float r_grf,
-                        float min_z, bool foot_contact, bool bad_collision, float (&obs)[A3_NOBS], float (&terms)[6],
-                        float& total, bool& done) {
+OM_HD void a3_task_step(const A3TaskConst& C, const A3TaskIn& f, A3TaskRegs& s, A3Targets& tc, const Seq& seq, float l_grf,
+                        float r_grf, float min_z, bool foot_contact, bool bad_collision, float (&obs)[A3_NOBS],
+                        float (&terms)[6], float& total, bool& done) {
   s.phase += 1;                                                      // :248-250
   if (s.phase >= C.period) s.phase = 0;
-  const V3 lvel = f.lv + cross(f.lw, f.lfoot_p - f.root_p);          // mj_objectVelocity(XBODY), linear part
-  const V3 rvel = f.rv + cross(f.rw, f.rfoot_p - f.root_p);
-  V3 tgt{seq(s.t1, 0), seq(s.t1, 1), seq(s.t1, 2)};                  // :266-283
-  float dl = norm3(f.lsite - tgt), dr = norm3(f.rsite - tgt);
+  float dl = norm3(f.lsite - tc.p1), dr = norm3(f.rsite - tc.p1);    // :266-283
   if ((double)dl < C.target_radius || (double)dr < C.target_radius) {
     s.reached = 1;
     s.frames += 1;
@@ -141,18 +180,18 @@ OM_HD void a3_task_step(const A3TaskConst& C, const A3Feat& f, A3TaskRegs& s, co
     s.frames = 0;
   }
   if (s.reached && s.frames >= C.delay_frames) {                     // :286-289, update_target_steps :228-244
+    const int old_t2 = s.t2;
     s.t1 = s.t2;
     s.t2 += 1;
     if (s.t2 == s.seq_len) s.t2 = s.seq_len - 1;
     s.reached = 0;
     s.frames = 0;
-    tgt = V3{seq(s.t1, 0), seq(s.t1, 1), seq(s.t1, 2)};
-    dl = norm3(f.lsite - tgt);
-    dr = norm3(f.rsite - tgt);
+    tc.p1 = tc.p2;
+    tc.th1 = tc.th2;
+    if (s.t2 != old_t2) { tc.p2 = V3{seq(s.t2, 0), seq(s.t2, 1), seq(s.t2, 2)}; tc.th2 = seq(s.t2, 3); }
+    dl = norm3(f.lsite - tc.p1);
+    dr = norm3(f.rsite - tc.p1);
   }
-  const float th1 = seq(s.t1, 3);
-  const V3 tgt2{seq(s.t2, 0), seq(s.t2, 1), seq(s.t2, 2)};
-  const float th2 = seq(s.t2, 3);
 
   // ---- update_goal_steps :184-225: inv([R p; 0 1]) [Rz(theta) t; 0 1]
   float R[9];
@@ -162,9 +201,9 @@ OM_HD void a3_task_step(const A3TaskConst& C, const A3Feat& f, A3TaskRegs& s, co
   obs[32] = lrow[5];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    const V3 d = (i == 0 ? tgt : tgt2) - f.root_p;
+    const V3 d = (i == 0 ? tc.p1 : tc.p2) - f.root_p;
     float st, ct;
-    sincosf(i == 0 ? th1 : th2, &st, &ct);
+    sincosf(i == 0 ? tc.th1 : tc.th2, &st, &ct);
     const float a = fmaf(R[0], ct, R[3] * st), b = fmaf(R[1], ct, R[4] * st);   // column 0 of R^T Rz
     const float cy = sqrtf(fmaf(a, a, b * b));
     const bool walk = s.mode != A3_STANDING;
@@ -180,10 +219,10 @@ OM_HD void a3_task_step(const A3TaskConst& C, const A3Feat& f, A3TaskRegs& s, co
   const float PI4 = 0.78539816339744831f;
   const float nl = fminf(l_grf, C.fmax) / C.fmax * 2.f - 1.f, nr = fminf(r_grf, C.fmax) / C.fmax * 2.f - 1.f;
   const float frc = (tanf(PI4 * l_frc_c * nl) + tanf(PI4 * r_frc_c * nr)) * 0.5f;      // rewards.py:65-83
-  const float vl = fminf(norm3(lvel), C.vmax) / C.vmax * 2.f - 1.f, vr = fminf(norm3(rvel), C.vmax) / C.vmax * 2.f - 1.f;
+  const float vl = fminf(f.lvel_n, C.vmax) / C.vmax * 2.f - 1.f, vr = fminf(f.rvel_n, C.vmax) / C.vmax * 2.f - 1.f;
   const float vel = (tanf(PI4 * l_vel_c * vl) + tanf(PI4 * r_vel_c * vr)) * 0.5f;      // rewards.py:85-102
   float sh, ch;
-  sincosf(0.5f * th1, &sh, &ch);                                                       // euler2quat(0, 0, theta)
+  sincosf(0.5f * tc.th1, &sh, &ch);                                                    // euler2quat(0, 0, theta)
   const float inner = fmaf(ch, f.root_q.w, sh * f.root_q.z);
   const float orient = expf(-10.f * (1.f - inner * inner));                            // rewards.py:121-126
   // rewards.py:27-40; the dead-zone test is evaluated in double on the fp32 inputs (root z is qpos[2] itself)
@@ -193,10 +232,10 @@ OM_HD void a3_task_step(const A3TaskConst& C, const A3Feat& f, A3TaskRegs& s, co
   const float height = expf(-40.f * errf * errf);
   const float fd = fminf(dl, dr);                                                      // :56-72
   const float hit = s.reached ? expf(-fd / 0.25f) : 0.f;
-  const float mx = (tgt.x + tgt2.x) * 0.5f - f.root_p.x, my = (tgt.y + tgt2.y) * 0.5f - f.root_p.y;
+  const float mx = (tc.p1.x + tc.p2.x) * 0.5f - f.root_p.x, my = (tc.p1.y + tc.p2.y) * 0.5f - f.root_p.y;
   const float progress = expf(-sqrtf(fmaf(mx, mx, my * my)) * 0.5f);
   const float step_r = fmaf(0.8f, hit, 0.2f * progress);
-  const float hx = f.head_p.x - f.root_p.x, hy = f.head_p.y - f.root_p.y;
+  const float hx = f.head_x - f.root_p.x, hy = f.head_y - f.root_p.y;
   const float upper = expf(-10.f * fmaf(hx, hx, hy * hy));
   terms[0] = 0.150f * frc; terms[1] = 0.150f * vel; terms[2] = 0.050f * orient;
   terms[3] = 0.050f * height; terms[4] = 0.450f * step_r; terms[5] = 0.050f * upper;

@@ -31,6 +31,7 @@ extern "C" void host_a3_rollout(const float* lut6, int period, int delay, double
                                 float* obs, float* terms, float* reward, unsigned char* done) {
   const A3TaskConst C = make_const(lut6, period, delay, radius, gh, dz, fmax);
   A3TaskRegs s{ints[0], ints[1], ints[2], ints[3], ints[4], ints[5], ints[6]};
+  A3Targets tc = a3_targets_load(s, SeqHost{seq});
   for (int t = 0; t < T; ++t) {
     float q[A3_NQ], qd[A3_NV], o[A3_NOBS], tr[6], total;
     bool d;
@@ -41,7 +42,10 @@ extern "C" void host_a3_rollout(const float* lut6, int period, int delay, double
     A3Sink<NullFkSink> S{};
     om_fk_stick_figure_a3(q, qd, S);
     const int fl = (int)c[3];
-    a3_task_step(C, S.f, s, SeqHost{seq}, c[0], c[1], c[2], (fl & 1) != 0, (fl & 2) != 0, o, tr, total, d);
+    // through the 17-float record, like the time-parallel path
+    float rec[A3_NFEAT];
+    a3_task_in_store(a3_task_in(S.f), rec, 1);
+    a3_task_step(C, a3_task_in_load(rec, 1), s, tc, SeqHost{seq}, c[0], c[1], c[2], (fl & 1) != 0, (fl & 2) != 0, o, tr, total, d);
     std::memcpy(obs + t * A3_NOBS, o, sizeof o);
     std::memcpy(terms + t * 6, tr, sizeof tr);
     reward[t] = total;

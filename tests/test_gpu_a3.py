@@ -23,9 +23,13 @@ def _soa_t(x):
     return torch.as_tensor(np.ascontiguousarray(np.transpose(x, (1, 2, 0)), dtype=np.float32), device="cuda")
 
 
-@pytest.mark.parametrize("multi_step", [False, True])
-def test_a3_step_vs_reference_task_fixture(a3_model, multi_step):
+@pytest.mark.parametrize("multi_step", [False, "fused", "time_parallel"])
+def test_a3_step_vs_reference_task_fixture(a3_model, multi_step, monkeypatch):
+    """One step per call; T steps in one call through the fused one-thread-per-env kernel; and through the
+    time-parallel pair (FK pass over (env, t) + sequential task pass)."""
     import torch
+    if multi_step:
+        monkeypatch.setenv("OM_A3_SPLIT", "1" if multi_step == "time_parallel" else "0")
     gold = A.golden()
     n, T = gold["step_done"].shape
     task = _task(a3_model, n)
