@@ -293,8 +293,9 @@ extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const flo
   constexpr int BLOCK = 64;
   const int grid = ceil_div(n, BLOCK);
   cudaStream_t st = (cudaStream_t)stream;
-  // Few envs, several steps: the env axis alone cannot fill 148 SMs x 2048 threads -> time-parallel replay.
-  int split = !want_fk && n_steps >= 4 && (long long)n < 148LL * 1024;
+  // Several steps: time-parallel replay (measured faster than the fused kernel at 16384 and at 262144 envs x 64 steps:
+  // 0.37 vs 0.21 and 0.72 vs 0.65 of the HBM roofline); one step: the fused kernel, one launch.
+  int split = !want_fk && n_steps >= 2;
   if (const char* f = getenv("OM_A3_SPLIT")) split = atoi(f) != 0 && !want_fk;      // tuning / test hook
   if (split) {
     const size_t need = (size_t)n_steps * A3_NFEAT * (size_t)ld;

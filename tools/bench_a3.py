@@ -78,7 +78,7 @@ def measure(envs=16384, horizon=64, steps=20, warmup=3, per_step=False):
     return {"workload": f"A3 PPO walk rollout {n} envs x {T} steps (configs[2])", "per_step_launches": args.per_step,
             "value": n * T / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "task_kernel_ms": kms,
             "gpu_launches": Kn.launch_count(),
-            "roofline": {"bound": "hbm", "kernel": "a3_task_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
+            "roofline": {"bound": "hbm", "kernel": "a3_feat_kernel + a3_seq_kernel (time-parallel replay)", "achieved": achieved, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "bytes_per_env_step": BYTES_PER_ENV_STEP}}
 
 
