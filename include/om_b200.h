@@ -267,6 +267,24 @@ int om_adv_stats(const double* moments, int unbiased, double eps, double* stats,
  * stats[1]=denom (advantage normalisation); in place allowed. */
 int om_normalize(const float* x, const double* stats, int rows, int n, int ld, float* y, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * N1 (next row: the step immediately before the path): what feeds mj_step.
+ * om_action_affine: LocoEnvBase._preprocess_action (loco_env_base.py:1050-1069): ctrl = action * delta + mean
+ *   (delta, mean = half range / mid point of the actuator ctrlrange, loco_env_base.py:165-175).
+ * om_pd_torque: JVRC.step + do_simulation (environments/robot.py:88-115) around MujocoRobotInterface.step_pd
+ *   (interfaces/mujoco_robot_interface.py:425-443):  p = target (+ motor_offset when add_offset != 0),
+ *   tau = kp (p - q_act) + kd (v - dq_act),  ctrl = tau / gear.  vel_target NULL = zeros (robot.py:111).
+ * action / target / ctrl are [nu][ld]; qpos [nq][ld], qvel [nv][ld]. */
+typedef struct OmActionSpec { int nu; float delta[32], mean[32]; } OmActionSpec;
+typedef struct OmPdSpec {
+  int nu;
+  int32_t qposadr[32], dofadr[32];   /* qpos / qvel address of each actuated joint */
+  float kp[32], kd[32], gear[32], offset[32];
+} OmPdSpec;
+int om_action_affine(const OmActionSpec* spec, const float* action, int n, int ld, float* ctrl, void* stream);
+int om_pd_torque(const OmPdSpec* spec, const float* target, const float* vel_target, const float* qpos, const float* qvel,
+                 int add_offset, int n, int ld, float* ctrl, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

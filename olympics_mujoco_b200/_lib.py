@@ -64,6 +64,15 @@ class OmDiscDesc(C.Structure):
                [(k, C.c_void_p) for k in ("w1", "b1", "w2", "b2", "wmu", "bmu", "wlv", "blv", "wd", "bd")]
 
 
+class OmActionSpec(C.Structure):
+    _fields_ = [("nu", C.c_int), ("delta", C.c_float * 32), ("mean", C.c_float * 32)]
+
+
+class OmPdSpec(C.Structure):
+    _fields_ = [("nu", C.c_int), ("qposadr", C.c_int32 * 32), ("dofadr", C.c_int32 * 32), ("kp", C.c_float * 32),
+                ("kd", C.c_float * 32), ("gear", C.c_float * 32), ("offset", C.c_float * 32)]
+
+
 _P, _I, _F, _D = C.c_void_p, C.c_int, C.c_float, C.c_double
 _U64, _U32 = C.c_uint64, C.c_uint32
 
@@ -93,6 +102,8 @@ PROTOTYPES = {
     "om_disc_create": (_I, [C.POINTER(OmDiscDesc), C.POINTER(_P)]),
     "om_disc_destroy": (None, [_P]),
     "om_disc_reward": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "om_action_affine": (_I, [C.POINTER(OmActionSpec), _P, _I, _I, _P, _P]),
+    "om_pd_torque": (_I, [C.POINTER(OmPdSpec), _P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "om_ppo_returns": (_I, [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P]),
     "om_gae": (_I, [_P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P, _P]),
     "om_moments": (_I, [_P, _I, _I, _I, _I, _P, _P]),

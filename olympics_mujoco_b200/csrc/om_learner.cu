@@ -174,17 +174,49 @@ static int launch_affine_scan(const AffineIn& in, int T, int n, int ld, float* o
 }
 
 // ---------------------------------------------------------------- K6: moment partial sums
-// grid = (env chunks, C).  float64 accumulation: per-thread -> warp shuffle -> one atomicAdd per warp.
+// grid = (env chunks, C, row slices).  float64 accumulation: per-thread -> warp shuffle -> one atomicAdd per warp.
+// VEC = 4: 16-byte loads, four rows in flight per thread (64 B per thread outstanding -- a scalar one-load-per-iteration
+// loop left the 262 MB observation buffer at 1.9 TB/s); VEC = 1 serves unaligned or ragged (n % 4, ld % 4) buffers.
+template <int VEC>
 __global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ x, int rows, int C, int n, int ld,
                                                       double* __restrict__ out) {
   const int c = blockIdx.y;
   double s = 0.0, s2 = 0.0;
-  for (int r = blockIdx.z; r < rows; r += gridDim.z) {
-    const float* row = x + ((size_t)r * C + c) * ld;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-      const double v = row[i];
-      s += v;
-      s2 = fma(v, v, s2);
+  const int nv = n / VEC;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nv) {
+    constexpr int U = 4;
+    const int gz = gridDim.z;
+    int r = blockIdx.z;
+    for (; r + (U - 1) * gz < rows; r += U * gz) {
+      float v[U][VEC];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float* row = x + ((size_t)(r + u * gz) * C + c) * ld;
+        if (VEC == 4) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(row) + i);
+          v[u][0] = q.x; v[u][1 % VEC] = q.y; v[u][2 % VEC] = q.z; v[u][3 % VEC] = q.w;
+        } else {
+          v[u][0] = __ldg(row + i);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const double d = v[u][k];
+          s += d;
+          s2 = fma(d, d, s2);
+        }
+    }
+    for (; r < rows; r += gz) {
+      const float* row = x + ((size_t)r * C + c) * ld;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const double d = __ldg(row + (size_t)i * VEC + k);
+        s += d;
+        s2 = fma(d, d, s2);
+      }
     }
   }
 #pragma unroll
@@ -192,7 +224,7 @@ __global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ 
     s += __shfl_xor_sync(0xffffffffu, s, o);
     s2 += __shfl_xor_sync(0xffffffffu, s2, o);
   }
-  if ((threadIdx.x & 31) == 0) {
+  if ((threadIdx.x & 31) == 0 && (s != 0.0 || s2 != 0.0)) {
     atomicAdd(out + c, s);
     atomicAdd(out + C + c, s2);
   }
@@ -263,16 +295,18 @@ extern "C" int om_moments(const float* x, int rows, int C, int n, int ld, double
   OM_REQUIRE(rows >= 0 && C >= 1 && n >= 0 && ld >= n, "om_moments: bad sizes");
   if (rows == 0 || n == 0) return 0;
   OM_REQUIRE(x && out, "om_moments: null argument");
-  int gx = ceil_div(n, 256 * 4);
+  const bool vec = (n % 4 == 0) && (ld % 4 == 0) && ((uintptr_t)x % 16 == 0);
+  int gx = ceil_div(vec ? n / 4 : n, 256);
   if (gx < 1) gx = 1;
-  if (gx > 1184) gx = 1184;
-  // split the rows over grid.z until the launch has ~8 CTAs per SM
-  int gz = 1184 / (gx * C);
+  OM_REQUIRE(gx <= 65535 * 16, "om_moments: n too large for one launch");
+  // slice the rows over grid.z until the launch has ~8 CTAs per SM, keeping >= 4 rows per thread for the unrolled loop
+  int gz = 1184 / (gx * C > 0 ? gx * C : 1);
+  if (gz > rows / 4) gz = rows / 4;
   if (gz < 1) gz = 1;
-  if (gz > rows) gz = rows;
   if (gz > 65535) gz = 65535;
   dim3 grid(gx, C, gz);
-  moments_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, C, n, ld, out);
+  if (vec) moments_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, C, n, ld, out);
+  else moments_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, C, n, ld, out);
   OM_LAUNCHED();
   return 0;
 }

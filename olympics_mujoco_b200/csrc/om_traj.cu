@@ -199,15 +199,29 @@ __global__ void __launch_bounds__(BLOCK) play_h1_seq_kernel(PlayArgs a) {
 __global__ void __launch_bounds__(256) play_snapshot_kernel(OmPlayState live, OmPlayState snap, int n, int ld) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
-  snap.traj_no[e] = live.traj_no[e];
-  snap.step_no[e] = live.step_no[e];
-  snap.reset_count[e] = live.reset_count[e];
-  snap.xy_off[e] = live.xy_off[e];
-  snap.xy_off[(size_t)ld + e] = live.xy_off[(size_t)ld + e];
-  snap.prev_x_vel[e] = live.prev_x_vel[e];
+  // all loads first (the pointers may alias as far as the compiler knows: a load-store-load chain costs 34 round trips)
+  double cq[17], xo[2];
+  float pd[17];
+#pragma unroll
   for (int k = 0; k < 17; ++k) {
-    snap.curr_qpos[(size_t)k * ld + e] = live.curr_qpos[(size_t)k * ld + e];
-    snap.pending[(size_t)(17 + k) * ld + e] = live.pending[(size_t)(17 + k) * ld + e];
+    cq[k] = live.curr_qpos[(size_t)k * ld + e];
+    pd[k] = live.pending[(size_t)(17 + k) * ld + e];
+  }
+  xo[0] = live.xy_off[e];
+  xo[1] = live.xy_off[(size_t)ld + e];
+  const int32_t tr = live.traj_no[e], st = live.step_no[e];
+  const uint32_t rc = live.reset_count[e];
+  const float pxv = live.prev_x_vel[e];
+  snap.traj_no[e] = tr;
+  snap.step_no[e] = st;
+  snap.reset_count[e] = rc;
+  snap.xy_off[e] = xo[0];
+  snap.xy_off[(size_t)ld + e] = xo[1];
+  snap.prev_x_vel[e] = pxv;
+#pragma unroll
+  for (int k = 0; k < 17; ++k) {
+    snap.curr_qpos[(size_t)k * ld + e] = cq[k];
+    snap.pending[(size_t)(17 + k) * ld + e] = pd[k];
   }
 }
 

@@ -290,8 +290,12 @@ class LocoEnvBase:
     def _preprocess_action(self, action):
         """:1050-1069."""
         a = torch.as_tensor(action, device=self._device, dtype=torch.float32)
-        return a * torch.as_tensor(self.norm_act_delta, device=self._device, dtype=torch.float32) + \
-            torch.as_tensor(self.norm_act_mean, device=self._device, dtype=torch.float32)
+        single = a.dim() == 1
+        a = a.unsqueeze(0) if single else a
+        if getattr(self, "_action_kernel_spec", None) is None:
+            self._action_kernel_spec = Kn.make_action_spec(self.norm_act_delta, self.norm_act_mean)
+        ctrl = Kn.action_affine(self._action_kernel_spec, a.t().contiguous()).t()      # kernel works on [nu, n] SoA
+        return ctrl[0] if single else ctrl
 
     def attach_dynamics(self, fn):
         """``fn(env, ctrl [n, nu]) -> (qpos [n, nq], qvel [n, nv])``: the physics between two observations

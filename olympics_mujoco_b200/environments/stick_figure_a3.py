@@ -36,6 +36,14 @@ class JVRC:
         adr = [int(model.jnt_qposadr[model.jnt_names.index(j)]) for j in model.actuator_joint]
         self.motor_offset = np.array([self.init_qpos_[i] for i in adr])
         self.prev_action = None
+        dadr = [int(model.jnt_dofadr[model.jnt_names.index(j)]) for j in model.actuator_joint]
+        gear = np.asarray(model.actuator_gear, dtype=np.float64).reshape(len(adr), -1)[:, 0]
+        self._pd_spec = Kn.make_pd_spec(adr, dadr, self.kp, self.kd, gear, np.zeros(len(adr)))
+
+    def pd_ctrl(self, target, qpos, qvel):
+        """One PD evaluation of do_simulation (robot.py:109-115 around step_pd): ``ctrl = (kp (target - q) - kd dq) / gear``
+        for target [12, n], qpos [25, n], qvel [24, n]; the physics callable runs it once per simulation sub-step."""
+        return Kn.pd_torque(self._pd_spec, target, qpos, qvel, add_offset=False)
 
 
 class StickFigureA3:

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import OmA3Out, OmA3State, OmA3TaskDesc, OmDiscDesc, OmH1Spec, OmModelDesc, OmPlayOut, OmPlayState, check
+from ._lib import OmA3Out, OmA3State, OmA3TaskDesc, OmActionSpec, OmDiscDesc, OmH1Spec, OmPdSpec, OmModelDesc, OmPlayOut, OmPlayState, check
 from .mjcf import KinematicModel
 
 
@@ -291,6 +291,42 @@ class A3Task:
         check(_lib.load().om_a3_task_step(self.dm.handle, self.handle, _p(qpos, torch.float32), _p(qvel, torch.float32),
                                           _p(contact, torch.float32), T, C.byref(st), C.byref(po), n, max(n, 1), _stream()))
         return out
+
+
+# ------------------------------------------------------------------------------------------- actions (N1)
+def make_action_spec(delta, mean):
+    sp = OmActionSpec()
+    sp.nu = len(delta)
+    for a, (d, m) in enumerate(zip(delta, mean)):
+        sp.delta[a], sp.mean[a] = float(d), float(m)
+    return sp
+
+
+def make_pd_spec(qposadr, dofadr, kp, kd, gear, offset):
+    sp = OmPdSpec()
+    sp.nu = len(qposadr)
+    for a in range(sp.nu):
+        sp.qposadr[a], sp.dofadr[a] = int(qposadr[a]), int(dofadr[a])
+        sp.kp[a], sp.kd[a], sp.gear[a], sp.offset[a] = float(kp[a]), float(kd[a]), float(gear[a]), float(offset[a])
+    return sp
+
+
+def action_affine(spec, action, out=None):
+    """_preprocess_action: action [nu, n] in [-1, 1] -> ctrl [nu, n]."""
+    n = action.shape[-1]
+    out = torch.empty_like(action) if out is None else out
+    check(_lib.load().om_action_affine(C.byref(spec), _p(action, torch.float32), n, max(n, 1), _p(out, torch.float32), _stream()))
+    return out
+
+
+def pd_torque(spec, target, qpos, qvel, vel_target=None, add_offset=True, out=None):
+    """robot.py do_simulation inner body: target [nu, n] (+ motor offset), qpos [nq, n], qvel [nv, n] -> ctrl [nu, n]."""
+    n = target.shape[-1]
+    out = torch.empty_like(target) if out is None else out
+    check(_lib.load().om_pd_torque(C.byref(spec), _p(target, torch.float32), _p(vel_target, torch.float32),
+                                   _p(qpos, torch.float32), _p(qvel, torch.float32), int(bool(add_offset)), n, max(n, 1),
+                                   _p(out, torch.float32), _stream()))
+    return out
 
 
 # ------------------------------------------------------------------------------------------- discriminator (K4)
