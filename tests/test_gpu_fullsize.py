@@ -22,8 +22,8 @@ def _h1_setup(n, seed, env_id0=0):
 
 def test_h1_playback_full_size_properties(monkeypatch):
     """4096 envs x 500 steps: (1) the time-parallel kernel and the sequential-in-time kernel agree bit for bit on every
-    output; (2) the observation is exactly the table row of the recorded (traj_no, step_no); (3) the index advances by
-    one except at wrap resets, which happen exactly at step_no == T; (4) quaternions are unit; (5) the reward is
+    integer / gathered output and within the path's 1e-5 tolerance on the FK outputs; (2) the observation is exactly the
+    table row of the recorded (traj_no, step_no); (3) the index advances by one except at wrap resets, which happen exactly at step_no == T; (4) quaternions are unit; (5) the reward is
     exp(-(previous dq_pelvis_tx - 1.25)^2); (6) fallen is never raised on the non-terminal dataset."""
     import torch
     from olympics_mujoco_b200 import kernels as Kn
@@ -37,9 +37,15 @@ def test_h1_playback_full_size_properties(monkeypatch):
         outs[chunk] = (out, traj.traj_no.clone(), traj.step_no.clone(), traj.reset_count.clone(), state["curr_qpos"].clone())
     a, b = outs["7"], outs["1000000"]
     for k in a[0]:
-        assert torch.equal(a[0][k], b[0][k]), f"time-parallel and sequential kernels differ in {k}"
-    for i in range(1, 5):
+        if k in ("xpos", "xquat", "site_xpos", "cvel"):
+            # the Euler sum is re-associated through the float64 prefix table: q agrees to ~1e-15, its fp32 image and the
+            # FK outputs to the last bit or two
+            assert torch.allclose(a[0][k], b[0][k], rtol=1e-5, atol=1e-5), f"time-parallel vs sequential: {k}"
+        else:
+            assert torch.equal(a[0][k], b[0][k]), f"time-parallel and sequential kernels differ in {k}"
+    for i in range(1, 4):
         assert torch.equal(a[i], b[i])
+    assert torch.allclose(a[4], b[4], rtol=1e-13, atol=1e-13)
     out = a[0]
     tr, st = out["traj_no_t"].long(), out["step_no_t"].long()
     Tt = table.shape[2]
@@ -79,7 +85,11 @@ def test_a3_rollout_full_size_properties(a3_model, monkeypatch):
         task.reset(q0, v0, iteration_count=6000.0)
         if split == "0":
             qpos = q0[None] + 0.01 * torch.randn((T, 25, n), device="cuda", generator=g).cumsum(0)
-            qpos[:, 2] -= torch.linspace(0, 0.9, T, device="cuda")[:, None] * (torch.rand(n, device="cuda", generator=g) < 0.1)
+            # a tenth of the envs fold their legs (hip flexion, knee flexion) until the feet come up under the root
+            fold = torch.linspace(0, 1, T, device="cuda")[:, None] * (torch.rand(n, device="cuda", generator=g) < 0.1)
+            for hip, knee in ((7, 10), (13, 16)):
+                qpos[:, hip] -= 1.3 * fold
+                qpos[:, knee] -= 1.6 * fold
             qvel = torch.randn((T, 24, n), device="cuda", generator=g)
             con = torch.stack([torch.rand((T, n), device="cuda", generator=g) * 400, torch.rand((T, n), device="cuda", generator=g) * 400,
                                (torch.rand((T, n), device="cuda", generator=g) - 0.5) * 0.02,
@@ -105,7 +115,7 @@ def test_a3_rollout_full_size_properties(a3_model, monkeypatch):
     want_done = ((root_z.double() - foot_z.double()) < 0.6) | bad
     differ = (out["done"].bool() != want_done)
     assert int((differ & (margin > 2e-6)).sum()) == 0 and int(differ.sum()) <= 2
-    assert 0.01 < float(out["done"].float().mean()) < 0.5
+    assert bool((want_done & ~bad).any()) and bool(bad.any()) and 0.005 < float(out["done"].float().mean()) < 0.5
     assert torch.isfinite(out["obs"]).all() and torch.isfinite(out["reward"]).all()
     assert float(out["reward"].min()) > -0.31 and float(out["reward"].max()) < 1.0 + 1e-5   # 0.15*(2 tan terms in [-1,1]) + ...
 
