@@ -258,6 +258,11 @@ def run_ours(args):
             except Exception as e:                              # never lose the headline line to a side measurement
                 other["a3_error"] = repr(e)
             try:
+                import bench_h1_step
+                other["h1_single_step_1048576"] = bench_h1_step.measure(steps=10, warmup=3)
+            except Exception as e:
+                other["h1_step_error"] = repr(e)
+            try:
                 import bench_disc
                 other["disc_reward_65536"] = bench_disc.measure(steps=20, warmup=3)
             except Exception as e:

@@ -110,6 +110,11 @@ int om_h1_step(const OmModel* m, const OmH1Spec* spec, const float* qpos, const 
                float* xpos, float* xquat, float* site_xpos, float* cvel,
                float* obs, float* reward, uint8_t* absorbing, void* stream);
 
+/* LocoEnvBase.set_sim_state (loco_env_base.py:659-684) for joint-only specs: sample [2*n_obs_q][ld] in observation-spec
+ * order (positions then velocities) -> qpos [nq][ld], qvel [nv][ld] in MJCF order (the inverse of the gather above). */
+int om_set_sim_state(const OmModel* m, const OmH1Spec* spec, const float* sample, int n, int ld, float* qpos, float* qvel,
+                     void* stream);
+
 /* has_fallen over a batch of observations (create_dataset check, loco_env_base.py:950-957) */
 int om_h1_has_fallen(const float* obs, int n, int ld, uint8_t* fallen, void* stream);
 

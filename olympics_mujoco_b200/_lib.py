@@ -87,6 +87,7 @@ PROTOTYPES = {
     "om_model_is_specialised": (_I, [_P]),
     "om_fk": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
     "om_h1_step": (_I, [_P, C.POINTER(OmH1Spec), _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "om_set_sim_state": (_I, [_P, C.POINTER(OmH1Spec), _P, _I, _I, _P, _P, _P]),
     "om_h1_has_fallen": (_I, [_P, _I, _I, _P, _P]),
     "om_traj_create": (_I, [_P, _I, _I, _I, C.POINTER(_P)]),
     "om_traj_destroy": (None, [_P]),

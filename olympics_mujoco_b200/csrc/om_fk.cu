@@ -109,6 +109,18 @@ __global__ void __launch_bounds__(256) h1_fallen_kernel(const float* __restrict_
   fallen[env] = h1_has_fallen(obs[env], obs[(size_t)ld + env], obs[(size_t)2 * ld + env], obs[(size_t)3 * ld + env]) ? 1 : 0;
 }
 
+// set_sim_state (loco_env_base.py:659-684): sample rows in observation-spec order -> qpos / qvel rows in MJCF order
+__global__ void __launch_bounds__(256) set_sim_state_kernel(H1SpecDev sp, const float* __restrict__ sample, int n, int ld,
+                                                            float* __restrict__ qpos, float* __restrict__ qvel) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  const int nq = sp.n_obs_q;
+  for (int k = 0; k < nq; ++k) {
+    qpos[(size_t)sp.perm[k] * ld + env] = sample[(size_t)k * ld + env];
+    qvel[(size_t)sp.perm[k] * ld + env] = sample[(size_t)(nq + k) * ld + env];
+  }
+}
+
 int make_spec(const OmH1Spec* spec, const OmModel* m, H1SpecDev* out) {
   OM_REQUIRE(spec->n_obs_q >= 6 && spec->n_obs_q <= 32, "OmH1Spec.n_obs_q %d outside [6,32]", spec->n_obs_q);
   OM_REQUIRE(spec->n_obs_q <= m->host.nq && spec->n_obs_q <= m->host.nv, "OmH1Spec.n_obs_q exceeds nq/nv");
@@ -183,6 +195,19 @@ extern "C" int om_h1_has_fallen(const float* obs, int n, int ld, uint8_t* fallen
   if (n == 0) return 0;
   OM_REQUIRE(obs && fallen, "om_h1_has_fallen: null argument");
   h1_fallen_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(obs, n, ld, fallen);
+  OM_LAUNCHED();
+  return 0;
+}
+
+extern "C" int om_set_sim_state(const OmModel* m, const OmH1Spec* spec, const float* sample, int n, int ld, float* qpos,
+                                float* qvel, void* stream) {
+  OM_REQUIRE(m && spec, "om_set_sim_state: null model or spec");
+  OM_REQUIRE(n >= 0 && ld >= n, "om_set_sim_state: need 0 <= n <= ld");
+  if (n == 0) return 0;
+  OM_REQUIRE(sample && qpos && qvel, "om_set_sim_state: null argument");
+  H1SpecDev sp;
+  if (make_spec(spec, m, &sp)) return 1;
+  set_sim_state_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(sp, sample, n, ld, qpos, qvel);
   OM_LAUNCHED();
   return 0;
 }

@@ -191,6 +191,13 @@ class UnitreeH1(BaseHumanoidRobot):
         return self._out(self._modify_observation(cur_obs)), self._out(reward), self._out(absorbing), {}
 
     # ------------------------------------------------------------------ fused playback (loco_env_base.py:444-560)
+    def set_sim_state(self, sample):
+        """loco_env_base.py:659-684 as one kernel (the spec is joint positions then joint velocities)."""
+        sample = self._batched(sample).to(torch.float32)
+        if sample.shape[-1] != 2 * self._spec.n_obs_q:
+            return super().set_sim_state(sample)
+        Kn.set_sim_state(self._dm, self._spec, sample.t().contiguous(), self._data.qpos, self._data.qvel)
+
     def make_rollout_buffers(self, n_steps, want=("xpos", "xquat", "site_xpos", "cvel", "obs", "reward", "fallen",
                                                   "traj_no_t", "step_no_t")):
         m, n, dev = self._model, self.n_envs, self._device

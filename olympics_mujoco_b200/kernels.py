@@ -138,6 +138,13 @@ def h1_step(dm, spec, qpos, qvel, prev_x_vel, want_fk=True, out=None):
     return out
 
 
+def set_sim_state(dm, spec, sample, qpos, qvel):
+    """A7: sample [2*n_obs_q, n] (spec order) -> qpos [nq, n], qvel [nv, n] (MJCF order), in place."""
+    n = sample.shape[-1]
+    check(_lib.load().om_set_sim_state(dm.handle, C.byref(spec), _p(sample, torch.float32), n, max(n, 1),
+                                       _p(qpos, torch.float32), _p(qvel, torch.float32), _stream()))
+
+
 def h1_has_fallen(obs):
     n = obs.shape[-1]
     fallen = torch.empty(n, dtype=torch.uint8, device=obs.device)

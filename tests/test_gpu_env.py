@@ -141,3 +141,21 @@ def test_observation_helper_generic_spec():
                           v[:, [9]]], axis=1)
     assert_close(obs, exp, "generic obs")
     assert_close(oh.get_from_obs(torch.as_tensor(obs), "imu").numpy(), ref["site_xpos"][:, 0], "get_from_obs")
+
+
+def test_set_sim_state_kernel_matches_named_scatter():
+    """UnitreeH1.set_sim_state (one kernel) == the reference's per-key scatter (LocoEnvBase.set_sim_state)."""
+    import torch
+    from olympics_mujoco_b200 import LocoEnvBase
+    from olympics_mujoco_b200.environments.loco_env_base import LocoEnvBase as Base
+    env = LocoEnvBase.make("UnitreeH1.walk.real", n_envs=19, seed=2)
+    rng = np.random.default_rng(0)
+    sample = torch.as_tensor(rng.normal(0, 1, (19, 34)).astype(np.float32), device="cuda")
+    env.set_sim_state(sample)
+    q1, v1 = env.data.qpos.clone(), env.data.qvel.clone()
+    env.data.qpos.zero_(); env.data.qvel.zero_()
+    Base.set_sim_state(env, sample)
+    assert torch.equal(q1, env.data.qpos) and torch.equal(v1, env.data.qvel)
+    from oracle import h1 as OH
+    qo, vo = OH.set_sim_state(env._model, sample.cpu().numpy().astype(np.float64))
+    assert np.array_equal(q1.cpu().numpy().T, qo.astype(np.float32)) and np.array_equal(v1.cpu().numpy().T, vo.astype(np.float32))

@@ -1,0 +1,66 @@
+"""Timing of the single-step H1 API at BASELINE.json configs[4] scale: 1 048 576 envs (what one GPU of the 1M-env job
+runs when N = 1; N = 8 gives 131 072 per GPU): trajectory next-sample (K3) + fused FK / observation / absorbing / reward
+step (K1 + K2) per env step, launched per step like a live rollout.  One JSON line (measurement aid)."""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+BYTES_PER_ENV_STEP = 1517
+
+
+def measure(envs=1 << 20, steps=20, warmup=3):
+    import bench
+    from olympics_mujoco_b200 import kernels as Kn
+    from oracle import h1 as OH
+    model, table = bench.build_table()
+    n = envs
+    dm = Kn.DeviceModel(model)
+    spec = Kn.make_h1_spec(OH.perm(model), OH.x_vel_idx(model))
+    traj = Kn.DeviceTrajectory(table, n, seed=5)
+    sample = traj.reset()
+    perm = torch.as_tensor(OH.perm(model), device="cuda")
+    qpos, qvel = torch.empty((17, n), device="cuda"), torch.empty((17, n), device="cuda")
+    out = None
+
+    def step():
+        nonlocal out
+        traj.next(sample=sample)                       # K3: index + gather (+ wrap reset)
+        Kn.set_sim_state(dm, spec, sample, qpos, qvel)   # A7 (the physics would run here)
+        out = Kn.h1_step(dm, spec, qpos, qvel, sample[17], want_fk=True, out=out)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for a, b in ev:
+        traj.next(sample=sample)
+        Kn.set_sim_state(dm, spec, sample, qpos, qvel)
+        a.record()
+        out = Kn.h1_step(dm, spec, qpos, qvel, sample[17], want_fk=True, out=out)
+        b.record()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / steps
+    kms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {"hbm_gbs": 6650.0}
+    kernel_bytes = 136 + 1104 + 128 + 4 + 1 + 4                     # qpos/qvel in, FK + obs + reward + flag out, prev x-vel
+    ach = kernel_bytes * n / (kms * 1e-3) / 1e9
+    return {"workload": f"UnitreeH1 single env step, {n} envs (configs[4] per-GPU shard at N=1)", "value": n / (ms * 1e-3),
+            "unit": "env-steps/s", "ms_per_step": ms, "h1_step_kernel_ms": kms,
+            "roofline": {"bound": "hbm", "kernel": "h1_step_kernel<WRITE_FK>", "achieved": ach, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "bytes_per_env_step": kernel_bytes}}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=1 << 20)
+    ap.add_argument("--steps", type=int, default=20)
+    a = ap.parse_args()
+    print(json.dumps(measure(a.envs, a.steps)))
