@@ -104,31 +104,46 @@ __global__ void __launch_bounds__(BLOCK) a3_task_kernel(A3Args a) {
 // ---------------------------------------------------------------- time-parallel replay (few envs, many steps)
 // The only recurrence over time is the task's integer state; everything expensive (FK, the state-independent 31
 // observation rows) depends on (env, t) alone.  Pass 1 runs one thread per (env, t) -- 16384 envs x 64 steps fill the
-// machine instead of 256 CTAs of 64 threads -- and leaves a 17-float record per env-step; pass 2 walks the T records
-// of an env sequentially (one thread per env, ~250 instructions per step) and emits what depends on the task state.
+// machine instead of 256 CTAs of 64 threads -- evaluates every piece that is independent of the footstep-target state
+// (om_a3_task.cuh: a3_task_pre) and leaves a 16-float record per env-step; pass 2 walks the T records of an env
+// sequentially (one thread per env) through the target state machine and the two terms that depend on it.
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) a3_feat_kernel(A3Args a, float* __restrict__ feat) {
   const int env = blockIdx.x * BLOCK + threadIdx.x;
   const int t = blockIdx.y;
   if (env >= a.n) return;
   const size_t ld = a.ld, e = env;
-  float q[A3_NQ], qd[A3_NV];
+  float q[A3_NQ], qd[A3_NV], con[4];
   const float* qp = a.qpos + (size_t)t * A3_NQ * ld + e;
   const float* vp = a.qvel + (size_t)t * A3_NV * ld + e;
+  const float* cp = a.contact + (size_t)t * 4 * ld + e;
 #pragma unroll
   for (int k = 0; k < A3_NQ; ++k) q[k] = qp[k * ld];
 #pragma unroll
   for (int k = 0; k < A3_NV; ++k) qd[k] = vp[k * ld];
-  if (a.o.obs) {
-    float obs[A3_NOBS];
-    a3_obs_robot(q, qd, obs);
-    float* ob = a.o.obs + (size_t)t * A3_NOBS * ld + e;
 #pragma unroll
-    for (int k = 0; k < 31; ++k) ob[k * ld] = obs[k];
-  }
+  for (int k = 0; k < 4; ++k) con[k] = cp[k * ld];
+  const int phase = (a.ints[A3I_PHASE * ld + e] + t + 1) % a.C.period;     // walking_task.py:248-250, t + 1 increments
+  const int mode = a.ints[A3I_MODE * ld + e];
+  float obs[A3_NOBS], terms[6];
+  a3_obs_robot(q, qd, obs);
   A3Sink<NullFkSink> S{};
   om_fk_stick_figure_a3(q, qd, S);
-  a3_task_in_store(a3_task_in(S.f), feat + (size_t)t * A3_NFEAT * ld + e, ld);
+  bool done;
+  const int fl = (int)con[3];
+  const A3Rec rec = a3_task_pre(a.C, a3_task_in(S.f), phase, mode, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, terms,
+                                obs[31], obs[32], done);
+  a3_rec_store(rec, feat + (size_t)t * A3_NREC * ld + e, ld);
+  if (a.o.obs) {
+    float* ob = a.o.obs + (size_t)t * A3_NOBS * ld + e;
+#pragma unroll
+    for (int k = 0; k < 33; ++k) ob[k * ld] = obs[k];
+  }
+  if (a.o.terms) {
+    float* tp = a.o.terms + (size_t)t * 6 * ld + e;
+    tp[0] = terms[0]; tp[ld] = terms[1]; tp[3 * ld] = terms[3]; tp[5 * ld] = terms[5];
+  }
+  if (a.o.done) a.o.done[(size_t)t * ld + e] = done ? 1 : 0;
 }
 
 template <int BLOCK>
@@ -140,40 +155,28 @@ __global__ void __launch_bounds__(BLOCK) a3_seq_kernel(A3Args a, const float* __
                a.ints[A3I_MODE * ld + e], a.ints[A3I_SEQLEN * ld + e], a.ints[A3I_REACHED * ld + e]};
   const SeqGlobal seq{a.sequence + e, ld};
   A3Targets tc = a3_targets_load(s, seq);
-  auto load = [&](int t, A3TaskIn& in, float (&c_)[4]) {
-    in = a3_task_in_load(feat + (size_t)t * A3_NFEAT * ld + e, ld);
-    const float* cp = a.contact + (size_t)t * 4 * ld + e;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) c_[k] = cp[k * ld];
-  };
-  A3TaskIn in;
-  float con[4];
-  load(0, in, con);
+  A3TargetTrig tg = a3_target_trig(tc);
+  A3Rec in = a3_rec_load(feat + e, ld);
   for (int t = 0; t < a.T; ++t) {
-    A3TaskIn inn = in;
-    float conn[4] = {0.f, 0.f, 0.f, 0.f};
-    if (t + 1 < a.T) load(t + 1, inn, conn);                   // independent of the task state: overlaps this step
-    float obs[A3_NOBS], terms[6], total;
-    bool done;
-    const int fl = (int)con[3];
-    a3_task_step(a.C, in, s, tc, seq, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, obs, terms, total, done);
+    A3Rec inn = in;
+    if (t + 1 < a.T) inn = a3_rec_load(feat + (size_t)(t + 1) * A3_NREC * ld + e, ld);   // independent of the task state
+    float goal[8], t2, t4, total;
+    a3_task_seq(a.C, in, s, tc, tg, seq, goal, t2, t4, total);
     if (a.o.obs) {
-      float* ob = a.o.obs + (size_t)t * A3_NOBS * ld + e;
+      float* ob = a.o.obs + ((size_t)t * A3_NOBS + 33) * ld + e;
 #pragma unroll
-      for (int k = 31; k < A3_NOBS; ++k) ob[k * ld] = obs[k];
+      for (int k = 0; k < 8; ++k) ob[k * ld] = goal[k];
     }
     if (a.o.terms) {
       float* tp = a.o.terms + (size_t)t * 6 * ld + e;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) tp[k * ld] = terms[k];
+      tp[2 * ld] = t2;
+      tp[4 * ld] = t4;
     }
     if (a.o.reward) a.o.reward[(size_t)t * ld + e] = total;
-    if (a.o.done) a.o.done[(size_t)t * ld + e] = done ? 1 : 0;
     in = inn;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) con[k] = conn[k];
   }
-  a.ints[A3I_PHASE * ld + e] = s.phase; a.ints[A3I_T1 * ld + e] = s.t1; a.ints[A3I_T2 * ld + e] = s.t2;
+  a.ints[A3I_PHASE * ld + e] = (s.phase + a.T) % a.C.period;
+  a.ints[A3I_T1 * ld + e] = s.t1; a.ints[A3I_T2 * ld + e] = s.t2;
   a.ints[A3I_FRAMES * ld + e] = s.frames; a.ints[A3I_REACHED * ld + e] = s.reached;
 }
 
@@ -298,7 +301,7 @@ extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const flo
   int split = !want_fk && n_steps >= 2;
   if (const char* f = getenv("OM_A3_SPLIT")) split = atoi(f) != 0 && !want_fk;      // tuning / test hook
   if (split) {
-    const size_t need = (size_t)n_steps * A3_NFEAT * (size_t)ld;
+    const size_t need = (size_t)n_steps * A3_NREC * (size_t)ld;
     if (task->feat_floats < need) {
       if (task->feat) OM_CUDA_OK(cudaFree(task->feat));        // synchronises: no earlier call still reads it
       task->feat = nullptr;

@@ -244,6 +244,127 @@ OM_HD void a3_task_step(const A3TaskConst& C, const A3TaskIn& f, A3TaskRegs& s, 
   done = ((double)f.root_p.z - (double)fminf(f.lsite.z, f.rsite.z) < 0.6) || bad_collision;
 }
 
+// ---------------------------------------------------------------- time-parallel split of the step tail
+// Everything in WalkingTask.step / calc_reward / done that does NOT depend on the footstep-target state (t1, t2,
+// target_reached) depends on (env, t) alone -- including the phase clock, because phase(t) = (phase0 + t + 1) mod period
+// and the mode is fixed for an episode.  The (env, t)-parallel pass evaluates those pieces (four of the six reward
+// terms with their tanf/expf, done, the clock rows of the observation) and leaves a 16-float record; the sequential
+// pass keeps only the target state machine, the goal steps, the orientation and step terms.
+constexpr int A3_NREC = 16;
+struct A3Rec {
+  V3 root_p; Q4 root_q; V3 lsite, rsite;
+  float t01, t3, t5;                  // terms[0] + terms[1], terms[3], terms[5] (summed later in the reference's order)
+};
+OM_HD void a3_rec_store(const A3Rec& r, float* b, size_t ld) {
+  b[0] = r.root_p.x; b[ld] = r.root_p.y; b[2 * ld] = r.root_p.z;
+  b[3 * ld] = r.root_q.w; b[4 * ld] = r.root_q.x; b[5 * ld] = r.root_q.y; b[6 * ld] = r.root_q.z;
+  b[7 * ld] = r.lsite.x; b[8 * ld] = r.lsite.y; b[9 * ld] = r.lsite.z;
+  b[10 * ld] = r.rsite.x; b[11 * ld] = r.rsite.y; b[12 * ld] = r.rsite.z;
+  b[13 * ld] = r.t01; b[14 * ld] = r.t3; b[15 * ld] = r.t5;
+}
+OM_HD A3Rec a3_rec_load(const float* b, size_t ld) {
+  A3Rec r;
+  r.root_p = V3{b[0], b[ld], b[2 * ld]};
+  r.root_q = Q4{b[3 * ld], b[4 * ld], b[5 * ld], b[6 * ld]};
+  r.lsite = V3{b[7 * ld], b[8 * ld], b[9 * ld]};
+  r.rsite = V3{b[10 * ld], b[11 * ld], b[12 * ld]};
+  r.t01 = b[13 * ld]; r.t3 = b[14 * ld]; r.t5 = b[15 * ld];
+  return r;
+}
+
+// (env, t)-parallel part.  `phase` is the phase AFTER this step's increment.  Writes terms[0,1,3,5], obs[31,32], done.
+OM_HD A3Rec a3_task_pre(const A3TaskConst& C, const A3TaskIn& f, int phase, int mode, float l_grf, float r_grf, float min_z,
+                        bool foot_contact, bool bad_collision, float (&terms)[6], float& clock_sin, float& clock_cos,
+                        bool& done) {
+  const float* lrow = C.lut + (size_t)phase * A3_LUT_COLS;
+  clock_sin = lrow[4];
+  clock_cos = lrow[5];
+  float r_frc_c = 1.f, r_vel_c = -1.f, l_frc_c = 1.f, l_vel_c = -1.f;                  // STANDING :83-91
+  if (mode != A3_STANDING) { r_frc_c = lrow[0]; r_vel_c = lrow[1]; l_frc_c = lrow[2]; l_vel_c = lrow[3]; }
+  const float PI4 = 0.78539816339744831f;
+  const float nl = fminf(l_grf, C.fmax) / C.fmax * 2.f - 1.f, nr = fminf(r_grf, C.fmax) / C.fmax * 2.f - 1.f;
+  const float frc = (tanf(PI4 * l_frc_c * nl) + tanf(PI4 * r_frc_c * nr)) * 0.5f;      // rewards.py:65-83
+  const float vl = fminf(f.lvel_n, C.vmax) / C.vmax * 2.f - 1.f, vr = fminf(f.rvel_n, C.vmax) / C.vmax * 2.f - 1.f;
+  const float vel = (tanf(PI4 * l_vel_c * vl) + tanf(PI4 * r_vel_c * vr)) * 0.5f;      // rewards.py:85-102
+  double err = fabs((double)f.root_p.z - (foot_contact ? (double)min_z : 0.0) - C.goal_height_ref);   // rewards.py:27-40
+  if (err < C.deadzone) err = 0.0;
+  const float errf = (float)err;
+  const float height = expf(-40.f * errf * errf);
+  const float hx = f.head_x - f.root_p.x, hy = f.head_y - f.root_p.y;
+  const float upper = expf(-10.f * fmaf(hx, hx, hy * hy));
+  terms[0] = 0.150f * frc; terms[1] = 0.150f * vel; terms[3] = 0.050f * height; terms[5] = 0.050f * upper;
+  done = ((double)f.root_p.z - (double)fminf(f.lsite.z, f.rsite.z) < 0.6) || bad_collision;           // :298-319
+  A3Rec r;
+  r.root_p = f.root_p; r.root_q = f.root_q; r.lsite = f.lsite; r.rsite = f.rsite;
+  r.t01 = terms[0] + terms[1]; r.t3 = terms[3]; r.t5 = terms[5];
+  return r;
+}
+
+// sin / cos of the cached targets' headings (they change only when a target is reached)
+struct A3TargetTrig { float s1, c1, s2, c2, sh, ch; };
+OM_HD A3TargetTrig a3_target_trig(const A3Targets& tc) {
+  A3TargetTrig g;
+  sincosf(tc.th1, &g.s1, &g.c1);
+  sincosf(tc.th2, &g.s2, &g.c2);
+  sincosf(0.5f * tc.th1, &g.sh, &g.ch);
+  return g;
+}
+
+// Sequential part: target state machine (:266-289), goal steps (:184-225), orientation and step terms, total.
+// Does NOT touch s.phase (the caller tracks it).  Writes goal[8] (obs rows 33..40), terms[2], terms[4], total.
+template <class Seq>
+OM_HD void a3_task_seq(const A3TaskConst& C, const A3Rec& f, A3TaskRegs& s, A3Targets& tc, A3TargetTrig& tg, const Seq& seq,
+                       float (&goal)[8], float& t2_orient, float& t4_step, float& total) {
+  float dl = norm3(f.lsite - tc.p1), dr = norm3(f.rsite - tc.p1);
+  if ((double)dl < C.target_radius || (double)dr < C.target_radius) {
+    s.reached = 1;
+    s.frames += 1;
+  } else {
+    s.reached = 0;
+    s.frames = 0;
+  }
+  if (s.reached && s.frames >= C.delay_frames) {
+    const int old_t2 = s.t2;
+    s.t1 = s.t2;
+    s.t2 += 1;
+    if (s.t2 == s.seq_len) s.t2 = s.seq_len - 1;
+    s.reached = 0;
+    s.frames = 0;
+    tc.p1 = tc.p2;
+    tc.th1 = tc.th2;
+    if (s.t2 != old_t2) { tc.p2 = V3{seq(s.t2, 0), seq(s.t2, 1), seq(s.t2, 2)}; tc.th2 = seq(s.t2, 3); }
+    tg = a3_target_trig(tc);
+    dl = norm3(f.lsite - tc.p1);
+    dr = norm3(f.rsite - tc.p1);
+  }
+  if (s.mode != A3_STANDING) {
+    float R[9];
+    tf3_quat2mat(f.root_q, R);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const V3 d = (i == 0 ? tc.p1 : tc.p2) - f.root_p;
+      const float st = i == 0 ? tg.s1 : tg.s2, ct = i == 0 ? tg.c1 : tg.c2;
+      const float a = fmaf(R[0], ct, R[3] * st), b = fmaf(R[1], ct, R[4] * st);
+      const float cy = sqrtf(fmaf(a, a, b * b));
+      goal[0 + i] = fmaf(R[0], d.x, fmaf(R[3], d.y, R[6] * d.z));
+      goal[2 + i] = fmaf(R[1], d.x, fmaf(R[4], d.y, R[7] * d.z));
+      goal[4 + i] = fmaf(R[2], d.x, fmaf(R[5], d.y, R[8] * d.z));
+      goal[6 + i] = cy > A3_EPS4 ? atan2f(b, a) : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) goal[i] = 0.f;
+  }
+  const float inner = fmaf(tg.ch, f.root_q.w, tg.sh * f.root_q.z);
+  t2_orient = 0.050f * expf(-10.f * (1.f - inner * inner));                            // rewards.py:121-126
+  const float fd = fminf(dl, dr);                                                      // walking_task.py:56-72
+  const float hit = s.reached ? expf(-fd / 0.25f) : 0.f;
+  const float mx = (tc.p1.x + tc.p2.x) * 0.5f - f.root_p.x, my = (tc.p1.y + tc.p2.y) * 0.5f - f.root_p.y;
+  const float progress = expf(-sqrtf(fmaf(mx, mx, my * my)) * 0.5f);
+  t4_step = 0.450f * fmaf(0.8f, hit, 0.2f * progress);
+  total = (((f.t01 + t2_orient) + f.t3) + t4_step) + f.t5;                             // StickFigureA3.py:192, dict order
+}
+
 // ---------------------------------------------------------------- reset (A13)
 OM_HD void a3_reset_uniforms(uint64_t seed, uint32_t env_id, uint32_t reset_count, float (&u)[A3_NU]) {
 #pragma unroll

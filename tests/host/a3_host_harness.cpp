@@ -55,6 +55,45 @@ extern "C" void host_a3_rollout(const float* lut6, int period, int delay, double
   std::memcpy(ints, out, sizeof out);
 }
 
+// the time-parallel split (a3_feat_kernel + a3_seq_kernel of csrc/om_a3.cu) for one env
+extern "C" void host_a3_rollout_split(const float* lut6, int period, int delay, double radius, double gh, double dz, float fmax,
+                                      const float* qpos, const float* qvel, const float* contact, int T, int* ints, float* seq,
+                                      float* obs, float* terms, float* reward, unsigned char* done) {
+  const A3TaskConst C = make_const(lut6, period, delay, radius, gh, dz, fmax);
+  float* rec = new float[(size_t)T * A3_NREC];
+  for (int t = 0; t < T; ++t) {                                   // pass 1: any order
+    float q[A3_NQ], qd[A3_NV], o[A3_NOBS], tr[6];
+    bool d;
+    std::memcpy(q, qpos + t * A3_NQ, sizeof q);
+    std::memcpy(qd, qvel + t * A3_NV, sizeof qd);
+    const float* c = contact + t * 4;
+    a3_obs_robot(q, qd, o);
+    A3Sink<NullFkSink> S{};
+    om_fk_stick_figure_a3(q, qd, S);
+    const int fl = (int)c[3];
+    const int phase = (ints[0] + t + 1) % period;
+    const A3Rec r = a3_task_pre(C, a3_task_in(S.f), phase, ints[4], c[0], c[1], c[2], (fl & 1) != 0, (fl & 2) != 0, tr, o[31],
+                                o[32], d);
+    a3_rec_store(r, rec + (size_t)t * A3_NREC, 1);
+    std::memcpy(obs + t * A3_NOBS, o, 33 * sizeof(float));
+    terms[t * 6 + 0] = tr[0]; terms[t * 6 + 1] = tr[1]; terms[t * 6 + 3] = tr[3]; terms[t * 6 + 5] = tr[5];
+    done[t] = d ? 1 : 0;
+  }
+  A3TaskRegs s{ints[0], ints[1], ints[2], ints[3], ints[4], ints[5], ints[6]};
+  A3Targets tc = a3_targets_load(s, SeqHost{seq});
+  A3TargetTrig tg = a3_target_trig(tc);
+  for (int t = 0; t < T; ++t) {                                   // pass 2: sequential
+    float goal[8], t2, t4, total;
+    a3_task_seq(C, a3_rec_load(rec + (size_t)t * A3_NREC, 1), s, tc, tg, SeqHost{seq}, goal, t2, t4, total);
+    std::memcpy(obs + t * A3_NOBS + 33, goal, sizeof goal);
+    terms[t * 6 + 2] = t2; terms[t * 6 + 4] = t4;
+    reward[t] = total;
+  }
+  delete[] rec;
+  int out[7] = {(s.phase + T) % period, s.t1, s.t2, s.frames, s.mode, s.seq_len, s.reached};
+  std::memcpy(ints, out, sizeof out);
+}
+
 extern "C" void host_a3_reset(const float* lut6, int period, int delay, double radius, double gh, double dz, float fmax,
                               const float* init_qpos, unsigned long long seed, unsigned env, unsigned rc, float step_h,
                               float* qpos, float* qvel, int* ints, float* seq, float* obs) {

@@ -206,3 +206,11 @@ def test_a3_task_device_functions_on_host(a3_model):
         reward2, done2 = np.zeros_like(reward), np.zeros_like(done)
         lib.host_a3_rollout(*consts, P(qpos), P(qvel), P(con), T, P(ints2), P(seq), P(obs2), P(terms2), P(reward2), P(done2))
         assert np.array_equal(obs2, obs) and np.array_equal(done2, done) and np.array_equal(ints2, trace[-1])
+        # the time-parallel split (what a3_feat_kernel + a3_seq_kernel compute) agrees with the fused path
+        ints3 = gold["reset_ints"][e].astype(np.int32)
+        obs3, terms3 = np.zeros_like(obs), np.zeros_like(terms)
+        reward3, done3 = np.zeros_like(reward), np.zeros_like(done)
+        lib.host_a3_rollout_split(*consts, P(qpos), P(qvel), P(con), T, P(ints3), P(seq), P(obs3), P(terms3), P(reward3), P(done3))
+        assert np.array_equal(ints3, trace[-1]) and np.array_equal(done3, done)
+        assert_close(obs3, obs, "split obs", rtol=1e-6, atol=1e-6); assert_close(terms3, terms, "split terms", rtol=1e-6, atol=1e-6)
+        assert_close(reward3, reward, "split reward", rtol=1e-6, atol=1e-6)
