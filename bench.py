@@ -117,6 +117,15 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # Pin this rank to the CPUs next to its GPU BEFORE any pinned host buffer exists: the end-to-end leg moves 289 MB
+    # per step over PCIe into host memory, and with 8 ranks a remote NUMA node halves that bandwidth.
+    full_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, T = args.envs, args.horizon
@@ -269,6 +278,8 @@ def run_ours(args):
                 other["disc_error"] = repr(e)
             line["other_configs"] = other
         if not args.no_cpu_baseline:
+            if full_affinity is not None:
+                os.sched_setaffinity(0, full_affinity)          # the CPU baseline uses every host core
             from oracle import cpu_baseline
             res = cpu_baseline.run(model, table, steps=1, warmup=0, horizon=T, budget_s=args.cpu_budget)
             line["cpu_baseline"] = {"value": res["value"], "unit": "env-steps/s", "cores": res["cores"],

@@ -322,6 +322,38 @@ class LocoEnvBase:
             return dataset
         return deepcopy(self._dataset)
 
+    def load_dataset_and_get_traj_files(self, dataset_path, freq=None):
+        """:970-1044 (N4: the "perfect"-dataset format): a dataset ``{states [N, D], last [N], ...}`` (npz path or
+        dict) -> per-key trajectory dict for ``load_trajectory(dict(traj_files=...))``.  The two spec keys a dataset
+        does not carry (root x and z) are zeros, or -- with ``freq`` -- the running integral of their velocities,
+        restarted after every ``last == 1`` (vectorised: a segmented cumulative sum)."""
+        dataset = np.load(str(dataset_path), allow_pickle=True) if not isinstance(dataset_path, dict) else dataset_path
+        self._dataset = deepcopy({k: d for k, d in dataset.items()})
+        states = np.atleast_2d(np.asarray(dataset["states"], dtype=np.float64))
+        last = np.asarray(dataset["last"])
+        rel_keys = [spec[0] for spec in self.obs_helper.observation_spec]
+        num = len(states)
+        assert states.shape[1] == len(rel_keys) - 2, "a dataset state is the observation without the first two keys"
+        trajectories = dict()
+        for i, key in enumerate(rel_keys):
+            if i >= 2:
+                trajectories[key] = states[:, i - 2]
+            elif freq is None:
+                trajectories[key] = np.zeros(num)
+            else:
+                assert num > 2
+                inc = states[:-1, rel_keys.index("d" + key) - 2] / float(freq)
+                start = np.flatnonzero(last[:num - 1] == 1) + 1                 # samples that restart at 0
+                cs = np.concatenate([[0.0], np.cumsum(inc)])
+                seg = np.zeros(num, dtype=np.int64)
+                seg[start] = 1
+                base = np.concatenate([[0.0], cs[start]])[np.cumsum(seg)]        # running sum at the segment start
+                # sample j of a segment = sum of that segment's increments before j (the increment INTO a restart is dropped)
+                trajectories[key] = cs - base
+        if num > 2:
+            trajectories["split_points"] = np.concatenate([[0], np.squeeze(np.argwhere(last == 1) + 1, axis=-1)])
+        return trajectories
+
     # ------------------------------------------------------------------ playback
     def play_trajectory(self, n_episodes=None, n_steps_per_episode=None, render=False, record=False,
                         recorder_params=None):

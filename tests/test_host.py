@@ -214,3 +214,31 @@ def test_a3_task_device_functions_on_host(a3_model):
         assert np.array_equal(ints3, trace[-1]) and np.array_equal(done3, done)
         assert_close(obs3, obs, "split obs", rtol=1e-6, atol=1e-6); assert_close(terms3, terms, "split terms", rtol=1e-6, atol=1e-6)
         assert_close(reward3, reward, "split reward", rtol=1e-6, atol=1e-6)
+
+
+def test_perfect_dataset_conversion_matches_reference_restatement():
+    """N4: LocoEnvBase.load_dataset_and_get_traj_files (vectorised) against the loop-for-loop restatement of
+    loco_env_base.py:970-1044 (oracle/trajectory.py), with and without velocity integration, and the round trip
+    create_dataset -> converter -> Trajectory.  Host logic only (no GPU)."""
+    from types import SimpleNamespace
+    from olympics_mujoco_b200.environments.loco_env_base import LocoEnvBase
+    from oracle import h1 as OH
+    from oracle import trajectory as OT
+    from olympics_mujoco_b200 import mjcf
+    model = mjcf.load_builtin("unitree_h1")
+    keys = OH.keys(model)
+    rng = np.random.default_rng(4)
+    N = 257
+    states = rng.normal(0, 1, (N, 32))
+    last = np.zeros(N)
+    last[[40, 41, 120, 256]] = 1                                   # adjacent episode ends, and the final sample
+    fake = SimpleNamespace(obs_helper=SimpleNamespace(observation_spec=[(k, k[2:] if k.startswith("q_") else k[3:], None) for k in keys]),
+                           _dataset=None)
+    for freq in (None, 100.0):
+        got = LocoEnvBase.load_dataset_and_get_traj_files(fake, dict(states=states, last=last), freq=freq)
+        ref = OT.load_dataset_and_get_traj_files(states, last, keys, freq=freq)
+        assert list(got.keys()) == list(ref.keys())
+        for k in ref:
+            np.testing.assert_allclose(got[k], ref[k], rtol=0, atol=1e-12, err_msg=k)
+    assert list(got["split_points"]) == [0, 41, 42, 121, 257]
+    assert got["q_pelvis_tx"][41] == 0.0 and got["q_pelvis_tx"][42] == 0.0 and got["q_pelvis_tx"][121] == 0.0
