@@ -84,6 +84,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 16 consecutive TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -365,6 +376,217 @@ __global__ void __launch_bounds__(192, 1) disc_reward_kernel(DiscArgs a) {
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ---------------------------------------------------------------- VAIL, two CTAs per SM
+// The single-CTA kernel above leaves the tensor pipe idle at every layer boundary (layer l+1's first A chunk needs
+// layer l's complete accumulator) and during the head.  This variant halves every per-CTA resource -- 256 TMEM
+// columns, 100 KB of shared memory, <= 168 registers -- so that TWO CTAs share an SM and one CTA's boundaries and heads
+// hide under the other's MMAs.  To fit 256 TMEM columns every MMA is N = 128:
+//   layer 1 in two 128-column blocks (DA = cols 0-127), each feeding 8 K-chunks of layer 2 (DB = cols 128-255);
+//   the [mu; logvar] layer in two 128-row blocks whose rows are INTERLEAVED on the host (block h = mu[64h..64h+63] then
+//   logvar[64h..64h+63]) into DA again, so that the head consumes 64 latent dimensions per block.
+// One ring of 3 stages; a stage = 16 K-elements of A (hi, lo) and of B (hi, lo), 32 KB.
+constexpr int V2_KC = 16, V2_NS = 3, V2_ROWS = 128;
+constexpr int V2_A_BYTES = TILE * V2_KC * 4;           // one of hi / lo: 8 KB
+constexpr int V2_B_BYTES = V2_ROWS * V2_KC * 4;        // 8 KB
+constexpr int V2_STAGE_BYTES = 2 * V2_A_BYTES + 2 * V2_B_BYTES;
+constexpr int V2_NPAR = 256 + 128 + 256 + 128 + 1;     // b1, b2, b3 (interleaved like the rows), wd, bd
+constexpr int V2_CHUNKS_PER_TILE = 2 * (2 + 8) + 2 * 8;
+
+__device__ __forceinline__ void store_a16(uint8_t* stage, int row, const float (&a)[16]) {
+  float4* hi = reinterpret_cast<float4*>(stage) + row;                       // [kc][128 rows] float4
+  float4* lo = reinterpret_cast<float4*>(stage + V2_A_BYTES) + row;
+#pragma unroll
+  for (int kc = 0; kc < 4; ++kc) {
+    float4 h, l;
+    h.x = tf32_rna(a[4 * kc]); h.y = tf32_rna(a[4 * kc + 1]); h.z = tf32_rna(a[4 * kc + 2]); h.w = tf32_rna(a[4 * kc + 3]);
+    l.x = a[4 * kc] - h.x; l.y = a[4 * kc + 1] - h.y; l.z = a[4 * kc + 2] - h.z; l.w = a[4 * kc + 3] - h.w;
+    hi[kc * TILE] = h;
+    lo[kc * TILE] = l;
+  }
+}
+
+__global__ void __launch_bounds__(192, 2) disc_vail2_kernel(DiscArgs a) {
+  constexpr int Z = 128, DA = 0, DB = 128;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ring = smem;
+  float* par = reinterpret_cast<float*>(smem + V2_NS * V2_STAGE_BYTES);
+  float* s_mean = par + V2_NPAR + 3;
+  float* s_inv = s_mean + DISC_IN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_inv + DISC_IN);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * V2_NS);
+  const float* b1 = par;
+  const float* b2 = par + 256;
+  const float* b3 = par + 384;            // per 128-row block h: [bmu[64h..], blv[64h..]]
+  const float* wd = par + 640;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s_) { return bar0 + 8u * s_; };
+  auto b_full = [&](int s_) { return bar0 + 8u * (V2_NS + s_); };
+  auto s_free = [&](int s_) { return bar0 + 8u * (2 * V2_NS + s_); };
+
+  for (int i = tid; i < V2_NPAR; i += 192) par[i] = a.params[i];
+  if (tid < DISC_IN) { s_mean[tid] = a.mean[tid]; s_inv[tid] = 1.0f / a.stdv[tid]; }
+  if (tid == 0) {
+    for (int s_ = 0; s_ < V2_NS; ++s_) { mbar_init(a_full(s_), 128); mbar_init(b_full(s_), 1); mbar_init(s_free(s_), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int ntiles = (a.n + TILE - 1) / TILE;
+  int my_tiles = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) ++my_tiles;
+  const int total_chunks = my_tiles * V2_CHUNKS_PER_TILE;
+
+  if (warp == 5) {
+    // ===================================================== weight-copy issuer: the image repeats every tile
+    if (tid == 160) {
+      for (int g = 0; g < total_chunks; ++g) {
+        const int st = g % V2_NS, use = g / V2_NS;
+        if (use > 0) mbar_wait(s_free(st), (uint32_t)(use - 1) & 1u);
+        mbar_expect_tx(b_full(st), 2 * V2_B_BYTES);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.image) + (size_t)(g % V2_CHUNKS_PER_TILE) * 2 * V2_B_BYTES;
+        const uint32_t dst = smem_u32(ring + st * V2_STAGE_BYTES + 2 * V2_A_BYTES);
+        bulk_g2s(dst, src, V2_B_BYTES, b_full(st));
+        bulk_g2s(dst + V2_B_BYTES, src + V2_B_BYTES, V2_B_BYTES, b_full(st));
+      }
+    }
+  } else if (warp == 4) {
+    // ===================================================== MMA issuer
+    if (tid == 128) {
+      const uint32_t idesc = idesc_tf32(TILE, V2_ROWS);
+      const uint32_t lbo = TILE * 16, sbo = 128;                  // A and B both have 128 rows
+      for (int g = 0; g < total_chunks; ++g) {
+        const int st = g % V2_NS, use = g / V2_NS, c = g % V2_CHUNKS_PER_TILE;
+        // position in the tile schedule -> accumulator and "first" flag
+        uint32_t d_col;
+        bool first;
+        if (c < 20) {
+          const int r = c % 10;                                   // 0,1: layer 1 of this block; 2..9: layer 2
+          d_col = r < 2 ? DA : DB;
+          first = r < 2 ? (r == 0) : (c == 2);                    // layer 2 accumulates over both blocks
+        } else {
+          d_col = DA;
+          first = ((c - 20) % 8) == 0;
+        }
+        mbar_wait(a_full(st), (uint32_t)use & 1u);
+        mbar_wait(b_full(st), (uint32_t)use & 1u);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(ring + st * V2_STAGE_BYTES), a_lo = a_hi + V2_A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * V2_A_BYTES, b_lo = b_hi + V2_B_BYTES;
+#pragma unroll
+        for (int j = 0; j < V2_KC / 8; ++j) {
+          const uint32_t o = (uint32_t)j * 2 * lbo;
+          const uint64_t dah = smem_desc(a_hi + o, lbo, sbo), dal = smem_desc(a_lo + o, lbo, sbo);
+          const uint64_t dbh = smem_desc(b_hi + o, lbo, sbo), dbl = smem_desc(b_lo + o, lbo, sbo);
+          umma_tf32(tmem + d_col, dal, dbh, idesc, (first && j == 0) ? 0u : 1u);
+          umma_tf32(tmem + d_col, dah, dbl, idesc, 1u);
+          umma_tf32(tmem + d_col, dah, dbh, idesc, 1u);
+        }
+        umma_commit(s_free(st));
+      }
+    }
+  } else {
+    // ===================================================== producers / epilogue (128 threads)
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const float bd = par[V2_NPAR - 1];
+    int g = 0;
+    auto wait_chunk = [&](int h) {                         // all MMAs up to and including chunk h are complete
+      if (h >= 0) {
+        mbar_wait(s_free(h % V2_NS), (uint32_t)(h / V2_NS) & 1u);
+        tc_fence_after();
+      }
+    };
+    auto put = [&](const float (&act_in)[16]) {
+      wait_chunk(g - V2_NS);
+      store_a16(ring + (g % V2_NS) * V2_STAGE_BYTES, tid, act_in);
+      fence_proxy_async();
+      tc_fence_before();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_full(g % V2_NS)) : "memory");
+      ++g;
+    };
+    auto load_row = [&](int tile_, float (&raw)[DISC_IN]) {
+      const int env_ = tile_ * TILE + tid;
+#pragma unroll
+      for (int k = 0; k < DISC_IN; ++k) raw[k] = (tile_ < ntiles && env_ < a.n) ? a.s[(size_t)k * a.ld + env_] : 0.f;
+    };
+    float xn[DISC_IN];
+    load_row(blockIdx.x, xn);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int env = tile * TILE + tid;
+      const bool live = env < a.n;
+      float x[DISC_IN];
+#pragma unroll
+      for (int k = 0; k < DISC_IN; ++k) x[k] = live ? (xn[k] - s_mean[k]) * s_inv[k] : 0.f;
+      load_row(tile + gridDim.x, xn);
+#pragma unroll 1
+      for (int blk = 0; blk < 2; ++blk) {
+        {
+          float h0[16], h1[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { h0[i] = x[i]; h1[i] = x[16 + i]; }
+          put(h0);
+          put(h1);
+        }
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          if (c == 0) wait_chunk(g - 1);                                  // this layer-1 block is complete
+          float h[16];
+          tmem_ld16(lane_addr + DA + c * V2_KC, h);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) h[i] = fmaxf(h[i] + b1[blk * 128 + c * V2_KC + i], 0.f);
+          put(h);
+        }
+      }
+      float dval = 0.f;
+#pragma unroll 1
+      for (int hb = 0; hb < 2; ++hb) {
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          if (c == 0 && hb == 0) wait_chunk(g - 1);                       // layer 2 complete
+          float h[16];
+          tmem_ld16(lane_addr + DB + c * V2_KC, h);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) h[i] = fmaxf(h[i] + b2[c * V2_KC + i], 0.f);
+          put(h);
+        }
+        // head over latent dimensions 64 hb .. 64 hb + 63: z = mu + exp(logvar / 2) eps, d += wd . z
+        float e0[32], e1[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          e0[i] = (a.eps && live) ? a.eps[(size_t)(64 * hb + i) * a.ld + env] : 0.f;
+          e1[i] = (a.eps && live) ? a.eps[(size_t)(64 * hb + 32 + i) * a.ld + env] : 0.f;
+        }
+        wait_chunk(g - 1);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float mu[32], lv[32];
+          tmem_ld32(lane_addr + DA + q * 32, mu);
+          tmem_ld32(lane_addr + DA + 64 + q * 32, lv);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int j = 64 * hb + 32 * q + i;
+            const float e = q == 0 ? e0[i] : e1[i];
+            const float zz = fmaf(expf(0.5f * (lv[i] + b3[128 * hb + 64 + 32 * q + i])), e, mu[i] + b3[128 * hb + 32 * q + i]);
+            dval = fmaf(wd[j], zz, dval);
+          }
+        }
+      }
+      dval += bd;
+      if (live) {
+        const float one_minus_p = 1.f / (1.f + expf(dval));
+        a.reward[env] = -logf(one_minus_p + 1e-8f);
+        if (a.d_out) a.d_out[env] = dval;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 }  // namespace om
 
 using namespace om;
@@ -373,6 +595,8 @@ struct OmDisc {
   DiscShape sh;
   float* image = nullptr;
   float* params = nullptr;
+  float* image2 = nullptr;      // VAIL: chunk image / parameters of disc_vail2_kernel
+  float* params2 = nullptr;
 };
 
 static void split_tf32(float x, float* hi, float* lo) {
@@ -429,15 +653,57 @@ extern "C" int om_disc_create(const OmDiscDesc* d, OmDisc** out) {
   }
   par.insert(par.end(), d->wd, d->wd + (vail ? z : n2));
   par.push_back(d->bd[0]);
+  // ---- 2-CTA-per-SM VAIL variant: 16-column chunks, every B block 128 rows, [mu; logvar] rows interleaved per 64
+  std::vector<float> img2, par2;
+  if (vail) {
+    std::vector<float> w3i((size_t)2 * z * n2), b3i(2 * z);
+    for (int hb = 0; hb < 2; ++hb)
+      for (int r = 0; r < 64; ++r) {
+        std::memcpy(&w3i[(size_t)(128 * hb + r) * n2], d->wmu + (size_t)(64 * hb + r) * n2, sizeof(float) * n2);
+        std::memcpy(&w3i[(size_t)(128 * hb + 64 + r) * n2], d->wlv + (size_t)(64 * hb + r) * n2, sizeof(float) * n2);
+        b3i[128 * hb + r] = d->bmu[64 * hb + r];
+        b3i[128 * hb + 64 + r] = d->blv[64 * hb + r];
+      }
+    auto chunk16 = [&](const float* w, int ldw, int r0, int k0) {          // 128 rows x 16 columns: hi image, lo image
+      const size_t base = img2.size();
+      img2.resize(base + (size_t)V2_ROWS * V2_KC * 2);
+      float* hi = img2.data() + base;
+      float* lo = hi + (size_t)V2_ROWS * V2_KC;
+      for (int kc = 0; kc < V2_KC / 4; ++kc)
+        for (int r = 0; r < V2_ROWS; ++r)
+          for (int e = 0; e < 4; ++e)
+            split_tf32(w[(size_t)(r0 + r) * ldw + k0 + kc * 4 + e], hi + ((size_t)kc * V2_ROWS + r) * 4 + e,
+                       lo + ((size_t)kc * V2_ROWS + r) * 4 + e);
+    };
+    for (int blk = 0; blk < 2; ++blk) {
+      for (int c = 0; c < 2; ++c) chunk16(d->w1, DISC_IN, 128 * blk, 16 * c);
+      for (int c = 0; c < 8; ++c) chunk16(d->w2, n1, 0, 128 * blk + 16 * c);
+    }
+    for (int hb = 0; hb < 2; ++hb)
+      for (int c = 0; c < 8; ++c) chunk16(w3i.data(), n2, 128 * hb, 16 * c);
+    par2.insert(par2.end(), d->b1, d->b1 + n1);
+    par2.insert(par2.end(), d->b2, d->b2 + n2);
+    par2.insert(par2.end(), b3i.begin(), b3i.end());
+    par2.insert(par2.end(), d->wd, d->wd + z);
+    par2.push_back(d->bd[0]);
+  }
   OmDisc* h = new OmDisc();
   h->sh = DiscShape{d->kind, n1, n2, z};
   cudaError_t e = cudaMalloc(&h->image, img.size() * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&h->params, par.size() * sizeof(float));
   if (e == cudaSuccess) e = cudaMemcpy(h->image, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->params, par.data(), par.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && vail) {
+    e = cudaMalloc(&h->image2, img2.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&h->params2, par2.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(h->image2, img2.data(), img2.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->params2, par2.data(), par2.size() * sizeof(float), cudaMemcpyHostToDevice);
+  }
   if (e != cudaSuccess) {
     if (h->image) cudaFree(h->image);
     if (h->params) cudaFree(h->params);
+    if (h->image2) cudaFree(h->image2);
+    if (h->params2) cudaFree(h->params2);
     delete h;
     return fail("om_disc_create: device upload failed: %s (no CPU path)", cudaGetErrorString(e));
   }
@@ -449,6 +715,8 @@ extern "C" void om_disc_destroy(OmDisc* h) {
   if (!h) return;
   cudaFree(h->image);
   cudaFree(h->params);
+  if (h->image2) cudaFree(h->image2);
+  if (h->params2) cudaFree(h->params2);
   delete h;
 }
 
@@ -466,6 +734,19 @@ extern "C" int om_disc_reward(const OmDisc* h, const float* s, const float* mean
   const size_t smem = 2 * STAGE_A_BYTES + NSB * STAGE_B2_BYTES + (DISC_MAX_PAR + 4) * sizeof(float) + 12 * 8 + 16;
   DiscArgs a{h->sh, h->image, h->params, s, mean, stdv, eps, reward, d_out, n, ld};
   cudaStream_t st = (cudaStream_t)stream;
+  int two = h->sh.kind == 0;                                       // VAIL: two CTAs per SM
+  if (const char* f = getenv("OM_DISC_VAIL2")) two = two && atoi(f) != 0;        // tuning / test hook
+  if (two) {
+    const size_t smem2 = V2_NS * V2_STAGE_BYTES + (V2_NPAR + 3 + 2 * DISC_IN) * sizeof(float) + 3 * V2_NS * 8 + 16;
+    const int grid2 = ntiles < 2 * sms ? ntiles : 2 * sms;
+    DiscArgs a2 = a;
+    a2.image = h->image2;
+    a2.params = h->params2;
+    OM_CUDA_OK(cudaFuncSetAttribute(disc_vail2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    disc_vail2_kernel<<<grid2, 192, smem2, st>>>(a2);
+    OM_LAUNCHED();
+    return 0;
+  }
   if (h->sh.kind == 0) {
     OM_CUDA_OK(cudaFuncSetAttribute(disc_reward_kernel<256, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     disc_reward_kernel<256, 128, true><<<grid, 192, smem, st>>>(a);
