@@ -32,6 +32,13 @@ HORIZON = 500
 GAMMA, LAM = 0.99, 0.97
 
 
+def workload_config(n, T):
+    """`config` of BOTH arms (the reference arm adds `sample`)."""
+    return {"workload": f"UnitreeH1 walk playback rollout {n} envs x {T} steps per GPU + GAE (configs[1])",
+            "envs_per_gpu": n, "horizon": T, "l2": "rollout outputs (2.5 GB/step) exceed the 126 MB L2",
+            "gamma": GAMMA, "lam": LAM}
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -93,13 +100,12 @@ def run_reference(args):
         return
     from oracle import cpu_baseline
     model, table = build_table()
-    res = cpu_baseline.run(model, table, steps=args.steps, warmup=args.warmup, horizon=HORIZON)
+    res = cpu_baseline.run(model, table, steps=args.steps, warmup=args.warmup, horizon=args.horizon)
     line = {"impl": "reference", "metric": "env-steps/sec (FK+obs+reward+GAE)", "value": res["value"],
             "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "UnitreeH1 walk playback rollout 4096 envs x 500 steps + GAE (configs[1])",
-                       "sample": res["sample"]},
+            "config": dict(workload_config(args.envs, args.horizon), sample=res["sample"]),
             "cpu_baseline": {"value": res["value"], "unit": "env-steps/s", "cores": res["cores"], "kind": res["kind"],
                              "sample": res["sample"]},
             "e2e": {"value": res["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -245,13 +251,11 @@ def run_ours(args):
         line = {"metric": "env-steps/sec (FK+obs+reward+GAE)", "value": value, "unit": "env-steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"UnitreeH1 walk playback rollout {n} envs x {T} steps per GPU + GAE (configs[1])",
-                           "envs_per_gpu": n, "horizon": T, "l2": "rollout outputs (2.5 GB/step) exceed the 126 MB L2",
-                           "gamma": GAMMA, "lam": LAM},
+                "config": workload_config(n, T),
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": world * n * T / (float(e2e_ms) * 1e-3), "unit": "env-steps/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "roofline": {"bound": "hbm", "kernel": "play_h1_kernel (one episode, incl. end-of-episode reset)", "achieved": achieved,
+                "roofline": {"bound": "hbm", "kernel": "play_snapshot_kernel + play_h1_tp_kernel (one 500-step episode incl. its end-of-episode reset)", "achieved": achieved,
                              "peak": peaks["hbm_gbs"], "peak_source": which, "unit": "GB/s",
                              "frac": achieved / peaks["hbm_gbs"],
                              "traffic": NCU_TRAFFIC_BYTES_4096x500 if (n, T) == (4096, 500) else None,
