@@ -290,6 +290,15 @@ int om_action_affine(const OmActionSpec* spec, const float* action, int n, int l
 int om_pd_torque(const OmPdSpec* spec, const float* target, const float* vel_target, const float* qpos, const float* qvel,
                  int add_offset, int n, int ld, float* ctrl, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * N3 (next row, consumer side): the mirror-symmetry transforms of the PPO mirror loss (rl/algos/ppo.py:232-282 through
+ * rl/envs/wrappers.py:51-72 SymmetricEnv.mirror_observation / mirror_action / mirror_clock_observation).
+ * `mirrored` lists (StickFigureA3.py:118-129) encode a signed permutation: y[|m_i|] = sign(m_i) * x[i]
+ * (wrappers.py:75-82; index 0 is written 0.1 / -0.1 there).  negate[j] != 0 marks clock rows, whose mirrored value is
+ * sin(arcsin(y_j) + pi) = -y_j (wrappers.py:67-69).  x, y are [numel][ld]; y must not alias x. */
+typedef struct OmMirrorSpec { int numel; int32_t index[64]; float sign[64]; uint8_t negate[64]; } OmMirrorSpec;
+int om_mirror(const OmMirrorSpec* spec, const float* x, int n, int ld, float* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,10 @@ class OmPdSpec(C.Structure):
                 ("kd", C.c_float * 32), ("gear", C.c_float * 32), ("offset", C.c_float * 32)]
 
 
+class OmMirrorSpec(C.Structure):
+    _fields_ = [("numel", C.c_int), ("index", C.c_int32 * 64), ("sign", C.c_float * 64), ("negate", C.c_uint8 * 64)]
+
+
 _P, _I, _F, _D = C.c_void_p, C.c_int, C.c_float, C.c_double
 _U64, _U32 = C.c_uint64, C.c_uint32
 
@@ -105,6 +109,7 @@ PROTOTYPES = {
     "om_disc_reward": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "om_action_affine": (_I, [C.POINTER(OmActionSpec), _P, _I, _I, _P, _P]),
     "om_pd_torque": (_I, [C.POINTER(OmPdSpec), _P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "om_mirror": (_I, [C.POINTER(OmMirrorSpec), _P, _I, _I, _P, _P]),
     "om_ppo_returns": (_I, [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P]),
     "om_gae": (_I, [_P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P, _P]),
     "om_moments": (_I, [_P, _I, _I, _I, _I, _P, _P]),

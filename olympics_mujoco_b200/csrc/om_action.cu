@@ -55,3 +55,35 @@ extern "C" int om_pd_torque(const OmPdSpec* spec, const float* target, const flo
   OM_LAUNCHED();
   return 0;
 }
+
+// ---------------------------------------------------------------- N3: mirror-symmetry transforms
+//   SymmetricEnv.mirror_observation / mirror_action / mirror_clock_observation   rl/envs/wrappers.py:51-72
+//   _get_symmetry_matrix :75-82: mat[i, |m_i|] = sign(m_i)  =>  (x @ mat)[|m_i|] = sign(m_i) x[i]: a signed permutation,
+//   applied here as a scatter over SoA rows; clock rows c become sin(arcsin(y_c) + pi) = -y_c (:67-69).
+namespace om {
+__global__ void __launch_bounds__(256) mirror_kernel(OmMirrorSpec sp, const float* __restrict__ x, int n, int ld,
+                                                     float* __restrict__ y) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  for (int i = 0; i < sp.numel; ++i) {
+    const float v = x[(size_t)i * ld + e] * sp.sign[i];
+    y[(size_t)sp.index[i] * ld + e] = sp.negate[sp.index[i]] ? -v : v;
+  }
+}
+}  // namespace om
+
+extern "C" int om_mirror(const OmMirrorSpec* spec, const float* x, int n, int ld, float* y, void* stream) {
+  OM_REQUIRE(spec && spec->numel >= 0 && spec->numel <= 64, "om_mirror: need 0 <= numel <= 64");
+  OM_REQUIRE(n >= 0 && ld >= n, "om_mirror: need 0 <= n <= ld");
+  if (n == 0 || spec->numel == 0) return 0;
+  OM_REQUIRE(x && y && x != y, "om_mirror: null or aliased argument (the scatter is not in-place safe)");
+  uint64_t seen = 0;
+  for (int i = 0; i < spec->numel; ++i) {
+    OM_REQUIRE(spec->index[i] >= 0 && spec->index[i] < spec->numel, "om_mirror: index[%d] out of range", i);
+    seen |= 1ull << spec->index[i];
+  }
+  OM_REQUIRE(seen == (spec->numel == 64 ? ~0ull : (1ull << spec->numel) - 1), "om_mirror: indices are not a permutation");
+  om::mirror_kernel<<<om::ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(*spec, x, n, ld, y);
+  OM_LAUNCHED();
+  return 0;
+}

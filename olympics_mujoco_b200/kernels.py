@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import OmA3Out, OmA3State, OmA3TaskDesc, OmActionSpec, OmDiscDesc, OmH1Spec, OmPdSpec, OmModelDesc, OmPlayOut, OmPlayState, check
+from ._lib import OmA3Out, OmA3State, OmA3TaskDesc, OmActionSpec, OmDiscDesc, OmH1Spec, OmMirrorSpec, OmPdSpec, OmModelDesc, OmPlayOut, OmPlayState, check
 from .mjcf import KinematicModel
 
 
@@ -333,6 +333,26 @@ def pd_torque(spec, target, qpos, qvel, vel_target=None, add_offset=True, out=No
     check(_lib.load().om_pd_torque(C.byref(spec), _p(target, torch.float32), _p(vel_target, torch.float32),
                                    _p(qpos, torch.float32), _p(qvel, torch.float32), int(bool(add_offset)), n, max(n, 1),
                                    _p(out, torch.float32), _stream()))
+    return out
+
+
+def make_mirror_spec(mirrored, clock_inds=()):
+    """``mirrored`` as the reference writes it (signed indices, 0 encoded as +-0.1; StickFigureA3.py:118-129)."""
+    sp = OmMirrorSpec()
+    sp.numel = len(mirrored)
+    for i, m in enumerate(mirrored):
+        sp.index[i] = int(abs(int(m)))
+        sp.sign[i] = float(np.sign(m))
+    for c in clock_inds:
+        sp.negate[int(c)] = 1
+    return sp
+
+
+def mirror(spec, x, out=None):
+    """SymmetricEnv.mirror_observation / mirror_action (/ mirror_clock_observation with clock_inds): x [numel, n]."""
+    n = x.shape[-1]
+    out = torch.empty_like(x) if out is None else out
+    check(_lib.load().om_mirror(C.byref(spec), _p(x, torch.float32), n, max(n, 1), _p(out, torch.float32), _stream()))
     return out
 
 

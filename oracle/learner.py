@@ -166,3 +166,22 @@ def discrim_reward(d):
     """gail_TRPO.py:326-327."""
     plcy_prob = 1.0 / (1.0 + np.exp(-np.asarray(d, np.float64)))
     return (-np.log(1.0 - plcy_prob + 1e-8)).astype(np.float32)
+
+
+# ------------------------------------------------------------------ mirror symmetry (N3)
+def symmetry_matrix(mirrored):
+    """rl/envs/wrappers.py:75-82."""
+    numel = len(mirrored)
+    mat = np.zeros((numel, numel))
+    for i, j in zip(np.arange(numel), np.abs(np.array(mirrored).astype(int))):
+        mat[i, j] = np.sign(mirrored[i])
+    return mat
+
+
+def mirror(x, mirrored, clock_inds=()):
+    """SymmetricEnv.mirror_observation / mirror_action (wrappers.py:51-55) and, with ``clock_inds``,
+    mirror_clock_observation (:60-72)."""
+    y = np.asarray(x, np.float64) @ symmetry_matrix(mirrored)
+    for c in clock_inds:
+        y[:, c] = np.sin(np.arcsin(y[:, c]) + np.pi)
+    return y

@@ -138,3 +138,15 @@ def test_discriminator_oracle_vs_reference_networks():
     dg = L.gail_forward(pg, z["s"], z["gail_mean"], z["gail_std"])
     assert_close(dg, z["gail_d"][:, 0], "gail d", rtol=1e-4, atol=1e-5)
     assert_close(L.discrim_reward(dg), z["gail_reward"], "gail reward", rtol=1e-4, atol=1e-5)
+
+
+def test_mirror_oracle_vs_reference_symmetric_env():
+    """oracle.learner.mirror against the outputs of the reference's own SymmetricEnv (tests/golden/mirror_ref.npz,
+    generated by tools/gen_golden.py:gen_mirror from rl/envs/wrappers.py)."""
+    from oracle import learner as L
+    g = np.load(GOLDEN / "mirror_ref.npz")
+    np.testing.assert_allclose(L.mirror(g["obs"], g["mirrored_obs"]), g["mirror_obs"], rtol=0, atol=0)
+    np.testing.assert_allclose(L.mirror(g["act"], g["mirrored_acts"]), g["mirror_act"], rtol=0, atol=0)
+    np.testing.assert_allclose(L.mirror(g["obs"], g["mirrored_obs"], g["clock_inds"]), g["mirror_clock_obs"], rtol=0, atol=2e-7)
+    m = L.symmetry_matrix(g["mirrored_obs"])
+    assert np.array_equal(m @ m, np.eye(41))                       # the A3 observation mirror is an involution

@@ -428,6 +428,28 @@ def gen_a3_task():
     print("a3_task_ref: steps", out["step_terms"].shape, "max t1", ints[..., 1].max(), "done frac",
           out["step_done"].mean(), "modes", out["reset_ints"][:, 4])
 
+# ---------------------------------------------------------------- 8. mirror symmetry (rl/envs/wrappers.py)
+def gen_mirror():
+    import torch
+    wr = load("ref_wrappers", "rl/envs/wrappers.py")
+    base_mir_obs = [0.1, -1, 2, -3, -4, 5, -6, 13, -14, -15, 16, -17, 18, 7, -8, -9, 10, -11, 12,
+                    25, -26, -27, 28, -29, 30, 19, -20, -21, 22, -23, 24]                 # StickFigureA3.py:118-125
+    mirrored_obs = base_mir_obs + [len(base_mir_obs) + i for i in range(10)]
+    mirrored_acts = [6, -7, -8, 9, -10, 11, 0.1, -1, -2, 3, -4, 5]
+    clock_inds = [31, 32]
+    env = wr.SymmetricEnv(lambda: types.SimpleNamespace(base_obs_len=41), mirrored_obs=mirrored_obs,
+                          mirrored_act=mirrored_acts, clock_inds=clock_inds)
+    rng = np.random.default_rng(9)
+    obs = rng.normal(0, 1, (37, 41)).astype(np.float32)
+    ph = rng.integers(0, 88, 37)
+    obs[:, 31], obs[:, 32] = np.sin(2 * np.pi * ph / 88), np.cos(2 * np.pi * ph / 88)
+    act = rng.normal(0, 1, (37, 12)).astype(np.float32)
+    to, ta = torch.from_numpy(obs), torch.from_numpy(act)
+    np.savez(OUT / "mirror_ref.npz", mirrored_obs=np.array(mirrored_obs), mirrored_acts=np.array(mirrored_acts),
+             clock_inds=np.array(clock_inds), obs=obs, act=act, mirror_obs=env.mirror_observation(to).numpy(),
+             mirror_act=env.mirror_action(ta).numpy(), mirror_clock_obs=env.mirror_clock_observation(to).numpy())
+    print("mirror_ref: obs", obs.shape)
+
 
 if __name__ == "__main__":
     gen_trajectory()
@@ -437,3 +459,4 @@ if __name__ == "__main__":
     gen_saved_rollouts()
     gen_running_mean_std()
     gen_a3_task()
+    gen_mirror()
