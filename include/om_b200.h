@@ -169,6 +169,12 @@ int om_h1_play_from_velocity(const OmModel* m, const OmH1Spec* spec, const OmTra
                              uint32_t env_id0, double dt, int n_steps, int end_episode_reset,
                              const OmPlayState* state, const OmPlayOut* out, int n, int ld, void* stream);
 
+/* Fused LocoEnvBase.play_trajectory (loco_env_base.py:338-442): like the call above, but every step FORCES the model to the
+ * current trajectory sample (:408) instead of integrating its velocities; state->curr_qpos is not used (may be NULL). */
+int om_h1_play_trajectory(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, uint64_t seed, uint32_t env_id0,
+                          int n_steps, int end_episode_reset, const OmPlayState* state, const OmPlayOut* out, int n, int ld,
+                          void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K2 (A3 flavour): the tail of StickFigureA3.step (real_humanoid_robots/StickFigureA3.py:187-202) after
  * robot.step (= mj_step, which stays the reference's): WalkingTask.step (tasks/walking_task.py:246-293),

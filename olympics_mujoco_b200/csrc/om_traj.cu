@@ -81,6 +81,7 @@ struct PlayArgs {
   double dt;
   float target;
   int use_absorbing, n_steps, end_reset, n, ld;
+  int forced;         // 1 = play_trajectory (the model is forced to each sample), 0 = play_trajectory_from_velocity
   OmPlayState s;      // live carried state (written by the thread that runs the last step)
   OmPlayState snap;   // episode-start snapshot read by every chunk of the time-parallel kernel
   OmPlayOut o;
@@ -137,16 +138,22 @@ __global__ void __launch_bounds__(BLOCK) play_h1_seq_kernel(PlayArgs a) {
   float dq[17];
 #pragma unroll
   for (int k = 0; k < 17; ++k) {
-    cq[k] = a.s.curr_qpos[k * ld + e];
+    cq[k] = a.s.curr_qpos ? a.s.curr_qpos[k * ld + e] : 0.0;
     dq[k] = a.s.pending[(17 + k) * ld + e];
   }
   float pxv = a.s.prev_x_vel[e];
   float samp[36];
   bool have_samp = false;
-  for (int s = 0; s < a.n_steps; ++s) {
+  if (a.forced) {
 #pragma unroll
-    for (int k = 0; k < 17; ++k) cq[k] = fma(a.dt, (double)dq[k], cq[k]);   // :515-519
-    play_fk(cq, dq, a.o, (size_t)s, ld, e);                                          // :521-525
+    for (int k = 0; k < 17; ++k) cq[k] = a.s.pending[k * ld + e];                    // play_trajectory: q = sample (:408)
+  }
+  for (int s = 0; s < a.n_steps; ++s) {
+    if (!a.forced) {
+#pragma unroll
+      for (int k = 0; k < 17; ++k) cq[k] = fma(a.dt, (double)dq[k], cq[k]);          // :515-519
+    }
+    play_fk(cq, dq, a.o, (size_t)s, ld, e);                                          // :521-525 / :408-410
     ++st;                                                                            // :532
     const bool wrap = st >= a.t.T;
     if (wrap) {                                                                      // :534-537
@@ -157,7 +164,12 @@ __global__ void __launch_bounds__(BLOCK) play_h1_seq_kernel(PlayArgs a) {
     }
     traj_load_row(a.t, tr, st, samp);
     have_samp = true;
-    if (wrap) {
+    if (a.forced) {                   // the next step is forced to this sample (x, y re-centred in double, then fp32)
+      cq[0] = (float)(a.t.xy[((size_t)tr * a.t.T + st) * 2] - ox);
+      cq[1] = (float)(a.t.xy[((size_t)tr * a.t.T + st) * 2 + 1] - oy);
+#pragma unroll
+      for (int k = 2; k < 17; ++k) cq[k] = samp[k];
+    } else if (wrap) {
       cq[0] = 0.0; cq[1] = 0.0;       // x - x_off and y - y_off are exactly zero at the reset sample
 #pragma unroll
       for (int k = 2; k < 17; ++k) cq[k] = samp[k];
@@ -191,7 +203,7 @@ __global__ void __launch_bounds__(BLOCK) play_h1_seq_kernel(PlayArgs a) {
   a.s.xy_off[e] = ox;
   a.s.xy_off[ld + e] = oy;
 #pragma unroll
-  for (int k = 0; k < 17; ++k) a.s.curr_qpos[k * ld + e] = cq[k];
+  for (int k = 0; k < 17; ++k) if (a.s.curr_qpos) a.s.curr_qpos[k * ld + e] = cq[k];
   a.s.prev_x_vel[e] = pxv;
 }
 
@@ -201,12 +213,11 @@ __global__ void __launch_bounds__(256) play_snapshot_kernel(OmPlayState live, Om
   if (e >= n) return;
   // all loads first (the pointers may alias as far as the compiler knows: a load-store-load chain costs 34 round trips)
   double cq[17], xo[2];
-  float pd[17];
+  float pd[34];
 #pragma unroll
-  for (int k = 0; k < 17; ++k) {
-    cq[k] = live.curr_qpos[(size_t)k * ld + e];
-    pd[k] = live.pending[(size_t)(17 + k) * ld + e];
-  }
+  for (int k = 0; k < 17; ++k) cq[k] = live.curr_qpos ? live.curr_qpos[(size_t)k * ld + e] : 0.0;
+#pragma unroll
+  for (int k = 0; k < 34; ++k) pd[k] = live.pending[(size_t)k * ld + e];
   xo[0] = live.xy_off[e];
   xo[1] = live.xy_off[(size_t)ld + e];
   const int32_t tr = live.traj_no[e], st = live.step_no[e];
@@ -219,10 +230,9 @@ __global__ void __launch_bounds__(256) play_snapshot_kernel(OmPlayState live, Om
   snap.xy_off[(size_t)ld + e] = xo[1];
   snap.prev_x_vel[e] = pxv;
 #pragma unroll
-  for (int k = 0; k < 17; ++k) {
-    snap.curr_qpos[(size_t)k * ld + e] = cq[k];
-    snap.pending[(size_t)(17 + k) * ld + e] = pd[k];
-  }
+  for (int k = 0; k < 17; ++k) snap.curr_qpos[(size_t)k * ld + e] = cq[k];
+#pragma unroll
+  for (int k = 0; k < 34; ++k) snap.pending[(size_t)k * ld + e] = pd[k];
 }
 
 // The per-env recurrences of the playback loop are (a) the integer trajectory index, which only changes
@@ -256,7 +266,17 @@ __global__ void __launch_bounds__(BLOCK) play_h1_tp_kernel(PlayArgs a, int chunk
   float pxv;
   float samp[36];
   const double* c_hi = a.t.cdq + ((size_t)tr * (T + 1) + st + m) * 17;
-  if (first) {
+  if (a.forced) {
+    // play_trajectory: the sim state of step j0 IS the pending sample -- the carried one when nothing happened yet,
+    // else row (tr, st + m) re-centred with the offsets of the reset that opened this segment
+    if (first) { ox = a.snap.xy_off[e]; oy = a.snap.xy_off[ld + e]; }
+    else { ox = a.t.xy[((size_t)tr * T + st) * 2]; oy = a.t.xy[((size_t)tr * T + st) * 2 + 1]; }
+    if (first && m == 0) {
+#pragma unroll
+      for (int k = 0; k < 17; ++k) { cq[k] = a.snap.pending[k * ld + e]; dq[k] = a.snap.pending[(17 + k) * ld + e]; }
+      pxv = a.snap.prev_x_vel[e];
+    }
+  } else if (first) {
     ox = a.snap.xy_off[e]; oy = a.snap.xy_off[ld + e];
     const double* c_lo = a.t.cdq + ((size_t)tr * (T + 1) + st + 1) * 17;
 #pragma unroll
@@ -283,11 +303,19 @@ __global__ void __launch_bounds__(BLOCK) play_h1_tp_kernel(PlayArgs a, int chunk
 #pragma unroll
     for (int k = 0; k < 17; ++k) dq[k] = samp[17 + k];
     pxv = samp[17];
+    if (a.forced) {
+      cq[0] = (float)(a.t.xy[((size_t)tr * T + st) * 2] - ox);
+      cq[1] = (float)(a.t.xy[((size_t)tr * T + st) * 2 + 1] - oy);
+#pragma unroll
+      for (int k = 2; k < 17; ++k) cq[k] = samp[k];
+    }
   }
   // ---- walk the chunk (identical to the sequential kernel's loop body)
   for (int s = j0; s < j1; ++s) {
+    if (!a.forced) {
 #pragma unroll
-    for (int k = 0; k < 17; ++k) cq[k] = fma(a.dt, (double)dq[k], cq[k]);
+      for (int k = 0; k < 17; ++k) cq[k] = fma(a.dt, (double)dq[k], cq[k]);
+    }
     play_fk(cq, dq, a.o, (size_t)s, ld, e);
     ++st;
     const bool wrap = st >= T;
@@ -298,7 +326,12 @@ __global__ void __launch_bounds__(BLOCK) play_h1_tp_kernel(PlayArgs a, int chunk
       oy = a.t.xy[((size_t)tr * T + st) * 2 + 1];
     }
     traj_load_row(a.t, tr, st, samp);
-    if (wrap) {
+    if (a.forced) {
+      cq[0] = (float)(a.t.xy[((size_t)tr * T + st) * 2] - ox);
+      cq[1] = (float)(a.t.xy[((size_t)tr * T + st) * 2 + 1] - oy);
+#pragma unroll
+      for (int k = 2; k < 17; ++k) cq[k] = samp[k];
+    } else if (wrap) {
       cq[0] = 0.0; cq[1] = 0.0;
 #pragma unroll
       for (int k = 2; k < 17; ++k) cq[k] = samp[k];
@@ -331,7 +364,7 @@ __global__ void __launch_bounds__(BLOCK) play_h1_tp_kernel(PlayArgs a, int chunk
   a.s.xy_off[e] = ox;
   a.s.xy_off[ld + e] = oy;
 #pragma unroll
-  for (int k = 0; k < 17; ++k) a.s.curr_qpos[k * ld + e] = cq[k];
+  for (int k = 0; k < 17; ++k) if (a.s.curr_qpos) a.s.curr_qpos[k * ld + e] = cq[k];
   a.s.prev_x_vel[e] = pxv;
 }
 
@@ -440,9 +473,9 @@ extern "C" int om_traj_next(const OmTraj* t, uint64_t seed, uint32_t env_id0, in
   return 0;
 }
 
-extern "C" int om_h1_play_from_velocity(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, uint64_t seed,
-                                        uint32_t env_id0, double dt, int n_steps, int end_episode_reset,
-                                        const OmPlayState* state, const OmPlayOut* out, int n, int ld, void* stream) {
+static int play_impl(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, uint64_t seed, uint32_t env_id0, double dt,
+                     int n_steps, int end_episode_reset, const OmPlayState* state, const OmPlayOut* out, int n, int ld,
+                     void* stream, int forced) {
   OM_REQUIRE(m && spec && t && state && out, "om_h1_play_from_velocity: null argument");
   OM_REQUIRE(n >= 0 && ld >= n && n_steps >= 0, "om_h1_play_from_velocity: bad sizes");
   OM_REQUIRE(m->specialised == SPEC_H1, "om_h1_play_from_velocity: model is not the UnitreeH1 (arms disabled) model");
@@ -450,12 +483,12 @@ extern "C" int om_h1_play_from_velocity(const OmModel* m, const OmH1Spec* spec, 
   for (int k = 0; k < 17; ++k)
     OM_REQUIRE(spec->obs_perm[k] == OM_H1_PERM_HOST[k], "om_h1_play_from_velocity: observation spec differs from UnitreeH1's");
   if (n == 0) return 0;
-  OM_REQUIRE(state->traj_no && state->step_no && state->reset_count && state->xy_off && state->curr_qpos &&
+  OM_REQUIRE(state->traj_no && state->step_no && state->reset_count && state->xy_off && (forced || state->curr_qpos) &&
                  state->pending && state->prev_x_vel, "om_h1_play_from_velocity: incomplete state");
   PlayArgs a;
   a.t = t->d; a.seed = seed; a.env_id0 = env_id0; a.dt = dt; a.target = spec->target_velocity;
   a.use_absorbing = spec->use_absorbing_states; a.n_steps = n_steps; a.end_reset = end_episode_reset;
-  a.n = n; a.ld = ld; a.s = *state; a.snap = *state; a.o = *out;
+  a.n = n; a.ld = ld; a.s = *state; a.snap = *state; a.o = *out; a.forced = forced;
   constexpr int BLOCK = 128;
   // time-parallel when the env count alone cannot fill the machine (148 SMs x 2048 threads)
   const long long target_threads = 148LL * 2048;
@@ -463,7 +496,7 @@ extern "C" int om_h1_play_from_velocity(const OmModel* m, const OmH1Spec* spec, 
   int chunk = ceil_div(n_steps, chunks_wanted);
   if (const char* f = getenv("OM_PLAY_CHUNK")) chunk = atoi(f);     // tuning / test hook
   if (chunk < 1) chunk = 1;
-  if (chunk >= n_steps || state->curr_qpos == nullptr) {
+  if (chunk >= n_steps) {
     play_h1_seq_kernel<BLOCK><<<ceil_div(n, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(a);
   } else {
     // the carried state is read by every chunk and overwritten by the last one: snapshot the episode-start
@@ -495,4 +528,16 @@ extern "C" int om_h1_play_from_velocity(const OmModel* m, const OmH1Spec* spec, 
   }
   OM_LAUNCHED();
   return 0;
+}
+
+extern "C" int om_h1_play_from_velocity(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, uint64_t seed,
+                                        uint32_t env_id0, double dt, int n_steps, int end_episode_reset,
+                                        const OmPlayState* state, const OmPlayOut* out, int n, int ld, void* stream) {
+  return play_impl(m, spec, t, seed, env_id0, dt, n_steps, end_episode_reset, state, out, n, ld, stream, 0);
+}
+
+extern "C" int om_h1_play_trajectory(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, uint64_t seed, uint32_t env_id0,
+                                     int n_steps, int end_episode_reset, const OmPlayState* state, const OmPlayOut* out, int n,
+                                     int ld, void* stream) {
+  return play_impl(m, spec, t, seed, env_id0, 0.0, n_steps, end_episode_reset, state, out, n, ld, stream, 1);
 }

@@ -198,6 +198,28 @@ class UnitreeH1(BaseHumanoidRobot):
             return super().set_sim_state(sample)
         Kn.set_sim_state(self._dm, self._spec, sample.t().contiguous(), self._data.qpos, self._data.qvel)
 
+    def play_trajectory(self, n_episodes=None, n_steps_per_episode=None, render=False, record=False, recorder_params=None,
+                        out=None, want=None):
+        """loco_env_base.py:338-442 as one fused kernel per episode (``om_h1_play_trajectory``): the model is forced to
+        every trajectory sample, FK runs on it, the next sample gives the observation and the has_fallen flag.
+        Returns the last episode's time-major rollout buffers (the reference only renders)."""
+        assert self.trajectories is not None
+        if render or record:
+            raise NotImplementedError("rendering is outside the hot path; call with render=False")
+        assert n_episodes is not None and n_steps_per_episode is not None, "unbounded playback needs a viewer"
+        if not self._dm.specialised or len(self.obs_helper.observation_spec) != 34:
+            return super().play_trajectory(n_episodes, n_steps_per_episode, render, record, recorder_params)
+        dev = self.trajectories.device_state
+        self.reset()                                                             # :377
+        sample = self.trajectories.get_current_sample().t().contiguous()         # :379
+        state = dict(pending=sample.clone(), prev_x_vel=self._prev_x_vel)
+        res = None
+        for _ in range(n_episodes):
+            kw = {} if want is None else dict(want=want)
+            res = Kn.h1_play_from_velocity(self._dm, self._spec, dev, state, n_steps_per_episode, end_episode_reset=True,
+                                           out=out, forced=True, **kw)
+        return res
+
     def make_rollout_buffers(self, n_steps, want=("xpos", "xquat", "site_xpos", "cvel", "obs", "reward", "fallen",
                                                   "traj_no_t", "step_no_t")):
         m, n, dev = self._model, self.n_envs, self._device

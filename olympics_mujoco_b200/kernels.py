@@ -205,9 +205,10 @@ class DeviceTrajectory:
 
 def h1_play_from_velocity(dm, spec, traj: DeviceTrajectory, state, n_steps, dt=0.01, end_episode_reset=True,
                           want=("xpos", "xquat", "site_xpos", "cvel", "obs", "reward", "fallen", "traj_no_t", "step_no_t"),
-                          out=None):
+                          out=None, forced=False):
     """Fused playback of one episode (loco_env_base.py:511-557).  ``state``: dict with curr_qpos [17,n] f64,
-    pending [34,n] f32, prev_x_vel [n] f32 (the trajectory indices live in ``traj``)."""
+    pending [34,n] f32, prev_x_vel [n] f32 (the trajectory indices live in ``traj``).  ``forced``: play_trajectory
+    semantics (loco_env_base.py:404-432), the model is set to each sample instead of integrating velocities."""
     km, n = dm.km, traj.n
     dev = traj.traj_no.device
     sizes = dict(xpos=(km.nbody * 3, torch.float32), xquat=(km.nbody * 4, torch.float32),
@@ -219,14 +220,21 @@ def h1_play_from_velocity(dm, spec, traj: DeviceTrajectory, state, n_steps, dt=0
         if k not in out:
             c, dt_ = sizes[k]
             out[k] = torch.empty((n_steps, n) if c is None else (n_steps, c, n), dtype=dt_, device=dev)
+    cq = state.get("curr_qpos")
     ps = OmPlayState(traj_no=traj.traj_no.data_ptr(), step_no=traj.step_no.data_ptr(),
                      reset_count=traj.reset_count.data_ptr(), xy_off=traj.xy_off.data_ptr(),
-                     curr_qpos=_p(state["curr_qpos"], torch.float64).value, pending=_p(state["pending"], torch.float32).value,
+                     curr_qpos=None if cq is None else _p(cq, torch.float64).value,
+                     pending=_p(state["pending"], torch.float32).value,
                      prev_x_vel=_p(state["prev_x_vel"], torch.float32).value)
     po = OmPlayOut(**{k: (out[k].data_ptr() if k in out else None) for k in sizes})
-    check(_lib.load().om_h1_play_from_velocity(dm.handle, C.byref(spec), traj.handle, traj.seed, traj.env_id0, float(dt),
-                                               int(n_steps), int(bool(end_episode_reset)), C.byref(ps), C.byref(po),
-                                               n, max(n, 1), _stream()))
+    if forced:
+        check(_lib.load().om_h1_play_trajectory(dm.handle, C.byref(spec), traj.handle, traj.seed, traj.env_id0, int(n_steps),
+                                                int(bool(end_episode_reset)), C.byref(ps), C.byref(po), n, max(n, 1),
+                                                _stream()))
+    else:
+        check(_lib.load().om_h1_play_from_velocity(dm.handle, C.byref(spec), traj.handle, traj.seed, traj.env_id0, float(dt),
+                                                   int(n_steps), int(bool(end_episode_reset)), C.byref(ps), C.byref(po),
+                                                   n, max(n, 1), _stream()))
     return out
 
 

@@ -144,3 +144,44 @@ def play_trajectory_from_velocity(model, table, n_episodes, n_steps_per_episode,
     out["final"] = dict(traj_no=tr.traj_no, step_no=tr.step_no, reset_count=tr.reset_count,
                         curr_qpos=curr_qpos, pending_sample=sample)
     return out
+
+
+def play_trajectory(model, table, n_episodes, n_steps_per_episode, seed=0, env_id=0, record_fk=True):
+    """One env of ``LocoEnvBase.play_trajectory`` (loco_env_base.py:338-442, render/record off): every step forces the
+    model to the current trajectory sample (:408), runs mj_forward (:410), fetches the next sample / resets at the end
+    of a trajectory (:414-418) and checks has_fallen on it (:420-422); the episode ends with reset() (:432) while
+    ``sample`` stays the stale one.  Same record layout as play_trajectory_from_velocity."""
+    nj = len(perm(model))
+    xv = x_vel_idx(model)
+    tr = TrajectoryState(table, seed=seed, env_id=env_id)
+    rec = {k: [] for k in ("qpos", "qvel", "xpos", "xquat", "site_xpos", "cvel", "obs", "fallen", "reward", "traj_no",
+                           "step_no", "reset_count")}
+    tr.reset_trajectory()                                   # :377 reset()
+    sample = tr.get_current_sample()                        # :379
+    prev_obs = create_observation(sample)
+    for _ep in range(n_episodes):
+        for _j in range(n_steps_per_episode):
+            qpos, qvel = set_sim_state(model, sample)       # :408
+            rec["qpos"].append(qpos)
+            rec["qvel"].append(qvel)
+            if record_fk:
+                fk = K.forward(model, qpos[None], qvel[None])   # :410
+                for k in ("xpos", "xquat", "site_xpos", "cvel"):
+                    rec[k].append(fk[k][0])
+            sample = tr.get_next_sample()                   # :414
+            if sample is None:                              # :416-418
+                tr.reset_trajectory()
+                sample = tr.get_current_sample()
+            obs = create_observation(sample)                # :420
+            rec["obs"].append(obs)
+            rec["fallen"].append(bool(has_fallen(obs)))
+            rec["reward"].append(float(target_velocity_reward(prev_obs, xv)))
+            prev_obs = obs
+            rec["traj_no"].append(tr.traj_no)
+            rec["step_no"].append(tr.step_no)
+            rec["reset_count"].append(tr.reset_count)
+        s_ = tr.reset_trajectory()                          # :432 (sample stays the stale one)
+        prev_obs = create_observation(s_)
+    out = {k: np.asarray(v) for k, v in rec.items() if len(v)}
+    out["final"] = dict(traj_no=tr.traj_no, step_no=tr.step_no, reset_count=tr.reset_count, pending_sample=sample)
+    return out

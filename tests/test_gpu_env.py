@@ -92,8 +92,11 @@ def test_play_trajectory_and_dataset_and_trajectory_api():
     import torch
     from oracle import h1 as OH
     env = _make(4)
-    res = env.play_trajectory(n_episodes=1, n_steps_per_episode=60, render=False)
-    assert tuple(res["obs"].shape) == (4, 32) and not bool(res["has_fallen"].any())
+    res = env.play_trajectory(n_episodes=1, n_steps_per_episode=60, render=False)           # fused kernel
+    assert tuple(res["obs"].shape) == (60, 32, 4) and not bool(res["fallen"].any())
+    from olympics_mujoco_b200.environments.loco_env_base import LocoEnvBase as Base
+    loop = Base.play_trajectory(_make(4), n_episodes=1, n_steps_per_episode=60, render=False)  # per-step kernels, same seed
+    assert torch.equal(res["obs"][-1].t(), loop["obs"]) and not bool(loop["has_fallen"].any())
     ds = env.create_dataset()
     z = np.load(GOLDEN / "trajectory_ref.npz")
     assert ds["states"].shape == (149, 32) and np.array_equal(ds["last"], z["ds_last"])

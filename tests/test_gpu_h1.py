@@ -158,3 +158,39 @@ def test_play_trajectory_from_velocity_parity(h1_model, n_episodes, n_steps, chu
         assert int(dt.traj_no[e]) == fin["traj_no"] and int(dt.step_no[e]) == fin["step_no"]
         assert int(dt.reset_count[e]) == fin["reset_count"]
         assert_close(state["curr_qpos"][:, e].cpu().numpy(), fin["curr_qpos"], "curr_qpos", rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("chunk", ["1", "7", "100000"])      # time-parallel x2, sequential-in-time kernel
+@pytest.mark.parametrize("n_episodes,n_steps", [(1, 120), (3, 37)])
+def test_play_trajectory_forced_parity(h1_model, n_episodes, n_steps, chunk, monkeypatch):
+    """om_h1_play_trajectory (LocoEnvBase.play_trajectory, loco_env_base.py:338-442) against the oracle."""
+    import torch
+    monkeypatch.setenv("OM_PLAY_CHUNK", chunk)
+    from olympics_mujoco_b200 import kernels as Kn
+    from oracle import h1 as OH
+    tab = _table()
+    n, seed = 24, 101
+    dm = Kn.DeviceModel(h1_model)
+    spec = _spec(h1_model)
+    dt = Kn.DeviceTrajectory(tab, n, seed=seed)
+    sample = dt.reset()
+    state = dict(pending=sample.clone(), prev_x_vel=sample[17].clone())
+    outs = []
+    for _ in range(n_episodes):
+        o = Kn.h1_play_from_velocity(dm, spec, dt, state, n_steps, end_episode_reset=True, forced=True)
+        torch.cuda.synchronize()
+        outs.append({k: v.cpu().numpy() for k, v in o.items()})
+    cat = {k: np.concatenate([o[k] for o in outs], axis=0) for k in outs[0]}
+    for e in range(n):
+        ref = OH.play_trajectory(h1_model, tab, n_episodes, n_steps, seed=seed, env_id=e)
+        assert np.array_equal(cat["traj_no_t"][:, e], ref["traj_no"]) and np.array_equal(cat["step_no_t"][:, e], ref["step_no"])
+        assert np.array_equal(cat["fallen"][:, e].astype(bool), ref["fallen"])
+        assert np.array_equal(cat["obs"][:, :, e], ref["obs"].astype(np.float32))
+        assert_close(cat["reward"][:, e], ref["reward"], "reward")
+        assert_close(cat["xpos"][:, :, e], ref["xpos"].reshape(-1, 63), "xpos")
+        assert_close(cat["xquat"][:, :, e], ref["xquat"].reshape(-1, 84), "xquat")
+        assert_close(cat["cvel"][:, :, e], ref["cvel"].reshape(-1, 126), "cvel")
+        fin = ref["final"]
+        assert int(dt.traj_no[e]) == fin["traj_no"] and int(dt.step_no[e]) == fin["step_no"]
+        assert int(dt.reset_count[e]) == fin["reset_count"]
+        assert_close(state["pending"][:, e].cpu().numpy(), fin["pending_sample"], "pending sample", rtol=1e-6, atol=1e-6)
