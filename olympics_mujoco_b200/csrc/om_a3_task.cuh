@@ -85,9 +85,7 @@ struct A3TaskRegs { int phase, t1, t2, frames, mode, seq_len, reached; };
 
 OM_HD float norm3(V3 a) { return sqrtf(dot(a, a)); }
 
-// What WalkingTask.step / calc_reward / done read per env-step, reduced to 17 floats: this is also the record the
-// time-parallel path writes between its FK pass and its (sequential-in-time) task pass.
-constexpr int A3_NFEAT = 17;
+// What WalkingTask.step / calc_reward / done read per env-step, reduced to 17 floats
 struct A3TaskIn {
   V3 root_p; Q4 root_q; float head_x, head_y; V3 lsite, rsite; float lvel_n, rvel_n;
 };
@@ -99,25 +97,6 @@ OM_HD A3TaskIn a3_task_in(const A3Feat& f) {
   t.rvel_n = norm3(f.rv + cross(f.rw, f.rfoot_p - f.root_p));
   return t;
 }
-OM_HD void a3_task_in_store(const A3TaskIn& t, float* b, size_t ld) {
-  b[0] = t.root_p.x; b[ld] = t.root_p.y; b[2 * ld] = t.root_p.z;
-  b[3 * ld] = t.root_q.w; b[4 * ld] = t.root_q.x; b[5 * ld] = t.root_q.y; b[6 * ld] = t.root_q.z;
-  b[7 * ld] = t.head_x; b[8 * ld] = t.head_y;
-  b[9 * ld] = t.lsite.x; b[10 * ld] = t.lsite.y; b[11 * ld] = t.lsite.z;
-  b[12 * ld] = t.rsite.x; b[13 * ld] = t.rsite.y; b[14 * ld] = t.rsite.z;
-  b[15 * ld] = t.lvel_n; b[16 * ld] = t.rvel_n;
-}
-OM_HD A3TaskIn a3_task_in_load(const float* b, size_t ld) {
-  A3TaskIn t;
-  t.root_p = V3{b[0], b[ld], b[2 * ld]};
-  t.root_q = Q4{b[3 * ld], b[4 * ld], b[5 * ld], b[6 * ld]};
-  t.head_x = b[7 * ld]; t.head_y = b[8 * ld];
-  t.lsite = V3{b[9 * ld], b[10 * ld], b[11 * ld]};
-  t.rsite = V3{b[12 * ld], b[13 * ld], b[14 * ld]};
-  t.lvel_n = b[15 * ld]; t.rvel_n = b[16 * ld];
-  return t;
-}
-
 // sequence[t1], sequence[t2] kept in registers: they change only when a target is reached
 struct A3Targets { V3 p1; float th1; V3 p2; float th2; };
 template <class Seq>

@@ -38,21 +38,3 @@ def oracle_obs(model, gold, e, upto=None):
         obs[t], total[t], _, _ = OA.step_tail(model, gold["step_qpos"][e, t].astype(np.float64),
                                               gold["step_qvel"][e, t].astype(np.float64), ts, con, lut)
     return obs0, obs, total
-
-
-def decision_margins(model, gold, e):
-    """|value - threshold| of every float comparison that feeds an integer/bool output, per step (float64 oracle):
-    used to excuse fp32-vs-float64 flips only where the reference itself is within rounding of a threshold."""
-    from oracle import kinematics as K
-    ids = OA.A3Ids(model)
-    T = gold["step_done"].shape[1]
-    seq = gold["reset_sequence"][e]
-    m = np.empty(T)
-    for t in range(T):
-        fk = K.forward(model, gold["step_qpos"][e, t].astype(np.float64)[None], gold["step_qvel"][e, t].astype(np.float64)[None])
-        lp, rp = fk["site_xpos"][0, ids.lsite], fk["site_xpos"][0, ids.rsite]
-        t1_before = gold["step_ints"][e, t - 1, 1] if t > 0 else gold["reset_ints"][e, 1]
-        tgt = seq[t1_before][:3]
-        m[t] = min(abs(np.linalg.norm(lp - tgt) - 0.2), abs(np.linalg.norm(rp - tgt) - 0.2),
-                   abs(fk["xpos"][0, ids.root][2] - min(lp[2], rp[2]) - 0.6))
-    return m

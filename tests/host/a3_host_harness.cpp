@@ -42,10 +42,7 @@ extern "C" void host_a3_rollout(const float* lut6, int period, int delay, double
     A3Sink<NullFkSink> S{};
     om_fk_stick_figure_a3(q, qd, S);
     const int fl = (int)c[3];
-    // through the 17-float record, like the time-parallel path
-    float rec[A3_NFEAT];
-    a3_task_in_store(a3_task_in(S.f), rec, 1);
-    a3_task_step(C, a3_task_in_load(rec, 1), s, tc, SeqHost{seq}, c[0], c[1], c[2], (fl & 1) != 0, (fl & 2) != 0, o, tr, total, d);
+    a3_task_step(C, a3_task_in(S.f), s, tc, SeqHost{seq}, c[0], c[1], c[2], (fl & 1) != 0, (fl & 2) != 0, o, tr, total, d);
     std::memcpy(obs + t * A3_NOBS, o, sizeof o);
     std::memcpy(terms + t * 6, tr, sizeof tr);
     reward[t] = total;
