@@ -263,7 +263,7 @@ def generate_fk(model, fn_name):
                 if jt == JNT_SLIDE:
                     p = g.vfma(axis_w, dq, p)
                 elif jt == JNT_HINGE:
-                    g.emit(f"float s{j}, c{j}; sincosf(0.5f * ({dq}), &s{j}, &c{j});")
+                    g.emit(f"float s{j}, c{j}; om::om_sincos(0.5f * ({dq}), &s{j}, &c{j});")
                     sj, cj = E(n=f"s{j}"), E(n=f"c{j}")
                     qloc = [cj] + [g.mul(E(a), sj) for a in model.jnt_axis[j]]
                     qt = g.qmul(qt, qloc)
@@ -323,6 +323,134 @@ def generate_fk(model, fn_name):
     head = (f"// GENERATED by olympics_mujoco_b200/codegen.py from model '{model.name}' "
             f"(fingerprint {model_fingerprint(model)}) -- do not edit.\n"
             f"// nbody={model.nbody} njnt={model.njnt} nq={model.nq} nv={model.nv} nsite={model.nsite}\n"
+            f"template <class Sink>\nOM_HD void {fn_name}(const float (&q)[{model.nq}], "
+            f"const float (&qd)[{model.nv}], Sink& S) {{\n")
+    return head + body + "\n}\n"
+
+
+def generate_fk_pos(model, fn_name):
+    """Position/velocity-only variant for consumers that never read body orientations (the A3 walking task reads
+    xpos / site_xpos / point velocities and the root quaternion, which is qpos itself): the chain is carried as
+    ROTATION MATRICES, so an axis-aligned hinge costs 12 multiply-adds (two columns rotate) instead of a quaternion
+    product, a renormalisation and three quaternion-vector rotations, and a world joint axis is a column of the
+    parent's matrix.  Same quantities as ``generate_fk`` to fp32 round-off (checked against the float64 oracle by
+    tests/test_host.py).  Sink calls: S.xpos, S.site_xpos, S.vel_p for every body; S.xquat for free-joint bodies only.
+    """
+    g = Gen()
+    nb = model.nbody
+    c3 = lambda v: [E(x) for x in v]
+    I3 = [ONE, ZERO, ZERO, ZERO, ONE, ZERO, ZERO, ZERO, ONE]
+    pos = {0: [ZERO, ZERO, ZERO]}
+    rot = {0: list(I3)}
+    wvel = {0: [ZERO, ZERO, ZERO]}
+    lvel = {0: [ZERO, ZERO, ZERO]}
+    P = {}
+
+    def mv(R, v):
+        return [g.dot(R[3 * r:3 * r + 3], v) for r in range(3)]
+
+    def mm(A, B):
+        return [g.dot(A[3 * r:3 * r + 3], [B[c], B[3 + c], B[6 + c]]) for r in range(3) for c in range(3)]
+
+    def const_mat(q):
+        w, x, y, z = [float(v) for v in np.asarray(q, np.float64) / np.linalg.norm(q)]
+        return [E(v) for v in (1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+                               2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                               2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y))]
+
+    def is_identity_quat(q):
+        return abs(q[0] - 1.0) < 1e-15 and np.all(np.abs(q[1:]) < 1e-15)
+
+    q_in = lambda k: E(n=f"q[{k}]")
+    qd_in = lambda k: E(n=f"qd[{k}]")
+    g.emit("S.xpos(0, 0.0f, 0.0f, 0.0f);")
+    for i in range(1, nb):
+        g.emit(f"// ---- body {i}: {model.body_names[i]}")
+        pid = int(model.body_parentid[i])
+        rid = int(model.body_rootid[i])
+        jadr, jnum = int(model.body_jntadr[i]), int(model.body_jntnum[i])
+        w_i, v_i = list(wvel[pid]), list(lvel[pid])
+        if jnum == 1 and model.jnt_type[jadr] == JNT_FREE:
+            qa, da = int(model.jnt_qposadr[jadr]), int(model.jnt_dofadr[jadr])
+            p = [q_in(qa + k) for k in range(3)]
+            qt = g.qnormalize([q_in(qa + 3 + k) for k in range(4)])
+            g.emit(f"S.xquat({i}, {qt[0]}, {qt[1]}, {qt[2]}, {qt[3]});")
+            w, x, y, z = qt
+            two = E(2.0)
+            xx, yy, zz = g.mul(x, x), g.mul(y, y), g.mul(z, z)
+            xy, xz, yz, wx, wy, wz = g.mul(x, y), g.mul(x, z), g.mul(y, z), g.mul(w, x), g.mul(w, y), g.mul(w, z)
+            one_m2 = lambda a, b: g.fma(E(-2.0), g.add(a, b), ONE)
+            R = [one_m2(yy, zz), g.mul(two, g.sub(xy, wz)), g.mul(two, g.add(xz, wy)),
+                 g.mul(two, g.add(xy, wz)), one_m2(xx, zz), g.mul(two, g.sub(yz, wx)),
+                 g.mul(two, g.sub(xz, wy)), g.mul(two, g.add(yz, wx)), one_m2(xx, yy)]
+            if rid == i:
+                P[rid] = p
+            v_i = [g.add(v_i[k], qd_in(da + k)) for k in range(3)]
+            arm = g.vsub(P[rid], p)
+            for k in range(3):
+                axis = [R[k], R[3 + k], R[6 + k]]
+                w_i = g.vfma(axis, qd_in(da + 3 + k), w_i)
+                v_i = g.vfma(g.cross(axis, arm), qd_in(da + 3 + k), v_i)
+        else:
+            p = g.vadd(pos[pid], mv(rot[pid], c3(model.body_pos[i])))
+            bq = model.body_quat[i]
+            R = rot[pid] if is_identity_quat(bq) else mm(rot[pid], const_mat(bq))
+            joints = []
+            for j in range(jadr, jadr + jnum):
+                jt = int(model.jnt_type[j])
+                qa, da = int(model.jnt_qposadr[j]), int(model.jnt_dofadr[j])
+                ax = np.asarray(model.jnt_axis[j], np.float64)
+                axis_w = mv(R, c3(ax))
+                anchor = g.vadd(mv(R, c3(model.jnt_pos[j])), p)
+                joints.append((jt, da, axis_w, anchor))
+                dq = g.sub(q_in(qa), E(model.qpos0[qa]))
+                if jt == JNT_SLIDE:
+                    p = g.vfma(axis_w, dq, p)
+                elif jt == JNT_HINGE:
+                    g.emit(f"float s{j}, c{j}; om::om_sincos({dq}, &s{j}, &c{j});")
+                    sj, cj = E(n=f"s{j}"), E(n=f"c{j}")
+                    # Rodrigues: c I + (1 - c) a a^T + s [a]x, constants folded (axis-aligned: four live entries)
+                    omc = None
+                    K = [[0.0, -ax[2], ax[1]], [ax[2], 0.0, -ax[0]], [-ax[1], ax[0], 0.0]]
+                    rodr = []
+                    for r in range(3):
+                        for c in range(3):
+                            aa = float(np.float32(ax[r] * ax[c]))
+                            if abs(aa - (1.0 if r == c else 0.0)) < 1e-7 and abs(K[r][c]) < 1e-7 and r == c:
+                                rodr.append(ONE)               # diagonal entry on the axis itself
+                                continue
+                            e = g.mul(E(1.0 if r == c else 0.0), cj)
+                            if abs(aa) > 1e-7 and not (r == c and abs(aa - 1.0) < 1e-7):
+                                if omc is None:
+                                    omc = g.sub(ONE, cj)
+                                e = g.fma(E(aa), omc, e)
+                            e = g.fma(E(K[r][c]), sj, e)
+                            rodr.append(e)
+                    R = mm(R, rodr)
+                    jp = c3(model.jnt_pos[j])
+                    if any(x.c != 0.0 for x in jp):
+                        p = g.vsub(anchor, mv(R, jp))
+                else:
+                    raise NotImplementedError("ball joints are served by the table-driven kernel only")
+            if rid == i:
+                P[rid] = p
+            for jt, da, axis_w, anchor in joints:
+                if jt == JNT_SLIDE:
+                    v_i = g.vfma(axis_w, qd_in(da), v_i)
+                else:
+                    w_i = g.vfma(axis_w, qd_in(da), w_i)
+                    v_i = g.vfma(g.cross(axis_w, g.vsub(P[rid], anchor)), qd_in(da), v_i)
+        pos[i], rot[i], wvel[i], lvel[i] = p, R, w_i, v_i
+        g.emit(f"S.xpos({i}, {p[0]}, {p[1]}, {p[2]});")
+        g.emit(f"S.vel_p({i}, {w_i[0]}, {w_i[1]}, {w_i[2]}, {v_i[0]}, {v_i[1]}, {v_i[2]});")
+        for s in range(model.nsite):
+            if int(model.site_bodyid[s]) != i:
+                continue
+            sp = g.vadd(p, mv(R, c3(model.site_pos[s])))
+            g.emit(f"S.site_xpos({s}, {sp[0]}, {sp[1]}, {sp[2]});")
+    body = "\n".join(g.lines)
+    head = (f"// GENERATED by olympics_mujoco_b200/codegen.py (generate_fk_pos) from model '{model.name}' "
+            f"(fingerprint {model_fingerprint(model)}) -- do not edit.\n"
             f"template <class Sink>\nOM_HD void {fn_name}(const float (&q)[{model.nq}], "
             f"const float (&qd)[{model.nv}], Sink& S) {{\n")
     return head + body + "\n}\n"

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(BLOCK) a3_task_kernel(A3Args a) {
       in = a3_task_in(S.f);
     } else {
       A3Sink<NullFkSink> S{};
-      om_fk_stick_figure_a3(q, qd, S);
+      om_fk_pos_stick_figure_a3(q, qd, S);       // matrix-chain variant: no body orientations needed
       in = a3_task_in(S.f);
     }
     const int fl = (int)con[3];
@@ -102,13 +102,26 @@ __global__ void __launch_bounds__(BLOCK) a3_task_kernel(A3Args a) {
 }
 
 // ---------------------------------------------------------------- time-parallel replay (few envs, many steps)
-// The only recurrence over time is the task's integer state; everything expensive (FK, the state-independent 31
-// observation rows) depends on (env, t) alone.  Pass 1 runs one thread per (env, t) -- 16384 envs x 64 steps fill the
-// machine instead of 256 CTAs of 64 threads -- evaluates every piece that is independent of the footstep-target state
-// (om_a3_task.cuh: a3_task_pre) and leaves a 16-float record per env-step; pass 2 walks the T records of an env
-// sequentially (one thread per env) through the target state machine and the two terms that depend on it.
+// The only recurrence over time is the task's footstep-target state machine; everything expensive (FK, the
+// state-independent 33 observation rows, four reward terms) depends on (env, t) alone.
+//   a3_feat_kernel  one thread per (env, t): FK + a3_task_pre; leaves a 16-float record per env-step plus one byte of
+//                   "a foot is near candidate target j" bits (om_a3_task.cuh: a3_near_bits).  ~1900 instructions and
+//                   660 B of HBM traffic per env-step: issue time and memory time are of the same size.  (Measured and
+//                   rejected: persistent CTAs staging the next tile's inputs in shared memory with cp.async or
+//                   cp.async.bulk -- the CTAs fall into lockstep, load, compute and store phases stop overlapping
+//                   across CTAs, 112 us instead of 90 us.)
+//   a3_walk_kernel  one thread per env: the integer state machine over the T bytes (a few instructions per step),
+//                   leaves a one-byte (advances, reached) code per env-step and the final task state;
+//   a3_post_kernel  one thread per (env, t) again: goal steps, orientation and step terms, total.
+struct A3Scratch {
+  float* feat;          // [T][16][ld]
+  uint8_t* near;        // [T][ld]   candidate bits
+  uint8_t* code;        // [T][ld]   advances since the call started | reached << 3, after the step's update
+  int32_t* start;       // [2][ld]   t1, t2 at the start of the call
+};
+
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) a3_feat_kernel(A3Args a, float* __restrict__ feat) {
+__global__ void __launch_bounds__(BLOCK, 5) a3_feat_kernel(A3Args a, A3Scratch w, int ncand) {
   const int env = blockIdx.x * BLOCK + threadIdx.x;
   const int t = blockIdx.y;
   if (env >= a.n) return;
@@ -125,15 +138,22 @@ __global__ void __launch_bounds__(BLOCK) a3_feat_kernel(A3Args a, float* __restr
   for (int k = 0; k < 4; ++k) con[k] = cp[k * ld];
   const int phase = (a.ints[A3I_PHASE * ld + e] + t + 1) % a.C.period;     // walking_task.py:248-250, t + 1 increments
   const int mode = a.ints[A3I_MODE * ld + e];
+  const int t1_0 = a.ints[A3I_T1 * ld + e], t2_0 = a.ints[A3I_T2 * ld + e], seq_len = a.ints[A3I_SEQLEN * ld + e];
+  if (t == 0) {                                                            // start state of the call for the post pass
+    w.start[e] = t1_0;
+    w.start[ld + e] = t2_0;
+  }
   float obs[A3_NOBS], terms[6];
   a3_obs_robot(q, qd, obs);
   A3Sink<NullFkSink> S{};
-  om_fk_stick_figure_a3(q, qd, S);
+  om_fk_pos_stick_figure_a3(q, qd, S);           // matrix-chain variant: no body orientations needed
   bool done;
   const int fl = (int)con[3];
   const A3Rec rec = a3_task_pre(a.C, a3_task_in(S.f), phase, mode, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, terms,
                                 obs[31], obs[32], done);
-  a3_rec_store(rec, feat + (size_t)t * A3_NREC * ld + e, ld);
+  a3_rec_store(rec, w.feat + (size_t)t * A3_NREC * ld + e, ld);
+  w.near[(size_t)t * ld + e] =
+      (uint8_t)a3_near_bits(a.C, rec.lsite, rec.rsite, ncand, t1_0, t2_0, seq_len, SeqGlobal{a.sequence + e, ld});
   if (a.o.obs) {
     float* ob = a.o.obs + (size_t)t * A3_NOBS * ld + e;
 #pragma unroll
@@ -146,38 +166,56 @@ __global__ void __launch_bounds__(BLOCK) a3_feat_kernel(A3Args a, float* __restr
   if (a.o.done) a.o.done[(size_t)t * ld + e] = done ? 1 : 0;
 }
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) a3_seq_kernel(A3Args a, const float* __restrict__ feat) {
-  const int env = blockIdx.x * BLOCK + threadIdx.x;
+__global__ void __launch_bounds__(64) a3_walk_kernel(A3Args a, A3Scratch w) {
+  const int env = blockIdx.x * 64 + threadIdx.x;
   if (env >= a.n) return;
   const size_t ld = a.ld, e = env;
-  A3TaskRegs s{a.ints[A3I_PHASE * ld + e], a.ints[A3I_T1 * ld + e], a.ints[A3I_T2 * ld + e], a.ints[A3I_FRAMES * ld + e],
-               a.ints[A3I_MODE * ld + e], a.ints[A3I_SEQLEN * ld + e], a.ints[A3I_REACHED * ld + e]};
-  const SeqGlobal seq{a.sequence + e, ld};
-  A3Targets tc = a3_targets_load(s, seq);
-  A3TargetTrig tg = a3_target_trig(tc);
-  A3Rec in = a3_rec_load(feat + e, ld);
-  for (int t = 0; t < a.T; ++t) {
-    A3Rec inn = in;
-    if (t + 1 < a.T) inn = a3_rec_load(feat + (size_t)(t + 1) * A3_NREC * ld + e, ld);   // independent of the task state
-    float goal[8], t2, t4, total;
-    a3_task_seq(a.C, in, s, tc, tg, seq, goal, t2, t4, total);
-    if (a.o.obs) {
-      float* ob = a.o.obs + ((size_t)t * A3_NOBS + 33) * ld + e;
+  const int t1_0 = a.ints[A3I_T1 * ld + e], t2_0 = a.ints[A3I_T2 * ld + e], seq_len = a.ints[A3I_SEQLEN * ld + e];
+  A3Walk s{0, a.ints[A3I_FRAMES * ld + e], a.ints[A3I_REACHED * ld + e]};
+  constexpr int CH = 64;
+  for (int t0 = 0; t0 < a.T; t0 += CH) {
+    uint8_t nb[CH];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) ob[k * ld] = goal[k];
+    for (int i = 0; i < CH; ++i) nb[i] = t0 + i < a.T ? w.near[(size_t)(t0 + i) * ld + e] : 0;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      if (t0 + i < a.T) {
+        a3_walk_step(a.C, nb[i], s);
+        w.code[(size_t)(t0 + i) * ld + e] = (uint8_t)(s.j | (s.reached << 3));
+      }
     }
-    if (a.o.terms) {
-      float* tp = a.o.terms + (size_t)t * 6 * ld + e;
-      tp[2 * ld] = t2;
-      tp[4 * ld] = t4;
-    }
-    if (a.o.reward) a.o.reward[(size_t)t * ld + e] = total;
-    in = inn;
   }
-  a.ints[A3I_PHASE * ld + e] = (s.phase + a.T) % a.C.period;
-  a.ints[A3I_T1 * ld + e] = s.t1; a.ints[A3I_T2 * ld + e] = s.t2;
+  a.ints[A3I_PHASE * ld + e] = (a.ints[A3I_PHASE * ld + e] + a.T) % a.C.period;
+  a.ints[A3I_T1 * ld + e] = a3_cand(s.j, t1_0, t2_0, seq_len);
+  a.ints[A3I_T2 * ld + e] = a3_cand(s.j + 1, t1_0, t2_0, seq_len);
   a.ints[A3I_FRAMES * ld + e] = s.frames; a.ints[A3I_REACHED * ld + e] = s.reached;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) a3_post_kernel(A3Args a, A3Scratch w) {
+  const int env = blockIdx.x * BLOCK + threadIdx.x;
+  const int t = blockIdx.y;
+  if (env >= a.n) return;
+  const size_t ld = a.ld, e = env;
+  const A3Rec rec = a3_rec_load(w.feat + (size_t)t * A3_NREC * ld + e, ld);
+  const int code = w.code[(size_t)t * ld + e];
+  const int mode = a.ints[A3I_MODE * ld + e], seq_len = a.ints[A3I_SEQLEN * ld + e];
+  const int t1_0 = w.start[e], t2_0 = w.start[ld + e];
+  const int j = code & 7;
+  float goal[8], tm2, tm4, total;
+  a3_task_post(a.C, rec, mode, a3_cand(j, t1_0, t2_0, seq_len), a3_cand(j + 1, t1_0, t2_0, seq_len), (code >> 3) != 0,
+               SeqGlobal{a.sequence + e, ld}, goal, tm2, tm4, total);
+  if (a.o.obs) {
+    float* ob = a.o.obs + ((size_t)t * A3_NOBS + 33) * ld + e;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ob[k * ld] = goal[k];
+  }
+  if (a.o.terms) {
+    float* tp = a.o.terms + (size_t)t * 6 * ld + e;
+    tp[2 * ld] = tm2;
+    tp[4 * ld] = tm4;
+  }
+  if (a.o.reward) a.o.reward[(size_t)t * ld + e] = total;
 }
 
 struct A3ResetArgs {
@@ -203,7 +241,7 @@ __global__ void __launch_bounds__(128) a3_reset_kernel(A3ResetArgs a) {
   a3_reset_uniforms(a.seed, a.env_id0 + env, rc, u);
   a3_reset_qpos_qvel(a.init_qpos, u, q, qd);
   A3Sink<NullFkSink> S{};
-  om_fk_stick_figure_a3(q, qd, S);                                     // set_state -> mj_forward
+  om_fk_pos_stick_figure_a3(q, qd, S);                                 // set_state -> mj_forward
   A3TaskRegs s;
   a3_task_reset(a.C, S.f, u, a.step_h, s, SeqStore{a.sequence + e, ld});
 #pragma unroll
@@ -234,10 +272,10 @@ struct OmA3Task {
   A3TaskConst C;
   float* lut = nullptr;        // device [period][6]
   float* init_qpos = nullptr;  // device [25]
-  // record buffer of the time-parallel replay ([T][17][ld] floats), grown on demand and kept; one replay call per
-  // handle may be in flight at a time
-  mutable float* feat = nullptr;
-  mutable size_t feat_floats = 0;
+  // scratch of the time-parallel replay (records, state codes, env-block counters), grown on demand and kept; one
+  // replay call per handle may be in flight at a time
+  mutable void* scratch = nullptr;
+  mutable size_t scratch_bytes = 0;
 };
 
 extern "C" int om_a3_task_create(const OmA3TaskDesc* d, OmA3Task** out) {
@@ -268,6 +306,7 @@ extern "C" int om_a3_task_create(const OmA3TaskDesc* d, OmA3Task** out) {
   t->C.fmax = (float)(d->total_mass * 9.8 * 0.5);
   t->C.vmax = 0.2f;
   t->C.target_radius = d->target_radius;
+  t->C.near_d2 = a3_near_d2(d->target_radius);
   t->C.goal_height_ref = d->goal_height_ref;
   t->C.deadzone = 0.01 + 0.05 * d->goal_speed_ref;
   t->C.lut = t->lut;
@@ -279,7 +318,7 @@ extern "C" void om_a3_task_destroy(OmA3Task* t) {
   if (!t) return;
   cudaFree(t->lut);
   cudaFree(t->init_qpos);
-  if (t->feat) cudaFree(t->feat);
+  if (t->scratch) cudaFree(t->scratch);
   delete t;
 }
 
@@ -301,20 +340,42 @@ extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const flo
   int split = !want_fk && n_steps >= 2;
   if (const char* f = getenv("OM_A3_SPLIT")) split = atoi(f) != 0 && !want_fk;      // tuning / test hook
   if (split) {
-    const size_t need = (size_t)n_steps * A3_NREC * (size_t)ld;
-    if (task->feat_floats < need) {
-      if (task->feat) OM_CUDA_OK(cudaFree(task->feat));        // synchronises: no earlier call still reads it
-      task->feat = nullptr;
-      task->feat_floats = 0;
-      OM_CUDA_OK(cudaMalloc((void**)&task->feat, need * sizeof(float)));
-      task->feat_floats = need;
-    }
     constexpr int FB = 128;
-    a3_feat_kernel<FB><<<dim3(ceil_div(n, FB), n_steps), FB, 0, st>>>(a, task->feat);
-    OM_LAUNCHED();
-    constexpr int SB = 32;
-    a3_seq_kernel<SB><<<ceil_div(n, SB), SB, 0, st>>>(a, task->feat);
-    OM_LAUNCHED();
+    const int env_blocks = ceil_div(n, FB);
+    const size_t feat_b = (size_t)n_steps * A3_NREC * (size_t)ld * sizeof(float);
+    const size_t int_b = (size_t)2 * ld * sizeof(int32_t);
+    const size_t byte_b = (size_t)n_steps * (size_t)ld;
+    const size_t need = feat_b + int_b + 2 * byte_b;
+    if (task->scratch_bytes < need) {
+      if (task->scratch) OM_CUDA_OK(cudaFree(task->scratch));  // synchronises: no earlier call still reads it
+      task->scratch = nullptr;
+      task->scratch_bytes = 0;
+      OM_CUDA_OK(cudaMalloc(&task->scratch, need));
+      task->scratch_bytes = need;
+    }
+    char* base = (char*)task->scratch;
+    A3Scratch w{(float*)base, (uint8_t*)(base + feat_b + int_b), (uint8_t*)(base + feat_b + int_b + byte_b),
+                (int32_t*)(base + feat_b)};
+    // sub-calls no longer than the candidate bits cover (210 steps with the reference's 30 delay frames)
+    const int max_call = a3_max_steps_per_call(task->C.delay_frames);
+    for (int c0 = 0; c0 < n_steps; c0 += max_call) {
+      const int len = n_steps - c0 < max_call ? n_steps - c0 : max_call;
+      A3Args sub = a;
+      sub.qpos += (size_t)c0 * A3_NQ * ld; sub.qvel += (size_t)c0 * A3_NV * ld; sub.contact += (size_t)c0 * 4 * ld;
+      if (sub.o.obs) sub.o.obs += (size_t)c0 * A3_NOBS * ld;
+      if (sub.o.terms) sub.o.terms += (size_t)c0 * 6 * ld;
+      if (sub.o.reward) sub.o.reward += (size_t)c0 * ld;
+      if (sub.o.done) sub.o.done += (size_t)c0 * ld;
+      sub.T = len;
+      OM_REQUIRE(len <= 65535, "om_a3_task_step: at most 65535 steps per call");
+      if (getenv("OM_A3_FB64")) a3_feat_kernel<64><<<dim3(ceil_div(n, 64), len), 64, 0, st>>>(sub, w, a3_num_cand_host(len, task->C.delay_frames));
+      else a3_feat_kernel<FB><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, a3_num_cand_host(len, task->C.delay_frames));
+      OM_LAUNCHED();
+      a3_walk_kernel<<<ceil_div(n, 64), 64, 0, st>>>(sub, w);
+      OM_LAUNCHED();
+      a3_post_kernel<FB><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w);
+      OM_LAUNCHED();
+    }
     return 0;
   }
   if (want_fk) a3_task_kernel<BLOCK, true><<<grid, BLOCK, 0, st>>>(a);

@@ -14,6 +14,7 @@
 #include "om_math.cuh"
 #include "gen/a3_ids.h"
 #include "gen/fk_stick_figure_a3.cuh"
+#include "gen/fk_pos_stick_figure_a3.cuh"
 
 namespace om {
 
@@ -26,6 +27,7 @@ struct A3TaskConst {
   int period, delay_frames;
   float fmax, vmax;                   // rewards.py:66 (mass*9.8*0.5), :87 (0.2)
   double target_radius;               // walking_task.py:333
+  float near_d2;                      // smallest fp32 d2 with (double)sqrtf(d2) >= target_radius (a3_near_d2)
   double goal_height_ref, deadzone;   // StickFigureA3.py:110; rewards.py:36 (0.01 + 0.05*goal_speed_ref)
   const float* lut;                   // [period][6]: r_frc, r_vel, l_frc, l_vel clocks, sin/cos(2 pi phase/period)
 };
@@ -123,17 +125,46 @@ OM_HD void tf3_quat2mat(Q4 q, float (&m)[9]) {
 
 constexpr float A3_EPS4 = 8.8817842e-16f;     // transforms3d euler._EPS4 (4 * float64 eps)
 
-// StickFigureA3.get_obs rows 0..30 (everything that does not depend on the task state)
-OM_HD void a3_obs_robot(const float (&q)[A3_NQ], const float (&qd)[A3_NV], float (&obs)[A3_NOBS]) {
+// StickFigureA3.get_obs rows 0..3: euler2quat(roll, pitch, 0) of quat2euler(qpos[3:7]) (axes 'sxyz'), literally
+OM_NOINLINE Q4 a3_root_orient_trig(float qw, float qx, float qy, float qz) {
   float m[9];
-  tf3_quat2mat(Q4{q[3], q[4], q[5], q[6]}, m);                       // quat2euler(qpos[3:7])[0:2], axes 'sxyz'
+  tf3_quat2mat(Q4{qw, qx, qy, qz}, m);
   const float cy = sqrtf(fmaf(m[0], m[0], m[3] * m[3]));
   const float roll = cy > A3_EPS4 ? atan2f(m[7], m[8]) : atan2f(-m[5], m[4]);
   const float pitch = atan2f(-m[6], cy);
   float si, ci, sj, cj;
   sincosf(0.5f * roll, &si, &ci);
   sincosf(0.5f * pitch, &sj, &cj);
-  obs[0] = cj * ci; obs[1] = cj * si; obs[2] = sj * ci; obs[3] = -(sj * si);   // euler2quat(roll, pitch, 0)
+  return Q4{cj * ci, cj * si, sj * ci, -(sj * si)};
+}
+// The same quantity without inverse trigonometry: q = qz(yaw) qy(pitch) qx(roll) up to sign, so the observation is
+// conj(qz(yaw)) q with yaw = atan2(M10, M00); cos/sin of yaw/2 follow from (M00, M10)/cy by the half-angle formulas,
+// and the sign is the one that makes w = cos(pitch/2) cos(roll/2) non-negative.  Near gimbal lock (cy -> 0) the yaw
+// split is ill-conditioned and the literal path is taken.
+OM_HD void a3_root_orient(float qw, float qx, float qy, float qz, float* o) {
+  const float nq = fmaf(qw, qw, fmaf(qx, qx, fmaf(qy, qy, qz * qz)));
+  const float s2 = 2.0f / nq;
+  const float m00 = 1.0f - (qy * qy + qz * qz) * s2, m10 = (qx * qy + qw * qz) * s2;
+  const float cy2 = fmaf(m00, m00, m10 * m10);
+  if (!(cy2 > 1e-4f) || !(nq > 1e-12f)) {
+    const Q4 r = a3_root_orient_trig(qw, qx, qy, qz);
+    o[0] = r.w; o[1] = r.x; o[2] = r.y; o[3] = r.z;
+    return;
+  }
+  const float icy = rsqrtf(cy2), c = m00 * icy, sn = m10 * icy;
+  const float h = sqrtf(0.5f * (1.0f + fabsf(c)));            // the larger of |cos|, |sin| of yaw/2
+  const float g = sn / (2.0f * h);
+  const float chz = c >= 0.f ? h : fabsf(g), shz = c >= 0.f ? g : copysignf(h, sn);
+  const float inv = rsqrtf(nq);
+  float w = fmaf(chz, qw, shz * qz) * inv, x = fmaf(chz, qx, shz * qy) * inv;
+  float y = fmaf(chz, qy, -shz * qx) * inv, z = fmaf(chz, qz, -shz * qw) * inv;
+  const bool neg = w < 0.f || (w == 0.f && x < 0.f);
+  o[0] = neg ? -w : w; o[1] = neg ? -x : x; o[2] = neg ? -y : y; o[3] = neg ? -z : z;
+}
+
+// StickFigureA3.get_obs rows 0..30 (everything that does not depend on the task state)
+OM_HD void a3_obs_robot(const float (&q)[A3_NQ], const float (&qd)[A3_NV], float (&obs)[A3_NOBS]) {
+  a3_root_orient(q[3], q[4], q[5], q[6], obs);
 #pragma unroll
   for (int k = 0; k < 3; ++k) obs[4 + k] = qd[3 + k];
 #pragma unroll
@@ -182,7 +213,7 @@ OM_HD void a3_task_step(const A3TaskConst& C, const A3TaskIn& f, A3TaskRegs& s, 
   for (int i = 0; i < 2; ++i) {
     const V3 d = (i == 0 ? tc.p1 : tc.p2) - f.root_p;
     float st, ct;
-    sincosf(i == 0 ? tc.th1 : tc.th2, &st, &ct);
+    om_sincos(i == 0 ? tc.th1 : tc.th2, &st, &ct);
     const float a = fmaf(R[0], ct, R[3] * st), b = fmaf(R[1], ct, R[4] * st);   // column 0 of R^T Rz
     const float cy = sqrtf(fmaf(a, a, b * b));
     const bool walk = s.mode != A3_STANDING;
@@ -197,11 +228,11 @@ OM_HD void a3_task_step(const A3TaskConst& C, const A3TaskIn& f, A3TaskRegs& s, 
   if (s.mode != A3_STANDING) { r_frc_c = lrow[0]; r_vel_c = lrow[1]; l_frc_c = lrow[2]; l_vel_c = lrow[3]; }
   const float PI4 = 0.78539816339744831f;
   const float nl = fminf(l_grf, C.fmax) / C.fmax * 2.f - 1.f, nr = fminf(r_grf, C.fmax) / C.fmax * 2.f - 1.f;
-  const float frc = (tanf(PI4 * l_frc_c * nl) + tanf(PI4 * r_frc_c * nr)) * 0.5f;      // rewards.py:65-83
+  const float frc = (om_tan_q(PI4 * l_frc_c * nl) + om_tan_q(PI4 * r_frc_c * nr)) * 0.5f;      // rewards.py:65-83
   const float vl = fminf(f.lvel_n, C.vmax) / C.vmax * 2.f - 1.f, vr = fminf(f.rvel_n, C.vmax) / C.vmax * 2.f - 1.f;
-  const float vel = (tanf(PI4 * l_vel_c * vl) + tanf(PI4 * r_vel_c * vr)) * 0.5f;      // rewards.py:85-102
+  const float vel = (om_tan_q(PI4 * l_vel_c * vl) + om_tan_q(PI4 * r_vel_c * vr)) * 0.5f;      // rewards.py:85-102
   float sh, ch;
-  sincosf(0.5f * tc.th1, &sh, &ch);                                                    // euler2quat(0, 0, theta)
+  om_sincos(0.5f * tc.th1, &sh, &ch);                                                    // euler2quat(0, 0, theta)
   const float inner = fmaf(ch, f.root_q.w, sh * f.root_q.z);
   const float orient = expf(-10.f * (1.f - inner * inner));                            // rewards.py:121-126
   // rewards.py:27-40; the dead-zone test is evaluated in double on the fp32 inputs (root z is qpos[2] itself)
@@ -228,7 +259,8 @@ OM_HD void a3_task_step(const A3TaskConst& C, const A3TaskIn& f, A3TaskRegs& s, 
 // target_reached) depends on (env, t) alone -- including the phase clock, because phase(t) = (phase0 + t + 1) mod period
 // and the mode is fixed for an episode.  The (env, t)-parallel pass evaluates those pieces (four of the six reward
 // terms with their tanf/expf, done, the clock rows of the observation) and leaves a 16-float record; the sequential
-// pass keeps only the target state machine, the goal steps, the orientation and step terms.
+// pass keeps only the target state machine, reduced to integer work on per-candidate "target near" bits; a second
+// (env, t)-parallel pass finishes the goal steps, the orientation and step terms.
 constexpr int A3_NREC = 16;
 struct A3Rec {
   V3 root_p; Q4 root_q; V3 lsite, rsite;
@@ -262,9 +294,9 @@ OM_HD A3Rec a3_task_pre(const A3TaskConst& C, const A3TaskIn& f, int phase, int 
   if (mode != A3_STANDING) { r_frc_c = lrow[0]; r_vel_c = lrow[1]; l_frc_c = lrow[2]; l_vel_c = lrow[3]; }
   const float PI4 = 0.78539816339744831f;
   const float nl = fminf(l_grf, C.fmax) / C.fmax * 2.f - 1.f, nr = fminf(r_grf, C.fmax) / C.fmax * 2.f - 1.f;
-  const float frc = (tanf(PI4 * l_frc_c * nl) + tanf(PI4 * r_frc_c * nr)) * 0.5f;      // rewards.py:65-83
+  const float frc = (om_tan_q(PI4 * l_frc_c * nl) + om_tan_q(PI4 * r_frc_c * nr)) * 0.5f;      // rewards.py:65-83
   const float vl = fminf(f.lvel_n, C.vmax) / C.vmax * 2.f - 1.f, vr = fminf(f.rvel_n, C.vmax) / C.vmax * 2.f - 1.f;
-  const float vel = (tanf(PI4 * l_vel_c * vl) + tanf(PI4 * r_vel_c * vr)) * 0.5f;      // rewards.py:85-102
+  const float vel = (om_tan_q(PI4 * l_vel_c * vl) + om_tan_q(PI4 * r_vel_c * vr)) * 0.5f;      // rewards.py:85-102
   double err = fabs((double)f.root_p.z - (foot_contact ? (double)min_z : 0.0) - C.goal_height_ref);   // rewards.py:27-40
   if (err < C.deadzone) err = 0.0;
   const float errf = (float)err;
@@ -283,40 +315,77 @@ OM_HD A3Rec a3_task_pre(const A3TaskConst& C, const A3TaskIn& f, int phase, int 
 struct A3TargetTrig { float s1, c1, s2, c2, sh, ch; };
 OM_HD A3TargetTrig a3_target_trig(const A3Targets& tc) {
   A3TargetTrig g;
-  sincosf(tc.th1, &g.s1, &g.c1);
-  sincosf(tc.th2, &g.s2, &g.c2);
-  sincosf(0.5f * tc.th1, &g.sh, &g.ch);
+  om_sincos(tc.th1, &g.s1, &g.c1);
+  om_sincos(tc.th2, &g.s2, &g.c2);
+  om_sincos(0.5f * tc.th1, &g.sh, &g.ch);
   return g;
 }
 
-// Sequential part: target state machine (:266-289), goal steps (:184-225), orientation and step terms, total.
-// Does NOT touch s.phase (the caller tracks it).  Writes goal[8] (obs rows 33..40), terms[2], terms[4], total.
+// The target state machine (:266-289, update_target_steps :228-244) is the only recurrence over time.  Within one call
+// the target index t1 can only move along a chain fixed by the call's start state: candidate 0 = t1_0, candidate 1 =
+// t2_0, candidate j = min(t2_0 + j - 1, len - 1); t2 is always the next candidate.  The (env, t)-parallel pass
+// therefore evaluates "a foot is within target_radius of candidate j" for the first few candidates (one bit each),
+// and the recurrence shrinks to integer work on those bits: no geometry on the sequential path.
+constexpr int A3_MAX_CAND = 8;
+OM_HD int a3_cand(int j, int t1_0, int t2_0, int seq_len) {
+  if (j == 0) return t1_0;
+  const int k = t2_0 + j - 1;
+  return k < seq_len - 1 ? k : seq_len - 1;
+}
+// "(double)sqrtf(d2) < target_radius" as a threshold on d2 itself: sqrtf is correctly rounded, hence monotone, so the
+// two tests agree on every float.  Host-side helper (task creation, test harness).
+inline float a3_near_d2(double radius) {
+  float t = (float)(radius * radius);
+  while ((double)sqrtf(t) < radius) t = nextafterf(t, INFINITY);
+  while (t > 0.f && (double)sqrtf(nextafterf(t, 0.f)) >= radius) t = nextafterf(t, 0.f);
+  return t;
+}
 template <class Seq>
-OM_HD void a3_task_seq(const A3TaskConst& C, const A3Rec& f, A3TaskRegs& s, A3Targets& tc, A3TargetTrig& tg, const Seq& seq,
-                       float (&goal)[8], float& t2_orient, float& t4_step, float& total) {
-  float dl = norm3(f.lsite - tc.p1), dr = norm3(f.rsite - tc.p1);
-  if ((double)dl < C.target_radius || (double)dr < C.target_radius) {
-    s.reached = 1;
-    s.frames += 1;
+OM_HD uint32_t a3_near_bits(const A3TaskConst& C, V3 lsite, V3 rsite, int ncand, int t1_0, int t2_0, int seq_len, const Seq& seq) {
+  uint32_t bits = 0;
+#pragma unroll 1
+  for (int j = 0; j < ncand; ++j) {
+    const int k = a3_cand(j, t1_0, t2_0, seq_len);
+    const V3 p{seq(k, 0), seq(k, 1), seq(k, 2)};
+    const V3 a = lsite - p, b = rsite - p;
+    if (dot(a, a) < C.near_d2 || dot(b, b) < C.near_d2) bits |= 1u << j;        // norm3(.) < target_radius, see a3_near_d2
+  }
+  return bits;
+}
+struct A3Walk { int j, frames, reached; };       // j = number of target advances since the start of the call
+OM_HD void a3_walk_step(const A3TaskConst& C, uint32_t bits, A3Walk& w) {
+  if ((bits >> w.j) & 1u) {
+    w.reached = 1;
+    w.frames += 1;
   } else {
-    s.reached = 0;
-    s.frames = 0;
+    w.reached = 0;
+    w.frames = 0;
   }
-  if (s.reached && s.frames >= C.delay_frames) {
-    const int old_t2 = s.t2;
-    s.t1 = s.t2;
-    s.t2 += 1;
-    if (s.t2 == s.seq_len) s.t2 = s.seq_len - 1;
-    s.reached = 0;
-    s.frames = 0;
-    tc.p1 = tc.p2;
-    tc.th1 = tc.th2;
-    if (s.t2 != old_t2) { tc.p2 = V3{seq(s.t2, 0), seq(s.t2, 1), seq(s.t2, 2)}; tc.th2 = seq(s.t2, 3); }
-    tg = a3_target_trig(tc);
-    dl = norm3(f.lsite - tc.p1);
-    dr = norm3(f.rsite - tc.p1);
+  if (w.reached && w.frames >= C.delay_frames) {
+    w.j += 1;
+    w.reached = 0;
+    w.frames = 0;
   }
-  if (s.mode != A3_STANDING) {
+}
+// longest call the candidate bits cover: every advance needs max(delay_frames, 1) steps, the first may come at once
+constexpr int a3_max_steps_per_call(int delay_frames) { return (A3_MAX_CAND - 1) * (delay_frames > 1 ? delay_frames : 1); }
+inline int a3_num_cand_host(int n_steps, int delay_frames) {
+  const int d = delay_frames > 1 ? delay_frames : 1;
+  const int nc = 1 + (n_steps + d - 1) / d;
+  return nc < A3_MAX_CAND ? nc : A3_MAX_CAND;
+}
+
+// (env, t)-parallel again: goal steps (update_goal_steps :184-225), orientation and step terms, total, given the
+// state the machine was in after this step.  Writes goal[8] (obs rows 33..40), terms[2], terms[4], total.
+template <class Seq>
+OM_HD void a3_task_post(const A3TaskConst& C, const A3Rec& f, int mode, int t1, int t2, bool reached, const Seq& seq,
+                        float (&goal)[8], float& t2_orient, float& t4_step, float& total) {
+  A3TaskRegs s{};
+  s.t1 = t1; s.t2 = t2;
+  const A3Targets tc = a3_targets_load(s, seq);
+  const A3TargetTrig tg = a3_target_trig(tc);
+  const float dl = norm3(f.lsite - tc.p1), dr = norm3(f.rsite - tc.p1);
+  if (mode != A3_STANDING) {
     float R[9];
     tf3_quat2mat(f.root_q, R);
 #pragma unroll
@@ -337,7 +406,7 @@ OM_HD void a3_task_seq(const A3TaskConst& C, const A3Rec& f, A3TaskRegs& s, A3Ta
   const float inner = fmaf(tg.ch, f.root_q.w, tg.sh * f.root_q.z);
   t2_orient = 0.050f * expf(-10.f * (1.f - inner * inner));                            // rewards.py:121-126
   const float fd = fminf(dl, dr);                                                      // walking_task.py:56-72
-  const float hit = s.reached ? expf(-fd / 0.25f) : 0.f;
+  const float hit = reached ? expf(-fd / 0.25f) : 0.f;
   const float mx = (tc.p1.x + tc.p2.x) * 0.5f - f.root_p.x, my = (tc.p1.y + tc.p2.y) * 0.5f - f.root_p.y;
   const float progress = expf(-sqrtf(fmaf(mx, mx, my * my)) * 0.5f);
   t4_step = 0.450f * fmaf(0.8f, hit, 0.2f * progress);
@@ -366,8 +435,8 @@ OM_HD void a3_reset_qpos_qvel(const float* init_qpos, const float (&u)[A3_NU], f
   const float pitch = fmaf(u[51], 10.f, -5.f) * 0.017453292519943295f;
   const float yaw = fmaf(u[52], 2.f, -1.f) * 3.14159265358979323846f;
   float sj, cj, sk, ck;
-  sincosf(0.5f * pitch, &sj, &cj);
-  sincosf(0.5f * yaw, &sk, &ck);
+  om_sincos(0.5f * pitch, &sj, &cj);
+  om_sincos(0.5f * yaw, &sk, &ck);
   q[3] = cj * ck; q[4] = -(sj * sk); q[5] = sj * ck; q[6] = cj * sk;     // euler2quat(0, pitch, yaw)
 }
 
@@ -389,7 +458,7 @@ OM_HD void a3_task_reset(const A3TaskConst& C, const A3Feat& f, const float (&u)
   const float cyy = sqrtf(fmaf(R[0], R[0], R[3] * R[3]));
   const float yaw = cyy > A3_EPS4 ? atan2f(R[3], R[0]) : 0.f;
   float sy, cy;
-  sincosf(yaw, &sy, &cy);
+  om_sincos(yaw, &sy, &cy);
   const float mx = (f.lfoot_p.x + f.rfoot_p.x) * 0.5f, my = (f.lfoot_p.y + f.rfoot_p.y) * 0.5f;
   float x = 0.f, z = 0.f, y = half ? -0.15f : 0.15f;
   for (int i = 0; i < A3_MAX_STEPS; ++i) {

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) fk_generic_kernel(const ModelTab* __restr
           p = fma3(jaxis[jj], Q(qa) - tab.qpos0[qa], p);
         } else if (jt == OM_JNT_HINGE) {
           float s, c;
-          sincosf(0.5f * (Q(qa) - tab.qpos0[qa]), &s, &c);
+          om_sincos(0.5f * (Q(qa) - tab.qpos0[qa]), &s, &c);
           qt = qmul(qt, Q4{c, ax.x * s, ax.y * s, ax.z * s});
           p = janchor[jj] - qrot(qt, jp);
         } else if (jt == OM_JNT_BALL) {

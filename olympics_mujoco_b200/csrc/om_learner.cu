@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(1024) affine_scan_kernel(AffineIn in, int T, i
   __syncthreads();
   // carry-in of this segment = value at the first step of segment w+1 = fold of segments 31 .. w+1
   float X = 0.f;
-  for (int s = 31; s > w; --s) X = fmaf(sA[s][lane], X, sB[s][lane]);
+  for (int s = (int)blockDim.y - 1; s > w; --s) X = fmaf(sA[s][lane], X, sB[s][lane]);
 #pragma unroll
   for (int i = L - 1; i >= 0; --i) {
     X = fmaf(a[i], X, b[i]);
@@ -162,8 +162,12 @@ __global__ void __launch_bounds__(1024) affine_scan_kernel(AffineIn in, int T, i
 }
 
 static int launch_affine_scan(const AffineIn& in, int T, int n, int ld, float* o0, float* o1, cudaStream_t st) {
-  dim3 block(32, 32), grid(ceil_div(n, 32));
-  const int L = ceil_div(T, 32);
+  // L steps per warp, W = ceil(T / L) warps per CTA: short horizons take 8 steps per warp (T = 64: 8 warps, 7 segment
+  // folds and 4x more CTAs than 32 warps of 2 steps), long ones fill the 32 warps
+  const int l8 = ceil_div(T, 8) < 8 ? ceil_div(T, 8) : 8;
+  const int L = ceil_div(T, 32) > l8 ? ceil_div(T, 32) : l8;
+  const int Lp = L <= 1 ? 1 : L <= 2 ? 2 : L <= 4 ? 4 : L <= 8 ? 8 : L <= 16 ? 16 : 32;
+  dim3 block(32, ceil_div(T, Lp)), grid(ceil_div(n, 32));
   if (L <= 1) affine_scan_kernel<1><<<grid, block, 0, st>>>(in, T, n, ld, o0, o1);
   else if (L <= 2) affine_scan_kernel<2><<<grid, block, 0, st>>>(in, T, n, ld, o0, o1);
   else if (L <= 4) affine_scan_kernel<4><<<grid, block, 0, st>>>(in, T, n, ld, o0, o1);

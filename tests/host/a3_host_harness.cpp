@@ -13,7 +13,7 @@ using namespace om;
 static A3TaskConst make_const(const float* lut6, int period, int delay, double radius, double gh, double dz, float fmax) {
   A3TaskConst C;
   C.period = period; C.delay_frames = delay; C.fmax = fmax; C.vmax = 0.2f;
-  C.target_radius = radius; C.goal_height_ref = gh; C.deadzone = dz; C.lut = lut6;
+  C.target_radius = radius; C.near_d2 = a3_near_d2(radius); C.goal_height_ref = gh; C.deadzone = dz; C.lut = lut6;
   return C;
 }
 
@@ -40,7 +40,7 @@ extern "C" void host_a3_rollout(const float* lut6, int period, int delay, double
     const float* c = contact + t * 4;
     a3_obs_robot(q, qd, o);
     A3Sink<NullFkSink> S{};
-    om_fk_stick_figure_a3(q, qd, S);
+    om_fk_pos_stick_figure_a3(q, qd, S);
     const int fl = (int)c[3];
     a3_task_step(C, a3_task_in(S.f), s, tc, SeqHost{seq}, c[0], c[1], c[2], (fl & 1) != 0, (fl & 2) != 0, o, tr, total, d);
     std::memcpy(obs + t * A3_NOBS, o, sizeof o);
@@ -52,7 +52,7 @@ extern "C" void host_a3_rollout(const float* lut6, int period, int delay, double
   std::memcpy(ints, out, sizeof out);
 }
 
-// the time-parallel split (a3_feat_kernel + a3_seq_kernel of csrc/om_a3.cu) for one env
+// the time-parallel split (a3_feat_kernel with its state-machine tail + a3_post_kernel of csrc/om_a3.cu) for one env
 extern "C" void host_a3_rollout_split(const float* lut6, int period, int delay, double radius, double gh, double dz, float fmax,
                                       const float* qpos, const float* qvel, const float* contact, int T, int* ints, float* seq,
                                       float* obs, float* terms, float* reward, unsigned char* done) {
@@ -66,7 +66,7 @@ extern "C" void host_a3_rollout_split(const float* lut6, int period, int delay, 
     const float* c = contact + t * 4;
     a3_obs_robot(q, qd, o);
     A3Sink<NullFkSink> S{};
-    om_fk_stick_figure_a3(q, qd, S);
+    om_fk_pos_stick_figure_a3(q, qd, S);
     const int fl = (int)c[3];
     const int phase = (ints[0] + t + 1) % period;
     const A3Rec r = a3_task_pre(C, a3_task_in(S.f), phase, ints[4], c[0], c[1], c[2], (fl & 1) != 0, (fl & 2) != 0, tr, o[31],
@@ -76,18 +76,33 @@ extern "C" void host_a3_rollout_split(const float* lut6, int period, int delay, 
     terms[t * 6 + 0] = tr[0]; terms[t * 6 + 1] = tr[1]; terms[t * 6 + 3] = tr[3]; terms[t * 6 + 5] = tr[5];
     done[t] = d ? 1 : 0;
   }
-  A3TaskRegs s{ints[0], ints[1], ints[2], ints[3], ints[4], ints[5], ints[6]};
-  A3Targets tc = a3_targets_load(s, SeqHost{seq});
-  A3TargetTrig tg = a3_target_trig(tc);
-  for (int t = 0; t < T; ++t) {                                   // pass 2: sequential
-    float goal[8], t2, t4, total;
-    a3_task_seq(C, a3_rec_load(rec + (size_t)t * A3_NREC, 1), s, tc, tg, SeqHost{seq}, goal, t2, t4, total);
-    std::memcpy(obs + t * A3_NOBS + 33, goal, sizeof goal);
-    terms[t * 6 + 2] = t2; terms[t * 6 + 4] = t4;
-    reward[t] = total;
+  // passes B + C: integer walk over the candidate bits, then the state-dependent outputs.  Calls longer than the bits
+  // cover are cut into sub-calls exactly like om_a3_task_step does.
+  uint8_t* near = new uint8_t[T];
+  int st[7] = {ints[0], ints[1], ints[2], ints[3], ints[4], ints[5], ints[6]};
+  for (int c0 = 0; c0 < T; c0 += a3_max_steps_per_call(delay)) {
+    const int len = T - c0 < a3_max_steps_per_call(delay) ? T - c0 : a3_max_steps_per_call(delay);
+    const int nc = a3_num_cand_host(len, delay);
+    const int t1_0 = st[1], t2_0 = st[2], sl = st[5];
+    for (int t = c0; t < c0 + len; ++t) {
+      const A3Rec r = a3_rec_load(rec + (size_t)t * A3_NREC, 1);
+      near[t] = (uint8_t)a3_near_bits(C, r.lsite, r.rsite, nc, t1_0, t2_0, sl, SeqHost{seq});
+    }
+    A3Walk w{0, st[3], st[6]};
+    for (int t = c0; t < c0 + len; ++t) {
+      a3_walk_step(C, near[t], w);
+      float goal[8], t2, t4, total;
+      a3_task_post(C, a3_rec_load(rec + (size_t)t * A3_NREC, 1), st[4], a3_cand(w.j, t1_0, t2_0, sl),
+                   a3_cand(w.j + 1, t1_0, t2_0, sl), w.reached != 0, SeqHost{seq}, goal, t2, t4, total);
+      std::memcpy(obs + t * A3_NOBS + 33, goal, sizeof goal);
+      terms[t * 6 + 2] = t2; terms[t * 6 + 4] = t4;
+      reward[t] = total;
+    }
+    st[1] = a3_cand(w.j, t1_0, t2_0, sl); st[2] = a3_cand(w.j + 1, t1_0, t2_0, sl); st[3] = w.frames; st[6] = w.reached;
   }
+  delete[] near;
   delete[] rec;
-  int out[7] = {(s.phase + T) % period, s.t1, s.t2, s.frames, s.mode, s.seq_len, s.reached};
+  int out[7] = {(ints[0] + T) % period, st[1], st[2], st[3], st[4], st[5], st[6]};
   std::memcpy(ints, out, sizeof out);
 }
 
@@ -99,7 +114,7 @@ extern "C" void host_a3_reset(const float* lut6, int period, int delay, double r
   a3_reset_uniforms(seed, env, rc, u);
   a3_reset_qpos_qvel(init_qpos, u, q, qd);
   A3Sink<NullFkSink> S{};
-  om_fk_stick_figure_a3(q, qd, S);
+  om_fk_pos_stick_figure_a3(q, qd, S);
   A3TaskRegs s;
   a3_task_reset(C, S.f, u, step_h, s, SeqHostOut{seq});
   std::memcpy(qpos, q, sizeof q);

@@ -5,12 +5,15 @@
 #include <cstring>
 #define OM_HD inline
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+#include "om_math.cuh"
 #include "fk_unitree_h1.cuh"
 #include "fk_stick_figure_a3.cuh"
+#include "fk_pos_stick_figure_a3.cuh"
 
 struct HostSink {
   static constexpr bool want_site_xmat = true;
   float *xp, *xq, *sp, *sm, *cv, *cm;
+  float* vp = nullptr;
   void xpos(int b, float x, float y, float z) { xp[b*3]=x; xp[b*3+1]=y; xp[b*3+2]=z; }
   void xquat(int b, float w, float x, float y, float z) { xq[b*4]=w; xq[b*4+1]=x; xq[b*4+2]=y; xq[b*4+3]=z; }
   void site_xpos(int s, float x, float y, float z) { sp[s*3]=x; sp[s*3+1]=y; sp[s*3+2]=z; }
@@ -19,7 +22,8 @@ struct HostSink {
   void cvel(int b, float wx, float wy, float wz, float vx, float vy, float vz) {
     float v[6] = {wx,wy,wz,vx,vy,vz}; std::memcpy(cv + 6*b, v, sizeof v); }
   void com(float x, float y, float z) { cm[0]=x; cm[1]=y; cm[2]=z; }
-  void vel_p(int, float, float, float, float, float, float) {}
+  void vel_p(int b, float wx, float wy, float wz, float vx, float vy, float vz) {
+    if (vp) { float v[6] = {wx,wy,wz,vx,vy,vz}; std::memcpy(vp + 6*b, v, sizeof v); } }
 };
 
 extern "C" void host_fk_h1(const float* q, const float* qd, int n, float* xp, float* xq, float* sp, float* sm,
@@ -38,5 +42,23 @@ extern "C" void host_fk_a3(const float* q, const float* qd, int n, float* xp, fl
     std::memcpy(qq, q + 25*e, sizeof qq); std::memcpy(dd, qd + 24*e, sizeof dd);
     HostSink S{xp + 51*e, xq + 68*e, sp + 6*e, sm + 18*e, cv + 102*e, cm + 3*e};
     om_fk_stick_figure_a3(qq, dd, S);
+  }
+}
+
+// the matrix-chain variant (codegen.generate_fk_pos) next to the quaternion one: xpos, site_xpos, root xquat and the
+// spatial velocities about the root origin of both
+extern "C" void host_fk_a3_pos(const float* q, const float* qd, int n, float* xp, float* xq, float* sp, float* vp,
+                               float* vp_quat) {
+  static float dump[17 * 9 + 64];
+  for (int e = 0; e < n; ++e) {
+    float qq[25], dd[24];
+    std::memcpy(qq, q + 25*e, sizeof qq); std::memcpy(dd, qd + 24*e, sizeof dd);
+    HostSink S{xp + 51*e, xq + 68*e, sp + 6*e, dump, dump, dump};
+    S.vp = vp + 102*e;
+    om_fk_pos_stick_figure_a3(qq, dd, S);
+    static float xp2[51], xq2[68], sp2[6], sm2[18], cv2[102], cm2[3];
+    HostSink S2{xp2, xq2, sp2, sm2, cv2, cm2};
+    S2.vp = vp_quat + 102*e;
+    om_fk_stick_figure_a3(qq, dd, S2);
   }
 }

@@ -48,7 +48,9 @@ def test_generated_fk_matches_oracle_on_host(h1_model, a3_model, h1_states):
     d = Path(tempfile.mkdtemp())
     (d / "fk_unitree_h1.cuh").write_text(codegen.generate_fk(h1_model, "om_fk_unitree_h1"))
     (d / "fk_stick_figure_a3.cuh").write_text(codegen.generate_fk(a3_model, "om_fk_stick_figure_a3"))
-    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-I", str(d), str(ROOT / "tests/host/fk_host_harness.cpp"),
+    (d / "fk_pos_stick_figure_a3.cuh").write_text(codegen.generate_fk_pos(a3_model, "om_fk_pos_stick_figure_a3"))
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-I", str(d), "-I", str(ROOT / "olympics_mujoco_b200/csrc"),
+                           str(ROOT / "tests/host/fk_host_harness.cpp"),
                            "-o", str(d / "h.so")])
     lib = ctypes.CDLL(str(d / "h.so"))
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
@@ -64,6 +66,18 @@ def test_generated_fk_matches_oracle_on_host(h1_model, a3_model, h1_states):
         assert_close(xp, ref["xpos"], "xpos"); assert_close(xq, ref["xquat"], "xquat")
         assert_close(sp, ref["site_xpos"], "site_xpos"); assert_close(sm, ref["site_xmat"], "site_xmat")
         assert_close(cv, ref["cvel"], "cvel"); assert_close(cm, ref["subtree_com"][:, 1], "com")
+    # matrix-chain variant used by the A3 task kernels: positions vs the oracle, point velocities vs the quaternion chain
+    q, v = a3_random_states(a3_model, 256, seed=9)
+    n = q.shape[0]
+    q32, v32 = np.ascontiguousarray(q, np.float32), np.ascontiguousarray(v, np.float32)
+    xp = np.zeros((n, 17, 3), np.float32); xq = np.zeros((n, 17, 4), np.float32); sp = np.zeros((n, 2, 3), np.float32)
+    vp = np.zeros((n, 17, 6), np.float32); vq = np.zeros((n, 17, 6), np.float32)
+    lib.host_fk_a3_pos(P(q32), P(v32), n, P(xp), P(xq), P(sp), P(vp), P(vq))
+    ref = K.forward(a3_model, q32.astype(np.float64), v32.astype(np.float64))
+    assert_close(xp[:, 1:], ref["xpos"][:, 1:], "xpos (matrix chain)"); assert_close(sp, ref["site_xpos"], "site_xpos (matrix chain)")
+    assert_close(xq[:, 1], ref["xquat"][:, 1], "root xquat (matrix chain)")
+    assert np.abs(vq[:, 1:]).max() > 1.0
+    assert_close(vp[:, 1:], vq[:, 1:], "vel_p (matrix chain vs quaternion chain)", rtol=1e-5, atol=2e-5)
 
 
 def test_mjcf_compiler_on_a_small_model(tmp_path):

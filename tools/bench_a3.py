@@ -51,9 +51,9 @@ def measure(envs=16384, horizon=64, steps=20, warmup=3, per_step=False):
                 task.step(qpos[t], qvel[t], con[t], out={k: v[t] for k, v in out.items()})
         else:
             task.step(qpos, qvel, con, out=out)
-        if ev:
-            ev[1].record()
         ret, adv = Kn.ppo_returns(out["reward"], values[:-1], 0.99, path_end=out["done"], v_next=values[1:])
+        if ev:
+            ev[1].record()            # the 490 B/env-step of SURVEY 8(d) include the returns pass, so it is timed with the task
         mom.zero_()
         Kn.moments_scalar(adv, out=mom)
         stats = Kn.adv_stats(mom, unbiased=True, eps=1e-5)
@@ -78,7 +78,7 @@ def measure(envs=16384, horizon=64, steps=20, warmup=3, per_step=False):
     return {"workload": f"A3 PPO walk rollout {n} envs x {T} steps (configs[2])", "per_step_launches": args.per_step,
             "value": n * T / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "task_kernel_ms": kms,
             "gpu_launches": Kn.launch_count(),
-            "roofline": {"bound": "hbm", "kernel": "a3_feat_kernel + a3_seq_kernel (time-parallel replay)", "achieved": achieved, "peak": peaks["hbm_gbs"],
+            "roofline": {"bound": "hbm", "kernel": "a3_feat_kernel (+ state-machine tail) + a3_post_kernel + affine_scan/ppo_returns", "achieved": achieved, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "bytes_per_env_step": BYTES_PER_ENV_STEP}}
 
 
