@@ -407,7 +407,7 @@ def generate_fk_pos(model, fn_name):
                 if jt == JNT_SLIDE:
                     p = g.vfma(axis_w, dq, p)
                 elif jt == JNT_HINGE:
-                    g.emit(f"float s{j}, c{j}; om::om_sincos({dq}, &s{j}, &c{j});")
+                    g.emit(f"float s{j}, c{j}; om::om_sincos_hinge({dq}, &s{j}, &c{j});")
                     sj, cj = E(n=f"s{j}"), E(n=f"c{j}")
                     # Rodrigues: c I + (1 - c) a a^T + s [a]x, constants folded (axis-aligned: four live entries)
                     omc = None

@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(BLOCK) a3_task_kernel(A3Args a) {
 //                   cp.async.bulk -- the CTAs fall into lockstep, load, compute and store phases stop overlapping
 //                   across CTAs, 112 us instead of 90 us.)
 //   a3_walk_kernel  one thread per env: the integer state machine over the T bytes (a few instructions per step),
-//                   leaves a one-byte (advances, reached) code per env-step and the final task state;
+//                   leaves a one-byte (advances, reached) code per env-step and the final task state.  (Measured and
+//                   rejected: running it in the last-finishing feat CTA of each env block -- 147 us instead of 142.)
 //   a3_post_kernel  one thread per (env, t) again: goal steps, orientation and step terms, total.
 struct A3Scratch {
   float* feat;          // [T][16][ld]
@@ -120,12 +121,9 @@ struct A3Scratch {
   int32_t* start;       // [2][ld]   t1, t2 at the start of the call
 };
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 5) a3_feat_kernel(A3Args a, A3Scratch w, int ncand) {
-  const int env = blockIdx.x * BLOCK + threadIdx.x;
-  const int t = blockIdx.y;
-  if (env >= a.n) return;
-  const size_t ld = a.ld, e = env;
+// one env-step of the (env, t)-parallel pass
+__device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w, int ncand, int t, size_t e) {
+  const size_t ld = a.ld;
   float q[A3_NQ], qd[A3_NV], con[4];
   const float* qp = a.qpos + (size_t)t * A3_NQ * ld + e;
   const float* vp = a.qvel + (size_t)t * A3_NV * ld + e;
@@ -166,13 +164,13 @@ __global__ void __launch_bounds__(BLOCK, 5) a3_feat_kernel(A3Args a, A3Scratch w
   if (a.o.done) a.o.done[(size_t)t * ld + e] = done ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(64) a3_walk_kernel(A3Args a, A3Scratch w) {
-  const int env = blockIdx.x * 64 + threadIdx.x;
-  if (env >= a.n) return;
-  const size_t ld = a.ld, e = env;
+// The integer state machine over the T candidate bytes of one env (a few instructions per step); leaves a one-byte
+// (advances, reached) code per env-step and the final task state.
+template <int CH>
+__device__ __forceinline__ void a3_walk(const A3Args& a, const A3Scratch& w, size_t e) {
+  const size_t ld = a.ld;
   const int t1_0 = a.ints[A3I_T1 * ld + e], t2_0 = a.ints[A3I_T2 * ld + e], seq_len = a.ints[A3I_SEQLEN * ld + e];
   A3Walk s{0, a.ints[A3I_FRAMES * ld + e], a.ints[A3I_REACHED * ld + e]};
-  constexpr int CH = 64;
   for (int t0 = 0; t0 < a.T; t0 += CH) {
     uint8_t nb[CH];
 #pragma unroll
@@ -189,6 +187,17 @@ __global__ void __launch_bounds__(64) a3_walk_kernel(A3Args a, A3Scratch w) {
   a.ints[A3I_T1 * ld + e] = a3_cand(s.j, t1_0, t2_0, seq_len);
   a.ints[A3I_T2 * ld + e] = a3_cand(s.j + 1, t1_0, t2_0, seq_len);
   a.ints[A3I_FRAMES * ld + e] = s.frames; a.ints[A3I_REACHED * ld + e] = s.reached;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 5) a3_feat_kernel(A3Args a, A3Scratch w, int ncand) {
+  const int env = blockIdx.x * BLOCK + threadIdx.x;
+  if (env < a.n) a3_feat_item(a, w, ncand, blockIdx.y, env);
+}
+
+__global__ void __launch_bounds__(64) a3_walk_kernel(A3Args a, A3Scratch w) {
+  const int env = blockIdx.x * 64 + threadIdx.x;
+  if (env < a.n) a3_walk<64>(a, w, env);
 }
 
 template <int BLOCK>
@@ -342,10 +351,12 @@ extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const flo
   if (split) {
     constexpr int FB = 128;
     const int env_blocks = ceil_div(n, FB);
+    // layout: [records][start ints][candidate bytes][state codes]
     const size_t feat_b = (size_t)n_steps * A3_NREC * (size_t)ld * sizeof(float);
     const size_t int_b = (size_t)2 * ld * sizeof(int32_t);
     const size_t byte_b = (size_t)n_steps * (size_t)ld;
     const size_t need = feat_b + int_b + 2 * byte_b;
+    OM_REQUIRE(env_blocks <= 65535, "om_a3_task_step: at most %d envs per multi-step call", 65535 * FB);
     if (task->scratch_bytes < need) {
       if (task->scratch) OM_CUDA_OK(cudaFree(task->scratch));  // synchronises: no earlier call still reads it
       task->scratch = nullptr;
@@ -368,8 +379,8 @@ extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const flo
       if (sub.o.done) sub.o.done += (size_t)c0 * ld;
       sub.T = len;
       OM_REQUIRE(len <= 65535, "om_a3_task_step: at most 65535 steps per call");
-      if (getenv("OM_A3_FB64")) a3_feat_kernel<64><<<dim3(ceil_div(n, 64), len), 64, 0, st>>>(sub, w, a3_num_cand_host(len, task->C.delay_frames));
-      else a3_feat_kernel<FB><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, a3_num_cand_host(len, task->C.delay_frames));
+      const int ncand = a3_num_cand_host(len, task->C.delay_frames);
+      a3_feat_kernel<FB><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
       OM_LAUNCHED();
       a3_walk_kernel<<<ceil_div(n, 64), 64, 0, st>>>(sub, w);
       OM_LAUNCHED();
