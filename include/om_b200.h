@@ -247,6 +247,31 @@ void om_disc_destroy(OmDisc* d);
  * means z = mu); reward [ld]; d_out [ld] (may be NULL) = the raw discriminator logit. */
 int om_disc_reward(const OmDisc* d, const float* s, const float* mean, const float* std, const float* eps, int n, int ld,
                    float* reward, float* d_out, void* stream);
+/* The same forward pass for the discriminator FIT (N2; GAIL._fit_discriminator gail_TRPO.py:167-220 calls the network
+ * on [policy batch; expert batch]): any of reward / d_out (logit) / kl_out may be NULL.  kl_out [ld] (VAIL only) =
+ * VDBLoss.kl_divergence (imitation_lib/utils/math.py:83-86): 0.5 * sum_j (mu_j^2 + exp(logvar_j) - logvar_j - 1). */
+int om_disc_forward(const OmDisc* d, const float* s, const float* mean, const float* std, const float* eps, int n, int ld,
+                    float* reward, float* d_out, float* kl_out, void* stream);
+/* Loss statistics of one discriminator fit batch: logit [n_plcy + n_demo] (policy samples first, like the reference's
+ * np.concatenate([plcy, demo])), target [n] or NULL (= 0 for policy, 1 for expert samples), kl [n] or NULL.
+ * ACCUMULATES into sums[9] (float64, zero it first; all-reduce it across ranks before reading):
+ *   0 sum bce = max(x,0) - x t + log(1 + exp(-|x|))      GailDiscriminatorLoss.forward math.py:22-31
+ *   1 sum logit_bernoulli_entropy = (1 - sigmoid x) x - logsigmoid x                      math.py:33-38
+ *   2 sum kl                                                  3 policy samples with sigmoid < 0.5
+ *   4 expert samples with sigmoid > 0.5                       5 / 6 sum sigmoid over policy / expert samples
+ *   7 / 8 number of policy / expert samples
+ * dlogit [n] (may be NULL): d/dx of  sum(bce) - entcoeff * sum(entropy)  per sample, i.e. (sigmoid x - t) +
+ * entcoeff x sigmoid x (1 - sigmoid x); divide by the global n for the gradient of the mean loss. */
+int om_disc_loss_stats(const float* logit, const float* target, const float* kl, int n_plcy, int n_demo, float entcoeff,
+                       double* sums, float* dlogit, void* stream);
+/* Expert minibatch (N2; minibatch_generator(batch, demonstrations["states"], ["next_states"]) at
+ * gail_TRPO.py:175-206 = the first `batch` rows of a fresh random permutation): sample b of draw `draw` reads dataset row
+ * pi_e(b mod n_src) with e = b / n_src, pi_e a keyed 4-round Feistel permutation of [0, n_src) with cycle walking,
+ * round keys = Philox(seed; e, draw, stream 48) -- every epoch e is a sample WITHOUT replacement (contract:
+ * oracle/learner.py expert_indices).  src [D][ld_src] holds n_src + next rows (next_states = rows shifted by one,
+ * trajectory.py:170-171); out / out_next [D][ld_out] (out_next and idx_out may be NULL). */
+int om_expert_minibatch(const float* src, int n_src, int ld_src, int D, uint64_t seed, uint32_t draw, int batch, float* out,
+                        float* out_next, int32_t* idx_out, int ld_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K5: returns / advantages over a time-major rollout buffer [T][ld].

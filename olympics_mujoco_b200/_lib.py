@@ -107,6 +107,9 @@ PROTOTYPES = {
     "om_disc_create": (_I, [C.POINTER(OmDiscDesc), C.POINTER(_P)]),
     "om_disc_destroy": (None, [_P]),
     "om_disc_reward": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "om_disc_forward": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "om_disc_loss_stats": (_I, [_P, _P, _P, _I, _I, _F, _P, _P, _P]),
+    "om_expert_minibatch": (_I, [_P, _I, _I, _I, _U64, _U32, _I, _P, _P, _P, _I, _P]),
     "om_action_affine": (_I, [C.POINTER(OmActionSpec), _P, _I, _I, _P, _P]),
     "om_pd_torque": (_I, [C.POINTER(OmPdSpec), _P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "om_mirror": (_I, [C.POINTER(OmMirrorSpec), _P, _I, _I, _P, _P]),

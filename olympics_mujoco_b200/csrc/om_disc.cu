@@ -126,7 +126,7 @@ struct DiscArgs {
   const float* image;           // pre-split weight chunks
   const float* params;          // b1[n1], b2[n2], (VAIL: bmu|blv [2z]), head weights wd[z or n2], bd
   const float* s; const float* mean; const float* stdv; const float* eps;
-  float* reward; float* d_out;
+  float* reward; float* d_out; float* kl_out;
   int n, ld;
 };
 
@@ -159,7 +159,7 @@ constexpr int NSB = 4;
 constexpr int STAGE_B2_BYTES = 256 * KB * 4 * 2;       // 32 KB
 constexpr int COPY_PIECE = 8192;                       // several bulk copies in flight per sub-chunk
 
-template <int N1, int N2, bool VAIL>
+template <int N1, int N2, bool VAIL, bool KL>
 __global__ void __launch_bounds__(192, 1) disc_reward_kernel(DiscArgs a) {
   constexpr int ACT = VAIL ? ACT_RELU : ACT_TANH;
   constexpr int NB1 = N1 / 256;                 // 256-wide column blocks of layer 1
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(192, 1) disc_reward_kernel(DiscArgs a) {
           put_chunk(h);
         }
       }
-      float dval = 0.f;
+      float dval = 0.f, klv = 0.f;
       if (VAIL) {
 #pragma unroll 1
         for (int c = 0; c < N2 / KC; ++c) {                              // [mu; logvar] layer
@@ -339,8 +339,9 @@ __global__ void __launch_bounds__(192, 1) disc_reward_kernel(DiscArgs a) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int j = c * 32 + i;
-            const float zz = fmaf(expf(0.5f * (lv[i] + b3[Z + j])), e[i], mu[i] + b3[j]);
-            dval = fmaf(wd[j], zz, dval);
+            const float m = mu[i] + b3[j], l = lv[i] + b3[Z + j], sd = expf(0.5f * l);
+            dval = fmaf(wd[j], fmaf(sd, e[i], m), dval);
+            if (KL) klv += fmaf(m, m, fmaf(sd, sd, -l)) - 1.f;       // VDBLoss.kl_divergence, math.py:83-86
           }
         };
         float e0[32], e1[32];
@@ -365,8 +366,9 @@ __global__ void __launch_bounds__(192, 1) disc_reward_kernel(DiscArgs a) {
       if (live) {
         // 1 - sigmoid(d) evaluated as sigmoid(-d): no cancellation for large d (gail_TRPO.py:326-327)
         const float one_minus_p = 1.f / (1.f + expf(dval));
-        a.reward[env] = -logf(one_minus_p + 1e-8f);
+        if (a.reward) a.reward[env] = -logf(one_minus_p + 1e-8f);
         if (a.d_out) a.d_out[env] = dval;
+        if (VAIL && KL) a.kl_out[env] = 0.5f * klv;
       }
       // the next tile's layer-1 MMA overwrites the columns read above: put_chunk orders these loads before its arrive
     }
@@ -405,6 +407,7 @@ __device__ __forceinline__ void store_a16(uint8_t* stage, int row, const float (
   }
 }
 
+template <bool KL>
 __global__ void __launch_bounds__(192, 2) disc_vail2_kernel(DiscArgs a) {
   constexpr int Z = 128, DA = 0, DB = 128;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -540,7 +543,7 @@ __global__ void __launch_bounds__(192, 2) disc_vail2_kernel(DiscArgs a) {
           put(h);
         }
       }
-      float dval = 0.f;
+      float dval = 0.f, klv = 0.f;
 #pragma unroll 1
       for (int hb = 0; hb < 2; ++hb) {
 #pragma unroll 1
@@ -569,16 +572,19 @@ __global__ void __launch_bounds__(192, 2) disc_vail2_kernel(DiscArgs a) {
           for (int i = 0; i < 32; ++i) {
             const int j = 64 * hb + 32 * q + i;
             const float e = q == 0 ? e0[i] : e1[i];
-            const float zz = fmaf(expf(0.5f * (lv[i] + b3[128 * hb + 64 + 32 * q + i])), e, mu[i] + b3[128 * hb + 32 * q + i]);
-            dval = fmaf(wd[j], zz, dval);
+            const float m = mu[i] + b3[128 * hb + 32 * q + i], l = lv[i] + b3[128 * hb + 64 + 32 * q + i];
+            const float sd = expf(0.5f * l);
+            dval = fmaf(wd[j], fmaf(sd, e, m), dval);
+            if (KL) klv += fmaf(m, m, fmaf(sd, sd, -l)) - 1.f;       // VDBLoss.kl_divergence, math.py:83-86
           }
         }
       }
       dval += bd;
       if (live) {
         const float one_minus_p = 1.f / (1.f + expf(dval));
-        a.reward[env] = -logf(one_minus_p + 1e-8f);
+        if (a.reward) a.reward[env] = -logf(one_minus_p + 1e-8f);
         if (a.d_out) a.d_out[env] = dval;
+        if (KL) a.kl_out[env] = 0.5f * klv;
       }
     }
   }
@@ -722,17 +728,24 @@ extern "C" void om_disc_destroy(OmDisc* h) {
 
 extern "C" int om_disc_reward(const OmDisc* h, const float* s, const float* mean, const float* stdv, const float* eps, int n,
                               int ld, float* reward, float* d_out, void* stream) {
-  OM_REQUIRE(h, "om_disc_reward: null discriminator");
-  OM_REQUIRE(n >= 0 && ld >= n, "om_disc_reward: need 0 <= n <= ld");
+  OM_REQUIRE(reward || n == 0, "om_disc_reward: null argument");
+  return om_disc_forward(h, s, mean, stdv, eps, n, ld, reward, d_out, nullptr, stream);
+}
+
+extern "C" int om_disc_forward(const OmDisc* h, const float* s, const float* mean, const float* stdv, const float* eps, int n,
+                               int ld, float* reward, float* d_out, float* kl_out, void* stream) {
+  OM_REQUIRE(h, "om_disc_forward: null discriminator");
+  OM_REQUIRE(n >= 0 && ld >= n, "om_disc_forward: need 0 <= n <= ld");
   if (n == 0) return 0;
-  OM_REQUIRE(s && mean && stdv && reward, "om_disc_reward: null argument");
+  OM_REQUIRE(s && mean && stdv && (reward || d_out || kl_out), "om_disc_forward: null argument");
+  OM_REQUIRE(!kl_out || h->sh.kind == 0, "om_disc_forward: the KL term exists for the variational (VAIL) network only");
   int dev = 0, sms = 0;
   OM_CUDA_OK(cudaGetDevice(&dev));
   OM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int ntiles = ceil_div(n, TILE);
   const int grid = ntiles < sms ? ntiles : sms;                  // persistent: one CTA per SM
   const size_t smem = 2 * STAGE_A_BYTES + NSB * STAGE_B2_BYTES + (DISC_MAX_PAR + 4) * sizeof(float) + 12 * 8 + 16;
-  DiscArgs a{h->sh, h->image, h->params, s, mean, stdv, eps, reward, d_out, n, ld};
+  DiscArgs a{h->sh, h->image, h->params, s, mean, stdv, eps, reward, d_out, kl_out, n, ld};
   cudaStream_t st = (cudaStream_t)stream;
   int two = h->sh.kind == 0;                                       // VAIL: two CTAs per SM
   if (const char* f = getenv("OM_DISC_VAIL2")) two = two && atoi(f) != 0;        // tuning / test hook
@@ -742,17 +755,19 @@ extern "C" int om_disc_reward(const OmDisc* h, const float* s, const float* mean
     DiscArgs a2 = a;
     a2.image = h->image2;
     a2.params = h->params2;
-    OM_CUDA_OK(cudaFuncSetAttribute(disc_vail2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    disc_vail2_kernel<<<grid2, 192, smem2, st>>>(a2);
+    auto kern = kl_out ? disc_vail2_kernel<true> : disc_vail2_kernel<false>;
+    OM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    kern<<<grid2, 192, smem2, st>>>(a2);
     OM_LAUNCHED();
     return 0;
   }
   if (h->sh.kind == 0) {
-    OM_CUDA_OK(cudaFuncSetAttribute(disc_reward_kernel<256, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    disc_reward_kernel<256, 128, true><<<grid, 192, smem, st>>>(a);
+    auto kern = kl_out ? disc_reward_kernel<256, 128, true, true> : disc_reward_kernel<256, 128, true, false>;
+    OM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 192, smem, st>>>(a);
   } else {
-    OM_CUDA_OK(cudaFuncSetAttribute(disc_reward_kernel<512, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    disc_reward_kernel<512, 256, false><<<grid, 192, smem, st>>>(a);
+    OM_CUDA_OK(cudaFuncSetAttribute(disc_reward_kernel<512, 256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    disc_reward_kernel<512, 256, false, false><<<grid, 192, smem, st>>>(a);
   }
   OM_LAUNCHED();
   return 0;

@@ -256,6 +256,77 @@ __global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------- N2: discriminator-fit statistics, expert minibatch
+// One pass over the logits of [policy batch; expert batch]: per-sample fp32 terms, float64 sums (warp shuffle, one
+// atomicAdd per warp and statistic).
+__global__ void __launch_bounds__(256) disc_loss_kernel(const float* __restrict__ logit, const float* __restrict__ target,
+                                                        const float* __restrict__ kl, int n_plcy, int n, float entcoeff,
+                                                        double* __restrict__ sums, float* __restrict__ dlogit) {
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float x = logit[i];
+    const bool demo = i >= n_plcy;
+    const float t = target ? target[i] : (demo ? 1.f : 0.f);
+    const float sp = log1pf(expf(-fabsf(x)));                    // log(1 + exp(-|x|))
+    const float bce = fmaxf(x, 0.f) - x * t + sp;
+    const float sig = x >= 0.f ? 1.f / (1.f + expf(-x)) : expf(x) / (1.f + expf(x));
+    const float logsig = fminf(x, 0.f) - sp;                     // logsigmoid(x)
+    const float ent = (1.f - sig) * x - logsig;
+    acc[0] += bce; acc[1] += ent;
+    if (kl) acc[2] += kl[i];
+    if (demo) { acc[4] += x > 0.f ? 1.0 : 0.0; acc[6] += sig; }
+    else { acc[3] += x < 0.f ? 1.0 : 0.0; acc[5] += sig; }
+    if (dlogit) dlogit[i] = (sig - t) + entcoeff * x * sig * (1.f - sig);
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&sums[k], v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&sums[7], (double)n_plcy); atomicAdd(&sums[8], (double)(n - n_plcy)); }
+}
+
+// keyed permutation of [0, n): balanced Feistel network on 2 * half bits + cycle walking (contract: oracle/learner.py)
+OM_HD uint32_t om_mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+  return x;
+}
+OM_HD uint32_t om_feistel_perm(uint32_t v, uint32_t n, int half, U4 key) {
+  const uint32_t mask = (1u << half) - 1u;
+  do {
+    uint32_t l = v >> half, r = v & mask;
+    const uint32_t k[4] = {key.x, key.y, key.z, key.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t f = om_mix32(r ^ k[i]) & mask;
+      const uint32_t nl = r;
+      r = l ^ f;
+      l = nl;
+    }
+    v = (l << half) | r;
+  } while (v >= n);
+  return v;
+}
+constexpr uint32_t EXPERT_STREAM = 48;      // oracle/philox.py STREAM_EXPERT
+
+__global__ void __launch_bounds__(128) expert_minibatch_kernel(const float* __restrict__ src, int n_src, int ld_src, int D,
+                                                               uint64_t seed, uint32_t draw, int half, int batch,
+                                                               float* __restrict__ out, float* __restrict__ out_next,
+                                                               int32_t* __restrict__ idx_out, int ld_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const uint32_t epoch = (uint32_t)(b / n_src), i = (uint32_t)(b % n_src);
+  const uint32_t idx = om_feistel_perm(i, (uint32_t)n_src, half, om_draw(seed, epoch, draw, EXPERT_STREAM));
+  if (idx_out) idx_out[b] = (int32_t)idx;
+  for (int c = 0; c < D; ++c) {
+    const float* row = src + (size_t)c * ld_src + idx;
+    out[(size_t)c * ld_out + b] = row[0];
+    if (out_next) out_next[(size_t)c * ld_out + b] = row[1];
+  }
+}
+
 }  // namespace om
 
 using namespace om;
@@ -330,6 +401,34 @@ extern "C" int om_normalize(const float* x, const double* stats, int rows, int n
   if (gx > 592) gx = 592;
   dim3 grid(gx, rows);
   normalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, stats, rows, n, ld, y);
+  OM_LAUNCHED();
+  return 0;
+}
+
+extern "C" int om_disc_loss_stats(const float* logit, const float* target, const float* kl, int n_plcy, int n_demo,
+                                  float entcoeff, double* sums, float* dlogit, void* stream) {
+  OM_REQUIRE(n_plcy >= 0 && n_demo >= 0, "om_disc_loss_stats: bad sizes");
+  const int n = n_plcy + n_demo;
+  if (n == 0) return 0;
+  OM_REQUIRE(logit && sums, "om_disc_loss_stats: null argument");
+  const int grid = ceil_div(n, 256) < 148 * 8 ? ceil_div(n, 256) : 148 * 8;
+  disc_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logit, target, kl, n_plcy, n, entcoeff, sums, dlogit);
+  OM_LAUNCHED();
+  return 0;
+}
+
+extern "C" int om_expert_minibatch(const float* src, int n_src, int ld_src, int D, uint64_t seed, uint32_t draw, int batch,
+                                   float* out, float* out_next, int32_t* idx_out, int ld_out, void* stream) {
+  OM_REQUIRE(batch >= 0 && D >= 1 && n_src >= 1 && ld_out >= batch, "om_expert_minibatch: bad sizes");
+  OM_REQUIRE(ld_src >= n_src + (out_next ? 1 : 0), "om_expert_minibatch: the dataset needs n_src%s rows (ld_src = %d)",
+             out_next ? " + 1" : "", ld_src);
+  if (batch == 0) return 0;
+  OM_REQUIRE(src && out, "om_expert_minibatch: null argument");
+  int bits = 2;
+  while (bits < 32 && (1ull << bits) < (unsigned long long)n_src) ++bits;
+  const int half = (bits + 1) / 2;
+  expert_minibatch_kernel<<<ceil_div(batch, 128), 128, 0, (cudaStream_t)stream>>>(src, n_src, ld_src, D, seed, draw, half, batch,
+                                                                                 out, out_next, idx_out, ld_out);
   OM_LAUNCHED();
   return 0;
 }

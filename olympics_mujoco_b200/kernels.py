@@ -409,6 +409,48 @@ class Discriminator:
         return (reward, d) if want_d else reward
 
 
+    def forward(self, s, mean, std, eps=None, want_reward=False, want_kl=None):
+        """The forward pass of the discriminator FIT (gail_TRPO.py:167-220): -> dict(logit [n], kl [n] (VAIL),
+        reward [n] if asked).  Same kernel as ``reward``; the KL term is VDBLoss.kl_divergence per sample."""
+        n = s.shape[-1]
+        assert s.shape == (self.n_in, n) and (eps is None or eps.shape == (self.z, n))
+        want_kl = (self.kind == 0) if want_kl is None else want_kl
+        out = dict(logit=torch.empty(n, device=s.device))
+        if want_kl:
+            out["kl"] = torch.empty(n, device=s.device)
+        if want_reward:
+            out["reward"] = torch.empty(n, device=s.device)
+        check(_lib.load().om_disc_forward(self.handle, _p(s, torch.float32), _p(mean, torch.float32), _p(std, torch.float32),
+                                          _p(eps, torch.float32), n, max(n, 1), _p(out.get("reward")), _p(out["logit"]),
+                                          _p(out.get("kl")), _stream()))
+        return out
+
+
+def disc_loss_stats(logit, n_plcy, target=None, kl=None, entcoeff=1e-3, want_grad=False, out=None):
+    """N2: statistics of one discriminator-fit batch (layout in include/om_b200.h) accumulated into a float64 [9]
+    buffer; with ``want_grad`` also d(sum bce - entcoeff * sum entropy)/d logit per sample."""
+    n = logit.numel()
+    if out is None:
+        out = torch.zeros(9, dtype=torch.float64, device=logit.device)
+    grad = torch.empty_like(logit) if want_grad else None
+    check(_lib.load().om_disc_loss_stats(_p(logit, torch.float32), _p(target, torch.float32), _p(kl, torch.float32),
+                                         int(n_plcy), int(n - n_plcy), float(entcoeff), _p(out, torch.float64), _p(grad),
+                                         _stream()))
+    return (out, grad) if want_grad else out
+
+
+def expert_minibatch(src, n_src, seed, draw, batch, want_next=False, want_idx=False):
+    """N2: src [D, >= n_src (+1)] device-resident expert states -> (states [D, batch], next_states | None, idx | None)
+    by the keyed-permutation contract of om_expert_minibatch."""
+    d, ld = src.shape
+    out = torch.empty((d, batch), device=src.device)
+    nxt = torch.empty((d, batch), device=src.device) if want_next else None
+    idx = torch.empty(batch, dtype=torch.int32, device=src.device) if want_idx else None
+    check(_lib.load().om_expert_minibatch(_p(src, torch.float32), int(n_src), ld, d, int(seed), int(draw), int(batch),
+                                          _p(out), _p(nxt), _p(idx, torch.int32), max(batch, 1), _stream()))
+    return out, nxt, idx
+
+
 # ------------------------------------------------------------------------------------------- learner side
 def ppo_returns(rewards, values, gamma, path_end=None, v_next=None, v_last=None):
     """K5a over a [T, n] buffer -> (returns, advantages)."""

@@ -8,6 +8,8 @@
   followed by ``(adv-mean)/(np.std(adv)+1e-8)``.  PARITY UNPINNED by the reference (third party).
 * ``Standardizer``         restates ``imitation_lib/utils/networks.py:48-81``.
 * ``RunningMeanStd`` / ``normalization_params``  restate ``rl/envs/normalize.py:190-208`` and ``:48``.
+* ``gail_disc_loss`` / ``vdb_kl`` / ``vdb_loss``  restate ``imitation_lib/utils/math.py:11-86`` (pinned: the reference
+  classes, ``tests/golden/disc_loss_ref.npz``); ``expert_indices`` is the expert-minibatch RNG contract.
 * ``vail_forward`` / ``gail_forward`` / ``discrim_reward``  restate ``networks.py:258-284``,
   ``:208-234`` and ``gail_TRPO.py:320-327`` for the shapes fixed by
   ``examples/imitation_learning/utils.py:151-179`` + ``confs.yaml:113-130``.
@@ -166,6 +168,81 @@ def discrim_reward(d):
     """gail_TRPO.py:326-327."""
     plcy_prob = 1.0 / (1.0 + np.exp(-np.asarray(d, np.float64)))
     return (-np.log(1.0 - plcy_prob + 1e-8)).astype(np.float32)
+
+
+# ------------------------------------------------------------------ discriminator fit (N2)
+def logit_bernoulli_entropy(x):
+    """imitation_lib/utils/math.py:33-38: (1 - sigmoid x) x - logsigmoid x (stable form)."""
+    x = np.asarray(x, np.float64)
+    sp = np.log1p(np.exp(-np.abs(x)))
+    sig = np.where(x >= 0, 1.0 / (1.0 + np.exp(-np.abs(x))), np.exp(-np.abs(x)) / (1.0 + np.exp(-np.abs(x))))
+    return (1.0 - sig) * x - (np.minimum(x, 0.0) - sp)
+
+
+def bce_with_logits(x, t):
+    """math.py:24-26: max(x, 0) - x t + log(1 + exp(-|x|)), per sample."""
+    x, t = np.asarray(x, np.float64), np.asarray(t, np.float64)
+    return np.maximum(x, 0.0) - x * t + np.log1p(np.exp(-np.abs(x)))
+
+
+def gail_disc_loss(logits, targets, entcoeff=1e-3):
+    """GailDiscriminatorLoss.forward (math.py:22-31) and its gradient with respect to the logits."""
+    x, t = np.asarray(logits, np.float64).ravel(), np.asarray(targets, np.float64).ravel()
+    loss = bce_with_logits(x, t).mean() - entcoeff * logit_bernoulli_entropy(x).mean()
+    sig = 1.0 / (1.0 + np.exp(-x))
+    grad = ((sig - t) + entcoeff * x * sig * (1.0 - sig)) / x.size
+    return loss, grad
+
+
+def vdb_kl(mu, logvar):
+    """VDBLoss.kl_divergence (math.py:83-86), per sample."""
+    mu, logvar = np.asarray(mu, np.float64), np.asarray(logvar, np.float64)
+    return 0.5 * np.sum(mu ** 2 + np.exp(logvar) - logvar - 1.0, axis=1)
+
+
+def vdb_loss(logits, kl, targets, beta, info_constraint, lr_beta):
+    """VDBLoss.forward + _update_beta (math.py:55-81, use_bernoulli_ent=False) -> (loss, new beta)."""
+    x, t = np.asarray(logits, np.float64).ravel(), np.asarray(targets, np.float64).ravel()
+    bottleneck = np.mean(kl) - info_constraint
+    loss = bce_with_logits(x, t).mean() + beta * bottleneck
+    return loss, max(0.0, beta + lr_beta * bottleneck)
+
+
+STREAM_EXPERT = 48
+
+
+def _mix32(x):
+    x = np.asarray(x, np.uint64) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16); x = (x * np.uint64(0x85EBCA6B)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(13); x = (x * np.uint64(0xC2B2AE35)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16)
+    return x
+
+
+def expert_indices(seed, draw, batch, n_src):
+    """The expert-minibatch contract (stands in for mushroom_rl's minibatch_generator, which shuffles with NumPy's
+    global stream: gail_TRPO.py:175-206 takes the first ``batch`` rows of a fresh permutation).  Sample b reads row
+    pi_e(b mod n_src), e = b // n_src; pi_e = 4-round balanced Feistel network over 2*half bits with cycle walking,
+    round function mix32(r ^ key_i) (murmur3 finaliser), round keys = the four Philox words of
+    (seed; counter = (e, draw, STREAM_EXPERT, 0))."""
+    from . import philox
+    bits = 2
+    while (1 << bits) < n_src:
+        bits += 1
+    half = (bits + 1) // 2
+    mask = np.uint64((1 << half) - 1)
+    b = np.arange(batch, dtype=np.int64)
+    epoch, v = b // n_src, (b % n_src).astype(np.uint64)
+    keys = [k.astype(np.uint64) for k in philox.draw(seed, epoch, draw, STREAM_EXPERT)]
+    todo = np.ones(batch, bool)
+    while todo.any():
+        l, r = v[todo] >> np.uint64(half), v[todo] & mask
+        for k in keys:
+            f = _mix32(r ^ k[todo]) & mask
+            l, r = r, l ^ f
+        v[todo] = (l << np.uint64(half)) | r
+        todo = v >= np.uint64(n_src)
+    return v.astype(np.int64)
 
 
 # ------------------------------------------------------------------ mirror symmetry (N3)

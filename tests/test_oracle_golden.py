@@ -150,3 +150,37 @@ def test_mirror_oracle_vs_reference_symmetric_env():
     np.testing.assert_allclose(L.mirror(g["obs"], g["mirrored_obs"], g["clock_inds"]), g["mirror_clock_obs"], rtol=0, atol=2e-7)
     m = L.symmetry_matrix(g["mirrored_obs"])
     assert np.array_equal(m @ m, np.eye(41))                       # the A3 observation mirror is an involution
+
+
+def test_disc_fit_loss_oracle_vs_reference_losses():
+    """N2: oracle/learner.py's GAIL / VDB loss restatements against the reference's own GailDiscriminatorLoss and
+    VDBLoss (imitation_lib/utils/math.py, executed by tools/gen_golden.py:gen_disc_loss): value, autograd gradient,
+    per-sample entropy and KL, three consecutive beta updates."""
+    from oracle import learner as L
+    z = np.load(GOLDEN / "disc_loss_ref.npz")
+    loss, grad = L.gail_disc_loss(z["logits"], z["t01"], float(z["entcoeff"]))
+    assert abs(loss - float(z["gail_loss01"])) < 1e-6
+    assert_close(grad, z["gail_grad01"].ravel(), "d loss / d logit vs torch autograd", rtol=1e-5, atol=1e-9)
+    assert abs(L.gail_disc_loss(z["logits"], z["tnoisy"], float(z["entcoeff"]))[0] - float(z["gail_loss_noisy"])) < 1e-6
+    assert_close(L.logit_bernoulli_entropy(z["logits"]), z["ent"], "bernoulli entropy", rtol=1e-5, atol=1e-6)
+    kl = L.vdb_kl(z["mu"], z["logvar"])
+    assert_close(kl, z["kl"], "kl", rtol=1e-5, atol=1e-5)
+    beta = float(z["betas"][0])
+    for i in range(3):
+        loss, beta = L.vdb_loss(z["logits"], kl, z["t01"], beta, float(z["info_constraint"]), float(z["lr_beta"]))
+        assert abs(loss - z["vdb_losses"][i]) < 1e-5 * abs(z["vdb_losses"][i])
+        assert abs(beta - z["betas"][i + 1]) < 1e-7
+
+
+def test_expert_index_contract_is_a_permutation_per_epoch():
+    """N2: every epoch of the expert-minibatch contract is a sample without replacement (what taking the first batch of
+    mushroom_rl's shuffled minibatch_generator gives), draws differ, and the stream is reproducible."""
+    from oracle import learner as L
+    for n_src in (1, 2, 5, 1999, 4096, 70001):
+        idx = L.expert_indices(3, 0, 2 * n_src + 3, n_src)
+        assert sorted(idx[:n_src]) == list(range(n_src)) and sorted(idx[n_src:2 * n_src]) == list(range(n_src))
+    a, b = L.expert_indices(3, 0, 512, 1999), L.expert_indices(3, 1, 512, 1999)
+    assert not np.array_equal(a, b) and np.array_equal(a, L.expert_indices(3, 0, 512, 1999))
+    # roughly uniform first positions over many draws
+    first = np.array([L.expert_indices(9, d, 1, 10)[0] for d in range(2000)])
+    assert np.bincount(first, minlength=10).min() > 120

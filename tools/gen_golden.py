@@ -451,6 +451,42 @@ def gen_mirror():
     print("mirror_ref: obs", obs.shape)
 
 
+# ---------------------------------------------------------------- 9. discriminator fit losses (imitation_lib/utils/math.py)
+def gen_disc_loss():
+    """GailDiscriminatorLoss / VDBLoss exactly as GAIL._fit_discriminator and _discriminator_logging use them
+    (gail_TRPO.py:167-258, vail_TRPO.py:23-33): [policy; expert] logits, 0/1 and noisy targets, beta update."""
+    import torch
+    stub("mushroom_rl"); stub("mushroom_rl.utils")
+    stub("mushroom_rl.utils.angles", euler_to_quat=None)
+    stub("mushroom_rl.utils.torch", to_float_tensor=lambda x, *a: torch.as_tensor(x, dtype=torch.float32))
+    m = load("ref_il_math", "imitation_lib/utils/math.py")
+    rng = np.random.default_rng(11)
+    B = 96
+    logits = np.concatenate([rng.normal(-1.0, 2.5, B), rng.normal(1.5, 2.5, B)]).astype(np.float32)[:, None]
+    logits[3, 0], logits[B + 5, 0] = -30.0, 40.0                       # saturated samples
+    t01 = np.concatenate([np.zeros((B, 1)), np.ones((B, 1))]).astype(np.float32)
+    tnoisy = np.concatenate([rng.uniform(0.01, 0.10, (B, 1)), rng.uniform(0.80, 0.99, (B, 1))]).astype(np.float32)
+    mu = rng.normal(0, 0.7, (2 * B, 128)).astype(np.float32)
+    logvar = rng.normal(-0.5, 0.8, (2 * B, 128)).astype(np.float32)
+    gl = m.GailDiscriminatorLoss(entcoeff=1e-3)
+    tl = torch.from_numpy(logits).requires_grad_(True)
+    loss01 = gl(tl, torch.from_numpy(t01))
+    loss01.backward()
+    grad01 = tl.grad.numpy().copy()
+    loss_noisy = gl(torch.from_numpy(logits), torch.from_numpy(tnoisy)).item()
+    ent = gl.logit_bernoulli_entropy(torch.from_numpy(logits)).numpy()
+    vl = m.VDBLoss(info_constraint=0.5, lr_beta=1e-5)
+    kl = vl.kl_divergence(torch.from_numpy(mu), torch.from_numpy(logvar)).numpy()
+    betas, vlosses = [vl._beta], []
+    for _ in range(3):                                                  # three fits: beta moves
+        vlosses.append(vl((torch.from_numpy(logits), torch.from_numpy(mu), torch.from_numpy(logvar)), torch.from_numpy(t01)).item())
+        betas.append(float(vl._beta))
+    np.savez(OUT / "disc_loss_ref.npz", logits=logits, t01=t01, tnoisy=tnoisy, mu=mu, logvar=logvar, gail_loss01=loss01.item(),
+             gail_grad01=grad01, gail_loss_noisy=loss_noisy, ent=ent, kl=kl, vdb_losses=np.array(vlosses), betas=np.array(betas),
+             info_constraint=0.5, lr_beta=1e-5, entcoeff=1e-3)
+    print("disc_loss_ref: gail", loss01.item(), loss_noisy, "vdb", vlosses, "beta", betas)
+
+
 if __name__ == "__main__":
     gen_trajectory()
     gen_phase_clock()
@@ -460,3 +496,4 @@ if __name__ == "__main__":
     gen_running_mean_std()
     gen_a3_task()
     gen_mirror()
+    gen_disc_loss()
