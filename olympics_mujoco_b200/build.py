@@ -45,6 +45,9 @@ def generate():
     _write_if_changed(GEN / "fk_stick_figure_a3.cuh", "#pragma once\n" + codegen.generate_fk(a3, "om_fk_stick_figure_a3"))
     _write_if_changed(GEN / "fk_pos_stick_figure_a3.cuh",
                       "#pragma once\n" + codegen.generate_fk_pos(a3, "om_fk_pos_stick_figure_a3"))
+    parts = codegen.split_parts(h1, 3)
+    _write_if_changed(GEN / "fk_unitree_h1_parts.cuh", "#pragma once\n" + "".join(
+        codegen.generate_fk(h1, f"om_fk_unitree_h1_part{k}", part=p) for k, p in enumerate(parts)))
     _write_if_changed(GEN / "tables_unitree_h1.h", "#pragma once\n" + codegen.generate_tables(h1, "om_tab_h1"))
     _write_if_changed(GEN / "tables_stick_figure_a3.h", "#pragma once\n" + codegen.generate_tables(a3, "om_tab_a3"))
     perm = [int(h1.jnt_qposadr[h1.jnt_names.index(j)]) for j in H1_SPEC_JOINTS]

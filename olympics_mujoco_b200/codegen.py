@@ -200,8 +200,40 @@ def model_fingerprint(model):
     return h.hexdigest()[:16]
 
 
-def generate_fk(model, fn_name):
+def split_parts(model, nparts):
+    """Partition the bodies of a single-tree model into ``nparts`` groups of whole subtrees hanging off the tree root
+    (UnitreeH1: right leg / left leg / torso with the arms), balanced by a rough cost (hinges weigh 3, fixed bodies
+    1); the root body and the world go to the lightest group.  -> list of body-id sets."""
+    nb = model.nbody
+    root = 1
+    kids = [i for i in range(2, nb) if int(model.body_parentid[i]) == root]
+    sub = {k: [k] for k in kids}
+    for i in range(2, nb):
+        j = i
+        while int(model.body_parentid[j]) != root:
+            j = int(model.body_parentid[j])
+            if j == 0:
+                raise ValueError("split_parts needs a single tree hanging off body 1")
+        if j != i:
+            sub[j].append(i)
+    cost = {k: sum(1 + 3 * int(model.body_jntnum[b]) for b in v) for k, v in sub.items()}
+    parts = [set() for _ in range(nparts)]
+    load = [0] * nparts
+    for k in sorted(kids, key=lambda k: -cost[k]):
+        p = load.index(min(load))
+        parts[p].update(sub[k])
+        load[p] += cost[k]
+    parts[load.index(min(load))].update({0, root})
+    return parts
+
+
+def generate_fk(model, fn_name, part=None):
     """Return CUDA source text of ``template<class Sink> __device__ void <fn_name>(q, qd, S)``.
+
+    With ``part=(own_bodies, Exchange)`` the function evaluates only the bodies in ``own_bodies`` and their ancestors,
+    emits sink calls for ``own_bodies`` alone, and obtains the tree's centre of mass from a second template argument:
+    ``X.com_exchange(sx, sy, sz, 1/M, cx, cy, cz)`` receives this part's sum of m * xipos and returns the normalised total
+    (the caller combines the parts -- through shared memory in h1_step_split_kernel).
 
     Sink interface (all indices are literals so unused outputs are dead-code eliminated):
       S.xpos(b,x,y,z)  S.xquat(b,w,x,y,z)  S.site_xpos(s,x,y,z)  S.site_xmat(s,m0..m8)
@@ -210,6 +242,12 @@ def generate_fk(model, fn_name):
     """
     g = Gen()
     nb = model.nbody
+    own = set(range(nb)) if part is None else set(part)
+    needed = set(own)
+    for b in list(own):
+        while b != 0:
+            b = int(model.body_parentid[b])
+            needed.add(b)
     c3 = lambda v: [E(x) for x in v]
     pos = {0: [ZERO, ZERO, ZERO]}
     quat = {0: [ONE, ZERO, ZERO, ZERO]}
@@ -225,10 +263,13 @@ def generate_fk(model, fn_name):
     def qd_in(k):
         return E(n=f"qd[{k}]")
 
-    g.emit("S.xpos(0, 0.0f, 0.0f, 0.0f);")
-    g.emit("S.xquat(0, 1.0f, 0.0f, 0.0f, 0.0f);")
-    g.emit("S.cvel(0, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f);")
+    if 0 in own:
+        g.emit("S.xpos(0, 0.0f, 0.0f, 0.0f);")
+        g.emit("S.xquat(0, 1.0f, 0.0f, 0.0f, 0.0f);")
+        g.emit("S.cvel(0, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f);")
     for i in range(1, nb):
+        if i not in needed:
+            continue
         g.emit(f"// ---- body {i}: {model.body_names[i]}")
         pid = int(model.body_parentid[i])
         rid = int(model.body_rootid[i])
@@ -282,6 +323,8 @@ def generate_fk(model, fn_name):
                     v_i = g.vfma(g.cross(axis_w, g.vsub(P[rid], anchor)), qd_in(da), v_i)
             qt = g.qnormalize(qt)
         pos[i], quat[i], wvel[i], lvel[i] = p, qt, w_i, v_i
+        if i not in own:
+            continue
         g.emit(f"S.xpos({i}, {p[0]}, {p[1]}, {p[2]});")
         g.emit(f"S.xquat({i}, {qt[0]}, {qt[1]}, {qt[2]}, {qt[3]});")
         # spatial velocity about the tree root's origin P (before the shift to the subtree COM): lets a
@@ -306,13 +349,27 @@ def generate_fk(model, fn_name):
 
     g.emit("// ---- subtree centre of mass of each kinematic tree, then shift velocities to it")
     dvec = {}
-    for rid, acc in com_acc.items():
-        com = g.vscale(acc, E(1.0 / com_mass[rid]))
-        if rid == 1:
-            g.emit(f"S.com({com[0]}, {com[1]}, {com[2]});")
-        dvec[rid] = g.vsub(com, P[rid])
+    if part is not None:
+        if set(P) != {1}:
+            raise ValueError("a split FK needs a single kinematic tree rooted at body 1")
+        com_total_mass = float(sum(float(model.body_mass[b]) for b in range(1, nb) if int(model.body_rootid[b]) == 1))
+        acc = com_acc.get(1, [ZERO, ZERO, ZERO])
+        g.emit("float com_x, com_y, com_z;")
+        g.emit(f"X.com_exchange({acc[0]}, {acc[1]}, {acc[2]}, {_f(1.0 / com_total_mass)}, com_x, com_y, com_z);")
+        com = [E(n="com_x"), E(n="com_y"), E(n="com_z")]
+        if 1 in own:
+            g.emit("S.com(com_x, com_y, com_z);")
+        dvec[1] = g.vsub(com, P[1])
+    else:
+        for rid, acc in com_acc.items():
+            com = g.vscale(acc, E(1.0 / com_mass[rid]))
+            if rid == 1:
+                g.emit(f"S.com({com[0]}, {com[1]}, {com[2]});")
+            dvec[rid] = g.vsub(com, P[rid])
     # bodies without joints share their parent's cvel: emit each distinct value once
     for i in range(1, nb):
+        if i not in own:
+            continue
         rid = int(model.body_rootid[i])
         lin = g.vadd(lvel[i], g.cross(wvel[i], dvec[rid])) if rid in dvec else lvel[i]
         w = wvel[i]
@@ -323,8 +380,10 @@ def generate_fk(model, fn_name):
     head = (f"// GENERATED by olympics_mujoco_b200/codegen.py from model '{model.name}' "
             f"(fingerprint {model_fingerprint(model)}) -- do not edit.\n"
             f"// nbody={model.nbody} njnt={model.njnt} nq={model.nq} nv={model.nv} nsite={model.nsite}\n"
-            f"template <class Sink>\nOM_HD void {fn_name}(const float (&q)[{model.nq}], "
-            f"const float (&qd)[{model.nv}], Sink& S) {{\n")
+            + (f"// part: bodies {sorted(own)}\n" if part is not None else "") +
+            (f"template <class Sink, class Exchange>\n" if part is not None else f"template <class Sink>\n") +
+            f"OM_HD void {fn_name}(const float (&q)[{model.nq}], const float (&qd)[{model.nv}], Sink& S"
+            + (", Exchange& X" if part is not None else "") + ") {\n")
     return head + body + "\n}\n"
 
 

@@ -9,6 +9,7 @@ static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 #include "fk_unitree_h1.cuh"
 #include "fk_stick_figure_a3.cuh"
 #include "fk_pos_stick_figure_a3.cuh"
+#include "fk_unitree_h1_parts.cuh"
 
 struct HostSink {
   static constexpr bool want_site_xmat = true;
@@ -60,5 +61,31 @@ extern "C" void host_fk_a3_pos(const float* q, const float* qd, int n, float* xp
     HostSink S2{xp2, xq2, sp2, sm2, cv2, cm2};
     S2.vp = vp_quat + 102*e;
     om_fk_stick_figure_a3(qq, dd, S2);
+  }
+}
+
+// the three part functions of the split H1 kernel (csrc/om_fk.cu: h1_step_split_kernel): pass 1 collects the partial
+// centre-of-mass sums, pass 2 hands every part the combined centre of mass, like the shared-memory exchange does
+struct HostExchange {
+  float (*sum)[3]; int part; bool second;
+  void com_exchange(float sx, float sy, float sz, float inv_mass, float& cx, float& cy, float& cz) const {
+    if (!second) { sum[part][0] = sx; sum[part][1] = sy; sum[part][2] = sz; cx = cy = cz = 0.f; return; }
+    cx = ((sum[0][0] + sum[1][0]) + sum[2][0]) * inv_mass;
+    cy = ((sum[0][1] + sum[1][1]) + sum[2][1]) * inv_mass;
+    cz = ((sum[0][2] + sum[1][2]) + sum[2][2]) * inv_mass;
+  }
+};
+extern "C" void host_fk_h1_parts(const float* q, const float* qd, int n, float* xp, float* xq, float* sp, float* sm,
+                                 float* cv, float* cm) {
+  for (int e = 0; e < n; ++e) {
+    float qq[17], dd[17], sum[3][3];
+    std::memcpy(qq, q + 17*e, sizeof qq); std::memcpy(dd, qd + 17*e, sizeof dd);
+    HostSink S{xp + 63*e, xq + 84*e, sp + 3*e, sm + 9*e, cv + 126*e, cm + 3*e};
+    for (int pass = 0; pass < 2; ++pass) {
+      HostExchange X0{sum, 0, pass == 1}, X1{sum, 1, pass == 1}, X2{sum, 2, pass == 1};
+      om_fk_unitree_h1_part0(qq, dd, S, X0);
+      om_fk_unitree_h1_part1(qq, dd, S, X1);
+      om_fk_unitree_h1_part2(qq, dd, S, X2);
+    }
   }
 }

@@ -22,8 +22,10 @@ def _spec(model, **kw):
     return Kn.make_h1_spec(OH.perm(model), OH.x_vel_idx(model), **kw)
 
 
-def test_h1_step_parity(h1_model, h1_states):
+@pytest.mark.parametrize("threads_per_env", ["3", "1"])     # h1_step_split_kernel (default) / h1_step_kernel
+def test_h1_step_parity(h1_model, h1_states, threads_per_env, monkeypatch):
     import torch
+    monkeypatch.setenv("OM_H1_SPLIT", "1" if threads_per_env == "3" else "0")
     from olympics_mujoco_b200 import kernels as Kn
     from oracle import h1 as OH
     qpos, qvel = h1_states
