@@ -273,6 +273,7 @@ def run_ours(args):
             try:
                 import bench_h1_step
                 other["h1_single_step_1048576"] = bench_h1_step.measure(steps=10, warmup=3)
+                other["h1_single_step_131072"] = bench_h1_step.measure(envs=131072, steps=10, warmup=3)
             except Exception as e:
                 other["h1_step_error"] = repr(e)
             try:
