@@ -206,3 +206,37 @@ def test_stick_figure_a3_env_api(a3_model):
             assert_close(rewards["step_reward"][e].cpu().numpy(), rterms[4], "step_reward")
     single = StickFigureA3(seed=3)
     assert single.reset().shape == (41,)
+
+
+@pytest.mark.parametrize("delay,radius", [(0, 5.0), (1, 5.0), (2, 0.9), (5, 0.6), (30, 5.0), (7, 0.35)])
+def test_a3_replay_state_machine_stress(a3_model, delay, radius, monkeypatch):
+    """The candidate-bit state machine of the time-parallel replay (feat -> walk -> post kernels) against the fused
+    one-thread-per-env kernel under short delays and radii that make "target near" frequent or permanent: the target
+    advances every few steps, the candidate chain clamps at the last target, calls split into sub-calls.  Integer state
+    and flags identical, floats to 1e-6."""
+    import torch
+    from olympics_mujoco_b200 import kernels as Kn
+    from olympics_mujoco_b200.tasks.phase_clock import phase_clock_lut
+    from oracle import a3 as OA
+    gold = A.golden()
+    n, T = gold["step_done"].shape
+    dm = Kn.DeviceModel(a3_model)
+    qpos, qvel, con = _soa_t(gold["step_qpos"]), _soa_t(gold["step_qvel"]), _soa_t(A.contact4(gold["step_contact"]))
+    res = {}
+    for split in ("0", "1"):
+        monkeypatch.setenv("OM_A3_SPLIT", split)
+        task = Kn.A3Task(dm, n, phase_clock_lut(), OA.init_qpos(), delay_frames=delay, target_radius=radius)
+        ints = gold["reset_ints"].T.astype(np.int32).copy()
+        ints[:, 3:] = np.array([[3, 4, 5, 1, 1, 20, 1]], np.int32).T         # some envs start mid-plan with frames pending
+        task.ints.copy_(torch.as_tensor(ints))
+        task.sequence.copy_(torch.as_tensor(gold["reset_sequence"].reshape(n, 80).T.astype(np.float32)))
+        out = task.step(qpos, qvel, con)
+        torch.cuda.synchronize()
+        res[split] = ({k: v.cpu().numpy() for k, v in out.items()}, task.ints.cpu().numpy())
+    (a, ia), (b, ib) = res["0"], res["1"]
+    np.testing.assert_array_equal(ia, ib)
+    np.testing.assert_array_equal(a["done"], b["done"])
+    assert (ia[1] != gold["reset_ints"].T[1]).any()                            # targets did advance
+    assert_close(b["obs"], a["obs"], "obs", rtol=1e-6, atol=1e-6)
+    assert_close(b["terms"], a["terms"], "terms", rtol=1e-6, atol=1e-6)
+    assert_close(b["reward"], a["reward"], "reward", rtol=1e-6, atol=1e-6)

@@ -232,6 +232,28 @@ def test_a3_task_device_functions_on_host(a3_model):
         assert np.array_equal(ints3, trace[-1]) and np.array_equal(done3, done)
         assert_close(obs3, obs, "split obs", rtol=1e-6, atol=1e-6); assert_close(terms3, terms, "split terms", rtol=1e-6, atol=1e-6)
         assert_close(reward3, reward, "split reward", rtol=1e-6, atol=1e-6)
+    # candidate-bit state machine under stress: short delays and a radius that makes "near" frequent or permanent, so the
+    # target advances every few steps, the candidate chain clamps at the last target and calls split into sub-calls
+    e = 0
+    qpos, qvel = np.ascontiguousarray(gold["step_qpos"][e]), np.ascontiguousarray(gold["step_qvel"][e])
+    con = np.ascontiguousarray(A.contact4(gold["step_contact"][e]))
+    seq = np.ascontiguousarray(gold["reset_sequence"][e].reshape(-1), np.float32)
+    advanced = 0
+    for delay, radius in ((0, 5.0), (1, 5.0), (2, 0.9), (5, 0.6), (30, 5.0), (7, 0.35)):
+        c2 = (P(lut), OA.PERIOD, delay, ctypes.c_double(radius), ctypes.c_double(0.80), ctypes.c_double(0.01),
+              ctypes.c_float(a3_model.total_mass * 9.8 * 0.5))
+        for start in (gold["reset_ints"][e].astype(np.int32), np.array([3, 4, 5, 1, 1, 20, 1], np.int32)):
+            ia, ib = start.copy(), start.copy()
+            oa, ta = np.zeros((T, 41), np.float32), np.zeros((T, 6), np.float32)
+            ra, da = np.zeros(T, np.float32), np.zeros(T, np.uint8)
+            ob, tb, rb, db = np.zeros_like(oa), np.zeros_like(ta), np.zeros_like(ra), np.zeros_like(da)
+            lib.host_a3_rollout(*c2, P(qpos), P(qvel), P(con), T, P(ia), P(seq), P(oa), P(ta), P(ra), P(da))
+            lib.host_a3_rollout_split(*c2, P(qpos), P(qvel), P(con), T, P(ib), P(seq), P(ob), P(tb), P(rb), P(db))
+            assert np.array_equal(ia, ib), (delay, radius, ia, ib)
+            assert np.array_equal(da, db)
+            assert_close(ob, oa, "stress obs", rtol=1e-6, atol=1e-6); assert_close(rb, ra, "stress reward", rtol=1e-6, atol=1e-6)
+            advanced += int(ia[1] != start[1])
+    assert advanced >= 6
 
 
 def test_perfect_dataset_conversion_matches_reference_restatement():
