@@ -329,6 +329,19 @@ int om_pd_torque(const OmPdSpec* spec, const float* target, const float* vel_tar
  * sin(arcsin(y_j) + pi) = -y_j (wrappers.py:67-69).  x, y are [numel][ld]; y must not alias x. */
 typedef struct OmMirrorSpec { int numel; int32_t index[64]; float sign[64]; uint8_t negate[64]; } OmMirrorSpec;
 int om_mirror(const OmMirrorSpec* spec, const float* x, int n, int ld, float* y, void* stream);
+/* The minibatch losses of PPO.update_policy (rl/algos/ppo.py:231-282) from the quantities the actor / critic produced,
+ * one pass: logp, old_logp, adv, mask (NULL = 1), values / returns (NULL: no value loss) are [n]; entropy [nu][ld] (NULL:
+ * none) = pdf.entropy(); act = policy(obs), act_mirror = policy(mirror(obs)) [nu][ld] (NULL: no mirror loss), with
+ * action_mirror = the signed permutation of mirror_action (NULL: act_mirror is already mirrored).
+ * ACCUMULATES into sums[7] (float64; zero it, all-reduce it across ranks, then):
+ *   actor_loss = -sums[0]/n          entropy_penalty = -sums[1]/(n nu)     critic_loss = vf_coeff sums[2]/n
+ *   approx_kl = sums[3]/n            mirror_loss = sums[4]/(n nu)           clip_fraction = sums[5]/n        n = sums[6]
+ * dlogp / dvalues [n] (may be NULL) = d actor_loss / d log_probs and d critic_loss / d values with the LOCAL n as the
+ * mean's denominator (rescale by n_local / n_global under data parallelism). */
+int om_ppo_loss_stats(const float* logp, const float* old_logp, const float* adv, const float* mask, const float* values,
+                      const float* returns, const float* entropy, const float* act, const float* act_mirror,
+                      const OmMirrorSpec* action_mirror, int nu, int n, int ld, float clip, float vf_coeff, double* sums,
+                      float* dlogp, float* dvalues, void* stream);
 
 #ifdef __cplusplus
 }

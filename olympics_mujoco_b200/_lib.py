@@ -113,6 +113,7 @@ PROTOTYPES = {
     "om_action_affine": (_I, [C.POINTER(OmActionSpec), _P, _I, _I, _P, _P]),
     "om_pd_torque": (_I, [C.POINTER(OmPdSpec), _P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "om_mirror": (_I, [C.POINTER(OmMirrorSpec), _P, _I, _I, _P, _P]),
+    "om_ppo_loss_stats": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(OmMirrorSpec), _I, _I, _I, _F, _F, _P, _P, _P, _P]),
     "om_h1_play_trajectory": (_I, [_P, C.POINTER(OmH1Spec), _P, _U64, _U32, _I, _I,
                                    C.POINTER(OmPlayState), C.POINTER(OmPlayOut), _I, _I, _P]),
     "om_ppo_returns": (_I, [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P]),

@@ -288,6 +288,63 @@ __global__ void __launch_bounds__(256) disc_loss_kernel(const float* __restrict_
   if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&sums[7], (double)n_plcy); atomicAdd(&sums[8], (double)(n - n_plcy)); }
 }
 
+// ---------------------------------------------------------------- N3: PPO minibatch losses
+//   PPO.update_policy  rl/algos/ppo.py:231-282: clipped surrogate, entropy penalty, value loss, approximate KL, clip
+//   fraction and the mirror-symmetry loss (policy(obs) against mirror_action(policy(mirror(obs))), wrappers.py:54-55,
+//   the signed permutation applied on the fly) in ONE pass over the minibatch: per-sample fp32 terms, float64 sums.
+struct PpoLossArgs {
+  const float* logp; const float* old_logp; const float* adv; const float* mask; const float* values; const float* returns;
+  const float* entropy;       // [nu][ld] or null
+  const float* act;           // [nu][ld] policy(obs) or null
+  const float* act_mirror;    // [nu][ld] policy(mirror(obs)) BEFORE mirror_action
+  OmMirrorSpec mir;           // action mirror (identity when numel == 0)
+  int nu, n, ld;
+  float clip, vf_coeff;
+  double* sums; float* dlogp; float* dvalues;
+};
+__global__ void __launch_bounds__(256) ppo_loss_kernel(PpoLossArgs a) {
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  const float inv_n = 1.0f / (float)a.n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+    const float lr = a.logp[i] - a.old_logp[i];
+    const float ratio = expf(lr);
+    const float m = a.mask ? a.mask[i] : 1.f;
+    const float A = a.adv[i] * m;
+    const float lo = 1.f - a.clip, hi = 1.f + a.clip;
+    const float cpi = ratio * A, clp = fminf(fmaxf(ratio, lo), hi) * A;
+    acc[0] += fminf(cpi, clp);
+    acc[3] += (ratio - 1.f) - lr;
+    acc[5] += fabsf(ratio - 1.f) > a.clip ? 1.0 : 0.0;
+    if (a.values) {
+      const float d = a.returns[i] - a.values[i];
+      acc[2] += d * d;
+      if (a.dvalues) a.dvalues[i] = -2.f * a.vf_coeff * d * inv_n;
+    }
+    if (a.dlogp) {
+      const bool inside = ratio >= lo && ratio <= hi;                    // clamp passes the gradient on [lo, hi]
+      a.dlogp[i] = (inside || cpi < clp) ? -cpi * inv_n : 0.f;
+    }
+    if (a.entropy)
+      for (int k = 0; k < a.nu; ++k) acc[1] += a.entropy[(size_t)k * a.ld + i] * m;
+    if (a.act && a.act_mirror)
+      for (int k = 0; k < a.nu; ++k) {
+        // mirror_action: y[index[k]] = sign[k] * x[k]
+        const int j = a.mir.numel ? a.mir.index[k] : k;
+        const float s = a.mir.numel ? a.mir.sign[k] : 1.f;
+        const float d = a.act[(size_t)j * a.ld + i] - s * a.act_mirror[(size_t)k * a.ld + i];
+        acc[4] += d * d;
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&a.sums[k], v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.sums[6], (double)a.n);
+}
+
 // keyed permutation of [0, n): balanced Feistel network on 2 * half bits + cycle walking (contract: oracle/learner.py)
 OM_HD uint32_t om_mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
@@ -429,6 +486,30 @@ extern "C" int om_expert_minibatch(const float* src, int n_src, int ld_src, int 
   const int half = (bits + 1) / 2;
   expert_minibatch_kernel<<<ceil_div(batch, 128), 128, 0, (cudaStream_t)stream>>>(src, n_src, ld_src, D, seed, draw, half, batch,
                                                                                  out, out_next, idx_out, ld_out);
+  OM_LAUNCHED();
+  return 0;
+}
+
+extern "C" int om_ppo_loss_stats(const float* logp, const float* old_logp, const float* adv, const float* mask,
+                                 const float* values, const float* returns, const float* entropy, const float* act,
+                                 const float* act_mirror, const OmMirrorSpec* action_mirror, int nu, int n, int ld, float clip,
+                                 float vf_coeff, double* sums, float* dlogp, float* dvalues, void* stream) {
+  OM_REQUIRE(n >= 0 && ld >= n && nu >= 0 && nu <= 64, "om_ppo_loss_stats: bad sizes (n=%d ld=%d nu=%d)", n, ld, nu);
+  if (n == 0) return 0;
+  OM_REQUIRE(logp && old_logp && adv && sums, "om_ppo_loss_stats: null argument");
+  OM_REQUIRE(!values == !returns, "om_ppo_loss_stats: values and returns come together");
+  OM_REQUIRE(!act == !act_mirror, "om_ppo_loss_stats: act and act_mirror come together");
+  PpoLossArgs a{logp, old_logp, adv, mask, values, returns, entropy, act, act_mirror, {}, nu, n, ld, clip, vf_coeff, sums, dlogp,
+                dvalues};
+  a.mir.numel = 0;
+  if (action_mirror && act) {
+    OM_REQUIRE(action_mirror->numel == nu, "om_ppo_loss_stats: the action mirror has %d entries, nu = %d", action_mirror->numel, nu);
+    for (int k = 0; k < nu; ++k)
+      OM_REQUIRE(action_mirror->index[k] >= 0 && action_mirror->index[k] < nu, "om_ppo_loss_stats: mirror index[%d] out of range", k);
+    a.mir = *action_mirror;
+  }
+  const int grid = ceil_div(n, 256) < 148 * 8 ? ceil_div(n, 256) : 148 * 8;
+  ppo_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   OM_LAUNCHED();
   return 0;
 }

@@ -364,6 +364,24 @@ def mirror(spec, x, out=None):
     return out
 
 
+def ppo_loss_stats(logp, old_logp, adv, clip, mask=None, values=None, returns=None, vf_coeff=0.5, entropy=None, act=None,
+                   act_mirror=None, action_mirror=None, want_grad=True, out=None):
+    """N3: PPO.update_policy's losses in one pass (layout in include/om_b200.h) -> (sums float64 [7], dlogp, dvalues)."""
+    n = logp.numel()
+    nu = 0 if act is None and entropy is None else (act if act is not None else entropy).shape[0]
+    if out is None:
+        out = torch.zeros(7, dtype=torch.float64, device=logp.device)
+    dlogp = torch.empty(n, device=logp.device) if want_grad else None
+    dvalues = torch.empty(n, device=logp.device) if (want_grad and values is not None) else None
+    check(_lib.load().om_ppo_loss_stats(_p(logp, torch.float32), _p(old_logp, torch.float32), _p(adv, torch.float32),
+                                        _p(mask, torch.float32), _p(values, torch.float32), _p(returns, torch.float32),
+                                        _p(entropy, torch.float32), _p(act, torch.float32), _p(act_mirror, torch.float32),
+                                        C.byref(action_mirror) if action_mirror is not None else None, int(nu), n, max(n, 1),
+                                        float(clip), float(vf_coeff), _p(out, torch.float64), _p(dlogp), _p(dvalues),
+                                        _stream()))
+    return out, dlogp, dvalues
+
+
 # ------------------------------------------------------------------------------------------- discriminator (K4)
 class Discriminator:
     """OmDisc handle.  ``params``: dict of float32 arrays in torch.nn.Linear layout ([out, in] weights):

@@ -154,3 +154,20 @@ def _fit_batch(self, plcy_state, expert, loss, eps=None, noisy_targets=False):
 
 
 DiscriminatorReward.fit_batch = _fit_batch
+
+
+def ppo_update_losses(logp, old_logp, adv, mask, values, returns, clip=0.2, vf_coeff=0.5, entropy=None, act=None,
+                      act_mirror=None, action_mirror=None):
+    """``PPO.update_policy`` (``rl/algos/ppo.py:231-282``) over ALL ranks' minibatch shards -> (dict of the six values it
+    returns, d actor_loss / d log_probs, d critic_loss / d values), the gradients scaled for the global mean."""
+    sums, dlogp, dvalues = Kn.ppo_loss_stats(logp, old_logp, adv, clip, mask=mask, values=values, returns=returns,
+                                             vf_coeff=vf_coeff, entropy=entropy, act=act, act_mirror=act_mirror,
+                                             action_mirror=action_mirror)
+    n_local = logp.numel()
+    s = D.all_reduce_moments(sums).tolist()
+    n = s[6]
+    nu = act.shape[0] if act is not None else (entropy.shape[0] if entropy is not None else 1)
+    out = dict(actor_loss=-s[0] / n, entropy_penalty=-s[1] / (n * nu), critic_loss=vf_coeff * s[2] / n, approx_kl=s[3] / n,
+               mirror_loss=s[4] / (n * nu), clip_fraction=s[5] / n)
+    scale = n_local / n
+    return out, dlogp * scale, (dvalues * scale if dvalues is not None else None)

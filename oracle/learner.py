@@ -10,6 +10,8 @@
 * ``RunningMeanStd`` / ``normalization_params``  restate ``rl/envs/normalize.py:190-208`` and ``:48``.
 * ``gail_disc_loss`` / ``vdb_kl`` / ``vdb_loss``  restate ``imitation_lib/utils/math.py:11-86`` (pinned: the reference
   classes, ``tests/golden/disc_loss_ref.npz``); ``expert_indices`` is the expert-minibatch RNG contract.
+* ``ppo_losses``           restates ``PPO.update_policy`` (``rl/algos/ppo.py:231-282``); pinned: the reference method run
+  with stand-in actor / critic modules (``tests/golden/ppo_loss_ref.npz``).
 * ``vail_forward`` / ``gail_forward`` / ``discrim_reward``  restate ``networks.py:258-284``,
   ``:208-234`` and ``gail_TRPO.py:320-327`` for the shapes fixed by
   ``examples/imitation_learning/utils.py:151-179`` + ``confs.yaml:113-130``.
@@ -243,6 +245,30 @@ def expert_indices(seed, draw, batch, n_src):
         v[todo] = (l << np.uint64(half)) | r
         todo = v >= np.uint64(n_src)
     return v.astype(np.int64)
+
+
+# ------------------------------------------------------------------ PPO minibatch losses (N3)
+def ppo_losses(logp, old_logp, adv, mask, values, returns, entropy, det_actions, mirror_raw, mirrored_acts, clip, vf_coeff):
+    """PPO.update_policy (rl/algos/ppo.py:231-282) from the quantities the networks produced: clipped surrogate, entropy
+    penalty, value loss, approximate KL, mirror-symmetry loss (mirror_action applied to policy(mirror(obs)),
+    wrappers.py:54-55) and clip fraction; plus d(actor_loss)/d(log_probs) and d(critic_loss)/d(values)."""
+    f = lambda a: np.asarray(a, np.float64)
+    logp, old_logp, adv, mask, values, returns = (f(a).reshape(-1) for a in (logp, old_logp, adv, mask, values, returns))
+    n = logp.size
+    ratio = np.exp(logp - old_logp)
+    A = adv * mask
+    cpi, clp = ratio * A, np.clip(ratio, 1 - clip, 1 + clip) * A
+    out = dict(actor_loss=-np.minimum(cpi, clp).mean(),
+               entropy_penalty=-(f(entropy) * mask[:, None]).mean(),
+               critic_loss=vf_coeff * np.mean((returns - values) ** 2),
+               approx_kl=np.mean((ratio - 1) - (logp - old_logp)),
+               clip_fraction=np.mean(np.abs(ratio - 1) > clip))
+    mirrored = mirror(f(mirror_raw), mirrored_acts)
+    out["mirror_loss"] = np.mean((f(det_actions) - mirrored) ** 2)
+    inside = (ratio >= 1 - clip) & (ratio <= 1 + clip)
+    out["dlogp"] = -np.where(inside | (cpi < clp), ratio * A, 0.0) / n
+    out["dvalues"] = vf_coeff * 2.0 * (values - returns) / n
+    return out
 
 
 # ------------------------------------------------------------------ mirror symmetry (N3)

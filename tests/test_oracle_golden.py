@@ -184,3 +184,17 @@ def test_expert_index_contract_is_a_permutation_per_epoch():
     # roughly uniform first positions over many draws
     first = np.array([L.expert_indices(9, d, 1, 10)[0] for d in range(2000)])
     assert np.bincount(first, minlength=10).min() > 120
+
+
+def test_ppo_loss_oracle_vs_reference_update_policy():
+    """N3: oracle/learner.py ppo_losses against the six values PPO.update_policy returned (rl/algos/ppo.py:231-282, run by
+    tools/gen_golden.py:gen_ppo_loss with the reference's SymmetricEnv mirror functions) and torch autograd's gradients."""
+    from oracle import learner as L
+    z = np.load(GOLDEN / "ppo_loss_ref.npz")
+    o = L.ppo_losses(z["logp"], z["old_logp"], z["adv"], z["mask"], z["values"], z["returns"], z["entropy"], z["det_actions"],
+                     z["mirror_raw"], z["mirrored_acts"], float(z["clip"]), float(z["vf_coeff"]))
+    for k in ("actor_loss", "entropy_penalty", "critic_loss", "approx_kl", "mirror_loss", "clip_fraction"):
+        assert abs(o[k] - float(z[k])) < 2e-6 * max(1.0, abs(float(z[k]))), k
+    assert 0.05 < o["clip_fraction"] < 0.5
+    assert_close(o["dlogp"], z["dlogp"].ravel(), "d actor_loss / d logp", rtol=1e-5, atol=1e-9)
+    assert_close(o["dvalues"], z["dvalues"].ravel(), "d critic_loss / d values", rtol=1e-5, atol=1e-9)

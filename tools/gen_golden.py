@@ -487,6 +487,76 @@ def gen_disc_loss():
     print("disc_loss_ref: gail", loss01.item(), loss_noisy, "vdb", vlosses, "beta", betas)
 
 
+# ---------------------------------------------------------------- 10. PPO minibatch losses (rl/algos/ppo.py:231-282)
+def gen_ppo_loss():
+    """PPO.update_policy of the reference, executed with small stand-in actor / critic modules (a linear-Gaussian policy
+    with a state-independent std, a linear critic) and the reference's own SymmetricEnv mirror functions: the inputs the
+    loss kernel consumes (log-probs, advantages, mask, values, returns, entropies, deterministic and mirrored actions) and
+    the six numbers update_policy returns, plus autograd gradients with respect to log_probs and values."""
+    import torch
+    stub("ray", remote=lambda f: f)
+    stub("matplotlib"); stub("matplotlib.pyplot")
+    stub("rl"); stub("rl.envs", WrapEnv=object)
+    ppo = load("ref_ppo2", "rl/algos/ppo.py")
+    wr = load("ref_wrappers2", "rl/envs/wrappers.py")
+    base_mir_obs = [0.1, -1, 2, -3, -4, 5, -6, 13, -14, -15, 16, -17, 18, 7, -8, -9, 10, -11, 12,
+                    25, -26, -27, 28, -29, 30, 19, -20, -21, 22, -23, 24]
+    mirrored_obs = base_mir_obs + [len(base_mir_obs) + i for i in range(10)]
+    mirrored_acts = [6, -7, -8, 9, -10, 11, 0.1, -1, -2, 3, -4, 5]
+    env = wr.SymmetricEnv(lambda: types.SimpleNamespace(base_obs_len=41), mirrored_obs=mirrored_obs,
+                          mirrored_act=mirrored_acts, clock_inds=[31, 32])
+    torch.manual_seed(3)
+    B, nobs, nu = 200, 41, 12
+
+    class Actor(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(nobs, nu)
+            self.logstd = torch.nn.Parameter(torch.full((nu,), -0.7))
+        def forward(self, x):
+            return torch.tanh(self.lin(x))
+        def distribution(self, x):
+            return torch.distributions.Normal(self.forward(x), self.logstd.exp())
+
+    actor, old, critic = Actor(), Actor(), torch.nn.Linear(nobs, 1)
+    with torch.no_grad():
+        for p_new, p_old in zip(actor.parameters(), old.parameters()):
+            p_old.copy_(p_new + 0.004 * torch.randn_like(p_new))
+    algo = ppo.PPO.__new__(ppo.PPO)
+    algo.policy, algo.critic, algo.old_policy, algo.clip, algo.vf_coeff = actor, critic, old, 0.2, 0.5
+    obs = torch.randn(B, nobs)
+    ph = torch.randint(0, 88, (B,)).double()
+    obs[:, 31], obs[:, 32] = torch.sin(2 * np.pi * ph / 88).float(), torch.cos(2 * np.pi * ph / 88).float()
+    act = old.distribution(obs).sample()
+    ret, adv = torch.randn(B, 1), torch.randn(B, 1)
+    mask = (torch.rand(B, 1) > 0.1).float()
+    # what update_policy computes internally, recorded as the kernel's inputs (leaf copies for the gradients)
+    pdf = actor.distribution(obs)
+    logp = pdf.log_prob(act).sum(-1, keepdim=True).detach().requires_grad_(True)
+    old_logp = old.distribution(obs).log_prob(act).sum(-1, keepdim=True).detach()
+    values = critic(obs).detach().requires_grad_(True)
+    out = algo.update_policy(obs, act, ret, adv, mask, mirror_observation=env.mirror_clock_observation,
+                             mirror_action=env.mirror_action)
+    actor_loss, entropy_penalty, critic_loss, approx_kl, mirror_loss, clip_fraction = out
+    # the same expressions on the leaf copies -> gradients with respect to log_probs and values (ppo.py:244-256)
+    ratio = (logp - old_logp).exp()
+    a2 = -torch.min(ratio * adv * mask, ratio.clamp(1 - 0.2, 1 + 0.2) * adv * mask).mean()
+    c2 = 0.5 * torch.nn.functional.mse_loss(ret, values)
+    (a2 + c2).backward()
+    assert abs(a2.item() - actor_loss.item()) < 1e-7 and abs(c2.item() - critic_loss.item()) < 1e-7
+    with torch.no_grad():
+        det = actor(obs)
+        mir_raw = actor(env.mirror_clock_observation(obs))                 # policy(mirror(obs)) BEFORE mirror_action
+        ent = pdf.entropy()
+    np.savez(OUT / "ppo_loss_ref.npz", logp=logp.detach().numpy(), old_logp=old_logp.numpy(), adv=adv.numpy(), mask=mask.numpy(),
+             values=values.detach().numpy(), returns=ret.numpy(), entropy=ent.numpy(), det_actions=det.numpy(),
+             mirror_raw=mir_raw.numpy(), mirrored_acts=np.array(mirrored_acts), clip=0.2, vf_coeff=0.5,
+             actor_loss=actor_loss.item(), entropy_penalty=entropy_penalty.item(), critic_loss=critic_loss.item(),
+             approx_kl=approx_kl.item(), mirror_loss=mirror_loss.item(), clip_fraction=clip_fraction,
+             dlogp=logp.grad.numpy(), dvalues=values.grad.numpy())
+    print("ppo_loss_ref:", [float(x) if not hasattr(x, "item") else x.item() for x in out])
+
+
 if __name__ == "__main__":
     gen_trajectory()
     gen_phase_clock()
@@ -497,3 +567,4 @@ if __name__ == "__main__":
     gen_a3_task()
     gen_mirror()
     gen_disc_loss()
+    gen_ppo_loss()
