@@ -281,6 +281,7 @@ def run_ours(args):
             try:
                 import bench_disc
                 other["disc_reward_65536"] = bench_disc.measure(steps=20, warmup=3)
+                other["disc_reward_1048576"] = bench_disc.measure(envs=1 << 20, steps=10, warmup=3)   # steady state
             except Exception as e:
                 other["disc_error"] = repr(e)
             line["other_configs"] = other

@@ -16,6 +16,7 @@
 //   * warp-specialised: 4 producer/epilogue warps, one MMA-issuing thread, one copy-issuing thread, mbarriers only;
 //   * fp32 fidelity: every product is evaluated as 3xTF32 (a_hi b_hi + a_lo b_hi + a_hi b_lo, hi = cvt.rna.tf32), fp32
 //     accumulation in TMEM -- the north star's 1e-5 tolerance on rewards rules out plain TF32 (~1e-3).
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -371,6 +372,248 @@ __global__ void __launch_bounds__(192, 1) disc_reward_kernel(DiscArgs a) {
         if (VAIL && KL) a.kl_out[env] = 0.5f * klv;
       }
       // the next tile's layer-1 MMA overwrites the columns read above: put_chunk orders these loads before its arrive
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------- two producer warpgroups per CTA
+// Stall sampling of the kernel above puts the tensor pipe behind the PRODUCERS: one thread per sample turns 32 TMEM
+// columns into a hi / lo shared-memory chunk in ~250 instructions while the three MMAs of that chunk take less.  Here
+// eight producer warps share a tile: thread t and thread t + 128 own the same sample (TMEM lane t mod 128 -- a warp may
+// touch the 32 lanes given by its index mod 4) and each handles 16 of the 32 columns of every chunk, half of the input
+// row, half of the latent dimensions / head weights; the two partial head sums meet in shared memory behind one named
+// barrier.  Same rings, same schedule, same issuer code as above; 320 threads (warp 8 = MMA issuer, warp 9 = copies).
+__device__ __forceinline__ void store_a_half(uint8_t* stage, int row, int half, const float (&a)[16]) {
+  float4* hi = reinterpret_cast<float4*>(stage) + row;                       // [kc][128 rows] float4
+  float4* lo = reinterpret_cast<float4*>(stage + TILE * KC * 4) + row;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int kc = 4 * half + j;
+    float4 h, l;
+    h.x = tf32_rna(a[4 * j]); h.y = tf32_rna(a[4 * j + 1]); h.z = tf32_rna(a[4 * j + 2]); h.w = tf32_rna(a[4 * j + 3]);
+    l.x = a[4 * j] - h.x; l.y = a[4 * j + 1] - h.y; l.z = a[4 * j + 2] - h.z; l.w = a[4 * j + 3] - h.w;
+    hi[kc * TILE] = h;
+    lo[kc * TILE] = l;
+  }
+}
+
+template <int N1, int N2, bool VAIL, bool KL>
+__global__ void __launch_bounds__(320, 1) disc_reward_pg2_kernel(DiscArgs a) {
+  constexpr int ACT = VAIL ? ACT_RELU : ACT_TANH;
+  constexpr int NB1 = N1 / 256;
+  constexpr int Z = 128;
+  constexpr int N3 = 2 * Z;
+  constexpr int D1_COL = 0, D2_COL = 256, D3_COL = 0;
+  constexpr int HEAD_K = VAIL ? Z : N2;
+  constexpr int NPROD = 256;
+  static_assert(N1 % 256 == 0 && N2 % 32 == 0 && N2 <= 256, "unsupported discriminator shape");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* stA = smem;
+  uint8_t* stB = smem + 2 * STAGE_A_BYTES;
+  float* par = reinterpret_cast<float*>(stB + NSB * STAGE_B2_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(par + DISC_MAX_PAR + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* red = reinterpret_cast<float*>(tmem_slot + 4);                      // [2][128]: partial logit, partial KL of half 1
+  const float* b1 = par;
+  const float* b2 = par + N1;
+  const float* b3 = par + N1 + N2;
+  const float* wd = par + N1 + N2 + (VAIL ? N3 : 0);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s_) { return bar0 + 8u * s_; };
+  auto a_free = [&](int s_) { return bar0 + 8u * (2 + s_); };
+  auto b_full = [&](int s_) { return bar0 + 8u * (4 + s_); };
+  auto b_free = [&](int s_) { return bar0 + 8u * (8 + s_); };
+
+  constexpr int NPAR = N1 + N2 + (VAIL ? N3 : 0) + HEAD_K + 1;
+  for (int i = tid; i < NPAR; i += 320) par[i] = a.params[i];
+  float* s_mean = par + DISC_MAX_PAR - 2 * DISC_IN;
+  float* s_inv = s_mean + DISC_IN;
+  if (tid < DISC_IN) { s_mean[tid] = a.mean[tid]; s_inv[tid] = 1.0f / a.stdv[tid]; }
+  if (tid == 0) {
+    for (int s_ = 0; s_ < 2; ++s_) { mbar_init(a_full(s_), NPROD); mbar_init(a_free(s_), 1); }
+    for (int s_ = 0; s_ < NSB; ++s_) { mbar_init(b_full(s_), 1); mbar_init(b_free(s_), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int ntiles = (a.n + TILE - 1) / TILE;
+
+  if (warp == 9) {
+    // ===================================================== weight-copy issuer (as in disc_reward_kernel)
+    if (tid == 288) {
+      int qb = 0;
+      auto copy_chunk = [&](const float*& img, int rows) {
+        for (int hb = 0; hb < 2; ++hb, ++qb) {
+          const int sb = qb & (NSB - 1);
+          if (qb >= NSB) mbar_wait(b_free(sb), (uint32_t)((qb / NSB) - 1) & 1u);
+          const uint32_t bytes = (uint32_t)rows * KB * 4 * 2;
+          mbar_expect_tx(b_full(sb), bytes);
+          const uint32_t dst = smem_u32(stB + sb * STAGE_B2_BYTES);
+          for (uint32_t off = 0; off < bytes; off += COPY_PIECE)
+            bulk_g2s(dst + off, reinterpret_cast<const uint8_t*>(img) + off, COPY_PIECE, b_full(sb));
+          img += bytes / 4;
+        }
+      };
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const float* img = a.image;
+        for (int nb = 0; nb < NB1; ++nb) {
+          copy_chunk(img, 256);
+          for (int c = 0; c < 8; ++c) copy_chunk(img, N2);
+        }
+        if (VAIL)
+          for (int c = 0; c < N2 / KC; ++c) copy_chunk(img, N3);
+      }
+    }
+  } else if (warp == 8) {
+    // ===================================================== MMA issuer (as in disc_reward_kernel)
+    if (tid == 256) {
+      int ga = 0, qb = 0;
+      auto mma_chunk = [&](int rows, uint32_t d_col, bool first) {
+        const int sa = ga & 1;
+        mbar_wait(a_full(sa), (uint32_t)(ga >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(stA + sa * STAGE_A_BYTES), a_lo = a_hi + TILE * KC * 4;
+        const uint32_t a_lbo = TILE * 16, b_lbo = (uint32_t)rows * 16, sbo = 128;
+        const uint32_t idesc = idesc_tf32(TILE, rows);
+        for (int hb = 0; hb < 2; ++hb, ++qb) {
+          const int sb = qb & (NSB - 1);
+          mbar_wait(b_full(sb), (uint32_t)(qb / NSB) & 1u);
+          const uint32_t b_hi = smem_u32(stB + sb * STAGE_B2_BYTES), b_lo = b_hi + (uint32_t)rows * KB * 4;
+#pragma unroll
+          for (int j = 0; j < KB / 8; ++j) {
+            const uint32_t ao = (uint32_t)(hb * (KB / 8) + j) * 2 * a_lbo, bo = (uint32_t)j * 2 * b_lbo;
+            const uint64_t dah = smem_desc(a_hi + ao, a_lbo, sbo), dal = smem_desc(a_lo + ao, a_lbo, sbo);
+            const uint64_t dbh = smem_desc(b_hi + bo, b_lbo, sbo), dbl = smem_desc(b_lo + bo, b_lbo, sbo);
+            umma_tf32(tmem + d_col, dal, dbh, idesc, (first && hb == 0 && j == 0) ? 0u : 1u);
+            umma_tf32(tmem + d_col, dah, dbl, idesc, 1u);
+            umma_tf32(tmem + d_col, dah, dbh, idesc, 1u);
+          }
+          umma_commit(b_free(sb));
+        }
+        umma_commit(a_free(sa));
+        ++ga;
+      };
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int nb = 0; nb < NB1; ++nb) {
+          mma_chunk(256, D1_COL, true);
+          for (int c = 0; c < 8; ++c) mma_chunk(N2, D2_COL, nb == 0 && c == 0);
+        }
+        if (VAIL)
+          for (int c = 0; c < N2 / KC; ++c) mma_chunk(N3, D3_COL, c == 0);
+      }
+    }
+  } else {
+    // ===================================================== producers / epilogue (256 threads, two per sample)
+    const int row = tid & 127, half = tid >> 7;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const float bd = par[NPAR - 1];
+    int ga = 0;
+    auto wait_chunk = [&](int h) {
+      if (h >= 0) {
+        mbar_wait(a_free(h & 1), (uint32_t)(h >> 1) & 1u);
+        tc_fence_after();
+      }
+    };
+    auto put_half = [&](const float (&act_in)[16]) {
+      wait_chunk(ga - 2);
+      store_a_half(stA + (ga & 1) * STAGE_A_BYTES, row, half, act_in);
+      fence_proxy_async();
+      tc_fence_before();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_full(ga & 1)) : "memory");
+      ++ga;
+    };
+    auto load_row = [&](int tile_, float (&raw)[16]) {
+      const int env_ = tile_ * TILE + row;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) raw[k] = (tile_ < ntiles && env_ < a.n) ? a.s[(size_t)(16 * half + k) * a.ld + env_] : 0.f;
+    };
+    float xn[16];
+    load_row(blockIdx.x, xn);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int env = tile * TILE + row;
+      const bool live = env < a.n;
+      float x[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) x[k] = live ? (xn[k] - s_mean[16 * half + k]) * s_inv[16 * half + k] : 0.f;
+      load_row(tile + gridDim.x, xn);
+#pragma unroll 1
+      for (int nb = 0; nb < NB1; ++nb) {
+        put_half(x);                                                     // layer 1, column block nb
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {                                    // layer 2, K-chunks fed by this block
+          if (c == 0) wait_chunk(ga - 1);
+          float h[16];
+          tmem_ld16(lane_addr + D1_COL + c * KC + 16 * half, h);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) h[i] = act<ACT>(h[i] + b1[nb * 256 + c * KC + 16 * half + i]);
+          put_half(h);
+        }
+      }
+      float dval = 0.f, klv = 0.f;
+      if (VAIL) {
+#pragma unroll 1
+        for (int c = 0; c < N2 / KC; ++c) {                              // [mu; logvar] layer
+          if (c == 0) wait_chunk(ga - 1);
+          float h[16];
+          tmem_ld16(lane_addr + D2_COL + c * KC + 16 * half, h);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) h[i] = act<ACT>(h[i] + b2[c * KC + 16 * half + i]);
+          put_half(h);
+        }
+        // this half's 64 latent dimensions: z = mu + exp(logvar / 2) * eps, d += wd . z
+        static_assert(Z == 128, "head unrolled for z = 128");
+        float e0[32], e1[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          e0[i] = (a.eps && live) ? a.eps[(size_t)(64 * half + i) * a.ld + env] : 0.f;
+          e1[i] = (a.eps && live) ? a.eps[(size_t)(64 * half + 32 + i) * a.ld + env] : 0.f;
+        }
+        wait_chunk(ga - 1);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float mu[32], lv[32];
+          tmem_ld32(lane_addr + D3_COL + 64 * half + 32 * q, mu);
+          tmem_ld32(lane_addr + D3_COL + Z + 64 * half + 32 * q, lv);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int j = 64 * half + 32 * q + i;
+            const float m = mu[i] + b3[j], l = lv[i] + b3[Z + j], sd = expf(0.5f * l);
+            dval = fmaf(wd[j], fmaf(sd, q == 0 ? e0[i] : e1[i], m), dval);
+            if (KL) klv += fmaf(m, m, fmaf(sd, sd, -l)) - 1.f;
+          }
+        }
+      } else {
+        wait_chunk(ga - 1);
+#pragma unroll 1
+        for (int c = 0; c < N2 / 64; ++c) {
+          float h[32];
+          tmem_ld32(lane_addr + D2_COL + (N2 / 2) * half + c * 32, h);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int j = (N2 / 2) * half + c * 32 + i;
+            dval = fmaf(wd[j], act<ACT>(h[i] + b2[j]), dval);
+          }
+        }
+      }
+      // the two halves of a sample meet: half 1 hands its partial sums to half 0
+      if (half == 1) { red[row] = dval; red[128 + row] = klv; }
+      tc_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0 && live) {
+        dval += red[row] + bd;
+        const float one_minus_p = 1.f / (1.f + expf(dval));
+        if (a.reward) a.reward[env] = -logf(one_minus_p + 1e-8f);
+        if (a.d_out) a.d_out[env] = dval;
+        if (VAIL && KL) a.kl_out[env] = 0.5f * (klv + red[128 + row]);
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");                     // red[] may be rewritten by the next tile
     }
   }
   tc_fence_before();
@@ -758,6 +1001,21 @@ extern "C" int om_disc_forward(const OmDisc* h, const float* s, const float* mea
     auto kern = kl_out ? disc_vail2_kernel<true> : disc_vail2_kernel<false>;
     OM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     kern<<<grid2, 192, smem2, st>>>(a2);
+    OM_LAUNCHED();
+    return 0;
+  }
+  int pg2 = 1;                                                      // two producer warpgroups per CTA
+  if (const char* f = getenv("OM_DISC_PG2")) pg2 = atoi(f) != 0;                 // tuning / test hook
+  if (pg2) {
+    const size_t smem_pg2 = smem + 2 * 128 * sizeof(float);
+    if (h->sh.kind == 0) {
+      auto kern = kl_out ? disc_reward_pg2_kernel<256, 128, true, true> : disc_reward_pg2_kernel<256, 128, true, false>;
+      OM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pg2));
+      kern<<<grid, 320, smem_pg2, st>>>(a);
+    } else {
+      OM_CUDA_OK(cudaFuncSetAttribute(disc_reward_pg2_kernel<512, 256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pg2));
+      disc_reward_pg2_kernel<512, 256, false, false><<<grid, 320, smem_pg2, st>>>(a);
+    }
     OM_LAUNCHED();
     return 0;
   }
