@@ -114,6 +114,61 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------- configs[4]
+def sharded_1m(rank, world, local, table, rollouts=4, warmup=2):
+    """BASELINE.json configs[4]: 1 048 576 UnitreeH1 envs sharded by contiguous index range over the ranks, 64-step
+    rollouts (four 16-step playback calls into the same device buffers) and ONE all-reduce of the float64 observation
+    moments per rollout.  Every rank runs it; returns the aggregate (max-over-ranks time) on every rank."""
+    import torch
+    import torch.distributed as dist
+    from olympics_mujoco_b200 import distributed as D
+    from olympics_mujoco_b200 import kernels as Kn
+    from olympics_mujoco_b200.environments import LocoEnvBase
+    total, t_call, calls = 1 << 20, 16, 4
+    env_id0, n_local = D.env_shard(total, rank, world)
+    env = LocoEnvBase.make("UnitreeH1.walk.real", n_envs=n_local, traj_params=dict(table=table), seed=1234,
+                           env_id0=env_id0, device=f"cuda:{local}")
+    roll = env.make_rollout_buffers(t_call)
+    mom = torch.zeros(65, dtype=torch.float64, device="cuda")
+
+    def rollout():
+        mom.zero_()
+        for _ in range(calls):
+            out = env.play_trajectory_from_velocity(n_episodes=1, n_steps_per_episode=t_call, render=False, out=roll)
+            Kn.moments(out["obs"], out=mom)
+        if world > 1:
+            dist.all_reduce(mom)
+        return D.mean_std_from_moments(mom, "ppo_obs")
+
+    for _ in range(warmup):
+        rollout()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(rollouts):
+        rollout()
+    t1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([t0.elapsed_time(t1) / rollouts], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    del roll, env
+    torch.cuda.empty_cache()
+    ms = float(ms)
+    peaks, _ = measured_peaks()
+    per_gpu = BYTES_PER_ENV_STEP * (total / world) * t_call * calls / (ms * 1e-3) / 1e9
+    return {"workload": f"UnitreeH1 walk, 1048576 envs sharded over {world} GPU(s) (configs[4]): 64-step rollouts, one "
+                        "all-reduce of the observation moments per rollout", "envs_per_gpu": n_local, "value": total * t_call * calls / (ms * 1e-3),
+            "unit": "env-steps/s", "ms_per_rollout": ms, "scaling": "strong",
+            "roofline": {"bound": "hbm", "achieved_per_gpu": per_gpu, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": per_gpu / peaks["hbm_gbs"], "bytes_per_env_step": BYTES_PER_ENV_STEP,
+                         "note": "whole rollout incl. the moments pass and the all-reduce, not the kernel alone"}}
+
+
 # ------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -246,6 +301,13 @@ def run_ours(args):
     h2d = values_host.numel() * 4
     d2h = sum(v.numel() * v.element_size() for v in host.values())
 
+    sharded = None
+    if not args.no_other_configs:
+        try:
+            sharded = sharded_1m(rank, world, local, table)
+        except Exception as e:                                  # never lose the headline line to a side measurement
+            sharded = {"error": repr(e)}
+
     if rank == 0:
         peaks, which = measured_peaks()
         kernel_ms = float(kms)
@@ -265,7 +327,7 @@ def run_ours(args):
         if not args.no_other_configs:
             # the other BASELINE.json configs on this GPU (parity cases; measured here so that one file carries them)
             sys.path.insert(0, str(ROOT / "tools"))
-            other = {}
+            other = {"h1_1m_envs_sharded": sharded}
             try:
                 import bench_a3
                 other["a3_ppo_rollout_16384x64"] = bench_a3.measure(steps=10, warmup=3)
