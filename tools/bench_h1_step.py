@@ -16,14 +16,14 @@ BYTES_PER_ENV_STEP = 1517
 def measure(envs=1 << 20, steps=20, warmup=3):
     import bench
     from olympics_mujoco_b200 import kernels as Kn
-    from oracle import h1 as OH
+    from olympics_mujoco_b200.build import H1_SPEC_JOINTS
     model, table = bench.build_table()
     n = envs
     dm = Kn.DeviceModel(model)
-    spec = Kn.make_h1_spec(OH.perm(model), OH.x_vel_idx(model))
+    perm_list = [int(model.jnt_qposadr[model.jnt_names.index(j)]) for j in H1_SPEC_JOINTS]   # UnitreeH1.py:303-355
+    spec = Kn.make_h1_spec(perm_list, 15)                  # dq_pelvis_tx in the emitted 32-entry observation
     traj = Kn.DeviceTrajectory(table, n, seed=5)
     sample = traj.reset()
-    perm = torch.as_tensor(OH.perm(model), device="cuda")
     qpos, qvel = torch.empty((17, n), device="cuda"), torch.empty((17, n), device="cuda")
     out = None
 
