@@ -150,8 +150,9 @@ __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w
   const A3Rec rec = a3_task_pre(a.C, a3_task_in(S.f), phase, mode, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, terms,
                                 obs[31], obs[32], done);
   a3_rec_store(rec, w.feat + (size_t)t * A3_NREC * ld + e, ld);
+  const int nc = a3_cand_needed(t, a.ints[A3I_FRAMES * ld + e], a.C.delay_frames, ncand);   // later targets are out of reach
   w.near[(size_t)t * ld + e] =
-      (uint8_t)a3_near_bits(a.C, rec.lsite, rec.rsite, ncand, t1_0, t2_0, seq_len, SeqGlobal{a.sequence + e, ld});
+      (uint8_t)a3_near_bits(a.C, rec.lsite, rec.rsite, nc, t1_0, t2_0, seq_len, SeqGlobal{a.sequence + e, ld});
   if (a.o.obs) {
     float* ob = a.o.obs + (size_t)t * A3_NOBS * ld + e;
 #pragma unroll

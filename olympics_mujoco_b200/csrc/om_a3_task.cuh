@@ -352,6 +352,14 @@ OM_HD uint32_t a3_near_bits(const A3TaskConst& C, V3 lsite, V3 rsite, int ncand,
   }
   return bits;
 }
+// Candidates that can be consulted at step t of a call: advance k needs max(delay - frames0, 1) + (k - 1) max(delay, 1)
+// steps, and the new target's bit is first read on the step after the advance.
+OM_HD int a3_cand_needed(int t, int frames0, int delay_frames, int ncand) {
+  const int dm = delay_frames > 1 ? delay_frames : 1;
+  const int first = delay_frames - frames0 > 1 ? delay_frames - frames0 : 1;
+  const int n = t >= first ? 2 + (t - first) / dm : 1;
+  return n < ncand ? n : ncand;
+}
 struct A3Walk { int j, frames, reached; };       // j = number of target advances since the start of the call
 OM_HD void a3_walk_step(const A3TaskConst& C, uint32_t bits, A3Walk& w) {
   if ((bits >> w.j) & 1u) {

@@ -86,7 +86,7 @@ extern "C" void host_a3_rollout_split(const float* lut6, int period, int delay, 
     const int t1_0 = st[1], t2_0 = st[2], sl = st[5];
     for (int t = c0; t < c0 + len; ++t) {
       const A3Rec r = a3_rec_load(rec + (size_t)t * A3_NREC, 1);
-      near[t] = (uint8_t)a3_near_bits(C, r.lsite, r.rsite, nc, t1_0, t2_0, sl, SeqHost{seq});
+      near[t] = (uint8_t)a3_near_bits(C, r.lsite, r.rsite, a3_cand_needed(t - c0, st[3], delay, nc), t1_0, t2_0, sl, SeqHost{seq});
     }
     A3Walk w{0, st[3], st[6]};
     for (int t = c0; t < c0 + len; ++t) {

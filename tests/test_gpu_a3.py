@@ -228,6 +228,8 @@ def test_a3_replay_state_machine_stress(a3_model, delay, radius, monkeypatch):
         task = Kn.A3Task(dm, n, phase_clock_lut(), OA.init_qpos(), delay_frames=delay, target_radius=radius)
         ints = gold["reset_ints"].T.astype(np.int32).copy()
         ints[:, 3:] = np.array([[3, 4, 5, 1, 1, 20, 1]], np.int32).T         # some envs start mid-plan with frames pending
+        ints[:, 4] = [7, 2, 3, max(delay - 1, 0), 1, 20, 1]                   # one step short of an advance
+        ints[:, 5] = [7, 18, 19, delay + 3, 1, 20, 1]                         # overdue, at the end of the plan
         task.ints.copy_(torch.as_tensor(ints))
         task.sequence.copy_(torch.as_tensor(gold["reset_sequence"].reshape(n, 80).T.astype(np.float32)))
         out = task.step(qpos, qvel, con)

@@ -242,7 +242,8 @@ def test_a3_task_device_functions_on_host(a3_model):
     for delay, radius in ((0, 5.0), (1, 5.0), (2, 0.9), (5, 0.6), (30, 5.0), (7, 0.35)):
         c2 = (P(lut), OA.PERIOD, delay, ctypes.c_double(radius), ctypes.c_double(0.80), ctypes.c_double(0.01),
               ctypes.c_float(a3_model.total_mass * 9.8 * 0.5))
-        for start in (gold["reset_ints"][e].astype(np.int32), np.array([3, 4, 5, 1, 1, 20, 1], np.int32)):
+        for start in (gold["reset_ints"][e].astype(np.int32), np.array([3, 4, 5, 1, 1, 20, 1], np.int32),
+                      np.array([7, 2, 3, max(delay - 1, 0), 1, 20, 1], np.int32), np.array([7, 18, 19, delay + 3, 1, 20, 1], np.int32)):
             ia, ib = start.copy(), start.copy()
             oa, ta = np.zeros((T, 41), np.float32), np.zeros((T, 6), np.float32)
             ra, da = np.zeros(T, np.float32), np.zeros(T, np.uint8)
@@ -253,7 +254,7 @@ def test_a3_task_device_functions_on_host(a3_model):
             assert np.array_equal(da, db)
             assert_close(ob, oa, "stress obs", rtol=1e-6, atol=1e-6); assert_close(rb, ra, "stress reward", rtol=1e-6, atol=1e-6)
             advanced += int(ia[1] != start[1])
-    assert advanced >= 6
+    assert advanced >= 10
 
 
 def test_perfect_dataset_conversion_matches_reference_restatement():
