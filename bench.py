@@ -27,8 +27,8 @@ os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 BYTES_PER_ENV_STEP = 1517          # SURVEY.md section 8(d), config 2 (algorithmic HBM bytes of the playback step)
 # dram__bytes_read.sum + dram__bytes_write.sum of play_h1_tp_kernel at 4096 envs x 500 steps, one `ncu --set full`
-# capture (profiles/r01_play_h1_tp_raw.csv: 11.3 MB read + 2491.0 MB written per launch)
-NCU_TRAFFIC_BYTES_4096x500 = 11.327e6 + 2491.07e6
+# capture (profiles/r01d_play_h1_tp_raw.csv: 12.2 MB read + 2492.5 MB written per launch)
+NCU_TRAFFIC_BYTES_4096x500 = 12.228e6 + 2492.518e6
 N_ENVS = 4096
 HORIZON = 500
 GAMMA, LAM = 0.99, 0.97
