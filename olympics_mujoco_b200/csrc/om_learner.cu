@@ -228,9 +228,16 @@ __global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ 
     s += __shfl_xor_sync(0xffffffffu, s, o);
     s2 += __shfl_xor_sync(0xffffffffu, s2, o);
   }
-  if ((threadIdx.x & 31) == 0 && (s != 0.0 || s2 != 0.0)) {
-    atomicAdd(out + c, s);
-    atomicAdd(out + C + c, s2);
+  // one atomic pair per CTA: with C = 1 (advantages) every warp of the grid would otherwise queue on the same two L2
+  // addresses (8000 same-address double atomics made a 16 us kernel out of an 8 MB pass)
+  __shared__ double sh[2][8];
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+    if (t != 0.0) atomicAdd(out + threadIdx.x * C + c, t);
   }
   if (c == 0 && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 0) atomicAdd(out + 2 * C, (double)rows * (double)n);
 }
@@ -256,6 +263,27 @@ __global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict_
   }
 }
 
+// K per-thread float64 partial sums -> one atomicAdd per CTA and statistic (256-thread CTAs): warp shuffle, then the eight
+// warp leaders meet in shared memory.  Per-warp atomics would queue thousands of same-address updates in L2.
+template <int K>
+__device__ __forceinline__ void block_sum_atomic(double (&acc)[K], double* __restrict__ sums) {
+  __shared__ double sh[K][8];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+    if (t != 0.0) atomicAdd(&sums[threadIdx.x], t);
+  }
+}
+
 // ---------------------------------------------------------------- N2: discriminator-fit statistics, expert minibatch
 // One pass over the logits of [policy batch; expert batch]: per-sample fp32 terms, float64 sums (warp shuffle, one
 // atomicAdd per warp and statistic).
@@ -278,13 +306,7 @@ __global__ void __launch_bounds__(256) disc_loss_kernel(const float* __restrict_
     else { acc[3] += x < 0.f ? 1.0 : 0.0; acc[5] += sig; }
     if (dlogit) dlogit[i] = (sig - t) + entcoeff * x * sig * (1.f - sig);
   }
-#pragma unroll
-  for (int k = 0; k < 7; ++k) {
-    double v = acc[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&sums[k], v);
-  }
+  block_sum_atomic<7>(acc, sums);
   if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&sums[7], (double)n_plcy); atomicAdd(&sums[8], (double)(n - n_plcy)); }
 }
 
@@ -335,13 +357,7 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(PpoLossArgs a) {
         acc[4] += d * d;
       }
   }
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    double v = acc[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&a.sums[k], v);
-  }
+  block_sum_atomic<6>(acc, a.sums);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.sums[6], (double)a.n);
 }
 
