@@ -135,6 +135,20 @@ class ObservationHelper:
     def get_all_observation_keys(self):
         return list(self.obs_idx_map.keys())
 
+    def _modify_data(self, data, obs):
+        """mushroom_rl ``ObservationHelper._modify_data``: the inverse of ``_build_obs`` -- write a full observation
+        ([n, D] or [D], every spec entry present) back into the data arrays it was gathered from."""
+        obs = torch.as_tensor(obs, dtype=torch.float32, device=data.qpos.device)
+        if obs.dim() == 1:
+            obs = obs[None].expand(data.n, -1)
+        cur = 0
+        for key, name, ot in self.observation_spec:
+            rows = data.rows(name, ot)                       # a view into data.qpos / qvel / xpos ...
+            c = rows.shape[0]
+            rows.copy_(obs[:, cur:cur + c].t())
+            cur += c
+        return data
+
     def _build_obs_soa(self, data):
         parts = []
         for key, name, ot in self.observation_spec:

@@ -144,6 +144,11 @@ def test_observation_helper_generic_spec():
                           v[:, [9]]], axis=1)
     assert_close(obs, exp, "generic obs")
     assert_close(oh.get_from_obs(torch.as_tensor(obs), "imu").numpy(), ref["site_xpos"][:, 0], "get_from_obs")
+    # _modify_data is the inverse gather: a fresh data object written from the observation rebuilds the same observation
+    data2 = BatchedData(model, n)
+    oh._modify_data(data2, torch.as_tensor(obs))
+    assert np.array_equal(oh._build_obs(data2).cpu().numpy(), obs)
+    assert np.array_equal(data2.qpos[9].cpu().numpy(), q[:, 9]) and np.array_equal(data2.qvel[9].cpu().numpy(), v[:, 9])
 
 
 def test_set_sim_state_kernel_matches_named_scatter():
