@@ -136,8 +136,7 @@ def sharded_1m(rank, world, local, table, rollouts=4, warmup=2):
         for _ in range(calls):
             out = env.play_trajectory_from_velocity(n_episodes=1, n_steps_per_episode=t_call, render=False, out=roll)
             Kn.moments(out["obs"], out=mom)
-        if world > 1:
-            dist.all_reduce(mom)
+        D.all_reduce_moments(mom)                              # NVLink mailbox kernel (or NCCL), no-op at world 1
         return D.mean_std_from_moments(mom, "ppo_obs")
 
     for _ in range(warmup):
@@ -189,8 +188,13 @@ def run_ours(args):
         pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
     except Exception:
         pass
+    from olympics_mujoco_b200 import distributed as D
+    collective = "none"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # the path's only exchange: 68 float64 per rollout.  One small kernel over NVLink peer memory (csrc/om_mailbox.cu);
+        # NCCL if the mailboxes cannot be mapped (decided collectively, so every rank takes the same route)
+        collective = "nvlink_mailbox" if (not args.nccl and D.enable_mailbox(True)) else "nccl"
     n, T = args.envs, args.horizon
 
     model, table = build_table()
@@ -216,8 +220,7 @@ def run_ours(args):
         mom.zero_()
         Kn.moments_scalar(adv, out=mom[:3])
         Kn.moments(out["obs"], out=mom[3:])
-        if world > 1:
-            dist.all_reduce(mom)                               # the path's only exchange (520 B + 24 B, float64)
+        D.all_reduce_moments(mom)                              # the path's only exchange (520 B + 24 B, float64)
         stats = Kn.adv_stats(mom[:3], unbiased=False, eps=1e-8)
         Kn.normalize(adv, stats, out=adv)
         return out, vt, adv
@@ -315,7 +318,7 @@ def run_ours(args):
         line = {"metric": "env-steps/sec (FK+obs+reward+GAE)", "value": value, "unit": "env-steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(n, T),
+                "config": dict(workload_config(n, T), collective=collective),
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": world * n * T / (float(e2e_ms) * 1e-3), "unit": "env-steps/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -369,6 +372,7 @@ def main():
     ap.add_argument("--horizon", type=int, default=HORIZON)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--nccl", action="store_true", help="use NCCL for the moment all-reduce instead of the NVLink mailbox kernel")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

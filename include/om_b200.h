@@ -343,6 +343,22 @@ int om_ppo_loss_stats(const float* logp, const float* old_logp, const float* adv
                       const OmMirrorSpec* action_mirror, int nu, int n, int ld, float clip, float vf_coeff, double* sums,
                       float* dlogp, float* dvalues, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * S1 exchange over NVLink peer memory (one process per GPU): sum of <= 128 float64 values over the ranks, the path's only
+ * collective (where the reference reduces its moment sums: rl/envs/normalize.py:48, rl/algos/ppo.py:336,
+ * gail_TRPO.py:128, networks.py:76-81).  create: allocates this rank's mailbox and returns its CUDA IPC handle
+ * (OM_MAILBOX_HANDLE_BYTES bytes) for the caller to all-gather by any means; connect: maps every peer's mailbox;
+ * allreduce: one kernel on `stream` (stores to every mailbox, system-scope flags, rank-ordered sum: identical bits on
+ * every rank; in and out are device pointers, may alias).  Every rank must issue the same sequence of calls.  A peer
+ * that does not show up within 2 s sets the flag read by om_mailbox_timed_out instead of hanging the GPU. */
+#define OM_MAILBOX_HANDLE_BYTES 64
+typedef struct OmMailbox OmMailbox;
+int om_mailbox_create(int world, int rank, OmMailbox** out, unsigned char* handle_out);
+int om_mailbox_connect(OmMailbox* mb, const unsigned char* all_handles);
+int om_mailbox_allreduce(OmMailbox* mb, const double* in, double* out, int n, void* stream);
+int om_mailbox_timed_out(OmMailbox* mb, int* flag);
+void om_mailbox_destroy(OmMailbox* mb);
+
 #ifdef __cplusplus
 }
 #endif

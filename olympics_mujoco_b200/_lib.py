@@ -121,6 +121,11 @@ PROTOTYPES = {
     "om_moments": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "om_adv_stats": (_I, [_P, _I, _D, _P, _P]),
     "om_normalize": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "om_mailbox_create": (_I, [_I, _I, C.POINTER(_P), _P]),
+    "om_mailbox_connect": (_I, [_P, _P]),
+    "om_mailbox_allreduce": (_I, [_P, _P, _P, _I, _P]),
+    "om_mailbox_timed_out": (_I, [_P, C.POINTER(_I)]),
+    "om_mailbox_destroy": (None, [_P]),
 }
 
 

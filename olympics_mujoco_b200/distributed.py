@@ -42,10 +42,85 @@ def env_shard(n_total, rank, world_size):
     return env_id0, n_local
 
 
+class Mailbox:
+    """``om_mailbox_*``: sum of <= 128 float64 values over the ranks through mailboxes in each rank's HBM, mapped into
+    every peer process with CUDA IPC and written over NVLink by one small kernel per rank (csrc/om_mailbox.cu).  The IPC
+    handles travel once, through ``torch.distributed.all_gather_object``."""
+
+    MAX_N = 128
+
+    def __init__(self):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        self._lib, self._C = lib, C
+        world, rank = dist.get_world_size(), dist.get_rank()
+        h = C.c_void_p()
+        mine = (C.c_ubyte * 64)()
+        _lib.check(lib.om_mailbox_create(world, rank, C.byref(h), C.cast(mine, C.c_void_p)))
+        self.handle = h
+        gathered = [None] * world
+        dist.all_gather_object(gathered, bytes(mine))
+        blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(gathered))
+        rc = lib.om_mailbox_connect(self.handle, C.cast(blob, C.c_void_p))
+        ok = torch.tensor([1 if rc == 0 else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)              # all ranks use the mailbox, or none does
+        if int(ok) == 0:
+            self.close()
+            raise RuntimeError("mailbox: a peer mailbox could not be mapped: " + lib.om_last_error().decode())
+
+    def all_reduce(self, x):
+        from . import _lib
+        assert x.dtype == torch.float64 and x.is_cuda and x.is_contiguous() and x.numel() <= self.MAX_N
+        C = self._C
+        _lib.check(self._lib.om_mailbox_allreduce(self.handle, C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()), x.numel(),
+                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return x
+
+    def timed_out(self):
+        from . import _lib
+        f = self._C.c_int(0)
+        _lib.check(self._lib.om_mailbox_timed_out(self.handle, self._C.byref(f)))
+        return bool(f.value)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.om_mailbox_destroy(self.handle)
+            self.handle = None
+
+
+_mailbox = None
+_mailbox_state = "unset"          # "unset" | "on" | "off"
+
+
+def enable_mailbox(enable=True):
+    """Route ``all_reduce_moments`` through the NVLink mailbox kernel (collective call: every rank must make it).
+    Falls back to NCCL on every rank if any rank cannot map its peers.  Returns whether the mailbox is in use."""
+    global _mailbox, _mailbox_state
+    if _mailbox is not None:
+        _mailbox.close()
+        _mailbox = None
+    _mailbox_state = "off"
+    if enable and dist.is_initialized() and dist.get_world_size() > 1 and dist.get_backend() == "nccl":
+        try:
+            _mailbox = Mailbox()
+            _mailbox_state = "on"
+        except Exception as e:                                  # IPC not permitted, no peer access ...: NCCL it is
+            import warnings
+            warnings.warn(f"NVLink mailbox all-reduce unavailable ({e}); using NCCL")
+    return _mailbox_state == "on"
+
+
 def all_reduce_moments(mom):
-    """Sum a float64 moment buffer (``om_moments`` layout: sum[C], sumsq[C], count) over the ranks, in place."""
+    """Sum a float64 moment buffer (``om_moments`` layout: sum[C], sumsq[C], count) over the ranks, in place: the NVLink
+    mailbox kernel when ``enable_mailbox()`` set it up (CUDA float64, <= 128 values), else ``dist.all_reduce`` (NCCL on
+    the GPUs, gloo in the CPU tests)."""
     if dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(mom, op=dist.ReduceOp.SUM)
+        if (_mailbox is not None and mom.is_cuda and mom.dtype == torch.float64 and mom.is_contiguous()
+                and mom.numel() <= Mailbox.MAX_N):
+            _mailbox.all_reduce(mom)
+        else:
+            dist.all_reduce(mom, op=dist.ReduceOp.SUM)
     return mom
 
 
