@@ -311,6 +311,13 @@ def run_ours(args):
         except Exception as e:                                  # never lose the headline line to a side measurement
             sharded = {"error": repr(e)}
 
+    if collective == "nvlink_mailbox":
+        bad = torch.tensor([1.0 if D._mailbox.timed_out() else 0.0], device="cuda")
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if float(bad) > 0:                                      # a peer never delivered: the sums (not the timing) are void
+            collective = "nvlink_mailbox (a round timed out)"
+            sys.stderr.write("bench: the mailbox all-reduce timed out on some rank\n")
+
     if rank == 0:
         peaks, which = measured_peaks()
         kernel_ms = float(kms)
