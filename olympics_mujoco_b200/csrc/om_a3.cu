@@ -116,9 +116,14 @@ __global__ void __launch_bounds__(BLOCK) a3_task_kernel(A3Args a) {
 //   a3_post_kernel  one thread per (env, t) again: goal steps, orientation and step terms, total.
 struct A3Scratch {
   float* feat;          // [T][16][ld]
-  uint8_t* near;        // [T][ld]   candidate bits
-  uint8_t* code;        // [T][ld]   advances since the call started | reached << 3, after the step's update
+  // the two byte arrays are ENV-major ([ld][tp], tp = T rounded up to 16): the sequential pass reads and writes an env's
+  // bytes as 16-byte vectors (4 loads per 64 steps instead of 64 with their address arithmetic -- it runs one warp per
+  // scheduler, every instruction's latency is exposed); the (env, t)-parallel passes touch one byte per thread
+  uint8_t* near;        // candidate bits
+  uint8_t* code;        // advances since the call started | reached << 3, after the step's update
+  int tp;
   int32_t* start;       // [2][ld]   t1, t2 at the start of the call
+  float* trig;          // [A3_MAX_CAND + 1][4][ld]   sin, cos of candidate j's heading and of half of it (feat t = 0 -> post)
 };
 
 // one env-step of the (env, t)-parallel pass
@@ -134,12 +139,21 @@ __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w
   for (int k = 0; k < A3_NV; ++k) qd[k] = vp[k * ld];
 #pragma unroll
   for (int k = 0; k < 4; ++k) con[k] = cp[k * ld];
-  const int phase = (a.ints[A3I_PHASE * ld + e] + t + 1) % a.C.period;     // walking_task.py:248-250, t + 1 increments
+  int phase = a.ints[A3I_PHASE * ld + e] + (t + 1) % a.C.period;            // walking_task.py:248-250, t + 1 increments;
+  if (phase >= a.C.period) phase -= a.C.period;                            // the modulo is warp-uniform, the wrap a select
   const int mode = a.ints[A3I_MODE * ld + e];
   const int t1_0 = a.ints[A3I_T1 * ld + e], t2_0 = a.ints[A3I_T2 * ld + e], seq_len = a.ints[A3I_SEQLEN * ld + e];
   if (t == 0) {                                                            // start state of the call for the post pass
     w.start[e] = t1_0;
     w.start[ld + e] = t2_0;
+    for (int j = 0; j <= ncand; ++j) {             // headings of every target the call can reach, and of the one after
+      const float th = a.sequence[(size_t)(a3_cand(j, t1_0, t2_0, seq_len) * 4 + 3) * ld + e];
+      float sn, cs, sh, ch;
+      om_sincos(th, &sn, &cs);
+      om_sincos(0.5f * th, &sh, &ch);
+      float* tr = w.trig + (size_t)j * 4 * ld + e;
+      tr[0] = sn; tr[ld] = cs; tr[2 * ld] = sh; tr[3 * ld] = ch;
+    }
   }
   float obs[A3_NOBS], terms[6];
   a3_obs_robot(q, qd, obs);
@@ -151,7 +165,7 @@ __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w
                                 obs[31], obs[32], done);
   a3_rec_store(rec, w.feat + (size_t)t * A3_NREC * ld + e, ld);
   const int nc = a3_cand_needed(t, a.ints[A3I_FRAMES * ld + e], a.C.delay_frames, ncand);   // later targets are out of reach
-  w.near[(size_t)t * ld + e] =
+  w.near[e * w.tp + t] =
       (uint8_t)a3_near_bits(a.C, rec.lsite, rec.rsite, nc, t1_0, t2_0, seq_len, SeqGlobal{a.sequence + e, ld});
   if (a.o.obs) {
     float* ob = a.o.obs + (size_t)t * A3_NOBS * ld + e;
@@ -167,20 +181,34 @@ __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w
 
 // The integer state machine over the T candidate bytes of one env (a few instructions per step); leaves a one-byte
 // (advances, reached) code per env-step and the final task state.
-template <int CH>
 __device__ __forceinline__ void a3_walk(const A3Args& a, const A3Scratch& w, size_t e) {
   const size_t ld = a.ld;
   const int t1_0 = a.ints[A3I_T1 * ld + e], t2_0 = a.ints[A3I_T2 * ld + e], seq_len = a.ints[A3I_SEQLEN * ld + e];
   A3Walk s{0, a.ints[A3I_FRAMES * ld + e], a.ints[A3I_REACHED * ld + e]};
-  for (int t0 = 0; t0 < a.T; t0 += CH) {
-    uint8_t nb[CH];
+  const uint4* nb = reinterpret_cast<const uint4*>(w.near + e * w.tp);
+  uint4* cd = reinterpret_cast<uint4*>(w.code + e * w.tp);
+  for (int t0 = 0; t0 < a.T; t0 += 64) {
+    uint4 in[4];
 #pragma unroll
-    for (int i = 0; i < CH; ++i) nb[i] = t0 + i < a.T ? w.near[(size_t)(t0 + i) * ld + e] : 0;
+    for (int v = 0; v < 4; ++v) in[v] = t0 + 16 * v < a.T ? nb[(t0 >> 4) + v] : make_uint4(0, 0, 0, 0);
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      if (t0 + i < a.T) {
-        a3_walk_step(a.C, nb[i], s);
-        w.code[(size_t)(t0 + i) * ld + e] = (uint8_t)(s.j | (s.reached << 3));
+    for (int v = 0; v < 4; ++v) {
+      if (t0 + 16 * v < a.T) {
+        const uint32_t wi[4] = {in[v].x, in[v].y, in[v].z, in[v].w};
+        uint32_t wo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t o = 0;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            if (t0 + 16 * v + 4 * q + b < a.T) {                     // bytes past T are padding
+              a3_walk_step(a.C, (wi[q] >> (8 * b)) & 0xffu, s);
+              o |= (uint32_t)(s.j | (s.reached << 3)) << (8 * b);
+            }
+          }
+          wo[q] = o;
+        }
+        cd[(t0 >> 4) + v] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
       }
     }
   }
@@ -198,7 +226,7 @@ __global__ void __launch_bounds__(BLOCK, 5) a3_feat_kernel(A3Args a, A3Scratch w
 
 __global__ void __launch_bounds__(64) a3_walk_kernel(A3Args a, A3Scratch w) {
   const int env = blockIdx.x * 64 + threadIdx.x;
-  if (env < a.n) a3_walk<64>(a, w, env);
+  if (env < a.n) a3_walk(a, w, env);
 }
 
 template <int BLOCK>
@@ -208,13 +236,15 @@ __global__ void __launch_bounds__(BLOCK) a3_post_kernel(A3Args a, A3Scratch w) {
   if (env >= a.n) return;
   const size_t ld = a.ld, e = env;
   const A3Rec rec = a3_rec_load(w.feat + (size_t)t * A3_NREC * ld + e, ld);
-  const int code = w.code[(size_t)t * ld + e];
+  const int code = w.code[e * w.tp + t];
   const int mode = a.ints[A3I_MODE * ld + e], seq_len = a.ints[A3I_SEQLEN * ld + e];
   const int t1_0 = w.start[e], t2_0 = w.start[ld + e];
   const int j = code & 7;
+  const float* tr = w.trig + (size_t)j * 4 * ld + e;                   // candidate j, then candidate j + 1
+  const A3TargetTrig tg{tr[0], tr[ld], tr[4 * ld], tr[5 * ld], tr[2 * ld], tr[3 * ld]};
   float goal[8], tm2, tm4, total;
   a3_task_post(a.C, rec, mode, a3_cand(j, t1_0, t2_0, seq_len), a3_cand(j + 1, t1_0, t2_0, seq_len), (code >> 3) != 0,
-               SeqGlobal{a.sequence + e, ld}, goal, tm2, tm4, total);
+               SeqGlobal{a.sequence + e, ld}, &tg, goal, tm2, tm4, total);
   if (a.o.obs) {
     float* ob = a.o.obs + ((size_t)t * A3_NOBS + 33) * ld + e;
 #pragma unroll
@@ -315,6 +345,8 @@ extern "C" int om_a3_task_create(const OmA3TaskDesc* d, OmA3Task** out) {
   t->C.delay_frames = d->delay_frames;
   t->C.fmax = (float)(d->total_mass * 9.8 * 0.5);
   t->C.vmax = 0.2f;
+  t->C.inv_fmax = 1.0f / t->C.fmax;
+  t->C.inv_vmax = 1.0f / t->C.vmax;
   t->C.target_radius = d->target_radius;
   t->C.near_d2 = a3_near_d2(d->target_radius);
   t->C.goal_height_ref = d->goal_height_ref;
@@ -352,10 +384,11 @@ extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const flo
   if (split) {
     constexpr int FB = 128;
     const int env_blocks = ceil_div(n, FB);
-    // layout: [records][start ints][candidate bytes][state codes]
+    // layout: [records][start ints + heading table][candidate bytes][state codes]
     const size_t feat_b = (size_t)n_steps * A3_NREC * (size_t)ld * sizeof(float);
-    const size_t int_b = (size_t)2 * ld * sizeof(int32_t);
-    const size_t byte_b = (size_t)n_steps * (size_t)ld;
+    const size_t int_b = ((size_t)(2 + (A3_MAX_CAND + 1) * 4) * ld * sizeof(int32_t) + 15) / 16 * 16;   // byte arrays 16-B aligned
+    const int tp_max = (n_steps + 15) / 16 * 16;
+    const size_t byte_b = (size_t)tp_max * (size_t)ld;
     const size_t need = feat_b + int_b + 2 * byte_b;
     OM_REQUIRE(env_blocks <= 65535, "om_a3_task_step: at most %d envs per multi-step call", 65535 * FB);
     if (task->scratch_bytes < need) {
@@ -366,8 +399,8 @@ extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const flo
       task->scratch_bytes = need;
     }
     char* base = (char*)task->scratch;
-    A3Scratch w{(float*)base, (uint8_t*)(base + feat_b + int_b), (uint8_t*)(base + feat_b + int_b + byte_b),
-                (int32_t*)(base + feat_b)};
+    A3Scratch w{(float*)base, (uint8_t*)(base + feat_b + int_b), (uint8_t*)(base + feat_b + int_b + byte_b), 0,
+                (int32_t*)(base + feat_b), (float*)(base + feat_b) + 2 * (size_t)ld};
     // sub-calls no longer than the candidate bits cover (210 steps with the reference's 30 delay frames)
     const int max_call = a3_max_steps_per_call(task->C.delay_frames);
     for (int c0 = 0; c0 < n_steps; c0 += max_call) {
@@ -379,6 +412,7 @@ extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const flo
       if (sub.o.reward) sub.o.reward += (size_t)c0 * ld;
       if (sub.o.done) sub.o.done += (size_t)c0 * ld;
       sub.T = len;
+      w.tp = (len + 15) / 16 * 16;
       OM_REQUIRE(len <= 65535, "om_a3_task_step: at most 65535 steps per call");
       const int ncand = a3_num_cand_host(len, task->C.delay_frames);
       a3_feat_kernel<FB><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);

@@ -26,6 +26,7 @@ constexpr uint32_t A3_RESET_STREAM = 16;      // oracle/philox.py STREAM_A3_RESE
 struct A3TaskConst {
   int period, delay_frames;
   float fmax, vmax;                   // rewards.py:66 (mass*9.8*0.5), :87 (0.2)
+  float inv_fmax, inv_vmax;           // their fp32 reciprocals (x / xmax as one multiply)
   double target_radius;               // walking_task.py:333
   float near_d2;                      // smallest fp32 d2 with (double)sqrtf(d2) >= target_radius (a3_near_d2)
   double goal_height_ref, deadzone;   // StickFigureA3.py:110; rewards.py:36 (0.01 + 0.05*goal_speed_ref)
@@ -114,7 +115,7 @@ OM_HD void tf3_quat2mat(Q4 q, float (&m)[9]) {
     m[0] = 1.f; m[1] = 0.f; m[2] = 0.f; m[3] = 0.f; m[4] = 1.f; m[5] = 0.f; m[6] = 0.f; m[7] = 0.f; m[8] = 1.f;
     return;
   }
-  const float s = 2.0f / nq;
+  const float s = 2.0f * om_rcp(nq);
   const float X = q.x * s, Y = q.y * s, Z = q.z * s;
   const float wX = q.w * X, wY = q.w * Y, wZ = q.w * Z, xX = q.x * X, xY = q.x * Y, xZ = q.x * Z;
   const float yY = q.y * Y, yZ = q.y * Z, zZ = q.z * Z;
@@ -143,7 +144,7 @@ OM_NOINLINE Q4 a3_root_orient_trig(float qw, float qx, float qy, float qz) {
 // split is ill-conditioned and the literal path is taken.
 OM_HD void a3_root_orient(float qw, float qx, float qy, float qz, float* o) {
   const float nq = fmaf(qw, qw, fmaf(qx, qx, fmaf(qy, qy, qz * qz)));
-  const float s2 = 2.0f / nq;
+  const float s2 = 2.0f * om_rcp(nq);
   const float m00 = 1.0f - (qy * qy + qz * qz) * s2, m10 = (qx * qy + qw * qz) * s2;
   const float cy2 = fmaf(m00, m00, m10 * m10);
   if (!(cy2 > 1e-4f) || !(nq > 1e-12f)) {
@@ -153,7 +154,7 @@ OM_HD void a3_root_orient(float qw, float qx, float qy, float qz, float* o) {
   }
   const float icy = rsqrtf(cy2), c = m00 * icy, sn = m10 * icy;
   const float h = sqrtf(0.5f * (1.0f + fabsf(c)));            // the larger of |cos|, |sin| of yaw/2
-  const float g = sn / (2.0f * h);
+  const float g = 0.5f * sn * om_rcp(h);
   const float chz = c >= 0.f ? h : fabsf(g), shz = c >= 0.f ? g : copysignf(h, sn);
   const float inv = rsqrtf(nq);
   float w = fmaf(chz, qw, shz * qz) * inv, x = fmaf(chz, qx, shz * qy) * inv;
@@ -227,9 +228,9 @@ OM_HD void a3_task_step(const A3TaskConst& C, const A3TaskIn& f, A3TaskRegs& s, 
   float r_frc_c = 1.f, r_vel_c = -1.f, l_frc_c = 1.f, l_vel_c = -1.f;                  // STANDING :83-91
   if (s.mode != A3_STANDING) { r_frc_c = lrow[0]; r_vel_c = lrow[1]; l_frc_c = lrow[2]; l_vel_c = lrow[3]; }
   const float PI4 = 0.78539816339744831f;
-  const float nl = fminf(l_grf, C.fmax) / C.fmax * 2.f - 1.f, nr = fminf(r_grf, C.fmax) / C.fmax * 2.f - 1.f;
+  const float nl = fminf(l_grf, C.fmax) * C.inv_fmax * 2.f - 1.f, nr = fminf(r_grf, C.fmax) * C.inv_fmax * 2.f - 1.f;
   const float frc = (om_tan_q(PI4 * l_frc_c * nl) + om_tan_q(PI4 * r_frc_c * nr)) * 0.5f;      // rewards.py:65-83
-  const float vl = fminf(f.lvel_n, C.vmax) / C.vmax * 2.f - 1.f, vr = fminf(f.rvel_n, C.vmax) / C.vmax * 2.f - 1.f;
+  const float vl = fminf(f.lvel_n, C.vmax) * C.inv_vmax * 2.f - 1.f, vr = fminf(f.rvel_n, C.vmax) * C.inv_vmax * 2.f - 1.f;
   const float vel = (om_tan_q(PI4 * l_vel_c * vl) + om_tan_q(PI4 * r_vel_c * vr)) * 0.5f;      // rewards.py:85-102
   float sh, ch;
   om_sincos(0.5f * tc.th1, &sh, &ch);                                                    // euler2quat(0, 0, theta)
@@ -293,9 +294,9 @@ OM_HD A3Rec a3_task_pre(const A3TaskConst& C, const A3TaskIn& f, int phase, int 
   float r_frc_c = 1.f, r_vel_c = -1.f, l_frc_c = 1.f, l_vel_c = -1.f;                  // STANDING :83-91
   if (mode != A3_STANDING) { r_frc_c = lrow[0]; r_vel_c = lrow[1]; l_frc_c = lrow[2]; l_vel_c = lrow[3]; }
   const float PI4 = 0.78539816339744831f;
-  const float nl = fminf(l_grf, C.fmax) / C.fmax * 2.f - 1.f, nr = fminf(r_grf, C.fmax) / C.fmax * 2.f - 1.f;
+  const float nl = fminf(l_grf, C.fmax) * C.inv_fmax * 2.f - 1.f, nr = fminf(r_grf, C.fmax) * C.inv_fmax * 2.f - 1.f;
   const float frc = (om_tan_q(PI4 * l_frc_c * nl) + om_tan_q(PI4 * r_frc_c * nr)) * 0.5f;      // rewards.py:65-83
-  const float vl = fminf(f.lvel_n, C.vmax) / C.vmax * 2.f - 1.f, vr = fminf(f.rvel_n, C.vmax) / C.vmax * 2.f - 1.f;
+  const float vl = fminf(f.lvel_n, C.vmax) * C.inv_vmax * 2.f - 1.f, vr = fminf(f.rvel_n, C.vmax) * C.inv_vmax * 2.f - 1.f;
   const float vel = (om_tan_q(PI4 * l_vel_c * vl) + om_tan_q(PI4 * r_vel_c * vr)) * 0.5f;      // rewards.py:85-102
   double err = fabs((double)f.root_p.z - (foot_contact ? (double)min_z : 0.0) - C.goal_height_ref);   // rewards.py:27-40
   if (err < C.deadzone) err = 0.0;
@@ -356,9 +357,10 @@ OM_HD uint32_t a3_near_bits(const A3TaskConst& C, V3 lsite, V3 rsite, int ncand,
 // steps, and the new target's bit is first read on the step after the advance.
 OM_HD int a3_cand_needed(int t, int frames0, int delay_frames, int ncand) {
   const int dm = delay_frames > 1 ? delay_frames : 1;
-  const int first = delay_frames - frames0 > 1 ? delay_frames - frames0 : 1;
-  const int n = t >= first ? 2 + (t - first) / dm : 1;
-  return n < ncand ? n : ncand;
+  int reach = delay_frames - frames0 > 1 ? delay_frames - frames0 : 1;     // first step that can read candidate 1
+  int n = 1;
+  while (n < ncand && t >= reach) { ++n; reach += dm; }                    // (no integer division on the hot path)
+  return n;
 }
 struct A3Walk { int j, frames, reached; };       // j = number of target advances since the start of the call
 OM_HD void a3_walk_step(const A3TaskConst& C, uint32_t bits, A3Walk& w) {
@@ -385,13 +387,15 @@ inline int a3_num_cand_host(int n_steps, int delay_frames) {
 
 // (env, t)-parallel again: goal steps (update_goal_steps :184-225), orientation and step terms, total, given the
 // state the machine was in after this step.  Writes goal[8] (obs rows 33..40), terms[2], terms[4], total.
+// `tg`: sin / cos of the two targets' headings (a3_target_trig), computed here or read from the per-candidate table the
+// walk pass leaves (same function of the same angle: identical bits)
 template <class Seq>
 OM_HD void a3_task_post(const A3TaskConst& C, const A3Rec& f, int mode, int t1, int t2, bool reached, const Seq& seq,
-                        float (&goal)[8], float& t2_orient, float& t4_step, float& total) {
+                        const A3TargetTrig* tg_in, float (&goal)[8], float& t2_orient, float& t4_step, float& total) {
   A3TaskRegs s{};
   s.t1 = t1; s.t2 = t2;
   const A3Targets tc = a3_targets_load(s, seq);
-  const A3TargetTrig tg = a3_target_trig(tc);
+  const A3TargetTrig tg = tg_in ? *tg_in : a3_target_trig(tc);
   const float dl = norm3(f.lsite - tc.p1), dr = norm3(f.rsite - tc.p1);
   if (mode != A3_STANDING) {
     float R[9];

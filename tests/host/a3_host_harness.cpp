@@ -12,7 +12,7 @@ using namespace om;
 
 static A3TaskConst make_const(const float* lut6, int period, int delay, double radius, double gh, double dz, float fmax) {
   A3TaskConst C;
-  C.period = period; C.delay_frames = delay; C.fmax = fmax; C.vmax = 0.2f;
+  C.period = period; C.delay_frames = delay; C.fmax = fmax; C.vmax = 0.2f; C.inv_fmax = 1.0f / fmax; C.inv_vmax = 1.0f / 0.2f;
   C.target_radius = radius; C.near_d2 = a3_near_d2(radius); C.goal_height_ref = gh; C.deadzone = dz; C.lut = lut6;
   return C;
 }
@@ -93,7 +93,7 @@ extern "C" void host_a3_rollout_split(const float* lut6, int period, int delay, 
       a3_walk_step(C, near[t], w);
       float goal[8], t2, t4, total;
       a3_task_post(C, a3_rec_load(rec + (size_t)t * A3_NREC, 1), st[4], a3_cand(w.j, t1_0, t2_0, sl),
-                   a3_cand(w.j + 1, t1_0, t2_0, sl), w.reached != 0, SeqHost{seq}, goal, t2, t4, total);
+                   a3_cand(w.j + 1, t1_0, t2_0, sl), w.reached != 0, SeqHost{seq}, nullptr, goal, t2, t4, total);
       std::memcpy(obs + t * A3_NOBS + 33, goal, sizeof goal);
       terms[t * 6 + 2] = t2; terms[t * 6 + 4] = t4;
       reward[t] = total;
