@@ -130,12 +130,15 @@ __global__ void __launch_bounds__(1024) affine_scan_kernel(AffineIn in, int T, i
       } else {
         const uint8_t e = in.f0 ? in.f0[idx] : 0;
         vv[i] = in.v ? in.v[idx] : 0.f;
+        // loaded whether or not the flag needs it: a load that waits for the flag byte costs a second round trip per
+        // step (long_scoreboard was 56 % of this kernel's stalls at T = 64)
+        const float vnx = in.vn ? in.vn[idx] : 0.f;
         // R_t = gamma * Rin + r, where Rin is the bootstrap when a path ends at t
         if (endbuf) {
-          const float boot = (e == 1) ? 0.f : ((e == 2 && in.vn) ? in.vn[idx] : (in.v_last ? in.v_last[env] : 0.f));
+          const float boot = (e == 1) ? 0.f : ((e == 2 && in.vn) ? vnx : (in.v_last ? in.v_last[env] : 0.f));
           a[i] = 0.f; b[i] = fmaf(in.gamma, boot, r);
         } else if (e == 1) { a[i] = 0.f; b[i] = r; }
-        else if (e == 2) { a[i] = 0.f; b[i] = fmaf(in.gamma, in.vn ? in.vn[idx] : 0.f, r); }
+        else if (e == 2) { a[i] = 0.f; b[i] = fmaf(in.gamma, vnx, r); }
         else { a[i] = in.gamma; b[i] = r; }
       }
     }
