@@ -128,3 +128,21 @@ extern "C" void host_a3_reset(const float* lut6, int period, int delay, double r
   for (int k = 33; k < A3_NOBS; ++k) o[k] = 0.f;
   std::memcpy(obs, o, sizeof o);
 }
+
+// Property check of the candidate pruning (a3_cand_needed): walking the state machine over the FULL candidate bits and
+// over bits masked to the candidates declared reachable at each step must give the same (advances, frames, reached) at
+// every step.  Returns the first step at which they differ, or -1.
+extern "C" int host_a3_walk_pruning_check(int delay, int frames0, int reached0, int ncand, int T, const unsigned char* bits) {
+  A3TaskConst C{};
+  C.delay_frames = delay;
+  A3Walk full{0, frames0, reached0}, pruned{0, frames0, reached0};
+  for (int t = 0; t < T; ++t) {
+    const int nc = a3_cand_needed(t, frames0, delay, ncand);
+    const unsigned masked = bits[t] & ((1u << nc) - 1u);
+    a3_walk_step(C, bits[t], full);
+    a3_walk_step(C, masked, pruned);
+    if (full.j != pruned.j || full.frames != pruned.frames || full.reached != pruned.reached) return t;
+    if (full.j >= ncand) return -1;            // beyond the call's candidate budget (the ABI cuts calls before this)
+  }
+  return -1;
+}

@@ -255,6 +255,18 @@ def test_a3_task_device_functions_on_host(a3_model):
             assert_close(ob, oa, "stress obs", rtol=1e-6, atol=1e-6); assert_close(rb, ra, "stress reward", rtol=1e-6, atol=1e-6)
             advanced += int(ia[1] != start[1])
     assert advanced >= 10
+    # candidate pruning: bits of targets that cannot be reached yet are never consulted, for any bit pattern
+    rng = np.random.default_rng(5)
+    for trial in range(4000):
+        delay = int(rng.choice([0, 1, 2, 3, 7, 30]))
+        dm = max(delay, 1)
+        T_ = int(rng.integers(1, 7 * dm + 1))
+        ncand = min(8, 1 + -(-T_ // dm))
+        frames0 = int(rng.integers(0, delay + 4))
+        p_one = rng.choice([0.2, 0.6, 0.95, 1.0])
+        bits = np.packbits((rng.random((T_, 8)) < p_one), axis=1, bitorder="little").ravel().astype(np.uint8)
+        bad = lib.host_a3_walk_pruning_check(delay, frames0, int(rng.integers(0, 2)), ncand, T_, P(np.ascontiguousarray(bits)))
+        assert bad == -1, (delay, frames0, ncand, T_, bad)
 
 
 def test_perfect_dataset_conversion_matches_reference_restatement():
