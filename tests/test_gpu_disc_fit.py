@@ -87,8 +87,7 @@ def test_vail_forward_logit_and_kl_vs_oracle(kernel, monkeypatch):
     import torch
     from olympics_mujoco_b200 import kernels as Kn
     from oracle import learner as L
-    if kernel != "two_ctas_per_sm":
-        monkeypatch.setenv("OM_DISC_VAIL2", "0")
+    monkeypatch.setenv("OM_DISC_VAIL2", "1" if kernel == "two_ctas_per_sm" else "0")
     if kernel == "one_producer_group":
         monkeypatch.setenv("OM_DISC_PG2", "0")
     g = np.load(GOLDEN / "discriminator_ref.npz")
