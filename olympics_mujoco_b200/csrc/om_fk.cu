@@ -5,6 +5,7 @@
 #include "om_fk_generic.cuh"
 #include "om_sinks.cuh"
 #include "gen/fk_unitree_h1.cuh"
+#include "gen/h1_perm.h"
 #include "gen/fk_unitree_h1_parts.cuh"
 #include "gen/fk_stick_figure_a3.cuh"
 
@@ -62,13 +63,27 @@ __device__ __forceinline__ void h1_obs_reward(const H1SpecDev& sp, const float* 
                                               uint8_t* __restrict__ absorbing) {
   const int nq = sp.n_obs_q;
   float head[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k = 2; k < nq; ++k) {
-    const float v = qpos[(size_t)sp.perm[k] * ld + env];
-    if (k < 6) head[k - 2] = v;
-    if (obs) obs[(size_t)(k - 2) * ld + env] = v;
+  // fixed trip count + predicate: the (up to 64) loads issue back to back instead of one round trip per iteration
+  float qv[32], dv[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    if (k < nq) {
+      qv[k] = qpos[(size_t)sp.perm[k] * ld + env];
+      dv[k] = qvel[(size_t)sp.perm[k] * ld + env];
+    }
   }
-  if (obs)
-    for (int k = 0; k < nq; ++k) obs[(size_t)(nq - 2 + k) * ld + env] = qvel[(size_t)sp.perm[k] * ld + env];
+#pragma unroll
+  for (int k = 2; k < 32; ++k) {
+    if (k < nq) {
+      if (k < 6) head[k - 2] = qv[k];
+      if (obs) obs[(size_t)(k - 2) * ld + env] = qv[k];
+    }
+  }
+  if (obs) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+      if (k < nq) obs[(size_t)(nq - 2 + k) * ld + env] = dv[k];
+  }
   if (absorbing) absorbing[env] = (sp.use_absorbing && h1_has_fallen(head[0], head[1], head[2], head[3])) ? 1 : 0;
   if (reward) {
     const float d = prev_x_vel[env] - sp.target;
@@ -76,7 +91,11 @@ __device__ __forceinline__ void h1_obs_reward(const H1SpecDev& sp, const float* 
   }
 }
 
-template <int BLOCK, bool WRITE_FK>
+// STATIC_PERM: the observation spec is UnitreeH1's own (checked on the host against the generated table), so the
+// observation rows are a compile-time permutation of the 34 values the FK loads anyway -- no second, indirectly indexed
+// pass over qpos / qvel (whose runtime-length loop issued its 34 loads one round trip at a time: two thirds of a thread's
+// life at 1M envs).
+template <int BLOCK, bool WRITE_FK, bool STATIC_PERM>
 __global__ void __launch_bounds__(BLOCK) h1_step_kernel(H1SpecDev sp, const float* __restrict__ qpos,
                                                         const float* __restrict__ qvel,
                                                         const float* __restrict__ prev_x_vel, int n, int ld, FkOut o,
@@ -84,15 +103,31 @@ __global__ void __launch_bounds__(BLOCK) h1_step_kernel(H1SpecDev sp, const floa
                                                         uint8_t* __restrict__ absorbing) {
   const int env = blockIdx.x * BLOCK + threadIdx.x;
   if (env >= n) return;
-  h1_obs_reward(sp, qpos, qvel, prev_x_vel, ld, env, obs, reward, absorbing);
-  if (WRITE_FK) {
+  if (!STATIC_PERM) h1_obs_reward(sp, qpos, qvel, prev_x_vel, ld, env, obs, reward, absorbing);
+  if (WRITE_FK || STATIC_PERM) {
     float q[17], qd[17];
 #pragma unroll
     for (int k = 0; k < 17; ++k) q[k] = qpos[(size_t)k * ld + env];
 #pragma unroll
     for (int k = 0; k < 17; ++k) qd[k] = qvel[(size_t)k * ld + env];
-    SoaSink<false> S{o.xpos, o.xquat, o.site_xpos, nullptr, o.cvel, o.com, (size_t)ld, (size_t)env};
-    om_fk_unitree_h1(q, qd, S);
+    if (STATIC_PERM) {
+      if (obs) {
+#pragma unroll
+        for (int k = 2; k < 17; ++k) obs[(size_t)(k - 2) * ld + env] = q[OM_H1_PERM[k]];
+#pragma unroll
+        for (int k = 0; k < 17; ++k) obs[(size_t)(15 + k) * ld + env] = qd[OM_H1_PERM[k]];
+      }
+      if (absorbing)
+        absorbing[env] = (sp.use_absorbing && h1_has_fallen(q[OM_H1_PERM[2]], q[OM_H1_PERM[3]], q[OM_H1_PERM[4]], q[OM_H1_PERM[5]])) ? 1 : 0;
+      if (reward) {
+        const float d = prev_x_vel[env] - sp.target;
+        reward[env] = expf(-(d * d));
+      }
+    }
+    if (WRITE_FK) {
+      SoaSink<false> S{o.xpos, o.xquat, o.site_xpos, nullptr, o.cvel, o.com, (size_t)ld, (size_t)env};
+      om_fk_unitree_h1(q, qd, S);
+    }
   }
 }
 
@@ -253,11 +288,15 @@ extern "C" int om_h1_step(const OmModel* m, const OmH1Spec* spec, const float* q
   if (m->specialised == SPEC_H1) {
     // three threads per env for small batches (measured, CUDA-graph replays: 16384 envs 7.8 vs 9.0 us; 131072 envs 45 vs
     // 40 us; 1M envs 323 vs 303 us); OM_H1_SPLIT = 0 / 1 forces a path (tuning / tests)
+    bool own_spec = sp.n_obs_q == 17;                 // UnitreeH1's own observation spec: compile-time permutation
+    for (int k = 0; k < 17 && own_spec; ++k) own_spec = sp.perm[k] == OM_H1_PERM_HOST[k];
     bool split3 = want_fk && n <= 32768;
     if (const char* f = getenv("OM_H1_SPLIT")) split3 = want_fk && atoi(f) != 0;
     if (split3) h1_step_split_kernel<<<ceil_div(n, 32), dim3(32, 3), 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);
-    else if (want_fk) h1_step_kernel<BLOCK, true><<<grid, BLOCK, 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);
-    else h1_step_kernel<BLOCK, false><<<grid, BLOCK, 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);
+    else if (want_fk && own_spec) h1_step_kernel<BLOCK, true, true><<<grid, BLOCK, 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);
+    else if (want_fk) h1_step_kernel<BLOCK, true, false><<<grid, BLOCK, 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);
+    else if (own_spec) h1_step_kernel<BLOCK, false, true><<<grid, BLOCK, 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);
+    else h1_step_kernel<BLOCK, false, false><<<grid, BLOCK, 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);
     OM_LAUNCHED();
   } else {
     if (want_fk) {
