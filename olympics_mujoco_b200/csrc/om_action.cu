@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(256) mirror_kernel(OmMirrorSpec sp, const floa
                                                      float* __restrict__ y) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
-  for (int i = 0; i < sp.numel; ++i) {
+#pragma unroll 8
+  for (int i = 0; i < sp.numel; ++i) {                  // (the loads do not depend on the stores: x and y never alias)
     const float v = x[(size_t)i * ld + e] * sp.sign[i];
     y[(size_t)sp.index[i] * ld + e] = sp.negate[sp.index[i]] ? -v : v;
   }

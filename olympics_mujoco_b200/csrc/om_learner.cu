@@ -396,10 +396,23 @@ __global__ void __launch_bounds__(128) expert_minibatch_kernel(const float* __re
   const uint32_t epoch = (uint32_t)(b / n_src), i = (uint32_t)(b % n_src);
   const uint32_t idx = om_feistel_perm(i, (uint32_t)n_src, half, om_draw(seed, epoch, draw, EXPERT_STREAM));
   if (idx_out) idx_out[b] = (int32_t)idx;
-  for (int c = 0; c < D; ++c) {
-    const float* row = src + (size_t)c * ld_src + idx;
-    out[(size_t)c * ld_out + b] = row[0];
-    if (out_next) out_next[(size_t)c * ld_out + b] = row[1];
+  for (int c0 = 0; c0 < D; c0 += 8) {                   // eight gathers in flight, not one round trip per row
+    float v[8], w[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (c0 + u < D) {
+        const float* row = src + (size_t)(c0 + u) * ld_src + idx;
+        v[u] = row[0];
+        if (out_next) w[u] = row[1];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (c0 + u < D) {
+        out[(size_t)(c0 + u) * ld_out + b] = v[u];
+        if (out_next) out_next[(size_t)(c0 + u) * ld_out + b] = w[u];
+      }
+    }
   }
 }
 
