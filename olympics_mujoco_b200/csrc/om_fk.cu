@@ -162,6 +162,7 @@ struct SmemComExchange {
   }
 };
 
+template <bool STATIC_PERM>
 __global__ void __launch_bounds__(96) h1_step_split_kernel(H1SpecDev sp, const float* __restrict__ qpos,
                                                            const float* __restrict__ qvel,
                                                            const float* __restrict__ prev_x_vel, int n, int ld, FkOut o,
@@ -179,17 +180,30 @@ __global__ void __launch_bounds__(96) h1_step_split_kernel(H1SpecDev sp, const f
   for (int k = 0; k < 17; ++k) qd[k] = qvel[(size_t)k * ld + e];
   // observation rows (a permuted copy of qpos / qvel), reward and flag: split over the three warps
   if (live) {
-    const int nq = sp.n_obs_q;
-    for (int k = 2 + part; k < nq; k += 3) {
-      if (obs) obs[(size_t)(k - 2) * ld + env] = qpos[(size_t)sp.perm[k] * ld + env];
-    }
-    for (int k = part; k < nq; k += 3) {
-      if (obs) obs[(size_t)(nq - 2 + k) * ld + env] = qvel[(size_t)sp.perm[k] * ld + env];
-    }
-    if (part == 0 && absorbing) {
-      const float y = qpos[(size_t)sp.perm[2] * ld + env], ti = qpos[(size_t)sp.perm[3] * ld + env];
-      const float li = qpos[(size_t)sp.perm[4] * ld + env], ro = qpos[(size_t)sp.perm[5] * ld + env];
-      absorbing[env] = (sp.use_absorbing && h1_has_fallen(y, ti, li, ro)) ? 1 : 0;
+    if (STATIC_PERM) {                               // UnitreeH1's own spec: rows straight out of the registers
+      if (obs) {
+#pragma unroll
+        for (int k = 2; k < 17; ++k)
+          if ((k - 2) % 3 == part) obs[(size_t)(k - 2) * ld + env] = q[OM_H1_PERM[k]];
+#pragma unroll
+        for (int k = 0; k < 17; ++k)
+          if (k % 3 == part) obs[(size_t)(15 + k) * ld + env] = qd[OM_H1_PERM[k]];
+      }
+      if (part == 0 && absorbing)
+        absorbing[env] = (sp.use_absorbing && h1_has_fallen(q[OM_H1_PERM[2]], q[OM_H1_PERM[3]], q[OM_H1_PERM[4]], q[OM_H1_PERM[5]])) ? 1 : 0;
+    } else {
+      const int nq = sp.n_obs_q;
+      for (int k = 2 + part; k < nq; k += 3) {
+        if (obs) obs[(size_t)(k - 2) * ld + env] = qpos[(size_t)sp.perm[k] * ld + env];
+      }
+      for (int k = part; k < nq; k += 3) {
+        if (obs) obs[(size_t)(nq - 2 + k) * ld + env] = qvel[(size_t)sp.perm[k] * ld + env];
+      }
+      if (part == 0 && absorbing) {
+        const float y = qpos[(size_t)sp.perm[2] * ld + env], ti = qpos[(size_t)sp.perm[3] * ld + env];
+        const float li = qpos[(size_t)sp.perm[4] * ld + env], ro = qpos[(size_t)sp.perm[5] * ld + env];
+        absorbing[env] = (sp.use_absorbing && h1_has_fallen(y, ti, li, ro)) ? 1 : 0;
+      }
     }
     if (part == 1 && reward) {
       const float d = prev_x_vel[env] - sp.target;
@@ -286,13 +300,15 @@ extern "C" int om_h1_step(const OmModel* m, const OmH1Spec* spec, const float* q
   constexpr int BLOCK = 128;
   const int grid = ceil_div(n, BLOCK);
   if (m->specialised == SPEC_H1) {
-    // three threads per env for small batches (measured, CUDA-graph replays: 16384 envs 7.8 vs 9.0 us; 131072 envs 45 vs
-    // 40 us; 1M envs 323 vs 303 us); OM_H1_SPLIT = 0 / 1 forces a path (tuning / tests)
+    // three threads per env for small batches (measured, CUDA-graph replays, both with the compile-time observation
+    // permutation: 16384 envs 7.1 vs 7.3 us, 32768 envs 8.2 vs 9.0 us, 65536 envs 20.8 vs 15.4 us); OM_H1_SPLIT = 0 / 1
+    // forces a path (tuning / tests)
     bool own_spec = sp.n_obs_q == 17;                 // UnitreeH1's own observation spec: compile-time permutation
     for (int k = 0; k < 17 && own_spec; ++k) own_spec = sp.perm[k] == OM_H1_PERM_HOST[k];
     bool split3 = want_fk && n <= 32768;
     if (const char* f = getenv("OM_H1_SPLIT")) split3 = want_fk && atoi(f) != 0;
-    if (split3) h1_step_split_kernel<<<ceil_div(n, 32), dim3(32, 3), 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);
+    if (split3 && own_spec) h1_step_split_kernel<true><<<ceil_div(n, 32), dim3(32, 3), 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);
+    else if (split3) h1_step_split_kernel<false><<<ceil_div(n, 32), dim3(32, 3), 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);
     else if (want_fk && own_spec) h1_step_kernel<BLOCK, true, true><<<grid, BLOCK, 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);
     else if (want_fk) h1_step_kernel<BLOCK, true, false><<<grid, BLOCK, 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);
     else if (own_spec) h1_step_kernel<BLOCK, false, true><<<grid, BLOCK, 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);
