@@ -990,9 +990,10 @@ extern "C" int om_disc_forward(const OmDisc* h, const float* s, const float* mea
   const size_t smem = 2 * STAGE_A_BYTES + NSB * STAGE_B2_BYTES + (DISC_MAX_PAR + 4) * sizeof(float) + 12 * 8 + 16;
   DiscArgs a{h->sh, h->image, h->params, s, mean, stdv, eps, reward, d_out, kl_out, n, ld};
   cudaStream_t st = (cudaStream_t)stream;
-  // VAIL: two CTAs per SM for long launches (1M samples: 0.839 vs 0.852 ms), the two-producer-group kernel below for short
-  // ones, where its faster single tile counts (65536 samples: 73.7 vs 76.3 us)
-  int two = h->sh.kind == 0 && ntiles >= 8 * sms;
+  // VAIL: two CTAs per SM.  (The two-producer-group kernel below is 3 % faster at 65536 samples when timed alone -- 73.4
+  // vs 76.3 us -- but 15 % slower inside bench.py's process, after the large-buffer measurements: 88.8 us; the two-CTA
+  // kernel reads 76-78 us in both settings, so it stays the default.)
+  int two = h->sh.kind == 0;
   if (const char* f = getenv("OM_DISC_VAIL2")) two = h->sh.kind == 0 && atoi(f) != 0;      // tuning / test hook: force either
   if (two) {
     const size_t smem2 = V2_NS * V2_STAGE_BYTES + (V2_NPAR + 3 + 2 * DISC_IN) * sizeof(float) + 3 * V2_NS * 8 + 16;
