@@ -111,7 +111,7 @@ def run_reference(args):
             "cpu_baseline": {"value": res["value"], "unit": "env-steps/s", "cores": res["cores"], "kind": res["kind"],
                              "sample": res["sample"]},
             "e2e": {"value": res["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------- configs[4]
@@ -364,12 +364,26 @@ def run_ours(args):
             res = cpu_baseline.run(model, table, steps=1, warmup=0, horizon=T, budget_s=args.cpu_budget)
             line["cpu_baseline"] = {"value": res["value"], "unit": "env-steps/s", "cores": res["cores"],
                                     "kind": res["kind"], "sample": res["sample"]}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -382,6 +396,11 @@ def main():
     ap.add_argument("--nccl", action="store_true", help="use NCCL for the moment all-reduce instead of the NVLink mailbox kernel")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: whatever libraries print at the C level (NCCL's version banner under
+    # NCCL_DEBUG=VERSION/WARN ...) is sent to stderr for the duration of the run
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
