@@ -10,6 +10,7 @@ static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 #include "fk_stick_figure_a3.cuh"
 #include "fk_pos_stick_figure_a3.cuh"
 #include "fk_unitree_h1_parts.cuh"
+#include "fk_stick_figure_a3_parts.cuh"      // test-only: the partitioner on a free-joint-rooted tree
 
 struct HostSink {
   static constexpr bool want_site_xmat = true;
@@ -86,6 +87,23 @@ extern "C" void host_fk_h1_parts(const float* q, const float* qd, int n, float* 
       om_fk_unitree_h1_part0(qq, dd, S, X0);
       om_fk_unitree_h1_part1(qq, dd, S, X1);
       om_fk_unitree_h1_part2(qq, dd, S, X2);
+    }
+  }
+}
+
+// the same two-pass emulation for a three-way split of the StickFigureA3 tree (not used by any kernel: it checks the
+// part generator on a model whose root is a free joint and whose subtrees are unbalanced)
+extern "C" void host_fk_a3_parts(const float* q, const float* qd, int n, float* xp, float* xq, float* sp, float* sm,
+                                 float* cv, float* cm) {
+  for (int e = 0; e < n; ++e) {
+    float qq[25], dd[24], sum[3][3];
+    std::memcpy(qq, q + 25*e, sizeof qq); std::memcpy(dd, qd + 24*e, sizeof dd);
+    HostSink S{xp + 51*e, xq + 68*e, sp + 6*e, sm + 18*e, cv + 102*e, cm + 3*e};
+    for (int pass = 0; pass < 2; ++pass) {
+      HostExchange X0{sum, 0, pass == 1}, X1{sum, 1, pass == 1}, X2{sum, 2, pass == 1};
+      om_fk_stick_figure_a3_part0(qq, dd, S, X0);
+      om_fk_stick_figure_a3_part1(qq, dd, S, X1);
+      om_fk_stick_figure_a3_part2(qq, dd, S, X2);
     }
   }
 }

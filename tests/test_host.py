@@ -53,13 +53,18 @@ def test_generated_fk_matches_oracle_on_host(h1_model, a3_model, h1_states):
     assert sorted(b for p in parts for b in p) == list(range(h1_model.nbody))      # a partition of the bodies
     (d / "fk_unitree_h1_parts.cuh").write_text("".join(
         codegen.generate_fk(h1_model, f"om_fk_unitree_h1_part{k}", part=p) for k, p in enumerate(parts)))
+    parts_a3 = codegen.split_parts(a3_model, 3)
+    assert sorted(b for p in parts_a3 for b in p) == list(range(a3_model.nbody))
+    (d / "fk_stick_figure_a3_parts.cuh").write_text("".join(
+        codegen.generate_fk(a3_model, f"om_fk_stick_figure_a3_part{k}", part=p) for k, p in enumerate(parts_a3)))
     subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-I", str(d), "-I", str(ROOT / "olympics_mujoco_b200/csrc"),
                            str(ROOT / "tests/host/fk_host_harness.cpp"),
                            "-o", str(d / "h.so")])
     lib = ctypes.CDLL(str(d / "h.so"))
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     for model, fn, (q, v) in ((h1_model, "host_fk_h1", h1_states), (h1_model, "host_fk_h1_parts", h1_states),
-                              (a3_model, "host_fk_a3", a3_random_states(a3_model, 128, seed=8))):
+                              (a3_model, "host_fk_a3", a3_random_states(a3_model, 128, seed=8)),
+                              (a3_model, "host_fk_a3_parts", a3_random_states(a3_model, 128, seed=10))):
         n = q.shape[0]
         q32, v32 = np.ascontiguousarray(q, np.float32), np.ascontiguousarray(v, np.float32)
         xp = np.zeros((n, model.nbody, 3), np.float32); xq = np.zeros((n, model.nbody, 4), np.float32)
