@@ -146,3 +146,20 @@ extern "C" int host_a3_walk_pruning_check(int delay, int frames0, int reached0, 
   }
   return -1;
 }
+
+// closed-form root roll / pitch quaternion (a3_root_orient) next to the literal quat2euler -> euler2quat path
+extern "C" void host_a3_root_orient(const float* q, int n, float* closed, float* literal) {
+  for (int i = 0; i < n; ++i) {
+    a3_root_orient(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3], closed + 4 * i);
+    const Q4 r = a3_root_orient_trig(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
+    literal[4 * i] = r.w; literal[4 * i + 1] = r.x; literal[4 * i + 2] = r.y; literal[4 * i + 3] = r.z;
+  }
+}
+
+// bounded-range trigonometry of om_math.cuh
+extern "C" void host_trig(const float* x, int n, float* s, float* c, float* t) {
+  for (int i = 0; i < n; ++i) {
+    om_sincos(x[i], s + i, c + i);
+    t[i] = om_tan_q(x[i]);
+  }
+}

@@ -260,6 +260,33 @@ def test_a3_task_device_functions_on_host(a3_model):
             assert_close(ob, oa, "stress obs", rtol=1e-6, atol=1e-6); assert_close(rb, ra, "stress reward", rtol=1e-6, atol=1e-6)
             advanced += int(ia[1] != start[1])
     assert advanced >= 10
+    # bounded-range sin / cos / tan (om_math.cuh) against float64 libm: joint-angle range, many periods, the libm fallback
+    rng = np.random.default_rng(21)
+    xs = np.concatenate([rng.uniform(-3.2, 3.2, 200000), rng.uniform(-1000, 1000, 100000), rng.uniform(-1e5, 1e5, 50000),
+                         [0.0, -0.0, 1e6, -3e7, np.pi / 2, -np.pi]]).astype(np.float32)
+    sn, cs, tn = (np.zeros(xs.size, np.float32) for _ in range(3))
+    lib.host_trig(P(xs), xs.size, P(sn), P(cs), P(tn))
+    x64 = xs.astype(np.float64)
+    assert np.abs(sn - np.sin(x64)).max() < 1.5e-7 and np.abs(cs - np.cos(x64)).max() < 1.5e-7
+    small = (np.abs(x64) <= 0.7854) & (np.abs(x64) > 1e-30)
+    assert np.abs(tn[small] / np.tan(x64[small]) - 1.0).max() < 3e-7
+    small = np.abs(x64) <= 0.7854
+    assert_close(tn[~small], np.tan(x64[~small]), "tan fallback", rtol=2e-6, atol=1e-6)
+    # closed-form root roll / pitch quaternion against the literal quat2euler -> euler2quat path and the float64 oracle:
+    # random orientations of any scale and sign, yaw near +-pi, pitch up to 80 degrees
+    from oracle import tf3 as T3
+    rng = np.random.default_rng(12)
+    m = 4000
+    roll, pitch, yaw = rng.uniform(-3.1, 3.1, m), rng.uniform(-1.4, 1.4, m), rng.uniform(-np.pi, np.pi, m)
+    yaw[:50] = np.pi - 1e-4 * rng.random(50); yaw[50:100] = -np.pi + 1e-4 * rng.random(50)
+    quat = np.array([T3.euler2quat(r, p_, y) for r, p_, y in zip(roll, pitch, yaw)])
+    quat *= (rng.uniform(0.5, 2.0, m) * rng.choice([-1.0, 1.0], m))[:, None]           # unnormalised, either sign
+    q32 = np.ascontiguousarray(quat, np.float32)
+    closed, literal = np.zeros((m, 4), np.float32), np.zeros((m, 4), np.float32)
+    lib.host_a3_root_orient(P(q32), m, P(closed), P(literal))
+    want = np.array([T3.euler2quat(*T3.quat2euler(qq)[:2], 0.0) for qq in q32.astype(np.float64)])
+    assert_close(literal, want, "literal path vs oracle", rtol=0, atol=2e-6)
+    assert_close(closed, want, "closed form vs oracle", rtol=0, atol=2e-6)
     # candidate pruning: bits of targets that cannot be reached yet are never consulted, for any bit pattern
     rng = np.random.default_rng(5)
     for trial in range(4000):
