@@ -221,7 +221,7 @@ OM_HD void a3_task_step(const A3TaskConst& C, const A3TaskIn& f, A3TaskRegs& s, 
     obs[33 + i] = walk ? fmaf(R[0], d.x, fmaf(R[3], d.y, R[6] * d.z)) : 0.f;
     obs[35 + i] = walk ? fmaf(R[1], d.x, fmaf(R[4], d.y, R[7] * d.z)) : 0.f;
     obs[37 + i] = walk ? fmaf(R[2], d.x, fmaf(R[5], d.y, R[8] * d.z)) : 0.f;
-    obs[39 + i] = (walk && cy > A3_EPS4) ? atan2f(b, a) : 0.f;
+    obs[39 + i] = (walk && cy > A3_EPS4) ? om_atan2(b, a) : 0.f;
   }
 
   // ---- calc_reward :74-110
@@ -409,7 +409,7 @@ OM_HD void a3_task_post(const A3TaskConst& C, const A3Rec& f, int mode, int t1, 
       goal[0 + i] = fmaf(R[0], d.x, fmaf(R[3], d.y, R[6] * d.z));
       goal[2 + i] = fmaf(R[1], d.x, fmaf(R[4], d.y, R[7] * d.z));
       goal[4 + i] = fmaf(R[2], d.x, fmaf(R[5], d.y, R[8] * d.z));
-      goal[6 + i] = cy > A3_EPS4 ? atan2f(b, a) : 0.f;
+      goal[6 + i] = cy > A3_EPS4 ? om_atan2(b, a) : 0.f;
     }
   } else {
 #pragma unroll
@@ -468,7 +468,7 @@ OM_HD void a3_task_reset(const A3TaskConst& C, const A3Feat& f, const float (&u)
   float R[9];
   tf3_quat2mat(f.root_q, R);                                          // transform_sequence :113-135
   const float cyy = sqrtf(fmaf(R[0], R[0], R[3] * R[3]));
-  const float yaw = cyy > A3_EPS4 ? atan2f(R[3], R[0]) : 0.f;
+  const float yaw = cyy > A3_EPS4 ? om_atan2(R[3], R[0]) : 0.f;
   float sy, cy;
   om_sincos(yaw, &sy, &cy);
   const float mx = (f.lfoot_p.x + f.rfoot_p.x) * 0.5f, my = (f.lfoot_p.y + f.rfoot_p.y) * 0.5f;

@@ -163,3 +163,6 @@ extern "C" void host_trig(const float* x, int n, float* s, float* c, float* t) {
     t[i] = om_tan_q(x[i]);
   }
 }
+extern "C" void host_atan2(const float* y, const float* x, int n, float* r) {
+  for (int i = 0; i < n; ++i) r[i] = om_atan2(y[i], x[i]);
+}

@@ -272,6 +272,11 @@ def test_a3_task_device_functions_on_host(a3_model):
     assert np.abs(tn[small] / np.tan(x64[small]) - 1.0).max() < 3e-7
     small = np.abs(x64) <= 0.7854
     assert_close(tn[~small], np.tan(x64[~small]), "tan fallback", rtol=2e-6, atol=1e-6)
+    ya = np.concatenate([rng.normal(0, 1, 300000), [0.0, -0.0, 0.0, 1.0, -1.0, 1e-20, 3.0, -0.0]]).astype(np.float32)
+    xa = np.concatenate([rng.normal(0, 1, 300000), [1.0, -1.0, 0.0, 0.0, 0.0, 1e-25, -1e-20, -2.0]]).astype(np.float32)
+    ra = np.zeros(ya.size, np.float32)
+    lib.host_atan2(P(ya), P(xa), ya.size, P(ra))
+    assert np.abs(ra - np.arctan2(ya.astype(np.float64), xa.astype(np.float64))).max() < 4e-7        # 1.3 ulp at pi
     # closed-form root roll / pitch quaternion against the literal quat2euler -> euler2quat path and the float64 oracle:
     # random orientations of any scale and sign, yaw near +-pi, pitch up to 80 degrees
     from oracle import tf3 as T3
