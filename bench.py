@@ -26,19 +26,40 @@ sys.path.insert(0, str(ROOT))
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 BYTES_PER_ENV_STEP = 1517          # SURVEY.md section 8(d), config 2 (algorithmic HBM bytes of the playback step)
-# dram__bytes_read.sum + dram__bytes_write.sum of play_h1_tp_kernel at 4096 envs x 500 steps, one `ncu --set full`
-# capture (profiles/r01d_play_h1_tp_raw.csv: 12.2 MB read + 2492.5 MB written per launch)
-NCU_TRAFFIC_BYTES_4096x500 = 12.228e6 + 2492.518e6
+# dram__bytes_read.sum + dram__bytes_write.sum of play_h1_tp_kernel at 4096 envs x 500 steps come from the newest committed
+# `ncu --set full` capture of that launch shape (first file that exists); the line names the file and its hash
+TRAFFIC_PROFILES = ("profiles/r02_play_h1_tp_raw.csv", "profiles/r01d_play_h1_tp_raw.csv")
 N_ENVS = 4096
 HORIZON = 500
 GAMMA, LAM = 0.99, 0.97
 
 
 def workload_config(n, T):
-    """`config` of BOTH arms (the reference arm adds `sample`)."""
+    """`config` of BOTH arms, key for key (the reference arm's bounded sample is in its `cpu_baseline.sample`)."""
     return {"workload": f"UnitreeH1 walk playback rollout {n} envs x {T} steps per GPU + GAE (configs[1])",
             "envs_per_gpu": n, "horizon": T, "l2": "rollout outputs (2.5 GB/step) exceed the 126 MB L2",
             "gamma": GAMMA, "lam": LAM}
+
+
+def ncu_traffic(kernel_substr="play_h1_tp_kernel"):
+    """(bytes per launch, "file@sha16") of the playback kernel from the committed ncu summary, or (None, None)."""
+    import csv
+    import hashlib
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for rel in TRAFFIC_PROFILES:
+        f = ROOT / rel
+        if not f.exists():
+            continue
+        rows = list(csv.reader(open(f)))
+        hdr, units = rows[0], rows[1]
+        try:
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            row = next(r for r in rows[2:] if kernel_substr in r[0])
+            total = float(row[ir]) * scale[units[ir]] + float(row[iw]) * scale[units[iw]]
+        except (ValueError, StopIteration, KeyError):
+            continue
+        return total, f"{rel}@{hashlib.sha256(f.read_bytes()).hexdigest()[:16]}"
+    return None, None
 
 
 def measured_peaks():
@@ -107,7 +128,7 @@ def run_reference(args):
             "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args.envs, args.horizon), sample=res["sample"]),
+            "config": workload_config(args.envs, args.horizon),
             "cpu_baseline": {"value": res["value"], "unit": "env-steps/s", "cores": res["cores"], "kind": res["kind"],
                              "sample": res["sample"]},
             "e2e": {"value": res["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -133,11 +154,11 @@ def sharded_1m(rank, world, local, table, rollouts=4, warmup=2):
 
     def rollout():
         mom.zero_()
-        for _ in range(calls):
-            out = env.play_trajectory_from_velocity(n_episodes=1, n_steps_per_episode=t_call, render=False, out=roll)
-            Kn.moments(out["obs"], out=mom)
+        for c in range(calls):                                 # one 64-step rollout = four calls into the same buffers; the
+            env.play_trajectory_from_velocity(n_episodes=1, n_steps_per_episode=t_call, render=False, out=roll,
+                                              continue_episode=c > 0, obs_moments=mom)   # moments: fused into the kernel
         D.all_reduce_moments(mom)                              # NVLink mailbox kernel (or NCCL), no-op at world 1
-        return D.mean_std_from_moments(mom, "ppo_obs")
+        return Kn.moment_stats(mom, "ppo_obs")                 # one kernel
 
     for _ in range(warmup):
         rollout()
@@ -168,6 +189,50 @@ def sharded_1m(rank, world, local, table, rollouts=4, warmup=2):
                          "note": "whole rollout incl. the moments pass and the all-reduce, not the kernel alone"}}
 
 
+def collective_check(rank, world, use_mailbox):
+    """Once per run at N > 1: a known per-rank vector (small integers and dyadic fractions: every partial sum is exact in
+    float64, so the order of the additions cannot matter) is all-reduced through the route the bench uses (the NVLink
+    mailbox kernel) AND through NCCL; both must be bit-equal to each other and to the closed form, on every rank."""
+    import torch
+    import torch.distributed as dist
+    from olympics_mujoco_b200 import distributed as D
+    k = torch.arange(68, dtype=torch.float64, device="cuda")
+    x = (rank + 1) * (k + 1) + (rank % 4) * 0.25 + k * 2.0 ** -20
+    expect = (world * (world + 1) / 2) * (k + 1) + sum((r % 4) * 0.25 for r in range(world)) + world * k * 2.0 ** -20
+    via_nccl = x.clone()
+    dist.all_reduce(via_nccl, op=dist.ReduceOp.SUM)
+    ok = torch.equal(via_nccl, expect)
+    if use_mailbox:
+        for _ in range(3):                                     # both parity slots
+            via_mailbox = D.all_reduce_moments(x.clone())
+            ok = ok and torch.equal(via_mailbox, via_nccl)
+        torch.cuda.synchronize()
+        ok = ok and not D._mailbox.timed_out()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return "ok" if int(flag) == 1 else "MISMATCH"
+
+
+def compact(d):
+    """One side measurement -> the few numbers the record needs (the whole JSON line must stay short enough to survive a
+    truncated stdout tail)."""
+    if isinstance(d, list):
+        return [compact(x) for x in d]
+    if not isinstance(d, dict) or "error" in d:
+        return d
+    keep = {}
+    for k in ("value", "unit", "ms", "ms_per_step", "ms_per_rollout", "task_kernel_ms", "h1_step_kernel_ms", "live_step_ms", "live_step_eager_ms", "live_step_frac",
+              "eager_python_loop_ms_per_step", "envs_per_gpu", "scaling", "net"):
+        if k in d:
+            keep[k] = round(d[k], 5) if isinstance(d[k], float) and abs(d[k]) < 1e6 else d[k]
+    r = d.get("roofline")
+    if r:
+        for k in ("frac", "frac_executed", "frac_dram", "peak", "bound"):
+            if k in r:
+                keep[k] = round(r[k], 4) if isinstance(r[k], float) else r[k]
+    return keep
+
+
 # ------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -189,12 +254,13 @@ def run_ours(args):
     except Exception:
         pass
     from olympics_mujoco_b200 import distributed as D
-    collective = "none"
+    collective, coll_check = "none", None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         # the path's only exchange: 68 float64 per rollout.  One small kernel over NVLink peer memory (csrc/om_mailbox.cu);
         # NCCL if the mailboxes cannot be mapped (decided collectively, so every rank takes the same route)
         collective = "nvlink_mailbox" if (not args.nccl and D.enable_mailbox(True)) else "nccl"
+        coll_check = collective_check(rank, world, collective == "nvlink_mailbox")
     n, T = args.envs, args.horizon
 
     model, table = build_table()
@@ -210,18 +276,22 @@ def run_ours(args):
     ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
 
+    mom_adv, mom_obs = mom[:3], mom[3:]
+
     def hot_step(i=None, vals=values, roll=roll):
+        mom.zero_()
         if i is not None:
             ev_k0[i].record()
-        out = env.play_trajectory_from_velocity(n_episodes=1, n_steps_per_episode=T, render=False, out=roll)
+        # one call = the reference's call: reset() at its start (inside the kernel), 500 steps, end-of-episode reset; the
+        # observation moments (S1) are accumulated by the playback kernel itself
+        out = env.play_trajectory_from_velocity(n_episodes=1, n_steps_per_episode=T, render=False, out=roll,
+                                                obs_moments=mom_obs)
         if i is not None:
             ev_k1[i].record()
         vt, adv = Kn.gae(out["reward"], vals[:-1], vals[1:], out["fallen"], last, GAMMA, LAM)
-        mom.zero_()
-        Kn.moments_scalar(adv, out=mom[:3])
-        Kn.moments(out["obs"], out=mom[3:])
+        Kn.moments_scalar(adv, out=mom_adv)
         D.all_reduce_moments(mom)                              # the path's only exchange (520 B + 24 B, float64)
-        stats = Kn.adv_stats(mom[:3], unbiased=False, eps=1e-8)
+        stats = Kn.adv_stats(mom_adv, unbiased=False, eps=1e-8)
         Kn.normalize(adv, stats, out=adv)
         return out, vt, adv
 
@@ -314,30 +384,39 @@ def run_ours(args):
     if collective == "nvlink_mailbox":
         bad = torch.tensor([1.0 if D._mailbox.timed_out() else 0.0], device="cuda")
         dist.all_reduce(bad, op=dist.ReduceOp.MAX)
-        if float(bad) > 0:                                      # a peer never delivered: the sums (not the timing) are void
+        if float(bad) > 0:                                      # a peer never delivered: that round's sums are NaN there
             collective = "nvlink_mailbox (a round timed out)"
+            coll_check = "TIMEOUT"
             sys.stderr.write("bench: the mailbox all-reduce timed out on some rank\n")
 
     if rank == 0:
         peaks, which = measured_peaks()
         kernel_ms = float(kms)
         achieved = BYTES_PER_ENV_STEP * n * T / (kernel_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic() if (n, T) == (4096, 500) else (None, None)
         line = {"metric": "env-steps/sec (FK+obs+reward+GAE)", "value": value, "unit": "env-steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(workload_config(n, T), collective=collective),
+                "config": workload_config(n, T), "collective": collective, "collective_check": coll_check,
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": world * n * T / (float(e2e_ms) * 1e-3), "unit": "env-steps/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                # frac: ALGORITHMIC bytes (1517 B/env-step, of which the 280 B of trajectory-table and per-env
+                # state reads are L2 hits) / kernel time / measured copy peak; frac_dram: the DRAM bytes ncu counted for this
+                # launch shape / the same kernel time / the same peak -- the fraction of the HBM pins actually used
                 "roofline": {"bound": "hbm", "kernel": "play_snapshot_kernel + play_h1_tp_kernel (one 500-step episode incl. its end-of-episode reset)", "achieved": achieved,
                              "peak": peaks["hbm_gbs"], "peak_source": which, "unit": "GB/s",
                              "frac": achieved / peaks["hbm_gbs"],
-                             "traffic": NCU_TRAFFIC_BYTES_4096x500 if (n, T) == (4096, 500) else None,
+                             "frac_dram": (traffic / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if traffic else None,
+                             "traffic": traffic, "traffic_source": traffic_src,
                              "bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": kernel_ms}}
+        if sharded is not None:
+            # configs[4] (strong scaling over the ranks), compact and EARLY in the line so that it survives a cut tail
+            line["sharded_1m"] = compact(sharded)
         if not args.no_other_configs:
             # the other BASELINE.json configs on this GPU (parity cases; measured here so that one file carries them)
             sys.path.insert(0, str(ROOT / "tools"))
-            other = {"h1_1m_envs_sharded": sharded}
+            other = {}
             try:
                 import bench_a3
                 other["a3_ppo_rollout_16384x64"] = bench_a3.measure(steps=10, warmup=3)
@@ -356,7 +435,9 @@ def run_ours(args):
                 other["disc_reward_1048576"] = bench_disc.measure(envs=1 << 20, steps=10, warmup=3)   # steady state
             except Exception as e:
                 other["disc_error"] = repr(e)
-            line["other_configs"] = other
+            if args.verbose_other:
+                sys.stderr.write(json.dumps(other) + "\n")      # the full dictionaries, for the profiles/ record
+            line["other_configs"] = {k: compact(v) for k, v in other.items()}
         if not args.no_cpu_baseline:
             if full_affinity is not None:
                 os.sched_setaffinity(0, full_affinity)          # the CPU baseline uses every host core
@@ -364,6 +445,15 @@ def run_ours(args):
             res = cpu_baseline.run(model, table, steps=1, warmup=0, horizon=T, budget_s=args.cpu_budget)
             line["cpu_baseline"] = {"value": res["value"], "unit": "env-steps/s", "cores": res["cores"],
                                     "kind": res["kind"], "sample": res["sample"]}
+            # the reference-shaped Python loop, one core and one process per core
+            try:
+                one = cpu_baseline.python_loop(model, table, horizon=T)
+                many = cpu_baseline.python_multiproc(horizon=T)
+                line["cpu_baseline"]["python_loop_1core"] = {"value": one["value"], "sample": one["sample"]}
+                line["cpu_baseline"]["python_loop_multiproc"] = {"value": many["value"], "cores": many["cores"],
+                                                                 "sample": many["sample"]}
+            except Exception as e:
+                line["cpu_baseline"]["python_loop_error"] = repr(e)
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -395,6 +485,7 @@ def main():
     ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--nccl", action="store_true", help="use NCCL for the moment all-reduce instead of the NVLink mailbox kernel")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--verbose-other", action="store_true", help="full side-measurement dictionaries on stderr")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: whatever libraries print at the C level (NCCL's version banner under
     # NCCL_DEBUG=VERSION/WARN ...) is sent to stderr for the duration of the run

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define OM_ABI_VERSION 1
+#define OM_ABI_VERSION 2
 
 /* mjtJoint values (mujoco==2.3.6) */
 #define OM_JNT_FREE 0
@@ -43,6 +43,10 @@ int om_abi_version(void);
 /* number of kernels launched by this library since load / since om_reset_launch_count() */
 long long om_launch_count(void);
 void om_reset_launch_count(void);
+/* Tuning / test hook: force a kernel variant ("play_chunk", "h1_split", "a3_split", "serial_scan", "disc_vail2",
+ * "disc_pg2"; -1 / 0 = automatic).  The same knobs are initialised ONCE, when the library is loaded, from the OM_PLAY_CHUNK,
+ * OM_H1_SPLIT, ... environment variables; no launch path calls getenv. */
+int om_debug_set(const char* knob, int value);
 
 /* ------------------------------------------------------------------------------------------------
  * Model constants.  Replaces the mjModel produced by MuJoCo's MJCF compiler
@@ -149,14 +153,17 @@ int om_traj_next(const OmTraj* t, uint64_t seed, uint32_t env_id0, int auto_rese
 
 /* ------------------------------------------------------------------------------------------------
  * Fused playback: LocoEnvBase.play_trajectory_from_velocity (loco_env_base.py:444-560) for n envs,
- * one episode of n_steps steps per call (call once per episode; the end-of-episode reset :555-557 is
- * performed when end_episode_reset != 0).  Per step: Euler step of the 17 coordinates (:515-519),
+ * one episode of n_steps steps per call (call once per episode).  end_episode_reset is a bit set: OM_PLAY_END_RESET
+ * performs the end-of-episode reset (:555-557), OM_PLAY_START_RESET the reset() with which every call of the reference
+ * begins (:481; sample = get_current_sample(), curr_qpos = sample[:len_qpos]) -- inside the same launches.  Per step: Euler step of the 17 coordinates (:515-519),
  * set_sim_state (:659-684), K1, next sample / wrap reset (:532-537), observation from the next sample
  * (:539), has_fallen (:541), TargetVelocityReward on the previous observation.
  * State in/out: traj_no, step_no, reset_count, xy_off, curr_qpos [n_obs_q][ld] (spec order, float64),
  * pending [K][ld] (the `sample` variable of the loop), prev_x_vel [ld].
  * Outputs (any may be NULL), time-major [n_steps][C][ld]: xpos, xquat, site_xpos, cvel, obs, reward,
  * fallen (uint8), traj_no_t / step_no_t (int32 state after each step). */
+#define OM_PLAY_END_RESET 1
+#define OM_PLAY_START_RESET 2
 typedef struct OmPlayState {
   int32_t* traj_no; int32_t* step_no; uint32_t* reset_count; double* xy_off;
   double* curr_qpos; float* pending; float* prev_x_vel;
@@ -164,6 +171,8 @@ typedef struct OmPlayState {
 typedef struct OmPlayOut {
   float* xpos; float* xquat; float* site_xpos; float* cvel; float* obs; float* reward;
   uint8_t* fallen; int32_t* traj_no_t; int32_t* step_no_t;
+  double* obs_moments;   /* [65] float64 or NULL: S1 fused into the playback -- sum[32], sumsq[32] and count of the emitted
+                            observations are ADDED (om_moments layout and semantics: zero it first, all-reduce it after) */
 } OmPlayOut;
 int om_h1_play_from_velocity(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, uint64_t seed,
                              uint32_t env_id0, double dt, int n_steps, int end_episode_reset,
@@ -174,6 +183,26 @@ int om_h1_play_from_velocity(const OmModel* m, const OmH1Spec* spec, const OmTra
 int om_h1_play_trajectory(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, uint64_t seed, uint32_t env_id0,
                           int n_steps, int end_episode_reset, const OmPlayState* state, const OmPlayOut* out, int n, int ld,
                           void* stream);
+
+/* Fused LIVE step: one env step of a trajectory-driven rollout in one kernel -- get_next_sample with the wrap -> reset
+ * policy (trajectory.py:389-401, loco_env_base.py:534-537), set_sim_state (:659-684), K1, _create_observation
+ * (:737-767), has_fallen (UnitreeH1.py:162-203) and TargetVelocityReward on the PREVIOUS observation (mushroom_rl
+ * MuJoCo.step: reward(self._obs, action, cur_obs, absorbing), then self._obs = cur_obs).  Replaces the three launches
+ * om_traj_next -> om_set_sim_state -> om_h1_step, whose sample and qpos / qvel round-tripped through HBM.
+ * State in/out: traj_no, step_no [n], reset_count [n], xy_off [2][ld] float64, prev_x_vel [ld] (row x_vel_idx of the
+ * previous observation in, of this step's observation out).  Outputs, single step, any may be NULL: qpos / qvel [17][ld]
+ * (the MjData mirrors), xpos [63][ld], xquat [84][ld], site_xpos [3][ld], cvel [126][ld], obs [32][ld], reward [ld],
+ * absorbing [ld] uint8, wrapped [ld] uint8 (1 where the trajectory wrapped and the env was reset).  Safe to capture in a
+ * CUDA graph (no host synchronisation, no allocation). */
+typedef struct OmLiveState {
+  int32_t* traj_no; int32_t* step_no; uint32_t* reset_count; double* xy_off; float* prev_x_vel;
+} OmLiveState;
+typedef struct OmLiveOut {
+  float* qpos; float* qvel; float* xpos; float* xquat; float* site_xpos; float* cvel;
+  float* obs; float* reward; uint8_t* absorbing; uint8_t* wrapped;
+} OmLiveOut;
+int om_h1_live_step(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, uint64_t seed, uint32_t env_id0,
+                    const OmLiveState* state, const OmLiveOut* out, int n, int ld, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K2 (A3 flavour): the tail of StickFigureA3.step (real_humanoid_robots/StickFigureA3.py:187-202) after
@@ -299,6 +328,14 @@ int om_moments(const float* x, int rows, int C, int n, int ld, double* out, void
 /* stats[0] = mean, stats[1] = std + eps from a one-component moment buffer [sum, sumsq, count] (device);
  * unbiased != 0 -> torch.std (ppo.py:336, eps 1e-5), 0 -> np.std (gail_TRPO.py:128, eps 1e-8). */
 int om_adv_stats(const double* moments, int unbiased, double eps, double* stats, void* stream);
+/* mean[C] and denominator[C] (float64, and / or float32 copies; any output may be NULL) from a moment buffer
+ * [sum[C], sumsq[C], count] on the device -- one small kernel instead of a chain of host-framework ops:
+ *   kind 0 "standardizer"  sqrt(max(E[x^2] - mean^2, 1e-2))                 networks.py:76-81
+ *   kind 1 "ppo_obs"       sqrt(max(var, 0) + 1e-8)                         rl/envs/normalize.py:48
+ *   kind 2 "adv_ppo"       sqrt(max(var, 0) * n / (n - 1)) + 1e-5           rl/algos/ppo.py:336 (torch.std, unbiased)
+ *   kind 3 "adv_gail"      sqrt(max(var, 0)) + 1e-8                         gail_TRPO.py:128 (np.std) */
+int om_moment_stats(const double* moments, int C, int kind, double* mean, double* denom, float* mean32, float* denom32,
+                    void* stream);
 /* y = (x - mean) / denom element-wise for a [rows][ld] array with device scalars stats[0]=mean,
  * stats[1]=denom (advantage normalisation); in place allowed. */
 int om_normalize(const float* x, const double* stats, int rows, int n, int ld, float* y, void* stream);
@@ -349,13 +386,17 @@ int om_ppo_loss_stats(const float* logp, const float* old_logp, const float* adv
  * gail_TRPO.py:128, networks.py:76-81).  create: allocates this rank's mailbox and returns its CUDA IPC handle
  * (OM_MAILBOX_HANDLE_BYTES bytes) for the caller to all-gather by any means; connect: maps every peer's mailbox;
  * allreduce: one kernel on `stream` (stores to every mailbox, system-scope flags, rank-ordered sum: identical bits on
- * every rank; in and out are device pointers, may alias).  Every rank must issue the same sequence of calls.  A peer
- * that does not show up within 2 s sets the flag read by om_mailbox_timed_out instead of hanging the GPU. */
+ * every rank; in and out are device pointers, may alias).  Every rank must issue the same sequence of calls.  A round in
+ * which a peer does not show up within the timeout (default 30 s; env OM_MAILBOX_TIMEOUT_MS at create time or
+ * om_mailbox_set_timeout_ms; 0 = wait for ever) is given up on that rank: its whole output vector is NaN (never a
+ * partial sum) and the word read by om_mailbox_timed_out is set.  om_mailbox_timed_out synchronises with the device,
+ * reports whether a round gave up since the last call and clears the word. */
 #define OM_MAILBOX_HANDLE_BYTES 64
 typedef struct OmMailbox OmMailbox;
 int om_mailbox_create(int world, int rank, OmMailbox** out, unsigned char* handle_out);
 int om_mailbox_connect(OmMailbox* mb, const unsigned char* all_handles);
 int om_mailbox_allreduce(OmMailbox* mb, const double* in, double* out, int n, void* stream);
+int om_mailbox_set_timeout_ms(OmMailbox* mb, double ms);
 int om_mailbox_timed_out(OmMailbox* mb, int* flag);
 void om_mailbox_destroy(OmMailbox* mb);
 

@@ -40,7 +40,17 @@ class OmPlayState(C.Structure):
 class OmPlayOut(C.Structure):
     _fields_ = [("xpos", C.c_void_p), ("xquat", C.c_void_p), ("site_xpos", C.c_void_p), ("cvel", C.c_void_p),
                 ("obs", C.c_void_p), ("reward", C.c_void_p), ("fallen", C.c_void_p), ("traj_no_t", C.c_void_p),
-                ("step_no_t", C.c_void_p)]
+                ("step_no_t", C.c_void_p), ("obs_moments", C.c_void_p)]
+
+
+class OmLiveState(C.Structure):
+    _fields_ = [("traj_no", C.c_void_p), ("step_no", C.c_void_p), ("reset_count", C.c_void_p), ("xy_off", C.c_void_p),
+                ("prev_x_vel", C.c_void_p)]
+
+
+class OmLiveOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("qpos", "qvel", "xpos", "xquat", "site_xpos", "cvel", "obs", "reward",
+                                          "absorbing", "wrapped")]
 
 
 class OmA3TaskDesc(C.Structure):
@@ -86,6 +96,7 @@ PROTOTYPES = {
     "om_abi_version": (_I, []),
     "om_launch_count": (C.c_longlong, []),
     "om_reset_launch_count": (None, []),
+    "om_debug_set": (_I, [C.c_char_p, _I]),
     "om_model_create": (_I, [C.POINTER(OmModelDesc), C.POINTER(_P)]),
     "om_model_destroy": (None, [_P]),
     "om_model_is_specialised": (_I, [_P]),
@@ -100,6 +111,7 @@ PROTOTYPES = {
     "om_traj_next": (_I, [_P, _U64, _U32, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "om_h1_play_from_velocity": (_I, [_P, C.POINTER(OmH1Spec), _P, _U64, _U32, _D, _I, _I,
                                       C.POINTER(OmPlayState), C.POINTER(OmPlayOut), _I, _I, _P]),
+    "om_h1_live_step": (_I, [_P, C.POINTER(OmH1Spec), _P, _U64, _U32, C.POINTER(OmLiveState), C.POINTER(OmLiveOut), _I, _I, _P]),
     "om_a3_task_create": (_I, [C.POINTER(OmA3TaskDesc), C.POINTER(_P)]),
     "om_a3_task_destroy": (None, [_P]),
     "om_a3_task_step": (_I, [_P, _P, _P, _P, _P, _I, C.POINTER(OmA3State), C.POINTER(OmA3Out), _I, _I, _P]),
@@ -120,10 +132,12 @@ PROTOTYPES = {
     "om_gae": (_I, [_P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _P, _P, _P]),
     "om_moments": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "om_adv_stats": (_I, [_P, _I, _D, _P, _P]),
+    "om_moment_stats": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
     "om_normalize": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "om_mailbox_create": (_I, [_I, _I, C.POINTER(_P), _P]),
     "om_mailbox_connect": (_I, [_P, _P]),
     "om_mailbox_allreduce": (_I, [_P, _P, _P, _I, _P]),
+    "om_mailbox_set_timeout_ms": (_I, [_P, _D]),
     "om_mailbox_timed_out": (_I, [_P, C.POINTER(_I)]),
     "om_mailbox_destroy": (None, [_P]),
 }

@@ -380,7 +380,7 @@ extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const flo
   // Several steps: time-parallel replay (measured faster than the fused kernel at 16384 and at 262144 envs x 64 steps:
   // 0.37 vs 0.21 and 0.72 vs 0.65 of the HBM roofline); one step: the fused kernel, one launch.
   int split = !want_fk && n_steps >= 2;
-  if (const char* f = getenv("OM_A3_SPLIT")) split = atoi(f) != 0 && !want_fk;      // tuning / test hook
+  if (g_knobs.a3_split >= 0) split = g_knobs.a3_split != 0 && !want_fk;             // tuning / test hook (om_debug_set)
   if (split) {
     constexpr int FB = 128;
     const int env_blocks = ceil_div(n, FB);

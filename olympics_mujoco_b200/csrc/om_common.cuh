@@ -21,6 +21,18 @@ std::string& last_error();
 int fail(const char* fmt, ...);
 extern std::atomic<long long> g_launches;
 
+// Tuning / test knobs (om_debug_set; initialised ONCE from the OM_* environment variables when the library is loaded --
+// no getenv on any launch path).  -1 / 0 = automatic.
+struct Knobs {
+  int play_chunk = 0;     // OM_PLAY_CHUNK   time-chunk length of the time-parallel playback kernel
+  int h1_split = -1;      // OM_H1_SPLIT     1 / 0: force / forbid the three-threads-per-env H1 step kernel
+  int a3_split = -1;      // OM_A3_SPLIT     1 / 0: force / forbid the time-parallel A3 replay
+  int serial_scan = 0;    // OM_SERIAL_SCAN  1: one-thread-per-env returns / GAE kernels
+  int disc_vail2 = -1;    // OM_DISC_VAIL2   1 / 0: two-CTAs-per-SM VAIL kernel
+  int disc_pg2 = -1;      // OM_DISC_PG2     1 / 0: two producer warpgroups
+};
+extern Knobs g_knobs;
+
 #define OM_CUDA_OK(expr)                                                                     \
   do {                                                                                       \
     cudaError_t _e = (expr);                                                                 \

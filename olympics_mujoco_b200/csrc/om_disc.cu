@@ -994,7 +994,7 @@ extern "C" int om_disc_forward(const OmDisc* h, const float* s, const float* mea
   // vs 76.3 us -- but 15 % slower inside bench.py's process, after the large-buffer measurements: 88.8 us; the two-CTA
   // kernel reads 76-78 us in both settings, so it stays the default.)
   int two = h->sh.kind == 0;
-  if (const char* f = getenv("OM_DISC_VAIL2")) two = h->sh.kind == 0 && atoi(f) != 0;      // tuning / test hook: force either
+  if (g_knobs.disc_vail2 >= 0) two = h->sh.kind == 0 && g_knobs.disc_vail2 != 0;           // tuning / test hook: force either
   if (two) {
     const size_t smem2 = V2_NS * V2_STAGE_BYTES + (V2_NPAR + 3 + 2 * DISC_IN) * sizeof(float) + 3 * V2_NS * 8 + 16;
     const int grid2 = ntiles < 2 * sms ? ntiles : 2 * sms;
@@ -1008,7 +1008,7 @@ extern "C" int om_disc_forward(const OmDisc* h, const float* s, const float* mea
     return 0;
   }
   int pg2 = 1;                                                      // two producer warpgroups per CTA
-  if (const char* f = getenv("OM_DISC_PG2")) pg2 = atoi(f) != 0;                 // tuning / test hook
+  if (g_knobs.disc_pg2 >= 0) pg2 = g_knobs.disc_pg2 != 0;                        // tuning / test hook
   if (pg2) {
     const size_t smem_pg2 = smem + 2 * 128 * sizeof(float);
     if (h->sh.kind == 0) {

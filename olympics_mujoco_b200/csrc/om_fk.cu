@@ -302,11 +302,11 @@ extern "C" int om_h1_step(const OmModel* m, const OmH1Spec* spec, const float* q
   if (m->specialised == SPEC_H1) {
     // three threads per env for small batches (measured, CUDA-graph replays, both with the compile-time observation
     // permutation: 16384 envs 7.1 vs 7.3 us, 32768 envs 8.2 vs 9.0 us, 65536 envs 20.8 vs 15.4 us); OM_H1_SPLIT = 0 / 1
-    // forces a path (tuning / tests)
+    // forces a path (tuning / tests; om_debug_set "h1_split")
     bool own_spec = sp.n_obs_q == 17;                 // UnitreeH1's own observation spec: compile-time permutation
     for (int k = 0; k < 17 && own_spec; ++k) own_spec = sp.perm[k] == OM_H1_PERM_HOST[k];
     bool split3 = want_fk && n <= 32768;
-    if (const char* f = getenv("OM_H1_SPLIT")) split3 = want_fk && atoi(f) != 0;
+    if (g_knobs.h1_split >= 0) split3 = want_fk && g_knobs.h1_split != 0;
     if (split3 && own_spec) h1_step_split_kernel<true><<<ceil_div(n, 32), dim3(32, 3), 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);
     else if (split3) h1_step_split_kernel<false><<<ceil_div(n, 32), dim3(32, 3), 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);
     else if (want_fk && own_spec) h1_step_kernel<BLOCK, true, true><<<grid, BLOCK, 0, st>>>(sp, qpos, qvel, prev_x_vel, n, ld, o, obs, reward, absorbing);

@@ -111,11 +111,18 @@ __global__ void __launch_bounds__(1024) affine_scan_kernel(AffineIn in, int T, i
   const int env = blockIdx.x * 32 + lane;
   const bool live = env < n;
   const int t0 = w * L;
-  float a[L], b[L], vv[L];
+  // a_t is either 0 (a path / segment ends at t) or the constant g: one bit per step instead of a register.  Steps past
+  // the end of the buffer get (a, b) = (0, 0): everything behind the last step is zero anyway.  For L = 32 the values
+  // V(s_t) are re-read for the output instead of being kept (b[32] + vv[32] spilled 1.5 KB per thread).
+  constexpr bool KEEP_V = L <= 16;
+  const float g = in.mode == 0 ? in.gl : in.gamma;
+  float b[L], vv[KEEP_V ? L : 1];
+  uint32_t amask = 0;
 #pragma unroll
   for (int i = 0; i < L; ++i) {
     const int t = t0 + i;
-    a[i] = 1.f; b[i] = 0.f; vv[i] = 0.f;          // identity for t >= T
+    b[i] = 0.f;
+    if (KEEP_V) vv[i] = 0.f;
     if (live && t < T) {
       const size_t idx = (size_t)t * ld + env;
       const float r = in.r[idx];
@@ -124,29 +131,33 @@ __global__ void __launch_bounds__(1024) affine_scan_kernel(AffineIn in, int T, i
         const float v = in.v[idx], vn = in.vn[idx];
         const bool ab = in.f0 && in.f0[idx], la = (in.f1 && in.f1[idx]) || endbuf;
         const float boot = (la && ab) ? 0.f : in.gamma * vn;
-        a[i] = la ? 0.f : in.gl;
+        if (!la) amask |= 1u << i;
         b[i] = (r - v) + boot;
-        vv[i] = v;
+        if (KEEP_V) vv[i] = v;
       } else {
         const uint8_t e = in.f0 ? in.f0[idx] : 0;
-        vv[i] = in.v ? in.v[idx] : 0.f;
+        if (KEEP_V) vv[i] = in.v ? in.v[idx] : 0.f;
         // loaded whether or not the flag needs it: a load that waits for the flag byte costs a second round trip per
         // step (long_scoreboard was 56 % of this kernel's stalls at T = 64)
         const float vnx = in.vn ? in.vn[idx] : 0.f;
         // R_t = gamma * Rin + r, where Rin is the bootstrap when a path ends at t
         if (endbuf) {
           const float boot = (e == 1) ? 0.f : ((e == 2 && in.vn) ? vnx : (in.v_last ? in.v_last[env] : 0.f));
-          a[i] = 0.f; b[i] = fmaf(in.gamma, boot, r);
-        } else if (e == 1) { a[i] = 0.f; b[i] = r; }
-        else if (e == 2) { a[i] = 0.f; b[i] = fmaf(in.gamma, vnx, r); }
-        else { a[i] = in.gamma; b[i] = r; }
+          b[i] = fmaf(in.gamma, boot, r);
+        } else if (e == 1) { b[i] = r; }
+        else if (e == 2) { b[i] = fmaf(in.gamma, vnx, r); }
+        else { amask |= 1u << i; b[i] = r; }
       }
     }
   }
   // compose the segment from its last element backwards: X_{t0} = A * X_in + B
   float A = 1.f, B = 0.f;
 #pragma unroll
-  for (int i = L - 1; i >= 0; --i) { B = fmaf(a[i], B, b[i]); A = a[i] * A; }
+  for (int i = L - 1; i >= 0; --i) {
+    const float a = ((amask >> i) & 1u) ? g : 0.f;
+    B = fmaf(a, B, b[i]);
+    A = a * A;
+  }
   sA[w][lane] = A; sB[w][lane] = B;
   __syncthreads();
   // carry-in of this segment = value at the first step of segment w+1 = fold of segments 31 .. w+1
@@ -154,12 +165,16 @@ __global__ void __launch_bounds__(1024) affine_scan_kernel(AffineIn in, int T, i
   for (int s = (int)blockDim.y - 1; s > w; --s) X = fmaf(sA[s][lane], X, sB[s][lane]);
 #pragma unroll
   for (int i = L - 1; i >= 0; --i) {
-    X = fmaf(a[i], X, b[i]);
+    const float a = ((amask >> i) & 1u) ? g : 0.f;
+    X = fmaf(a, X, b[i]);
     const int t = t0 + i;
     if (live && t < T) {
       const size_t idx = (size_t)t * ld + env;
-      if (in.mode == 0) { if (out0) out0[idx] = X; if (out1) out1[idx] = X + vv[i]; }
-      else { if (out0) out0[idx] = X; if (out1) out1[idx] = X - vv[i]; }
+      if (out0) out0[idx] = X;
+      if (out1) {
+        const float v = KEEP_V ? vv[i] : (in.v ? in.v[idx] : 0.f);
+        out1[idx] = in.mode == 0 ? X + v : X - v;
+      }
     }
   }
 }
@@ -254,6 +269,27 @@ __global__ void adv_stats_kernel(const double* __restrict__ mom, int unbiased, d
   if (unbiased && cnt > 1.0) var = var * cnt / (cnt - 1.0);
   stats[0] = mean;
   stats[1] = sqrt(var) + eps;
+}
+
+// mean / denominator per component from [sum[C], sumsq[C], count] (om_moment_stats kinds; distributed.mean_std_from_moments)
+__global__ void __launch_bounds__(128) moment_stats_kernel(const double* __restrict__ mom, int C, int kind,
+                                                           double* __restrict__ mean, double* __restrict__ denom,
+                                                           float* __restrict__ mean32, float* __restrict__ denom32) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double n = mom[2 * C];
+  const double m = mom[c] / n;
+  const double var = mom[C + c] / n - m * m;
+  const double v0 = var > 0.0 ? var : 0.0;
+  double d;
+  if (kind == 0) d = sqrt(var > 1e-2 ? var : 1e-2);
+  else if (kind == 1) d = sqrt(v0 + 1e-8);
+  else if (kind == 2) d = sqrt(v0 * n / (n - 1.0)) + 1e-5;
+  else d = sqrt(v0) + 1e-8;
+  if (mean) mean[c] = m;
+  if (denom) denom[c] = d;
+  if (mean32) mean32[c] = (float)m;
+  if (denom32) denom32[c] = (float)d;
 }
 
 __global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict__ x, const double* __restrict__ stats,
@@ -427,7 +463,7 @@ extern "C" int om_ppo_returns(const float* rewards, const float* values, const u
   if (T == 0 || n == 0) return 0;
   OM_REQUIRE(rewards && (ret || adv), "om_ppo_returns: null argument");
   OM_REQUIRE(!adv || values, "om_ppo_returns: advantages need values");
-  if (T <= 1024 && T >= 8 && (long long)n < 148LL * 2048 && !getenv("OM_SERIAL_SCAN")) {
+  if (T <= 1024 && T >= 8 && (long long)n < 148LL * 2048 && !g_knobs.serial_scan) {
     AffineIn in{rewards, values, v_next, path_end, nullptr, v_last, gamma, 0.f, 1};
     launch_affine_scan(in, T, n, ld, ret, adv, (cudaStream_t)stream);
   } else {
@@ -444,7 +480,7 @@ extern "C" int om_gae(const float* rewards, const float* v, const float* v_next,
   OM_REQUIRE(T >= 0 && n >= 0 && ld >= n, "om_gae: bad sizes");
   if (T == 0 || n == 0) return 0;
   OM_REQUIRE(rewards && v && v_next && (adv || v_target), "om_gae: null argument");
-  if (T <= 1024 && T >= 8 && (long long)n < 148LL * 2048 && !getenv("OM_SERIAL_SCAN")) {
+  if (T <= 1024 && T >= 8 && (long long)n < 148LL * 2048 && !g_knobs.serial_scan) {
     AffineIn in{rewards, v, v_next, absorbing, last, nullptr, gamma, gamma * lam, 0};
     launch_affine_scan(in, T, n, ld, adv, v_target, (cudaStream_t)stream);
   } else {
@@ -478,6 +514,14 @@ extern "C" int om_moments(const float* x, int rows, int C, int n, int ld, double
 extern "C" int om_adv_stats(const double* moments, int unbiased, double eps, double* stats, void* stream) {
   OM_REQUIRE(moments && stats, "om_adv_stats: null argument");
   adv_stats_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(moments, unbiased, eps, stats);
+  OM_LAUNCHED();
+  return 0;
+}
+
+extern "C" int om_moment_stats(const double* moments, int C, int kind, double* mean, double* denom, float* mean32,
+                               float* denom32, void* stream) {
+  OM_REQUIRE(moments && C >= 1 && kind >= 0 && kind <= 3, "om_moment_stats: bad argument (C=%d kind=%d)", C, kind);
+  moment_stats_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(moments, C, kind, mean, denom, mean32, denom32);
   OM_LAUNCHED();
   return 0;
 }

@@ -5,8 +5,10 @@
 // ONE small kernel per rank (a) stores its partial sums, tagged with the round's sequence number, into every rank's
 // mailbox over NVLink, (b) spins on its own mailbox until every rank's words carry the tag, (c) adds the world's
 // contributions in rank order -- every rank gets bit-identical sums.  Two parity slots let a fast rank start the
-// next round while a slow one still reads the previous.  A spin that exceeds the timeout sets an error word instead of
-// hanging the GPU; the host checks it.
+// next round while a slow one still reads the previous.  A spin that exceeds the timeout (30 s by default, 0 = wait for
+// ever like NCCL) gives the round up: the whole output vector is NaN on that rank -- never a partial sum -- and an error
+// word is set that the host reads (and clears) with om_mailbox_timed_out.
+#include <cstdlib>
 #include <cstring>
 
 #include "om_common.cuh"
@@ -41,37 +43,46 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
+// in / out may alias (no __restrict__): thread tid reads in[tid] before it writes out[tid].
+// timeout_ns == 0 waits for ever (what NCCL does).  A round that times out publishes NO partial sum: every value of the
+// round's output is NaN on the rank that gave up, and its timed_out word is set for the host (om_mailbox_timed_out).
 __global__ void __launch_bounds__(MB_MAX_N) mailbox_allreduce_kernel(MailPeers peers, MailBox* mine, int world, int rank,
-                                                                     const double* __restrict__ in, double* __restrict__ out,
-                                                                     int n, unsigned long long timeout_ns) {
+                                                                     const double* in, double* out, int n,
+                                                                     unsigned long long timeout_ns) {
   __shared__ unsigned long long s_seq;
   const int tid = threadIdx.x;
   if (tid == 0) s_seq = ++mine->seq;
   __syncthreads();
   const unsigned long long flag = (s_seq & 0xffffffffull) << 32;
   const int parity = (int)(s_seq & 1ull);
-  if (tid >= n) return;
-  const unsigned long long bits = (unsigned long long)__double_as_longlong(in[tid]);
-  const unsigned long long w0 = (bits & 0xffffffffull) | flag, w1 = (bits >> 32) | flag;
-  for (int p = 0; p < world; ++p) {                                 // NVLink stores (p == rank: local)
-    unsigned long long* dst = peers.box[p]->word[parity][rank][tid];
-    st_relaxed_sys(dst, w0);
-    st_relaxed_sys(dst + 1, w1);
-  }
   double s = 0.0;
-  const unsigned long long t0 = global_timer_ns();
-  for (int r = 0; r < world; ++r) {                                 // rank order: identical bits on every rank
-    const unsigned long long* src = mine->word[parity][r][tid];
-    unsigned long long a, b;
-    for (;;) {
-      a = ld_relaxed_sys(src);
-      b = ld_relaxed_sys(src + 1);
-      if ((a & 0xffffffff00000000ull) == flag && (b & 0xffffffff00000000ull) == flag) break;
-      if (global_timer_ns() - t0 > timeout_ns) { mine->timed_out = 1u; break; }
+  int gave_up = 0;
+  if (tid < n) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(in[tid]);
+    const unsigned long long w0 = (bits & 0xffffffffull) | flag, w1 = (bits >> 32) | flag;
+    for (int p = 0; p < world; ++p) {                               // NVLink stores (p == rank: local)
+      unsigned long long* dst = peers.box[p]->word[parity][rank][tid];
+      st_relaxed_sys(dst, w0);
+      st_relaxed_sys(dst + 1, w1);
     }
-    s += __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+    const unsigned long long t0 = global_timer_ns();
+    for (int r = 0; r < world && !gave_up; ++r) {                   // rank order: identical bits on every rank
+      const unsigned long long* src = mine->word[parity][r][tid];
+      unsigned long long a, b;
+      for (;;) {
+        a = ld_relaxed_sys(src);
+        b = ld_relaxed_sys(src + 1);
+        if ((a & 0xffffffff00000000ull) == flag && (b & 0xffffffff00000000ull) == flag) break;
+        if (timeout_ns && global_timer_ns() - t0 > timeout_ns) { gave_up = 1; break; }
+      }
+      s += __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+    }
   }
-  out[tid] = s;
+  if (__syncthreads_or(gave_up)) {                                  // all or nothing: never a partly summed vector
+    if (tid == 0) mine->timed_out = 1u;
+    s = __longlong_as_double(0x7ff8000000000000ll);
+  }
+  if (tid < n) out[tid] = s;
 }
 
 }  // namespace om
@@ -80,6 +91,7 @@ using namespace om;
 
 struct OmMailbox {
   int world = 1, rank = 0, connected = 0;
+  unsigned long long timeout_ns = 30000000000ull;     // 30 s; OM_MAILBOX_TIMEOUT_MS / om_mailbox_set_timeout_ms, 0 = never
   MailBox* mine = nullptr;
   MailPeers peers{};
   bool opened[MB_MAX_WORLD] = {};
@@ -91,6 +103,7 @@ extern "C" int om_mailbox_create(int world, int rank, OmMailbox** out, unsigned 
   static_assert(sizeof(cudaIpcMemHandle_t) == OM_MAILBOX_HANDLE_BYTES, "handle size");
   OmMailbox* mb = new OmMailbox();
   mb->world = world; mb->rank = rank;
+  if (const char* f = getenv("OM_MAILBOX_TIMEOUT_MS")) mb->timeout_ns = (unsigned long long)(atof(f) * 1e6);   // read once, here
   cudaError_t e = cudaMalloc((void**)&mb->mine, sizeof(MailBox));
   if (e == cudaSuccess) e = cudaMemset(mb->mine, 0, sizeof(MailBox));
   cudaIpcMemHandle_t h;
@@ -131,15 +144,24 @@ extern "C" int om_mailbox_allreduce(OmMailbox* mb, const double* in, double* out
   if (n == 0) return 0;
   OM_REQUIRE(in && out, "om_mailbox_allreduce: null argument");
   mailbox_allreduce_kernel<<<1, MB_MAX_N, 0, (cudaStream_t)stream>>>(mb->peers, mb->mine, mb->world, mb->rank, in, out, n,
-                                                                     2000000000ull /* 2 s */);
+                                                                     mb->timeout_ns);
   OM_LAUNCHED();
   return 0;
 }
 
+extern "C" int om_mailbox_set_timeout_ms(OmMailbox* mb, double ms) {
+  OM_REQUIRE(mb && ms >= 0.0, "om_mailbox_set_timeout_ms: bad argument");
+  mb->timeout_ns = (unsigned long long)(ms * 1e6);
+  return 0;
+}
+
+// Synchronises with the device (a host read of the word).  Reports whether any round since the last call gave up, and
+// clears the word so that the next report is about the rounds after this one.
 extern "C" int om_mailbox_timed_out(OmMailbox* mb, int* flag) {
   OM_REQUIRE(mb && flag, "om_mailbox_timed_out: null argument");
   unsigned int v = 0;
   OM_CUDA_OK(cudaMemcpy(&v, &mb->mine->timed_out, sizeof v, cudaMemcpyDeviceToHost));
+  if (v) OM_CUDA_OK(cudaMemset(&mb->mine->timed_out, 0, sizeof v));
   *flag = (int)v;
   return 0;
 }

@@ -1,5 +1,6 @@
 // Model handle: uploads the mjModel-like tables and decides which kernel family serves them.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "om_common.cuh"
@@ -22,6 +23,21 @@ int fail(const char* fmt, ...) {
   return 1;
 }
 std::atomic<long long> g_launches{0};
+
+static int env_int(const char* name, int dflt) {
+  const char* f = getenv(name);
+  return f ? atoi(f) : dflt;
+}
+Knobs g_knobs = [] {
+  Knobs k;
+  k.play_chunk = env_int("OM_PLAY_CHUNK", 0);
+  k.h1_split = env_int("OM_H1_SPLIT", -1);
+  k.a3_split = env_int("OM_A3_SPLIT", -1);
+  k.serial_scan = env_int("OM_SERIAL_SCAN", 0);
+  k.disc_vail2 = env_int("OM_DISC_VAIL2", -1);
+  k.disc_pg2 = env_int("OM_DISC_PG2", -1);
+  return k;
+}();
 
 template <class T>
 static bool same_i(const int* a, const T* b, int n) {
@@ -54,6 +70,19 @@ extern "C" const char* om_last_error(void) { return om::last_error().c_str(); }
 extern "C" int om_abi_version(void) { return OM_ABI_VERSION; }
 extern "C" long long om_launch_count(void) { return om::g_launches.load(); }
 extern "C" void om_reset_launch_count(void) { om::g_launches.store(0); }
+
+extern "C" int om_debug_set(const char* knob, int value) {
+  OM_REQUIRE(knob, "om_debug_set: null knob");
+  const std::string k(knob);
+  if (k == "play_chunk") g_knobs.play_chunk = value > 0 ? value : 0;
+  else if (k == "h1_split") g_knobs.h1_split = value;
+  else if (k == "a3_split") g_knobs.a3_split = value;
+  else if (k == "serial_scan") g_knobs.serial_scan = value;
+  else if (k == "disc_vail2") g_knobs.disc_vail2 = value;
+  else if (k == "disc_pg2") g_knobs.disc_pg2 = value;
+  else return fail("om_debug_set: unknown knob '%s'", knob);
+  return 0;
+}
 
 extern "C" int om_model_create(const OmModelDesc* d, OmModel** out) {
   OM_REQUIRE(d && out, "om_model_create: null argument");

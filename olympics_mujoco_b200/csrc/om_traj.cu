@@ -85,6 +85,7 @@ struct PlayArgs {
   OmPlayState s;      // live carried state (written by the thread that runs the last step)
   OmPlayState snap;   // episode-start snapshot read by every chunk of the time-parallel kernel
   OmPlayOut o;
+  double* obs_moments;   // = o.obs_moments (S1 fused into the playback), or null
 };
 
 OM_HD bool h1_fallen_f(float y, float tilt, float lst, float rot) {
@@ -110,8 +111,20 @@ OM_HD void play_fk(const double (&qs)[17], const float (&dq)[17], const OmPlayOu
 }
 
 // obs / fallen / reward / integer state of one step from the freshly gathered sample row
-OM_HD void play_emit(const float (&samp)[36], float prev_x_vel, const PlayArgs& a, size_t slot, size_t env, int tr, int st) {
+//   acc (may be null): this thread's column of the CTA's float64 observation-moment accumulators in shared memory,
+//   rows 0..31 = sum, 32..63 = sum of squares, row stride ACC_STRIDE
+constexpr int PLAY_BLOCK = 128;
+OM_HD void play_emit(const float (&samp)[36], float prev_x_vel, const PlayArgs& a, size_t slot, size_t env, int tr, int st,
+                     double* acc = nullptr) {
   const size_t ld = a.ld;
+  if (acc) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const double v = (double)samp[k + 2];
+      acc[k * PLAY_BLOCK] += v;
+      acc[(32 + k) * PLAY_BLOCK] = fma(v, v, acc[(32 + k) * PLAY_BLOCK]);
+    }
+  }
   if (a.o.obs) {
     float* ob = a.o.obs + slot * 32 * ld + env;
 #pragma unroll
@@ -126,10 +139,30 @@ OM_HD void play_emit(const float (&samp)[36], float prev_x_vel, const PlayArgs& 
   if (a.o.step_no_t) a.o.step_no_t[slot * ld + env] = st;
 }
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) play_h1_seq_kernel(PlayArgs a) {
-  const int env = blockIdx.x * BLOCK + threadIdx.x;
-  if (env >= a.n) return;
+// S1 fused into the playback (was a second pass over the [T][32][n] observation buffer: 262 MB re-read per 4096 x 500
+// rollout): every thread adds the observation rows it emits to its own float64 column in shared memory (64 KB per CTA,
+// no registers -- the FK already uses 254), the CTA folds the 128 columns once at the end and issues 64 float64 atomic
+// adds into obs_moments = [sum[32], sumsq[32], count] (om_moments layout; Standardizer networks.py:76-81,
+// RunningMeanStd normalize.py:190-208).
+OM_HD void play_acc_zero(double* acc_all) {
+  for (int i = threadIdx.x; i < 64 * PLAY_BLOCK; i += PLAY_BLOCK) acc_all[i] = 0.0;
+  __syncthreads();
+}
+OM_HD void play_acc_reduce(const double* acc_all, double* __restrict__ obs_moments) {
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int row = warp; row < 64; row += PLAY_BLOCK / 32) {
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < PLAY_BLOCK / 32; ++c) s += acc_all[row * PLAY_BLOCK + c * 32 + lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0 && s != 0.0) atomicAdd(obs_moments + row, s);
+  }
+}
+
+template <int BLOCK, bool MOM>
+__device__ __forceinline__ void play_h1_seq_body(const PlayArgs& a, int env, double* acc) {
   const size_t ld = a.ld, e = env;
   int tr = a.s.traj_no[e], st = a.s.step_no[e];
   uint32_t rc = a.s.reset_count[e];
@@ -176,7 +209,7 @@ __global__ void __launch_bounds__(BLOCK) play_h1_seq_kernel(PlayArgs a) {
     }
 #pragma unroll
     for (int k = 0; k < 17; ++k) dq[k] = samp[17 + k];
-    play_emit(samp, pxv, a, (size_t)s, e, tr, st);                                   // :539-541
+    play_emit(samp, pxv, a, (size_t)s, e, tr, st, MOM ? acc : nullptr);              // :539-541
     pxv = samp[17];
   }
   // write the loop's `sample` variable back (x, y re-centred) before the end-of-episode reset
@@ -207,10 +240,58 @@ __global__ void __launch_bounds__(BLOCK) play_h1_seq_kernel(PlayArgs a) {
   a.s.prev_x_vel[e] = pxv;
 }
 
+template <int BLOCK, bool MOM>
+__global__ void __launch_bounds__(BLOCK) play_h1_seq_kernel(PlayArgs a) {
+  static_assert(BLOCK == PLAY_BLOCK, "accumulator layout");
+  extern __shared__ double play_acc[];
+  const int env = blockIdx.x * BLOCK + threadIdx.x;
+  if (MOM) play_acc_zero(play_acc);
+  if (env < a.n) play_h1_seq_body<BLOCK, MOM>(a, env, play_acc + threadIdx.x);
+  if (MOM) {
+    play_acc_reduce(play_acc, a.obs_moments);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.obs_moments + 64, (double)a.n * (double)a.n_steps);
+  }
+}
+
 // ---------------------------------------------------------------- fused playback, time-parallel
-__global__ void __launch_bounds__(256) play_snapshot_kernel(OmPlayState live, OmPlayState snap, int n, int ld) {
+// reset() at the START of a playback call (loco_env_base.py:481 / :377: every call begins with self.reset();
+// sample = get_current_sample(); curr_qpos = sample[:len_qpos]) for one env: the draw, then the carried state is written
+// to `dst` (the live state for the sequential kernel, the episode-start snapshot for the time-parallel one).
+OM_HD void play_start_reset(const PlayArgs& a, const OmPlayState& src, const OmPlayState& dst, int env) {
+  const size_t ld = a.ld, e = env;
+  int tr, st;
+  const uint32_t rc = src.reset_count[e];
+  traj_draw(a.t, a.seed, a.env_id0 + env, rc, tr, st);
+  float samp[36];
+  traj_load_row(a.t, tr, st, samp);
+  dst.traj_no[e] = tr;
+  dst.step_no[e] = st;
+  dst.reset_count[e] = rc + 1;
+  dst.xy_off[e] = a.t.xy[((size_t)tr * a.t.T + st) * 2];
+  dst.xy_off[ld + e] = a.t.xy[((size_t)tr * a.t.T + st) * 2 + 1];
+  samp[0] = 0.f; samp[1] = 0.f;                  // x - x_off and y - y_off are exactly zero at the reset sample
+#pragma unroll
+  for (int k = 0; k < 34; ++k) dst.pending[k * ld + e] = samp[k];
+  if (dst.curr_qpos) {
+#pragma unroll
+    for (int k = 0; k < 17; ++k) dst.curr_qpos[k * ld + e] = (double)samp[k];
+  }
+  dst.prev_x_vel[e] = samp[17];
+}
+
+__global__ void __launch_bounds__(256) play_start_reset_kernel(PlayArgs a) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < a.n) play_start_reset(a, a.s, a.s, e);
+}
+
+template <bool RESET>
+__global__ void __launch_bounds__(256) play_snapshot_kernel(PlayArgs a, OmPlayState live, OmPlayState snap, int n, int ld) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
+  if (RESET) {                                   // the call starts with reset(): the snapshot IS the reset state
+    play_start_reset(a, live, snap, e);
+    return;
+  }
   // all loads first (the pointers may alias as far as the compiler knows: a load-store-load chain costs 34 round trips)
   double cq[17], xo[2];
   float pd[34];
@@ -241,10 +322,8 @@ __global__ void __launch_bounds__(256) play_snapshot_kernel(OmPlayState live, Om
 // reconstruct the loop state in front of ANY step j0 in O(#resets) and then walk `chunk` steps exactly like
 // the sequential kernel.  grid = (env tiles, time chunks): 4096 envs x 500 steps become ~300k threads
 // instead of 4096, which is what lets a 4096-env rollout fill the 148 SMs.
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) play_h1_tp_kernel(PlayArgs a, int chunk) {
-  const int env = blockIdx.x * BLOCK + threadIdx.x;
-  if (env >= a.n) return;
+template <int BLOCK, bool MOM>
+__device__ __forceinline__ void play_h1_tp_body(const PlayArgs& a, int chunk, int env, double* acc) {
   const int j0 = blockIdx.y * chunk, j1 = min(j0 + chunk, a.n_steps);
   const size_t ld = a.ld, e = env;
   const int T = a.t.T;
@@ -338,7 +417,7 @@ __global__ void __launch_bounds__(BLOCK) play_h1_tp_kernel(PlayArgs a, int chunk
     }
 #pragma unroll
     for (int k = 0; k < 17; ++k) dq[k] = samp[17 + k];
-    play_emit(samp, pxv, a, (size_t)s, e, tr, st);
+    play_emit(samp, pxv, a, (size_t)s, e, tr, st, MOM ? acc : nullptr);
     pxv = samp[17];
   }
   if (j1 != a.n_steps) return;
@@ -366,6 +445,94 @@ __global__ void __launch_bounds__(BLOCK) play_h1_tp_kernel(PlayArgs a, int chunk
 #pragma unroll
   for (int k = 0; k < 17; ++k) if (a.s.curr_qpos) a.s.curr_qpos[k * ld + e] = cq[k];
   a.s.prev_x_vel[e] = pxv;
+}
+
+template <int BLOCK, bool MOM>
+__global__ void __launch_bounds__(BLOCK) play_h1_tp_kernel(PlayArgs a, int chunk) {
+  static_assert(BLOCK == PLAY_BLOCK, "accumulator layout");
+  extern __shared__ double play_acc[];
+  const int env = blockIdx.x * BLOCK + threadIdx.x;
+  if (MOM) play_acc_zero(play_acc);
+  if (env < a.n) play_h1_tp_body<BLOCK, MOM>(a, chunk, env, play_acc + threadIdx.x);
+  if (MOM) {
+    play_acc_reduce(play_acc, a.obs_moments);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(a.obs_moments + 64, (double)a.n * (double)a.n_steps);
+  }
+}
+
+// ---------------------------------------------------------------- fused live step
+// One env step of a trajectory-driven rollout in ONE kernel (was traj_next -> set_sim_state -> h1_step, the sample and
+// qpos / qvel round-tripping through HBM between three launches): advance the trajectory index (wrap -> reset,
+// loco_env_base.py:534-537), gather the sample row (get_next_sample, trajectory.py:389-401), scatter it into qpos / qvel
+// (set_sim_state :659-684; only written when the caller wants the MjData mirrors), K1 on it, observation
+// (_create_observation :737-767), has_fallen, TargetVelocityReward on the PREVIOUS observation (mushroom MuJoCo.step:
+// reward(self._obs, action, cur_obs, absorbing); self._obs = cur_obs).
+struct LiveArgs {
+  TrajDev t;
+  uint64_t seed;
+  uint32_t env_id0;
+  float target;
+  int use_absorbing, n, ld;
+  int32_t* traj_no; int32_t* step_no; uint32_t* reset_count; double* xy_off; float* prev_x_vel;
+  float* qpos; float* qvel;
+  float* xpos; float* xquat; float* site_xpos; float* cvel;
+  float* obs; float* reward; uint8_t* absorbing; uint8_t* wrapped;
+};
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) h1_live_step_kernel(LiveArgs a) {
+  const int env = blockIdx.x * BLOCK + threadIdx.x;
+  if (env >= a.n) return;
+  const size_t ld = a.ld, e = env;
+  const int T = a.t.T;
+  int tr = a.traj_no[e], st = a.step_no[e] + 1;
+  double ox = a.xy_off[e], oy = a.xy_off[ld + e];
+  const float pxv = a.prev_x_vel[e];
+  const bool wrap = st >= T;
+  if (wrap) {
+    const uint32_t rc = a.reset_count[e];
+    traj_draw(a.t, a.seed, a.env_id0 + env, rc, tr, st);
+    a.reset_count[e] = rc + 1;
+    ox = a.t.xy[((size_t)tr * T + st) * 2];
+    oy = a.t.xy[((size_t)tr * T + st) * 2 + 1];
+    a.xy_off[e] = ox;
+    a.xy_off[ld + e] = oy;
+    a.traj_no[e] = tr;
+  }
+  a.step_no[e] = st;
+  if (a.wrapped) a.wrapped[e] = wrap ? 1 : 0;
+  float samp[36];
+  traj_load_row(a.t, tr, st, samp);
+  samp[0] = (float)(a.t.xy[((size_t)tr * T + st) * 2] - ox);
+  samp[1] = (float)(a.t.xy[((size_t)tr * T + st) * 2 + 1] - oy);
+  float q[17], qd[17];
+#pragma unroll
+  for (int k = 0; k < 17; ++k) {
+    q[OM_H1_PERM[k]] = samp[k];
+    qd[OM_H1_PERM[k]] = samp[17 + k];
+  }
+  if (a.qpos) {
+#pragma unroll
+    for (int k = 0; k < 17; ++k) a.qpos[k * ld + e] = q[k];
+  }
+  if (a.qvel) {
+#pragma unroll
+    for (int k = 0; k < 17; ++k) a.qvel[k * ld + e] = qd[k];
+  }
+  if (a.obs) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) a.obs[k * ld + e] = samp[k + 2];
+  }
+  if (a.absorbing) a.absorbing[e] = (a.use_absorbing && h1_fallen_f(samp[2], samp[3], samp[4], samp[5])) ? 1 : 0;
+  if (a.reward) {
+    const float d = pxv - a.target;
+    a.reward[e] = expf(-(d * d));
+  }
+  a.prev_x_vel[e] = samp[17];                     // dq_pelvis_tx: emitted row 15 of UnitreeH1's own spec (checked on the host)
+  if (a.xpos || a.xquat || a.site_xpos || a.cvel) {
+    SoaSink<false> S{a.xpos, a.xquat, a.site_xpos, nullptr, a.cvel, nullptr, ld, e};
+    om_fk_unitree_h1(q, qd, S);
+  }
 }
 
 }  // namespace om
@@ -487,17 +654,33 @@ static int play_impl(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, ui
                  state->pending && state->prev_x_vel, "om_h1_play_from_velocity: incomplete state");
   PlayArgs a;
   a.t = t->d; a.seed = seed; a.env_id0 = env_id0; a.dt = dt; a.target = spec->target_velocity;
-  a.use_absorbing = spec->use_absorbing_states; a.n_steps = n_steps; a.end_reset = end_episode_reset;
+  a.use_absorbing = spec->use_absorbing_states; a.n_steps = n_steps; a.end_reset = end_episode_reset & 1;
+  const bool start_reset = (end_episode_reset & 2) != 0;          // OM_PLAY_START_RESET
   a.n = n; a.ld = ld; a.s = *state; a.snap = *state; a.o = *out; a.forced = forced;
-  constexpr int BLOCK = 128;
+  a.obs_moments = out->obs_moments;
+  constexpr int BLOCK = PLAY_BLOCK;
+  const bool mom = a.obs_moments != nullptr;
+  const size_t acc_bytes = mom ? (size_t)64 * PLAY_BLOCK * sizeof(double) : 0;
+  static const bool smem_opt_in = [] {              // 64 KB of dynamic shared memory for the moment columns: opt in once
+    const int bytes = 64 * PLAY_BLOCK * (int)sizeof(double);
+    cudaFuncSetAttribute(play_h1_seq_kernel<BLOCK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(play_h1_tp_kernel<BLOCK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return true;
+  }();
+  (void)smem_opt_in;
   // time-parallel when the env count alone cannot fill the machine (148 SMs x 2048 threads)
   const long long target_threads = 148LL * 2048;
   const long long chunks_wanted = target_threads / n > 0 ? target_threads / n : 1;
   int chunk = ceil_div(n_steps, chunks_wanted);
-  if (const char* f = getenv("OM_PLAY_CHUNK")) chunk = atoi(f);     // tuning / test hook
+  if (g_knobs.play_chunk > 0) chunk = g_knobs.play_chunk;            // tuning / test hook (om_debug_set)
   if (chunk < 1) chunk = 1;
   if (chunk >= n_steps) {
-    play_h1_seq_kernel<BLOCK><<<ceil_div(n, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(a);
+    if (start_reset) {
+      play_start_reset_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(a);
+      OM_LAUNCHED();
+    }
+    if (mom) play_h1_seq_kernel<BLOCK, true><<<ceil_div(n, BLOCK), BLOCK, acc_bytes, (cudaStream_t)stream>>>(a);
+    else play_h1_seq_kernel<BLOCK, false><<<ceil_div(n, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(a);
   } else {
     // the carried state is read by every chunk and overwritten by the last one: snapshot the episode-start
     // state (stream-ordered scratch) so that no thread can observe another's end-of-episode write
@@ -519,10 +702,12 @@ static int play_impl(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, ui
     a.snap.traj_no = (int32_t*)p; p += L * 4;
     a.snap.step_no = (int32_t*)p; p += L * 4;
     a.snap.reset_count = (uint32_t*)p;
-    play_snapshot_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a.s, a.snap, n, ld);
+    if (start_reset) play_snapshot_kernel<true><<<ceil_div(n, 256), 256, 0, st>>>(a, a.s, a.snap, n, ld);
+    else play_snapshot_kernel<false><<<ceil_div(n, 256), 256, 0, st>>>(a, a.s, a.snap, n, ld);
     OM_LAUNCHED();
     dim3 grid(ceil_div(n, BLOCK), ceil_div(n_steps, chunk));
-    play_h1_tp_kernel<BLOCK><<<grid, BLOCK, 0, st>>>(a, chunk);
+    if (mom) play_h1_tp_kernel<BLOCK, true><<<grid, BLOCK, acc_bytes, st>>>(a, chunk);
+    else play_h1_tp_kernel<BLOCK, false><<<grid, BLOCK, 0, st>>>(a, chunk);
     OM_LAUNCHED();
     return 0;
   }
@@ -540,4 +725,29 @@ extern "C" int om_h1_play_trajectory(const OmModel* m, const OmH1Spec* spec, con
                                      int n_steps, int end_episode_reset, const OmPlayState* state, const OmPlayOut* out, int n,
                                      int ld, void* stream) {
   return play_impl(m, spec, t, seed, env_id0, 0.0, n_steps, end_episode_reset, state, out, n, ld, stream, 1);
+}
+
+extern "C" int om_h1_live_step(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, uint64_t seed, uint32_t env_id0,
+                               const OmLiveState* state, const OmLiveOut* out, int n, int ld, void* stream) {
+  OM_REQUIRE(m && spec && t && state && out, "om_h1_live_step: null argument");
+  OM_REQUIRE(n >= 0 && ld >= n, "om_h1_live_step: need 0 <= n <= ld (n=%d ld=%d)", n, ld);
+  OM_REQUIRE(m->specialised == SPEC_H1, "om_h1_live_step: model is not the UnitreeH1 (arms disabled) model");
+  OM_REQUIRE(spec->n_obs_q == 17 && t->d.K == 34, "om_h1_live_step: expects the 34-key H1 trajectory");
+  OM_REQUIRE(spec->x_vel_idx == 15, "om_h1_live_step: x_vel_idx must be 15 (dq_pelvis_tx of UnitreeH1's own spec)");
+  for (int k = 0; k < 17; ++k)
+    OM_REQUIRE(spec->obs_perm[k] == OM_H1_PERM_HOST[k], "om_h1_live_step: observation spec differs from UnitreeH1's");
+  if (n == 0) return 0;
+  OM_REQUIRE(state->traj_no && state->step_no && state->reset_count && state->xy_off && state->prev_x_vel,
+             "om_h1_live_step: incomplete state");
+  LiveArgs a;
+  a.t = t->d; a.seed = seed; a.env_id0 = env_id0; a.target = spec->target_velocity;
+  a.use_absorbing = spec->use_absorbing_states; a.n = n; a.ld = ld;
+  a.traj_no = state->traj_no; a.step_no = state->step_no; a.reset_count = state->reset_count; a.xy_off = state->xy_off;
+  a.prev_x_vel = state->prev_x_vel;
+  a.qpos = out->qpos; a.qvel = out->qvel; a.xpos = out->xpos; a.xquat = out->xquat; a.site_xpos = out->site_xpos;
+  a.cvel = out->cvel; a.obs = out->obs; a.reward = out->reward; a.absorbing = out->absorbing; a.wrapped = out->wrapped;
+  constexpr int BLOCK = 128;
+  h1_live_step_kernel<BLOCK><<<ceil_div(n, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(a);
+  OM_LAUNCHED();
+  return 0;
 }

@@ -42,14 +42,21 @@ def env_shard(n_total, rank, world_size):
     return env_id0, n_local
 
 
+class MailboxTimeout(RuntimeError):
+    """A peer did not deliver its partial sums within the timeout: the round's output on this rank is NaN."""
+
+
 class Mailbox:
     """``om_mailbox_*``: sum of <= 128 float64 values over the ranks through mailboxes in each rank's HBM, mapped into
     every peer process with CUDA IPC and written over NVLink by one small kernel per rank (csrc/om_mailbox.cu).  The IPC
-    handles travel once, through ``torch.distributed.all_gather_object``."""
+    handles travel once, through ``torch.distributed.all_gather_object``.
+
+    Construction is collective and never raises on one rank only: the status of the local create step is gathered with
+    the handle, so every rank takes the same decision (use the mailbox / fall back) at the same point."""
 
     MAX_N = 128
 
-    def __init__(self):
+    def __init__(self, timeout_ms=None):
         import ctypes as C
         from . import _lib
         lib = _lib.load()
@@ -57,31 +64,55 @@ class Mailbox:
         world, rank = dist.get_world_size(), dist.get_rank()
         h = C.c_void_p()
         mine = (C.c_ubyte * 64)()
-        _lib.check(lib.om_mailbox_create(world, rank, C.byref(h), C.cast(mine, C.c_void_p)))
-        self.handle = h
+        rc = lib.om_mailbox_create(world, rank, C.byref(h), C.cast(mine, C.c_void_p))
+        err = lib.om_last_error().decode() if rc != 0 else ""
+        self.handle = h if rc == 0 else None
         gathered = [None] * world
-        dist.all_gather_object(gathered, bytes(mine))
-        blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(gathered))
-        rc = lib.om_mailbox_connect(self.handle, C.cast(blob, C.c_void_p))
-        ok = torch.tensor([1 if rc == 0 else 0], device="cuda")
+        dist.all_gather_object(gathered, (rc, bytes(mine)))                     # unconditional: no rank is left waiting
+        created = all(g[0] == 0 for g in gathered)
+        if created:
+            blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(g[1] for g in gathered))
+            rc = lib.om_mailbox_connect(self.handle, C.cast(blob, C.c_void_p))
+            if rc != 0:
+                err = lib.om_last_error().decode()
+        ok = torch.tensor([1 if (created and rc == 0) else 0], device="cuda")
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)              # all ranks use the mailbox, or none does
         if int(ok) == 0:
             self.close()
-            raise RuntimeError("mailbox: a peer mailbox could not be mapped: " + lib.om_last_error().decode())
+            raise RuntimeError("mailbox: unavailable on some rank" + (f" (this rank: {err})" if err else ""))
+        if timeout_ms is not None:
+            self.set_timeout_ms(timeout_ms)
 
-    def all_reduce(self, x):
+    def set_timeout_ms(self, ms):
+        """0 waits for ever (NCCL's behaviour); the default is 30 s (or OM_MAILBOX_TIMEOUT_MS at creation)."""
         from . import _lib
-        assert x.dtype == torch.float64 and x.is_cuda and x.is_contiguous() and x.numel() <= self.MAX_N
+        _lib.check(self._lib.om_mailbox_set_timeout_ms(self.handle, float(ms)))
+
+    def all_reduce(self, x, out=None):
+        """Enqueue one round on the current stream.  In place by default.  A round that times out leaves NaN in every
+        output value on the rank that gave up (never a partial sum); ``check()`` turns that into an exception at the
+        caller's next host synchronisation point."""
+        from . import _lib
+        out = x if out is None else out
+        for t in (x, out):
+            assert t.dtype == torch.float64 and t.is_cuda and t.is_contiguous() and t.numel() <= self.MAX_N
+        assert out.numel() == x.numel()
         C = self._C
-        _lib.check(self._lib.om_mailbox_allreduce(self.handle, C.c_void_p(x.data_ptr()), C.c_void_p(x.data_ptr()), x.numel(),
+        _lib.check(self._lib.om_mailbox_allreduce(self.handle, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), x.numel(),
                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        return x
+        return out
 
     def timed_out(self):
+        """Synchronises; True if a round gave up since the last call (the device word is cleared)."""
         from . import _lib
         f = self._C.c_int(0)
         _lib.check(self._lib.om_mailbox_timed_out(self.handle, self._C.byref(f)))
         return bool(f.value)
+
+    def check(self):
+        if self.timed_out():
+            raise MailboxTimeout("NVLink mailbox all-reduce: a peer did not deliver within the timeout; the sums of that "
+                                 "round are NaN on this rank (redo the round, e.g. over NCCL)")
 
     def close(self):
         if getattr(self, "handle", None):
@@ -93,9 +124,9 @@ _mailbox = None
 _mailbox_state = "unset"          # "unset" | "on" | "off"
 
 
-def enable_mailbox(enable=True):
+def enable_mailbox(enable=True, timeout_ms=None):
     """Route ``all_reduce_moments`` through the NVLink mailbox kernel (collective call: every rank must make it).
-    Falls back to NCCL on every rank if any rank cannot map its peers.  Returns whether the mailbox is in use."""
+    Falls back to NCCL on every rank if any rank cannot create or map a mailbox.  Returns whether the mailbox is in use."""
     global _mailbox, _mailbox_state
     if _mailbox is not None:
         _mailbox.close()
@@ -103,12 +134,19 @@ def enable_mailbox(enable=True):
     _mailbox_state = "off"
     if enable and dist.is_initialized() and dist.get_world_size() > 1 and dist.get_backend() == "nccl":
         try:
-            _mailbox = Mailbox()
+            _mailbox = Mailbox(timeout_ms=timeout_ms)
             _mailbox_state = "on"
         except Exception as e:                                  # IPC not permitted, no peer access ...: NCCL it is
             import warnings
             warnings.warn(f"NVLink mailbox all-reduce unavailable ({e}); using NCCL")
     return _mailbox_state == "on"
+
+
+def mailbox_check():
+    """Host synchronisation point of the mailbox route: raises ``MailboxTimeout`` if a round since the last check gave up
+    (its output is NaN on this rank).  No-op when the mailbox is not in use."""
+    if _mailbox is not None:
+        _mailbox.check()
 
 
 def all_reduce_moments(mom):
@@ -127,7 +165,13 @@ def all_reduce_moments(mom):
 def mean_std_from_moments(mom, kind):
     """``kind``: "standardizer" (networks.py:76-81: std = sqrt(max(E[x^2]-mean^2, 1e-2))), "ppo_obs"
     (normalize.py:48: sqrt(var + 1e-8)), "adv_ppo" (ppo.py:336: unbiased std + 1e-5), "adv_gail"
-    (gail_TRPO.py:128: population std + 1e-8).  Returns (mean, denominator) float64."""
+    (gail_TRPO.py:128: population std + 1e-8).  Returns (mean, denominator) float64.  A CUDA buffer goes through ONE
+    kernel (``om_moment_stats``); the torch expressions below serve host tensors (the gloo tests)."""
+    if mom.is_cuda:
+        from . import kernels as Kn
+        if kind not in Kn.MOMENT_KINDS:
+            raise ValueError(kind)
+        return Kn.moment_stats(mom, kind)
     c = (mom.numel() - 1) // 2
     s, ss, n = mom[:c], mom[c:2 * c], mom[2 * c]
     mean = s / n

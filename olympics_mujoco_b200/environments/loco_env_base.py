@@ -83,8 +83,11 @@ class LocoEnvBase:
         self._random_start, self._init_step_no = random_start, init_step_no
         self._use_absorbing_states = use_absorbing_states
         self._dynamics = None
+        self._dynamics_soa = False
+        self._action_kernel_spec = None
         self._obs = None
         self._play_state = None
+        self._live = None
 
     # ------------------------------------------------------------------ registry / factory
     @classmethod
@@ -152,11 +155,23 @@ class LocoEnvBase:
         sample = self._batched(sample).to(torch.float32)
         spec = self.obs_helper.observation_spec
         assert sample.shape[-1] == len(spec)
-        for i, (key, name, ot) in enumerate(spec):
-            if ot == ObservationType.JOINT_POS:
-                self._data.qpos[self._data.joint_rows(name)[0]] = sample[:, i]
-            elif ot == ObservationType.JOINT_VEL:
-                self._data.qvel[self._data.joint_rows(name)[1]] = sample[:, i]
+        if getattr(self, "_scatter_idx", None) is None:         # spec column -> qpos / qvel row, built once
+            cq, rq, cv, rv = [], [], [], []
+            for i, (key, name, ot) in enumerate(spec):
+                if ot == ObservationType.JOINT_POS:
+                    rows = self._data.joint_rows(name)[0]
+                    assert rows.stop - rows.start == 1, "set_sim_state handles single-dof joints (as the reference's specs do)"
+                    cq.append(i); rq.append(rows.start)
+                elif ot == ObservationType.JOINT_VEL:
+                    rows = self._data.joint_rows(name)[1]
+                    assert rows.stop - rows.start == 1
+                    cv.append(i); rv.append(rows.start)
+            t = lambda a: torch.as_tensor(a, dtype=torch.long, device=self._device)
+            self._scatter_idx = (t(cq), t(rq), t(cv), t(rv))
+        cq, rq, cv, rv = self._scatter_idx
+        st = sample.t()
+        self._data.qpos.index_copy_(0, rq, st.index_select(0, cq))       # two scatters instead of one per key
+        self._data.qvel.index_copy_(0, rv, st.index_select(0, cv))
 
     def set_state(self, qpos, qvel):
         """:1155-1160: write qpos/qvel ([n, nq], [n, nv]) and run the forward pass (K1)."""

@@ -169,19 +169,33 @@ class UnitreeH1(BaseHumanoidRobot):
         self._play_state = None
         return out
 
+    def attach_dynamics(self, fn, soa=False):
+        """``soa=True``: ``fn(env, ctrl [nu, n]) -> (qpos [nq, n], qvel [nv, n])`` float32 CUDA tensors in the kernels' own
+        layout (component-major, env index contiguous) -- ``step`` then runs without a single transposing copy."""
+        super().attach_dynamics(fn)
+        self._dynamics_soa = bool(soa)
+
     def step(self, action):
-        """action [n, nu] in [-1, 1] -> (obs, reward, absorbing, info).  The physics between observations comes
-        from the attached dynamics; everything after it is one fused kernel (K1 + K2)."""
+        """action [n, nu] in [-1, 1] ([nu, n] with SoA dynamics) -> (obs, reward, absorbing, info).  The physics between
+        observations comes from the attached dynamics; everything after it is one fused kernel (K1 + K2)."""
         if self._dynamics is None:
             raise RuntimeError("step() needs a dynamics backend: env.attach_dynamics(fn).  Contact dynamics "
                                "(mj_step) are outside this package's hot path.")
-        ctrl = self._preprocess_action(self._batched(action))
-        qpos, qvel = self._dynamics(self, ctrl)
         d = self._data
-        d.qpos.copy_(torch.as_tensor(qpos, device=self._device, dtype=torch.float32).reshape(self.n_envs, -1).t())
-        d.qvel.copy_(torch.as_tensor(qvel, device=self._device, dtype=torch.float32).reshape(self.n_envs, -1).t())
+        if getattr(self, "_dynamics_soa", False):
+            if getattr(self, "_action_kernel_spec", None) is None:
+                self._action_kernel_spec = Kn.make_action_spec(self.norm_act_delta, self.norm_act_mean)
+            ctrl = Kn.action_affine(self._action_kernel_spec, action)               # [nu, n], no transposes
+            qpos, qvel = self._dynamics(self, ctrl)
+            assert qpos.shape == d.qpos.shape and qvel.shape == d.qvel.shape, "SoA dynamics return [nq, n], [nv, n]"
+        else:
+            ctrl = self._preprocess_action(self._batched(action))
+            qpos, qvel = self._dynamics(self, ctrl)
+            d.qpos.copy_(torch.as_tensor(qpos, device=self._device, dtype=torch.float32).reshape(self.n_envs, -1).t())
+            d.qvel.copy_(torch.as_tensor(qvel, device=self._device, dtype=torch.float32).reshape(self.n_envs, -1).t())
+            qpos, qvel = d.qpos, d.qvel
         prev_obs = self._obs
-        out = Kn.h1_step(self._dm, self._spec, d.qpos, d.qvel, self._prev_x_vel,
+        out = Kn.h1_step(self._dm, self._spec, qpos, qvel, self._prev_x_vel,
                          out=dict(xpos=d.xpos, xquat=d.xquat, site_xpos=d.site_xpos, cvel=d.cvel))
         cur_obs = out["obs"].t()
         absorbing = out["absorbing"].bool()
@@ -190,6 +204,63 @@ class UnitreeH1(BaseHumanoidRobot):
         self._prev_x_vel.copy_(out["obs"][self._spec.x_vel_idx])
         return self._out(self._modify_observation(cur_obs)), self._out(reward), self._out(absorbing), {}
 
+    # ------------------------------------------------------------------ fused live step / graph
+    def _live_stepper(self):
+        if not self._dm.specialised or len(self.obs_helper.observation_spec) != 34 or not self._fused_reward:
+            raise NotImplementedError("the fused live step is generated for the default UnitreeH1 (arms disabled) with the "
+                                      "target-velocity reward")
+        if getattr(self, "_live", None) is None:
+            if self._obs is None:
+                self.reset()
+            d = self._data
+            self._live = Kn.H1LiveStep(self._dm, self._spec, self.trajectories.device_state, self._prev_x_vel,
+                                       out=dict(qpos=d.qpos, qvel=d.qvel, xpos=d.xpos, xquat=d.xquat, site_xpos=d.site_xpos,
+                                                cvel=d.cvel))
+        return self._live
+
+    def step_trajectory(self):
+        """One env step driven by the loaded trajectory instead of physics -- what ``play_trajectory`` does per step
+        (loco_env_base.py:404-422): next sample (wrap -> reset), ``set_sim_state``, the forward pass, observation,
+        ``has_fallen``, reward on the previous observation -- as ONE kernel and one C call (``om_h1_live_step``).
+        Returns ``(obs, reward, absorbing, info)`` like ``step``; the tensors are views of buffers that the next call
+        overwrites."""
+        live = self._live_stepper()
+        out = live()
+        self._obs = out["obs"].t()
+        return (self._out(self._modify_observation(self._obs)), self._out(out["reward"]), self._out(out["absorbing"].bool()),
+                {})
+
+    def step_graph(self, n_steps, want=("obs", "reward", "absorbing")):
+        """Capture ``n_steps`` consecutive fused live steps into ONE CUDA graph.  Returns ``(replay, buffers)``: every
+        ``replay()`` advances all envs by ``n_steps`` and fills the time-major buffers ``[n_steps, C, n]`` (``want`` may
+        also name xpos, xquat, site_xpos, cvel, wrapped).  A launch-bound inner loop belongs in a graph: at 131 072 envs a
+        replayed step costs what the kernel costs."""
+        live = self._live_stepper()
+        n, dev = self.n_envs, self._device
+        bufs = {}
+        for k in want:
+            c, dt_ = Kn.H1LiveStep.KEYS[k]
+            bufs[k] = torch.empty((n_steps, n) if c is None else (n_steps, c, n), dtype=dt_, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        base = dict(live.out)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            live.rebind(out={k: v[0] for k, v in bufs.items()}, stream=side.cuda_stream)()      # warm-up outside the capture
+            side.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                for t in range(n_steps):
+                    live.rebind(out={k: v[t] for k, v in bufs.items()}, stream=torch.cuda.current_stream().cuda_stream)()
+        torch.cuda.current_stream().wait_stream(side)
+        live.out = base
+        live.rebind()
+
+        def replay():
+            graph.replay()
+            self._obs = bufs["obs"][-1].t() if "obs" in bufs else self._obs
+            return bufs
+        return replay, bufs
+
     # ------------------------------------------------------------------ fused playback (loco_env_base.py:444-560)
     def set_sim_state(self, sample):
         """loco_env_base.py:659-684 as one kernel (the spec is joint positions then joint velocities)."""
@@ -197,28 +268,6 @@ class UnitreeH1(BaseHumanoidRobot):
         if sample.shape[-1] != 2 * self._spec.n_obs_q:
             return super().set_sim_state(sample)
         Kn.set_sim_state(self._dm, self._spec, sample.t().contiguous(), self._data.qpos, self._data.qvel)
-
-    def play_trajectory(self, n_episodes=None, n_steps_per_episode=None, render=False, record=False, recorder_params=None,
-                        out=None, want=None):
-        """loco_env_base.py:338-442 as one fused kernel per episode (``om_h1_play_trajectory``): the model is forced to
-        every trajectory sample, FK runs on it, the next sample gives the observation and the has_fallen flag.
-        Returns the last episode's time-major rollout buffers (the reference only renders)."""
-        assert self.trajectories is not None
-        if render or record:
-            raise NotImplementedError("rendering is outside the hot path; call with render=False")
-        assert n_episodes is not None and n_steps_per_episode is not None, "unbounded playback needs a viewer"
-        if not self._dm.specialised or len(self.obs_helper.observation_spec) != 34:
-            return super().play_trajectory(n_episodes, n_steps_per_episode, render, record, recorder_params)
-        dev = self.trajectories.device_state
-        self.reset()                                                             # :377
-        sample = self.trajectories.get_current_sample().t().contiguous()         # :379
-        state = dict(pending=sample.clone(), prev_x_vel=self._prev_x_vel)
-        res = None
-        for _ in range(n_episodes):
-            kw = {} if want is None else dict(want=want)
-            res = Kn.h1_play_from_velocity(self._dm, self._spec, dev, state, n_steps_per_episode, end_episode_reset=True,
-                                           out=out, forced=True, **kw)
-        return res
 
     def make_rollout_buffers(self, n_steps, want=("xpos", "xquat", "site_xpos", "cvel", "obs", "reward", "fallen",
                                                   "traj_no_t", "step_no_t")):
@@ -230,26 +279,49 @@ class UnitreeH1(BaseHumanoidRobot):
         return {k: torch.empty((n_steps, n) if spec[k][0] is None else (n_steps, spec[k][0], n), dtype=spec[k][1],
                                device=dev) for k in want}
 
-    def play_trajectory_from_velocity(self, n_episodes=None, n_steps_per_episode=None, render=False, record=False,
-                                      recorder_params=None, out=None, want=None):
-        """Replays the loaded trajectory by integrating its joint velocities (reference semantics, one fused
-        kernel per episode).  Returns the last episode's time-major rollout buffers ([T, C, n] SoA; use
-        ``kernels.env_major`` for [T, n, ...] views) -- the reference returns nothing and only renders."""
+    def _play(self, forced, n_episodes, n_steps_per_episode, render, record, out, want, continue_episode, obs_moments):
+        """Both playback calls: every call of the reference begins with ``reset()`` (:377 / :481) and ends every episode
+        with one (:432 / :555).  The first call resets through the Python API (it also allocates the carried state);
+        later calls perform the same reset INSIDE the first kernel of the call.  ``continue_episode=True`` (extension)
+        skips the reset at the start and carries the state of the previous call on."""
         assert self.trajectories is not None
         if render or record:
             raise NotImplementedError("rendering is outside the hot path; call with render=False")
         assert n_episodes is not None and n_steps_per_episode is not None, "unbounded playback needs a viewer"
-        if not self._dm.specialised or len(self.obs_helper.observation_spec) != 34:
-            raise NotImplementedError("fused playback is generated for the default UnitreeH1 (arms disabled)")
         dev = self.trajectories.device_state
+        start_reset = not continue_episode
         if self._play_state is None:
-            self.reset()                                                             # :481
-            sample = self.trajectories.get_current_sample().t().contiguous()         # :483
+            self.reset()                                                             # :377 / :481
+            sample = self.trajectories.get_current_sample().t().contiguous()         # :379 / :483
             self._play_state = dict(curr_qpos=sample[:17].double().contiguous(), pending=sample.clone(),
                                     prev_x_vel=self._prev_x_vel)
+            start_reset = False
         res = None
-        for _ in range(n_episodes):
-            kw = {} if want is None else dict(want=want)
-            res = Kn.h1_play_from_velocity(self._dm, self._spec, dev, self._play_state, n_steps_per_episode,
-                                           dt=self.dt, end_episode_reset=True, out=out, **kw)
+        kw = {} if want is None else dict(want=want)
+        for ep in range(n_episodes):
+            res = Kn.h1_play_from_velocity(self._dm, self._spec, dev, self._play_state, n_steps_per_episode, dt=self.dt,
+                                           end_episode_reset=True, out=out, forced=forced, obs_moments=obs_moments,
+                                           start_reset=start_reset and ep == 0, **kw)
+        # the env is left in the state of the final reset(): the pending sample is its observation
+        self._obs = self._play_state["pending"][2:].t()
         return res
+
+    def play_trajectory(self, n_episodes=None, n_steps_per_episode=None, render=False, record=False, recorder_params=None,
+                        out=None, want=None, continue_episode=False, obs_moments=None):
+        """loco_env_base.py:338-442 as one fused kernel per episode (``om_h1_play_trajectory``): the model is forced to
+        every trajectory sample, FK runs on it, the next sample gives the observation and the has_fallen flag.
+        Returns the last episode's time-major rollout buffers (the reference only renders)."""
+        if not self._dm.specialised or len(self.obs_helper.observation_spec) != 34:
+            return super().play_trajectory(n_episodes, n_steps_per_episode, render, record, recorder_params)
+        return self._play(True, n_episodes, n_steps_per_episode, render, record, out, want, continue_episode, obs_moments)
+
+    def play_trajectory_from_velocity(self, n_episodes=None, n_steps_per_episode=None, render=False, record=False,
+                                      recorder_params=None, out=None, want=None, continue_episode=False, obs_moments=None):
+        """Replays the loaded trajectory by integrating its joint velocities (reference semantics -- a ``reset()`` at the
+        start of EVERY call and after every episode -- one fused kernel per episode).  Returns the last episode's
+        time-major rollout buffers ([T, C, n] SoA; use ``kernels.env_major`` for [T, n, ...] views) -- the reference
+        returns nothing and only renders.  ``obs_moments``: float64 [65] buffer that receives the moment sums of the
+        emitted observations (S1 fused into the kernel)."""
+        if not self._dm.specialised or len(self.obs_helper.observation_spec) != 34:
+            raise NotImplementedError("fused playback is generated for the default UnitreeH1 (arms disabled)")
+        return self._play(False, n_episodes, n_steps_per_episode, render, record, out, want, continue_episode, obs_moments)

@@ -12,7 +12,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import OmA3Out, OmA3State, OmA3TaskDesc, OmActionSpec, OmDiscDesc, OmH1Spec, OmMirrorSpec, OmPdSpec, OmModelDesc, OmPlayOut, OmPlayState, check
+from ._lib import (OmA3Out, OmA3State, OmA3TaskDesc, OmActionSpec, OmDiscDesc, OmH1Spec, OmLiveOut, OmLiveState, OmMirrorSpec,
+                   OmPdSpec, OmModelDesc, OmPlayOut, OmPlayState, check)
 from .mjcf import KinematicModel
 
 
@@ -205,10 +206,13 @@ class DeviceTrajectory:
 
 def h1_play_from_velocity(dm, spec, traj: DeviceTrajectory, state, n_steps, dt=0.01, end_episode_reset=True,
                           want=("xpos", "xquat", "site_xpos", "cvel", "obs", "reward", "fallen", "traj_no_t", "step_no_t"),
-                          out=None, forced=False):
+                          out=None, forced=False, obs_moments=None, start_reset=False):
     """Fused playback of one episode (loco_env_base.py:511-557).  ``state``: dict with curr_qpos [17,n] f64,
     pending [34,n] f32, prev_x_vel [n] f32 (the trajectory indices live in ``traj``).  ``forced``: play_trajectory
-    semantics (loco_env_base.py:404-432), the model is set to each sample instead of integrating velocities."""
+    semantics (loco_env_base.py:404-432), the model is set to each sample instead of integrating velocities.
+    ``obs_moments``: float64 [65] device buffer; the kernel ADDS sum[32], sumsq[32], count of the observations it emits
+    (S1 fused into the playback: no second pass over the observation buffer).  ``start_reset``: the call begins with
+    the reference's ``reset()`` (loco_env_base.py:481), performed inside the kernel (no state tensor is read before it)."""
     km, n = dm.km, traj.n
     dev = traj.traj_no.device
     sizes = dict(xpos=(km.nbody * 3, torch.float32), xquat=(km.nbody * 4, torch.float32),
@@ -227,15 +231,62 @@ def h1_play_from_velocity(dm, spec, traj: DeviceTrajectory, state, n_steps, dt=0
                      pending=_p(state["pending"], torch.float32).value,
                      prev_x_vel=_p(state["prev_x_vel"], torch.float32).value)
     po = OmPlayOut(**{k: (out[k].data_ptr() if k in out else None) for k in sizes})
+    if obs_moments is not None:
+        if obs_moments.numel() != 65:
+            raise ValueError("obs_moments must hold 2 * 32 + 1 float64 values")
+        po.obs_moments = _p(obs_moments, torch.float64).value
+    flags = (1 if end_episode_reset else 0) | (2 if start_reset else 0)
     if forced:
         check(_lib.load().om_h1_play_trajectory(dm.handle, C.byref(spec), traj.handle, traj.seed, traj.env_id0, int(n_steps),
-                                                int(bool(end_episode_reset)), C.byref(ps), C.byref(po), n, max(n, 1),
-                                                _stream()))
+                                                flags, C.byref(ps), C.byref(po), n, max(n, 1), _stream()))
     else:
         check(_lib.load().om_h1_play_from_velocity(dm.handle, C.byref(spec), traj.handle, traj.seed, traj.env_id0, float(dt),
-                                                   int(n_steps), int(bool(end_episode_reset)), C.byref(ps), C.byref(po),
-                                                   n, max(n, 1), _stream()))
+                                                   int(n_steps), flags, C.byref(ps), C.byref(po), n, max(n, 1), _stream()))
     return out
+
+
+class H1LiveStep:
+    """``om_h1_live_step`` with every argument bound once: one fused kernel per env step (next sample / wrap reset +
+    set_sim_state + FK + observation + has_fallen + reward), one ctypes call per step with no per-call marshalling --
+    the eager Python loop stays within a few microseconds of host time per step.  ``out``: dict of SoA tensors (any of
+    qpos, qvel, xpos, xquat, site_xpos, cvel, obs, reward, absorbing, wrapped); missing FK / mirror outputs are not
+    computed.  ``prev_x_vel`` [n] float32 is carried in place.  Graph-capturable."""
+
+    KEYS = dict(qpos=(17, torch.float32), qvel=(17, torch.float32), xpos=(63, torch.float32), xquat=(84, torch.float32),
+                site_xpos=(3, torch.float32), cvel=(126, torch.float32), obs=(32, torch.float32), reward=(None, torch.float32),
+                absorbing=(None, torch.uint8), wrapped=(None, torch.uint8))
+
+    def __init__(self, dm, spec, traj: DeviceTrajectory, prev_x_vel, out=None,
+                 want=("xpos", "xquat", "site_xpos", "cvel", "obs", "reward", "absorbing")):
+        n, dev = traj.n, traj.traj_no.device
+        self.dm, self.spec, self.traj, self.n = dm, spec, traj, n
+        self.prev_x_vel = prev_x_vel
+        self.out = dict(out or {})
+        for k in want:
+            if k not in self.out:
+                c, dt_ = self.KEYS[k]
+                self.out[k] = torch.empty((n,) if c is None else (c, n), dtype=dt_, device=dev)
+        self._fn = _lib.load().om_h1_live_step
+        self.rebind()
+
+    def rebind(self, out=None, stream=None):
+        """Point the call at other output tensors (e.g. the next time slot of a rollout buffer) / another stream."""
+        if out is not None:
+            self.out.update(out)
+        traj = self.traj
+        self._state = OmLiveState(traj_no=traj.traj_no.data_ptr(), step_no=traj.step_no.data_ptr(),
+                                  reset_count=traj.reset_count.data_ptr(), xy_off=traj.xy_off.data_ptr(),
+                                  prev_x_vel=_p(self.prev_x_vel, torch.float32).value)
+        self._out = OmLiveOut(**{k: _p(v, self.KEYS[k][1]).value for k, v in self.out.items()})
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        self._args = (self.dm.handle, C.byref(self.spec), traj.handle, traj.seed, traj.env_id0, C.byref(self._state),
+                      C.byref(self._out), self.n, max(self.n, 1), C.c_void_p(st))
+        return self
+
+    def __call__(self):
+        if self._fn(*self._args):
+            check(1)
+        return self.out
 
 
 # ------------------------------------------------------------------------------------------- A3
@@ -519,6 +570,22 @@ def adv_stats(mom, unbiased, eps):
     return stats
 
 
+MOMENT_KINDS = dict(standardizer=0, ppo_obs=1, adv_ppo=2, adv_gail=3)
+
+
+def moment_stats(mom, kind, want32=False):
+    """(mean [C], denominator [C]) float64 from a moment buffer [sum[C], sumsq[C], count] in one kernel (the formulas of
+    ``distributed.mean_std_from_moments``); with ``want32`` also float32 copies (what ``Discriminator.reward`` takes)."""
+    c = (mom.numel() - 1) // 2
+    mean = torch.empty(c, dtype=torch.float64, device=mom.device)
+    denom = torch.empty(c, dtype=torch.float64, device=mom.device)
+    m32 = torch.empty(c, dtype=torch.float32, device=mom.device) if want32 else None
+    d32 = torch.empty(c, dtype=torch.float32, device=mom.device) if want32 else None
+    check(_lib.load().om_moment_stats(_p(mom, torch.float64), c, MOMENT_KINDS[kind], _p(mean), _p(denom), _p(m32), _p(d32),
+                                      _stream()))
+    return (mean, denom, m32, d32) if want32 else (mean, denom)
+
+
 def normalize(x, stats, out=None):
     """(x - stats[0]) / stats[1] over a [rows, n] buffer."""
     x2 = x.view(1, -1) if x.dim() == 1 else x
@@ -527,6 +594,11 @@ def normalize(x, stats, out=None):
     check(_lib.load().om_normalize(_p(x2, torch.float32), _p(stats, torch.float64), rows, n, max(n, 1),
                                    _p(out, torch.float32), _stream()))
     return out
+
+
+def debug_set(knob, value):
+    """Tuning / test hook (``om_debug_set``): force a kernel variant; -1 / 0 = automatic."""
+    check(_lib.load().om_debug_set(knob.encode(), int(value)))
 
 
 def launch_count():

@@ -59,33 +59,42 @@ def forward(cm, qpos, qvel):
     return out
 
 
-def h1_play(cm, perm, table, seed, env_id0, n_env, n_steps, dt=0.01, target=1.25, record=True):
+def h1_play_buffers(km, K, n_env, n_steps):
+    """Output arrays of ``h1_play(record=True)``; allocate once and pass as ``out=`` to keep page faults and zero
+    fills out of a timed region."""
+    return dict(xpos=np.zeros((n_env, n_steps, km.nbody * 3)), xquat=np.zeros((n_env, n_steps, km.nbody * 4)),
+                site_xpos=np.zeros((n_env, n_steps, km.nsite * 3)), cvel=np.zeros((n_env, n_steps, km.nbody * 6)),
+                obs=np.zeros((n_env, n_steps, K - 2)), reward=np.zeros((n_env, n_steps)),
+                fallen=np.zeros((n_env, n_steps), np.uint8), traj_no=np.zeros((n_env, n_steps), np.int32),
+                step_no=np.zeros((n_env, n_steps), np.int32), checksum=np.zeros(n_env))
+
+
+def h1_play(cm, perm, table, seed, env_id0, n_env, n_steps, dt=0.01, target=1.25, record=True, out=None):
     km = cm.km
     table = np.ascontiguousarray(table, np.float64)
     K, n_traj, T = table.shape
     perm = np.ascontiguousarray(perm, np.int32)
-    out = {}
-    if record:
-        out = dict(xpos=np.zeros((n_env, n_steps, km.nbody * 3)), xquat=np.zeros((n_env, n_steps, km.nbody * 4)),
-                   site_xpos=np.zeros((n_env, n_steps, km.nsite * 3)), cvel=np.zeros((n_env, n_steps, km.nbody * 6)),
-                   obs=np.zeros((n_env, n_steps, K - 2)), reward=np.zeros((n_env, n_steps)),
-                   fallen=np.zeros((n_env, n_steps), np.uint8), traj_no=np.zeros((n_env, n_steps), np.int32),
-                   step_no=np.zeros((n_env, n_steps), np.int32))
-    chk = np.zeros(n_env)
+    if out is None:
+        out = h1_play_buffers(km, K, n_env, n_steps) if record else dict(checksum=np.zeros(n_env))
+    else:
+        assert out["reward"].shape == (n_env, n_steps)
     g = lambda k: _p(out.get(k))
     lib().or_h1_play(C.byref(cm.c), _p(perm), _p(table), K, n_traj, T, C.c_uint64(seed), C.c_uint32(env_id0), n_env, n_steps,
                      C.c_double(dt), C.c_double(target), g("xpos"), g("xquat"), g("site_xpos"), g("cvel"), g("obs"),
-                     g("reward"), g("fallen"), g("traj_no"), g("step_no"), _p(chk))
-    out["checksum"] = chk
+                     g("reward"), g("fallen"), g("traj_no"), g("step_no"), _p(out["checksum"]))
     return out
 
 
-def gae(r, v, v_next, absorbing, last, gamma, lam):
-    """Env-major [n_env, T] arrays."""
+def gae_buffers(n_env, n_steps):
+    return np.zeros((n_env, n_steps)), np.zeros((n_env, n_steps))
+
+
+def gae(r, v, v_next, absorbing, last, gamma, lam, out=None):
+    """Env-major [n_env, T] arrays.  ``out`` = (adv, v_target) preallocated (``gae_buffers``)."""
     r, v, v_next = (np.ascontiguousarray(a, np.float64) for a in (r, v, v_next))
     absorbing = np.ascontiguousarray(absorbing, np.uint8)
     last = np.ascontiguousarray(last, np.uint8)
-    adv, vt = np.zeros_like(r), np.zeros_like(r)
+    adv, vt = (np.zeros_like(r), np.zeros_like(r)) if out is None else out
     lib().or_gae(_p(r), _p(v), _p(v_next), _p(absorbing), _p(last), C.c_double(gamma), C.c_double(lam), r.shape[0], r.shape[1],
                  _p(adv), _p(vt))
     return vt, adv

@@ -94,17 +94,18 @@ def step(model, qpos, qvel, prev_obs):
 
 
 def play_trajectory_from_velocity(model, table, n_episodes, n_steps_per_episode, seed=0, env_id=0,
-                                  record_fk=True):
+                                  record_fk=True, traj_state=None):
     """One env of loco_env_base.py:444-560 (render/record off), recording what each step computes.
 
     Returns dict of arrays indexed [episode*n_steps + step]: qpos, qvel (sim state handed to
     mj_forward), xpos, xquat, site_xpos, cvel (its outputs), obs/fallen (from the NEXT trajectory
     sample, :539-541), reward (TargetVelocityReward on the previous obs, the step() convention),
-    traj_no / step_no / reset_count (integer state after the step).
+    traj_no / step_no / reset_count (integer state after the step).  ``traj_state``: the ``final["traj_state"]`` of a
+    previous call -- a SECOND call on the same env object (it begins with its own reset(), :481).
     """
     nj = len(perm(model))
     xv = x_vel_idx(model)
-    tr = TrajectoryState(table, seed=seed, env_id=env_id)
+    tr = TrajectoryState(table, seed=seed, env_id=env_id) if traj_state is None else traj_state
     rec = {k: [] for k in ("qpos", "qvel", "xpos", "xquat", "site_xpos", "cvel", "obs", "fallen",
                            "reward", "traj_no", "step_no", "reset_count")}
     tr.reset_trajectory()                                   # :481 reset()
@@ -142,7 +143,7 @@ def play_trajectory_from_velocity(model, table, n_episodes, n_steps_per_episode,
         curr_qpos = s[:nj].copy()                           # :557 (sample stays the stale one)
     out = {k: np.asarray(v) for k, v in rec.items() if len(v)}
     out["final"] = dict(traj_no=tr.traj_no, step_no=tr.step_no, reset_count=tr.reset_count,
-                        curr_qpos=curr_qpos, pending_sample=sample)
+                        curr_qpos=curr_qpos, pending_sample=sample, traj_state=tr)
     return out
 
 

@@ -34,6 +34,23 @@ def assert_close(actual, expected, name="", rtol=RTOL, atol=ATOL):
                              f"{actual[i]!r} vs {expected[i]!r} (err {err[i]:.3e}, tol {tol[i]:.3e})")
 
 
+_KNOB_DEFAULTS = dict(play_chunk=0, h1_split=-1, a3_split=-1, serial_scan=0, disc_vail2=-1, disc_pg2=-1)
+
+
+@pytest.fixture
+def om_knob():
+    """Set a tuning / test knob of libom_b200 (``om_debug_set``: forces a kernel variant) for one test; every knob is
+    back on automatic afterwards.  The library reads its OM_* environment variables only once, at load."""
+    from olympics_mujoco_b200 import _lib
+    lib = _lib.load()
+
+    def set_knob(name, value):
+        _lib.check(lib.om_debug_set(name.encode(), int(value)))
+    yield set_knob
+    for k, v in _KNOB_DEFAULTS.items():
+        lib.om_debug_set(k.encode(), v)
+
+
 @pytest.fixture(scope="session")
 def h1_model():
     from olympics_mujoco_b200 import mjcf

@@ -24,12 +24,12 @@ def _soa_t(x):
 
 
 @pytest.mark.parametrize("multi_step", [False, "fused", "time_parallel"])
-def test_a3_step_vs_reference_task_fixture(a3_model, multi_step, monkeypatch):
+def test_a3_step_vs_reference_task_fixture(a3_model, multi_step, om_knob):
     """One step per call; T steps in one call through the fused one-thread-per-env kernel; and through the
     time-parallel pair (FK pass over (env, t) + sequential task pass)."""
     import torch
     if multi_step:
-        monkeypatch.setenv("OM_A3_SPLIT", "1" if multi_step == "time_parallel" else "0")
+        om_knob("a3_split", int("1" if multi_step == "time_parallel" else "0"))
     gold = A.golden()
     n, T = gold["step_done"].shape
     task = _task(a3_model, n)
@@ -209,7 +209,7 @@ def test_stick_figure_a3_env_api(a3_model):
 
 
 @pytest.mark.parametrize("delay,radius", [(0, 5.0), (1, 5.0), (2, 0.9), (5, 0.6), (30, 5.0), (7, 0.35)])
-def test_a3_replay_state_machine_stress(a3_model, delay, radius, monkeypatch):
+def test_a3_replay_state_machine_stress(a3_model, delay, radius, om_knob):
     """The candidate-bit state machine of the time-parallel replay (feat -> walk -> post kernels) against the fused
     one-thread-per-env kernel under short delays and radii that make "target near" frequent or permanent: the target
     advances every few steps, the candidate chain clamps at the last target, calls split into sub-calls.  Integer state
@@ -224,7 +224,7 @@ def test_a3_replay_state_machine_stress(a3_model, delay, radius, monkeypatch):
     qpos, qvel, con = _soa_t(gold["step_qpos"]), _soa_t(gold["step_qvel"]), _soa_t(A.contact4(gold["step_contact"]))
     res = {}
     for split in ("0", "1"):
-        monkeypatch.setenv("OM_A3_SPLIT", split)
+        om_knob("a3_split", int(split))
         task = Kn.A3Task(dm, n, phase_clock_lut(), OA.init_qpos(), delay_frames=delay, target_radius=radius)
         ints = gold["reset_ints"].T.astype(np.int32).copy()
         ints[:, 3:] = np.array([[3, 4, 5, 1, 1, 20, 1]], np.int32).T         # some envs start mid-plan with frames pending

@@ -81,15 +81,15 @@ def test_loss_statistics_vs_reference_losses(noisy):
 
 
 @pytest.mark.parametrize("kernel", ["two_ctas_per_sm", "one_cta_per_sm", "one_producer_group"])
-def test_vail_forward_logit_and_kl_vs_oracle(kernel, monkeypatch):
+def test_vail_forward_logit_and_kl_vs_oracle(kernel, om_knob):
     """The fit's forward pass (logit + per-sample KL) out of the tcgen05 kernels against the float64 oracle and the
     reference network's own mu / logvar (discriminator_ref.npz); ragged sample counts."""
     import torch
     from olympics_mujoco_b200 import kernels as Kn
     from oracle import learner as L
-    monkeypatch.setenv("OM_DISC_VAIL2", "1" if kernel == "two_ctas_per_sm" else "0")
+    om_knob("disc_vail2", int("1" if kernel == "two_ctas_per_sm" else "0"))
     if kernel == "one_producer_group":
-        monkeypatch.setenv("OM_DISC_PG2", "0")
+        om_knob("disc_pg2", int("0"))
     g = np.load(GOLDEN / "discriminator_ref.npz")
     p = {k: g["v_" + k] for k in ("w1", "b1", "w2", "b2", "wmu", "bmu", "wlv", "blv", "wd", "bd")}
     disc = Kn.Discriminator("vail", p)

@@ -167,3 +167,138 @@ def test_set_sim_state_kernel_matches_named_scatter():
     from oracle import h1 as OH
     qo, vo = OH.set_sim_state(env._model, sample.cpu().numpy().astype(np.float64))
     assert np.array_equal(q1.cpu().numpy().T, qo.astype(np.float32)) and np.array_equal(v1.cpu().numpy().T, vo.astype(np.float32))
+
+
+def test_playback_resets_at_the_start_of_every_call_like_the_reference():
+    """loco_env_base.py:481: EVERY call of play_trajectory_from_velocity begins with reset() (a fresh draw), and every
+    episode ends with one.  Two calls on one env object == the oracle called twice on one trajectory state; the second
+    call's reset runs inside the playback kernel.  continue_episode=True (extension) carries the state on instead: two
+    one-episode calls == one two-episode call."""
+    import torch
+    from oracle import h1 as OH
+    n, T = 6, 70
+    for chunk_note, steps in (("sequential kernel", T), ("time-parallel kernel", 400)):
+        env = _make(n)
+        a = {k: v.clone() for k, v in env.play_trajectory_from_velocity(1, steps, render=False).items()}
+        b = env.play_trajectory_from_velocity(1, steps, render=False)
+        for e in range(n):
+            r1 = OH.play_trajectory_from_velocity(env._model, _table(), 1, steps, seed=77, env_id=e, record_fk=(e == 0))
+            r2 = OH.play_trajectory_from_velocity(env._model, _table(), 1, steps, seed=77, env_id=e, record_fk=(e == 0),
+                                                  traj_state=r1["final"]["traj_state"])
+            for out, ref in ((a, r1), (b, r2)):
+                assert np.array_equal(out["traj_no_t"][:, e].cpu().numpy(), ref["traj_no"]), chunk_note
+                assert np.array_equal(out["step_no_t"][:, e].cpu().numpy(), ref["step_no"]), chunk_note
+                assert np.array_equal(out["obs"][:, :, e].cpu().numpy(), ref["obs"].astype(np.float32))
+                assert_close(out["reward"][:, e].cpu().numpy(), ref["reward"], "reward")
+                if e == 0:
+                    assert_close(out["xpos"][:, :, e].cpu().numpy(), ref["xpos"].reshape(steps, 63), "xpos")
+            assert int(env.trajectories.device_state.reset_count[e]) == r2["final"]["reset_count"]
+        # the env is left in the state of the last reset(): its observation is the pending sample
+        tr = env.trajectories.device_state
+        tab = _table()
+        ref = np.stack([tab[2:, int(x), int(y)] for x, y in zip(tr.traj_no.cpu(), tr.step_no.cpu())]).astype(np.float32)
+        assert np.array_equal(env._obs.cpu().numpy(), ref)
+    env1, env2 = _make(n), _make(n)
+    two = env1.play_trajectory_from_velocity(2, T, render=False)
+    env2.play_trajectory_from_velocity(1, T, render=False)
+    cont = env2.play_trajectory_from_velocity(1, T, render=False, continue_episode=True)
+    for k in ("traj_no_t", "step_no_t", "obs", "xpos", "reward"):
+        assert torch.equal(two[k], cont[k]), k
+
+
+def test_playback_fused_observation_moments():
+    """S1 fused into the playback kernels: obs_moments == om_moments over the emitted observation buffer == float64 sums."""
+    import torch
+    from olympics_mujoco_b200 import kernels as Kn
+    for n, T in ((40, 33), (300, 260)):                       # sequential-in-time kernel, time-parallel kernel
+        env = _make(n)
+        mom = torch.zeros(65, dtype=torch.float64, device="cuda")
+        out = env.play_trajectory_from_velocity(1, T, render=False, obs_moments=mom)
+        ref = Kn.moments(out["obs"])
+        torch.cuda.synchronize()
+        o = out["obs"].double()
+        exact = torch.cat([o.sum(dim=(0, 2)), (o * o).sum(dim=(0, 2)), torch.tensor([float(n * T)], dtype=torch.float64, device="cuda")])
+        assert float(mom[64]) == n * T
+        assert_close(mom.cpu().numpy(), exact.cpu().numpy(), "fused moments vs float64 sums", rtol=1e-12, atol=1e-9)
+        assert_close(mom.cpu().numpy(), ref.cpu().numpy(), "fused moments vs om_moments", rtol=1e-12, atol=1e-9)
+        out2 = env.play_trajectory_from_velocity(1, T, render=False, obs_moments=mom)      # accumulates
+        assert float(mom[64]) == 2 * n * T
+
+
+def test_fused_live_step_matches_three_kernel_path_and_oracle():
+    """om_h1_live_step (one kernel: next sample / wrap reset + set_sim_state + FK + obs + has_fallen + reward) against
+    (a) om_traj_next -> om_set_sim_state -> om_h1_step bit for bit and (b) the oracle; step_graph replays == eager steps."""
+    import torch
+    from olympics_mujoco_b200 import kernels as Kn
+    from oracle import h1 as OH
+    from oracle.trajectory import TrajectoryState
+    n, steps = 48, 130                                        # table T = 50: every env wraps (and resets) at least twice
+    env, env_b = _make(n), _make(n)
+    obs0 = env.reset().clone()
+    env_b.reset()
+    trb = env_b.trajectories.device_state
+    sample = Kn.soa(34, n)
+    pxv = env_b._prev_x_vel.clone()
+    oracle_states = []
+    for e in range(3):
+        ts = TrajectoryState(_table(), seed=77, env_id=e)
+        ts.reset_trajectory()
+        oracle_states.append((ts, OH.create_observation(ts.get_current_sample())))
+    for s in range(steps):
+        obs, reward, absorbing, _ = env.step_trajectory()
+        trb.next(sample=sample)
+        Kn.set_sim_state(env_b._dm, env_b._spec, sample, env_b.data.qpos, env_b.data.qvel)
+        ref = Kn.h1_step(env_b._dm, env_b._spec, env_b.data.qpos, env_b.data.qvel, pxv)
+        assert torch.equal(obs, ref["obs"].t()) and torch.equal(reward, ref["reward"]), s
+        assert torch.equal(absorbing, ref["absorbing"].bool())
+        for k in ("xpos", "xquat", "site_xpos", "cvel", "qpos", "qvel"):
+            assert torch.equal(getattr(env.data, k), ref[k] if k in ref else getattr(env_b.data, k)), (k, s)
+        pxv = ref["obs"][15].clone()
+        for e, (ts, prev) in enumerate(oracle_states):
+            smp = ts.get_next_sample()
+            if smp is None:
+                smp = ts.reset_trajectory()
+            q, v = OH.set_sim_state(env._model, smp.astype(np.float32).astype(np.float64))
+            o = OH.step(env._model, q[None], v[None], prev[None])
+            assert np.array_equal(obs[e].cpu().numpy(), o["obs"][0].astype(np.float32))
+            assert_close(float(reward[e]), o["reward"][0], "reward")
+            assert_close(env.data.xpos[:, e].cpu().numpy().reshape(21, 3), o["xpos"][0], "xpos")
+            assert int(env.trajectories.device_state.step_no[e]) == ts.step_no
+            oracle_states[e] = (ts, o["obs"][0])
+    # graph: 2 replays x 16 captured steps == 32 eager steps from the same state
+    env_g, env_e = _make(n), _make(n)
+    env_g.reset(); env_e.reset()
+    replay, bufs = env_g.step_graph(16, want=("obs", "reward", "absorbing", "xpos", "wrapped"))
+    for r in range(2):
+        replay()
+        torch.cuda.synchronize()
+        for t in range(16):
+            obs, reward, absorbing, _ = env_e.step_trajectory()
+            assert torch.equal(bufs["obs"][t].t(), obs) and torch.equal(bufs["reward"][t], reward)
+            assert torch.equal(bufs["xpos"][t], env_e.data.xpos)
+    assert torch.equal(env_g.trajectories.device_state.step_no, env_e.trajectories.device_state.step_no)
+
+
+def test_step_with_soa_dynamics_needs_no_transposes():
+    import torch
+    env_a, env_s = _make(20), _make(20)
+    env_a.reset(); env_s.reset()
+    ga, gs = (torch.Generator(device="cuda").manual_seed(5) for _ in range(2))
+
+    def dyn_aos(e, ctrl):
+        dq = 0.01 * torch.randn((17, e.n_envs), device="cuda", generator=ga)
+        return (e.data.qpos + dq).t(), (e.data.qvel + 10 * dq).t()
+
+    def dyn_soa(e, ctrl):
+        assert tuple(ctrl.shape) == (11, e.n_envs)
+        dq = 0.01 * torch.randn((17, e.n_envs), device="cuda", generator=gs)
+        return e.data.qpos + dq, e.data.qvel + 10 * dq
+
+    env_a.attach_dynamics(dyn_aos)
+    env_s.attach_dynamics(dyn_soa, soa=True)
+    act = torch.rand((20, 11), device="cuda") * 2 - 1
+    for _ in range(3):
+        oa, ra, aa, _ = env_a.step(act)
+        os_, rs, as_, _ = env_s.step(act.t().contiguous())
+        assert torch.equal(oa, os_) and torch.equal(ra, rs) and torch.equal(aa, as_)
+        assert torch.equal(env_a.data.xpos, env_s.data.xpos)

@@ -20,7 +20,7 @@ def _h1_setup(n, seed, env_id0=0):
     return model, table, dm, spec, traj, state
 
 
-def test_h1_playback_full_size_properties(monkeypatch):
+def test_h1_playback_full_size_properties(om_knob):
     """4096 envs x 500 steps: (1) the time-parallel kernel and the sequential-in-time kernel agree bit for bit on every
     integer / gathered output and within the path's 1e-5 tolerance on the FK outputs; (2) the observation is exactly the
     table row of the recorded (traj_no, step_no); (3) the index advances by one except at wrap resets, which happen exactly at step_no == T; (4) quaternions are unit; (5) the reward is
@@ -30,7 +30,7 @@ def test_h1_playback_full_size_properties(monkeypatch):
     n, T, seed = 4096, 500, 4242
     outs = {}
     for chunk in ("7", "1000000"):
-        monkeypatch.setenv("OM_PLAY_CHUNK", chunk)
+        om_knob("play_chunk", int(chunk))
         model, table, dm, spec, traj, state = _h1_setup(n, seed)
         out = Kn.h1_play_from_velocity(dm, spec, traj, state, T)
         torch.cuda.synchronize()
@@ -66,7 +66,7 @@ def test_h1_playback_full_size_properties(monkeypatch):
     assert torch.isfinite(out["cvel"]).all() and torch.isfinite(out["xpos"]).all()
 
 
-def test_a3_rollout_full_size_properties(a3_model, monkeypatch):
+def test_a3_rollout_full_size_properties(a3_model, om_knob):
     """16384 envs x 64 steps: the fused kernel and the time-parallel pair agree (integers and flags bit for bit,
     floats to fp32 rounding); phase advances mod 88; done == (root z - lowest foot site z < 0.6) | bad collision as
     recomputed from the K1 kernel's outputs; observation rows that are pure copies are exact."""
@@ -79,7 +79,7 @@ def test_a3_rollout_full_size_properties(a3_model, monkeypatch):
     g = torch.Generator(device="cuda").manual_seed(3)
     res = {}
     for split in ("0", "1"):
-        monkeypatch.setenv("OM_A3_SPLIT", split)
+        om_knob("a3_split", int(split))
         task = Kn.A3Task(dm, n, phase_clock_lut(), OA.init_qpos(), seed=11)
         q0, v0 = Kn.soa(25, n), Kn.soa(24, n)
         task.reset(q0, v0, iteration_count=6000.0)

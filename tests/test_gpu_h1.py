@@ -23,9 +23,9 @@ def _spec(model, **kw):
 
 
 @pytest.mark.parametrize("threads_per_env", ["3", "1"])     # h1_step_split_kernel (default) / h1_step_kernel
-def test_h1_step_parity(h1_model, h1_states, threads_per_env, monkeypatch):
+def test_h1_step_parity(h1_model, h1_states, threads_per_env, om_knob):
     import torch
-    monkeypatch.setenv("OM_H1_SPLIT", "1" if threads_per_env == "3" else "0")
+    om_knob("h1_split", int("1" if threads_per_env == "3" else "0"))
     from olympics_mujoco_b200 import kernels as Kn
     from oracle import h1 as OH
     qpos, qvel = h1_states
@@ -126,9 +126,9 @@ def test_trajectory_state_machine():
 
 @pytest.mark.parametrize("chunk", ["1", "7", "100000"])      # time-parallel x2, sequential-in-time kernel
 @pytest.mark.parametrize("n_episodes,n_steps", [(1, 120), (3, 37)])
-def test_play_trajectory_from_velocity_parity(h1_model, n_episodes, n_steps, chunk, monkeypatch):
+def test_play_trajectory_from_velocity_parity(h1_model, n_episodes, n_steps, chunk, om_knob):
     import torch
-    monkeypatch.setenv("OM_PLAY_CHUNK", chunk)
+    om_knob("play_chunk", int(chunk))
     from olympics_mujoco_b200 import kernels as Kn
     from oracle import h1 as OH
     tab = _table()
@@ -164,10 +164,10 @@ def test_play_trajectory_from_velocity_parity(h1_model, n_episodes, n_steps, chu
 
 @pytest.mark.parametrize("chunk", ["1", "7", "100000"])      # time-parallel x2, sequential-in-time kernel
 @pytest.mark.parametrize("n_episodes,n_steps", [(1, 120), (3, 37)])
-def test_play_trajectory_forced_parity(h1_model, n_episodes, n_steps, chunk, monkeypatch):
+def test_play_trajectory_forced_parity(h1_model, n_episodes, n_steps, chunk, om_knob):
     """om_h1_play_trajectory (LocoEnvBase.play_trajectory, loco_env_base.py:338-442) against the oracle."""
     import torch
-    monkeypatch.setenv("OM_PLAY_CHUNK", chunk)
+    om_knob("play_chunk", int(chunk))
     from olympics_mujoco_b200 import kernels as Kn
     from oracle import h1 as OH
     tab = _table()

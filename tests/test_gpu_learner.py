@@ -37,10 +37,10 @@ def test_ppo_returns_vs_reference_buffer():
 
 @pytest.mark.parametrize("serial", [False, True])
 @pytest.mark.parametrize("T,n", [(64, 1000), (1, 5), (37, 1), (500, 45)])
-def test_ppo_returns_segmented(T, n, serial, monkeypatch):
+def test_ppo_returns_segmented(T, n, serial, om_knob):
     from olympics_mujoco_b200 import kernels as Kn
     if serial:
-        monkeypatch.setenv("OM_SERIAL_SCAN", "1")
+        om_knob("serial_scan", int("1"))
     from oracle import learner as L
     rng = np.random.default_rng(T + n)
     r = rng.normal(0, 1, (T, n)).astype(np.float32)
@@ -56,10 +56,10 @@ def test_ppo_returns_segmented(T, n, serial, monkeypatch):
 
 @pytest.mark.parametrize("serial", [False, True])                 # affine-scan kernel / one-thread-per-env kernel
 @pytest.mark.parametrize("T,n", [(64, 513), (1000, 3), (500, 70), (1, 1), (1500, 33)])
-def test_gae_vs_mushroom_restatement(T, n, serial, monkeypatch):
+def test_gae_vs_mushroom_restatement(T, n, serial, om_knob):
     from olympics_mujoco_b200 import kernels as Kn
     if serial:
-        monkeypatch.setenv("OM_SERIAL_SCAN", "1")
+        om_knob("serial_scan", int("1"))
     from oracle import learner as L
     rng = np.random.default_rng(T * 7 + n)
     r = rng.normal(0, 1, (T, n)).astype(np.float32)

@@ -1,6 +1,7 @@
 """GPU test of the NVLink mailbox all-reduce ABI (csrc/om_mailbox.cu) in a single process: a world of one rank is the
 identity, repeated rounds alternate the parity slots, sizes up to 128 values.  The multi-rank check (bit-identical sums on
-every rank, equal to NCCL, late ranks) is tools/check_mailbox.py under torchrun; bench.py uses the mailbox at N > 1."""
+every rank, equal to NCCL, late and timed-out ranks) is tests/test_gpu_mailbox_multi.py (torchrun / two GPUs); bench.py
+checks the mailbox against NCCL bit for bit at N > 1 (`collective_check`)."""
 import ctypes as C
 
 import numpy as np
@@ -33,5 +34,10 @@ def test_mailbox_world_of_one_is_identity_over_many_rounds():
         _lib.check(lib.om_mailbox_timed_out(h, C.byref(flag)))
         assert flag.value == 0
         assert lib.om_mailbox_allreduce(h, None, None, 129, st) != 0          # more than 128 values: refused
+        _lib.check(lib.om_mailbox_set_timeout_ms(h, 0.0))                     # 0 = wait for ever
+        _lib.check(lib.om_mailbox_allreduce(h, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), n, st))
+        torch.cuda.synchronize()
+        assert torch.equal(x, y)
+        assert lib.om_mailbox_set_timeout_ms(h, -1.0) != 0
     finally:
         lib.om_mailbox_destroy(h)

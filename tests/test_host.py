@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, f"declared but not exported: {missing}"
     assert declared == set(_lib.PROTOTYPES), "ctypes prototypes out of sync with the header"
-    assert _lib.load().om_abi_version() == 1
+    assert _lib.load().om_abi_version() == 2
 
 
 def test_compute_entry_points_fail_loudly_without_gpu():

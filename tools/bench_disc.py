@@ -13,6 +13,38 @@ sys.path.insert(0, str(ROOT))
 FLOP = {"vail": 2 * (32 * 256 + 256 * 128 + 2 * 128 * 128 + 128), "gail": 2 * (32 * 512 + 512 * 256 + 256)}
 
 
+_TF32_PEAK = None
+
+
+def tf32_peak():
+    """Dense TF32 tensor-pipe rate MEASURED on this GPU: cuBLAS fp32 matmul with TF32 allowed, 8192^3, best of 10 (CUDA
+    events) -- the same recipe MEASURED_PEAKS.json uses for bf16.  A measuring stick only: no library GEMM is on the path."""
+    global _TF32_PEAK
+    if _TF32_PEAK is None:
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            m = 8192
+            a = torch.randn((m, m), device="cuda")
+            b = torch.randn((m, m), device="cuda")
+            for _ in range(3):
+                a @ b
+            torch.cuda.synchronize()
+            best = float("inf")
+            for _ in range(10):
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                a @ b
+                t1.record()
+                torch.cuda.synchronize()
+                best = min(best, t0.elapsed_time(t1))
+            _TF32_PEAK = 2.0 * m ** 3 / (best * 1e-3) / 1e12
+            del a, b
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+    return _TF32_PEAK
+
+
 def measure(envs=65536, steps=50, warmup=5):
     args = argparse.Namespace(envs=envs, steps=steps, warmup=warmup)
     res = []
@@ -44,11 +76,12 @@ def measure(envs=65536, steps=50, warmup=5):
             tot += t0.elapsed_time(t1)
         ms = tot / args.steps
         useful = FLOP[kind] * n / (ms * 1e-3) / 1e12
-        peak_tf32 = peaks["bf16_tflops"] / 2
-        res.append({"workload": f"{kind.upper()} discriminator reward, {n} envs (configs[3])", "ms": ms,
+        peak_tf32 = tf32_peak()
+        res.append({"workload": f"{kind.upper()} discriminator reward, {n} envs (configs[3])", "net": kind, "ms": ms,
                     "value": n / (ms * 1e-3), "unit": "samples/s",
                     "roofline": {"bound": "tensor", "achieved": useful, "executed_3xtf32": 3 * useful, "unit": "TFLOP/s",
-                                 "peak": peak_tf32, "peak_note": "measured bf16 burst / 2 (TF32 rate)",
+                                 "peak": peak_tf32, "peak_note": "TF32 matmul 8192^3 measured in this process (best of 10)",
+                                 "bf16_burst_half": peaks["bf16_tflops"] / 2,
                                  "frac": useful / peak_tf32, "frac_executed": 3 * useful / peak_tf32,
                                  "flop_per_sample": FLOP[kind]}})
     return res

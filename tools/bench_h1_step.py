@@ -63,6 +63,34 @@ def measure(envs=1 << 20, steps=20, warmup=3):
         return t0.elapsed_time(t1) / (reps * steps)
 
     ms, kms = replay(g_step), replay(g_kernel)
+    # the FUSED live step (om_h1_live_step: next sample + scatter + FK + obs + flag + reward in one kernel, one C call with
+    # pre-bound arguments): graph-replayed and launched eagerly from Python
+    pxv = sample[17].clone()
+    live = Kn.H1LiveStep(dm, spec, traj, pxv, out=dict(out, qpos=qpos, qvel=qvel))
+    for _ in range(warmup):
+        live()
+    g_live = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        live.rebind(stream=side.cuda_stream)
+        live()
+        side.synchronize()
+        with torch.cuda.graph(g_live, stream=side):
+            for _ in range(steps):
+                live()
+    torch.cuda.synchronize()
+    live.rebind()
+    live_graph_ms = replay(g_live)
+    live_eager = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(4 * steps):
+            live()
+        t1.record()
+        torch.cuda.synchronize()
+        live_eager.append(t0.elapsed_time(t1) / (4 * steps))
+    live_eager_ms = min(live_eager)
     # the same loop launched eagerly from Python, for the record
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
@@ -73,9 +101,12 @@ def measure(envs=1 << 20, steps=20, warmup=3):
     eager_ms = t0.elapsed_time(t1) / steps
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {"hbm_gbs": 6650.0}
     kernel_bytes = 136 + 1104 + 128 + 4 + 1 + 4                     # qpos/qvel in, FK + obs + reward + flag out, prev x-vel
+    # live_step_frac: the fused live step on SURVEY 8(d)'s 1517 B/env-step (it additionally writes the qpos / qvel mirrors)
     ach = kernel_bytes * n / (kms * 1e-3) / 1e9
     return {"workload": f"UnitreeH1 single env step, {n} envs (configs[4] per-GPU shard at N=1)", "value": n / (ms * 1e-3),
             "unit": "env-steps/s", "ms_per_step": ms, "h1_step_kernel_ms": kms, "eager_python_loop_ms_per_step": eager_ms,
+            "live_step_ms": live_graph_ms, "live_step_eager_ms": live_eager_ms,
+            "live_step_frac": BYTES_PER_ENV_STEP * n / (live_graph_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
             "timing": "CUDA-graph replay of `steps` consecutive env steps",
             "roofline": {"bound": "hbm", "kernel": "h1_step_kernel<WRITE_FK> (h1_step_split_kernel up to 32768 envs)", "achieved": ach, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "bytes_per_env_step": kernel_bytes}}
