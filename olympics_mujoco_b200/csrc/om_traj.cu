@@ -111,20 +111,9 @@ OM_HD void play_fk(const double (&qs)[17], const float (&dq)[17], const OmPlayOu
 }
 
 // obs / fallen / reward / integer state of one step from the freshly gathered sample row
-//   acc (may be null): this thread's column of the CTA's float64 observation-moment accumulators in shared memory,
-//   rows 0..31 = sum, 32..63 = sum of squares, row stride ACC_STRIDE
 constexpr int PLAY_BLOCK = 128;
-OM_HD void play_emit(const float (&samp)[36], float prev_x_vel, const PlayArgs& a, size_t slot, size_t env, int tr, int st,
-                     double* acc = nullptr) {
+OM_HD void play_emit(const float (&samp)[36], float prev_x_vel, const PlayArgs& a, size_t slot, size_t env, int tr, int st) {
   const size_t ld = a.ld;
-  if (acc) {
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const double v = (double)samp[k + 2];
-      acc[k * PLAY_BLOCK] += v;
-      acc[(32 + k) * PLAY_BLOCK] = fma(v, v, acc[(32 + k) * PLAY_BLOCK]);
-    }
-  }
   if (a.o.obs) {
     float* ob = a.o.obs + slot * 32 * ld + env;
 #pragma unroll
@@ -139,30 +128,75 @@ OM_HD void play_emit(const float (&samp)[36], float prev_x_vel, const PlayArgs& 
   if (a.o.step_no_t) a.o.step_no_t[slot * ld + env] = st;
 }
 
-// S1 fused into the playback (was a second pass over the [T][32][n] observation buffer: 262 MB re-read per 4096 x 500
-// rollout): every thread adds the observation rows it emits to its own float64 column in shared memory (64 KB per CTA,
-// no registers -- the FK already uses 254), the CTA folds the 128 columns once at the end and issues 64 float64 atomic
-// adds into obs_moments = [sum[32], sumsq[32], count] (om_moments layout; Standardizer networks.py:76-81,
-// RunningMeanStd normalize.py:190-208).
-OM_HD void play_acc_zero(double* acc_all) {
-  for (int i = threadIdx.x; i < 64 * PLAY_BLOCK; i += PLAY_BLOCK) acc_all[i] = 0.0;
-  __syncthreads();
-}
-OM_HD void play_acc_reduce(const double* acc_all, double* __restrict__ obs_moments) {
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int row = warp; row < 64; row += PLAY_BLOCK / 32) {
-    double s = 0.0;
+// S1 of the playback WITHOUT touching the observation buffer: every observation a playback call emits is a row of the
+// (L2-resident) trajectory table, and an env walks the table in contiguous runs -- rows st0+1 .. T-1 of its trajectory, then
+// after each wrap reset rows st' .. of the drawn one.  With float64 prefix sums of the rows and of their squares
+// (TrajDev::psum, 1 MB for 4 x 500 samples) the moment sums of a whole call are a few prefix differences per env and
+// channel: one small kernel instead of a second pass over the [T][32][n] observation buffer (262 MB re-read per 4096 x 500 rollout; an
+// in-kernel accumulation through shared memory cost the playback kernel 75 us of LSU bandwidth).  Layout of the result:
+// om_moments' [sum[32], sumsq[32], count] (Standardizer networks.py:76-81, RunningMeanStd normalize.py:190-208).
+constexpr int PM_ENVS = 4;     // envs per warp
+__global__ void __launch_bounds__(256) play_moments_kernel(PlayArgs a, OmPlayState start, int start_reset) {
+  // a warp takes PM_ENVS envs one after the other with its LANES ON THE 64 STATISTIC ROWS (lane l: rows l and l + 32), so
+  // that every prefix-table access is one coalesced 256-byte read and no cross-lane reduction is needed; the 8 warps of
+  // the CTA meet in shared memory: 64 atomics per 32 envs.  (One thread per env with 64 accumulators each made every load
+  // a 32-way scattered access: 34 us for 4096 envs; per-warp atomics queued 2048 same-line float64 updates: 12 us.)
+  __shared__ double part[8][64];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int env0 = (blockIdx.x * 8 + w) * PM_ENVS;
+  const int T = a.t.T;
+  int tr_[PM_ENVS], st_[PM_ENVS];
+  uint32_t rc_[PM_ENVS];
 #pragma unroll
-    for (int c = 0; c < PLAY_BLOCK / 32; ++c) s += acc_all[row * PLAY_BLOCK + c * 32 + lane];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0 && s != 0.0) atomicAdd(obs_moments + row, s);
+  for (int u = 0; u < PM_ENVS; ++u) {                  // the state loads of all envs first (independent round trips)
+    const int env = env0 + u;
+    const bool live = env < a.n;
+    tr_[u] = live ? start.traj_no[env] : 0;
+    st_[u] = live ? start.step_no[env] : 0;
+    rc_[u] = live ? start.reset_count[env] : 0u;
   }
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+  for (int u = 0; u < PM_ENVS; ++u) {
+    const int env = env0 + u;
+    if (env >= a.n) break;
+    int tr = tr_[u], st = st_[u];
+    uint32_t rc = rc_[u];
+    if (start_reset) { traj_draw(a.t, a.seed, a.env_id0 + env, rc, tr, st); ++rc; }
+    int left = a.n_steps;
+    int lo = st + 1;                                   // the start row itself was emitted by the previous step / by reset()
+    while (left > 0) {
+      if (lo >= T) {                                   // wrap -> reset: the drawn sample itself is the next observation
+        traj_draw(a.t, a.seed, a.env_id0 + env, rc, tr, st);
+        ++rc;
+        lo = st;
+      }
+      const int hi = min(T, lo + left);                // rows lo .. hi-1
+      const double* p_lo = a.t.psum + ((size_t)tr * (T + 1) + lo) * 64 + lane;
+      const double* p_hi = a.t.psum + ((size_t)tr * (T + 1) + hi) * 64 + lane;
+      const double h0 = __ldg(p_hi), h1 = __ldg(p_hi + 32), l0 = __ldg(p_lo), l1 = __ldg(p_lo + 32);
+      s0 += h0 - l0;
+      s1 += h1 - l1;
+      left -= hi - lo;
+      lo = hi;
+    }
+  }
+  part[w][lane] = s0;
+  part[w][lane + 32] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += part[k][threadIdx.x];
+    if (v != 0.0) atomicAdd(a.obs_moments + threadIdx.x, v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.obs_moments + 64, (double)a.n * (double)a.n_steps);
 }
 
-template <int BLOCK, bool MOM>
-__device__ __forceinline__ void play_h1_seq_body(const PlayArgs& a, int env, double* acc) {
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) play_h1_seq_kernel(PlayArgs a) {
+  const int env = blockIdx.x * BLOCK + threadIdx.x;
+  if (env >= a.n) return;
   const size_t ld = a.ld, e = env;
   int tr = a.s.traj_no[e], st = a.s.step_no[e];
   uint32_t rc = a.s.reset_count[e];
@@ -209,7 +243,7 @@ __device__ __forceinline__ void play_h1_seq_body(const PlayArgs& a, int env, dou
     }
 #pragma unroll
     for (int k = 0; k < 17; ++k) dq[k] = samp[17 + k];
-    play_emit(samp, pxv, a, (size_t)s, e, tr, st, MOM ? acc : nullptr);              // :539-541
+    play_emit(samp, pxv, a, (size_t)s, e, tr, st);                                   // :539-541
     pxv = samp[17];
   }
   // write the loop's `sample` variable back (x, y re-centred) before the end-of-episode reset
@@ -238,19 +272,6 @@ __device__ __forceinline__ void play_h1_seq_body(const PlayArgs& a, int env, dou
 #pragma unroll
   for (int k = 0; k < 17; ++k) if (a.s.curr_qpos) a.s.curr_qpos[k * ld + e] = cq[k];
   a.s.prev_x_vel[e] = pxv;
-}
-
-template <int BLOCK, bool MOM>
-__global__ void __launch_bounds__(BLOCK) play_h1_seq_kernel(PlayArgs a) {
-  static_assert(BLOCK == PLAY_BLOCK, "accumulator layout");
-  extern __shared__ double play_acc[];
-  const int env = blockIdx.x * BLOCK + threadIdx.x;
-  if (MOM) play_acc_zero(play_acc);
-  if (env < a.n) play_h1_seq_body<BLOCK, MOM>(a, env, play_acc + threadIdx.x);
-  if (MOM) {
-    play_acc_reduce(play_acc, a.obs_moments);
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.obs_moments + 64, (double)a.n * (double)a.n_steps);
-  }
 }
 
 // ---------------------------------------------------------------- fused playback, time-parallel
@@ -322,8 +343,10 @@ __global__ void __launch_bounds__(256) play_snapshot_kernel(PlayArgs a, OmPlaySt
 // reconstruct the loop state in front of ANY step j0 in O(#resets) and then walk `chunk` steps exactly like
 // the sequential kernel.  grid = (env tiles, time chunks): 4096 envs x 500 steps become ~300k threads
 // instead of 4096, which is what lets a 4096-env rollout fill the 148 SMs.
-template <int BLOCK, bool MOM>
-__device__ __forceinline__ void play_h1_tp_body(const PlayArgs& a, int chunk, int env, double* acc) {
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) play_h1_tp_kernel(PlayArgs a, int chunk) {
+  const int env = blockIdx.x * BLOCK + threadIdx.x;
+  if (env >= a.n) return;
   const int j0 = blockIdx.y * chunk, j1 = min(j0 + chunk, a.n_steps);
   const size_t ld = a.ld, e = env;
   const int T = a.t.T;
@@ -417,7 +440,7 @@ __device__ __forceinline__ void play_h1_tp_body(const PlayArgs& a, int chunk, in
     }
 #pragma unroll
     for (int k = 0; k < 17; ++k) dq[k] = samp[17 + k];
-    play_emit(samp, pxv, a, (size_t)s, e, tr, st, MOM ? acc : nullptr);
+    play_emit(samp, pxv, a, (size_t)s, e, tr, st);
     pxv = samp[17];
   }
   if (j1 != a.n_steps) return;
@@ -445,19 +468,6 @@ __device__ __forceinline__ void play_h1_tp_body(const PlayArgs& a, int chunk, in
 #pragma unroll
   for (int k = 0; k < 17; ++k) if (a.s.curr_qpos) a.s.curr_qpos[k * ld + e] = cq[k];
   a.s.prev_x_vel[e] = pxv;
-}
-
-template <int BLOCK, bool MOM>
-__global__ void __launch_bounds__(BLOCK) play_h1_tp_kernel(PlayArgs a, int chunk) {
-  static_assert(BLOCK == PLAY_BLOCK, "accumulator layout");
-  extern __shared__ double play_acc[];
-  const int env = blockIdx.x * BLOCK + threadIdx.x;
-  if (MOM) play_acc_zero(play_acc);
-  if (env < a.n) play_h1_tp_body<BLOCK, MOM>(a, chunk, env, play_acc + threadIdx.x);
-  if (MOM) {
-    play_acc_reduce(play_acc, a.obs_moments);
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(a.obs_moments + 64, (double)a.n * (double)a.n_steps);
-  }
 }
 
 // ---------------------------------------------------------------- fused live step
@@ -569,12 +579,29 @@ extern "C" int om_traj_create(const double* table, int K, int n_traj, int T, OmT
       for (int k = 0; k < nq; ++k)
         cdq[((size_t)tr * (T + 1) + s + 1) * nq + k] =
             cdq[((size_t)tr * (T + 1) + s) * nq + k] + (double)rows[((size_t)tr * T + s) * kpad + nq + k];
+  // exclusive prefix sums of the emitted observation rows (channels 2 .. K-1, fp32-rounded as stored) and of their squares,
+  // float64: psum[tr][i][c] = sum_{j<i} row_j[c+2], psum[tr][i][32+c] = sum_{j<i} row_j[c+2]^2  (34-key tables only)
+  std::vector<double> psum;
+  if (K == 34) {
+    psum.assign((size_t)n_traj * (T + 1) * 64, 0.0);
+    for (int tr = 0; tr < n_traj; ++tr)
+      for (int s = 0; s < T; ++s)
+        for (int c = 0; c < 32; ++c) {
+          const double v = (double)rows[((size_t)tr * T + s) * kpad + c + 2];
+          const size_t at = ((size_t)tr * (T + 1) + s) * 64;
+          psum[at + 64 + c] = psum[at + c] + v;
+          psum[at + 64 + 32 + c] = psum[at + 32 + c] + v * v;
+        }
+  }
   OmTraj* t = new OmTraj();
   t->d.K = K; t->d.kpad = kpad; t->d.n_traj = n_traj; t->d.T = T;
   float* drows = nullptr;
   double* dxy = nullptr;
   double* dcdq = nullptr;
+  double* dpsum = nullptr;
   cudaError_t e = cudaMalloc(&drows, rows.size() * sizeof(float));
+  if (e == cudaSuccess && !psum.empty()) e = cudaMalloc(&dpsum, psum.size() * sizeof(double));
+  if (e == cudaSuccess && !psum.empty()) e = cudaMemcpy(dpsum, psum.data(), psum.size() * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&dxy, xy.size() * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&dcdq, cdq.size() * sizeof(double));
   if (e == cudaSuccess) e = cudaMemcpy(drows, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -584,12 +611,14 @@ extern "C" int om_traj_create(const double* table, int K, int n_traj, int T, OmT
     if (drows) cudaFree(drows);
     if (dxy) cudaFree(dxy);
     if (dcdq) cudaFree(dcdq);
+    if (dpsum) cudaFree(dpsum);
     delete t;
     return fail("om_traj_create: device upload failed: %s (no CPU path)", cudaGetErrorString(e));
   }
   t->d.rows = drows;
   t->d.xy = dxy;
   t->d.cdq = dcdq;
+  t->d.psum = dpsum;
   *out = t;
   return 0;
 }
@@ -599,6 +628,7 @@ extern "C" void om_traj_destroy(OmTraj* t) {
   cudaFree((void*)t->d.rows);
   cudaFree((void*)t->d.xy);
   cudaFree((void*)t->d.cdq);
+  if (t->d.psum) cudaFree((void*)t->d.psum);
   if (t->scratch) cudaFree(t->scratch);
   delete t;
 }
@@ -660,14 +690,11 @@ static int play_impl(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, ui
   a.obs_moments = out->obs_moments;
   constexpr int BLOCK = PLAY_BLOCK;
   const bool mom = a.obs_moments != nullptr;
-  const size_t acc_bytes = mom ? (size_t)64 * PLAY_BLOCK * sizeof(double) : 0;
-  static const bool smem_opt_in = [] {              // 64 KB of dynamic shared memory for the moment columns: opt in once
-    const int bytes = 64 * PLAY_BLOCK * (int)sizeof(double);
-    cudaFuncSetAttribute(play_h1_seq_kernel<BLOCK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(play_h1_tp_kernel<BLOCK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    return true;
-  }();
-  (void)smem_opt_in;
+  OM_REQUIRE(!mom || t->d.psum, "om_h1_play_from_velocity: this trajectory handle has no prefix tables");
+  if (mom) {                                        // reads the START state: before anything below touches it
+    play_moments_kernel<<<ceil_div(n, 8 * PM_ENVS), 256, 0, (cudaStream_t)stream>>>(a, a.s, start_reset ? 1 : 0);
+    OM_LAUNCHED();
+  }
   // time-parallel when the env count alone cannot fill the machine (148 SMs x 2048 threads)
   const long long target_threads = 148LL * 2048;
   const long long chunks_wanted = target_threads / n > 0 ? target_threads / n : 1;
@@ -679,8 +706,7 @@ static int play_impl(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, ui
       play_start_reset_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(a);
       OM_LAUNCHED();
     }
-    if (mom) play_h1_seq_kernel<BLOCK, true><<<ceil_div(n, BLOCK), BLOCK, acc_bytes, (cudaStream_t)stream>>>(a);
-    else play_h1_seq_kernel<BLOCK, false><<<ceil_div(n, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(a);
+    play_h1_seq_kernel<BLOCK><<<ceil_div(n, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(a);
   } else {
     // the carried state is read by every chunk and overwritten by the last one: snapshot the episode-start
     // state (stream-ordered scratch) so that no thread can observe another's end-of-episode write
@@ -706,8 +732,7 @@ static int play_impl(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, ui
     else play_snapshot_kernel<false><<<ceil_div(n, 256), 256, 0, st>>>(a, a.s, a.snap, n, ld);
     OM_LAUNCHED();
     dim3 grid(ceil_div(n, BLOCK), ceil_div(n_steps, chunk));
-    if (mom) play_h1_tp_kernel<BLOCK, true><<<grid, BLOCK, acc_bytes, st>>>(a, chunk);
-    else play_h1_tp_kernel<BLOCK, false><<<grid, BLOCK, 0, st>>>(a, chunk);
+    play_h1_tp_kernel<BLOCK><<<grid, BLOCK, 0, st>>>(a, chunk);
     OM_LAUNCHED();
     return 0;
   }

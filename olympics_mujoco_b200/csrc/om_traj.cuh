@@ -9,6 +9,8 @@ struct TrajDev {
   const double* xy;    // [n_traj][T][2]   channels 0,1 (root x, y) in float64
   const double* cdq;   // [n_traj][T+1][K/2] exclusive prefix sums of the velocity channels (float64):
                        //   cdq[tr][i][k] = sum_{j<i} rows[tr][j][K/2+k]  (time-parallel playback)
+  const double* psum;  // [n_traj][T+1][64] exclusive prefix sums of the observation rows (channels 2..33) and of their
+                       //   squares, float64 (S1 of a playback call as prefix differences); null unless K == 34
   int K, kpad, n_traj, T;
 };
 

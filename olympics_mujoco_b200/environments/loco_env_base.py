@@ -89,6 +89,20 @@ class LocoEnvBase:
         self._play_state = None
         self._live = None
 
+    # the current observation (mushroom's ``self._obs``); a fused playback call leaves it to be derived on first use
+    @property
+    def _obs(self):
+        lazy = self.__dict__.get("_obs_lazy")
+        if lazy is not None:
+            self.__dict__["_obs_value"] = lazy()
+            self.__dict__["_obs_lazy"] = None
+        return self.__dict__.get("_obs_value")
+
+    @_obs.setter
+    def _obs(self, value):
+        self.__dict__["_obs_value"] = value
+        self.__dict__["_obs_lazy"] = None
+
     # ------------------------------------------------------------------ registry / factory
     @classmethod
     def register(cls):

@@ -188,6 +188,11 @@ class UnitreeH1(BaseHumanoidRobot):
             ctrl = Kn.action_affine(self._action_kernel_spec, action)               # [nu, n], no transposes
             qpos, qvel = self._dynamics(self, ctrl)
             assert qpos.shape == d.qpos.shape and qvel.shape == d.qvel.shape, "SoA dynamics return [nq, n], [nv, n]"
+            if qpos is not d.qpos:                            # a dynamics that writes env.data.qpos / qvel in place and
+                d.qpos.copy_(qpos)                            # returns them costs no copy at all
+            if qvel is not d.qvel:
+                d.qvel.copy_(qvel)
+            qpos, qvel = d.qpos, d.qvel
         else:
             ctrl = self._preprocess_action(self._batched(action))
             qpos, qvel = self._dynamics(self, ctrl)
@@ -245,8 +250,13 @@ class UnitreeH1(BaseHumanoidRobot):
         side.wait_stream(torch.cuda.current_stream())
         base = dict(live.out)
         graph = torch.cuda.CUDAGraph()
+        tr = self.trajectories.device_state
+        carried = [tr.traj_no, tr.step_no, tr.reset_count, tr.xy_off, self._prev_x_vel]
         with torch.cuda.stream(side):
+            saved = [t.clone() for t in carried]
             live.rebind(out={k: v[0] for k, v in bufs.items()}, stream=side.cuda_stream)()      # warm-up outside the capture
+            for t, s0 in zip(carried, saved):                                                   # ... that leaves no trace
+                t.copy_(s0)
             side.synchronize()
             with torch.cuda.graph(graph, stream=side):
                 for t in range(n_steps):
@@ -302,8 +312,9 @@ class UnitreeH1(BaseHumanoidRobot):
             res = Kn.h1_play_from_velocity(self._dm, self._spec, dev, self._play_state, n_steps_per_episode, dt=self.dt,
                                            end_episode_reset=True, out=out, forced=forced, obs_moments=obs_moments,
                                            start_reset=start_reset and ep == 0, **kw)
-        # the env is left in the state of the final reset(): the pending sample is its observation
-        self._obs = self._play_state["pending"][2:].t()
+        # the env is left in the state of the final reset() (:432 / :555): its observation is that sample's, fetched on
+        # first use (the loop's `sample` variable -- our `pending` -- stays the stale one, as in the reference)
+        self.__dict__["_obs_lazy"] = lambda: self._create_observation(self.trajectories.get_current_sample())
         return res
 
     def play_trajectory(self, n_episodes=None, n_steps_per_episode=None, render=False, record=False, recorder_params=None,

@@ -251,8 +251,11 @@ def test_fused_live_step_matches_three_kernel_path_and_oracle():
         ref = Kn.h1_step(env_b._dm, env_b._spec, env_b.data.qpos, env_b.data.qvel, pxv)
         assert torch.equal(obs, ref["obs"].t()) and torch.equal(reward, ref["reward"]), s
         assert torch.equal(absorbing, ref["absorbing"].bool())
-        for k in ("xpos", "xquat", "site_xpos", "cvel", "qpos", "qvel"):
-            assert torch.equal(getattr(env.data, k), ref[k] if k in ref else getattr(env_b.data, k)), (k, s)
+        for k in ("qpos", "qvel"):
+            assert torch.equal(getattr(env.data, k), getattr(env_b.data, k)), (k, s)
+        for k in ("xpos", "xquat", "site_xpos", "cvel"):     # same generated FK inlined into two kernels (the three-kernel
+            # path may take the three-threads-per-env variant): equal to fp32 rounding, not necessarily bit for bit
+            assert_close(getattr(env.data, k).cpu().numpy(), ref[k].cpu().numpy(), f"{k} step {s}", rtol=2e-6, atol=2e-6)
         pxv = ref["obs"][15].clone()
         for e, (ts, prev) in enumerate(oracle_states):
             smp = ts.get_next_sample()
