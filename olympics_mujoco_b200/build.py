@@ -45,6 +45,9 @@ def generate():
     _write_if_changed(GEN / "fk_stick_figure_a3.cuh", "#pragma once\n" + codegen.generate_fk(a3, "om_fk_stick_figure_a3"))
     _write_if_changed(GEN / "fk_pos_stick_figure_a3.cuh",
                       "#pragma once\n" + codegen.generate_fk_pos(a3, "om_fk_pos_stick_figure_a3"))
+    # float64 twin of the position FK: the exact slow path of the A3 threshold decisions (done, target_reached)
+    _write_if_changed(GEN / "fk_pos_f64_stick_figure_a3.cuh",
+                      "#pragma once\n" + codegen.generate_fk_pos(a3, "om_fk_pos_f64_stick_figure_a3", scalar="double"))
     parts = codegen.split_parts(h1, 3)
     _write_if_changed(GEN / "fk_unitree_h1_parts.cuh", "#pragma once\n" + "".join(
         codegen.generate_fk(h1, f"om_fk_unitree_h1_part{k}", part=p) for k, p in enumerate(parts)))

@@ -21,12 +21,23 @@ import numpy as np
 from .mjcf import JNT_BALL, JNT_FREE, JNT_HINGE, JNT_SLIDE
 
 
+# Scalar type of the code being emitted: "float" (the kernels' arithmetic) or "double" (the exact slow path of the A3
+# threshold decisions, generate_fk_pos(..., scalar="double")).  Constants are rounded to fp32 only in float mode.
+_SCALAR = "float"
+
+
 def _f(x):
-    """Shortest fp32 literal that round-trips."""
+    """Shortest literal that round-trips in the scalar type being emitted."""
+    if _SCALAR == "double":
+        return repr(float(x)) if float(x) != int(float(x)) or abs(float(x)) > 1e15 else f"{float(x):.1f}"
     v = np.float32(x)
     if v == 0:
         return "0.0f"
     return np.format_float_scientific(v, unique=True, trim="0") + "f"
+
+
+def _num(c):
+    return float(c) if _SCALAR == "double" else np.float32(c)
 
 
 class E:
@@ -34,7 +45,7 @@ class E:
     __slots__ = ("c", "n")
 
     def __init__(self, c=None, n=None):
-        self.c = None if c is None else float(np.float32(c))
+        self.c = None if c is None else (float(c) if _SCALAR == "double" else float(np.float32(c)))
         self.n = n
 
     @property
@@ -59,7 +70,7 @@ class Gen:
     def tmp(self, expr):
         self.k += 1
         name = f"t{self.k}"
-        self.emit(f"float {name} = {expr};")
+        self.emit(f"{_SCALAR} {name} = {expr};")
         return E(n=name)
 
     # ---- scalar algebra with folding
@@ -70,7 +81,7 @@ class Gen:
 
     def mul(self, a, b):
         if a.is_const and b.is_const:
-            return E(np.float32(a.c) * np.float32(b.c))
+            return E(_num(a.c) * _num(b.c))
         if a.is_const:
             a, b = b, a
         if b.is_const:
@@ -84,7 +95,7 @@ class Gen:
 
     def add(self, a, b):
         if a.is_const and b.is_const:
-            return E(np.float32(a.c) + np.float32(b.c))
+            return E(_num(a.c) + _num(b.c))
         if a.is_const and a.c == 0.0:
             return b
         if b.is_const and b.c == 0.0:
@@ -93,7 +104,7 @@ class Gen:
 
     def sub(self, a, b):
         if a.is_const and b.is_const:
-            return E(np.float32(a.c) - np.float32(b.c))
+            return E(_num(a.c) - _num(b.c))
         if b.is_const and b.c == 0.0:
             return a
         if a.is_const and a.c == 0.0:
@@ -107,7 +118,7 @@ class Gen:
         if (a.is_const and a.c == 0.0) or (b.is_const and b.c == 0.0):
             return c
         if a.is_const and b.is_const:
-            return self.add(E(np.float32(a.c) * np.float32(b.c)), c)
+            return self.add(E(_num(a.c) * _num(b.c)), c)
         if c.is_const and c.c == 0.0:
             return self.mul(a, b)
         if a.is_const and a.c == 1.0:
@@ -118,7 +129,7 @@ class Gen:
             return self.sub(c, b)
         if b.is_const and b.c == -1.0:
             return self.sub(c, a)
-        return self.tmp(f"fmaf({a}, {b}, {c})")
+        return self.tmp(f"{'fma' if _SCALAR == 'double' else 'fmaf'}({a}, {b}, {c})")
 
     def dot(self, a, b):
         acc = ZERO
@@ -173,7 +184,7 @@ class Gen:
             a = a / np.linalg.norm(a)
             return [E(x) for x in a]
         n2 = self.dot(q, q)
-        inv = self.tmp(f"rsqrtf({n2})")
+        inv = self.tmp(f"1.0 / sqrt({n2})" if _SCALAR == "double" else f"rsqrtf({n2})")
         return [self.mul(x, inv) for x in q]
 
     def quat2mat(self, q):
@@ -387,7 +398,17 @@ def generate_fk(model, fn_name, part=None):
     return head + body + "\n}\n"
 
 
-def generate_fk_pos(model, fn_name):
+def generate_fk_pos(model, fn_name, scalar="float"):
+    global _SCALAR, ZERO, ONE
+    prev = _SCALAR
+    _SCALAR = scalar
+    try:
+        return _generate_fk_pos(model, fn_name)
+    finally:
+        _SCALAR = prev
+
+
+def _generate_fk_pos(model, fn_name):
     """Position/velocity-only variant for consumers that never read body orientations (the A3 walking task reads
     xpos / site_xpos / point velocities and the root quaternion, which is qpos itself): the chain is carried as
     ROTATION MATRICES, so an axis-aligned hinge costs 12 multiply-adds (two columns rotate) instead of a quaternion
@@ -422,7 +443,7 @@ def generate_fk_pos(model, fn_name):
 
     q_in = lambda k: E(n=f"q[{k}]")
     qd_in = lambda k: E(n=f"qd[{k}]")
-    g.emit("S.xpos(0, 0.0f, 0.0f, 0.0f);")
+    g.emit(f"S.xpos(0, {_f(0.0)}, {_f(0.0)}, {_f(0.0)});")
     for i in range(1, nb):
         g.emit(f"// ---- body {i}: {model.body_names[i]}")
         pid = int(model.body_parentid[i])
@@ -466,7 +487,10 @@ def generate_fk_pos(model, fn_name):
                 if jt == JNT_SLIDE:
                     p = g.vfma(axis_w, dq, p)
                 elif jt == JNT_HINGE:
-                    g.emit(f"float s{j}, c{j}; om::om_sincos_hinge({dq}, &s{j}, &c{j});")
+                    if _SCALAR == "double":
+                        g.emit(f"double s{j}, c{j}; sincos({dq}, &s{j}, &c{j});")
+                    else:
+                        g.emit(f"float s{j}, c{j}; om::om_sincos_hinge({dq}, &s{j}, &c{j});")
                     sj, cj = E(n=f"s{j}"), E(n=f"c{j}")
                     # Rodrigues: c I + (1 - c) a a^T + s [a]x, constants folded (axis-aligned: four live entries)
                     omc = None
@@ -474,7 +498,7 @@ def generate_fk_pos(model, fn_name):
                     rodr = []
                     for r in range(3):
                         for c in range(3):
-                            aa = float(np.float32(ax[r] * ax[c]))
+                            aa = float(_num(ax[r] * ax[c]))
                             if abs(aa - (1.0 if r == c else 0.0)) < 1e-7 and abs(K[r][c]) < 1e-7 and r == c:
                                 rodr.append(ONE)               # diagonal entry on the axis itself
                                 continue
@@ -510,8 +534,8 @@ def generate_fk_pos(model, fn_name):
     body = "\n".join(g.lines)
     head = (f"// GENERATED by olympics_mujoco_b200/codegen.py (generate_fk_pos) from model '{model.name}' "
             f"(fingerprint {model_fingerprint(model)}) -- do not edit.\n"
-            f"template <class Sink>\nOM_HD void {fn_name}(const float (&q)[{model.nq}], "
-            f"const float (&qd)[{model.nv}], Sink& S) {{\n")
+            f"template <class Sink>\nOM_HD void {fn_name}(const {_SCALAR} (&q)[{model.nq}], "
+            f"const {_SCALAR} (&qd)[{model.nv}], Sink& S) {{\n")
     return head + body + "\n}\n"
 
 

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(BLOCK) a3_task_kernel(A3Args a) {
       in = a3_task_in(S.f);
     }
     const int fl = (int)con[3];
-    a3_task_step(a.C, in, s, tc, seq, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, obs, terms, total, done);
+    a3_task_step(a.C, A3Exact{a.qpos + (size_t)t * A3_NQ * ld + e, ld}, in, s, tc, seq, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, obs, terms, total, done);
     if (a.o.obs) {
       float* ob = a.o.obs + (size_t)t * A3_NOBS * ld + e;
 #pragma unroll
@@ -161,12 +161,13 @@ __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w
   om_fk_pos_stick_figure_a3(q, qd, S);           // matrix-chain variant: no body orientations needed
   bool done;
   const int fl = (int)con[3];
+  const A3Exact ex{qp, ld};                      // float64 site positions: re-read and computed only if a decision is within A3_BAND
   const A3Rec rec = a3_task_pre(a.C, a3_task_in(S.f), phase, mode, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, terms,
-                                obs[31], obs[32], done);
+                                obs[31], obs[32], done, ex);
   a3_rec_store(rec, w.feat + (size_t)t * A3_NREC * ld + e, ld);
   const int nc = a3_cand_needed(t, a.ints[A3I_FRAMES * ld + e], a.C.delay_frames, ncand);   // later targets are out of reach
   w.near[e * w.tp + t] =
-      (uint8_t)a3_near_bits(a.C, rec.lsite, rec.rsite, nc, t1_0, t2_0, seq_len, SeqGlobal{a.sequence + e, ld});
+      (uint8_t)a3_near_bits(a.C, rec.lsite, rec.rsite, nc, t1_0, t2_0, seq_len, SeqGlobal{a.sequence + e, ld}, ex);
   if (a.o.obs) {
     float* ob = a.o.obs + (size_t)t * A3_NOBS * ld + e;
 #pragma unroll
@@ -349,6 +350,7 @@ extern "C" int om_a3_task_create(const OmA3TaskDesc* d, OmA3Task** out) {
   t->C.inv_vmax = 1.0f / t->C.vmax;
   t->C.target_radius = d->target_radius;
   t->C.near_d2 = a3_near_d2(d->target_radius);
+  a3_near_band(d->target_radius, &t->C.near_lo2, &t->C.near_hi2);
   t->C.goal_height_ref = d->goal_height_ref;
   t->C.deadzone = 0.01 + 0.05 * d->goal_speed_ref;
   t->C.lut = t->lut;

@@ -15,6 +15,7 @@
 #include "gen/a3_ids.h"
 #include "gen/fk_stick_figure_a3.cuh"
 #include "gen/fk_pos_stick_figure_a3.cuh"
+#include "gen/fk_pos_f64_stick_figure_a3.cuh"
 
 namespace om {
 
@@ -29,6 +30,7 @@ struct A3TaskConst {
   float inv_fmax, inv_vmax;           // their fp32 reciprocals (x / xmax as one multiply)
   double target_radius;               // walking_task.py:333
   float near_d2;                      // smallest fp32 d2 with (double)sqrtf(d2) >= target_radius (a3_near_d2)
+  float near_lo2, near_hi2;           // (radius -+ A3_BAND)^2 rounded outwards: outside [lo2, hi2] the fp32 test decides
   double goal_height_ref, deadzone;   // StickFigureA3.py:110; rewards.py:36 (0.01 + 0.05*goal_speed_ref)
   const float* lut;                   // [period][6]: r_frc, r_vel, l_frc, l_vel clocks, sin/cos(2 pi phase/period)
 };
@@ -83,6 +85,74 @@ struct A3Sink {
     else if (b == OM_A3_RFOOT) { f.rw = V3{wx, wy, wz}; f.rv = V3{vx, vy, vz}; }
   }
 };
+
+// ---------------------------------------------------------------- exact threshold decisions (A10 target_reached, A12 done)
+// The reference takes both decisions in float64 on MuJoCo's float64 site positions (walking_task.py:266-283, :298-319).
+// Here the site positions come out of an fp32 chain (error ~1e-6 m), so a decision whose fp32 margin is below A3_BAND
+// (1e-5 m, ten times the chain's error) is RE-EVALUATED from a float64 forward pass of the same fp32 inputs
+// (gen/fk_pos_f64_*.cuh, generated from the same tables): the flags are then functions of the float64 arithmetic alone,
+// i.e. bit-identical to the float64 oracle on the same (fp32-representable) qpos / contact / sequence inputs.  About one
+// env-step in 10^4 takes the slow path; it is one out-of-line call.
+constexpr double A3_BAND = 1e-5;
+struct A3SiteSinkF64 {
+  static constexpr bool want_site_xmat = false;
+  double ls[3], rs[3];
+  OM_HD void xpos(int, double, double, double) {}
+  OM_HD void xquat(int, double, double, double, double) {}
+  OM_HD void site_xpos(int s, double x, double y, double z) {
+    if (s == OM_A3_LSITE) { ls[0] = x; ls[1] = y; ls[2] = z; }
+    else if (s == OM_A3_RSITE) { rs[0] = x; rs[1] = y; rs[2] = z; }
+  }
+  OM_HD void vel_p(int, double, double, double, double, double, double) {}
+};
+struct A3SitesF64 { double ls[3], rs[3]; };
+// q: component k of the env-step's qpos at q[k * ld] (the kernels pass the global SoA pointer: the slow path re-reads its 25
+// inputs instead of keeping the caller's register copy alive and addressable)
+OM_NOINLINE A3SitesF64 a3_sites_f64(const float* q, size_t ld) {
+  double qd[A3_NQ], v0[A3_NV];
+#pragma unroll
+  for (int k = 0; k < A3_NQ; ++k) qd[k] = (double)q[k * ld];
+#pragma unroll
+  for (int k = 0; k < A3_NV; ++k) v0[k] = 0.0;
+  A3SiteSinkF64 S{};
+  om_fk_pos_f64_stick_figure_a3(qd, v0, S);
+  A3SitesF64 r;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { r.ls[k] = S.ls[k]; r.rs[k] = S.rs[k]; }
+  return r;
+}
+// where the slow path finds the env-step's qpos
+struct A3Exact {
+  const float* q;
+  size_t ld;
+  OM_HD A3SitesF64 get() const { return a3_sites_f64(q, ld); }
+};
+// done (:298-319): root z (= qpos[2], exact) - lowest foot-site z < 0.6
+OM_HD bool a3_done_height(float root_z, float lz, float rz, const A3Exact& ex) {
+  const double h = (double)root_z - (double)fminf(lz, rz);
+  if (fabs(h - 0.6) > A3_BAND) return h < 0.6;
+  const A3SitesF64 s = ex.get();
+  return (double)root_z - fmin(s.ls[2], s.rs[2]) < 0.6;
+}
+// "a foot is within target_radius of p" (:266-269): np.linalg.norm(foot - target) < radius, either foot
+OM_HD bool a3_near_exact(const A3TaskConst& C, V3 lsite, V3 rsite, V3 p, const A3Exact& ex) {
+  const V3 a = lsite - p, b = rsite - p;
+  const float dl2 = dot(a, a), dr2 = dot(b, b);
+  if (dl2 < C.near_lo2 || dr2 < C.near_lo2) return true;          // certainly inside
+  if (dl2 > C.near_hi2 && dr2 > C.near_hi2) return false;         // certainly outside
+  const A3SitesF64 s = ex.get();
+  const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
+  const double lx = s.ls[0] - px, ly = s.ls[1] - py, lz = s.ls[2] - pz;
+  const double rx = s.rs[0] - px, ry = s.rs[1] - py, rz = s.rs[2] - pz;
+  return sqrt(lx * lx + ly * ly + lz * lz) < C.target_radius || sqrt(rx * rx + ry * ry + rz * rz) < C.target_radius;
+}
+inline void a3_near_band(double radius, float* lo2, float* hi2) {     // host: task creation, test harness
+  float lo = (float)((radius - A3_BAND) * (radius - A3_BAND)), hi = (float)((radius + A3_BAND) * (radius + A3_BAND));
+  while ((double)lo > (radius - A3_BAND) * (radius - A3_BAND)) lo = nextafterf(lo, 0.f);
+  while ((double)hi < (radius + A3_BAND) * (radius + A3_BAND)) hi = nextafterf(hi, INFINITY);
+  *lo2 = radius > A3_BAND ? lo : 0.f;
+  *hi2 = hi;
+}
 
 struct A3TaskRegs { int phase, t1, t2, frames, mode, seq_len, reached; };
 
@@ -177,13 +247,13 @@ OM_HD void a3_obs_robot(const float (&q)[A3_NQ], const float (&qd)[A3_NV], float
 // WalkingTask.step + calc_reward + done for one env.  Seq: float operator()(int step, int component); `tc` caches
 // sequence[t1] / sequence[t2] across steps.  Fills obs[31..40], the six weighted terms, their sum and done.
 template <class Seq>
-OM_HD void a3_task_step(const A3TaskConst& C, const A3TaskIn& f, A3TaskRegs& s, A3Targets& tc, const Seq& seq, float l_grf,
-                        float r_grf, float min_z, bool foot_contact, bool bad_collision, float (&obs)[A3_NOBS],
-                        float (&terms)[6], float& total, bool& done) {
+OM_HD void a3_task_step(const A3TaskConst& C, const A3Exact& ex, const A3TaskIn& f, A3TaskRegs& s, A3Targets& tc,
+                        const Seq& seq, float l_grf, float r_grf, float min_z, bool foot_contact, bool bad_collision,
+                        float (&obs)[A3_NOBS], float (&terms)[6], float& total, bool& done) {
   s.phase += 1;                                                      // :248-250
   if (s.phase >= C.period) s.phase = 0;
   float dl = norm3(f.lsite - tc.p1), dr = norm3(f.rsite - tc.p1);    // :266-283
-  if ((double)dl < C.target_radius || (double)dr < C.target_radius) {
+  if (a3_near_exact(C, f.lsite, f.rsite, tc.p1, ex)) {
     s.reached = 1;
     s.frames += 1;
   } else {
@@ -251,8 +321,8 @@ OM_HD void a3_task_step(const A3TaskConst& C, const A3TaskIn& f, A3TaskRegs& s, 
   terms[0] = 0.150f * frc; terms[1] = 0.150f * vel; terms[2] = 0.050f * orient;
   terms[3] = 0.050f * height; terms[4] = 0.450f * step_r; terms[5] = 0.050f * upper;
   total = ((((terms[0] + terms[1]) + terms[2]) + terms[3]) + terms[4]) + terms[5];      // StickFigureA3.py:192
-  // ---- done :298-319 (difference of the fp32 heights taken in double, threshold in double)
-  done = ((double)f.root_p.z - (double)fminf(f.lsite.z, f.rsite.z) < 0.6) || bad_collision;
+  // ---- done :298-319 (float64 decision, see a3_done_height)
+  done = a3_done_height(f.root_p.z, f.lsite.z, f.rsite.z, ex) || bad_collision;
 }
 
 // ---------------------------------------------------------------- time-parallel split of the step tail
@@ -287,7 +357,7 @@ OM_HD A3Rec a3_rec_load(const float* b, size_t ld) {
 // (env, t)-parallel part.  `phase` is the phase AFTER this step's increment.  Writes terms[0,1,3,5], obs[31,32], done.
 OM_HD A3Rec a3_task_pre(const A3TaskConst& C, const A3TaskIn& f, int phase, int mode, float l_grf, float r_grf, float min_z,
                         bool foot_contact, bool bad_collision, float (&terms)[6], float& clock_sin, float& clock_cos,
-                        bool& done) {
+                        bool& done, const A3Exact& ex) {
   const float* lrow = C.lut + (size_t)phase * A3_LUT_COLS;
   clock_sin = lrow[4];
   clock_cos = lrow[5];
@@ -305,7 +375,7 @@ OM_HD A3Rec a3_task_pre(const A3TaskConst& C, const A3TaskIn& f, int phase, int 
   const float hx = f.head_x - f.root_p.x, hy = f.head_y - f.root_p.y;
   const float upper = expf(-10.f * fmaf(hx, hx, hy * hy));
   terms[0] = 0.150f * frc; terms[1] = 0.150f * vel; terms[3] = 0.050f * height; terms[5] = 0.050f * upper;
-  done = ((double)f.root_p.z - (double)fminf(f.lsite.z, f.rsite.z) < 0.6) || bad_collision;           // :298-319
+  done = a3_done_height(f.root_p.z, f.lsite.z, f.rsite.z, ex) || bad_collision;                       // :298-319
   A3Rec r;
   r.root_p = f.root_p; r.root_q = f.root_q; r.lsite = f.lsite; r.rsite = f.rsite;
   r.t01 = terms[0] + terms[1]; r.t3 = terms[3]; r.t5 = terms[5];
@@ -342,14 +412,14 @@ inline float a3_near_d2(double radius) {
   return t;
 }
 template <class Seq>
-OM_HD uint32_t a3_near_bits(const A3TaskConst& C, V3 lsite, V3 rsite, int ncand, int t1_0, int t2_0, int seq_len, const Seq& seq) {
+OM_HD uint32_t a3_near_bits(const A3TaskConst& C, V3 lsite, V3 rsite, int ncand, int t1_0, int t2_0, int seq_len, const Seq& seq,
+                            const A3Exact& ex) {
   uint32_t bits = 0;
 #pragma unroll 1
   for (int j = 0; j < ncand; ++j) {
     const int k = a3_cand(j, t1_0, t2_0, seq_len);
     const V3 p{seq(k, 0), seq(k, 1), seq(k, 2)};
-    const V3 a = lsite - p, b = rsite - p;
-    if (dot(a, a) < C.near_d2 || dot(b, b) < C.near_d2) bits |= 1u << j;        // norm3(.) < target_radius, see a3_near_d2
+    if (a3_near_exact(C, lsite, rsite, p, ex)) bits |= 1u << j;                 // float64 decision near the radius
   }
   return bits;
 }

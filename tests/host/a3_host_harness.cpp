@@ -14,6 +14,7 @@ static A3TaskConst make_const(const float* lut6, int period, int delay, double r
   A3TaskConst C;
   C.period = period; C.delay_frames = delay; C.fmax = fmax; C.vmax = 0.2f; C.inv_fmax = 1.0f / fmax; C.inv_vmax = 1.0f / 0.2f;
   C.target_radius = radius; C.near_d2 = a3_near_d2(radius); C.goal_height_ref = gh; C.deadzone = dz; C.lut = lut6;
+  a3_near_band(radius, &C.near_lo2, &C.near_hi2);
   return C;
 }
 
@@ -42,7 +43,7 @@ extern "C" void host_a3_rollout(const float* lut6, int period, int delay, double
     A3Sink<NullFkSink> S{};
     om_fk_pos_stick_figure_a3(q, qd, S);
     const int fl = (int)c[3];
-    a3_task_step(C, a3_task_in(S.f), s, tc, SeqHost{seq}, c[0], c[1], c[2], (fl & 1) != 0, (fl & 2) != 0, o, tr, total, d);
+    a3_task_step(C, A3Exact{qpos + t * A3_NQ, 1}, a3_task_in(S.f), s, tc, SeqHost{seq}, c[0], c[1], c[2], (fl & 1) != 0, (fl & 2) != 0, o, tr, total, d);
     std::memcpy(obs + t * A3_NOBS, o, sizeof o);
     std::memcpy(terms + t * 6, tr, sizeof tr);
     reward[t] = total;
@@ -69,8 +70,9 @@ extern "C" void host_a3_rollout_split(const float* lut6, int period, int delay, 
     om_fk_pos_stick_figure_a3(q, qd, S);
     const int fl = (int)c[3];
     const int phase = (ints[0] + t + 1) % period;
+    const A3Exact ex{qpos + t * A3_NQ, 1};
     const A3Rec r = a3_task_pre(C, a3_task_in(S.f), phase, ints[4], c[0], c[1], c[2], (fl & 1) != 0, (fl & 2) != 0, tr, o[31],
-                                o[32], d);
+                                o[32], d, ex);
     a3_rec_store(r, rec + (size_t)t * A3_NREC, 1);
     std::memcpy(obs + t * A3_NOBS, o, 33 * sizeof(float));
     terms[t * 6 + 0] = tr[0]; terms[t * 6 + 1] = tr[1]; terms[t * 6 + 3] = tr[3]; terms[t * 6 + 5] = tr[5];
@@ -86,7 +88,8 @@ extern "C" void host_a3_rollout_split(const float* lut6, int period, int delay, 
     const int t1_0 = st[1], t2_0 = st[2], sl = st[5];
     for (int t = c0; t < c0 + len; ++t) {
       const A3Rec r = a3_rec_load(rec + (size_t)t * A3_NREC, 1);
-      near[t] = (uint8_t)a3_near_bits(C, r.lsite, r.rsite, a3_cand_needed(t - c0, st[3], delay, nc), t1_0, t2_0, sl, SeqHost{seq});
+      const A3Exact ex{qpos + t * A3_NQ, 1};
+      near[t] = (uint8_t)a3_near_bits(C, r.lsite, r.rsite, a3_cand_needed(t - c0, st[3], delay, nc), t1_0, t2_0, sl, SeqHost{seq}, ex);
     }
     A3Walk w{0, st[3], st[6]};
     for (int t = c0; t < c0 + len; ++t) {
@@ -145,6 +148,14 @@ extern "C" int host_a3_walk_pruning_check(int delay, int frames0, int reached0, 
     if (full.j >= ncand) return -1;            // beyond the call's candidate budget (the ABI cuts calls before this)
   }
   return -1;
+}
+
+// float64 site positions of the exact-decision slow path (gen/fk_pos_f64_*.cuh) for the oracle comparison
+extern "C" void host_a3_sites_f64(const float* qpos, int n, double* lsite, double* rsite) {
+  for (int i = 0; i < n; ++i) {
+    const A3SitesF64 s = a3_sites_f64(qpos + (size_t)i * A3_NQ, 1);
+    for (int k = 0; k < 3; ++k) { lsite[3 * i + k] = s.ls[k]; rsite[3 * i + k] = s.rs[k]; }
+  }
 }
 
 // closed-form root roll / pitch quaternion (a3_root_orient) next to the literal quat2euler -> euler2quat path

@@ -92,3 +92,27 @@ def test_fk_properties_large(h1_model):
     assert float(cv[:, :3].abs().max()) == 0.0
     ref = torch.tensor([0.7, -0.2, 0.1], device="cuda").view(1, 3, 1)
     assert float((cv[:, 3:] - ref).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("name,builtin,force_generic", [("h1", "unitree_h1", False), ("h1", "unitree_h1", True),
+                                                        ("h1_arms", "unitree_h1_arms", False),
+                                                        ("a3", "stick_figure_a3", False), ("a3", "stick_figure_a3", True)])
+def test_fk_vs_independent_checker_fixture(name, builtin, force_generic):
+    """The CUDA kernels against the INDEPENDENT checker's fixture (tools/fk_independent.py: own MJCF reader, homogeneous
+    transforms, numerically differentiated velocities) -- not against the oracle the kernels were developed with."""
+    from conftest import GOLDEN
+    from olympics_mujoco_b200 import mjcf
+    g = np.load(GOLDEN / "fk_independent_ref.npz")
+    model = mjcf.load_builtin(builtin)
+    q, v = g[name + "_qpos"], g[name + "_qvel"]
+    n = q.shape[0]
+    dm, out = _run(model, q, v, force_generic)
+    assert_close(out["xpos"].T.reshape(n, model.nbody, 3), g[name + "_xpos"], "xpos")
+    quat = out["xquat"].T.reshape(n, model.nbody, 4)
+    ref_q = g[name + "_xquat"]
+    s = np.sign(np.sum(quat * ref_q, axis=-1, keepdims=True))
+    assert_close(quat, ref_q * np.where(s == 0, 1.0, s), "xquat (up to the sign of the quaternion)")
+    assert_close(out["site_xpos"].T.reshape(n, model.nsite, 3), g[name + "_site_xpos"], "site_xpos")
+    assert_close(out["site_xmat"].T.reshape(n, model.nsite, 3, 3), g[name + "_site_xmat"], "site_xmat")
+    assert_close(out["cvel"].T.reshape(n, model.nbody, 6), g[name + "_cvel"], "cvel")
+    assert_close(out["subtree_com"].T, g[name + "_subtree_com"][:, 1], "subtree_com")

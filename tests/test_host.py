@@ -332,3 +332,45 @@ def test_perfect_dataset_conversion_matches_reference_restatement():
             np.testing.assert_allclose(got[k], ref[k], rtol=0, atol=1e-12, err_msg=k)
     assert list(got["split_points"]) == [0, 41, 42, 121, 257]
     assert got["q_pelvis_tx"][41] == 0.0 and got["q_pelvis_tx"][42] == 0.0 and got["q_pelvis_tx"][121] == 0.0
+
+
+def test_a3_threshold_decisions_are_float64_exact_on_host(a3_model):
+    """A10 target_reached / A12 done: the fp32 device functions decide near their thresholds through a float64 forward
+    pass of the same inputs (om_a3_task.cuh: a3_done_height, a3_near_exact).  On adversarial inputs whose margin is a few
+    fp32 ulps (1e-8 m; the fp32 chain's own error is 1e-6 m) every flag equals the float64 oracle's -- no excusals."""
+    import a3_common as A
+    from olympics_mujoco_b200 import build
+    from oracle import a3 as OA
+    from oracle import kinematics as K
+    build.generate()
+    d = Path(tempfile.mkdtemp())
+    csrc = ROOT / "olympics_mujoco_b200" / "csrc"
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-I", str(csrc), str(ROOT / "tests/host/a3_host_harness.cpp"),
+                           "-o", str(d / "a3.so")])
+    lib = ctypes.CDLL(str(d / "a3.so"))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    cases = A.threshold_cases(a3_model, n=200, seed=3)
+    q = np.ascontiguousarray(cases["qpos"])
+    n = len(q)
+    assert cases["planted"].mean() > 0.95 and np.median(cases["margin"]) < 1e-6
+    assert 0.1 < cases["want_done"].mean() < 0.9 and 0.1 < cases["want_reached"].mean() < 0.9
+    # the float64 twin of the position FK against the oracle
+    ls, rs = np.zeros((n, 3)), np.zeros((n, 3))
+    lib.host_a3_sites_f64(P(q), n, P(ls), P(rs))
+    fk = K.forward(a3_model, q.astype(np.float64), np.zeros((n, 24)))
+    assert_close(ls, fk["site_xpos"][:, a3_model.site_id("lf_force")], "float64 left site", rtol=1e-13, atol=1e-13)
+    assert_close(rs, fk["site_xpos"][:, a3_model.site_id("rf_force")], "float64 right site", rtol=1e-13, atol=1e-13)
+    lut = np.ascontiguousarray(A.lut6())
+    consts = (P(lut), OA.PERIOD, OA.DELAY_FRAMES, ctypes.c_double(0.2), ctypes.c_double(0.80), ctypes.c_double(0.01),
+              ctypes.c_float(a3_model.total_mass * 9.8 * 0.5))
+    v, con = np.zeros(24, np.float32), np.array([100.0, 100.0, 0.0, 1.0], np.float32)
+    for fn in (lib.host_a3_rollout, lib.host_a3_rollout_split):
+        got_done, got_reached = np.zeros(n, bool), np.zeros(n, bool)
+        for i in range(n):
+            ints, seq = cases["ints"][i].copy(), np.ascontiguousarray(cases["seq"][i])
+            obs, terms = np.zeros(41, np.float32), np.zeros(6, np.float32)
+            rew, dn = np.zeros(1, np.float32), np.zeros(1, np.uint8)
+            fn(*consts, P(q[i]), P(v), P(con), 1, P(ints), P(seq), P(obs), P(terms), P(rew), P(dn))
+            got_done[i], got_reached[i] = bool(dn[0]), bool(ints[6])
+        assert np.array_equal(got_done, cases["want_done"]), np.flatnonzero(got_done != cases["want_done"])
+        assert np.array_equal(got_reached, cases["want_reached"]), np.flatnonzero(got_reached != cases["want_reached"])
