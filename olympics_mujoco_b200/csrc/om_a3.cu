@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(BLOCK) a3_task_kernel(A3Args a) {
       in = a3_task_in(S.f);
     }
     const int fl = (int)con[3];
-    a3_task_step(a.C, A3Exact{a.qpos + (size_t)t * A3_NQ * ld + e, ld}, in, s, tc, seq, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, obs, terms, total, done);
+    a3_task_step(a.C, A3Exact{a.qpos + (size_t)t * A3_NQ * ld + e, ld, false, false}, in, s, tc, seq, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, obs, terms, total, done);
     if (a.o.obs) {
       float* ob = a.o.obs + (size_t)t * A3_NOBS * ld + e;
 #pragma unroll
@@ -124,6 +124,8 @@ struct A3Scratch {
   int tp;
   int32_t* start;       // [2][ld]   t1, t2 at the start of the call
   float* trig;          // [A3_MAX_CAND + 1][4][ld]   sin, cos of candidate j's heading and of half of it (feat t = 0 -> post)
+  uint32_t* fix_count;  // number of env-steps whose threshold decisions a3_fix_kernel re-takes in float64
+  uint32_t* fix_list;   // [T * n]  t * n + env
 };
 
 // one env-step of the (env, t)-parallel pass
@@ -161,7 +163,7 @@ __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w
   om_fk_pos_stick_figure_a3(q, qd, S);           // matrix-chain variant: no body orientations needed
   bool done;
   const int fl = (int)con[3];
-  const A3Exact ex{qp, ld};                      // float64 site positions: re-read and computed only if a decision is within A3_BAND
+  A3Exact ex{qp, ld, true, false};               // decisions within A3_BAND of a threshold are only NOTED here (a3_fix_kernel)
   const A3Rec rec = a3_task_pre(a.C, a3_task_in(S.f), phase, mode, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, terms,
                                 obs[31], obs[32], done, ex);
   a3_rec_store(rec, w.feat + (size_t)t * A3_NREC * ld + e, ld);
@@ -178,6 +180,37 @@ __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w
     tp[0] = terms[0]; tp[ld] = terms[1]; tp[3 * ld] = terms[3]; tp[5 * ld] = terms[5];
   }
   if (a.o.done) a.o.done[(size_t)t * ld + e] = done ? 1 : 0;
+  if (ex.unsure) w.fix_list[atomicAdd(w.fix_count, 1u)] = (uint32_t)t * (uint32_t)a.n + (uint32_t)e;
+}
+
+// Re-takes, in float64, the threshold decisions the (env, t)-parallel pass could not settle in fp32 (margin below A3_BAND:
+// about one env-step in 10^4): `done` and the candidate bits of the listed env-steps.  Grid-stride over the work list.
+__global__ void __launch_bounds__(64) a3_fix_kernel(A3Args a, A3Scratch w, int ncand) {
+  const uint32_t count = *w.fix_count;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const uint32_t item = w.fix_list[i];
+    const int t = (int)(item / (uint32_t)a.n);
+    const size_t e = item % (uint32_t)a.n, ld = a.ld;
+    const float* qp = a.qpos + (size_t)t * A3_NQ * ld + e;
+    const A3SitesF64 s = a3_sites_f64(qp, ld);
+    if (a.o.done) {
+      const int fl = (int)a.contact[((size_t)t * 4 + 3) * ld + e];
+      a.o.done[(size_t)t * ld + e] = ((double)qp[2 * ld] - fmin(s.ls[2], s.rs[2]) < 0.6 || (fl & 2) != 0) ? 1 : 0;
+    }
+    const int t1_0 = a.ints[A3I_T1 * ld + e], t2_0 = a.ints[A3I_T2 * ld + e], seq_len = a.ints[A3I_SEQLEN * ld + e];
+    const int nc = a3_cand_needed(t, a.ints[A3I_FRAMES * ld + e], a.C.delay_frames, ncand);
+    uint32_t bits = 0;
+    for (int j = 0; j < nc; ++j) {
+      const int k = a3_cand(j, t1_0, t2_0, seq_len);
+      const double px = (double)a.sequence[(size_t)(k * 4) * ld + e], py = (double)a.sequence[(size_t)(k * 4 + 1) * ld + e];
+      const double pz = (double)a.sequence[(size_t)(k * 4 + 2) * ld + e];
+      const double lx = s.ls[0] - px, ly = s.ls[1] - py, lz = s.ls[2] - pz;
+      const double rx = s.rs[0] - px, ry = s.rs[1] - py, rz = s.rs[2] - pz;
+      if (sqrt(lx * lx + ly * ly + lz * lz) < a.C.target_radius || sqrt(rx * rx + ry * ry + rz * rz) < a.C.target_radius)
+        bits |= 1u << j;
+    }
+    w.near[e * w.tp + t] = (uint8_t)bits;
+  }
 }
 
 // The integer state machine over the T candidate bytes of one env (a few instructions per step); leaves a one-byte
@@ -234,6 +267,7 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) a3_post_kernel(A3Args a, A3Scratch w) {
   const int env = blockIdx.x * BLOCK + threadIdx.x;
   const int t = blockIdx.y;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *w.fix_count = 0u;      // consumed by a3_fix_kernel: ready for the next call
   if (env >= a.n) return;
   const size_t ld = a.ld, e = env;
   const A3Rec rec = a3_rec_load(w.feat + (size_t)t * A3_NREC * ld + e, ld);
@@ -317,6 +351,7 @@ struct OmA3Task {
   // replay call per handle may be in flight at a time
   mutable void* scratch = nullptr;
   mutable size_t scratch_bytes = 0;
+  mutable void* fix_count_at = nullptr;   // where the zero-initialised work-list counter of the current scratch layout lives
 };
 
 extern "C" int om_a3_task_create(const OmA3TaskDesc* d, OmA3Task** out) {
@@ -391,7 +426,8 @@ extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const flo
     const size_t int_b = ((size_t)(2 + (A3_MAX_CAND + 1) * 4) * ld * sizeof(int32_t) + 15) / 16 * 16;   // byte arrays 16-B aligned
     const int tp_max = (n_steps + 15) / 16 * 16;
     const size_t byte_b = (size_t)tp_max * (size_t)ld;
-    const size_t need = feat_b + int_b + 2 * byte_b;
+    const size_t fix_b = ((size_t)(n_steps < a3_max_steps_per_call(task->C.delay_frames) ? n_steps : a3_max_steps_per_call(task->C.delay_frames)) * (size_t)n + 4) * sizeof(uint32_t);
+    const size_t need = feat_b + int_b + 2 * byte_b + 16 + fix_b;
     OM_REQUIRE(env_blocks <= 65535, "om_a3_task_step: at most %d envs per multi-step call", 65535 * FB);
     if (task->scratch_bytes < need) {
       if (task->scratch) OM_CUDA_OK(cudaFree(task->scratch));  // synchronises: no earlier call still reads it
@@ -399,10 +435,18 @@ extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const flo
       task->scratch_bytes = 0;
       OM_CUDA_OK(cudaMalloc(&task->scratch, need));
       task->scratch_bytes = need;
+      task->fix_count_at = nullptr;
     }
     char* base = (char*)task->scratch;
+    char* fix_base = base + ((feat_b + int_b + 2 * byte_b + 15) / 16) * 16;
     A3Scratch w{(float*)base, (uint8_t*)(base + feat_b + int_b), (uint8_t*)(base + feat_b + int_b + byte_b), 0,
-                (int32_t*)(base + feat_b), (float*)(base + feat_b) + 2 * (size_t)ld};
+                (int32_t*)(base + feat_b), (float*)(base + feat_b) + 2 * (size_t)ld, (uint32_t*)fix_base, (uint32_t*)fix_base + 4};
+    if (task->fix_count_at != (void*)w.fix_count) {          // the work-list counter starts at zero; a3_post_kernel re-zeroes it
+      OM_CUDA_OK(cudaMemsetAsync(w.fix_count, 0, 16, st));
+      task->fix_count_at = (void*)w.fix_count;
+    }
+    OM_REQUIRE((unsigned long long)a3_max_steps_per_call(task->C.delay_frames) * (unsigned long long)n < 0xffffffffull,
+               "om_a3_task_step: too many envs for one multi-step call");
     // sub-calls no longer than the candidate bits cover (210 steps with the reference's 30 delay frames)
     const int max_call = a3_max_steps_per_call(task->C.delay_frames);
     for (int c0 = 0; c0 < n_steps; c0 += max_call) {
@@ -418,6 +462,8 @@ extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const flo
       OM_REQUIRE(len <= 65535, "om_a3_task_step: at most 65535 steps per call");
       const int ncand = a3_num_cand_host(len, task->C.delay_frames);
       a3_feat_kernel<FB><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
+      OM_LAUNCHED();
+      a3_fix_kernel<<<64, 64, 0, st>>>(sub, w, ncand);             // float64 re-decisions of the noted env-steps (usually ~1e-4 of them)
       OM_LAUNCHED();
       a3_walk_kernel<<<ceil_div(n, 64), 64, 0, st>>>(sub, w);
       OM_LAUNCHED();

@@ -121,25 +121,31 @@ OM_NOINLINE A3SitesF64 a3_sites_f64(const float* q, size_t ld) {
   for (int k = 0; k < 3; ++k) { r.ls[k] = S.ls[k]; r.rs[k] = S.rs[k]; }
   return r;
 }
-// where the slow path finds the env-step's qpos
+// Where the slow path finds the env-step's qpos -- or, with `defer` (the (env, t)-parallel replay kernel, whose hot
+// path must stay free of an out-of-line call and of its register saves), only a note that this env-step needs one: the
+// fp32 decision is returned for now and a3_fix_kernel re-takes it in float64 from the work list.
 struct A3Exact {
   const float* q;
   size_t ld;
+  bool defer;
+  bool unsure;
   OM_HD A3SitesF64 get() const { return a3_sites_f64(q, ld); }
 };
 // done (:298-319): root z (= qpos[2], exact) - lowest foot-site z < 0.6
-OM_HD bool a3_done_height(float root_z, float lz, float rz, const A3Exact& ex) {
+OM_HD bool a3_done_height(float root_z, float lz, float rz, A3Exact& ex) {
   const double h = (double)root_z - (double)fminf(lz, rz);
   if (fabs(h - 0.6) > A3_BAND) return h < 0.6;
+  if (ex.defer) { ex.unsure = true; return h < 0.6; }
   const A3SitesF64 s = ex.get();
   return (double)root_z - fmin(s.ls[2], s.rs[2]) < 0.6;
 }
 // "a foot is within target_radius of p" (:266-269): np.linalg.norm(foot - target) < radius, either foot
-OM_HD bool a3_near_exact(const A3TaskConst& C, V3 lsite, V3 rsite, V3 p, const A3Exact& ex) {
+OM_HD bool a3_near_exact(const A3TaskConst& C, V3 lsite, V3 rsite, V3 p, A3Exact& ex) {
   const V3 a = lsite - p, b = rsite - p;
   const float dl2 = dot(a, a), dr2 = dot(b, b);
   if (dl2 < C.near_lo2 || dr2 < C.near_lo2) return true;          // certainly inside
   if (dl2 > C.near_hi2 && dr2 > C.near_hi2) return false;         // certainly outside
+  if (ex.defer) { ex.unsure = true; return dl2 < C.near_d2 || dr2 < C.near_d2; }
   const A3SitesF64 s = ex.get();
   const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
   const double lx = s.ls[0] - px, ly = s.ls[1] - py, lz = s.ls[2] - pz;
@@ -247,7 +253,7 @@ OM_HD void a3_obs_robot(const float (&q)[A3_NQ], const float (&qd)[A3_NV], float
 // WalkingTask.step + calc_reward + done for one env.  Seq: float operator()(int step, int component); `tc` caches
 // sequence[t1] / sequence[t2] across steps.  Fills obs[31..40], the six weighted terms, their sum and done.
 template <class Seq>
-OM_HD void a3_task_step(const A3TaskConst& C, const A3Exact& ex, const A3TaskIn& f, A3TaskRegs& s, A3Targets& tc,
+OM_HD void a3_task_step(const A3TaskConst& C, A3Exact ex, const A3TaskIn& f, A3TaskRegs& s, A3Targets& tc,
                         const Seq& seq, float l_grf, float r_grf, float min_z, bool foot_contact, bool bad_collision,
                         float (&obs)[A3_NOBS], float (&terms)[6], float& total, bool& done) {
   s.phase += 1;                                                      // :248-250
@@ -357,7 +363,7 @@ OM_HD A3Rec a3_rec_load(const float* b, size_t ld) {
 // (env, t)-parallel part.  `phase` is the phase AFTER this step's increment.  Writes terms[0,1,3,5], obs[31,32], done.
 OM_HD A3Rec a3_task_pre(const A3TaskConst& C, const A3TaskIn& f, int phase, int mode, float l_grf, float r_grf, float min_z,
                         bool foot_contact, bool bad_collision, float (&terms)[6], float& clock_sin, float& clock_cos,
-                        bool& done, const A3Exact& ex) {
+                        bool& done, A3Exact& ex) {
   const float* lrow = C.lut + (size_t)phase * A3_LUT_COLS;
   clock_sin = lrow[4];
   clock_cos = lrow[5];
@@ -413,7 +419,7 @@ inline float a3_near_d2(double radius) {
 }
 template <class Seq>
 OM_HD uint32_t a3_near_bits(const A3TaskConst& C, V3 lsite, V3 rsite, int ncand, int t1_0, int t2_0, int seq_len, const Seq& seq,
-                            const A3Exact& ex) {
+                            A3Exact& ex) {
   uint32_t bits = 0;
 #pragma unroll 1
   for (int j = 0; j < ncand; ++j) {

@@ -43,7 +43,7 @@ extern "C" void host_a3_rollout(const float* lut6, int period, int delay, double
     A3Sink<NullFkSink> S{};
     om_fk_pos_stick_figure_a3(q, qd, S);
     const int fl = (int)c[3];
-    a3_task_step(C, A3Exact{qpos + t * A3_NQ, 1}, a3_task_in(S.f), s, tc, SeqHost{seq}, c[0], c[1], c[2], (fl & 1) != 0, (fl & 2) != 0, o, tr, total, d);
+    a3_task_step(C, A3Exact{qpos + t * A3_NQ, 1, false, false}, a3_task_in(S.f), s, tc, SeqHost{seq}, c[0], c[1], c[2], (fl & 1) != 0, (fl & 2) != 0, o, tr, total, d);
     std::memcpy(obs + t * A3_NOBS, o, sizeof o);
     std::memcpy(terms + t * 6, tr, sizeof tr);
     reward[t] = total;
@@ -70,7 +70,7 @@ extern "C" void host_a3_rollout_split(const float* lut6, int period, int delay, 
     om_fk_pos_stick_figure_a3(q, qd, S);
     const int fl = (int)c[3];
     const int phase = (ints[0] + t + 1) % period;
-    const A3Exact ex{qpos + t * A3_NQ, 1};
+    A3Exact ex{qpos + t * A3_NQ, 1, false, false};
     const A3Rec r = a3_task_pre(C, a3_task_in(S.f), phase, ints[4], c[0], c[1], c[2], (fl & 1) != 0, (fl & 2) != 0, tr, o[31],
                                 o[32], d, ex);
     a3_rec_store(r, rec + (size_t)t * A3_NREC, 1);
@@ -88,7 +88,7 @@ extern "C" void host_a3_rollout_split(const float* lut6, int period, int delay, 
     const int t1_0 = st[1], t2_0 = st[2], sl = st[5];
     for (int t = c0; t < c0 + len; ++t) {
       const A3Rec r = a3_rec_load(rec + (size_t)t * A3_NREC, 1);
-      const A3Exact ex{qpos + t * A3_NQ, 1};
+      A3Exact ex{qpos + t * A3_NQ, 1, false, false};
       near[t] = (uint8_t)a3_near_bits(C, r.lsite, r.rsite, a3_cand_needed(t - c0, st[3], delay, nc), t1_0, t2_0, sl, SeqHost{seq}, ex);
     }
     A3Walk w{0, st[3], st[6]};

@@ -89,8 +89,8 @@ def test_a3_reset_vs_reference_task_fixture(a3_model):
 
 def test_a3_random_states_large_with_fk_outputs(a3_model):
     """4096 envs: reset on the GPU, then one step on random post-physics states with the MjData fields written;
-    a sample of envs is replayed through the float64 oracle.  Integer / bool outputs must be identical except where
-    the float64 decision value itself lies within 2e-6 of its threshold (fp32 rounding of the FK)."""
+    a sample of envs is replayed through the float64 oracle.  Integer / bool outputs must be identical (no tolerance on a
+    flag: the kernels re-take near-threshold decisions in float64)."""
     import torch
     from oracle import a3 as OA
     from oracle import kinematics as K
@@ -128,10 +128,11 @@ def test_a3_random_states_large_with_fk_outputs(a3_model):
     for e in sample:
         _, _, ts, _ = OA.reset(a3_model, seed, 1000 + int(e), 0, iteration_count=5000.0)
         assert [ts.phase, ts.t1, ts.t2, ts.target_reached_frames, ts.mode, ts.seq_len, int(ts.target_reached)] == list(ints0[e])
-        assert_close(np.asarray(ts.sequence), seq_dev[e, :ts.seq_len], "footstep plan of the reset")
+        L = len(ts.sequence)
+        assert_close(np.asarray(ts.sequence)[:ts.seq_len], seq_dev[e, :ts.seq_len], "footstep plan of the reset")
         # the flags are exact functions of the fp32 INPUTS (qpos, contact summary, footstep plan): the oracle steps on the
         # plan the device holds (its own float64 plan differs from it by fp32 rounding)
-        ts.sequence = [row.copy() for row in seq_dev[e, :ts.seq_len]]
+        ts.sequence = [seq_dev[e, k].copy() if k < ts.seq_len else np.asarray(ts.sequence[k]).copy() for k in range(L)]
         c = c5[e].astype(np.float64)
         con = OA.Contact(l_grf=c[0], r_grf=c[1], min_z=c[2], foot_contact=bool(c[3]), bad_collision=bool(c[4]))
         obs, total, done, terms = OA.step_tail(a3_model, q[e].astype(np.float64), v[e].astype(np.float64), ts, con, lut)

@@ -119,7 +119,8 @@ def test_a3_rollout_full_size_properties(a3_model, om_knob):
     bad = (con[:, 3] >= 2)
     want_done = torch.as_tensor((h < 0.6).reshape(T, n), device="cuda") | bad
     assert torch.equal(out["done"].bool(), want_done)
-    assert int((np.abs(h - 0.6) < 1e-5).sum()) > 0                                          # the slow path was exercised
+    # (whether any of these env-steps needed the float64 re-decision depends on the draw; the adversarial inputs of
+    # test_gpu_a3.py::test_a3_threshold_flags_equal_float64_oracle_on_adversarial_inputs always do)
     # full-size parity against the oracle: 24 envs stepped through all 64 steps by the float64 restatement of the task
     seq_dev = task.sequence.cpu().numpy().T.reshape(n, 20, 4).astype(np.float64)
     lut = phase_clock_lut()
@@ -131,7 +132,7 @@ def test_a3_rollout_full_size_properties(a3_model, om_knob):
     for e in rng.choice(n, 24, replace=False):
         _, _, ts, _ = OA.reset(a3_model, 11, int(e), 0, iteration_count=6000.0)
         assert [ts.phase, ts.t1, ts.t2, ts.target_reached_frames, ts.mode, ts.seq_len, int(ts.target_reached)] == list(ints0[:, e].cpu().numpy())
-        ts.sequence = [row.copy() for row in seq_dev[e, :ts.seq_len]]
+        ts.sequence = [seq_dev[e, k].copy() if k < ts.seq_len else np.asarray(ts.sequence[k]).copy() for k in range(len(ts.sequence))]
         for t in range(T):
             c = conh[t, :, e].astype(np.float64)
             fl = int(c[3])
