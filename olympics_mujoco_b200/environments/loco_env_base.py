@@ -53,17 +53,28 @@ class LocoEnvBase:
     def __init__(self, model, action_spec, observation_spec, collision_groups=None, gamma=0.99, horizon=1000,
                  n_substeps=10, reward_type=None, reward_params=None, traj_params=None, random_start=True,
                  init_step_no=None, timestep=0.001, use_foot_forces=False, use_absorbing_states=True,
-                 n_envs=None, device="cuda", seed=0, env_id0=0, **_ignored_viewer_params):
-        if use_foot_forces:
-            raise NotImplementedError("use_foot_forces needs the contact solver, which is outside this path")
+                 n_envs=None, device="cuda", seed=0, env_id0=0, random_env_reset=True, **_ignored_viewer_params):
         self._single = n_envs is None
         self.n_envs = 1 if n_envs is None else int(n_envs)
         self._device, self._seed, self._env_id0 = device, int(seed), int(env_id0)
-        self._model = model
+        # mushroom_rl MultiMuJoCo (loco_env_base.py:143-155, reset :586-599): a LIST of models -- the reference passes one
+        # xml handle per carried weight -- with one MjData / ObservationHelper each; every reset() switches the env object
+        # to the next model, or to a random one.  All n envs of this object share the current model, as the reference's
+        # single env does.
+        models = list(model) if isinstance(model, (list, tuple)) else [model]
+        self._models = models
         self._timestep, self._n_substeps, self._n_intermediate_steps = timestep, n_substeps, 1
-        self._data = BatchedData(model, self.n_envs, device=device)
-        self._dm = Kn.DeviceModel(model)
-        self.obs_helper = ObservationHelper(observation_spec, model, self._data, max_joint_velocity=None)
+        self._datas = [BatchedData(m, self.n_envs, device=device) for m in models]
+        self._dms = [Kn.DeviceModel(m) for m in models]
+        self.obs_helpers = [ObservationHelper(observation_spec, m, d, max_joint_velocity=None)
+                            for m, d in zip(models, self._datas)]
+        self._current_model_idx, self._random_env_reset, self._model_resets = 0, bool(random_env_reset), 0
+        model = models[0]
+        self._model, self._data, self._dm, self.obs_helper = model, self._datas[0], self._dms[0], self.obs_helpers[0]
+        # mean ground reaction forces (RunningAveragedWindow over the n_intermediate_steps = 1 of a step, :1160-1174):
+        # what the contact solver measured enters through set_ground_forces / the dynamics callable
+        self._grf = torch.zeros((self._get_grf_size(), self.n_envs), dtype=torch.float32, device=device) \
+            if use_foot_forces else None
         self._action_spec = list(action_spec) if action_spec else list(model.actuator_names)
         a_idx = [model.actuator_names.index(a) for a in self._action_spec]
         low = np.where(model.actuator_ctrllimited[a_idx], model.actuator_ctrlrange[a_idx, 0], -np.inf)
@@ -216,9 +227,29 @@ class LocoEnvBase:
         """:568-604 (imitation-learning branch)."""
         self._data.qpos[:] = torch.as_tensor(self._model.qpos0, dtype=torch.float32, device=self._device)[:, None]
         self._data.qvel.zero_()                                                              # mj_resetData
+        if self._grf is not None:
+            self._grf.zero_()                                                                # mean_grf.reset() :584
+        if len(self._models) > 1:                                                            # MultiMuJoCo :586-599
+            if self._random_env_reset:
+                # np.random.randint in the reference; here the Philox contract (stream 32, counter = number of resets)
+                from ..utils.philox import STREAM_MODEL_RESET, philox_randint
+                self._current_model_idx = philox_randint(self._seed, self._env_id0, self._model_resets, STREAM_MODEL_RESET,
+                                                         len(self._models))
+            else:
+                self._current_model_idx = self._current_model_idx + 1 if self._current_model_idx < len(self._models) - 1 else 0
+            self._model_resets += 1
+            self._select_model(self._current_model_idx)
         self.setup(obs)
         self._obs = self._create_observation(self.obs_helper._build_obs(self._data))
         return self._out(self._modify_observation(self._obs))
+
+    def _select_model(self, idx):
+        prev = self._data
+        self._model, self._data = self._models[idx], self._datas[idx]
+        self._dm, self.obs_helper = self._dms[idx], self.obs_helpers[idx]
+        if prev is not self._data:
+            self._scatter_idx = None
+            self._live = None
 
     def setup(self, obs):
         """:606-657."""
@@ -246,12 +277,36 @@ class LocoEnvBase:
             self.set_sim_state(sample)
 
     # ------------------------------------------------------------------ observations
+    @staticmethod
+    def _get_grf_size():
+        """:1087-1103: four force sensors x 3 by default; UnitreeH1 overrides it (two feet, 6)."""
+        return 12
+
+    def set_ground_forces(self, grf):
+        """The contact solver's output for the step just simulated: ``_get_ground_forces()`` ([n, grf_size], newtons;
+        UnitreeH1.py:113-121 = floor-foot_r[:3], floor-foot_l[:3]).  The solver is outside this package (north star), so
+        the forces are an INPUT -- pushed here, or returned as a third value by the dynamics callable.  With one
+        intermediate step the running-average window (:1160-1174) holds exactly this sample."""
+        if self._grf is None:
+            raise RuntimeError("the environment was made without use_foot_forces=True")
+        g = self._batched(torch.as_tensor(grf, device=self._device, dtype=torch.float32))
+        assert g.shape == (self.n_envs, self._get_grf_size())
+        self._grf.copy_(g.t())
+
     def _get_observation_space(self):
-        return self.info.observation_space.low[2:], self.info.observation_space.high[2:]
+        """:712-735."""
+        low, high = self.info.observation_space.low[2:], self.info.observation_space.high[2:]
+        if self._use_foot_forces:
+            inf = np.ones(self._get_grf_size()) * np.inf
+            return np.concatenate([low, -inf]), np.concatenate([high, inf])
+        return low, high
 
     def _create_observation(self, obs):
-        """:737-767: drop the root x and y entries."""
-        return obs[..., 2:].contiguous()
+        """:737-767: drop the root x and y entries; with use_foot_forces append mean_grf / 1000."""
+        obs = obs[..., 2:]
+        if self._use_foot_forces:
+            return torch.cat([obs, self._grf.t().to(obs.dtype).expand(*obs.shape[:-1], -1) / 1000.0], dim=-1).contiguous()
+        return obs.contiguous()
 
     def _modify_observation(self, obs):
         return obs
@@ -409,8 +464,41 @@ class LocoEnvBase:
         return dict(obs=self._out(obs), has_fallen=self._out(fallen_any))
 
     def play_trajectory_from_velocity(self, n_episodes=None, n_steps_per_episode=None, render=False, record=False,
-                                      recorder_params=None, out=None, want=None):
-        raise NotImplementedError
+                                      recorder_params=None, **_fused_only):
+        """:444-560 with per-step kernels (K3 + A7 + K1), for any model / observation spec of joint entries: the Euler step
+        of the joint positions runs in float64 like the reference's.  (The default UnitreeH1 overrides this with ONE fused
+        kernel per episode.)  Returns the last observation and whether any step had fallen."""
+        assert self.trajectories is not None
+        if render or record:
+            raise NotImplementedError("rendering is outside the hot path; call with render=False")
+        assert n_episodes is not None and n_steps_per_episode is not None, "unbounded playback needs a viewer"
+        self.reset()                                                             # :481
+        sample = self.trajectories.get_current_sample().clone()                  # :483   [n, K]
+        len_qpos, len_qvel = self._len_qpos_qvel()
+        curr_qpos = sample[:, :len_qpos].double()
+        dev = self.trajectories.device_state
+        fallen_any = torch.zeros(self.n_envs, dtype=torch.bool, device=self._device)
+        obs = None
+        for _ in range(n_episodes):
+            for _ in range(n_steps_per_episode):
+                qvel = sample[:, len_qpos:len_qpos + len_qvel].double()
+                qpos = curr_qpos + self.dt * qvel                                # :515-517
+                sample = sample.clone()
+                sample[:, :len_qpos] = qpos.to(sample.dtype)                     # :519
+                self.set_sim_state(sample)                                       # :521
+                self.forward()                                                   # :525
+                curr_qpos = qpos                                                 # :529 (_get_joint_pos reads it back)
+                wrapped = torch.zeros(self.n_envs, dtype=torch.uint8, device=self._device)
+                dev.next(sample=self.trajectories._sample, wrapped=wrapped, auto_reset=True)   # :532-537
+                sample = self.trajectories._sample.t().clone()
+                w = wrapped.bool()
+                if bool(w.any()):
+                    curr_qpos = torch.where(w[:, None], sample[:, :len_qpos].double(), curr_qpos)
+                obs = self._create_observation(sample)                           # :539
+                fallen_any |= self._has_fallen(obs, batched=True)                # :541
+            self.reset()                                                         # :555
+            curr_qpos = self._get_joint_pos().double()                           # :557
+        return dict(obs=self._out(obs), has_fallen=self._out(fallen_any))
 
     def stop(self):
         pass

@@ -32,7 +32,7 @@ class BaseHumanoidRobot(LocoEnvBase):
         ``dict(traj_path=...)``, ``dict(traj_files=...)`` or ``dict(table=...)``.  When the reference's dataset
         file is absent (they are not redistributable / not available offline) a synthetic dataset-shaped
         trajectory is used, with the same warning the reference gives before falling back to its mini datasets."""
-        if task == "walk":
+        if task in ("walk", "carry"):
             mdp = env(reward_type="target_velocity", reward_params=dict(target_velocity=1.25), **kwargs)
         elif task == "run":
             mdp = env(reward_type="target_velocity", reward_params=dict(target_velocity=2.5), **kwargs)
@@ -69,25 +69,27 @@ class UnitreeH1(BaseHumanoidRobot):
 
     def __init__(self, disable_arms=True, disable_back_joint=False, hold_weight=False, weight_mass=None, xml_path=None,
                  **kwargs):
+        """UnitreeH1.py:38-111.  ``hold_weight``: a jointless "weight" body under torso_link (arms fixed in their MJCF
+        orientation); ``weight_mass=None`` builds one model per valid weight (0.1, 1, 5, 10 kg) and every reset() switches
+        the env object to one of them (MultiMuJoCo)."""
         if hold_weight:
-            raise NotImplementedError("the 'carry' variants add bodies to the MJCF; not built in this round")
+            assert disable_arms is True, ("If you want Unitree H1 to carry a weight, please disable the arms. "
+                                          "They will be kept fixed.")
         action_spec = self._get_action_specification()
         observation_spec = self._get_observation_specification()
         self._hidable_obs = ("positions", "velocities", "foot_forces", "weight")
         self._disable_arms, self._disable_back_joint = disable_arms, disable_back_joint
+        self._hold_weight, self._weight_mass = hold_weight, weight_mass
+        self._valid_weights = list(mjcf.H1_VALID_WEIGHTS)
         joints_to_remove, motors_to_remove, _ = self._get_xml_modifications()
         obs_to_remove = ["q_" + j for j in joints_to_remove] + ["dq_" + j for j in joints_to_remove]
         observation_spec = [e for e in observation_spec if e[0] not in obs_to_remove]
         action_spec = [a for a in action_spec if a not in motors_to_remove]
-        if xml_path is not None:                       # compile the user's MJCF (the reference's h1.xml)
-            model = mjcf.compile_unitree_h1(xml_path, disable_arms=disable_arms, disable_back_joint=disable_back_joint)
-        elif disable_arms and not disable_back_joint:
-            model = mjcf.load_builtin("unitree_h1")
-        elif not disable_arms and not disable_back_joint:
-            model = mjcf.load_builtin("unitree_h1_arms")
-        else:
-            raise ValueError("disable_back_joint=True needs xml_path (no pre-compiled table for that variant)")
-        super().__init__(model, action_spec, observation_spec, **kwargs)
+        base = mjcf.compile_mjcf(xml_path, name="UnitreeH1") if xml_path is not None else None   # the user's h1.xml
+        weights = [None] if not hold_weight else ([weight_mass] if weight_mass is not None else self._valid_weights)
+        models = [mjcf.unitree_h1_variant(disable_arms, disable_back_joint, hold_weight, w, base=base) for w in weights]
+        super().__init__(models if len(models) > 1 else models[0], action_spec, observation_spec, **kwargs)
+        model = self._model
         js = [e[1] for e in observation_spec if e[2] == ObservationType.JOINT_POS]
         perm = [int(model.jnt_qposadr[model.jnt_names.index(j)]) for j in js]
         rf = self._reward_function
@@ -153,11 +155,16 @@ class UnitreeH1(BaseHumanoidRobot):
         check_validity_task_mode_dataset(UnitreeH1.__name__, task, None, dataset_type,
                                          *UnitreeH1.valid_task_confs.get_all())
         if task == "carry":
-            raise NotImplementedError("the 'carry' variants add bodies to the MJCF; not built in this round")
+            # The reference's BaseHumanoidRobot.generate leaves `mdp` unbound for "carry" (base_humanoid_robot.py:143-150
+            # handles only "walk" and "run"), although its docstring describes the task: "walking while carrying an unknown
+            # weight".  That is what is built here: the walk MDP (target 1.25 m/s, the walk dataset) holding a weight.
+            kwargs.setdefault("hold_weight", True)
         if dataset_type == "real":
             path = "datasets/humanoids/real/05-run_UnitreeH1.npz" if task == "run" else \
                 "datasets/humanoids/real/02-constspeed_UnitreeH1.npz"
-        else:
+        else:                                                                   # UnitreeH1.py:226-238
+            assert kwargs.get("use_foot_forces", False) is False and kwargs.get("disable_arms", True) is True
+            assert kwargs.get("disable_back_joint", False) is False and kwargs.get("hold_weight", False) is False
             path = "datasets/humanoids/perfect/unitreeh1_%s/perfect_expert_dataset_det.npz" % ("run" if task == "run" else "walk")
         return BaseHumanoidRobot.generate(UnitreeH1, path, task, dataset_type, clip_trajectory_to_joint_ranges=True,
                                           **kwargs)
@@ -175,6 +182,14 @@ class UnitreeH1(BaseHumanoidRobot):
         super().attach_dynamics(fn)
         self._dynamics_soa = bool(soa)
 
+    def _take_dynamics(self, res):
+        """(qpos, qvel) or (qpos, qvel, ground_forces [n, 6]): the third value is what the contact solver measured
+        (``_get_ground_forces``, UnitreeH1.py:113-121) and feeds the GRF part of the observation."""
+        if len(res) == 3:
+            self.set_ground_forces(res[2])
+            return res[0], res[1]
+        return res
+
     def step(self, action):
         """action [n, nu] in [-1, 1] ([nu, n] with SoA dynamics) -> (obs, reward, absorbing, info).  The physics between
         observations comes from the attached dynamics; everything after it is one fused kernel (K1 + K2)."""
@@ -186,7 +201,7 @@ class UnitreeH1(BaseHumanoidRobot):
             if getattr(self, "_action_kernel_spec", None) is None:
                 self._action_kernel_spec = Kn.make_action_spec(self.norm_act_delta, self.norm_act_mean)
             ctrl = Kn.action_affine(self._action_kernel_spec, action)               # [nu, n], no transposes
-            qpos, qvel = self._dynamics(self, ctrl)
+            qpos, qvel = self._take_dynamics(self._dynamics(self, ctrl))
             assert qpos.shape == d.qpos.shape and qvel.shape == d.qvel.shape, "SoA dynamics return [nq, n], [nv, n]"
             if qpos is not d.qpos:                            # a dynamics that writes env.data.qpos / qvel in place and
                 d.qpos.copy_(qpos)                            # returns them costs no copy at all
@@ -195,7 +210,7 @@ class UnitreeH1(BaseHumanoidRobot):
             qpos, qvel = d.qpos, d.qvel
         else:
             ctrl = self._preprocess_action(self._batched(action))
-            qpos, qvel = self._dynamics(self, ctrl)
+            qpos, qvel = self._take_dynamics(self._dynamics(self, ctrl))
             d.qpos.copy_(torch.as_tensor(qpos, device=self._device, dtype=torch.float32).reshape(self.n_envs, -1).t())
             d.qvel.copy_(torch.as_tensor(qvel, device=self._device, dtype=torch.float32).reshape(self.n_envs, -1).t())
             qpos, qvel = d.qpos, d.qvel
@@ -203,6 +218,8 @@ class UnitreeH1(BaseHumanoidRobot):
         out = Kn.h1_step(self._dm, self._spec, qpos, qvel, self._prev_x_vel,
                          out=dict(xpos=d.xpos, xquat=d.xquat, site_xpos=d.site_xpos, cvel=d.cvel))
         cur_obs = out["obs"].t()
+        if self._use_foot_forces:                                # _create_observation :737-767: append mean_grf / 1000
+            cur_obs = torch.cat([cur_obs, self._grf.t() / 1000.0], dim=1)
         absorbing = out["absorbing"].bool()
         reward = out["reward"] if self._fused_reward else self.reward(prev_obs, ctrl, cur_obs, absorbing)
         self._obs = cur_obs
@@ -211,7 +228,8 @@ class UnitreeH1(BaseHumanoidRobot):
 
     # ------------------------------------------------------------------ fused live step / graph
     def _live_stepper(self):
-        if not self._dm.specialised or len(self.obs_helper.observation_spec) != 34 or not self._fused_reward:
+        if (not self._dm.specialised or len(self.obs_helper.observation_spec) != 34 or not self._fused_reward
+                or self._use_foot_forces):
             raise NotImplementedError("the fused live step is generated for the default UnitreeH1 (arms disabled) with the "
                                       "target-velocity reward")
         if getattr(self, "_live", None) is None:
@@ -333,6 +351,7 @@ class UnitreeH1(BaseHumanoidRobot):
         time-major rollout buffers ([T, C, n] SoA; use ``kernels.env_major`` for [T, n, ...] views) -- the reference
         returns nothing and only renders.  ``obs_moments``: float64 [65] buffer that receives the moment sums of the
         emitted observations (S1 fused into the kernel)."""
-        if not self._dm.specialised or len(self.obs_helper.observation_spec) != 34:
-            raise NotImplementedError("fused playback is generated for the default UnitreeH1 (arms disabled)")
+        if not self._dm.specialised or len(self.obs_helper.observation_spec) != 34 or self._use_foot_forces:
+            # other variants (arms, no back joint, carried weight, foot forces): per-step kernels of the base class
+            return super().play_trajectory_from_velocity(n_episodes, n_steps_per_episode, render, record, recorder_params)
         return self._play(False, n_episodes, n_steps_per_episode, render, record, out, want, continue_episode, obs_moments)

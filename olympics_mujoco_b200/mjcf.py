@@ -115,6 +115,74 @@ class KinematicModel:
     def site_id(self, name):
         return self.site_names.index(name)
 
+    # ------------------------------------------------------------- table-level model edits
+    # The reference edits the MJCF through dm_control before MuJoCo compiles it (loco_env_base.py:836-868
+    # _delete_from_xml_handle; UnitreeH1.py:245-261 _add_weight).  The same edits on the COMPILED tables give the same
+    # model (checked against a fresh compile of the edited MJCF in tests/test_host.py), so every variant of a robot can be
+    # built from the tables shipped with the package, without the reference's XML at hand.
+    def without_joints(self, names, name=None):
+        """The model with the named (single-dof) joints and the actuators that drive them removed."""
+        import copy
+        drop = [self.jnt_names.index(n) for n in names]
+        for j in drop:
+            if int(self.jnt_type[j]) not in (JNT_SLIDE, JNT_HINGE):
+                raise ValueError("without_joints handles slide / hinge joints")
+        keep = [j for j in range(self.njnt) if j not in drop]
+        m = copy.deepcopy(self)
+        m.name = name or self.name
+        qmap = {int(self.jnt_qposadr[j]): None for j in drop}
+        keep_q = [k for k in range(self.nq) if k not in qmap]
+        m.qpos0 = self.qpos0[keep_q].copy()
+        m.nq, m.nv = self.nq - len(drop), self.nv - len(drop)
+        for f in ("jnt_type", "jnt_bodyid", "jnt_axis", "jnt_pos", "jnt_range", "jnt_limited"):
+            setattr(m, f, np.asarray(getattr(self, f))[keep].copy())
+        m.jnt_names = [self.jnt_names[j] for j in keep]
+        qa, da = 0, 0
+        m.jnt_qposadr, m.jnt_dofadr = np.zeros(len(keep), np.int32), np.zeros(len(keep), np.int32)
+        for i, j in enumerate(keep):
+            m.jnt_qposadr[i], m.jnt_dofadr[i] = qa, da
+            t = int(self.jnt_type[j])
+            qa += 7 if t == JNT_FREE else 4 if t == JNT_BALL else 1
+            da += _NV[t]
+        m.body_jntadr, m.body_jntnum = np.full(self.nbody, -1, np.int32), np.zeros(self.nbody, np.int32)
+        for i in range(len(keep)):
+            b = int(m.jnt_bodyid[i])
+            if m.body_jntnum[b] == 0:
+                m.body_jntadr[b] = i
+            m.body_jntnum[b] += 1
+        ka = [a for a in range(self.nu) if self.actuator_joint[a] not in names]
+        m.actuator_names = [self.actuator_names[a] for a in ka]
+        m.actuator_joint = [self.actuator_joint[a] for a in ka]
+        m.actuator_gear = np.asarray(self.actuator_gear)[ka].copy()
+        m.actuator_ctrlrange = np.asarray(self.actuator_ctrlrange)[ka].copy()
+        m.actuator_ctrllimited = np.asarray(self.actuator_ctrllimited)[ka].copy()
+        return m
+
+    def with_child_body(self, parent, body_name, mass, ipos, pos=(0.0, 0.0, 0.0), name=None):
+        """The model with one more jointless body hanging off ``parent``.  Supported where the new body is the LAST one in
+        MuJoCo's depth-first numbering (the parent's subtree ends the tree), which is where dm_control's ``add`` puts it
+        for the H1 torso."""
+        import copy
+        pid = self.body_id(parent)
+        b = self.nbody - 1
+        while b != pid:                                  # the last body must descend from the parent
+            if b == 0:
+                raise ValueError(f"a child of {parent!r} would not be the last body of the tree")
+            b = int(self.body_parentid[b])
+        m = copy.deepcopy(self)
+        m.name = name or self.name
+        m.body_names = self.body_names + [body_name]
+        app = lambda a, v: np.concatenate([np.asarray(a), np.asarray(v, dtype=np.asarray(a).dtype).reshape((1,) + np.asarray(a).shape[1:])])
+        m.body_parentid = app(self.body_parentid, pid)
+        m.body_rootid = app(self.body_rootid, self.body_rootid[pid])
+        m.body_pos = app(self.body_pos, pos)
+        m.body_quat = app(self.body_quat, [1.0, 0, 0, 0])
+        m.body_ipos = app(self.body_ipos, ipos)
+        m.body_mass = app(self.body_mass, mass)
+        m.body_jntadr = app(self.body_jntadr, -1)
+        m.body_jntnum = app(self.body_jntnum, 0)
+        return m
+
     # ------------------------------------------------------------- (de)serialise
     _ARRAYS = ("body_parentid body_rootid body_pos body_quat body_ipos body_mass body_jntadr "
                "body_jntnum jnt_type jnt_bodyid jnt_axis jnt_pos jnt_qposadr jnt_dofadr jnt_range "
@@ -397,8 +465,41 @@ H1_ARM_QUATS = {"left_shoulder_pitch_link": [1.0, 0.25, 0.1, 0.0],          # Un
                 "left_elbow_link": [1.0, 0.0, 0.25, 0.0]}
 
 
-def compile_unitree_h1(xml_path, disable_arms=True, disable_back_joint=False):
+H1_VALID_WEIGHTS = [0.1, 1.0, 5.0, 10.0]                                    # UnitreeH1.py:62
+# UnitreeH1._add_weight (UnitreeH1.py:245-261): body "weight" under torso_link with TWO box geoms of `mass` each
+H1_WEIGHT_GEOM_POS = ((0.35, 0.0, 0.1), (0.9, 0.0, 0.1))
+
+
+def unitree_h1_variant(disable_arms=True, disable_back_joint=False, hold_weight=False, weight_mass=None, base=None):
+    """Every UnitreeH1 variant the constructor switches select (UnitreeH1.py:38-111), from the shipped tables:
+    arms disabled -> arm joints removed and, unless a weight is carried, the arms re-oriented (the default table);
+    back joint removed; ``hold_weight`` -> a jointless "weight" body of 2 x ``weight_mass`` under torso_link, arms kept in
+    their MJCF orientation.  ``base``: a compiled full model (arms + back) to derive from instead of the shipped one."""
+    if hold_weight and not disable_arms:
+        raise AssertionError("If you want Unitree H1 to carry a weight, please disable the arms. They will be kept fixed.")
+    if disable_arms and not hold_weight and base is None:
+        m = load_builtin("unitree_h1")
+    else:
+        m = base if base is not None else load_builtin("unitree_h1_arms")
+        if disable_arms:
+            m = m.without_joints(H1_ARM_JOINTS, name="UnitreeH1")
+            if not hold_weight:
+                for b, q in H1_ARM_QUATS.items():
+                    m.body_quat[m.body_id(b)] = _normalize(np.asarray(q, dtype=np.float64))
+    if disable_back_joint:
+        m = m.without_joints(["back_bkz"], name=m.name)
+    if hold_weight:
+        w = float(weight_mass)
+        com = np.mean(np.asarray(H1_WEIGHT_GEOM_POS), axis=0)               # two equal masses
+        m = m.with_child_body("torso_link", "weight", 2.0 * w, com, name=m.name)
+    return m
+
+
+def compile_unitree_h1(xml_path, disable_arms=True, disable_back_joint=False, hold_weight=False, weight_mass=None):
     """UnitreeH1 model with the constructor's XML edits applied (UnitreeH1.py:70-88)."""
+    if hold_weight:
+        full = compile_mjcf(xml_path, name="UnitreeH1")
+        return unitree_h1_variant(disable_arms, disable_back_joint, True, weight_mass, base=full)
     rm_j, rm_a, quats = [], [], None
     if disable_arms:
         rm_j += H1_ARM_JOINTS

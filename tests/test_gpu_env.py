@@ -305,3 +305,94 @@ def test_step_with_soa_dynamics_needs_no_transposes():
         os_, rs, as_, _ = env_s.step(act.t().contiguous())
         assert torch.equal(oa, os_) and torch.equal(ra, rs) and torch.equal(aa, as_)
         assert torch.equal(env_a.data.xpos, env_s.data.xpos)
+
+
+def _variant_table(model):
+    """The golden 34-key table restricted to the keys this model's spec keeps (e.g. without the back joint)."""
+    from oracle import h1 as OH
+    full = ["q_" + j for j in OH._SPEC_JOINTS] + ["dq_" + j for j in OH._SPEC_JOINTS]
+    full = [k for k in full if not any(a in k for a in OH.ARM_JOINTS)]
+    keep = [full.index(k) for k in OH.keys(model)]
+    return _table()[keep]
+
+
+@pytest.mark.parametrize("kw", [dict(disable_back_joint=True), dict(hold_weight=True, weight_mass=5.0), dict(use_foot_forces=True)])
+def test_unitree_h1_variants_step_and_generic_playback(kw):
+    """UnitreeH1.py:38-111 variants: the back joint removed, a carried weight, foot forces in the observation.  step() on
+    attached dynamics against the oracle on the variant's model; play_trajectory_from_velocity through the per-step
+    kernels of the base class against the oracle's playback."""
+    import torch
+    import olympics_mujoco_b200 as om
+    from oracle import h1 as OH
+    from oracle import kinematics as K
+    n = 12
+    from olympics_mujoco_b200 import mjcf
+    table = _variant_table(mjcf.unitree_h1_variant(**{k: v for k, v in kw.items() if k != "use_foot_forces"}))
+    env = om.LocoEnvBase.make("UnitreeH1.walk.real", n_envs=n, traj_params=dict(table=table), seed=31, **kw)
+    model = env._model
+    nq = model.nq
+    nobs = 2 * nq - 2 + (6 if kw.get("use_foot_forces") else 0)
+    assert env.info.observation_space.shape == (nobs,) and not env._dm.specialised or kw.get("use_foot_forces")
+    if kw.get("hold_weight"):
+        assert model.body_names[-1] == "weight" and abs(model.total_mass - 61.437) < 1e-9
+    obs0 = env.reset().clone()
+    assert tuple(obs0.shape) == (n, nobs)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    grf = torch.rand((n, 6), device="cuda", generator=g) * 400
+
+    def dynamics(e, ctrl):
+        q = e.data.qpos.t() + 0.02 * torch.randn((n, nq), device="cuda", generator=g)
+        v = e.data.qvel.t() + 0.2 * torch.randn((n, nq), device="cuda", generator=g)
+        return (q, v, grf) if kw.get("use_foot_forces") else (q, v)
+
+    env.attach_dynamics(dynamics)
+    prev = obs0
+    for _ in range(2):
+        obs, reward, absorbing, _ = env.step(torch.zeros((n, len(env._action_spec)), device="cuda"))
+        q = env.data.qpos.t().double().cpu().numpy()
+        v = env.data.qvel.t().double().cpu().numpy()
+        ref = OH.step(model, q, v, prev[:, :2 * nq - 2].double().cpu().numpy())
+        assert np.array_equal(obs[:, :2 * nq - 2].cpu().numpy(), ref["obs"].astype(np.float32))
+        if kw.get("use_foot_forces"):
+            assert torch.equal(obs[:, -6:], grf / 1000.0)                       # _create_observation :737-767
+        assert np.array_equal(absorbing.cpu().numpy(), ref["absorbing"])
+        assert_close(reward.cpu().numpy(), ref["reward"], "reward")
+        assert_close(env.data.xpos.t().cpu().numpy().reshape(n, model.nbody, 3), ref["xpos"], "xpos")
+        assert_close(env.data.cvel.t().cpu().numpy().reshape(n, model.nbody, 6), ref["cvel"], "cvel (COM includes the weight)")
+        prev = obs.clone()
+    if kw.get("use_foot_forces"):
+        return
+    # generic playback (per-step kernels) against the oracle's playback on the same variant
+    T = 70
+    env2 = om.LocoEnvBase.make("UnitreeH1.walk.real", n_envs=n, traj_params=dict(table=table), seed=31, **kw)
+    res = env2.play_trajectory_from_velocity(n_episodes=1, n_steps_per_episode=T, render=False)
+    for e in range(3):
+        ref = OH.play_trajectory_from_velocity(model, table, 1, T, seed=31, env_id=e, record_fk=False)
+        assert np.array_equal(res["obs"][e].cpu().numpy(), ref["obs"][-1].astype(np.float32))
+        assert bool(res["has_fallen"][e]) == bool(ref["fallen"].any())
+        assert int(env2.trajectories.device_state.reset_count[e]) == ref["final"]["reset_count"]
+
+
+def test_multi_model_reset_switches_the_carried_weight():
+    """MultiMuJoCo (loco_env_base.py:586-599): hold_weight with weight_mass=None builds one model per valid weight; every
+    reset() moves the env object to the next one (random_env_reset=False) or to a Philox-drawn one."""
+    import torch
+    import olympics_mujoco_b200 as om
+    from olympics_mujoco_b200.utils.philox import STREAM_MODEL_RESET, philox_randint
+    env = om.LocoEnvBase.make("UnitreeH1.carry.real", n_envs=4, traj_params=dict(table=_table()), seed=9, random_env_reset=False)
+    assert len(env._models) == 4 and [m.body_mass[-1] for m in env._models] == [0.2, 2.0, 10.0, 20.0]
+    seen = []
+    for _ in range(6):
+        env.reset()
+        seen.append(env._current_model_idx)
+        env.forward()
+        com_z = float(env.data.subtree_com[2, 0])
+        seen[-1] = (seen[-1], round(com_z, 6))
+    assert [s[0] for s in seen] == [1, 2, 3, 0, 1, 2]
+    assert len({s[1] for s in seen[:4]}) == 4                              # a heavier weight moves the centre of mass
+    rnd = om.LocoEnvBase.make("UnitreeH1.carry.real", n_envs=4, traj_params=dict(table=_table()), seed=9)
+    got = []
+    for k in range(8):
+        rnd.reset()
+        got.append(rnd._current_model_idx)
+    assert got == [philox_randint(9, 0, k, STREAM_MODEL_RESET, 4) for k in range(8)] and len(set(got)) > 1

@@ -374,3 +374,45 @@ def test_a3_threshold_decisions_are_float64_exact_on_host(a3_model):
             got_done[i], got_reached[i] = bool(dn[0]), bool(ints[6])
         assert np.array_equal(got_done, cases["want_done"]), np.flatnonzero(got_done != cases["want_done"])
         assert np.array_equal(got_reached, cases["want_reached"]), np.flatnonzero(got_reached != cases["want_reached"])
+
+
+def test_unitree_h1_variants_from_shipped_tables():
+    """UnitreeH1.py:38-111: every constructor variant (arms, back joint, carried weight) is derived from the shipped tables
+    by table-level edits; each equals a fresh compile of the edited MJCF (when the reference is at hand) and its kinematics
+    equal the INDEPENDENT checker's fixture (always)."""
+    from olympics_mujoco_b200 import mjcf
+    from oracle import kinematics as K
+    g = np.load(ROOT / "tests" / "golden" / "fk_independent_ref.npz")
+    xml = Path("/root/reference/olympic_mujoco/environments/data/unitree_h1/h1.xml")
+    for kw in (dict(), dict(disable_back_joint=True), dict(disable_arms=False), dict(disable_arms=False, disable_back_joint=True),
+               dict(hold_weight=True, weight_mass=5.0)):
+        m = mjcf.unitree_h1_variant(**kw)
+        if xml.exists():
+            ref = mjcf.compile_unitree_h1(xml, **kw)
+            for k in mjcf.KinematicModel._ARRAYS:
+                assert np.array_equal(np.asarray(getattr(m, k)), np.asarray(getattr(ref, k))), (kw, k)
+            assert m.jnt_names == ref.jnt_names and m.actuator_names == ref.actuator_names and m.body_names == ref.body_names
+    for name, m in (("h1_noback", mjcf.unitree_h1_variant(disable_back_joint=True)),
+                    ("h1_carry", mjcf.unitree_h1_variant(hold_weight=True, weight_mass=5.0))):
+        out = K.forward(m, g[name + "_qpos"], g[name + "_qvel"])
+        assert list(g[name + "_body_names"][1:]) == list(m.body_names[1:])
+        assert_close(m.body_mass, g[name + "_body_mass"], "masses", rtol=1e-12, atol=1e-12)
+        for k in ("xpos", "site_xpos", "subtree_com"):
+            assert_close(out[k], g[f"{name}_{k}"], f"{name} {k}", rtol=1e-12, atol=1e-12)
+        assert_close(out["cvel"], g[name + "_cvel"], f"{name} cvel", rtol=1e-8, atol=5e-9)
+    carry = mjcf.unitree_h1_variant(hold_weight=True, weight_mass=1.0)
+    assert carry.body_names[-1] == "weight" and carry.body_mass[-1] == 2.0 and carry.nq == 17
+    # arms are NOT re-oriented when a weight is held (UnitreeH1.py:84-85)
+    assert_close(carry.body_quat[carry.body_id("left_shoulder_pitch_link")],
+                 mjcf.load_builtin("unitree_h1_arms").body_quat[carry.body_id("left_shoulder_pitch_link")], "arm quat", 0, 0)
+    with pytest.raises(AssertionError, match="disable the arms"):
+        mjcf.unitree_h1_variant(disable_arms=False, hold_weight=True, weight_mass=1.0)
+
+
+def test_host_philox_matches_the_contract():
+    from olympics_mujoco_b200.utils import philox as HP
+    from oracle import philox as OP
+    for seed, env, cnt, stream in ((0, 0, 0, 0), (1234, 77, 3, 32), (2 ** 40 + 5, 4095, 9, 16)):
+        want = [int(x) for x in OP.draw(seed, np.uint32(env), np.uint32(cnt), stream)]
+        assert list(HP.philox4x32_10((env, cnt, stream, 0), (seed & 0xFFFFFFFF, seed >> 32))) == want
+        assert HP.philox_randint(seed, env, cnt, stream, 4) == int(OP.to_int(np.uint32(want[0]), 4))
