@@ -138,14 +138,14 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------- configs[4]
 def sharded_1m(rank, world, local, table, rollouts=4, warmup=2):
     """BASELINE.json configs[4]: 1 048 576 UnitreeH1 envs sharded by contiguous index range over the ranks, 64-step
-    rollouts (four 16-step playback calls into the same device buffers) and ONE all-reduce of the float64 observation
+    rollouts (two 32-step playback calls into the same device buffers) and ONE all-reduce of the float64 observation
     moments per rollout.  Every rank runs it; returns the aggregate (max-over-ranks time) on every rank."""
     import torch
     import torch.distributed as dist
     from olympics_mujoco_b200 import distributed as D
     from olympics_mujoco_b200 import kernels as Kn
     from olympics_mujoco_b200.environments import LocoEnvBase
-    total, t_call, calls = 1 << 20, 16, 4
+    total, t_call, calls = 1 << 20, 32, 2
     env_id0, n_local = D.env_shard(total, rank, world)
     env = LocoEnvBase.make("UnitreeH1.walk.real", n_envs=n_local, traj_params=dict(table=table), seed=1234,
                            env_id0=env_id0, device=f"cuda:{local}")
@@ -154,7 +154,7 @@ def sharded_1m(rank, world, local, table, rollouts=4, warmup=2):
 
     def rollout():
         mom.zero_()
-        for c in range(calls):                                 # one 64-step rollout = four calls into the same buffers; the
+        for c in range(calls):                                 # one 64-step rollout = two calls into the same buffers; the
             env.play_trajectory_from_velocity(n_episodes=1, n_steps_per_episode=t_call, render=False, out=roll,
                                               continue_episode=c > 0, obs_moments=mom)   # moments: fused into the kernel
         D.all_reduce_moments(mom)                              # NVLink mailbox kernel (or NCCL), no-op at world 1

@@ -556,6 +556,9 @@ struct OmTraj {
   // One playback call per handle may be in flight at a time.
   mutable char* scratch = nullptr;
   mutable size_t scratch_bytes = 0;
+  // fork / join of the observation-moments kernel beside the time-parallel playback kernel (both only READ the snapshot)
+  mutable cudaStream_t side = nullptr;
+  mutable cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 extern "C" int om_traj_create(const double* table, int K, int n_traj, int T, OmTraj** out) {
@@ -630,6 +633,9 @@ extern "C" void om_traj_destroy(OmTraj* t) {
   cudaFree((void*)t->d.cdq);
   if (t->d.psum) cudaFree((void*)t->d.psum);
   if (t->scratch) cudaFree(t->scratch);
+  if (t->ev_fork) cudaEventDestroy(t->ev_fork);
+  if (t->ev_join) cudaEventDestroy(t->ev_join);
+  if (t->side) cudaStreamDestroy(t->side);
   delete t;
 }
 
@@ -691,10 +697,6 @@ static int play_impl(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, ui
   constexpr int BLOCK = PLAY_BLOCK;
   const bool mom = a.obs_moments != nullptr;
   OM_REQUIRE(!mom || t->d.psum, "om_h1_play_from_velocity: this trajectory handle has no prefix tables");
-  if (mom) {                                        // reads the START state: before anything below touches it
-    play_moments_kernel<<<ceil_div(n, 8 * PM_ENVS), 256, 0, (cudaStream_t)stream>>>(a, a.s, start_reset ? 1 : 0);
-    OM_LAUNCHED();
-  }
   // time-parallel when the env count alone cannot fill the machine (148 SMs x 2048 threads)
   const long long target_threads = 148LL * 2048;
   const long long chunks_wanted = target_threads / n > 0 ? target_threads / n : 1;
@@ -702,6 +704,10 @@ static int play_impl(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, ui
   if (g_knobs.play_chunk > 0) chunk = g_knobs.play_chunk;            // tuning / test hook (om_debug_set)
   if (chunk < 1) chunk = 1;
   if (chunk >= n_steps) {
+    if (mom) {                                      // reads the START state: before anything below touches it
+      play_moments_kernel<<<ceil_div(n, 8 * PM_ENVS), 256, 0, (cudaStream_t)stream>>>(a, a.s, start_reset ? 1 : 0);
+      OM_LAUNCHED();
+    }
     if (start_reset) {
       play_start_reset_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(a);
       OM_LAUNCHED();
@@ -732,8 +738,24 @@ static int play_impl(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, ui
     else play_snapshot_kernel<false><<<ceil_div(n, 256), 256, 0, st>>>(a, a.s, a.snap, n, ld);
     OM_LAUNCHED();
     dim3 grid(ceil_div(n, BLOCK), ceil_div(n_steps, chunk));
+    if (mom) {
+      // The moments kernel (L2-bound: prefix-table reads) runs BESIDE the playback kernel (DRAM-bound) on a side stream:
+      // both only read the snapshot, which now holds the state after the call's start reset.  Plain fork / join with two
+      // events, legal under stream capture.
+      if (!t->side) {
+        OM_CUDA_OK(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
+        OM_CUDA_OK(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
+        OM_CUDA_OK(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
+      }
+      OM_CUDA_OK(cudaEventRecord(t->ev_fork, st));
+      OM_CUDA_OK(cudaStreamWaitEvent(t->side, t->ev_fork, 0));
+      play_moments_kernel<<<ceil_div(n, 8 * PM_ENVS), 256, 0, t->side>>>(a, a.snap, 0);
+      OM_LAUNCHED();
+      OM_CUDA_OK(cudaEventRecord(t->ev_join, t->side));
+    }
     play_h1_tp_kernel<BLOCK><<<grid, BLOCK, 0, st>>>(a, chunk);
     OM_LAUNCHED();
+    if (mom) OM_CUDA_OK(cudaStreamWaitEvent(st, t->ev_join, 0));
     return 0;
   }
   OM_LAUNCHED();

@@ -520,35 +520,32 @@ class LocoEnvBase:
 
 
 class ValidTaskConf:
-    """:1381-1455."""
+    """The valid (task, mode, data_type) settings of an environment (reference ``loco_env_base.py:1381-1455``): same
+    constructor, ``get_all`` and ``get_all_combinations`` results.  A forbidden triple may hold ``None`` wildcards."""
+
+    _FIELDS = ("task", "mode", "data_type")
 
     def __init__(self, tasks=None, modes=None, data_types=None, non_combinable=None):
+        if non_combinable is not None and any(len(triple) != 3 for triple in non_combinable):
+            raise AssertionError("non_combinable entries are (task, mode, data_type) triples")
         self.tasks, self.modes, self.data_types, self.non_combinable = tasks, modes, data_types, non_combinable
-        if non_combinable is not None:
-            for nc in non_combinable:
-                assert len(nc) == 3
 
     def get_all(self):
-        return deepcopy(self.tasks), deepcopy(self.modes), deepcopy(self.data_types), deepcopy(self.non_combinable)
+        return tuple(deepcopy(x) for x in (self.tasks, self.modes, self.data_types, self.non_combinable))
+
+    @staticmethod
+    def _hits(choice, forbidden):
+        return all(f is None or f == c for c, f in zip(choice, forbidden))
 
     def get_all_combinations(self):
-        confs = []
-        tasks = self.tasks if self.tasks is not None else [None]
-        modes = self.modes if self.modes is not None else [None]
-        data_types = self.data_types if self.data_types is not None else [None]
-        for t, m, dt in product(tasks, modes, data_types):
-            conf = dict()
-            if t is not None:
-                conf["task"] = t
-            if m is not None:
-                conf["mode"] = m
-            if dt is not None:
-                conf["data_type"] = dt
-            if self.non_combinable is not None:
-                for bad_t, bad_m, bad_dt in self.non_combinable:
-                    if not ((t == bad_t or bad_t is None) and (m == bad_m or bad_m is None)
-                            and (dt == bad_dt or bad_dt is None)):
-                        confs.append(conf)
+        axes = [values if values is not None else [None] for values in (self.tasks, self.modes, self.data_types)]
+        out = []
+        for choice in product(*axes):
+            conf = {k: v for k, v in zip(self._FIELDS, choice) if v is not None}
+            if self.non_combinable is None:
+                out.append(conf)
             else:
-                confs.append(conf)
-        return confs
+                # the reference appends the combination once per forbidden triple it does NOT match (so a list of several
+                # triples repeats entries); every environment in the tree declares at most one triple
+                out.extend(conf for forbidden in self.non_combinable if not self._hits(choice, forbidden))
+        return out

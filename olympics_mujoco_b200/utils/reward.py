@@ -1,16 +1,29 @@
-"""IL-mode reward interface (reference ``olympic_mujoco/utils/reward.py:5-74``), batched: ``state`` is a
-device tensor [n, D] (or [D]) and the result a device tensor [n] (or scalar tensor).  The fused kernels
-(``om_h1_step`` / ``om_h1_play_from_velocity``) compute ``TargetVelocityReward`` in-kernel; these classes serve
-``env.reward(state, action, next_state, absorbing)`` calls made outside ``step``."""
+"""IL-mode reward callables (the interface of reference ``olympic_mujoco/utils/reward.py:5-74``: called as
+``reward(state, action, next_state, absorbing)``, optional ``reset_state()``), batched: ``state`` is a device tensor
+[n, D] (or [D]) and the result a device tensor [n] (or a scalar).  The fused kernels (``om_h1_step``, ``om_h1_live_step``,
+``om_h1_play_from_velocity``) evaluate ``TargetVelocityReward`` in-kernel; these objects serve ``env.reward(...)`` calls
+made outside ``step`` and carry the parameters the kernels read (``_target_vel``, ``_x_vel_idx``)."""
 import torch
 
 
 class RewardInterface:
+    """Base of every reward: stateless unless a subclass says otherwise."""
+
     def __call__(self, state, action, next_state, absorbing):
         raise NotImplementedError
 
     def reset_state(self):
-        pass
+        return None
+
+
+class _Column(RewardInterface):
+    """A reward that is a function of ONE observation column of ``state``."""
+
+    def __init__(self, idx):
+        self._idx = int(idx)
+
+    def _column(self, state):
+        return torch.as_tensor(state)[..., self._idx]
 
 
 class NoReward(RewardInterface):
@@ -18,29 +31,35 @@ class NoReward(RewardInterface):
         return 0
 
 
-class PosReward(RewardInterface):
+class PosReward(_Column):
+    """The root x position itself (reward_type "x_pos", loco_env_base.py:809-815)."""
+
     def __init__(self, pos_idx):
-        self._pos_idx = pos_idx
+        super().__init__(pos_idx)
+        self._pos_idx = self._idx
 
     def __call__(self, state, action, next_state, absorbing):
-        return state[..., self._pos_idx]
+        return self._column(state)
 
 
 class CustomReward(RewardInterface):
+    """``reward_callback(state, action, next_state)``; 0 without one."""
+
     def __init__(self, reward_callback=None):
         self._reward_callback = reward_callback
 
     def __call__(self, state, action, next_state, absorbing):
-        if self._reward_callback is not None:
-            return self._reward_callback(state, action, next_state)
-        return 0
+        cb = self._reward_callback
+        return 0 if cb is None else cb(state, action, next_state)
 
 
-class TargetVelocityReward(RewardInterface):
+class TargetVelocityReward(_Column):
+    """exp(-(v_x - v_target)^2) on the root x velocity (reward.py:66-74; target 1.25 walk / 2.5 run)."""
+
     def __init__(self, target_velocity, x_vel_idx):
-        self._target_vel = target_velocity
-        self._x_vel_idx = x_vel_idx
+        super().__init__(x_vel_idx)
+        self._target_vel, self._x_vel_idx = target_velocity, self._idx
 
     def __call__(self, state, action, next_state, absorbing):
-        x_vel = torch.as_tensor(state)[..., self._x_vel_idx]
-        return torch.exp(-torch.square(x_vel - self._target_vel))
+        err = self._column(state) - self._target_vel
+        return torch.exp(-(err * err))
