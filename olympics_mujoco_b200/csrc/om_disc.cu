@@ -96,10 +96,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// cvt.rna.tf32.f32 (round to nearest, ties away from zero) as two integer-pipe instructions: the conversion instruction
+// issues on the XU pipe (16 lanes / clk / SM), which ncu showed 62 % busy -- busier than the tensor pipe -- in
+// disc_vail2_kernel (36 chunks x 16 conversions per sample).  Same bits as the host-side split_tf32.
+__device__ __forceinline__ float tf32_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+// h[i] = relu(h[i] + bias[i]) for 16 consecutive parameters read from shared memory as four 128-bit loads (64-byte
+// aligned; scalar loads made the bias reads a third of the kernel's shared-memory wavefronts)
+__device__ __forceinline__ void bias_relu16(float (&h)[16], const float* bias) {
+  const float4* q = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = q[i];
+    h[4 * i] = fmaxf(h[4 * i] + t.x, 0.f); h[4 * i + 1] = fmaxf(h[4 * i + 1] + t.y, 0.f);
+    h[4 * i + 2] = fmaxf(h[4 * i + 2] + t.z, 0.f); h[4 * i + 3] = fmaxf(h[4 * i + 3] + t.w, 0.f);
+  }
 }
 
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row x 16-byte core matrices,
@@ -781,8 +791,7 @@ __global__ void __launch_bounds__(192, 2) disc_vail2_kernel(DiscArgs a) {
           if (c == 0) wait_chunk(g - 1);                                  // this layer-1 block is complete
           float h[16];
           tmem_ld16(lane_addr + DA + c * V2_KC, h);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) h[i] = fmaxf(h[i] + b1[blk * 128 + c * V2_KC + i], 0.f);
+          bias_relu16(h, b1 + blk * 128 + c * V2_KC);
           put(h);
         }
       }
@@ -794,8 +803,7 @@ __global__ void __launch_bounds__(192, 2) disc_vail2_kernel(DiscArgs a) {
           if (c == 0 && hb == 0) wait_chunk(g - 1);                       // layer 2 complete
           float h[16];
           tmem_ld16(lane_addr + DB + c * V2_KC, h);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) h[i] = fmaxf(h[i] + b2[c * V2_KC + i], 0.f);
+          bias_relu16(h, b2 + c * V2_KC);
           put(h);
         }
         // head over latent dimensions 64 hb .. 64 hb + 63: z = mu + exp(logvar / 2) eps, d += wd . z
@@ -811,14 +819,24 @@ __global__ void __launch_bounds__(192, 2) disc_vail2_kernel(DiscArgs a) {
           float mu[32], lv[32];
           tmem_ld32(lane_addr + DA + q * 32, mu);
           tmem_ld32(lane_addr + DA + 64 + q * 32, lv);
+          const float4* bm4 = reinterpret_cast<const float4*>(b3 + 128 * hb + 32 * q);
+          const float4* bl4 = reinterpret_cast<const float4*>(b3 + 128 * hb + 64 + 32 * q);
+          const float4* wv4 = reinterpret_cast<const float4*>(wd + 64 * hb + 32 * q);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int j = 64 * hb + 32 * q + i;
-            const float e = q == 0 ? e0[i] : e1[i];
-            const float m = mu[i] + b3[128 * hb + 32 * q + i], l = lv[i] + b3[128 * hb + 64 + 32 * q + i];
-            const float sd = expf(0.5f * l);
-            dval = fmaf(wd[j], fmaf(sd, e, m), dval);
-            if (KL) klv += fmaf(m, m, fmaf(sd, sd, -l)) - 1.f;       // VDBLoss.kl_divergence, math.py:83-86
+          for (int i4 = 0; i4 < 8; ++i4) {
+            // biases / head weights: one 128-bit shared-memory load per four latent dimensions
+            const float4 bm_ = bm4[i4], bl_ = bl4[i4], wv_ = wv4[i4];
+            const float bmv[4] = {bm_.x, bm_.y, bm_.z, bm_.w}, blv[4] = {bl_.x, bl_.y, bl_.z, bl_.w};
+            const float wvv[4] = {wv_.x, wv_.y, wv_.z, wv_.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int i = 4 * i4 + k;
+              const float e = q == 0 ? e0[i] : e1[i];
+              const float m = mu[i] + bmv[k], l = lv[i] + blv[k];
+              const float sd = expf(0.5f * l);
+              dval = fmaf(wvv[k], fmaf(sd, e, m), dval);
+              if (KL) klv += fmaf(m, m, fmaf(sd, sd, -l)) - 1.f;       // VDBLoss.kl_divergence, math.py:83-86
+            }
           }
         }
       }
