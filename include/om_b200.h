@@ -243,6 +243,19 @@ typedef struct OmA3Out {
  * carried from step to step in registers. */
 int om_a3_task_step(const OmModel* m, const OmA3Task* task, const float* qpos, const float* qvel, const float* contact,
                     int n_steps, const OmA3State* state, const OmA3Out* out, int n, int ld, void* stream);
+/* The same step tail for a ROLLOUT BUFFER, finished with the discounted returns of PPOBuffer.finish_path
+ * (rl/algos/ppo.py:68-84, bootstrap :195-196, advantage :335) -- BASELINE configs[2]: obs / reward / done + returns.  Same
+ * results as om_a3_task_step followed by om_ppo_returns(out->reward, values, path_end, v_next, v_last, gamma, ...), enqueued
+ * by ONE call (the scan kernel follows the task kernels on the same stream).  path_end NULL = the done flags of this call
+ * (1 = terminated, bootstrap 0); out->reward and returns->ret are required. */
+typedef struct OmA3Returns {
+  const float* values; const float* v_next; const float* v_last; const uint8_t* path_end;
+  float gamma;
+  float* ret; float* adv;
+} OmA3Returns;
+int om_a3_task_rollout(const OmModel* m, const OmA3Task* task, const float* qpos, const float* qvel, const float* contact,
+                       int n_steps, const OmA3State* state, const OmA3Out* out, const OmA3Returns* returns, int n, int ld,
+                       void* stream);
 /* StickFigureA3.reset_model (StickFigureA3.py:205-235) + WalkingTask.reset (walking_task.py:321-397) for the envs
  * selected by mask (NULL = all).  Draws follow the Philox contract: key = seed, counter = (env_id0 + i,
  * reset_count[i], 16 + block, 0), 15 blocks = 60 uniforms in the order documented in oracle/a3.py.

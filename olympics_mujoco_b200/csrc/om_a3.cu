@@ -23,7 +23,7 @@ struct A3Args {
 
 struct SeqGlobal {
   const float* base; size_t ld;
-  OM_HD float operator()(int t, int c) const { return base[(size_t)(t * 4 + c) * ld]; }
+  OM_HD float operator()(int t, int c) const { return base[(unsigned)(t * 4 + c) * (unsigned)ld]; }     // 80 rows: 32-bit offsets
 };
 struct SeqStore {
   float* base; size_t ld;
@@ -128,19 +128,27 @@ struct A3Scratch {
   uint32_t* fix_list;   // [T * n]  t * n + env
 };
 
+// Row k of a per-(env, t) SoA block: ONE 64-bit base pointer per array (it carries t and the env), rows addressed by the
+// 32-bit, warp-uniform offset k * ld -- one IMAD.WIDE per access.  Written as (t * C + k) * ld + e in size_t the compiler
+// spent five integer instructions on every one of the ~120 loads and stores of this kernel: a third of its instructions.
+// (om_a3_task_step checks that rows * ld fits 32 bits.)
+__device__ __forceinline__ const float* row(const float* base, unsigned k, unsigned ld) { return base + k * ld; }
+__device__ __forceinline__ float* row(float* base, unsigned k, unsigned ld) { return base + k * ld; }
+
 // one env-step of the (env, t)-parallel pass
 __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w, int ncand, int t, size_t e) {
   const size_t ld = a.ld;
+  const unsigned lu = (unsigned)a.ld;
   float q[A3_NQ], qd[A3_NV], con[4];
   const float* qp = a.qpos + (size_t)t * A3_NQ * ld + e;
   const float* vp = a.qvel + (size_t)t * A3_NV * ld + e;
   const float* cp = a.contact + (size_t)t * 4 * ld + e;
 #pragma unroll
-  for (int k = 0; k < A3_NQ; ++k) q[k] = qp[k * ld];
+  for (int k = 0; k < A3_NQ; ++k) q[k] = *row(qp, k, lu);
 #pragma unroll
-  for (int k = 0; k < A3_NV; ++k) qd[k] = vp[k * ld];
+  for (int k = 0; k < A3_NV; ++k) qd[k] = *row(vp, k, lu);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) con[k] = cp[k * ld];
+  for (int k = 0; k < 4; ++k) con[k] = *row(cp, k, lu);
   int phase = a.ints[A3I_PHASE * ld + e] + (t + 1) % a.C.period;            // walking_task.py:248-250, t + 1 increments;
   if (phase >= a.C.period) phase -= a.C.period;                            // the modulo is warp-uniform, the wrap a select
   const int mode = a.ints[A3I_MODE * ld + e];
@@ -166,18 +174,18 @@ __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w
   A3Exact ex{qp, ld, true, false};               // decisions within A3_BAND of a threshold are only NOTED here (a3_fix_kernel)
   const A3Rec rec = a3_task_pre(a.C, a3_task_in(S.f), phase, mode, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, terms,
                                 obs[31], obs[32], done, ex);
-  a3_rec_store(rec, w.feat + (size_t)t * A3_NREC * ld + e, ld);
+  a3_rec_store(rec, w.feat + (size_t)t * A3_NREC * ld + e, lu);
   const int nc = a3_cand_needed(t, a.ints[A3I_FRAMES * ld + e], a.C.delay_frames, ncand);   // later targets are out of reach
   w.near[e * w.tp + t] =
       (uint8_t)a3_near_bits(a.C, rec.lsite, rec.rsite, nc, t1_0, t2_0, seq_len, SeqGlobal{a.sequence + e, ld}, ex);
   if (a.o.obs) {
     float* ob = a.o.obs + (size_t)t * A3_NOBS * ld + e;
 #pragma unroll
-    for (int k = 0; k < 33; ++k) ob[k * ld] = obs[k];
+    for (int k = 0; k < 33; ++k) *row(ob, k, lu) = obs[k];
   }
   if (a.o.terms) {
     float* tp = a.o.terms + (size_t)t * 6 * ld + e;
-    tp[0] = terms[0]; tp[ld] = terms[1]; tp[3 * ld] = terms[3]; tp[5 * ld] = terms[5];
+    tp[0] = terms[0]; *row(tp, 1, lu) = terms[1]; *row(tp, 3, lu) = terms[3]; *row(tp, 5, lu) = terms[5];
   }
   if (a.o.done) a.o.done[(size_t)t * ld + e] = done ? 1 : 0;
   if (ex.unsure) w.fix_list[atomicAdd(w.fix_count, 1u)] = (uint32_t)t * (uint32_t)a.n + (uint32_t)e;
@@ -252,8 +260,8 @@ __device__ __forceinline__ void a3_walk(const A3Args& a, const A3Scratch& w, siz
   a.ints[A3I_FRAMES * ld + e] = s.frames; a.ints[A3I_REACHED * ld + e] = s.reached;
 }
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 5) a3_feat_kernel(A3Args a, A3Scratch w, int ncand) {
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) a3_feat_kernel(A3Args a, A3Scratch w, int ncand) {
   const int env = blockIdx.x * BLOCK + threadIdx.x;
   if (env < a.n) a3_feat_item(a, w, ncand, blockIdx.y, env);
 }
@@ -270,29 +278,34 @@ __global__ void __launch_bounds__(BLOCK) a3_post_kernel(A3Args a, A3Scratch w) {
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *w.fix_count = 0u;      // consumed by a3_fix_kernel: ready for the next call
   if (env >= a.n) return;
   const size_t ld = a.ld, e = env;
-  const A3Rec rec = a3_rec_load(w.feat + (size_t)t * A3_NREC * ld + e, ld);
+  const unsigned lu = (unsigned)a.ld;
+  const A3Rec rec = a3_rec_load(w.feat + (size_t)t * A3_NREC * ld + e, lu);
   const int code = w.code[e * w.tp + t];
   const int mode = a.ints[A3I_MODE * ld + e], seq_len = a.ints[A3I_SEQLEN * ld + e];
   const int t1_0 = w.start[e], t2_0 = w.start[ld + e];
   const int j = code & 7;
-  const float* tr = w.trig + (size_t)j * 4 * ld + e;                   // candidate j, then candidate j + 1
-  const A3TargetTrig tg{tr[0], tr[ld], tr[4 * ld], tr[5 * ld], tr[2 * ld], tr[3 * ld]};
+  const float* tr = w.trig + e + (unsigned)(j * 4) * lu;               // candidate j, then candidate j + 1
+  const A3TargetTrig tg{tr[0], *row(tr, 1, lu), *row(tr, 4, lu), *row(tr, 5, lu), *row(tr, 2, lu), *row(tr, 3, lu)};
   float goal[8], tm2, tm4, total;
   a3_task_post(a.C, rec, mode, a3_cand(j, t1_0, t2_0, seq_len), a3_cand(j + 1, t1_0, t2_0, seq_len), (code >> 3) != 0,
                SeqGlobal{a.sequence + e, ld}, &tg, goal, tm2, tm4, total);
   if (a.o.obs) {
     float* ob = a.o.obs + ((size_t)t * A3_NOBS + 33) * ld + e;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) ob[k * ld] = goal[k];
+    for (int k = 0; k < 8; ++k) *row(ob, k, lu) = goal[k];
   }
   if (a.o.terms) {
     float* tp = a.o.terms + (size_t)t * 6 * ld + e;
-    tp[2 * ld] = tm2;
-    tp[4 * ld] = tm4;
+    *row(tp, 2, lu) = tm2;
+    *row(tp, 4, lu) = tm4;
   }
   if (a.o.reward) a.o.reward[(size_t)t * ld + e] = total;
 }
 
+// (Measured and rejected: finishing the discounted returns inside the post pass -- a CTA owning 32 envs x all steps, each
+// thread walking 8 consecutive steps and composing the affine recurrence from the rewards it has just computed.  Bit-equal
+// to post + affine_scan, but 52 us unrolled (instruction cache) / 59 us rolled against 28 + 10 us for the two kernels: one
+// thread per (env, t) hides the record / table latencies far better than eight sequential steps per thread.)
 struct A3ResetArgs {
   A3TaskConst C;
   const float* init_qpos;   // device [25]
@@ -401,12 +414,13 @@ extern "C" void om_a3_task_destroy(OmA3Task* t) {
   delete t;
 }
 
-extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const float* qpos, const float* qvel,
-                               const float* contact, int n_steps, const OmA3State* state, const OmA3Out* out, int n, int ld,
-                               void* stream) {
+static int a3_step_impl(const OmModel* m, const OmA3Task* task, const float* qpos, const float* qvel, const float* contact,
+                        int n_steps, const OmA3State* state, const OmA3Out* out, const OmA3Returns* rets, int n, int ld,
+                        void* stream) {
   OM_REQUIRE(m && task && state && out, "om_a3_task_step: null argument");
   OM_REQUIRE(m->specialised == SPEC_A3, "om_a3_task_step: model is not the StickFigureA3 model");
   OM_REQUIRE(n >= 0 && ld >= n && n_steps >= 0, "om_a3_task_step: bad sizes (n=%d ld=%d n_steps=%d)", n, ld, n_steps);
+  OM_REQUIRE((unsigned long long)ld * 128ull < 0xffffffffull, "om_a3_task_step: ld too large for 32-bit row offsets");
   if (n == 0 || n_steps == 0) return 0;
   OM_REQUIRE(qpos && qvel && contact && state->ints && state->sequence, "om_a3_task_step: null input / state");
   A3Args a{task->C, qpos, qvel, contact, state->ints, state->sequence, *out, n_steps, n, ld};
@@ -461,7 +475,9 @@ extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const flo
       w.tp = (len + 15) / 16 * 16;
       OM_REQUIRE(len <= 65535, "om_a3_task_step: at most 65535 steps per call");
       const int ncand = a3_num_cand_host(len, task->C.delay_frames);
-      a3_feat_kernel<FB><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
+      if (g_knobs.a3_feat_minb == 6) a3_feat_kernel<FB, 6><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
+      else if (g_knobs.a3_feat_minb == 4) a3_feat_kernel<FB, 4><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
+      else a3_feat_kernel<FB, 5><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
       OM_LAUNCHED();
       a3_fix_kernel<<<64, 64, 0, st>>>(sub, w, ncand);             // float64 re-decisions of the noted env-steps (usually ~1e-4 of them)
       OM_LAUNCHED();
@@ -470,12 +486,34 @@ extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const flo
       a3_post_kernel<FB><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w);
       OM_LAUNCHED();
     }
+    if (rets)                                     // the returns scan over the rewards just written (same stream, same call)
+      return om_ppo_returns(out->reward, rets->values, rets->path_end ? rets->path_end : out->done, rets->v_next, rets->v_last,
+                            rets->gamma, n_steps, n, ld, rets->ret, rets->adv, stream);
     return 0;
   }
   if (want_fk) a3_task_kernel<BLOCK, true><<<grid, BLOCK, 0, st>>>(a);
   else a3_task_kernel<BLOCK, false><<<grid, BLOCK, 0, st>>>(a);
   OM_LAUNCHED();
+  if (rets)
+    return om_ppo_returns(out->reward, rets->values, rets->path_end ? rets->path_end : out->done, rets->v_next, rets->v_last,
+                          rets->gamma, n_steps, n, ld, rets->ret, rets->adv, stream);
   return 0;
+}
+
+extern "C" int om_a3_task_step(const OmModel* m, const OmA3Task* task, const float* qpos, const float* qvel,
+                               const float* contact, int n_steps, const OmA3State* state, const OmA3Out* out, int n, int ld,
+                               void* stream) {
+  return a3_step_impl(m, task, qpos, qvel, contact, n_steps, state, out, nullptr, n, ld, stream);
+}
+
+extern "C" int om_a3_task_rollout(const OmModel* m, const OmA3Task* task, const float* qpos, const float* qvel,
+                                  const float* contact, int n_steps, const OmA3State* state, const OmA3Out* out,
+                                  const OmA3Returns* returns, int n, int ld, void* stream) {
+  OM_REQUIRE(returns && out, "om_a3_task_rollout: null argument");
+  OM_REQUIRE(out->reward && returns->ret, "om_a3_task_rollout: the reward and ret buffers are required");
+  OM_REQUIRE(returns->path_end || out->done, "om_a3_task_rollout: the returns need the done flags (out->done) or path_end");
+  OM_REQUIRE(!returns->adv || returns->values, "om_a3_task_rollout: advantages need values");
+  return a3_step_impl(m, task, qpos, qvel, contact, n_steps, state, out, returns, n, ld, stream);
 }
 
 extern "C" int om_a3_reset(const OmModel* m, const OmA3Task* task, uint64_t seed, uint32_t env_id0, const uint8_t* mask,

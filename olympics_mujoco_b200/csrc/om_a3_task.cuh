@@ -343,20 +343,21 @@ struct A3Rec {
   V3 root_p; Q4 root_q; V3 lsite, rsite;
   float t01, t3, t5;                  // terms[0] + terms[1], terms[3], terms[5] (summed later in the reference's order)
 };
-OM_HD void a3_rec_store(const A3Rec& r, float* b, size_t ld) {
-  b[0] = r.root_p.x; b[ld] = r.root_p.y; b[2 * ld] = r.root_p.z;
-  b[3 * ld] = r.root_q.w; b[4 * ld] = r.root_q.x; b[5 * ld] = r.root_q.y; b[6 * ld] = r.root_q.z;
-  b[7 * ld] = r.lsite.x; b[8 * ld] = r.lsite.y; b[9 * ld] = r.lsite.z;
-  b[10 * ld] = r.rsite.x; b[11 * ld] = r.rsite.y; b[12 * ld] = r.rsite.z;
-  b[13 * ld] = r.t01; b[14 * ld] = r.t3; b[15 * ld] = r.t5;
+// ld as a 32-bit row stride: b + k * ld is one widening multiply-add per row (see om_a3.cu: row())
+OM_HD void a3_rec_store(const A3Rec& r, float* b, unsigned ld) {
+  b[0] = r.root_p.x; b[ld] = r.root_p.y; b[2u * ld] = r.root_p.z;
+  b[3u * ld] = r.root_q.w; b[4u * ld] = r.root_q.x; b[5u * ld] = r.root_q.y; b[6u * ld] = r.root_q.z;
+  b[7u * ld] = r.lsite.x; b[8u * ld] = r.lsite.y; b[9u * ld] = r.lsite.z;
+  b[10u * ld] = r.rsite.x; b[11u * ld] = r.rsite.y; b[12u * ld] = r.rsite.z;
+  b[13u * ld] = r.t01; b[14u * ld] = r.t3; b[15u * ld] = r.t5;
 }
-OM_HD A3Rec a3_rec_load(const float* b, size_t ld) {
+OM_HD A3Rec a3_rec_load(const float* b, unsigned ld) {
   A3Rec r;
-  r.root_p = V3{b[0], b[ld], b[2 * ld]};
-  r.root_q = Q4{b[3 * ld], b[4 * ld], b[5 * ld], b[6 * ld]};
-  r.lsite = V3{b[7 * ld], b[8 * ld], b[9 * ld]};
-  r.rsite = V3{b[10 * ld], b[11 * ld], b[12 * ld]};
-  r.t01 = b[13 * ld]; r.t3 = b[14 * ld]; r.t5 = b[15 * ld];
+  r.root_p = V3{b[0], b[ld], b[2u * ld]};
+  r.root_q = Q4{b[3u * ld], b[4u * ld], b[5u * ld], b[6u * ld]};
+  r.lsite = V3{b[7u * ld], b[8u * ld], b[9u * ld]};
+  r.rsite = V3{b[10u * ld], b[11u * ld], b[12u * ld]};
+  r.t01 = b[13u * ld]; r.t3 = b[14u * ld]; r.t5 = b[15u * ld];
   return r;
 }
 

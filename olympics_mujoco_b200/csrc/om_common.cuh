@@ -30,6 +30,7 @@ struct Knobs {
   int serial_scan = 0;    // OM_SERIAL_SCAN  1: one-thread-per-env returns / GAE kernels
   int disc_vail2 = -1;    // OM_DISC_VAIL2   1 / 0: two-CTAs-per-SM VAIL kernel
   int disc_pg2 = -1;      // OM_DISC_PG2     1 / 0: two producer warpgroups
+  int a3_feat_minb = 5;   // OM_A3_FEAT_MINB 4 / 5 / 6: resident CTAs per SM the A3 replay kernel is compiled for (tuning)
 };
 extern Knobs g_knobs;
 

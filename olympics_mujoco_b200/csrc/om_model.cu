@@ -36,6 +36,7 @@ Knobs g_knobs = [] {
   k.serial_scan = env_int("OM_SERIAL_SCAN", 0);
   k.disc_vail2 = env_int("OM_DISC_VAIL2", -1);
   k.disc_pg2 = env_int("OM_DISC_PG2", -1);
+  k.a3_feat_minb = env_int("OM_A3_FEAT_MINB", 5);
   return k;
 }();
 
@@ -80,6 +81,7 @@ extern "C" int om_debug_set(const char* knob, int value) {
   else if (k == "serial_scan") g_knobs.serial_scan = value;
   else if (k == "disc_vail2") g_knobs.disc_vail2 = value;
   else if (k == "disc_pg2") g_knobs.disc_pg2 = value;
+  else if (k == "a3_feat_minb") g_knobs.a3_feat_minb = value;
   else return fail("om_debug_set: unknown knob '%s'", knob);
   return 0;
 }

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (OmA3Out, OmA3State, OmA3TaskDesc, OmActionSpec, OmDiscDesc, OmH1Spec, OmLiveOut, OmLiveState, OmMirrorSpec,
+from ._lib import (OmA3Out, OmA3Returns, OmA3State, OmA3TaskDesc, OmActionSpec, OmDiscDesc, OmH1Spec, OmLiveOut, OmLiveState, OmMirrorSpec,
                    OmPdSpec, OmModelDesc, OmPlayOut, OmPlayState, check)
 from .mjcf import KinematicModel
 
@@ -336,9 +336,12 @@ class A3Task:
                                       _stream()))
         return obs
 
-    def step(self, qpos, qvel, contact, want=("obs", "terms", "reward", "done"), out=None):
+    def step(self, qpos, qvel, contact, want=("obs", "terms", "reward", "done"), out=None, returns=None):
         """The StickFigureA3.step tail on post-physics states.  qpos [25,n] (one step) or [T,25,n] (replay of T
-        recorded steps); qvel / contact ([4,n]: l_grf, r_grf, min contact z, flags) likewise."""
+        recorded steps); qvel / contact ([4,n]: l_grf, r_grf, min contact z, flags) likewise.
+        ``returns``: dict(values [T,n], gamma, v_next=None, v_last=None, path_end=None) -- the rollout is finished with
+        PPOBuffer.finish_path's discounted returns by the same call (``om_a3_task_rollout``); ``out`` then also holds
+        ``ret`` and ``adv`` [T,n]."""
         T = 1 if qpos.dim() == 2 else qpos.shape[0]
         n, dev = self.n, qpos.device
         assert qpos.shape[-2:] == (25, n) and qvel.shape[-2:] == (24, n) and contact.shape[-2:] == (4, n)
@@ -351,9 +354,21 @@ class A3Task:
                 shape = ((n,) if c is None else (c, n)) if qpos.dim() == 2 else ((T, n) if c is None else (T, c, n))
                 out[k] = torch.empty(shape, dtype=dt_, device=dev)
         for k, t in out.items():
-            _p(t, sizes[k][1])
+            _p(t, torch.float32 if k in ("ret", "adv") else sizes[k][1])
         po = OmA3Out(**{k: (out[k].data_ptr() if k in out else None) for k in sizes})
         st = self._state()
+        if returns is not None:
+            assert qpos.dim() == 3 and "reward" in out and "done" in out
+            for k in ("ret", "adv"):
+                if k not in out:
+                    out[k] = torch.empty((T, n), dtype=torch.float32, device=dev)
+            g = lambda k, dt_=torch.float32: None if returns.get(k) is None else _p(returns[k], dt_).value
+            pr = OmA3Returns(values=g("values"), v_next=g("v_next"), v_last=g("v_last"), path_end=g("path_end", torch.uint8),
+                             gamma=float(returns["gamma"]), ret=out["ret"].data_ptr(), adv=out["adv"].data_ptr())
+            check(_lib.load().om_a3_task_rollout(self.dm.handle, self.handle, _p(qpos, torch.float32), _p(qvel, torch.float32),
+                                                 _p(contact, torch.float32), T, C.byref(st), C.byref(po), C.byref(pr), n,
+                                                 max(n, 1), _stream()))
+            return out
         check(_lib.load().om_a3_task_step(self.dm.handle, self.handle, _p(qpos, torch.float32), _p(qvel, torch.float32),
                                           _p(contact, torch.float32), T, C.byref(st), C.byref(po), n, max(n, 1), _stream()))
         return out

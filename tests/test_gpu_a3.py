@@ -271,3 +271,56 @@ def test_a3_replay_state_machine_stress(a3_model, delay, radius, om_knob):
     assert_close(b["obs"], a["obs"], "obs", rtol=1e-6, atol=1e-6)
     assert_close(b["terms"], a["terms"], "terms", rtol=1e-6, atol=1e-6)
     assert_close(b["reward"], a["reward"], "reward", rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("T,n", [(64, 1000), (37, 130), (230, 96)])
+def test_a3_rollout_with_fused_returns_equals_step_then_ppo_returns(a3_model, T, n):
+    """om_a3_task_rollout (configs[2]: obs / reward / done + PPOBuffer.finish_path returns, one call) ==
+    om_a3_task_step followed by om_ppo_returns, bit for bit on every output; T = 230 takes the several-sub-call route;
+    the returns are also checked against the reference's PPOBuffer restatement."""
+    import torch
+    from olympics_mujoco_b200 import kernels as Kn
+    from oracle import learner as L
+    g = torch.Generator(device="cuda").manual_seed(5)
+    res = {}
+    for fused in (False, True):
+        task = _task(a3_model, n, seed=3)
+        q0, v0 = Kn.soa(25, n), Kn.soa(24, n)
+        task.reset(q0, v0, iteration_count=5000.0)
+        if not fused:
+            qpos = q0[None] + 0.01 * torch.randn((T, 25, n), device="cuda", generator=g).cumsum(0)
+            fold = torch.linspace(0, 1, T, device="cuda")[:, None] * (torch.rand(n, device="cuda", generator=g) < 0.3)
+            for hip, knee in ((7, 10), (13, 16)):
+                qpos[:, hip] -= 1.5 * fold
+                qpos[:, knee] -= 1.6 * fold
+            qvel = torch.randn((T, 24, n), device="cuda", generator=g)
+            con = torch.stack([torch.rand((T, n), device="cuda", generator=g) * 400, torch.rand((T, n), device="cuda", generator=g) * 400,
+                               (torch.rand((T, n), device="cuda", generator=g) - 0.5) * 0.02,
+                               (torch.rand((T, n), device="cuda", generator=g) < 0.7).float()], dim=1).contiguous()
+            values = torch.randn((T + 1, n), device="cuda", generator=g)
+            v_last = torch.randn(n, device="cuda", generator=g)
+            out = task.step(qpos, qvel, con)
+            ret, adv = Kn.ppo_returns(out["reward"], values[:-1].contiguous(), 0.99, path_end=out["done"], v_next=values[1:].contiguous(),
+                                      v_last=v_last)
+            res[fused] = dict(out, ret=ret, adv=adv, ints=task.ints.clone())
+        else:
+            out = task.step(qpos, qvel, con, returns=dict(values=values[:-1].contiguous(), v_next=values[1:].contiguous(),
+                                                          v_last=v_last, gamma=0.99))
+            res[fused] = dict(out, ints=task.ints.clone())
+    torch.cuda.synchronize()
+    for k in ("obs", "terms", "reward", "done", "ret", "adv", "ints"):
+        assert torch.equal(res[False][k], res[True][k]), k
+    assert bool(res[True]["done"].any())
+    r, d, v = (res[True][k].cpu().numpy() for k in ("reward", "done", "ret"))
+    vals, vl = values.cpu().numpy(), v_last.cpu().numpy()
+    for e in range(0, n, max(1, n // 7)):
+        want = L.ppo_returns_path_end(r[:, e], d[:, e], 0.99, v_last=vl[e]) if hasattr(L, "ppo_returns_path_end") else None
+        if want is None:                                   # plain restatement of finish_path over the done-delimited paths
+            want = np.zeros(T)
+            R = float(vl[e])
+            for t in range(T - 1, -1, -1):
+                if d[t, e] == 1:
+                    R = 0.0
+                R = float(r[t, e]) + 0.99 * R
+                want[t] = R
+        assert_close(v[:, e], want, "returns vs finish_path", rtol=2e-5, atol=2e-5)

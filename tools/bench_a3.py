@@ -15,7 +15,7 @@ sys.path.insert(0, str(ROOT))
 BYTES_PER_ENV_STEP = 490          # SURVEY.md 8(d) config 3 (FK fused, not materialised)
 
 
-def measure(envs=16384, horizon=64, steps=20, warmup=3, per_step=False):
+def measure(envs=16384, horizon=64, steps=20, warmup=3, per_step=False, fused_returns=True):
     args = argparse.Namespace(envs=envs, horizon=horizon, steps=steps, warmup=warmup, per_step=per_step)
     from olympics_mujoco_b200 import kernels as Kn
     from olympics_mujoco_b200 import mjcf
@@ -39,6 +39,8 @@ def measure(envs=16384, horizon=64, steps=20, warmup=3, per_step=False):
     values = torch.randn((T + 1, n), device="cuda", generator=g)
     out = dict(obs=torch.empty((T, 41, n), device="cuda"), terms=torch.empty((T, 6, n), device="cuda"),
                reward=torch.empty((T, n), device="cuda"), done=torch.empty((T, n), dtype=torch.uint8, device="cuda"))
+    if fused_returns and not per_step:
+        out.update(ret=torch.empty((T, n), device="cuda"), adv=torch.empty((T, n), device="cuda"))
     ints0, seq0 = task.ints.clone(), task.sequence.clone()
     mom = torch.zeros(3, dtype=torch.float64, device="cuda")
 
@@ -49,9 +51,14 @@ def measure(envs=16384, horizon=64, steps=20, warmup=3, per_step=False):
         if args.per_step:
             for t in range(T):
                 task.step(qpos[t], qvel[t], con[t], out={k: v[t] for k, v in out.items()})
+        elif fused_returns:
+            # obs / reward / done AND the discounted returns enqueued by one call (om_a3_task_rollout)
+            res = task.step(qpos, qvel, con, out=out, returns=dict(values=values[:-1], v_next=values[1:], gamma=0.99))
+            ret, adv = res["ret"], res["adv"]
         else:
             task.step(qpos, qvel, con, out=out)
-        ret, adv = Kn.ppo_returns(out["reward"], values[:-1], 0.99, path_end=out["done"], v_next=values[1:])
+        if args.per_step or not fused_returns:
+            ret, adv = Kn.ppo_returns(out["reward"], values[:-1], 0.99, path_end=out["done"], v_next=values[1:])
         if ev:
             ev[1].record()            # the 490 B/env-step of SURVEY 8(d) include the returns pass, so it is timed with the task
         mom.zero_()
@@ -76,9 +83,10 @@ def measure(envs=16384, horizon=64, steps=20, warmup=3, per_step=False):
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {"hbm_gbs": 6650.0}
     achieved = BYTES_PER_ENV_STEP * n * T / (kms * 1e-3) / 1e9
     return {"workload": f"A3 PPO walk rollout {n} envs x {T} steps (configs[2])", "per_step_launches": args.per_step,
+            "fused_returns": bool(fused_returns and not args.per_step),
             "value": n * T / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "task_kernel_ms": kms,
             "gpu_launches": Kn.launch_count(),
-            "roofline": {"bound": "hbm", "kernel": "a3_feat_kernel (+ state-machine tail) + a3_post_kernel + affine_scan/ppo_returns", "achieved": achieved, "peak": peaks["hbm_gbs"],
+            "roofline": {"bound": "hbm", "kernel": "a3_feat_kernel + a3_fix_kernel + a3_walk_kernel + a3_post_kernel + affine_scan_kernel (om_a3_task_rollout: one call)", "achieved": achieved, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "bytes_per_env_step": BYTES_PER_ENV_STEP}}
 
 
@@ -89,8 +97,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--per-step", action="store_true", help="launch the step kernel once per env step (the live-rollout pattern)")
+    ap.add_argument("--separate-returns", action="store_true", help="om_a3_task_step + om_ppo_returns instead of om_a3_task_rollout")
     a = ap.parse_args()
-    print(json.dumps(measure(a.envs, a.horizon, a.steps, a.warmup, a.per_step)))
+    print(json.dumps(measure(a.envs, a.horizon, a.steps, a.warmup, a.per_step, not a.separate_returns)))
 
 
 if __name__ == "__main__":
