@@ -124,8 +124,6 @@ struct A3Scratch {
   int tp;
   int32_t* start;       // [2][ld]   t1, t2 at the start of the call
   float* trig;          // [A3_MAX_CAND + 1][4][ld]   sin, cos of candidate j's heading and of half of it (feat t = 0 -> post)
-  uint32_t* fix_count;  // number of env-steps whose threshold decisions a3_fix_kernel re-takes in float64
-  uint32_t* fix_list;   // [T * n]  t * n + env
 };
 
 // Row k of a per-(env, t) SoA block: ONE 64-bit base pointer per array (it carries t and the env), rows addressed by the
@@ -171,13 +169,15 @@ __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w
   om_fk_pos_stick_figure_a3(q, qd, S);           // matrix-chain variant: no body orientations needed
   bool done;
   const int fl = (int)con[3];
-  A3Exact ex{qp, ld, true, false};               // decisions within A3_BAND of a threshold are only NOTED here (a3_fix_kernel)
+  A3Exact ex{qp, ld, true, false};               // decisions within A3_BAND of a threshold are only NOTED here (bit 7 below)
   const A3Rec rec = a3_task_pre(a.C, a3_task_in(S.f), phase, mode, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, terms,
                                 obs[31], obs[32], done, ex);
   a3_rec_store(rec, w.feat + (size_t)t * A3_NREC * ld + e, lu);
   const int nc = a3_cand_needed(t, a.ints[A3I_FRAMES * ld + e], a.C.delay_frames, ncand);   // later targets are out of reach
-  w.near[e * w.tp + t] =
-      (uint8_t)a3_near_bits(a.C, rec.lsite, rec.rsite, nc, t1_0, t2_0, seq_len, SeqGlobal{a.sequence + e, ld}, ex);
+  const uint32_t bits = a3_near_bits(a.C, rec.lsite, rec.rsite, nc, t1_0, t2_0, seq_len, SeqGlobal{a.sequence + e, ld}, ex);
+  // bit 7: a decision of this env-step (done, or one of the candidate bits) is within A3_BAND of its threshold; the
+  // sequential pass re-takes it in float64 (a3_refix) before it consumes the byte -- about one env-step in 10^4
+  w.near[e * w.tp + t] = (uint8_t)(bits | (ex.unsure ? 0x80u : 0u));
   if (a.o.obs) {
     float* ob = a.o.obs + (size_t)t * A3_NOBS * ld + e;
 #pragma unroll
@@ -188,42 +188,37 @@ __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w
     tp[0] = terms[0]; *row(tp, 1, lu) = terms[1]; *row(tp, 3, lu) = terms[3]; *row(tp, 5, lu) = terms[5];
   }
   if (a.o.done) a.o.done[(size_t)t * ld + e] = done ? 1 : 0;
-  if (ex.unsure) w.fix_list[atomicAdd(w.fix_count, 1u)] = (uint32_t)t * (uint32_t)a.n + (uint32_t)e;
 }
 
-// Re-takes, in float64, the threshold decisions the (env, t)-parallel pass could not settle in fp32 (margin below A3_BAND:
-// about one env-step in 10^4): `done` and the candidate bits of the listed env-steps.  Grid-stride over the work list.
-__global__ void __launch_bounds__(64) a3_fix_kernel(A3Args a, A3Scratch w, int ncand) {
-  const uint32_t count = *w.fix_count;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-    const uint32_t item = w.fix_list[i];
-    const int t = (int)(item / (uint32_t)a.n);
-    const size_t e = item % (uint32_t)a.n, ld = a.ld;
-    const float* qp = a.qpos + (size_t)t * A3_NQ * ld + e;
-    const A3SitesF64 s = a3_sites_f64(qp, ld);
-    if (a.o.done) {
-      const int fl = (int)a.contact[((size_t)t * 4 + 3) * ld + e];
-      a.o.done[(size_t)t * ld + e] = ((double)qp[2 * ld] - fmin(s.ls[2], s.rs[2]) < 0.6 || (fl & 2) != 0) ? 1 : 0;
-    }
-    const int t1_0 = a.ints[A3I_T1 * ld + e], t2_0 = a.ints[A3I_T2 * ld + e], seq_len = a.ints[A3I_SEQLEN * ld + e];
-    const int nc = a3_cand_needed(t, a.ints[A3I_FRAMES * ld + e], a.C.delay_frames, ncand);
-    uint32_t bits = 0;
-    for (int j = 0; j < nc; ++j) {
-      const int k = a3_cand(j, t1_0, t2_0, seq_len);
-      const double px = (double)a.sequence[(size_t)(k * 4) * ld + e], py = (double)a.sequence[(size_t)(k * 4 + 1) * ld + e];
-      const double pz = (double)a.sequence[(size_t)(k * 4 + 2) * ld + e];
-      const double lx = s.ls[0] - px, ly = s.ls[1] - py, lz = s.ls[2] - pz;
-      const double rx = s.rs[0] - px, ry = s.rs[1] - py, rz = s.rs[2] - pz;
-      if (sqrt(lx * lx + ly * ly + lz * lz) < a.C.target_radius || sqrt(rx * rx + ry * ry + rz * rz) < a.C.target_radius)
-        bits |= 1u << j;
-    }
-    w.near[e * w.tp + t] = (uint8_t)bits;
+// Re-takes, in float64, the threshold decisions of ONE env-step that the (env, t)-parallel pass could not settle in fp32
+// (margin below A3_BAND): rewrites its `done` flag and returns its exact candidate bits.  Out of line: it is called by the
+// sequential pass for about one env-step in 10^4.
+__device__ __noinline__ uint32_t a3_refix(const A3Args& a, int ncand, int t, size_t e) {
+  const size_t ld = a.ld;
+  const float* qp = a.qpos + (size_t)t * A3_NQ * ld + e;
+  const A3SitesF64 s = a3_sites_f64(qp, ld);
+  if (a.o.done) {
+    const int fl = (int)a.contact[((size_t)t * 4 + 3) * ld + e];
+    a.o.done[(size_t)t * ld + e] = ((double)qp[2 * ld] - fmin(s.ls[2], s.rs[2]) < 0.6 || (fl & 2) != 0) ? 1 : 0;
   }
+  const int t1_0 = a.ints[A3I_T1 * ld + e], t2_0 = a.ints[A3I_T2 * ld + e], seq_len = a.ints[A3I_SEQLEN * ld + e];
+  const int nc = a3_cand_needed(t, a.ints[A3I_FRAMES * ld + e], a.C.delay_frames, ncand);
+  uint32_t bits = 0;
+  for (int j = 0; j < nc; ++j) {
+    const int k = a3_cand(j, t1_0, t2_0, seq_len);
+    const double px = (double)a.sequence[(size_t)(k * 4) * ld + e], py = (double)a.sequence[(size_t)(k * 4 + 1) * ld + e];
+    const double pz = (double)a.sequence[(size_t)(k * 4 + 2) * ld + e];
+    const double lx = s.ls[0] - px, ly = s.ls[1] - py, lz = s.ls[2] - pz;
+    const double rx = s.rs[0] - px, ry = s.rs[1] - py, rz = s.rs[2] - pz;
+    if (sqrt(lx * lx + ly * ly + lz * lz) < a.C.target_radius || sqrt(rx * rx + ry * ry + rz * rz) < a.C.target_radius)
+      bits |= 1u << j;
+  }
+  return bits;
 }
 
 // The integer state machine over the T candidate bytes of one env (a few instructions per step); leaves a one-byte
 // (advances, reached) code per env-step and the final task state.
-__device__ __forceinline__ void a3_walk(const A3Args& a, const A3Scratch& w, size_t e) {
+__device__ __forceinline__ void a3_walk(const A3Args& a, const A3Scratch& w, int ncand, size_t e) {
   const size_t ld = a.ld;
   const int t1_0 = a.ints[A3I_T1 * ld + e], t2_0 = a.ints[A3I_T2 * ld + e], seq_len = a.ints[A3I_SEQLEN * ld + e];
   A3Walk s{0, a.ints[A3I_FRAMES * ld + e], a.ints[A3I_REACHED * ld + e]};
@@ -236,7 +231,16 @@ __device__ __forceinline__ void a3_walk(const A3Args& a, const A3Scratch& w, siz
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
       if (t0 + 16 * v < a.T) {
-        const uint32_t wi[4] = {in[v].x, in[v].y, in[v].z, in[v].w};
+        uint32_t wi[4] = {in[v].x, in[v].y, in[v].z, in[v].w};
+        if ((wi[0] | wi[1] | wi[2] | wi[3]) & 0x80808080u) {         // rare: a flagged env-step among these sixteen
+#pragma unroll 1
+          for (int k = 0; k < 16; ++k) {
+            if (((wi[k >> 2] >> (8 * (k & 3))) & 0x80u) && t0 + 16 * v + k < a.T) {
+              const uint32_t exact = a3_refix(a, ncand, t0 + 16 * v + k, e);
+              wi[k >> 2] = (wi[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (exact << (8 * (k & 3)));
+            }
+          }
+        }
         uint32_t wo[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -266,16 +270,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) a3_feat_kernel(A3Args a, A3Scratc
   if (env < a.n) a3_feat_item(a, w, ncand, blockIdx.y, env);
 }
 
-__global__ void __launch_bounds__(64) a3_walk_kernel(A3Args a, A3Scratch w) {
+__global__ void __launch_bounds__(64) a3_walk_kernel(A3Args a, A3Scratch w, int ncand) {
   const int env = blockIdx.x * 64 + threadIdx.x;
-  if (env < a.n) a3_walk(a, w, env);
+  if (env < a.n) a3_walk(a, w, ncand, env);
 }
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) a3_post_kernel(A3Args a, A3Scratch w) {
   const int env = blockIdx.x * BLOCK + threadIdx.x;
   const int t = blockIdx.y;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *w.fix_count = 0u;      // consumed by a3_fix_kernel: ready for the next call
   if (env >= a.n) return;
   const size_t ld = a.ld, e = env;
   const unsigned lu = (unsigned)a.ld;
@@ -364,7 +367,6 @@ struct OmA3Task {
   // replay call per handle may be in flight at a time
   mutable void* scratch = nullptr;
   mutable size_t scratch_bytes = 0;
-  mutable void* fix_count_at = nullptr;   // where the zero-initialised work-list counter of the current scratch layout lives
 };
 
 extern "C" int om_a3_task_create(const OmA3TaskDesc* d, OmA3Task** out) {
@@ -440,8 +442,7 @@ static int a3_step_impl(const OmModel* m, const OmA3Task* task, const float* qpo
     const size_t int_b = ((size_t)(2 + (A3_MAX_CAND + 1) * 4) * ld * sizeof(int32_t) + 15) / 16 * 16;   // byte arrays 16-B aligned
     const int tp_max = (n_steps + 15) / 16 * 16;
     const size_t byte_b = (size_t)tp_max * (size_t)ld;
-    const size_t fix_b = ((size_t)(n_steps < a3_max_steps_per_call(task->C.delay_frames) ? n_steps : a3_max_steps_per_call(task->C.delay_frames)) * (size_t)n + 4) * sizeof(uint32_t);
-    const size_t need = feat_b + int_b + 2 * byte_b + 16 + fix_b;
+    const size_t need = feat_b + int_b + 2 * byte_b;
     OM_REQUIRE(env_blocks <= 65535, "om_a3_task_step: at most %d envs per multi-step call", 65535 * FB);
     if (task->scratch_bytes < need) {
       if (task->scratch) OM_CUDA_OK(cudaFree(task->scratch));  // synchronises: no earlier call still reads it
@@ -449,18 +450,10 @@ static int a3_step_impl(const OmModel* m, const OmA3Task* task, const float* qpo
       task->scratch_bytes = 0;
       OM_CUDA_OK(cudaMalloc(&task->scratch, need));
       task->scratch_bytes = need;
-      task->fix_count_at = nullptr;
     }
     char* base = (char*)task->scratch;
-    char* fix_base = base + ((feat_b + int_b + 2 * byte_b + 15) / 16) * 16;
     A3Scratch w{(float*)base, (uint8_t*)(base + feat_b + int_b), (uint8_t*)(base + feat_b + int_b + byte_b), 0,
-                (int32_t*)(base + feat_b), (float*)(base + feat_b) + 2 * (size_t)ld, (uint32_t*)fix_base, (uint32_t*)fix_base + 4};
-    if (task->fix_count_at != (void*)w.fix_count) {          // the work-list counter starts at zero; a3_post_kernel re-zeroes it
-      OM_CUDA_OK(cudaMemsetAsync(w.fix_count, 0, 16, st));
-      task->fix_count_at = (void*)w.fix_count;
-    }
-    OM_REQUIRE((unsigned long long)a3_max_steps_per_call(task->C.delay_frames) * (unsigned long long)n < 0xffffffffull,
-               "om_a3_task_step: too many envs for one multi-step call");
+                (int32_t*)(base + feat_b), (float*)(base + feat_b) + 2 * (size_t)ld};
     // sub-calls no longer than the candidate bits cover (210 steps with the reference's 30 delay frames)
     const int max_call = a3_max_steps_per_call(task->C.delay_frames);
     for (int c0 = 0; c0 < n_steps; c0 += max_call) {
@@ -479,9 +472,7 @@ static int a3_step_impl(const OmModel* m, const OmA3Task* task, const float* qpo
       else if (g_knobs.a3_feat_minb == 4) a3_feat_kernel<FB, 4><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
       else a3_feat_kernel<FB, 5><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
       OM_LAUNCHED();
-      a3_fix_kernel<<<64, 64, 0, st>>>(sub, w, ncand);             // float64 re-decisions of the noted env-steps (usually ~1e-4 of them)
-      OM_LAUNCHED();
-      a3_walk_kernel<<<ceil_div(n, 64), 64, 0, st>>>(sub, w);
+      a3_walk_kernel<<<ceil_div(n, 64), 64, 0, st>>>(sub, w, ncand);
       OM_LAUNCHED();
       a3_post_kernel<FB><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w);
       OM_LAUNCHED();

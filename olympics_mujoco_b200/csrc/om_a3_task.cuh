@@ -123,7 +123,7 @@ OM_NOINLINE A3SitesF64 a3_sites_f64(const float* q, size_t ld) {
 }
 // Where the slow path finds the env-step's qpos -- or, with `defer` (the (env, t)-parallel replay kernel, whose hot
 // path must stay free of an out-of-line call and of its register saves), only a note that this env-step needs one: the
-// fp32 decision is returned for now and a3_fix_kernel re-takes it in float64 from the work list.
+// fp32 decision is returned for now, the env-step's byte is flagged and the sequential pass re-takes it in float64.
 struct A3Exact {
   const float* q;
   size_t ld;
@@ -404,7 +404,7 @@ OM_HD A3TargetTrig a3_target_trig(const A3Targets& tc) {
 // t2_0, candidate j = min(t2_0 + j - 1, len - 1); t2 is always the next candidate.  The (env, t)-parallel pass
 // therefore evaluates "a foot is within target_radius of candidate j" for the first few candidates (one bit each),
 // and the recurrence shrinks to integer work on those bits: no geometry on the sequential path.
-constexpr int A3_MAX_CAND = 8;
+constexpr int A3_MAX_CAND = 7;     // candidate bits 0..6 of the per-step byte; bit 7 flags a decision to re-take in float64
 OM_HD int a3_cand(int j, int t1_0, int t2_0, int seq_len) {
   if (j == 0) return t1_0;
   const int k = t2_0 + j - 1;

@@ -133,14 +133,23 @@ class VDBLoss(GailDiscriminatorLoss):
         return loss, grad / stats["n"], stats
 
 
-def _fit_batch(self, plcy_state, expert, loss, eps=None, noisy_targets=False):
+def _fit_batch(self, plcy_state, expert, loss, eps=None, noisy_targets=False, logging_forwards=False):
     """One epoch of ``GAIL._fit_discriminator`` up to (not including) the weight update: sample the expert half, fold
-    [policy; expert] into the standardiser (``gail_TRPO.py:200-201``), forward, loss + statistics.
-    -> (loss value, stats, batch dict with ``inputs`` [32, 2n], ``logit``, ``kl``, ``dlogit``, ``target``)."""
+    [policy; expert] into the standardiser, forward, loss + statistics.
+    -> (loss value, stats, batch dict with ``inputs`` [32, 2n], ``logit``, ``kl``, ``dlogit``, ``target``).
+
+    Standardiser bookkeeping, as the reference does it: the discriminator's input standardiser and ``_D_standardizer``
+    are ONE object (``examples/imitation_learning/utils.py``), and it updates on EVERY forward (``networks.py:66-71``).
+    One fit epoch therefore folds the [policy; expert] batch in TWICE before the batch is standardised -- the explicit
+    ``update_mean_std`` (``gail_TRPO.py:200-201``) and the forward inside ``D.fit`` -- and, when a summary writer is
+    attached, ``_discriminator_logging`` (:222-258) runs six more forwards afterwards (two on the full batch, two on
+    each half: four batch-equivalents).  The same counts are replayed here (``logging_forwards`` = a writer is attached);
+    the moment sums of a batch are computed once and added with the multiplicity."""
     n = plcy_state.shape[-1]
     demo, _, _ = expert.sample(n)
     inputs = torch.cat([plcy_state, demo], dim=1)
-    self.standardizer.update(inputs)
+    batch_moments = Kn.moments(inputs)
+    self.standardizer.update_from_moments(2.0 * batch_moments)
     mean, std = self.standardizer.snapshot_f32()
     if self.kind == "vail" and eps is None:
         eps = torch.randn((self.disc.z, 2 * n), device=inputs.device, generator=self._gen)
@@ -150,6 +159,8 @@ def _fit_batch(self, plcy_state, expert, loss, eps=None, noisy_targets=False):
         u = torch.rand(2 * n, device=inputs.device, generator=self._gen)
         target = torch.cat([0.01 + 0.09 * u[:n], 0.80 + 0.19 * u[n:]])
     value, dlogit, stats = loss(fw["logit"], n, target=target, kl=fw.get("kl"))
+    if logging_forwards:
+        self.standardizer.update_from_moments(4.0 * batch_moments)
     return value, stats, dict(inputs=inputs, target=target, dlogit=dlogit, eps=eps, **fw)
 
 

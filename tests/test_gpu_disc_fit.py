@@ -129,8 +129,11 @@ def test_fit_batch_end_to_end_vs_oracle():
     idx = L.expert_indices(4, 0, n, 500)
     inputs = np.concatenate([plcy, expert_states[idx]])
     assert np.array_equal(batch["inputs"].cpu().numpy().T, inputs)
+    # the reference folds the batch in TWICE before it is standardised: the explicit update_mean_std (gail_TRPO.py:200-201)
+    # and the forward inside D.fit (networks.py:66-71) -- one Standardizer object serves both
     sd = L.Standardizer()
     sd.update_mean_std(inputs)
+    sd.forward(inputs)
     mean32, std32 = sd.mean.astype(np.float32).astype(np.float64), sd.std.astype(np.float32).astype(np.float64)
     d64, mu, lv = L.vail_forward({k: v.astype(np.float64) for k, v in p.items()}, inputs, eps, mean32, std32)
     assert_close(batch["logit"].cpu().numpy(), d64, "logit")
@@ -139,3 +142,23 @@ def test_fit_batch_end_to_end_vs_oracle():
     assert abs(value - want) < 1e-5 * abs(want) and abs(vl.beta - beta) < 1e-9
     sig = 1 / (1 + np.exp(-d64))
     assert_close(batch["dlogit"].cpu().numpy(), (sig - t) / (2 * n), "bce gradient", rtol=1e-4, atol=1e-8)
+    # running sums after one fit epoch (with the logging forwards of an attached summary writer) plus one reward call,
+    # against the reference Standardizer restatement replaying the reference's call sequence
+    dr2 = DiscriminatorReward("vail", p, seed=0)
+    ex2 = ExpertDataset(ds, seed=4)
+    dr2.fit_batch(_t(plcy.T), ex2, VDBLoss(0.5, 1e-5), eps=_t(eps.T), logging_forwards=True)
+    reward_states = g["s"][40:168]
+    dr2.make_discrim_reward(_t(reward_states.T), eps=_t(eps[:128].T))
+    torch.cuda.synchronize()
+    sd2 = L.Standardizer()
+    sd2.update_mean_std(inputs)                      # gail_TRPO.py:200-201
+    sd2.forward(inputs)                              # D.fit
+    for x in (inputs, inputs[n:], inputs[:n], inputs, inputs[n:], inputs[:n]):
+        sd2.forward(x)                               # _discriminator_logging :222-258 (full, demo, policy, full, demo, policy)
+    sd2.forward(reward_states)                       # make_discrim_reward :320-327
+    run = dr2.standardizer.running.cpu().numpy()
+    assert_close(run[:32], sd2._sum, "running sum", rtol=1e-12, atol=1e-9)
+    assert_close(run[32:64], sd2._sumsq, "running sum of squares", rtol=1e-12, atol=1e-9)
+    assert abs(run[64] - float(sd2._count[0])) < 1e-9
+    assert_close(dr2.standardizer.mean.cpu().numpy(), sd2.mean, "mean", rtol=1e-12, atol=1e-12)
+    assert_close(dr2.standardizer.std.cpu().numpy(), sd2.std, "std", rtol=1e-12, atol=1e-12)
