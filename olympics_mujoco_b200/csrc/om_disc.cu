@@ -854,6 +854,255 @@ __global__ void __launch_bounds__(192, 2) disc_vail2_kernel(DiscArgs a) {
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+
+// ---------------------------------------------------------------- VAIL, two CTAs per SM, A operand in TENSOR MEMORY
+// Why: with both operands in shared memory (the kernels above) a 3xTF32 k-step of 8 moves 12 KB of A reads + 12 KB of B
+// reads through the SM's 128 B/clk shared-memory port in the 192 cycles its three M128 x N128 MMAs take, plus the 8 KB
+// the producers store for the next A chunk and the 8 KB the bulk copy writes for the next B chunk: 213 B/clk wanted, 128
+// available -- both SS kernels run at ~1.65x their tensor-pipe floor, whatever the producers do (measured: dropping the
+// A stores buys 12 %, dropping the producers' loads and arithmetic 8 %).  Here the activations never touch shared memory:
+// the epilogue of layer l writes the hi / lo A chunks of layer l + 1 straight into TMEM (tcgen05.st: thread t owns lane t
+// = sample t, exactly the layout the MMA wants for an M = 128 A operand) and the MMA reads them from there
+// (tcgen05.mma [d], [a_tmem], b_desc).  Shared memory then carries the weights only: 107 B/clk.
+// TMEM budget of a CTA (256 columns, two CTAs per SM): ACC1 = 64 (a 64-wide block of layer 1, later of [mu; logvar]),
+// ACC2 = 128 (layer 2), A ring = 2 stages x (16 hi + 16 lo) columns.  Hence 64-wide blocks: layer 1 in four blocks each
+// feeding four K-chunks of layer 2; the [mu; logvar] layer in four blocks of 32 + 32 interleaved rows (host side), the head
+// consuming 32 latent dimensions per block.  56 chunks of 16 K-elements per tile.
+// MEASURED (B200, round 2): parity-green, but 82.0 us at 65536 samples and 975 us at 1 M against 74.2 / 815 us for
+// disc_vail2_kernel.  The TMEM budget forces 16-element chunks, a two-stage A ring and nine accumulator drains per tile
+// (vail2: five); each chunk costs a tcgen05.ld -> split -> tcgen05.st -> wait::st -> mbarrier -> MMA -> commit round
+// trip of ~1200 cycles against 192-384 cycles of MMA, so the kernel is handshake-latency-bound although its
+// shared-memory traffic is half.  Kept selectable (om_debug_set "disc_vail2" = 3) and under test; NOT the default.
+// What would make it pay: one CTA per SM with all 512 columns (128-wide blocks, a four-stage ring of 32-element chunks).
+constexpr int V3_KC = 16, V3_NSB = 4, V3_NSA = 2;
+constexpr int V3_STAGE_B = 128 * V3_KC * 4 * 2;          // 16 KB: the largest B chunk (128 rows, hi + lo)
+constexpr int V3_ACC1 = 0, V3_ACC2 = 64, V3_AR = 192;
+constexpr int V3_NPAR = 256 + 128 + 256 + 128 + 1;       // b1, b2, b3 (interleaved like the rows), wd, bd
+constexpr int V3_CHUNKS = 4 * (2 + 4) + 4 * 8;           // 56
+__host__ __device__ constexpr int v3_rows(int c) { return c < 24 ? ((c % 6) < 2 ? 64 : 128) : 64; }
+__host__ __device__ constexpr int v3_offset_bytes(int c) {          // start of chunk c in the image
+  int o = 0;
+  for (int i = 0; i < c; ++i) o += v3_rows(i) * V3_KC * 4 * 2;
+  return o;
+}
+constexpr int V3_IMAGE_BYTES = v3_offset_bytes(V3_CHUNKS);
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+// 16 consecutive TMEM columns of this thread's lane <- registers
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+                 "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+                 "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+                 "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <bool KL>
+__global__ void __launch_bounds__(192, 2) disc_vail3_kernel(DiscArgs a) {
+  constexpr int Z = 128;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ring = smem;
+  float* par = reinterpret_cast<float*>(smem + V3_NSB * V3_STAGE_B);
+  float* s_mean = par + V3_NPAR + 3;
+  float* s_inv = s_mean + DISC_IN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_inv + DISC_IN);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * V3_NSA + 2 * V3_NSB);
+  const float* b1 = par;
+  const float* b2 = par + 256;
+  const float* b3 = par + 384;            // per 64-row block h: [bmu[32h..32h+31], blv[32h..32h+31]]
+  const float* wd = par + 640;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s_) { return bar0 + 8u * s_; };
+  auto a_free = [&](int s_) { return bar0 + 8u * (V3_NSA + s_); };
+  auto b_full = [&](int s_) { return bar0 + 8u * (2 * V3_NSA + s_); };
+  auto b_free = [&](int s_) { return bar0 + 8u * (2 * V3_NSA + V3_NSB + s_); };
+
+  for (int i = tid; i < V3_NPAR; i += 192) par[i] = a.params[i];
+  if (tid < DISC_IN) { s_mean[tid] = a.mean[tid]; s_inv[tid] = 1.0f / a.stdv[tid]; }
+  if (tid == 0) {
+    for (int s_ = 0; s_ < V3_NSA; ++s_) { mbar_init(a_full(s_), 128); mbar_init(a_free(s_), 1); }
+    for (int s_ = 0; s_ < V3_NSB; ++s_) { mbar_init(b_full(s_), 1); mbar_init(b_free(s_), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int ntiles = (a.n + TILE - 1) / TILE;
+  int my_tiles = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) ++my_tiles;
+  const int total_chunks = my_tiles * V3_CHUNKS;
+
+  if (warp == 5) {
+    // ===================================================== weight-copy issuer: the image repeats every tile
+    if (tid == 160) {
+      int c = 0, off = 0;
+      for (int g = 0; g < total_chunks; ++g) {
+        const int st = g % V3_NSB, use = g / V3_NSB;
+        const int bytes = v3_rows(c) * V3_KC * 4 * 2;
+        if (use > 0) mbar_wait(b_free(st), (uint32_t)(use - 1) & 1u);
+        mbar_expect_tx(b_full(st), bytes);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.image) + off;
+        const uint32_t dst = smem_u32(ring + st * V3_STAGE_B);
+        bulk_g2s(dst, src, bytes / 2, b_full(st));
+        bulk_g2s(dst + bytes / 2, src + bytes / 2, bytes / 2, b_full(st));
+        off += bytes;
+        if (++c == V3_CHUNKS) { c = 0; off = 0; }
+      }
+    }
+  } else if (warp == 4) {
+    // ===================================================== MMA issuer
+    if (tid == 128) {
+      int c = 0;
+      for (int g = 0; g < total_chunks; ++g) {
+        const int sa = g % V3_NSA, sb = g % V3_NSB;
+        const int rows = v3_rows(c);
+        uint32_t d_col;
+        bool first;
+        if (c < 24) {
+          const int r = c % 6;                                   // 0,1: layer 1 of this block; 2..5: layer 2
+          d_col = r < 2 ? V3_ACC1 : V3_ACC2;
+          first = r < 2 ? (r == 0) : (c == 2);                   // layer 2 accumulates over the four blocks
+        } else {
+          d_col = V3_ACC1;
+          first = ((c - 24) % 8) == 0;
+        }
+        const uint32_t idesc = idesc_tf32(TILE, rows);
+        const uint32_t lbo = (uint32_t)rows * 16, sbo = 128;
+        mbar_wait(a_full(sa), (uint32_t)(g / V3_NSA) & 1u);
+        mbar_wait(b_full(sb), (uint32_t)(g / V3_NSB) & 1u);
+        tc_fence_after();
+        const uint32_t a_hi = tmem + V3_AR + sa * 32, a_lo = a_hi + 16;
+        const uint32_t b_hi = smem_u32(ring + sb * V3_STAGE_B), b_lo = b_hi + rows * V3_KC * 4;
+#pragma unroll
+        for (int j = 0; j < V3_KC / 8; ++j) {
+          const uint32_t o = (uint32_t)j * 2 * lbo;
+          const uint64_t dbh = smem_desc(b_hi + o, lbo, sbo), dbl = smem_desc(b_lo + o, lbo, sbo);
+          umma_tf32_ts(tmem + d_col, a_lo + 8 * j, dbh, idesc, (first && j == 0) ? 0u : 1u);
+          umma_tf32_ts(tmem + d_col, a_hi + 8 * j, dbl, idesc, 1u);
+          umma_tf32_ts(tmem + d_col, a_hi + 8 * j, dbh, idesc, 1u);
+        }
+        umma_commit(a_free(sa));
+        umma_commit(b_free(sb));
+        if (++c == V3_CHUNKS) c = 0;
+      }
+    }
+  } else {
+    // ===================================================== producers / epilogue (128 threads; thread t = TMEM lane t)
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const float bd = par[V3_NPAR - 1];
+    int g = 0;
+    auto wait_chunk = [&](int h) {                         // all MMAs up to and including chunk h are complete
+      if (h >= 0) {
+        mbar_wait(a_free(h % V3_NSA), (uint32_t)(h / V3_NSA) & 1u);
+        tc_fence_after();
+      }
+    };
+    auto put = [&](const float (&act_in)[16]) {
+      float hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { hi[i] = tf32_rna(act_in[i]); lo[i] = act_in[i] - hi[i]; }
+      wait_chunk(g - V3_NSA);                              // the MMAs that read this A stage last are complete
+      const uint32_t at = lane_addr + V3_AR + (g % V3_NSA) * 32;
+      tmem_st16(at, hi);
+      tmem_st16(at + 16, lo);
+      tmem_wait_st();
+      tc_fence_before();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_full(g % V3_NSA)) : "memory");
+      ++g;
+    };
+    auto load_row = [&](int tile_, float (&raw)[DISC_IN]) {
+      const int env_ = tile_ * TILE + tid;
+#pragma unroll
+      for (int k = 0; k < DISC_IN; ++k) raw[k] = (tile_ < ntiles && env_ < a.n) ? a.s[(size_t)k * a.ld + env_] : 0.f;
+    };
+    float xn[DISC_IN];
+    load_row(blockIdx.x, xn);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int env = tile * TILE + tid;
+      const bool live = env < a.n;
+      float x[DISC_IN];
+#pragma unroll
+      for (int k = 0; k < DISC_IN; ++k) x[k] = live ? (xn[k] - s_mean[k]) * s_inv[k] : 0.f;
+      load_row(tile + gridDim.x, xn);
+#pragma unroll 1
+      for (int blk = 0; blk < 4; ++blk) {
+        {
+          float h0[16], h1[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { h0[i] = x[i]; h1[i] = x[16 + i]; }
+          put(h0);
+          put(h1);
+        }
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          if (c == 0) wait_chunk(g - 1);                                  // this layer-1 block is complete
+          float h[16];
+          tmem_ld16(lane_addr + V3_ACC1 + c * V3_KC, h);
+          bias_relu16(h, b1 + blk * 64 + c * V3_KC);
+          put(h);
+        }
+      }
+      float dval = 0.f, klv = 0.f;
+#pragma unroll 1
+      for (int hb = 0; hb < 4; ++hb) {
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          if (c == 0 && hb == 0) wait_chunk(g - 1);                       // layer 2 complete
+          float h[16];
+          tmem_ld16(lane_addr + V3_ACC2 + c * V3_KC, h);
+          bias_relu16(h, b2 + c * V3_KC);
+          put(h);
+        }
+        // head over latent dimensions 32 hb .. 32 hb + 31: z = mu + exp(logvar / 2) eps, d += wd . z
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) e[i] = (a.eps && live) ? a.eps[(size_t)(32 * hb + i) * a.ld + env] : 0.f;
+        wait_chunk(g - 1);
+        float mu[32], lv[32];
+        tmem_ld32(lane_addr + V3_ACC1, mu);
+        tmem_ld32(lane_addr + V3_ACC1 + 32, lv);
+        const float4* bm4 = reinterpret_cast<const float4*>(b3 + 64 * hb);
+        const float4* bl4 = reinterpret_cast<const float4*>(b3 + 64 * hb + 32);
+        const float4* wv4 = reinterpret_cast<const float4*>(wd + 32 * hb);
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 bm_ = bm4[i4], bl_ = bl4[i4], wv_ = wv4[i4];
+          const float bmv[4] = {bm_.x, bm_.y, bm_.z, bm_.w}, blv[4] = {bl_.x, bl_.y, bl_.z, bl_.w};
+          const float wvv[4] = {wv_.x, wv_.y, wv_.z, wv_.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = 4 * i4 + k;
+            const float m = mu[i] + bmv[k], l = lv[i] + blv[k];
+            const float sd = expf(0.5f * l);
+            dval = fmaf(wvv[k], fmaf(sd, e[i], m), dval);
+            if (KL) klv += fmaf(m, m, fmaf(sd, sd, -l)) - 1.f;       // VDBLoss.kl_divergence, math.py:83-86
+          }
+        }
+      }
+      dval += bd;
+      if (live) {
+        const float one_minus_p = 1.f / (1.f + expf(dval));
+        if (a.reward) a.reward[env] = -logf(one_minus_p + 1e-8f);
+        if (a.d_out) a.d_out[env] = dval;
+        if (KL) a.kl_out[env] = 0.5f * klv;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 }  // namespace om
 
 using namespace om;
@@ -864,6 +1113,8 @@ struct OmDisc {
   float* params = nullptr;
   float* image2 = nullptr;      // VAIL: chunk image / parameters of disc_vail2_kernel
   float* params2 = nullptr;
+  float* image3 = nullptr;      // VAIL: chunk image / parameters of disc_vail3_kernel (A operand in TMEM)
+  float* params3 = nullptr;
 };
 
 static void split_tf32(float x, float* hi, float* lo) {
@@ -954,6 +1205,42 @@ extern "C" int om_disc_create(const OmDiscDesc* d, OmDisc** out) {
     par2.insert(par2.end(), d->wd, d->wd + z);
     par2.push_back(d->bd[0]);
   }
+  // ---- VAIL with the A operand in TMEM (disc_vail3_kernel): 64-row blocks of layer 1 and of [mu; logvar] (rows
+  //      interleaved per 32), 128-row chunks of layer 2, all 16 columns wide, in the kernel's issue order
+  std::vector<float> img3, par3;
+  if (vail) {
+    std::vector<float> w3i((size_t)2 * z * n2), b3i(2 * z);
+    for (int hb = 0; hb < 4; ++hb)
+      for (int r = 0; r < 32; ++r) {
+        std::memcpy(&w3i[(size_t)(64 * hb + r) * n2], d->wmu + (size_t)(32 * hb + r) * n2, sizeof(float) * n2);
+        std::memcpy(&w3i[(size_t)(64 * hb + 32 + r) * n2], d->wlv + (size_t)(32 * hb + r) * n2, sizeof(float) * n2);
+        b3i[64 * hb + r] = d->bmu[32 * hb + r];
+        b3i[64 * hb + 32 + r] = d->blv[32 * hb + r];
+      }
+    auto chunk = [&](const float* w, int ldw, int r0, int rows, int k0) {       // rows x 16 columns: hi image, lo image
+      const size_t base = img3.size();
+      img3.resize(base + (size_t)rows * V3_KC * 2);
+      float* hi = img3.data() + base;
+      float* lo = hi + (size_t)rows * V3_KC;
+      for (int kc = 0; kc < V3_KC / 4; ++kc)
+        for (int r = 0; r < rows; ++r)
+          for (int e = 0; e < 4; ++e)
+            split_tf32(w[(size_t)(r0 + r) * ldw + k0 + kc * 4 + e], hi + ((size_t)kc * rows + r) * 4 + e,
+                       lo + ((size_t)kc * rows + r) * 4 + e);
+    };
+    for (int blk = 0; blk < 4; ++blk) {
+      for (int c = 0; c < 2; ++c) chunk(d->w1, DISC_IN, 64 * blk, 64, 16 * c);
+      for (int c = 0; c < 4; ++c) chunk(d->w2, n1, 0, 128, 64 * blk + 16 * c);
+    }
+    for (int hb = 0; hb < 4; ++hb)
+      for (int c = 0; c < 8; ++c) chunk(w3i.data(), n2, 64 * hb, 64, 16 * c);
+    if (img3.size() * sizeof(float) != (size_t)V3_IMAGE_BYTES) return fail("om_disc_create: internal image size mismatch");
+    par3.insert(par3.end(), d->b1, d->b1 + n1);
+    par3.insert(par3.end(), d->b2, d->b2 + n2);
+    par3.insert(par3.end(), b3i.begin(), b3i.end());
+    par3.insert(par3.end(), d->wd, d->wd + z);
+    par3.push_back(d->bd[0]);
+  }
   OmDisc* h = new OmDisc();
   h->sh = DiscShape{d->kind, n1, n2, z};
   cudaError_t e = cudaMalloc(&h->image, img.size() * sizeof(float));
@@ -965,12 +1252,18 @@ extern "C" int om_disc_create(const OmDiscDesc* d, OmDisc** out) {
     if (e == cudaSuccess) e = cudaMalloc(&h->params2, par2.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(h->image2, img2.data(), img2.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->params2, par2.data(), par2.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&h->image3, img3.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&h->params3, par3.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(h->image3, img3.data(), img3.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->params3, par3.data(), par3.size() * sizeof(float), cudaMemcpyHostToDevice);
   }
   if (e != cudaSuccess) {
     if (h->image) cudaFree(h->image);
     if (h->params) cudaFree(h->params);
     if (h->image2) cudaFree(h->image2);
     if (h->params2) cudaFree(h->params2);
+    if (h->image3) cudaFree(h->image3);
+    if (h->params3) cudaFree(h->params3);
     delete h;
     return fail("om_disc_create: device upload failed: %s (no CPU path)", cudaGetErrorString(e));
   }
@@ -984,6 +1277,8 @@ extern "C" void om_disc_destroy(OmDisc* h) {
   cudaFree(h->params);
   if (h->image2) cudaFree(h->image2);
   if (h->params2) cudaFree(h->params2);
+  if (h->image3) cudaFree(h->image3);
+  if (h->params3) cudaFree(h->params3);
   delete h;
 }
 
@@ -1013,6 +1308,18 @@ extern "C" int om_disc_forward(const OmDisc* h, const float* s, const float* mea
   // kernel reads 76-78 us in both settings, so it stays the default.)
   int two = h->sh.kind == 0;
   if (g_knobs.disc_vail2 >= 0) two = h->sh.kind == 0 && g_knobs.disc_vail2 != 0;           // tuning / test hook: force either
+  if (h->sh.kind == 0 && g_knobs.disc_vail2 == 3) {            // A operand in TMEM (opt-in: measured slower, see the kernel)
+    const size_t smem3 = V3_NSB * V3_STAGE_B + (V3_NPAR + 3 + 2 * DISC_IN) * sizeof(float) + (2 * V3_NSA + 2 * V3_NSB) * 8 + 16;
+    const int grid3 = ntiles < 2 * sms ? ntiles : 2 * sms;
+    DiscArgs a3 = a;
+    a3.image = h->image3;
+    a3.params = h->params3;
+    auto kern = kl_out ? disc_vail3_kernel<true> : disc_vail3_kernel<false>;
+    OM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    kern<<<grid3, 192, smem3, st>>>(a3);
+    OM_LAUNCHED();
+    return 0;
+  }
   if (two) {
     const size_t smem2 = V2_NS * V2_STAGE_BYTES + (V2_NPAR + 3 + 2 * DISC_IN) * sizeof(float) + 3 * V2_NS * 8 + 16;
     const int grid2 = ntiles < 2 * sms ? ntiles : 2 * sms;
