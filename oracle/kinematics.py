@@ -11,8 +11,10 @@ Conventions (MuJoCo): quaternions ``[w,x,y,z]``; ``xmat`` row-major; spatial vec
 
 All functions are batched over a leading env axis ``N`` and loop in Python only over bodies/joints,
 in the engine's order, so a single env (``N=1``) follows the engine statement by statement.
-PARITY UNPINNED by the reference (it has no FK fixtures); see ``tests/test_oracle_fk.py`` for the
-analytic checks that pin it instead.
+PARITY UNPINNED by the reference (it has no FK fixtures, and MuJoCo cannot be installed here).  Pinned instead by an
+independent second checker that shares no code with this file (``tools/fk_independent.py``: own MJCF reader, 4x4
+homogeneous transforms, numerically differentiated velocities; ``tests/test_fk_independent.py``) and by the analytic
+known answers of ``tests/test_oracle_fk.py``.
 """
 from __future__ import annotations
 

@@ -5,7 +5,8 @@
 not installed here.  These are restatements of its published algorithms for the default axes
 ``'sxyz'`` (static frame, x-y-z order): ``quaternions.quat2mat``, ``euler.mat2euler``,
 ``euler.quat2euler``, ``euler.euler2quat``, ``euler.euler2mat(0,0,yaw)``, ``quaternions.mat2quat``.
-PARITY UNPINNED by the reference; checked by round-trip properties in ``tests/test_oracle_tf3.py``.
+Unpinned by the reference; pinned against SciPy's ``Rotation`` (an independent implementation of the same
+conventions) in ``tests/test_oracle_third_party_pins.py``, plus round-trip properties.
 """
 import numpy as np
 
