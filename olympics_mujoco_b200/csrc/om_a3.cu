@@ -271,12 +271,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) a3_feat_kernel(A3Args a, A3Scratc
 }
 
 __global__ void __launch_bounds__(64) a3_walk_kernel(A3Args a, A3Scratch w, int ncand) {
+  pdl_wait();
   const int env = blockIdx.x * 64 + threadIdx.x;
   if (env < a.n) a3_walk(a, w, ncand, env);
 }
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) a3_post_kernel(A3Args a, A3Scratch w) {
+  pdl_wait();
   const int env = blockIdx.x * BLOCK + threadIdx.x;
   const int t = blockIdx.y;
   if (env >= a.n) return;
@@ -472,9 +474,9 @@ static int a3_step_impl(const OmModel* m, const OmA3Task* task, const float* qpo
       else if (g_knobs.a3_feat_minb == 4) a3_feat_kernel<FB, 4><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
       else a3_feat_kernel<FB, 5><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
       OM_LAUNCHED();
-      a3_walk_kernel<<<ceil_div(n, 64), 64, 0, st>>>(sub, w, ncand);
+      OM_CUDA_OK(launch_pdl(a3_walk_kernel, dim3(ceil_div(n, 64)), dim3(64), 0, st, sub, w, ncand));
       OM_LAUNCHED();
-      a3_post_kernel<FB><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w);
+      OM_CUDA_OK(launch_pdl(a3_post_kernel<FB>, dim3(env_blocks, len), dim3(FB), 0, st, sub, w));
       OM_LAUNCHED();
     }
     if (rets)                                     // the returns scan over the rewards just written (same stream, same call)

@@ -54,6 +54,25 @@ extern Knobs g_knobs;
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch: a chain of small kernels on one stream (snapshot -> playback -> scan -> moments -> stats ->
+// normalise; feat -> walk -> post -> scan) pays a launch-and-drain gap at every boundary.  Launched with this attribute a
+// kernel's CTAs are scheduled while its predecessor drains; the kernel itself calls pdl_wait() (griddepcontrol.wait) before it
+// touches anything the predecessor wrote, which blocks until the predecessor has completed and flushed -- whatever kernel
+// that was (ours or the caller's).  No early trigger is used, so nothing else about the ordering changes.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 // ---------------------------------------------------------------- device tables of a model
 constexpr int MAXB = OM_MAX_BODY;
 constexpr int MAXJ = OM_MAX_JNT;

@@ -107,6 +107,7 @@ template <int L>
 __global__ void __launch_bounds__(1024) affine_scan_kernel(AffineIn in, int T, int n, int ld, float* __restrict__ out0,
                                                            float* __restrict__ out1) {
   __shared__ float sA[32][33], sB[32][33];
+  pdl_wait();
   const int lane = threadIdx.x, w = threadIdx.y;
   const int env = blockIdx.x * 32 + lane;
   const bool live = env < n;
@@ -186,12 +187,12 @@ static int launch_affine_scan(const AffineIn& in, int T, int n, int ld, float* o
   const int L = ceil_div(T, 32) > l8 ? ceil_div(T, 32) : l8;
   const int Lp = L <= 1 ? 1 : L <= 2 ? 2 : L <= 4 ? 4 : L <= 8 ? 8 : L <= 16 ? 16 : 32;
   dim3 block(32, ceil_div(T, Lp)), grid(ceil_div(n, 32));
-  if (L <= 1) affine_scan_kernel<1><<<grid, block, 0, st>>>(in, T, n, ld, o0, o1);
-  else if (L <= 2) affine_scan_kernel<2><<<grid, block, 0, st>>>(in, T, n, ld, o0, o1);
-  else if (L <= 4) affine_scan_kernel<4><<<grid, block, 0, st>>>(in, T, n, ld, o0, o1);
-  else if (L <= 8) affine_scan_kernel<8><<<grid, block, 0, st>>>(in, T, n, ld, o0, o1);
-  else if (L <= 16) affine_scan_kernel<16><<<grid, block, 0, st>>>(in, T, n, ld, o0, o1);
-  else affine_scan_kernel<32><<<grid, block, 0, st>>>(in, T, n, ld, o0, o1);
+  if (L <= 1) launch_pdl(affine_scan_kernel<1>, grid, block, 0, st, in, T, n, ld, o0, o1);
+  else if (L <= 2) launch_pdl(affine_scan_kernel<2>, grid, block, 0, st, in, T, n, ld, o0, o1);
+  else if (L <= 4) launch_pdl(affine_scan_kernel<4>, grid, block, 0, st, in, T, n, ld, o0, o1);
+  else if (L <= 8) launch_pdl(affine_scan_kernel<8>, grid, block, 0, st, in, T, n, ld, o0, o1);
+  else if (L <= 16) launch_pdl(affine_scan_kernel<16>, grid, block, 0, st, in, T, n, ld, o0, o1);
+  else launch_pdl(affine_scan_kernel<32>, grid, block, 0, st, in, T, n, ld, o0, o1);
   return 0;
 }
 
@@ -202,6 +203,7 @@ static int launch_affine_scan(const AffineIn& in, int T, int n, int ld, float* o
 template <int VEC>
 __global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ x, int rows, int C, int n, int ld,
                                                       double* __restrict__ out) {
+  pdl_wait();
   const int c = blockIdx.y;
   double s = 0.0, s2 = 0.0;
   const int nv = n / VEC;
@@ -262,6 +264,7 @@ __global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ 
 
 // mean / (std + eps) of a single-component moment buffer [sum, sumsq, count] -> stats[0..1]
 __global__ void adv_stats_kernel(const double* __restrict__ mom, int unbiased, double eps, double* __restrict__ stats) {
+  pdl_wait();
   const double cnt = mom[2];
   const double mean = mom[0] / cnt;
   double var = mom[1] / cnt - mean * mean;
@@ -294,6 +297,7 @@ __global__ void __launch_bounds__(128) moment_stats_kernel(const double* __restr
 
 __global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict__ x, const double* __restrict__ stats,
                                                         int rows, int n, int ld, float* __restrict__ y) {
+  pdl_wait();
   const double mean = stats[0], inv = 1.0 / stats[1];
   const int r = blockIdx.y;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -505,15 +509,15 @@ extern "C" int om_moments(const float* x, int rows, int C, int n, int ld, double
   if (gz < 1) gz = 1;
   if (gz > 65535) gz = 65535;
   dim3 grid(gx, C, gz);
-  if (vec) moments_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, C, n, ld, out);
-  else moments_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, C, n, ld, out);
+  if (vec) OM_CUDA_OK(launch_pdl(moments_kernel<4>, grid, dim3(256), 0, (cudaStream_t)stream, x, rows, C, n, ld, out));
+  else OM_CUDA_OK(launch_pdl(moments_kernel<1>, grid, dim3(256), 0, (cudaStream_t)stream, x, rows, C, n, ld, out));
   OM_LAUNCHED();
   return 0;
 }
 
 extern "C" int om_adv_stats(const double* moments, int unbiased, double eps, double* stats, void* stream) {
   OM_REQUIRE(moments && stats, "om_adv_stats: null argument");
-  adv_stats_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(moments, unbiased, eps, stats);
+  OM_CUDA_OK(launch_pdl(adv_stats_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, moments, unbiased, eps, stats));
   OM_LAUNCHED();
   return 0;
 }
@@ -533,7 +537,7 @@ extern "C" int om_normalize(const float* x, const double* stats, int rows, int n
   int gx = ceil_div(n, 256);
   if (gx > 592) gx = 592;
   dim3 grid(gx, rows);
-  normalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, stats, rows, n, ld, y);
+  OM_CUDA_OK(launch_pdl(normalize_kernel, grid, dim3(256), 0, (cudaStream_t)stream, x, stats, rows, n, ld, y));
   OM_LAUNCHED();
   return 0;
 }

@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(256) play_snapshot_kernel(PlayArgs a, OmPlaySt
 // instead of 4096, which is what lets a 4096-env rollout fill the 148 SMs.
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) play_h1_tp_kernel(PlayArgs a, int chunk) {
+  pdl_wait();                                    // launched while the snapshot kernel drains
   const int env = blockIdx.x * BLOCK + threadIdx.x;
   if (env >= a.n) return;
   const int j0 = blockIdx.y * chunk, j1 = min(j0 + chunk, a.n_steps);
@@ -753,7 +754,7 @@ static int play_impl(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, ui
       OM_LAUNCHED();
       OM_CUDA_OK(cudaEventRecord(t->ev_join, t->side));
     }
-    play_h1_tp_kernel<BLOCK><<<grid, BLOCK, 0, st>>>(a, chunk);
+    OM_CUDA_OK(launch_pdl(play_h1_tp_kernel<BLOCK>, grid, dim3(BLOCK), 0, st, a, chunk));
     OM_LAUNCHED();
     if (mom) OM_CUDA_OK(cudaStreamWaitEvent(st, t->ev_join, 0));
     return 0;
