@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) a3_feat_kernel(A3Args a, A3Scratc
 }
 
 __global__ void __launch_bounds__(64) a3_walk_kernel(A3Args a, A3Scratch w, int ncand) {
+  pdl_trigger();                                 // 256 small CTAs: let the post pass's CTAs take the idle SMs now
   pdl_wait();
   const int env = blockIdx.x * 64 + threadIdx.x;
   if (env < a.n) a3_walk(a, w, ncand, env);

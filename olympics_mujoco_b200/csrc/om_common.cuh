@@ -71,6 +71,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Called at the START of a TINY kernel: its dependent's CTAs may become resident right away (the machine is otherwise idle)
+// and park in pdl_wait() until this kernel has completed -- the dependent's launch and ramp-up hide under this kernel.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 
 // ---------------------------------------------------------------- device tables of a model

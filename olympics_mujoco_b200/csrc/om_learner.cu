@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ 
 
 // mean / (std + eps) of a single-component moment buffer [sum, sumsq, count] -> stats[0..1]
 __global__ void adv_stats_kernel(const double* __restrict__ mom, int unbiased, double eps, double* __restrict__ stats) {
+  pdl_trigger();
   pdl_wait();
   const double cnt = mom[2];
   const double mean = mom[0] / cnt;

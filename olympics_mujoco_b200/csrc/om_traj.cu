@@ -307,6 +307,7 @@ __global__ void __launch_bounds__(256) play_start_reset_kernel(PlayArgs a) {
 
 template <bool RESET>
 __global__ void __launch_bounds__(256) play_snapshot_kernel(PlayArgs a, OmPlayState live, OmPlayState snap, int n, int ld) {
+  pdl_trigger();                                 // a few CTAs: the playback kernel's first wave may become resident now
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   if (RESET) {                                   // the call starts with reset(): the snapshot IS the reset state
@@ -492,6 +493,7 @@ struct LiveArgs {
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) h1_live_step_kernel(LiveArgs a) {
+  pdl_wait();                                    // consecutive live steps: this launch overlaps the previous step's drain
   const int env = blockIdx.x * BLOCK + threadIdx.x;
   if (env >= a.n) return;
   const size_t ld = a.ld, e = env;
@@ -795,7 +797,7 @@ extern "C" int om_h1_live_step(const OmModel* m, const OmH1Spec* spec, const OmT
   a.qpos = out->qpos; a.qvel = out->qvel; a.xpos = out->xpos; a.xquat = out->xquat; a.site_xpos = out->site_xpos;
   a.cvel = out->cvel; a.obs = out->obs; a.reward = out->reward; a.absorbing = out->absorbing; a.wrapped = out->wrapped;
   constexpr int BLOCK = 128;
-  h1_live_step_kernel<BLOCK><<<ceil_div(n, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(a);
+  OM_CUDA_OK(launch_pdl(h1_live_step_kernel<BLOCK>, dim3(ceil_div(n, BLOCK)), dim3(BLOCK), 0, (cudaStream_t)stream, a));
   OM_LAUNCHED();
   return 0;
 }
