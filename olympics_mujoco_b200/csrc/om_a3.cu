@@ -151,6 +151,17 @@ __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w
   if (phase >= a.C.period) phase -= a.C.period;                            // the modulo is warp-uniform, the wrap a select
   const int mode = a.ints[A3I_MODE * ld + e];
   const int t1_0 = a.ints[A3I_T1 * ld + e], t2_0 = a.ints[A3I_T2 * ld + e], seq_len = a.ints[A3I_SEQLEN * ld + e];
+  const int frames0 = a.ints[A3I_FRAMES * ld + e];
+  // The candidate targets' rows are a SECOND level of dependent loads (ints -> row index -> row), consumed only after the
+  // forward pass: ask for their lines now, without registers, so that they arrive under the FK arithmetic.
+  const int nc = a3_cand_needed(t, frames0, a.C.delay_frames, ncand);      // later targets are out of reach
+#pragma unroll 1
+  for (int j = 0; j < nc; ++j) {
+    const float* p = a.sequence + e + (unsigned)(a3_cand(j, t1_0, t2_0, seq_len) * 4) * lu;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(row(p, 1, lu)));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(row(p, 2, lu)));
+  }
   if (t == 0) {                                                            // start state of the call for the post pass
     w.start[e] = t1_0;
     w.start[ld + e] = t2_0;
@@ -173,7 +184,6 @@ __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w
   const A3Rec rec = a3_task_pre(a.C, a3_task_in(S.f), phase, mode, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, terms,
                                 obs[31], obs[32], done, ex);
   a3_rec_store(rec, w.feat + (size_t)t * A3_NREC * ld + e, lu);
-  const int nc = a3_cand_needed(t, a.ints[A3I_FRAMES * ld + e], a.C.delay_frames, ncand);   // later targets are out of reach
   const uint32_t bits = a3_near_bits(a.C, rec.lsite, rec.rsite, nc, t1_0, t2_0, seq_len, SeqGlobal{a.sequence + e, ld}, ex);
   // bit 7: a decision of this env-step (done, or one of the candidate bits) is within A3_BAND of its threshold; the
   // sequential pass re-takes it in float64 (a3_refix) before it consumes the byte -- about one env-step in 10^4
@@ -285,10 +295,21 @@ __global__ void __launch_bounds__(BLOCK) a3_post_kernel(A3Args a, A3Scratch w) {
   if (env >= a.n) return;
   const size_t ld = a.ld, e = env;
   const unsigned lu = (unsigned)a.ld;
-  const A3Rec rec = a3_rec_load(w.feat + (size_t)t * A3_NREC * ld + e, lu);
   const int code = w.code[e * w.tp + t];
   const int mode = a.ints[A3I_MODE * ld + e], seq_len = a.ints[A3I_SEQLEN * ld + e];
   const int t1_0 = w.start[e], t2_0 = w.start[ld + e];
+  // the two targets' rows depend on the state code (a second level of dependent loads): in most env-steps no target has
+  // been reached yet in this call, so ask for the rows of candidates 0 and 1 while the record is being loaded
+  {
+    const float* p0 = a.sequence + e + (unsigned)(t1_0 * 4) * lu;
+    const float* p1 = a.sequence + e + (unsigned)(a3_cand(1, t1_0, t2_0, seq_len) * 4) * lu;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(row(p0, c, lu)));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(row(p1, c, lu)));
+    }
+  }
+  const A3Rec rec = a3_rec_load(w.feat + (size_t)t * A3_NREC * ld + e, lu);
   const int j = code & 7;
   const float* tr = w.trig + e + (unsigned)(j * 4) * lu;               // candidate j, then candidate j + 1
   const A3TargetTrig tg{tr[0], *row(tr, 1, lu), *row(tr, 4, lu), *row(tr, 5, lu), *row(tr, 2, lu), *row(tr, 3, lu)};
