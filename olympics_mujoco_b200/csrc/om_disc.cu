@@ -1103,6 +1103,244 @@ __global__ void __launch_bounds__(192, 2) disc_vail3_kernel(DiscArgs a) {
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+
+// ---------------------------------------------------------------- VAIL, ONE CTA per SM, A operand in tensor memory
+// The answer to what held disc_vail3_kernel back: with all 512 TMEM columns a CTA affords 128-wide accumulator blocks
+// (ACC1a, ACC1b, ACC2) and a two-stage A ring of 32-element chunks, so a tile is 13 A chunks and 18 B chunks instead of
+// 56 + 56, every A chunk is produced ONCE (the input chunk feeds both layer-1 blocks, each layer-2 chunk both [mu; logvar]
+// blocks), and the accumulators a layer reads are never the ones the MMA pipe is writing:
+//   A0      = x                         -> B W1[0:128]   -> ACC1a      and  B W1[128:256] -> ACC1b
+//   A1..A4  = relu(ACC1a + b1[0:128])   -> B W2[:, 0:128]   (4 chunks) -> ACC2
+//   A5..A8  = relu(ACC1b + b1[128:256]) -> B W2[:, 128:256] (4 chunks) -> ACC2
+//   A9..A12 = relu(ACC2 + b2)           -> B [mu; lv][0:64] -> ACC1a   and  B [mu; lv][64:128] -> ACC1b
+//   head(h0) reads ACC1a, head(h1) reads ACC1b (z = mu + exp(lv / 2) eps, d += wd . z)
+// Two producer warpgroups (threads t and t + 128 own sample t and split every chunk's 32 columns, the input row and the
+// head, as in disc_reward_pg2_kernel), one MMA-issuing thread, one copy-issuing thread.  Besides the rings there is one
+// mbarrier per "accumulator complete" event (r1a, r1b, r2, r3a, r3b: one phase per tile) and h_done (the heads have
+// finished reading ACC1a / ACC1b: the next tile's layer 1 may overwrite them).  Shared memory carries weights only
+// (six 32 KB stages).
+constexpr int V4_KC = 32, V4_NSB = 6, V4_NSA = 2;
+constexpr int V4_STAGE_B = 128 * V4_KC * 4 * 2;          // 32 KB: 128 rows x 32 K, hi + lo
+constexpr int V4_ACC1A = 0, V4_ACC1B = 128, V4_ACC2 = 256, V4_AR = 384;
+constexpr int V4_BCHUNKS = 2 + 8 + 8;
+constexpr int V4_ACHUNKS = 13;
+enum { V4_R1A = 0, V4_R1B, V4_R2, V4_R3A, V4_R3B, V4_NR };
+
+template <bool KL>
+__global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ring = smem;
+  float* par = reinterpret_cast<float*>(smem + V4_NSB * V4_STAGE_B);
+  float* s_mean = par + V2_NPAR + 3;
+  float* s_inv = s_mean + DISC_IN;
+  float* red = s_inv + DISC_IN;                                 // [2][128] partial head sums of the second warpgroup
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * V4_NSA + 2 * V4_NSB + V4_NR + 1);
+  const float* b1 = par;
+  const float* b2 = par + 256;
+  const float* b3 = par + 384;            // per 128-row block h: [bmu[64h..64h+63], blv[64h..64h+63]]
+  const float* wd = par + 640;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s_) { return bar0 + 8u * s_; };
+  auto a_free = [&](int s_) { return bar0 + 8u * (V4_NSA + s_); };
+  auto b_full = [&](int s_) { return bar0 + 8u * (2 * V4_NSA + s_); };
+  auto b_free = [&](int s_) { return bar0 + 8u * (2 * V4_NSA + V4_NSB + s_); };
+  auto ready = [&](int k) { return bar0 + 8u * (2 * V4_NSA + 2 * V4_NSB + k); };
+  const uint32_t h_done = bar0 + 8u * (2 * V4_NSA + 2 * V4_NSB + V4_NR);
+
+  for (int i = tid; i < V2_NPAR; i += 320) par[i] = a.params[i];
+  if (tid < DISC_IN) { s_mean[tid] = a.mean[tid]; s_inv[tid] = 1.0f / a.stdv[tid]; }
+  if (tid == 0) {
+    for (int s_ = 0; s_ < V4_NSA; ++s_) { mbar_init(a_full(s_), 256); mbar_init(a_free(s_), 1); }
+    for (int s_ = 0; s_ < V4_NSB; ++s_) { mbar_init(b_full(s_), 1); mbar_init(b_free(s_), 1); }
+    for (int k = 0; k < V4_NR; ++k) mbar_init(ready(k), 1);
+    mbar_init(h_done, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int ntiles = (a.n + TILE - 1) / TILE;
+  int my_tiles = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) ++my_tiles;
+
+  if (warp == 9) {
+    // ===================================================== weight-copy issuer: 18 chunks of 32 KB per tile, MMA order
+    if (tid == 288) {
+      const int total = my_tiles * V4_BCHUNKS;
+      for (int q = 0; q < total; ++q) {
+        const int st = q % V4_NSB, use = q / V4_NSB;
+        if (use > 0) mbar_wait(b_free(st), (uint32_t)(use - 1) & 1u);
+        mbar_expect_tx(b_full(st), V4_STAGE_B);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.image) + (size_t)(q % V4_BCHUNKS) * V4_STAGE_B;
+        const uint32_t dst = smem_u32(ring + st * V4_STAGE_B);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) bulk_g2s(dst + p * (V4_STAGE_B / 4), src + p * (V4_STAGE_B / 4), V4_STAGE_B / 4, b_full(st));
+      }
+    }
+  } else if (warp == 8) {
+    // ===================================================== MMA issuer
+    if (tid == 256) {
+      const uint32_t idesc = idesc_tf32(TILE, 128);
+      const uint32_t lbo = 128 * 16, sbo = 128;
+      int ga = 0, qb = 0;
+      // one B chunk against the A chunk in stage sa: 4 k-steps x (lo.hi, hi.lo, hi.hi)
+      auto mma_chunk = [&](int sa, uint32_t d_col, bool first) {
+        const int sb = qb % V4_NSB;
+        mbar_wait(b_full(sb), (uint32_t)(qb / V4_NSB) & 1u);
+        tc_fence_after();
+        const uint32_t a_hi = tmem + V4_AR + sa * 64, a_lo = a_hi + 32;
+        const uint32_t b_hi = smem_u32(ring + sb * V4_STAGE_B), b_lo = b_hi + V4_STAGE_B / 2;
+#pragma unroll
+        for (int j = 0; j < V4_KC / 8; ++j) {
+          const uint32_t o = (uint32_t)j * 2 * lbo;
+          const uint64_t dbh = smem_desc(b_hi + o, lbo, sbo), dbl = smem_desc(b_lo + o, lbo, sbo);
+          umma_tf32_ts(tmem + d_col, a_lo + 8 * j, dbh, idesc, (first && j == 0) ? 0u : 1u);
+          umma_tf32_ts(tmem + d_col, a_hi + 8 * j, dbl, idesc, 1u);
+          umma_tf32_ts(tmem + d_col, a_hi + 8 * j, dbh, idesc, 1u);
+        }
+        umma_commit(b_free(sb));
+        ++qb;
+      };
+      auto next_a = [&]() {
+        const int sa = ga % V4_NSA;
+        mbar_wait(a_full(sa), (uint32_t)(ga / V4_NSA) & 1u);
+        tc_fence_after();
+        return sa;
+      };
+      for (int it = 0; it < my_tiles; ++it) {
+        if (it > 0) { mbar_wait(h_done, (uint32_t)(it - 1) & 1u); tc_fence_after(); }      // ACC1a / ACC1b have been read
+        int sa = next_a();                                              // A0 = x
+        mma_chunk(sa, V4_ACC1A, true);
+        umma_commit(ready(V4_R1A));
+        mma_chunk(sa, V4_ACC1B, true);
+        umma_commit(a_free(sa)); ++ga;
+        umma_commit(ready(V4_R1B));
+        for (int c = 0; c < 8; ++c) {                                   // A1..A8 -> layer 2
+          sa = next_a();
+          mma_chunk(sa, V4_ACC2, c == 0);
+          umma_commit(a_free(sa)); ++ga;
+        }
+        umma_commit(ready(V4_R2));
+        for (int c = 0; c < 4; ++c) {                                   // A9..A12 -> [mu; lv] blocks 0 and 1
+          sa = next_a();
+          mma_chunk(sa, V4_ACC1A, c == 0);
+          if (c == 3) umma_commit(ready(V4_R3A));
+          mma_chunk(sa, V4_ACC1B, c == 0);
+          umma_commit(a_free(sa)); ++ga;
+        }
+        umma_commit(ready(V4_R3B));
+      }
+    }
+  } else {
+    // ===================================================== producers / epilogue: 2 warpgroups, thread t and t + 128 = sample t
+    const int half = warp >> 2, row = tid & 127;                       // a warp may touch TMEM lanes 32 (warp % 4) ..
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const float bd = par[V2_NPAR - 1];
+    int ga = 0;
+    auto put = [&](const float (&act_in)[16]) {                        // this thread's 16 of the chunk's 32 columns
+      float hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { hi[i] = tf32_rna(act_in[i]); lo[i] = act_in[i] - hi[i]; }
+      if (ga >= V4_NSA) { mbar_wait(a_free(ga % V4_NSA), (uint32_t)(ga / V4_NSA - 1) & 1u); tc_fence_after(); }
+      const uint32_t at = lane_addr + V4_AR + (ga % V4_NSA) * 64 + 16 * half;
+      tmem_st16(at, hi);
+      tmem_st16(at + 32, lo);
+      tmem_wait_st();
+      tc_fence_before();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_full(ga % V4_NSA)) : "memory");
+      ++ga;
+    };
+    auto wait_ready = [&](int k, int it) { mbar_wait(ready(k), (uint32_t)it & 1u); tc_fence_after(); };
+    auto load_row = [&](int tile_, float (&raw)[16]) {
+      const int env_ = tile_ * TILE + row;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) raw[k] = (tile_ < ntiles && env_ < a.n) ? a.s[(size_t)(16 * half + k) * a.ld + env_] : 0.f;
+    };
+    float xn[16];
+    load_row(blockIdx.x, xn);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int env = tile * TILE + row;
+      const bool live = env < a.n;
+      {
+        float x[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = live ? (xn[k] - s_mean[16 * half + k]) * s_inv[16 * half + k] : 0.f;
+        put(x);                                                         // A0
+      }
+      load_row(tile + gridDim.x, xn);
+#pragma unroll 1
+      for (int blk = 0; blk < 2; ++blk) {                               // A1..A8: relu(layer 1 + b1)
+        wait_ready(blk == 0 ? V4_R1A : V4_R1B, it);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float h[16];
+          tmem_ld16(lane_addr + (blk == 0 ? V4_ACC1A : V4_ACC1B) + c * V4_KC + 16 * half, h);
+          bias_relu16(h, b1 + blk * 128 + c * V4_KC + 16 * half);
+          put(h);
+        }
+      }
+      wait_ready(V4_R2, it);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {                                     // A9..A12: relu(layer 2 + b2)
+        float h[16];
+        tmem_ld16(lane_addr + V4_ACC2 + c * V4_KC + 16 * half, h);
+        bias_relu16(h, b2 + c * V4_KC + 16 * half);
+        put(h);
+      }
+      float dval = 0.f, klv = 0.f;
+#pragma unroll 1
+      for (int hb = 0; hb < 2; ++hb) {                                  // heads: this thread's 32 of the block's 64 latents
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) e[i] = (a.eps && live) ? a.eps[(size_t)(64 * hb + 32 * half + i) * a.ld + env] : 0.f;
+        wait_ready(hb == 0 ? V4_R3A : V4_R3B, it);
+        const uint32_t acc = lane_addr + (hb == 0 ? V4_ACC1A : V4_ACC1B);
+        float mu[32], lv[32];
+        tmem_ld32(acc + 32 * half, mu);
+        tmem_ld32(acc + 64 + 32 * half, lv);
+        const float4* bm4 = reinterpret_cast<const float4*>(b3 + 128 * hb + 32 * half);
+        const float4* bl4 = reinterpret_cast<const float4*>(b3 + 128 * hb + 64 + 32 * half);
+        const float4* wv4 = reinterpret_cast<const float4*>(wd + 64 * hb + 32 * half);
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 bm_ = bm4[i4], bl_ = bl4[i4], wv_ = wv4[i4];
+          const float bmv[4] = {bm_.x, bm_.y, bm_.z, bm_.w}, blv[4] = {bl_.x, bl_.y, bl_.z, bl_.w};
+          const float wvv[4] = {wv_.x, wv_.y, wv_.z, wv_.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = 4 * i4 + k;
+            const float m = mu[i] + bmv[k], l = lv[i] + blv[k];
+            const float sd = expf(0.5f * l);
+            dval = fmaf(wvv[k], fmaf(sd, e[i], m), dval);
+            if (KL) klv += fmaf(m, m, fmaf(sd, sd, -l)) - 1.f;       // VDBLoss.kl_divergence, math.py:83-86
+          }
+        }
+      }
+      tc_fence_before();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(h_done) : "memory");   // ACC1a / ACC1b may be overwritten
+      // the two halves of a sample meet: half 1 hands its partial sums to half 0
+      if (half == 1) { red[row] = dval; red[128 + row] = klv; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0 && live) {
+        dval += red[row] + bd;
+        const float one_minus_p = 1.f / (1.f + expf(dval));
+        if (a.reward) a.reward[env] = -logf(one_minus_p + 1e-8f);
+        if (a.d_out) a.d_out[env] = dval;
+        if (KL) a.kl_out[env] = 0.5f * (klv + red[128 + row]);
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");                     // red[] may be rewritten by the next tile
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace om
 
 using namespace om;
@@ -1115,6 +1353,7 @@ struct OmDisc {
   float* params2 = nullptr;
   float* image3 = nullptr;      // VAIL: chunk image / parameters of disc_vail3_kernel (A operand in TMEM)
   float* params3 = nullptr;
+  float* image4 = nullptr;      // VAIL: chunk image of disc_vail4_kernel (one CTA per SM, A in TMEM); parameters = params2
 };
 
 static void split_tf32(float x, float* hi, float* lo) {
@@ -1241,6 +1480,35 @@ extern "C" int om_disc_create(const OmDiscDesc* d, OmDisc** out) {
     par3.insert(par3.end(), d->wd, d->wd + z);
     par3.push_back(d->bd[0]);
   }
+  // ---- VAIL, one CTA per SM, A operand in TMEM (disc_vail4_kernel): 18 chunks of 128 rows x 32 columns in MMA order;
+  //      the [mu; logvar] rows interleaved per 64 exactly as for disc_vail2_kernel (whose parameter block it shares)
+  std::vector<float> img4;
+  if (vail) {
+    std::vector<float> w3i((size_t)2 * z * n2);
+    for (int hb = 0; hb < 2; ++hb)
+      for (int r = 0; r < 64; ++r) {
+        std::memcpy(&w3i[(size_t)(128 * hb + r) * n2], d->wmu + (size_t)(64 * hb + r) * n2, sizeof(float) * n2);
+        std::memcpy(&w3i[(size_t)(128 * hb + 64 + r) * n2], d->wlv + (size_t)(64 * hb + r) * n2, sizeof(float) * n2);
+      }
+    auto chunk32 = [&](const float* w, int ldw, int r0, int k0) {          // 128 rows x 32 columns: hi image, lo image
+      const size_t base = img4.size();
+      img4.resize(base + (size_t)128 * V4_KC * 2);
+      float* hi = img4.data() + base;
+      float* lo = hi + (size_t)128 * V4_KC;
+      for (int kc = 0; kc < V4_KC / 4; ++kc)
+        for (int r = 0; r < 128; ++r)
+          for (int e = 0; e < 4; ++e)
+            split_tf32(w[(size_t)(r0 + r) * ldw + k0 + kc * 4 + e], hi + ((size_t)kc * 128 + r) * 4 + e,
+                       lo + ((size_t)kc * 128 + r) * 4 + e);
+    };
+    chunk32(d->w1, DISC_IN, 0, 0);
+    chunk32(d->w1, DISC_IN, 128, 0);
+    for (int c = 0; c < 8; ++c) chunk32(d->w2, n1, 0, 32 * c);
+    for (int c = 0; c < 4; ++c) {
+      chunk32(w3i.data(), n2, 0, 32 * c);
+      chunk32(w3i.data(), n2, 128, 32 * c);
+    }
+  }
   OmDisc* h = new OmDisc();
   h->sh = DiscShape{d->kind, n1, n2, z};
   cudaError_t e = cudaMalloc(&h->image, img.size() * sizeof(float));
@@ -1256,6 +1524,8 @@ extern "C" int om_disc_create(const OmDiscDesc* d, OmDisc** out) {
     if (e == cudaSuccess) e = cudaMalloc(&h->params3, par3.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(h->image3, img3.data(), img3.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->params3, par3.data(), par3.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&h->image4, img4.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(h->image4, img4.data(), img4.size() * sizeof(float), cudaMemcpyHostToDevice);
   }
   if (e != cudaSuccess) {
     if (h->image) cudaFree(h->image);
@@ -1264,6 +1534,7 @@ extern "C" int om_disc_create(const OmDiscDesc* d, OmDisc** out) {
     if (h->params2) cudaFree(h->params2);
     if (h->image3) cudaFree(h->image3);
     if (h->params3) cudaFree(h->params3);
+    if (h->image4) cudaFree(h->image4);
     delete h;
     return fail("om_disc_create: device upload failed: %s (no CPU path)", cudaGetErrorString(e));
   }
@@ -1279,6 +1550,7 @@ extern "C" void om_disc_destroy(OmDisc* h) {
   if (h->params2) cudaFree(h->params2);
   if (h->image3) cudaFree(h->image3);
   if (h->params3) cudaFree(h->params3);
+  if (h->image4) cudaFree(h->image4);
   delete h;
 }
 
@@ -1308,6 +1580,18 @@ extern "C" int om_disc_forward(const OmDisc* h, const float* s, const float* mea
   // kernel reads 76-78 us in both settings, so it stays the default.)
   int two = h->sh.kind == 0;
   if (g_knobs.disc_vail2 >= 0) two = h->sh.kind == 0 && g_knobs.disc_vail2 != 0;           // tuning / test hook: force either
+  if (h->sh.kind == 0 && g_knobs.disc_vail2 == 4) {            // one CTA per SM, A operand in TMEM
+    const size_t smem4 = V4_NSB * V4_STAGE_B + (V2_NPAR + 3 + 2 * DISC_IN + 256) * sizeof(float) +
+                         (2 * V4_NSA + 2 * V4_NSB + V4_NR + 1) * 8 + 16;
+    DiscArgs a4 = a;
+    a4.image = h->image4;
+    a4.params = h->params2;
+    auto kern = kl_out ? disc_vail4_kernel<true> : disc_vail4_kernel<false>;
+    OM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+    kern<<<grid, 320, smem4, st>>>(a4);
+    OM_LAUNCHED();
+    return 0;
+  }
   if (h->sh.kind == 0 && g_knobs.disc_vail2 == 3) {            // A operand in TMEM (opt-in: measured slower, see the kernel)
     const size_t smem3 = V3_NSB * V3_STAGE_B + (V3_NPAR + 3 + 2 * DISC_IN) * sizeof(float) + (2 * V3_NSA + 2 * V3_NSB) * 8 + 16;
     const int grid3 = ntiles < 2 * sms ? ntiles : 2 * sms;

@@ -1,5 +1,5 @@
-timeout 300 python -m pytest tests/test_gpu_disc.py -m gpu -x -q -k "a_in_tmem or two_ctas" 2>&1 | tail -15
-for v in 1 3; do echo "OM_DISC_VAIL2=$v"; OM_DISC_VAIL2=$v timeout 120 python tools/bench_disc.py --steps 30 2>&1 | python -c "
+timeout 300 python -m pytest tests/test_gpu_disc.py -m gpu -x -q -k "one_cta" 2>&1 | tail -15
+for v in 1 4; do echo "OM_DISC_VAIL2=$v"; OM_DISC_VAIL2=$v timeout 120 python tools/bench_disc.py --steps 30 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)
