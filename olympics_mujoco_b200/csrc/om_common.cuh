@@ -28,7 +28,8 @@ struct Knobs {
   int h1_split = -1;      // OM_H1_SPLIT     1 / 0: force / forbid the three-threads-per-env H1 step kernel
   int a3_split = -1;      // OM_A3_SPLIT     1 / 0: force / forbid the time-parallel A3 replay
   int serial_scan = 0;    // OM_SERIAL_SCAN  1: one-thread-per-env returns / GAE kernels
-  int disc_vail2 = -1;    // OM_DISC_VAIL2   1 / 0: two-CTAs-per-SM VAIL kernel; 3: the variant with the A operand in TMEM
+  int disc_vail2 = -1;    // OM_DISC_VAIL2   VAIL kernel: -1 / 4 one CTA per SM with the A operand in TMEM (default), 1 two CTAs per SM
+                          //                 (shared-memory operands), 3 two CTAs per SM with A in TMEM, 0 the kernels that also serve GAIL
   int disc_pg2 = -1;      // OM_DISC_PG2     1 / 0: two producer warpgroups
   int a3_feat_minb = 5;   // OM_A3_FEAT_MINB 4 / 5 / 6: resident CTAs per SM the A3 replay kernel is compiled for (tuning)
 };

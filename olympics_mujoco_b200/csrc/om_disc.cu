@@ -1580,7 +1580,10 @@ extern "C" int om_disc_forward(const OmDisc* h, const float* s, const float* mea
   // kernel reads 76-78 us in both settings, so it stays the default.)
   int two = h->sh.kind == 0;
   if (g_knobs.disc_vail2 >= 0) two = h->sh.kind == 0 && g_knobs.disc_vail2 != 0;           // tuning / test hook: force either
-  if (h->sh.kind == 0 && g_knobs.disc_vail2 == 4) {            // one CTA per SM, A operand in TMEM
+  // VAIL default: disc_vail4_kernel (one CTA per SM, A operand in TMEM): 69 us at 65536 samples / 796 us at 1 M against 74 /
+  // 815 for the two-CTA shared-memory kernel (knob 1), 82 / 975 for the two-CTA TMEM kernel (knob 3), 72 / 841 for the
+  // two-producer-group shared-memory kernel (knob 0)
+  if (h->sh.kind == 0 && (g_knobs.disc_vail2 == 4 || g_knobs.disc_vail2 < 0)) {
     const size_t smem4 = V4_NSB * V4_STAGE_B + (V2_NPAR + 3 + 2 * DISC_IN + 256) * sizeof(float) +
                          (2 * V4_NSA + 2 * V4_NSB + V4_NR + 1) * 8 + 16;
     DiscArgs a4 = a;

@@ -1,16 +1,4 @@
-timeout 300 python -m pytest tests/test_gpu_disc.py -m gpu -x -q -k "one_cta" 2>&1 | tail -15
-for v in 1 4; do echo "OM_DISC_VAIL2=$v"; OM_DISC_VAIL2=$v timeout 120 python tools/bench_disc.py --steps 30 2>&1 | python -c "
+python -m pytest tests/test_gpu_disc.py tests/test_gpu_disc_fit.py -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
 import sys,json
-for l in sys.stdin:
-    try: d=json.loads(l)
-    except Exception: print(l.strip()[:200]); continue
-    print(d['net'], round(d['ms']*1000,1),'us', 'frac_exec', round(d['roofline']['frac_executed'],3), 'peak', round(d['roofline']['peak'],1))
-"
-OM_DISC_VAIL2=$v timeout 120 python tools/bench_disc.py --steps 10 --envs 1048576 2>&1 | python -c "
-import sys,json
-for l in sys.stdin:
-    try: d=json.loads(l)
-    except Exception: print(l.strip()[:200]); continue
-    print(d['net'], '1M', round(d['ms']*1000,1),'us', 'frac_exec', round(d['roofline']['frac_executed'],3))
-"
-done
+d=json.loads(sys.stdin.read()); print(d['ms_per_step']); print(json.dumps(d['other_configs']['disc_reward_65536'])); print(json.dumps(d['other_configs']['disc_reward_1048576'])); print(json.dumps(d['other_configs']['a3_ppo_rollout_16384x64']))"

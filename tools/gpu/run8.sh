@@ -1,7 +1,10 @@
-# 8-GPU: D2H ceiling probe, then the bench at N=8 (mailbox) for the record
-nvidia-smi topo -m > gpurun_out/r02d_topo.txt 2>&1; lscpu | grep -i "numa\|socket\|model name\|^CPU(s)" > gpurun_out/r02d_lscpu.txt 2>&1
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 tools/probe_d2h.py 2> gpurun_out/r02d_probe.err | tail -1 > gpurun_out/r02d_probe_d2h.json
-cat gpurun_out/r02d_probe_d2h.json; tail -3 gpurun_out/r02d_probe.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 8 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02d_bench_n8.json 2> gpurun_out/r02d_bench_n8.err
-tail -c 300 gpurun_out/r02d_bench_n8.err; cut -c1-2500 gpurun_out/r02d_bench_n8.json
-head -30 gpurun_out/r02d_topo.txt; cat gpurun_out/r02d_lscpu.txt
+python tools/bench_a3.py --steps 10 --warmup 3 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('task_kernel_ms','ms_per_step','host_enqueue_ms_per_step','eager_task_kernel_ms','timing','gpu_launches')}, d['roofline']['frac'])"
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --verbose-other 2>&1 >/dev/null | python -c "
+import sys,json
+for l in sys.stdin:
+    try: d=json.loads(l)
+    except Exception: continue
+    for k in ('a3_ppo_rollout_16384x64','a3_ppo_rollout_262144x64'):
+        print(k, {j:d[k][j] for j in ('task_kernel_ms','ms_per_step','host_enqueue_ms_per_step','eager_task_kernel_ms','timing')}, d[k]['roofline']['frac'])"
