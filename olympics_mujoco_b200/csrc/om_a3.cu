@@ -235,22 +235,39 @@ __device__ __forceinline__ void a3_walk(const A3Args& a, const A3Scratch& w, int
   const uint4* nb = reinterpret_cast<const uint4*>(w.near + e * w.tp);
   uint4* cd = reinterpret_cast<uint4*>(w.code + e * w.tp);
   for (int t0 = 0; t0 < a.T; t0 += 64) {
-    uint4 in[4];
+    uint32_t wi[16];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) in[v] = t0 + 16 * v < a.T ? nb[(t0 >> 4) + v] : make_uint4(0, 0, 0, 0);
+    for (int v = 0; v < 4; ++v) {
+      const uint4 in = t0 + 16 * v < a.T ? nb[(t0 >> 4) + v] : make_uint4(0, 0, 0, 0);
+      wi[4 * v] = in.x; wi[4 * v + 1] = in.y; wi[4 * v + 2] = in.z; wi[4 * v + 3] = in.w;
+    }
+    uint32_t any = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) any |= wi[q];
+    if (any & 0x80808080u) {                                         // rare: a flagged env-step among these 64
+      // One bit per flagged byte, then one float64 re-decision per loop trip: every lane of the warp that holds a flagged
+      // byte makes its FIRST trip together with the others (same code, no divergence), so a warp pays for the largest
+      // count in one lane -- almost always one -- not for the sum over its lanes.
+      uint64_t pend = 0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q)                                   // bits 7, 15, 23, 31 of word q -> bits 4q .. 4q + 3
+        pend |= (uint64_t)(((wi[q] & 0x80808080u) * 0x00204081u) >> 28) << (4 * q);
+#pragma unroll 1
+      while (pend) {
+        const int k = __ffsll((long long)pend) - 1;
+        pend &= pend - 1;
+        if (t0 + k < a.T) {
+          const uint32_t exact = a3_refix(a, ncand, t0 + k, e);
+          const uint32_t keep = ~(0xffu << (8 * (k & 3))), put = exact << (8 * (k & 3));
+#pragma unroll
+          for (int q = 0; q < 16; ++q)                               // static indices: wi stays in registers
+            if (q == (k >> 2)) wi[q] = (wi[q] & keep) | put;
+        }
+      }
+    }
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
       if (t0 + 16 * v < a.T) {
-        uint32_t wi[4] = {in[v].x, in[v].y, in[v].z, in[v].w};
-        if ((wi[0] | wi[1] | wi[2] | wi[3]) & 0x80808080u) {         // rare: a flagged env-step among these sixteen
-#pragma unroll 1
-          for (int k = 0; k < 16; ++k) {
-            if (((wi[k >> 2] >> (8 * (k & 3))) & 0x80u) && t0 + 16 * v + k < a.T) {
-              const uint32_t exact = a3_refix(a, ncand, t0 + 16 * v + k, e);
-              wi[k >> 2] = (wi[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (exact << (8 * (k & 3)));
-            }
-          }
-        }
         uint32_t wo[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -258,7 +275,7 @@ __device__ __forceinline__ void a3_walk(const A3Args& a, const A3Scratch& w, int
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             if (t0 + 16 * v + 4 * q + b < a.T) {                     // bytes past T are padding
-              a3_walk_step(a.C, (wi[q] >> (8 * b)) & 0xffu, s);
+              a3_walk_step(a.C, (wi[4 * v + q] >> (8 * b)) & 0xffu, s);
               o |= (uint32_t)(s.j | (s.reached << 3)) << (8 * b);
             }
           }
