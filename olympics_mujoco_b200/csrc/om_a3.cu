@@ -112,8 +112,11 @@ __global__ void __launch_bounds__(BLOCK) a3_task_kernel(A3Args a) {
 //                   across CTAs, 112 us instead of 90 us.)
 //   a3_walk_kernel  one thread per env: the integer state machine over the T bytes (a few instructions per step),
 //                   leaves a one-byte (advances, reached) code per env-step and the final task state.  (Measured and
-//                   rejected: running it in the last-finishing feat CTA of each env block -- 147 us instead of 142.)
-//   a3_post_kernel  one thread per (env, t) again: goal steps, orientation and step terms, total.
+//                   rejected: running it in the last-finishing feat CTA of each env block -- 147 us instead of 142; and
+//                   as the first `env_blocks` CTAs of the post kernel -- the float64 re-decision's registers become the
+//                   post kernel's: 128 registers, or 64 with spills, 150 us instead of 121.)
+//   a3_post_kernel  one thread per (env, t) again: goal steps, orientation and step terms, total.  Starts while the walk
+//                   runs and waits per env block (see a3_walk_kernel): the walk costs 2 us of the call instead of 17.
 struct A3Scratch {
   float* feat;          // [T][16][ld]
   // the two byte arrays are ENV-major ([ld][tp], tp = T rounded up to 16): the sequential pass reads and writes an env's
@@ -124,6 +127,9 @@ struct A3Scratch {
   int tp;
   int32_t* start;       // [2][ld]   t1, t2 at the start of the call
   float* trig;          // [A3_MAX_CAND + 1][4][ld]   sin, cos of candidate j's heading and of half of it (feat t = 0 -> post)
+  // [1 + env blocks]: word b + 1 = "the state codes of env block b are written" (walk -> post).  Zeroed by the feat kernel
+  // of the same call, so a replayed CUDA graph starts from zero too.
+  int* sync;
 };
 
 // Row k of a per-(env, t) SoA block: ONE 64-bit base pointer per array (it carries t and the env), rows addressed by the
@@ -163,6 +169,7 @@ __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w
     asm volatile("prefetch.global.L1 [%0];" ::"l"(row(p, 2, lu)));
   }
   if (t == 0) {                                                            // start state of the call for the post pass
+    if (threadIdx.x == 0) w.sync[1 + blockIdx.x] = 0;
     w.start[e] = t1_0;
     w.start[ld + e] = t2_0;
     for (int j = 0; j <= ncand; ++j) {             // headings of every target the call can reach, and of the one after
@@ -297,22 +304,32 @@ __global__ void __launch_bounds__(BLOCK, MINB) a3_feat_kernel(A3Args a, A3Scratc
   if (env < a.n) a3_feat_item(a, w, ncand, blockIdx.y, env);
 }
 
-__global__ void __launch_bounds__(64) a3_walk_kernel(A3Args a, A3Scratch w, int ncand) {
-  pdl_trigger();                                 // 256 small CTAs: let the post pass's CTAs take the idle SMs now
+// The sequential pass and the second (env, t)-parallel pass OVERLAP.  The walk kernel (one thread per env, one CTA per
+// block of 128 envs) waits for the feat kernel, lets its dependent launch, walks, and publishes one flag per env block;
+// the post kernel's CTAs are therefore scheduled while the walk runs (every walk CTA is resident by then, so nothing a
+// post CTA waits for can be starved), load their records, wait for THEIR block's flag and finish their env-steps.  An
+// env block whose walk has to re-take decisions in float64 (a3_refix, ~5 us) holds back only its own CTAs, and the
+// launch boundary between the two passes is gone.  The post kernel does not call griddepcontrol.wait: it is launched
+// only once every walk CTA is past its own wait, i.e. after the feat kernel has completed and flushed, and what the walk
+// writes it reads behind the flag (release / acquire at gpu scope).
+__global__ void __launch_bounds__(128) a3_walk_kernel(A3Args a, A3Scratch w, int ncand) {
   pdl_wait();
-  const int env = blockIdx.x * 64 + threadIdx.x;
+  pdl_trigger();
+  const int env = blockIdx.x * 128 + threadIdx.x;
   if (env < a.n) a3_walk(a, w, ncand, env);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(w.sync + 1 + blockIdx.x), "r"(1) : "memory");
 }
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) a3_post_kernel(A3Args a, A3Scratch w) {
-  pdl_wait();
-  const int env = blockIdx.x * BLOCK + threadIdx.x;
   const int t = blockIdx.y;
-  if (env >= a.n) return;
-  const size_t ld = a.ld, e = env;
+  const int env = blockIdx.x * BLOCK + threadIdx.x;
+  const bool live = env < a.n;
+  const size_t ld = a.ld, e = live ? env : 0;
   const unsigned lu = (unsigned)a.ld;
-  const int code = w.code[e * w.tp + t];
+  const int* flag = w.sync + 1 + blockIdx.x;
   const int mode = a.ints[A3I_MODE * ld + e], seq_len = a.ints[A3I_SEQLEN * ld + e];
   const int t1_0 = w.start[e], t2_0 = w.start[ld + e];
   // the two targets' rows depend on the state code (a second level of dependent loads): in most env-steps no target has
@@ -327,6 +344,18 @@ __global__ void __launch_bounds__(BLOCK) a3_post_kernel(A3Args a, A3Scratch w) {
     }
   }
   const A3Rec rec = a3_rec_load(w.feat + (size_t)t * A3_NREC * ld + e, lu);
+  {
+    if (threadIdx.x == 0) {
+      int ready;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(ready) : "l"(flag) : "memory");
+        if (!ready) __nanosleep(64);
+      } while (!ready);
+    }
+    __syncthreads();
+  }
+  if (!live) return;
+  const int code = __ldcg(w.code + e * w.tp + t);                      // written by another CTA of this kernel: not through L1
   const int j = code & 7;
   const float* tr = w.trig + e + (unsigned)(j * 4) * lu;               // candidate j, then candidate j + 1
   const A3TargetTrig tg{tr[0], *row(tr, 1, lu), *row(tr, 4, lu), *row(tr, 5, lu), *row(tr, 2, lu), *row(tr, 3, lu)};
@@ -478,12 +507,13 @@ static int a3_step_impl(const OmModel* m, const OmA3Task* task, const float* qpo
   if (split) {
     constexpr int FB = 128;
     const int env_blocks = ceil_div(n, FB);
-    // layout: [records][start ints + heading table][candidate bytes][state codes]
+    // layout: [records][start ints + heading table][candidate bytes][state codes][ticket + env-block flags]
     const size_t feat_b = (size_t)n_steps * A3_NREC * (size_t)ld * sizeof(float);
     const size_t int_b = ((size_t)(2 + (A3_MAX_CAND + 1) * 4) * ld * sizeof(int32_t) + 15) / 16 * 16;   // byte arrays 16-B aligned
     const int tp_max = (n_steps + 15) / 16 * 16;
     const size_t byte_b = (size_t)tp_max * (size_t)ld;
-    const size_t need = feat_b + int_b + 2 * byte_b;
+    const size_t byte_pad = (2 * byte_b + 15) / 16 * 16;
+    const size_t need = feat_b + int_b + byte_pad + (size_t)(1 + env_blocks) * sizeof(int);
     OM_REQUIRE(env_blocks <= 65535, "om_a3_task_step: at most %d envs per multi-step call", 65535 * FB);
     if (task->scratch_bytes < need) {
       if (task->scratch) OM_CUDA_OK(cudaFree(task->scratch));  // synchronises: no earlier call still reads it
@@ -494,7 +524,7 @@ static int a3_step_impl(const OmModel* m, const OmA3Task* task, const float* qpo
     }
     char* base = (char*)task->scratch;
     A3Scratch w{(float*)base, (uint8_t*)(base + feat_b + int_b), (uint8_t*)(base + feat_b + int_b + byte_b), 0,
-                (int32_t*)(base + feat_b), (float*)(base + feat_b) + 2 * (size_t)ld};
+                (int32_t*)(base + feat_b), (float*)(base + feat_b) + 2 * (size_t)ld, (int*)(base + feat_b + int_b + byte_pad)};
     // sub-calls no longer than the candidate bits cover (210 steps with the reference's 30 delay frames)
     const int max_call = a3_max_steps_per_call(task->C.delay_frames);
     for (int c0 = 0; c0 < n_steps; c0 += max_call) {
@@ -513,7 +543,8 @@ static int a3_step_impl(const OmModel* m, const OmA3Task* task, const float* qpo
       else if (g_knobs.a3_feat_minb == 4) a3_feat_kernel<FB, 4><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
       else a3_feat_kernel<FB, 5><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
       OM_LAUNCHED();
-      OM_CUDA_OK(launch_pdl(a3_walk_kernel, dim3(ceil_div(n, 64)), dim3(64), 0, st, sub, w, ncand));
+      static_assert(FB == 128, "a3_walk_kernel publishes one flag per 128 envs");
+      OM_CUDA_OK(launch_pdl(a3_walk_kernel, dim3(env_blocks), dim3(FB), 0, st, sub, w, ncand));
       OM_LAUNCHED();
       OM_CUDA_OK(launch_pdl(a3_post_kernel<FB>, dim3(env_blocks, len), dim3(FB), 0, st, sub, w));
       OM_LAUNCHED();

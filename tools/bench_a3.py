@@ -124,7 +124,7 @@ def measure(envs=16384, horizon=64, steps=20, warmup=3, per_step=False, fused_re
             "value": n * T / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "task_kernel_ms": kms,
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "timing": timing,
             "eager_ms_per_step": eager_ms, "eager_task_kernel_ms": eager_kms,
-            "roofline": {"bound": "hbm", "kernel": "a3_feat_kernel + a3_fix_kernel + a3_walk_kernel + a3_post_kernel + affine_scan_kernel (om_a3_task_rollout: one call)", "achieved": achieved, "peak": peaks["hbm_gbs"],
+            "roofline": {"bound": "hbm", "kernel": "a3_feat_kernel + a3_walk_kernel + a3_post_kernel + affine_scan_kernel (om_a3_task_rollout: one call)", "achieved": achieved, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "bytes_per_env_step": BYTES_PER_ENV_STEP}}
 
 
