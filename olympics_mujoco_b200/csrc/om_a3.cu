@@ -116,20 +116,21 @@ __global__ void __launch_bounds__(BLOCK) a3_task_kernel(A3Args a) {
 //                   as the first `env_blocks` CTAs of the post kernel -- the float64 re-decision's registers become the
 //                   post kernel's: 128 registers, or 64 with spills, 150 us instead of 121.)
 //   a3_post_kernel  one thread per (env, t) again: goal steps, orientation and step terms, total.  Starts while the walk
-//                   runs and waits per env block (see a3_walk_kernel): the walk costs 2 us of the call instead of 17.
+//                   runs, each thread waiting for its own state code (see a3_walk_kernel): the walk costs 2 us of the
+//                   call instead of 17.
 struct A3Scratch {
   float* feat;          // [T][16][ld]
-  // the two byte arrays are ENV-major ([ld][tp], tp = T rounded up to 16): the sequential pass reads and writes an env's
-  // bytes as 16-byte vectors (4 loads per 64 steps instead of 64 with their address arithmetic -- it runs one warp per
-  // scheduler, every instruction's latency is exposed); the (env, t)-parallel passes touch one byte per thread
-  uint8_t* near;        // candidate bits
-  uint8_t* code;        // advances since the call started | reached << 3, after the step's update
+  // ONE byte per env-step, ENV-major ([ld][tp], tp = T rounded up to 16), written twice:
+  //   by the feat pass   candidate bits 0..5 | 0x40 if a decision has to be re-taken in float64    (bit 7 clear)
+  //   by the walk pass   advances since the call started | reached << 3 | 0x80, after the step's update
+  // The sequential pass reads and rewrites an env's bytes in place as 16-byte vectors (4 loads per 64 steps instead of 64
+  // with their address arithmetic -- it runs one warp per scheduler, every instruction's latency is exposed); the
+  // (env, t)-parallel passes touch one byte per thread.  Bit 7 is what the post pass, which starts while the walk runs,
+  // waits for.
+  uint8_t* step;
   int tp;
   int32_t* start;       // [2][ld]   t1, t2 at the start of the call
   float* trig;          // [A3_MAX_CAND + 1][4][ld]   sin, cos of candidate j's heading and of half of it (feat t = 0 -> post)
-  // [1 + env blocks]: word b + 1 = "the state codes of env block b are written" (walk -> post).  Zeroed by the feat kernel
-  // of the same call, so a replayed CUDA graph starts from zero too.
-  int* sync;
 };
 
 // Row k of a per-(env, t) SoA block: ONE 64-bit base pointer per array (it carries t and the env), rows addressed by the
@@ -169,7 +170,6 @@ __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w
     asm volatile("prefetch.global.L1 [%0];" ::"l"(row(p, 2, lu)));
   }
   if (t == 0) {                                                            // start state of the call for the post pass
-    if (threadIdx.x == 0) w.sync[1 + blockIdx.x] = 0;
     w.start[e] = t1_0;
     w.start[ld + e] = t2_0;
     for (int j = 0; j <= ncand; ++j) {             // headings of every target the call can reach, and of the one after
@@ -187,14 +187,14 @@ __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w
   om_fk_pos_stick_figure_a3(q, qd, S);           // matrix-chain variant: no body orientations needed
   bool done;
   const int fl = (int)con[3];
-  A3Exact ex{qp, ld, true, false};               // decisions within A3_BAND of a threshold are only NOTED here (bit 7 below)
+  A3Exact ex{qp, ld, true, false};               // decisions within A3_BAND of a threshold are only NOTED here (bit 6 below)
   const A3Rec rec = a3_task_pre(a.C, a3_task_in(S.f), phase, mode, con[0], con[1], con[2], (fl & 1) != 0, (fl & 2) != 0, terms,
                                 obs[31], obs[32], done, ex);
   a3_rec_store(rec, w.feat + (size_t)t * A3_NREC * ld + e, lu);
   const uint32_t bits = a3_near_bits(a.C, rec.lsite, rec.rsite, nc, t1_0, t2_0, seq_len, SeqGlobal{a.sequence + e, ld}, ex);
-  // bit 7: a decision of this env-step (done, or one of the candidate bits) is within A3_BAND of its threshold; the
+  // bit 6: a decision of this env-step (done, or one of the candidate bits) is within A3_BAND of its threshold; the
   // sequential pass re-takes it in float64 (a3_refix) before it consumes the byte -- about one env-step in 10^4
-  w.near[e * w.tp + t] = (uint8_t)(bits | (ex.unsure ? 0x80u : 0u));
+  w.step[e * w.tp + t] = (uint8_t)(bits | (ex.unsure ? 0x40u : 0u));
   if (a.o.obs) {
     float* ob = a.o.obs + (size_t)t * A3_NOBS * ld + e;
 #pragma unroll
@@ -239,8 +239,8 @@ __device__ __forceinline__ void a3_walk(const A3Args& a, const A3Scratch& w, int
   const size_t ld = a.ld;
   const int t1_0 = a.ints[A3I_T1 * ld + e], t2_0 = a.ints[A3I_T2 * ld + e], seq_len = a.ints[A3I_SEQLEN * ld + e];
   A3Walk s{0, a.ints[A3I_FRAMES * ld + e], a.ints[A3I_REACHED * ld + e]};
-  const uint4* nb = reinterpret_cast<const uint4*>(w.near + e * w.tp);
-  uint4* cd = reinterpret_cast<uint4*>(w.code + e * w.tp);
+  uint4* cd = reinterpret_cast<uint4*>(w.step + e * w.tp);
+  const uint4* nb = cd;
   for (int t0 = 0; t0 < a.T; t0 += 64) {
     uint32_t wi[16];
 #pragma unroll
@@ -251,14 +251,14 @@ __device__ __forceinline__ void a3_walk(const A3Args& a, const A3Scratch& w, int
     uint32_t any = 0;
 #pragma unroll
     for (int q = 0; q < 16; ++q) any |= wi[q];
-    if (any & 0x80808080u) {                                         // rare: a flagged env-step among these 64
+    if (any & 0x40404040u) {                                         // rare: a flagged env-step among these 64
       // One bit per flagged byte, then one float64 re-decision per loop trip: every lane of the warp that holds a flagged
       // byte makes its FIRST trip together with the others (same code, no divergence), so a warp pays for the largest
       // count in one lane -- almost always one -- not for the sum over its lanes.
       uint64_t pend = 0;
 #pragma unroll
-      for (int q = 0; q < 16; ++q)                                   // bits 7, 15, 23, 31 of word q -> bits 4q .. 4q + 3
-        pend |= (uint64_t)(((wi[q] & 0x80808080u) * 0x00204081u) >> 28) << (4 * q);
+      for (int q = 0; q < 16; ++q)                                   // bits 6, 14, 22, 30 of word q -> bits 4q .. 4q + 3
+        pend |= (uint64_t)((((wi[q] & 0x40404040u) << 1) * 0x00204081u) >> 28) << (4 * q);
 #pragma unroll 1
       while (pend) {
         const int k = __ffsll((long long)pend) - 1;
@@ -283,7 +283,7 @@ __device__ __forceinline__ void a3_walk(const A3Args& a, const A3Scratch& w, int
           for (int b = 0; b < 4; ++b) {
             if (t0 + 16 * v + 4 * q + b < a.T) {                     // bytes past T are padding
               a3_walk_step(a.C, (wi[4 * v + q] >> (8 * b)) & 0xffu, s);
-              o |= (uint32_t)(s.j | (s.reached << 3)) << (8 * b);
+              o |= (uint32_t)(s.j | (s.reached << 3) | 0x80) << (8 * b);
             }
           }
           wo[q] = o;
@@ -304,32 +304,28 @@ __global__ void __launch_bounds__(BLOCK, MINB) a3_feat_kernel(A3Args a, A3Scratc
   if (env < a.n) a3_feat_item(a, w, ncand, blockIdx.y, env);
 }
 
-// The sequential pass and the second (env, t)-parallel pass OVERLAP.  The walk kernel (one thread per env, one CTA per
-// block of 128 envs) waits for the feat kernel, lets its dependent launch, walks, and publishes one flag per env block;
-// the post kernel's CTAs are therefore scheduled while the walk runs (every walk CTA is resident by then, so nothing a
-// post CTA waits for can be starved), load their records, wait for THEIR block's flag and finish their env-steps.  An
-// env block whose walk has to re-take decisions in float64 (a3_refix, ~5 us) holds back only its own CTAs, and the
-// launch boundary between the two passes is gone.  The post kernel does not call griddepcontrol.wait: it is launched
-// only once every walk CTA is past its own wait, i.e. after the feat kernel has completed and flushed, and what the walk
-// writes it reads behind the flag (release / acquire at gpu scope).
-__global__ void __launch_bounds__(128) a3_walk_kernel(A3Args a, A3Scratch w, int ncand) {
+// The sequential pass and the second (env, t)-parallel pass OVERLAP.  The walk kernel (one thread per env) waits for the
+// feat kernel, lets its dependent launch, and walks; the post kernel's CTAs are therefore scheduled while the walk runs
+// (every walk CTA has started by then, so nothing a post thread waits for can be starved), load their records, and each
+// thread waits for bit 7 of ITS state code -- the one thing it reads from the walk, so the byte is its own flag and no
+// fence is involved.  An env whose walk has to re-take decisions in float64 (a3_refix, ~5 us) holds back only the
+// warps it sits in, and the launch boundary between the two passes is gone.  The post kernel does not call
+// griddepcontrol.wait: it is launched only once every walk CTA is past its own wait, i.e. after the feat kernel has
+// completed and flushed.
+__global__ void __launch_bounds__(64) a3_walk_kernel(A3Args a, A3Scratch w, int ncand) {
   pdl_wait();
   pdl_trigger();
-  const int env = blockIdx.x * 128 + threadIdx.x;
+  const int env = blockIdx.x * 64 + threadIdx.x;
   if (env < a.n) a3_walk(a, w, ncand, env);
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(w.sync + 1 + blockIdx.x), "r"(1) : "memory");
 }
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) a3_post_kernel(A3Args a, A3Scratch w) {
   const int t = blockIdx.y;
   const int env = blockIdx.x * BLOCK + threadIdx.x;
-  const bool live = env < a.n;
-  const size_t ld = a.ld, e = live ? env : 0;
+  if (env >= a.n) return;
+  const size_t ld = a.ld, e = env;
   const unsigned lu = (unsigned)a.ld;
-  const int* flag = w.sync + 1 + blockIdx.x;
   const int mode = a.ints[A3I_MODE * ld + e], seq_len = a.ints[A3I_SEQLEN * ld + e];
   const int t1_0 = w.start[e], t2_0 = w.start[ld + e];
   // the two targets' rows depend on the state code (a second level of dependent loads): in most env-steps no target has
@@ -344,23 +340,16 @@ __global__ void __launch_bounds__(BLOCK) a3_post_kernel(A3Args a, A3Scratch w) {
     }
   }
   const A3Rec rec = a3_rec_load(w.feat + (size_t)t * A3_NREC * ld + e, lu);
+  int code;
   {
-    if (threadIdx.x == 0) {
-      int ready;
-      do {
-        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(ready) : "l"(flag) : "memory");
-        if (!ready) __nanosleep(64);
-      } while (!ready);
-    }
-    __syncthreads();
+    const volatile uint8_t* cp = w.step + e * w.tp + t;                // volatile: from L2, where the walk's store lands
+    while (!((code = *cp) & 0x80)) __nanosleep(100);
   }
-  if (!live) return;
-  const int code = __ldcg(w.code + e * w.tp + t);                      // written by another CTA of this kernel: not through L1
   const int j = code & 7;
   const float* tr = w.trig + e + (unsigned)(j * 4) * lu;               // candidate j, then candidate j + 1
   const A3TargetTrig tg{tr[0], *row(tr, 1, lu), *row(tr, 4, lu), *row(tr, 5, lu), *row(tr, 2, lu), *row(tr, 3, lu)};
   float goal[8], tm2, tm4, total;
-  a3_task_post(a.C, rec, mode, a3_cand(j, t1_0, t2_0, seq_len), a3_cand(j + 1, t1_0, t2_0, seq_len), (code >> 3) != 0,
+  a3_task_post(a.C, rec, mode, a3_cand(j, t1_0, t2_0, seq_len), a3_cand(j + 1, t1_0, t2_0, seq_len), (code & 8) != 0,
                SeqGlobal{a.sequence + e, ld}, &tg, goal, tm2, tm4, total);
   if (a.o.obs) {
     float* ob = a.o.obs + ((size_t)t * A3_NOBS + 33) * ld + e;
@@ -507,13 +496,12 @@ static int a3_step_impl(const OmModel* m, const OmA3Task* task, const float* qpo
   if (split) {
     constexpr int FB = 128;
     const int env_blocks = ceil_div(n, FB);
-    // layout: [records][start ints + heading table][candidate bytes][state codes][ticket + env-block flags]
+    // layout: [records][start ints + heading table][per-step bytes]
     const size_t feat_b = (size_t)n_steps * A3_NREC * (size_t)ld * sizeof(float);
     const size_t int_b = ((size_t)(2 + (A3_MAX_CAND + 1) * 4) * ld * sizeof(int32_t) + 15) / 16 * 16;   // byte arrays 16-B aligned
     const int tp_max = (n_steps + 15) / 16 * 16;
     const size_t byte_b = (size_t)tp_max * (size_t)ld;
-    const size_t byte_pad = (2 * byte_b + 15) / 16 * 16;
-    const size_t need = feat_b + int_b + byte_pad + (size_t)(1 + env_blocks) * sizeof(int);
+    const size_t need = feat_b + int_b + byte_b;
     OM_REQUIRE(env_blocks <= 65535, "om_a3_task_step: at most %d envs per multi-step call", 65535 * FB);
     if (task->scratch_bytes < need) {
       if (task->scratch) OM_CUDA_OK(cudaFree(task->scratch));  // synchronises: no earlier call still reads it
@@ -523,8 +511,8 @@ static int a3_step_impl(const OmModel* m, const OmA3Task* task, const float* qpo
       task->scratch_bytes = need;
     }
     char* base = (char*)task->scratch;
-    A3Scratch w{(float*)base, (uint8_t*)(base + feat_b + int_b), (uint8_t*)(base + feat_b + int_b + byte_b), 0,
-                (int32_t*)(base + feat_b), (float*)(base + feat_b) + 2 * (size_t)ld, (int*)(base + feat_b + int_b + byte_pad)};
+    A3Scratch w{(float*)base, (uint8_t*)(base + feat_b + int_b), 0,
+                (int32_t*)(base + feat_b), (float*)(base + feat_b) + 2 * (size_t)ld};
     // sub-calls no longer than the candidate bits cover (210 steps with the reference's 30 delay frames)
     const int max_call = a3_max_steps_per_call(task->C.delay_frames);
     for (int c0 = 0; c0 < n_steps; c0 += max_call) {
@@ -543,8 +531,7 @@ static int a3_step_impl(const OmModel* m, const OmA3Task* task, const float* qpo
       else if (g_knobs.a3_feat_minb == 4) a3_feat_kernel<FB, 4><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
       else a3_feat_kernel<FB, 5><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
       OM_LAUNCHED();
-      static_assert(FB == 128, "a3_walk_kernel publishes one flag per 128 envs");
-      OM_CUDA_OK(launch_pdl(a3_walk_kernel, dim3(env_blocks), dim3(FB), 0, st, sub, w, ncand));
+      OM_CUDA_OK(launch_pdl(a3_walk_kernel, dim3(ceil_div(n, 64)), dim3(64), 0, st, sub, w, ncand));
       OM_LAUNCHED();
       OM_CUDA_OK(launch_pdl(a3_post_kernel<FB>, dim3(env_blocks, len), dim3(FB), 0, st, sub, w));
       OM_LAUNCHED();

@@ -404,7 +404,8 @@ OM_HD A3TargetTrig a3_target_trig(const A3Targets& tc) {
 // t2_0, candidate j = min(t2_0 + j - 1, len - 1); t2 is always the next candidate.  The (env, t)-parallel pass
 // therefore evaluates "a foot is within target_radius of candidate j" for the first few candidates (one bit each),
 // and the recurrence shrinks to integer work on those bits: no geometry on the sequential path.
-constexpr int A3_MAX_CAND = 7;     // candidate bits 0..6 of the per-step byte; bit 7 flags a decision to re-take in float64
+constexpr int A3_MAX_CAND = 6;     // candidate bits 0..5 of the per-step byte; bit 6 flags a decision to re-take in float64,
+                                   // bit 7 marks the byte as rewritten by the sequential pass (om_a3.cu: A3Scratch::step)
 OM_HD int a3_cand(int j, int t1_0, int t2_0, int seq_len) {
   if (j == 0) return t1_0;
   const int k = t2_0 + j - 1;
