@@ -903,6 +903,20 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
                : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// Load without the wait: several loads in flight, then tmem_ld_wait() on each register set (the "+r" operands keep the
+// compiler from using the registers before the wait).
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
 
 template <bool KL>
 __global__ void __launch_bounds__(192, 2) disc_vail3_kernel(DiscArgs a) {
@@ -1126,7 +1140,25 @@ constexpr int V4_BCHUNKS = 2 + 8 + 8;
 constexpr int V4_ACHUNKS = 13;
 enum { V4_R1A = 0, V4_R1B, V4_R2, V4_R3A, V4_R3B, V4_NR };
 
-template <bool KL>
+//
+// Where the time goes (cycle counters in the MMA-issuing thread, 1 M samples = 56 tiles per CTA): 27.7 k cycles per tile,
+// of which 19.8 k issuing / blocked on a full MMA queue -- 216 M128 x N128 x K8 TF32 MMAs at 92 cycles each against 64
+// nominal, i.e. the pipe itself delivers the equivalent of 812 TFLOP/s, more than the 705-760 cuBLAS reaches on this
+// part -- 3.6 k waiting for A chunks (1.2 k of it for the next tile's input chunk, behind the heads), 3.2 k for the heads
+// to release the layer-1 blocks, 1.1 k for weights.  At 65536 samples a CTA has 3 or 4 tiles (512 tiles over 148 SMs:
+// 3.46 rounded up to 4 is 13.5 % lost to the tile count alone): 4 x 27.8 k cycles = 58 us of the 68-70 us call, the rest
+// is launch, prologue and the last tile's heads.  Measured and neutral (within the +-1.5 us between boxes): handing an A
+// chunk over one put() late so that its TMEM-store latency sits under the next chunk's arithmetic, four TMEM loads in
+// flight per block, requesting the first weight chunks and input rows ahead of the prologue -- all three are in the code.
+//
+// ROT (opt-in, om_debug_set("disc_vail2", 5); measured 1-2 % SLOWER: 70.2 us / 817 us against 69.9 / 802 -- the MMA pipe
+// then writes an accumulator block while the heads read the other two out of TMEM, and the heads, not the layer-1 MMAs,
+// are the longer side of that overlap): the three accumulator blocks change roles from tile to tile, (L1a/L3a, L1b/L3b, L2)(i + 1) = (L2, L1a/L3a, L1b/L3b)(i),
+// so that the next tile's layer 1 does not have to wait for this tile's heads: its first block goes into the block this
+// tile's layer 2 used (read out once A12 exists), its second block into the one head a has finished with, its layer 2 into
+// the one head b has finished with (h_done becomes two barriers), and the producers hand over the next tile's A0 BEFORE
+// they turn to the heads -- the MMA pipe runs the next tile's layer 1 under this tile's heads.
+template <bool KL, bool ROT>
 __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem;
@@ -1135,7 +1167,7 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
   float* s_inv = s_mean + DISC_IN;
   float* red = s_inv + DISC_IN;                                 // [2][128] partial head sums of the second warpgroup
   uint64_t* bars = reinterpret_cast<uint64_t*>(red + 256);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * V4_NSA + 2 * V4_NSB + V4_NR + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * V4_NSA + 2 * V4_NSB + V4_NR + 2);
   const float* b1 = par;
   const float* b2 = par + 256;
   const float* b3 = par + 384;            // per 128-row block h: [bmu[64h..64h+63], blv[64h..64h+63]]
@@ -1147,15 +1179,45 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
   auto b_full = [&](int s_) { return bar0 + 8u * (2 * V4_NSA + s_); };
   auto b_free = [&](int s_) { return bar0 + 8u * (2 * V4_NSA + V4_NSB + s_); };
   auto ready = [&](int k) { return bar0 + 8u * (2 * V4_NSA + 2 * V4_NSB + k); };
-  const uint32_t h_done = bar0 + 8u * (2 * V4_NSA + 2 * V4_NSB + V4_NR);
+  const uint32_t h_done = bar0 + 8u * (2 * V4_NSA + 2 * V4_NSB + V4_NR);       // head b (and, without ROT, head a) has read
+  const uint32_t h_done_a = h_done + 8u;                                       // ROT: head a has read its block
+  // accumulator blocks of tile `it`: P = layer-1 block a, then [mu; lv] block a; Q = the same for b; R = layer 2
+  auto acc_p = [&](int it_) { return ROT ? (uint32_t)(128 * ((3 - it_ % 3) % 3)) : (uint32_t)V4_ACC1A; };
+  auto acc_q = [&](int it_) { return ROT ? (uint32_t)(128 * ((4 - it_ % 3) % 3)) : (uint32_t)V4_ACC1B; };
+  auto acc_r = [&](int it_) { return ROT ? (uint32_t)(128 * ((5 - it_ % 3) % 3)) : (uint32_t)V4_ACC2; };
 
+  const int ntiles = (a.n + TILE - 1) / TILE;
+  int my_tiles = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) ++my_tiles;
+  // Prologue: the first weight chunks and the first input rows are requested BEFORE the parameter loads, the TMEM
+  // allocation and the CTA-wide barrier, so that their DRAM / L2 latency runs under those (at 65536 samples a CTA has only
+  // three or four tiles: every microsecond in front of the first MMA is 1.5 % of the call).
+  float xn[16];
+  if (warp < 8) {
+    const int half_ = warp >> 2, env_ = blockIdx.x * TILE + (tid & 127);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) xn[k] = env_ < a.n ? a.s[(size_t)(16 * half_ + k) * a.ld + env_] : 0.f;
+  }
+  int q_first = 0;                                                  // weight chunks already requested (copy thread only)
+  if (tid == 288) {
+    for (int s_ = 0; s_ < V4_NSB; ++s_) { mbar_init(b_full(s_), 1); mbar_init(b_free(s_), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int total = my_tiles * V4_BCHUNKS;
+    for (; q_first < V4_NSB && q_first < total; ++q_first) {
+      mbar_expect_tx(b_full(q_first), V4_STAGE_B);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.image) + (size_t)q_first * V4_STAGE_B;
+      const uint32_t dst = smem_u32(ring + q_first * V4_STAGE_B);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) bulk_g2s(dst + p * (V4_STAGE_B / 4), src + p * (V4_STAGE_B / 4), V4_STAGE_B / 4, b_full(q_first));
+    }
+  }
   for (int i = tid; i < V2_NPAR; i += 320) par[i] = a.params[i];
   if (tid < DISC_IN) { s_mean[tid] = a.mean[tid]; s_inv[tid] = 1.0f / a.stdv[tid]; }
   if (tid == 0) {
     for (int s_ = 0; s_ < V4_NSA; ++s_) { mbar_init(a_full(s_), 256); mbar_init(a_free(s_), 1); }
-    for (int s_ = 0; s_ < V4_NSB; ++s_) { mbar_init(b_full(s_), 1); mbar_init(b_free(s_), 1); }
     for (int k = 0; k < V4_NR; ++k) mbar_init(ready(k), 1);
     mbar_init(h_done, 256);
+    mbar_init(h_done_a, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -1163,15 +1225,12 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int ntiles = (a.n + TILE - 1) / TILE;
-  int my_tiles = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) ++my_tiles;
 
   if (warp == 9) {
     // ===================================================== weight-copy issuer: 18 chunks of 32 KB per tile, MMA order
     if (tid == 288) {
       const int total = my_tiles * V4_BCHUNKS;
-      for (int q = 0; q < total; ++q) {
+      for (int q = q_first; q < total; ++q) {
         const int st = q % V4_NSB, use = q / V4_NSB;
         if (use > 0) mbar_wait(b_free(st), (uint32_t)(use - 1) & 1u);
         mbar_expect_tx(b_full(st), V4_STAGE_B);
@@ -1212,24 +1271,29 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
         return sa;
       };
       for (int it = 0; it < my_tiles; ++it) {
-        if (it > 0) { mbar_wait(h_done, (uint32_t)(it - 1) & 1u); tc_fence_after(); }      // ACC1a / ACC1b have been read
+        const uint32_t P = acc_p(it), Q = acc_q(it), R = acc_r(it);
+        // without ROT: P and Q are what the previous tile's heads read.  With ROT: P is the previous tile's layer-2 block,
+        // read out before its last layer-3 chunk was issued; Q waits for head a, R for head b.
+        if (!ROT && it > 0) { mbar_wait(h_done, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
         int sa = next_a();                                              // A0 = x
-        mma_chunk(sa, V4_ACC1A, true);
+        mma_chunk(sa, P, true);
         umma_commit(ready(V4_R1A));
-        mma_chunk(sa, V4_ACC1B, true);
+        if (ROT && it > 0) { mbar_wait(h_done_a, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
+        mma_chunk(sa, Q, true);
         umma_commit(a_free(sa)); ++ga;
         umma_commit(ready(V4_R1B));
+        if (ROT && it > 0) { mbar_wait(h_done, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
         for (int c = 0; c < 8; ++c) {                                   // A1..A8 -> layer 2
           sa = next_a();
-          mma_chunk(sa, V4_ACC2, c == 0);
+          mma_chunk(sa, R, c == 0);
           umma_commit(a_free(sa)); ++ga;
         }
         umma_commit(ready(V4_R2));
-        for (int c = 0; c < 4; ++c) {                                   // A9..A12 -> [mu; lv] blocks 0 and 1
+        for (int c = 0; c < 4; ++c) {                                   // A9..A12 -> [mu; lv] blocks a and b
           sa = next_a();
-          mma_chunk(sa, V4_ACC1A, c == 0);
+          mma_chunk(sa, P, c == 0);
           if (c == 3) umma_commit(ready(V4_R3A));
-          mma_chunk(sa, V4_ACC1B, c == 0);
+          mma_chunk(sa, Q, c == 0);
           umma_commit(a_free(sa)); ++ga;
         }
         umma_commit(ready(V4_R3B));
@@ -1241,18 +1305,47 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float bd = par[V2_NPAR - 1];
     int ga = 0;
+    // A chunk is handed over in two steps: put() splits it and issues the TMEM stores; publish() -- wait for the stores,
+    // arrive on a_full -- is made by the NEXT put() after its own split, so the store latency sits under that arithmetic
+    // instead of in front of the MMA (per-chunk producer latency, not the MMA pipe, bounded this kernel: 13 chunks x
+    // ~0.8 us against 7 us of MMA per tile).  publish() must be called by hand before waiting on anything the pending chunk
+    // feeds (an accumulator-complete barrier of its own layer).
+    int pending = -1;
+    auto publish = [&]() {
+      if (pending >= 0) {
+        tmem_wait_st();
+        tc_fence_before();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_full(pending)) : "memory");
+        pending = -1;
+      }
+    };
     auto put = [&](const float (&act_in)[16]) {                        // this thread's 16 of the chunk's 32 columns
       float hi[16], lo[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) { hi[i] = tf32_rna(act_in[i]); lo[i] = act_in[i] - hi[i]; }
+      publish();
       if (ga >= V4_NSA) { mbar_wait(a_free(ga % V4_NSA), (uint32_t)(ga / V4_NSA - 1) & 1u); tc_fence_after(); }
       const uint32_t at = lane_addr + V4_AR + (ga % V4_NSA) * 64 + 16 * half;
       tmem_st16(at, hi);
       tmem_st16(at + 32, lo);
-      tmem_wait_st();
-      tc_fence_before();
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_full(ga % V4_NSA)) : "memory");
+      pending = ga % V4_NSA;
       ++ga;
+    };
+    // four chunks out of one accumulator block: all four loads in flight, then bias + relu + put chunk by chunk
+    auto put_block = [&](uint32_t acc, const float* bias) {
+      uint32_t r[4][16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16_nowait(lane_addr + acc + c * V4_KC + 16 * half, r[c]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_wait(r[c]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float h[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) h[i] = __uint_as_float(r[c][i]);
+        bias_relu16(h, bias + c * V4_KC + 16 * half);
+        put(h);
+      }
     };
     auto wait_ready = [&](int k, int it) { mbar_wait(ready(k), (uint32_t)it & 1u); tc_fence_after(); };
     auto load_row = [&](int tile_, float (&raw)[16]) {
@@ -1260,38 +1353,36 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
 #pragma unroll
       for (int k = 0; k < 16; ++k) raw[k] = (tile_ < ntiles && env_ < a.n) ? a.s[(size_t)(16 * half + k) * a.ld + env_] : 0.f;
     };
-    float xn[16];
-    load_row(blockIdx.x, xn);
+    auto put_input = [&](int tile_) {                                   // A0 of tile_ from the prefetched row
+      const bool live_ = tile_ * TILE + row < a.n;
+      float x[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) x[k] = live_ ? (xn[k] - s_mean[16 * half + k]) * s_inv[16 * half + k] : 0.f;
+      put(x);
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int env = tile * TILE + row;
       const bool live = env < a.n;
-      {
-        float x[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = live ? (xn[k] - s_mean[16 * half + k]) * s_inv[16 * half + k] : 0.f;
-        put(x);                                                         // A0
+      const uint32_t P = acc_p(it), Q = acc_q(it), R = acc_r(it);
+      if (!ROT || it == 0) {
+        put_input(tile);                                                // A0
+        publish();
+        load_row(tile + gridDim.x, xn);
       }
-      load_row(tile + gridDim.x, xn);
 #pragma unroll 1
       for (int blk = 0; blk < 2; ++blk) {                               // A1..A8: relu(layer 1 + b1)
-        wait_ready(blk == 0 ? V4_R1A : V4_R1B, it);
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          float h[16];
-          tmem_ld16(lane_addr + (blk == 0 ? V4_ACC1A : V4_ACC1B) + c * V4_KC + 16 * half, h);
-          bias_relu16(h, b1 + blk * 128 + c * V4_KC + 16 * half);
-          put(h);
-        }
+        wait_ready(blk == 0 ? V4_R1A : V4_R1B, it);                     // (A4 may be pending here: R1B does not need it)
+        put_block(blk == 0 ? P : Q, b1 + blk * 128);
       }
+      publish();                                                        // A8: layer 2 cannot complete without it
       wait_ready(V4_R2, it);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {                                     // A9..A12: relu(layer 2 + b2)
-        float h[16];
-        tmem_ld16(lane_addr + V4_ACC2 + c * V4_KC + 16 * half, h);
-        bias_relu16(h, b2 + c * V4_KC + 16 * half);
-        put(h);
+      put_block(R, b2);                                                 // A9..A12: relu(layer 2 + b2)
+      if (ROT && tile + (int)gridDim.x < ntiles) {                      // the next tile's A0, ahead of this tile's heads
+        put_input(tile + gridDim.x);
+        load_row(tile + 2 * gridDim.x, xn);
       }
+      publish();                                                        // A12 (or the next A0)
       float dval = 0.f, klv = 0.f;
 #pragma unroll 1
       for (int hb = 0; hb < 2; ++hb) {                                  // heads: this thread's 32 of the block's 64 latents
@@ -1299,10 +1390,14 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) e[i] = (a.eps && live) ? a.eps[(size_t)(64 * hb + 32 * half + i) * a.ld + env] : 0.f;
         wait_ready(hb == 0 ? V4_R3A : V4_R3B, it);
-        const uint32_t acc = lane_addr + (hb == 0 ? V4_ACC1A : V4_ACC1B);
+        const uint32_t acc = lane_addr + (hb == 0 ? P : Q);
         float mu[32], lv[32];
         tmem_ld32(acc + 32 * half, mu);
         tmem_ld32(acc + 64 + 32 * half, lv);
+        if (ROT && hb == 0) {                                           // block P has been read (tmem_ld32 waits for its data)
+          tc_fence_before();
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(h_done_a) : "memory");
+        }
         const float4* bm4 = reinterpret_cast<const float4*>(b3 + 128 * hb + 32 * half);
         const float4* bl4 = reinterpret_cast<const float4*>(b3 + 128 * hb + 64 + 32 * half);
         const float4* wv4 = reinterpret_cast<const float4*>(wd + 64 * hb + 32 * half);
@@ -1583,13 +1678,15 @@ extern "C" int om_disc_forward(const OmDisc* h, const float* s, const float* mea
   // VAIL default: disc_vail4_kernel (one CTA per SM, A operand in TMEM): 69 us at 65536 samples / 796 us at 1 M against 74 /
   // 815 for the two-CTA shared-memory kernel (knob 1), 82 / 975 for the two-CTA TMEM kernel (knob 3), 72 / 841 for the
   // two-producer-group shared-memory kernel (knob 0)
-  if (h->sh.kind == 0 && (g_knobs.disc_vail2 == 4 || g_knobs.disc_vail2 < 0)) {
+  if (h->sh.kind == 0 && (g_knobs.disc_vail2 == 4 || g_knobs.disc_vail2 == 5 || g_knobs.disc_vail2 < 0)) {
     const size_t smem4 = V4_NSB * V4_STAGE_B + (V2_NPAR + 3 + 2 * DISC_IN + 256) * sizeof(float) +
-                         (2 * V4_NSA + 2 * V4_NSB + V4_NR + 1) * 8 + 16;
+                         (2 * V4_NSA + 2 * V4_NSB + V4_NR + 2) * 8 + 16;
+    const bool rot = g_knobs.disc_vail2 == 5;
     DiscArgs a4 = a;
     a4.image = h->image4;
     a4.params = h->params2;
-    auto kern = kl_out ? disc_vail4_kernel<true> : disc_vail4_kernel<false>;
+    auto kern = rot ? (kl_out ? disc_vail4_kernel<true, true> : disc_vail4_kernel<false, true>)
+                    : (kl_out ? disc_vail4_kernel<true, false> : disc_vail4_kernel<false, false>);
     OM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
     kern<<<grid, 320, smem4, st>>>(a4);
     OM_LAUNCHED();
