@@ -1242,61 +1242,79 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
     }
   } else if (warp == 8) {
     // ===================================================== MMA issuer
+    // One thread issues 216 MMAs per tile, and its own instruction stream is what paces them if it is not kept short: a
+    // back-to-back M128 x N128 x K8 TF32 MMA takes 64 cycles (tools/micro/umma_rate.cu, SS and TS alike), but with the
+    // stage index a run-time value every shared-memory descriptor cost four dependent uniform-datapath instructions and
+    // an MMA went out every 92 cycles.  18 weight chunks per tile is a multiple of the six stages, so with the tile body
+    // unrolled the stage of every chunk is a compile-time constant and a descriptor is ONE add: (ring address >> 4) +
+    // (constant offset | the constant leading-byte-offset field); the A chunks alternate between two TMEM stages whose
+    // order flips from tile to tile (13 chunks per tile), kept as two registers that are swapped.
     if (tid == 256) {
+      static_assert(V4_BCHUNKS % V4_NSB == 0 && V4_ACHUNKS % V4_NSA == 1, "stage bookkeeping of the unrolled tile body");
       const uint32_t idesc = idesc_tf32(TILE, 128);
-      const uint32_t lbo = 128 * 16, sbo = 128;
-      int ga = 0, qb = 0;
-      // one B chunk against the A chunk in stage sa: 4 k-steps x (lo.hi, hi.lo, hi.hi)
-      auto mma_chunk = [&](int sa, uint32_t d_col, bool first) {
-        const int sb = qb % V4_NSB;
-        mbar_wait(b_full(sb), (uint32_t)(qb / V4_NSB) & 1u);
-        tc_fence_after();
-        const uint32_t a_hi = tmem + V4_AR + sa * 64, a_lo = a_hi + 32;
-        const uint32_t b_hi = smem_u32(ring + sb * V4_STAGE_B), b_lo = b_hi + V4_STAGE_B / 2;
-#pragma unroll
-        for (int j = 0; j < V4_KC / 8; ++j) {
-          const uint32_t o = (uint32_t)j * 2 * lbo;
-          const uint64_t dbh = smem_desc(b_hi + o, lbo, sbo), dbl = smem_desc(b_lo + o, lbo, sbo);
-          umma_tf32_ts(tmem + d_col, a_lo + 8 * j, dbh, idesc, (first && j == 0) ? 0u : 1u);
-          umma_tf32_ts(tmem + d_col, a_hi + 8 * j, dbl, idesc, 1u);
-          umma_tf32_ts(tmem + d_col, a_hi + 8 * j, dbh, idesc, 1u);
-        }
-        umma_commit(b_free(sb));
-        ++qb;
-      };
-      auto next_a = [&]() {
-        const int sa = ga % V4_NSA;
-        mbar_wait(a_full(sa), (uint32_t)(ga / V4_NSA) & 1u);
-        tc_fence_after();
-        return sa;
-      };
+      constexpr uint32_t LBO16 = 128, SBO16 = 8;                        // 2048 B and 128 B in 16-byte units
+      constexpr uint32_t DESC_HI = SBO16 | (1u << 14);                  // bits 32..45 stride byte offset, bit 46 version 1
+      const uint32_t ring16 = smem_u32(ring) >> 4;                      // < 2^14: the address field cannot overflow
+      auto bdesc = [&](uint32_t off16) { return ((uint64_t)DESC_HI << 32) | (uint64_t)(ring16 + (off16 + (LBO16 << 16))); };
+      uint32_t a_st[2] = {tmem + V4_AR, tmem + V4_AR + 64};             // TMEM stage of this tile's even / odd A chunks
+      uint32_t a_fu[2] = {a_full(0), a_full(1)}, a_fr[2] = {a_free(0), a_free(1)};
+      int ga = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        const uint32_t P = acc_p(it), Q = acc_q(it), R = acc_r(it);
+        const uint32_t P = tmem + acc_p(it), Q = tmem + acc_q(it), R = tmem + acc_r(it);
+        const uint32_t itp = (uint32_t)it & 1u;
+        // B chunk q of the tile (stage q % 6, its (3 it + q / 6)-th use) against the A chunk in TMEM stage `ab`:
+        // 4 k-steps x (lo.hi, hi.lo, hi.hi)
+        auto mma_chunk = [&](int q, uint32_t ab, uint32_t d, bool first) {
+          const int sb = q % V4_NSB;
+          mbar_wait(b_full(sb), (itp ^ (uint32_t)(q / V4_NSB)) & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int j = 0; j < V4_KC / 8; ++j) {
+            const uint64_t dbh = bdesc((uint32_t)(sb * (V4_STAGE_B / 16) + j * 2 * LBO16));
+            const uint64_t dbl = bdesc((uint32_t)(sb * (V4_STAGE_B / 16) + V4_STAGE_B / 32 + j * 2 * LBO16));
+            umma_tf32_ts(d, ab + 32 + 8 * j, dbh, idesc, (first && j == 0) ? 0u : 1u);
+            umma_tf32_ts(d, ab + 8 * j, dbl, idesc, 1u);
+            umma_tf32_ts(d, ab + 8 * j, dbh, idesc, 1u);
+          }
+          umma_commit(b_free(sb));
+        };
+        auto next_a = [&](int k) {                                      // A chunk k of the tile: wait, return its TMEM stage
+          mbar_wait(a_fu[k & 1], (uint32_t)(ga >> 1) & 1u);
+          tc_fence_after();
+          ++ga;
+          return a_st[k & 1];
+        };
         // without ROT: P and Q are what the previous tile's heads read.  With ROT: P is the previous tile's layer-2 block,
         // read out before its last layer-3 chunk was issued; Q waits for head a, R for head b.
         if (!ROT && it > 0) { mbar_wait(h_done, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
-        int sa = next_a();                                              // A0 = x
-        mma_chunk(sa, P, true);
+        uint32_t ab = next_a(0);                                        // A0 = x
+        mma_chunk(0, ab, P, true);
         umma_commit(ready(V4_R1A));
         if (ROT && it > 0) { mbar_wait(h_done_a, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
-        mma_chunk(sa, Q, true);
-        umma_commit(a_free(sa)); ++ga;
+        mma_chunk(1, ab, Q, true);
+        umma_commit(a_fr[0]);
         umma_commit(ready(V4_R1B));
         if (ROT && it > 0) { mbar_wait(h_done, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
+#pragma unroll
         for (int c = 0; c < 8; ++c) {                                   // A1..A8 -> layer 2
-          sa = next_a();
-          mma_chunk(sa, R, c == 0);
-          umma_commit(a_free(sa)); ++ga;
+          ab = next_a(1 + c);
+          mma_chunk(2 + c, ab, R, c == 0);
+          umma_commit(a_fr[(1 + c) & 1]);
         }
         umma_commit(ready(V4_R2));
+#pragma unroll
         for (int c = 0; c < 4; ++c) {                                   // A9..A12 -> [mu; lv] blocks a and b
-          sa = next_a();
-          mma_chunk(sa, P, c == 0);
+          ab = next_a(9 + c);
+          mma_chunk(10 + 2 * c, ab, P, c == 0);
           if (c == 3) umma_commit(ready(V4_R3A));
-          mma_chunk(sa, Q, c == 0);
-          umma_commit(a_free(sa)); ++ga;
+          mma_chunk(11 + 2 * c, ab, Q, c == 0);
+          umma_commit(a_fr[(9 + c) & 1]);
         }
         umma_commit(ready(V4_R3B));
+        // 13 A chunks per tile: the next tile's even chunks live in the other stage
+        { const uint32_t t_ = a_st[0]; a_st[0] = a_st[1]; a_st[1] = t_; }
+        { const uint32_t t_ = a_fu[0]; a_fu[0] = a_fu[1]; a_fu[1] = t_; }
+        { const uint32_t t_ = a_fr[0]; a_fr[0] = a_fr[1]; a_fr[1] = t_; }
       }
     }
   } else {
