@@ -1141,24 +1141,30 @@ constexpr int V4_ACHUNKS = 13;
 enum { V4_R1A = 0, V4_R1B, V4_R2, V4_R3A, V4_R3B, V4_NR };
 
 //
-// Where the time goes (cycle counters in the MMA-issuing thread, 1 M samples = 56 tiles per CTA): 27.7 k cycles per tile,
-// of which 19.8 k issuing / blocked on a full MMA queue -- 216 M128 x N128 x K8 TF32 MMAs at 92 cycles each against 64
-// nominal, i.e. the pipe itself delivers the equivalent of 812 TFLOP/s, more than the 705-760 cuBLAS reaches on this
-// part -- 3.6 k waiting for A chunks (1.2 k of it for the next tile's input chunk, behind the heads), 3.2 k for the heads
-// to release the layer-1 blocks, 1.1 k for weights.  At 65536 samples a CTA has 3 or 4 tiles (512 tiles over 148 SMs:
-// 3.46 rounded up to 4 is 13.5 % lost to the tile count alone): 4 x 27.8 k cycles = 58 us of the 68-70 us call, the rest
-// is launch, prologue and the last tile's heads.  Measured and neutral (within the +-1.5 us between boxes): handing an A
-// chunk over one put() late so that its TMEM-store latency sits under the next chunk's arithmetic, four TMEM loads in
-// flight per block, requesting the first weight chunks and input rows ahead of the prologue -- all three are in the code.
+// Where the time goes at 1 M samples (56 tiles per CTA; clock counters in the MMA-issuing thread and in a producer thread,
+// experiments that are not in the tree).  (a) The issuing thread itself paced the MMAs until its tile body was unrolled
+// (see the MMA issuer below): 27.7 k -> 23 k cycles per tile, 802 -> 720 us, 69 -> 64 us at 65536 samples.  (b) A tile's
+// timeline as a producer thread sees it: layer 1 complete at 1.7 k cycles, layer 2 at 11.2 k (8 chunks in 9.5 k cycles
+// against 6.1 k of MMA: the hand-over chain MMA-commit -> a_free -> tcgen05.st -> wait::st -> a_full -> issue of a two-stage
+// ring is longer than one chunk's 768 MMA cycles), layer 3 at 18.2 / 21.6 k (MMA-bound: two weight chunks per A chunk),
+// heads + output until 24.7 k.  216 MMAs are 13.8 k cycles: the pipe is busy 60 % of a tile.  (c) At 65536 samples a CTA
+// has 3 or 4 tiles (512 tiles over 148 SMs: 3.46 rounded up to 4 is 13.5 % lost to the tile count alone): 4 x 23 k cycles
+// = 48 us of the 64 us call, the rest is launch, prologue and the last tile's heads.
+// Measured against that, all parity-green, none faster: handing an A chunk over one put() late so that its TMEM-store
+// latency sits under the next chunk's arithmetic, four TMEM loads in flight per block, the first weight chunks and input
+// rows requested ahead of the prologue (neutral, kept); ROT = 1 / 2 below (next tile's layer 1 under this tile's heads:
+// 1-4 % slower -- the same threads must produce the next tile's A chunks after the heads, and its input chunk queues
+// for a ring stage in front of the heads); and a third warpgroup that does nothing but heads, with layer-1 block b
+// issued after the first half of layer 2 so that nothing early waits for them (448 threads at 128 registers: 80 us / 832
+// us -- the heads then compete with the producers for issue slots, and the producers' hand-over chain is what bounds
+// layer 2).  What would help is a deeper A ring, and tensor memory has no columns left for one.
 //
-// ROT (opt-in, om_debug_set("disc_vail2", 5); measured 1-2 % SLOWER: 70.2 us / 817 us against 69.9 / 802 -- the MMA pipe
-// then writes an accumulator block while the heads read the other two out of TMEM, and the heads, not the layer-1 MMAs,
-// are the longer side of that overlap): the three accumulator blocks change roles from tile to tile, (L1a/L3a, L1b/L3b, L2)(i + 1) = (L2, L1a/L3a, L1b/L3b)(i),
-// so that the next tile's layer 1 does not have to wait for this tile's heads: its first block goes into the block this
-// tile's layer 2 used (read out once A12 exists), its second block into the one head a has finished with, its layer 2 into
-// the one head b has finished with (h_done becomes two barriers), and the producers hand over the next tile's A0 BEFORE
-// they turn to the heads -- the MMA pipe runs the next tile's layer 1 under this tile's heads.
-template <bool KL, bool ROT>
+// ROT (opt-in through om_debug_set("disc_vail2", 6 / 5)): 1 = the next tile's input chunk is handed over before the
+// heads and the two layer-1 blocks are released one by one (h_done_a after head a's loads, h_done after head b's);
+// 2 = the three accumulator blocks change roles from tile to tile instead, (L1a/L3a, L1b/L3b, L2)(i + 1) = (L2, L1a/L3a,
+// L1b/L3b)(i): the next tile's first layer-1 block goes into the block this tile's layer 2 used (read out once A12
+// exists), its second into the one head a has finished with, its layer 2 into the one head b has finished with.
+template <bool KL, int ROT>
 __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem;
@@ -1182,9 +1188,9 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
   const uint32_t h_done = bar0 + 8u * (2 * V4_NSA + 2 * V4_NSB + V4_NR);       // head b (and, without ROT, head a) has read
   const uint32_t h_done_a = h_done + 8u;                                       // ROT: head a has read its block
   // accumulator blocks of tile `it`: P = layer-1 block a, then [mu; lv] block a; Q = the same for b; R = layer 2
-  auto acc_p = [&](int it_) { return ROT ? (uint32_t)(128 * ((3 - it_ % 3) % 3)) : (uint32_t)V4_ACC1A; };
-  auto acc_q = [&](int it_) { return ROT ? (uint32_t)(128 * ((4 - it_ % 3) % 3)) : (uint32_t)V4_ACC1B; };
-  auto acc_r = [&](int it_) { return ROT ? (uint32_t)(128 * ((5 - it_ % 3) % 3)) : (uint32_t)V4_ACC2; };
+  auto acc_p = [&](int it_) { return ROT == 2 ? (uint32_t)(128 * ((3 - it_ % 3) % 3)) : (uint32_t)V4_ACC1A; };
+  auto acc_q = [&](int it_) { return ROT == 2 ? (uint32_t)(128 * ((4 - it_ % 3) % 3)) : (uint32_t)V4_ACC1B; };
+  auto acc_r = [&](int it_) { return ROT == 2 ? (uint32_t)(128 * ((5 - it_ % 3) % 3)) : (uint32_t)V4_ACC2; };
 
   const int ntiles = (a.n + TILE - 1) / TILE;
   int my_tiles = 0;
@@ -1286,15 +1292,21 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
         };
         // without ROT: P and Q are what the previous tile's heads read.  With ROT: P is the previous tile's layer-2 block,
         // read out before its last layer-3 chunk was issued; Q waits for head a, R for head b.
-        if (!ROT && it > 0) { mbar_wait(h_done, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
+        // ROT 0: P and Q are what the previous tile's heads read, both released by h_done.
+        // ROT 1: the same blocks, released one by one -- P by head a (h_done_a), Q by head b (h_done).
+        // ROT 2: P is the previous tile's layer-2 block, read out before its last layer-3 chunk was issued; Q waits for
+        //        head a, R for head b.
+        if (ROT == 0 && it > 0) { mbar_wait(h_done, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
+        if (ROT == 1 && it > 0) { mbar_wait(h_done_a, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
         uint32_t ab = next_a(0);                                        // A0 = x
         mma_chunk(0, ab, P, true);
         umma_commit(ready(V4_R1A));
-        if (ROT && it > 0) { mbar_wait(h_done_a, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
+        if (ROT == 2 && it > 0) { mbar_wait(h_done_a, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
+        if (ROT == 1 && it > 0) { mbar_wait(h_done, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
         mma_chunk(1, ab, Q, true);
         umma_commit(a_fr[0]);
         umma_commit(ready(V4_R1B));
-        if (ROT && it > 0) { mbar_wait(h_done, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
+        if (ROT == 2 && it > 0) { mbar_wait(h_done, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {                                   // A1..A8 -> layer 2
           ab = next_a(1 + c);
@@ -1696,15 +1708,16 @@ extern "C" int om_disc_forward(const OmDisc* h, const float* s, const float* mea
   // VAIL default: disc_vail4_kernel (one CTA per SM, A operand in TMEM): 69 us at 65536 samples / 796 us at 1 M against 74 /
   // 815 for the two-CTA shared-memory kernel (knob 1), 82 / 975 for the two-CTA TMEM kernel (knob 3), 72 / 841 for the
   // two-producer-group shared-memory kernel (knob 0)
-  if (h->sh.kind == 0 && (g_knobs.disc_vail2 == 4 || g_knobs.disc_vail2 == 5 || g_knobs.disc_vail2 < 0)) {
+  if (h->sh.kind == 0 && (g_knobs.disc_vail2 == 4 || g_knobs.disc_vail2 == 5 || g_knobs.disc_vail2 == 6 || g_knobs.disc_vail2 < 0)) {
     const size_t smem4 = V4_NSB * V4_STAGE_B + (V2_NPAR + 3 + 2 * DISC_IN + 256) * sizeof(float) +
                          (2 * V4_NSA + 2 * V4_NSB + V4_NR + 2) * 8 + 16;
-    const bool rot = g_knobs.disc_vail2 == 5;
+    const int rot = g_knobs.disc_vail2 == 5 ? 2 : g_knobs.disc_vail2 == 6 ? 1 : 0;
     DiscArgs a4 = a;
     a4.image = h->image4;
     a4.params = h->params2;
-    auto kern = rot ? (kl_out ? disc_vail4_kernel<true, true> : disc_vail4_kernel<false, true>)
-                    : (kl_out ? disc_vail4_kernel<true, false> : disc_vail4_kernel<false, false>);
+    auto kern = rot == 2 ? (kl_out ? disc_vail4_kernel<true, 2> : disc_vail4_kernel<false, 2>)
+              : rot == 1 ? (kl_out ? disc_vail4_kernel<true, 1> : disc_vail4_kernel<false, 1>)
+                         : (kl_out ? disc_vail4_kernel<true, 0> : disc_vail4_kernel<false, 0>);
     OM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
     kern<<<grid, 320, smem4, st>>>(a4);
     OM_LAUNCHED();
