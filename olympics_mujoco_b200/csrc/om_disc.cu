@@ -53,6 +53,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// One lane of a CONVERGED warp.  The MMA-issuing code is entered through this rather than through `tid == ...`: ptxas then
+// knows that a single thread executes it and emits the tcgen05.mma instructions back to back; behind a thread-index test it
+// wraps every one of them in a five-instruction elect / vote loop, and at ~70 cycles of issue per 64-cycle MMA the issuing
+// thread, not the tensor pipe, paced the N = 128 kernels.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -241,7 +250,7 @@ __global__ void __launch_bounds__(192, 1) disc_reward_kernel(DiscArgs a) {
     }
   } else if (warp == 4) {
     // ===================================================== MMA issuer
-    if (tid == 128) {
+    if (elect_one_sync()) {
       int ga = 0, qb = 0;
       auto mma_chunk = [&](int rows, uint32_t d_col, bool first) {
         const int sa = ga & 1;
@@ -483,7 +492,7 @@ __global__ void __launch_bounds__(320, 1) disc_reward_pg2_kernel(DiscArgs a) {
     }
   } else if (warp == 8) {
     // ===================================================== MMA issuer (as in disc_reward_kernel)
-    if (tid == 256) {
+    if (elect_one_sync()) {
       int ga = 0, qb = 0;
       auto mma_chunk = [&](int rows, uint32_t d_col, bool first) {
         const int sa = ga & 1;
@@ -711,7 +720,7 @@ __global__ void __launch_bounds__(192, 2) disc_vail2_kernel(DiscArgs a) {
     }
   } else if (warp == 4) {
     // ===================================================== MMA issuer
-    if (tid == 128) {
+    if (elect_one_sync()) {
       const uint32_t idesc = idesc_tf32(TILE, V2_ROWS);
       const uint32_t lbo = TILE * 16, sbo = 128;                  // A and B both have 128 rows
       for (int g = 0; g < total_chunks; ++g) {
@@ -975,7 +984,7 @@ __global__ void __launch_bounds__(192, 2) disc_vail3_kernel(DiscArgs a) {
     }
   } else if (warp == 4) {
     // ===================================================== MMA issuer
-    if (tid == 128) {
+    if (elect_one_sync()) {
       int c = 0;
       for (int g = 0; g < total_chunks; ++g) {
         const int sa = g % V3_NSA, sb = g % V3_NSB;
@@ -1187,6 +1196,8 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
   auto ready = [&](int k) { return bar0 + 8u * (2 * V4_NSA + 2 * V4_NSB + k); };
   const uint32_t h_done = bar0 + 8u * (2 * V4_NSA + 2 * V4_NSB + V4_NR);       // head b (and, without ROT, head a) has read
   const uint32_t h_done_a = h_done + 8u;                                       // ROT: head a has read its block
+  constexpr bool EARLY = ROT == 1 || ROT == 2;     // the next tile's input chunk is handed over before this tile's heads
+  constexpr bool ALT = ROT == 3;                   // the two producer warpgroups take alternate A chunks (one ring stage each)
   // accumulator blocks of tile `it`: P = layer-1 block a, then [mu; lv] block a; Q = the same for b; R = layer 2
   auto acc_p = [&](int it_) { return ROT == 2 ? (uint32_t)(128 * ((3 - it_ % 3) % 3)) : (uint32_t)V4_ACC1A; };
   auto acc_q = [&](int it_) { return ROT == 2 ? (uint32_t)(128 * ((4 - it_ % 3) % 3)) : (uint32_t)V4_ACC1B; };
@@ -1198,11 +1209,18 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
   // Prologue: the first weight chunks and the first input rows are requested BEFORE the parameter loads, the TMEM
   // allocation and the CTA-wide barrier, so that their DRAM / L2 latency runs under those (at 65536 samples a CTA has only
   // three or four tiles: every microsecond in front of the first MMA is 1.5 % of the call).
-  float xn[16];
+  float xn[ALT ? 32 : 16];
   if (warp < 8) {
-    const int half_ = warp >> 2, env_ = blockIdx.x * TILE + (tid & 127);
+    const int half_ = warp >> 2;
+    if (ALT) {                                      // warpgroup h hands over the input chunk of tiles h, h + 2, ...: whole rows
+      const int tile_ = blockIdx.x + half_ * gridDim.x, env_ = tile_ * TILE + (tid & 127);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) xn[k] = env_ < a.n ? a.s[(size_t)(16 * half_ + k) * a.ld + env_] : 0.f;
+      for (int k = 0; k < (ALT ? 32 : 0); ++k) xn[k] = (tile_ < ntiles && env_ < a.n) ? a.s[(size_t)k * a.ld + env_] : 0.f;
+    } else {
+      const int env_ = blockIdx.x * TILE + (tid & 127);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) xn[k] = env_ < a.n ? a.s[(size_t)(16 * half_ + k) * a.ld + env_] : 0.f;
+    }
   }
   int q_first = 0;                                                  // weight chunks already requested (copy thread only)
   if (tid == 288) {
@@ -1220,7 +1238,7 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
   for (int i = tid; i < V2_NPAR; i += 320) par[i] = a.params[i];
   if (tid < DISC_IN) { s_mean[tid] = a.mean[tid]; s_inv[tid] = 1.0f / a.stdv[tid]; }
   if (tid == 0) {
-    for (int s_ = 0; s_ < V4_NSA; ++s_) { mbar_init(a_full(s_), 256); mbar_init(a_free(s_), 1); }
+    for (int s_ = 0; s_ < V4_NSA; ++s_) { mbar_init(a_full(s_), ALT ? 128 : 256); mbar_init(a_free(s_), 1); }
     for (int k = 0; k < V4_NR; ++k) mbar_init(ready(k), 1);
     mbar_init(h_done, 256);
     mbar_init(h_done_a, 256);
@@ -1255,7 +1273,7 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
     // unrolled the stage of every chunk is a compile-time constant and a descriptor is ONE add: (ring address >> 4) +
     // (constant offset | the constant leading-byte-offset field); the A chunks alternate between two TMEM stages whose
     // order flips from tile to tile (13 chunks per tile), kept as two registers that are swapped.
-    if (tid == 256) {
+    if (elect_one_sync()) {
       static_assert(V4_BCHUNKS % V4_NSB == 0 && V4_ACHUNKS % V4_NSA == 1, "stage bookkeeping of the unrolled tile body");
       const uint32_t idesc = idesc_tf32(TILE, 128);
       constexpr uint32_t LBO16 = 128, SBO16 = 8;                        // 2048 B and 128 B in 16-byte units
@@ -1296,7 +1314,7 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
         // ROT 1: the same blocks, released one by one -- P by head a (h_done_a), Q by head b (h_done).
         // ROT 2: P is the previous tile's layer-2 block, read out before its last layer-3 chunk was issued; Q waits for
         //        head a, R for head b.
-        if (ROT == 0 && it > 0) { mbar_wait(h_done, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
+        if ((ROT == 0 || ROT == 3) && it > 0) { mbar_wait(h_done, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
         if (ROT == 1 && it > 0) { mbar_wait(h_done_a, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
         uint32_t ab = next_a(0);                                        // A0 = x
         mma_chunk(0, ab, P, true);
@@ -1395,7 +1413,56 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
       const int env = tile * TILE + row;
       const bool live = env < a.n;
       const uint32_t P = acc_p(it), Q = acc_q(it), R = acc_r(it);
-      if (!ROT || it == 0) {
+      if constexpr (ALT) {
+        // Chunk k of the tile is the (13 it + k)-th of the kernel and lives in ring stage (13 it + k) & 1: warpgroup `half`
+        // produces the chunks of stage `half`, all 32 columns of its row -- every second chunk, so that it has TWO chunks'
+        // MMA time for the hand-over chain (a_free -> tcgen05.st -> wait::st -> a_full) that bounds layer 2 when both
+        // warpgroups work on every chunk.
+        const int par = (half + it) & 1;                                // this tile: k = par, par + 2, ...
+        auto put32 = [&](const float (&act)[32]) {
+          if (ga > 0) { mbar_wait(a_free(half), (uint32_t)(ga - 1) & 1u); tc_fence_after(); }   // ga: this stage's uses
+          const uint32_t at = lane_addr + V4_AR + half * 64;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            float hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { hi[i] = tf32_rna(act[16 * g + i]); lo[i] = act[16 * g + i] - hi[i]; }
+            tmem_st16(at + 16 * g, hi);
+            tmem_st16(at + 32 + 16 * g, lo);
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_full(half)) : "memory");
+          ++ga;
+        };
+        if (par == 0) {                                                 // k = 0: the input chunk
+          float x[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) x[k] = live ? (xn[k % (ALT ? 32 : 16)] - s_mean[k]) * s_inv[k] : 0.f;
+          put32(x);
+          const int tile_ = tile + 2 * (int)gridDim.x, env_ = tile_ * TILE + row;   // this warpgroup's next input chunk
+#pragma unroll
+          for (int k = 0; k < (ALT ? 32 : 0); ++k) xn[k] = (tile_ < ntiles && env_ < a.n) ? a.s[(size_t)k * a.ld + env_] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {                                   // k = 2 j + 1 (par = 1) or 2 j + 2 (par = 0)
+          const int blk = j >> 1;                                       // 0: layer-1 block a, 1: block b, 2: layer 2
+          const int c = 2 * (j & 1) + (par ^ 1);                        // chunk of the block
+          if ((j & 1) == 0) wait_ready(blk == 0 ? V4_R1A : blk == 1 ? V4_R1B : V4_R2, it);
+          float h[32];
+          tmem_ld32(lane_addr + (blk == 0 ? P : blk == 1 ? Q : R) + c * V4_KC, h);
+          const float* bias = (blk == 2 ? b2 : b1 + blk * 128) + c * V4_KC;
+          float h0[16], h1[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { h0[i] = h[i]; h1[i] = h[16 + i]; }
+          bias_relu16(h0, bias);
+          bias_relu16(h1, bias + 16);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { h[i] = h0[i]; h[16 + i] = h1[i]; }
+          put32(h);
+        }
+      } else {
+      if (!EARLY || it == 0) {
         put_input(tile);                                                // A0
         publish();
         load_row(tile + gridDim.x, xn);
@@ -1408,11 +1475,12 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
       publish();                                                        // A8: layer 2 cannot complete without it
       wait_ready(V4_R2, it);
       put_block(R, b2);                                                 // A9..A12: relu(layer 2 + b2)
-      if (ROT && tile + (int)gridDim.x < ntiles) {                      // the next tile's A0, ahead of this tile's heads
+      if (EARLY && tile + (int)gridDim.x < ntiles) {                    // the next tile's A0, ahead of this tile's heads
         put_input(tile + gridDim.x);
         load_row(tile + 2 * gridDim.x, xn);
       }
       publish();                                                        // A12 (or the next A0)
+      }
       float dval = 0.f, klv = 0.f;
 #pragma unroll 1
       for (int hb = 0; hb < 2; ++hb) {                                  // heads: this thread's 32 of the block's 64 latents
@@ -1424,7 +1492,7 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
         float mu[32], lv[32];
         tmem_ld32(acc + 32 * half, mu);
         tmem_ld32(acc + 64 + 32 * half, lv);
-        if (ROT && hb == 0) {                                           // block P has been read (tmem_ld32 waits for its data)
+        if (EARLY && hb == 0) {                                         // block P has been read (tmem_ld32 waits for its data)
           tc_fence_before();
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(h_done_a) : "memory");
         }
@@ -1708,14 +1776,16 @@ extern "C" int om_disc_forward(const OmDisc* h, const float* s, const float* mea
   // VAIL default: disc_vail4_kernel (one CTA per SM, A operand in TMEM): 69 us at 65536 samples / 796 us at 1 M against 74 /
   // 815 for the two-CTA shared-memory kernel (knob 1), 82 / 975 for the two-CTA TMEM kernel (knob 3), 72 / 841 for the
   // two-producer-group shared-memory kernel (knob 0)
-  if (h->sh.kind == 0 && (g_knobs.disc_vail2 == 4 || g_knobs.disc_vail2 == 5 || g_knobs.disc_vail2 == 6 || g_knobs.disc_vail2 < 0)) {
+  if (h->sh.kind == 0 && (g_knobs.disc_vail2 == 4 || g_knobs.disc_vail2 == 5 || g_knobs.disc_vail2 == 6 || g_knobs.disc_vail2 == 7 ||
+                            g_knobs.disc_vail2 < 0)) {
     const size_t smem4 = V4_NSB * V4_STAGE_B + (V2_NPAR + 3 + 2 * DISC_IN + 256) * sizeof(float) +
                          (2 * V4_NSA + 2 * V4_NSB + V4_NR + 2) * 8 + 16;
-    const int rot = g_knobs.disc_vail2 == 5 ? 2 : g_knobs.disc_vail2 == 6 ? 1 : 0;
+    const int rot = g_knobs.disc_vail2 == 5 ? 2 : g_knobs.disc_vail2 == 6 ? 1 : g_knobs.disc_vail2 == 7 ? 3 : 0;
     DiscArgs a4 = a;
     a4.image = h->image4;
     a4.params = h->params2;
-    auto kern = rot == 2 ? (kl_out ? disc_vail4_kernel<true, 2> : disc_vail4_kernel<false, 2>)
+    auto kern = rot == 3 ? (kl_out ? disc_vail4_kernel<true, 3> : disc_vail4_kernel<false, 3>)
+              : rot == 2 ? (kl_out ? disc_vail4_kernel<true, 2> : disc_vail4_kernel<false, 2>)
               : rot == 1 ? (kl_out ? disc_vail4_kernel<true, 1> : disc_vail4_kernel<false, 1>)
                          : (kl_out ? disc_vail4_kernel<true, 0> : disc_vail4_kernel<false, 0>);
     OM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));

@@ -80,14 +80,14 @@ def test_loss_statistics_vs_reference_losses(noisy):
         assert abs(vl.beta - z["betas"][i + 1]) < 1e-7
 
 
-@pytest.mark.parametrize("kernel", ["a_in_tmem_one_cta", "a_in_tmem_rotating", "a_in_tmem_split_release", "a_in_tmem_two_ctas", "two_ctas_per_sm", "one_cta_per_sm", "one_producer_group"])
+@pytest.mark.parametrize("kernel", ["a_in_tmem_one_cta", "a_in_tmem_rotating", "a_in_tmem_split_release", "alternating_producers", "a_in_tmem_two_ctas", "two_ctas_per_sm", "one_cta_per_sm", "one_producer_group"])
 def test_vail_forward_logit_and_kl_vs_oracle(kernel, om_knob):
     """The fit's forward pass (logit + per-sample KL) out of the tcgen05 kernels against the float64 oracle and the
     reference network's own mu / logvar (discriminator_ref.npz); ragged sample counts."""
     import torch
     from olympics_mujoco_b200 import kernels as Kn
     from oracle import learner as L
-    om_knob("disc_vail2", {"a_in_tmem_one_cta": 4, "a_in_tmem_rotating": 5, "a_in_tmem_split_release": 6, "a_in_tmem_two_ctas": 3, "two_ctas_per_sm": 1}.get(kernel, 0))
+    om_knob("disc_vail2", {"a_in_tmem_one_cta": 4, "a_in_tmem_rotating": 5, "a_in_tmem_split_release": 6, "alternating_producers": 7, "a_in_tmem_two_ctas": 3, "two_ctas_per_sm": 1}.get(kernel, 0))
     if kernel == "one_producer_group":
         om_knob("disc_pg2", int("0"))
     g = np.load(GOLDEN / "discriminator_ref.npz")
