@@ -1288,10 +1288,11 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
         const uint32_t itp = (uint32_t)it & 1u;
         // B chunk q of the tile (stage q % 6, its (3 it + q / 6)-th use) against the A chunk in TMEM stage `ab`:
         // 4 k-steps x (lo.hi, hi.lo, hi.hi)
+        // (the weights are waited for BEFORE the A chunk: they arrive chunks ahead, the A chunk is what the MMA pipe is
+        // waiting for, and every mbarrier wait costs the issuing thread ~100 cycles even when the phase is long complete)
+        auto wait_b = [&](int q) { mbar_wait(b_full(q % V4_NSB), (itp ^ (uint32_t)(q / V4_NSB)) & 1u); tc_fence_after(); };
         auto mma_chunk = [&](int q, uint32_t ab, uint32_t d, bool first) {
           const int sb = q % V4_NSB;
-          mbar_wait(b_full(sb), (itp ^ (uint32_t)(q / V4_NSB)) & 1u);
-          tc_fence_after();
 #pragma unroll
           for (int j = 0; j < V4_KC / 8; ++j) {
             const uint64_t dbh = bdesc((uint32_t)(sb * (V4_STAGE_B / 16) + j * 2 * LBO16));
@@ -1316,9 +1317,11 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
         //        head a, R for head b.
         if ((ROT == 0 || ROT == 3) && it > 0) { mbar_wait(h_done, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
         if (ROT == 1 && it > 0) { mbar_wait(h_done_a, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
+        wait_b(0);
         uint32_t ab = next_a(0);                                        // A0 = x
         mma_chunk(0, ab, P, true);
         umma_commit(ready(V4_R1A));
+        wait_b(1);
         if (ROT == 2 && it > 0) { mbar_wait(h_done_a, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
         if (ROT == 1 && it > 0) { mbar_wait(h_done, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
         mma_chunk(1, ab, Q, true);
@@ -1327,6 +1330,7 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
         if (ROT == 2 && it > 0) { mbar_wait(h_done, (uint32_t)(it - 1) & 1u); tc_fence_after(); }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {                                   // A1..A8 -> layer 2
+          wait_b(2 + c);
           ab = next_a(1 + c);
           mma_chunk(2 + c, ab, R, c == 0);
           umma_commit(a_fr[(1 + c) & 1]);
@@ -1334,9 +1338,11 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
         umma_commit(ready(V4_R2));
 #pragma unroll
         for (int c = 0; c < 4; ++c) {                                   // A9..A12 -> [mu; lv] blocks a and b
+          wait_b(10 + 2 * c);
           ab = next_a(9 + c);
           mma_chunk(10 + 2 * c, ab, P, c == 0);
           if (c == 3) umma_commit(ready(V4_R3A));
+          wait_b(11 + 2 * c);
           mma_chunk(11 + 2 * c, ab, Q, c == 0);
           umma_commit(a_fr[(9 + c) & 1]);
         }
