@@ -1150,25 +1150,29 @@ constexpr int V4_ACHUNKS = 13;
 enum { V4_R1A = 0, V4_R1B, V4_R2, V4_R3A, V4_R3B, V4_NR };
 
 //
-// Where the time goes at 1 M samples (56 tiles per CTA; clock counters in the MMA-issuing thread and in a producer thread,
-// experiments that are not in the tree).  (a) The issuing thread itself paced the MMAs until its tile body was unrolled
-// (see the MMA issuer below): 27.7 k -> 23 k cycles per tile, 802 -> 720 us, 69 -> 64 us at 65536 samples.  (b) A tile's
-// timeline as a producer thread sees it: layer 1 complete at 1.7 k cycles, layer 2 at 11.2 k (8 chunks in 9.5 k cycles
-// against 6.1 k of MMA: the hand-over chain MMA-commit -> a_free -> tcgen05.st -> wait::st -> a_full -> issue of a two-stage
-// ring is longer than one chunk's 768 MMA cycles), layer 3 at 18.2 / 21.6 k (MMA-bound: two weight chunks per A chunk),
-// heads + output until 24.7 k.  216 MMAs are 13.8 k cycles: the pipe is busy 60 % of a tile.  (c) At 65536 samples a CTA
-// has 3 or 4 tiles (512 tiles over 148 SMs: 3.46 rounded up to 4 is 13.5 % lost to the tile count alone): 4 x 23 k cycles
-// = 48 us of the 64 us call, the rest is launch, prologue and the last tile's heads.
+// Where the time goes (clock counters in the MMA-issuing thread and in a producer thread; experiments that are not in the
+// tree).  (a) The issuing thread itself paced the MMAs: a back-to-back M128 x N128 x K8 TF32 MMA takes 64 cycles
+// (tools/micro/umma_rate.cu), but it went out every 92 cycles while the weight stage was a run-time index (four dependent
+// uniform-datapath instructions per descriptor), every ~71 while the issuing code sat behind `tid == 256` (ptxas wraps
+// each tcgen05.mma in a five-instruction elect / vote loop unless the branch is taken through elect.sync), plus ~100
+// cycles per mbarrier wait even on a completed phase.  Unrolled tile body + elect_one_sync + weights waited for before the
+// A chunk: 27.7 k -> 22.6 k cycles per tile at 1 M samples (802 -> 659 us), 69 -> 59 us at 65536.  (b) A tile's timeline
+// now (65536 samples, 19.5 k cycles): input chunk + layer 1 + first hand-over 1.9 k, layer 2 eight chunks of ~830 (768 of
+// MMA + what is left of the hand-over chain MMA-commit -> a_free -> tcgen05.st -> wait::st -> a_full -> issue of a two-stage
+// ring), 1.7 k at the layer-2 -> layer-3 boundary, layer 3 four chunks of 1536 (MMA-bound), heads and output 3.5 k with
+// 1.5 k of MMA under them.  216 MMAs are 13.8 k cycles: the pipe is busy 71 % of a tile.  (c) At 65536 samples a CTA has 3
+// or 4 tiles (512 tiles over 148 SMs: 3.46 rounded up to 4 is 13.5 % lost to the tile count alone); the CTA's whole life
+// is 81.5 k cycles, 4 k of them prologue and drain -- and 59 us, because under this load the SM clock is ~1.4 GHz, not the
+// 1.96 GHz of the memory-bound kernels (the same reason cuBLAS's TF32 GEMM reaches 640-760 of a nominal 1150 TFLOP/s).
 // Measured against that, all parity-green, none faster: handing an A chunk over one put() late so that its TMEM-store
 // latency sits under the next chunk's arithmetic, four TMEM loads in flight per block, the first weight chunks and input
 // rows requested ahead of the prologue (neutral, kept); ROT = 1 / 2 below (next tile's layer 1 under this tile's heads:
-// 1-4 % slower -- the same threads must produce the next tile's A chunks after the heads, and its input chunk queues
-// for a ring stage in front of the heads); and a third warpgroup that does nothing but heads, with layer-1 block b
-// issued after the first half of layer 2 so that nothing early waits for them (448 threads at 128 registers: 80 us / 832
-// us -- the heads then compete with the producers for issue slots, and the producers' hand-over chain is what bounds
-// layer 2).  What would help is a deeper A ring, and tensor memory has no columns left for one.
+// the next layer 2 does start 1.5 k cycles earlier, and this tile's layer 3 ends 1.5 k later); ROT = 3, the two producer
+// warpgroups on alternate chunks, one ring stage each (identical time: the producers are not what layer 2 waits for); and
+// a third warpgroup that does nothing but heads, with layer-1 block b issued after the first half of layer 2 (448 threads
+// at 128 registers: 80 us / 832 us, not kept).
 //
-// ROT (opt-in through om_debug_set("disc_vail2", 6 / 5)): 1 = the next tile's input chunk is handed over before the
+// ROT (opt-in through om_debug_set("disc_vail2", 6 / 5 / 7)): 3 = alternating producer warpgroups; 1 = the next tile's input chunk is handed over before the
 // heads and the two layer-1 blocks are released one by one (h_done_a after head a's loads, h_done after head b's);
 // 2 = the three accumulator blocks change roles from tile to tile instead, (L1a/L3a, L1b/L3b, L2)(i + 1) = (L2, L1a/L3a,
 // L1b/L3b)(i): the next tile's first layer-1 block goes into the block this tile's layer 2 used (read out once A12
