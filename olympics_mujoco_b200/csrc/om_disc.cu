@@ -1161,9 +1161,10 @@ enum { V4_R1A = 0, V4_R1B, V4_R2, V4_R3A, V4_R3B, V4_NR };
 // MMA + what is left of the hand-over chain MMA-commit -> a_free -> tcgen05.st -> wait::st -> a_full -> issue of a two-stage
 // ring), 1.7 k at the layer-2 -> layer-3 boundary, layer 3 four chunks of 1536 (MMA-bound), heads and output 3.5 k with
 // 1.5 k of MMA under them.  216 MMAs are 13.8 k cycles: the pipe is busy 71 % of a tile.  (c) At 65536 samples a CTA has 3
-// or 4 tiles (512 tiles over 148 SMs: 3.46 rounded up to 4 is 13.5 % lost to the tile count alone); the CTA's whole life
-// is 81.5 k cycles, 4 k of them prologue and drain -- and 59 us, because under this load the SM clock is ~1.4 GHz, not the
-// 1.96 GHz of the memory-bound kernels (the same reason cuBLAS's TF32 GEMM reaches 640-760 of a nominal 1150 TFLOP/s).
+// or 4 tiles (512 tiles over 148 SMs: 3.46 rounded up to 4 is 13.5 % lost to the tile count alone); a four-tile CTA
+// lives 81 k cycles with its inputs in L2 (45.8 us at the 1.77 GHz the SM clock shows under this load, globaltimer against
+// clock64), 90 k = 50.8 us after the L2 flush the benchmark does, 4 k of them prologue and drain; the benchmark's 59 us
+// are that plus launch, block scheduling and completion.
 // Measured against that, all parity-green, none faster: handing an A chunk over one put() late so that its TMEM-store
 // latency sits under the next chunk's arithmetic, four TMEM loads in flight per block, the first weight chunks and input
 // rows requested ahead of the prologue (neutral, kept); ROT = 1 / 2 below (next tile's layer 1 under this tile's heads:

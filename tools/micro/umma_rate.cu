@@ -67,6 +67,8 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out, int n_mma, int r
     }
     const int nblk = 384 / N;
     int blk = 0;
+    unsigned long long g0, g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     const long long t0 = clock64();
     for (int i = 0; i < n_mma; i += 12) {                             // `run` = 12 or 1: accumulate flag pattern only
       const uint32_t d = tmem + (uint32_t)(blk * N);
@@ -81,6 +83,8 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out, int n_mma, int r
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                    : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
     const long long t2 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    out[2 * gridDim.x + blockIdx.x] = (long long)(g1 - g0);       // nanoseconds: SM clock = cycles / ns
     out[blockIdx.x * 2] = t1 - t0;          // cycles the issuing thread needed (blocked when the MMA queue is full)
     out[blockIdx.x * 2 + 1] = t2 - t0;      // until the last MMA has completed
   }
@@ -92,19 +96,20 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out, int n_mma, int r
 template <bool TF32, bool TS, int N>
 void run(const char* name, int grid, int n_mma, int run_len) {
   long long* out;
-  cudaMalloc(&out, sizeof(long long) * 2 * grid);
+  cudaMalloc(&out, sizeof(long long) * 3 * grid);
   auto k = probe<TF32, TS, N>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   for (int rep = 0; rep < 2; ++rep) k<<<grid, 128, 64 * 1024>>>(out, n_mma, run_len);
   cudaError_t e = cudaDeviceSynchronize();
-  long long h[2 * 148];
-  cudaMemcpy(h, out, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost);
-  double issue = 0, total = 0;
-  for (int i = 0; i < grid; ++i) { issue += h[2 * i]; total += h[2 * i + 1]; }
+  long long h[3 * 148];
+  cudaMemcpy(h, out, sizeof(long long) * 3 * grid, cudaMemcpyDeviceToHost);
+  double issue = 0, total = 0, ns = 0;
+  for (int i = 0; i < grid; ++i) { issue += h[2 * i]; total += h[2 * i + 1]; ns += h[2 * grid + i]; }
   const double k_per = TF32 ? 8 : 16;
   const double cyc = total / grid / n_mma;
-  printf("%-34s grid %3d run %2d: %6.1f cycles / MMA (issue loop %6.1f)  = %5.0f MAC/clk/SM  %s\n", name, grid, run_len, cyc,
-         issue / grid / n_mma, 128.0 * N * k_per / cyc, e == cudaSuccess ? "" : cudaGetErrorString(e));
+  printf("%-20s grid %3d run %2d: %6.1f cycles / MMA (issue loop %6.1f) = %5.0f MAC/clk/SM at %4.0f MHz = %5.0f TFLOP/s  %s\n", name,
+         grid, run_len, cyc, issue / grid / n_mma, 128.0 * N * k_per / cyc, total / ns * 1e3,
+         2.0 * 128.0 * N * k_per * n_mma * grid / (ns / grid) * 1e-3, e == cudaSuccess ? "" : cudaGetErrorString(e));
   cudaFree(out);
 }
 
@@ -118,6 +123,7 @@ int main() {
     run<false, false, 128>("bf16 K=16 SS N=128", grid, 4092, 12);
     run<false, true, 256>("bf16 K=16 TS N=256", grid, 4092, 12);
     run<true, true, 128>("tf32 K=8  TS N=128", grid, 4092, 1);
+    run<true, true, 128>("tf32 K=8  TS N=128", grid, 40920, 12);       // 1.4 ms: long enough for the clock to settle
   }
   return 0;
 }
