@@ -513,7 +513,7 @@ static int a3_step_impl(const OmModel* m, const OmA3Task* task, const float* qpo
     char* base = (char*)task->scratch;
     A3Scratch w{(float*)base, (uint8_t*)(base + feat_b + int_b), 0,
                 (int32_t*)(base + feat_b), (float*)(base + feat_b) + 2 * (size_t)ld};
-    // sub-calls no longer than the candidate bits cover (210 steps with the reference's 30 delay frames)
+    // sub-calls no longer than the candidate bits cover (150 steps with the reference's 30 delay frames)
     const int max_call = a3_max_steps_per_call(task->C.delay_frames);
     for (int c0 = 0; c0 < n_steps; c0 += max_call) {
       const int len = n_steps - c0 < max_call ? n_steps - c0 : max_call;
