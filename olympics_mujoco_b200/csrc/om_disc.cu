@@ -1404,6 +1404,9 @@ __global__ void __launch_bounds__(320, 1) disc_vail4_kernel(DiscArgs a) {
         for (int i = 0; i < 16; ++i) h[i] = __uint_as_float(r[c][i]);
         bias_relu16(h, bias + c * V4_KC + 16 * half);
         put(h);
+        // the first chunk of a block is what the idle MMA pipe is waiting for, and behind the last one comes a wait and
+        // a round of loads, not arithmetic: those two are handed over at once
+        if (c == 0 || c == 3) publish();
       }
     };
     auto wait_ready = [&](int k, int it) { mbar_wait(ready(k), (uint32_t)it & 1u); tc_fence_after(); };
