@@ -296,14 +296,27 @@ __global__ void __launch_bounds__(128) moment_stats_kernel(const double* __restr
   if (denom32) denom32[c] = (float)d;
 }
 
-__global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict__ x, const double* __restrict__ stats,
-                                                        int rows, int n, int ld, float* __restrict__ y) {
+__global__ void __launch_bounds__(256) normalize_kernel(const float* x, const double* __restrict__ stats, int rows, int n, int ld,
+                                                        float* y) {            // y may be x (in place): no __restrict__
   pdl_wait();
   const double mean = stats[0], inv = 1.0 / stats[1];
   const int r = blockIdx.y;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const size_t idx = (size_t)r * ld + i;
     y[idx] = (float)(((double)x[idx] - mean) * inv);
+  }
+}
+
+// The same over a CONTIGUOUS buffer (ld == n, 16-byte aligned, element count a multiple of four): one grid-stride pass of
+// 128-bit accesses instead of rows x n / 256 CTAs of one element per thread (8.7 -> 4 us for the 500 x 4096 advantages).
+__global__ void __launch_bounds__(256) normalize_flat_kernel(const float4* x, const double* __restrict__ stats, size_t n4,
+                                                             float4* y) {       // y may be x (in place): no __restrict__
+  pdl_wait();
+  const double mean = stats[0], inv = 1.0 / stats[1];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    y[i] = make_float4((float)(((double)v.x - mean) * inv), (float)(((double)v.y - mean) * inv),
+                       (float)(((double)v.z - mean) * inv), (float)(((double)v.w - mean) * inv));
   }
 }
 
@@ -535,6 +548,16 @@ extern "C" int om_normalize(const float* x, const double* stats, int rows, int n
   OM_REQUIRE(rows >= 0 && n >= 0 && ld >= n, "om_normalize: bad sizes");
   if (rows == 0 || n == 0) return 0;
   OM_REQUIRE(x && stats && y, "om_normalize: null argument");
+  const size_t total = (size_t)rows * (size_t)n;
+  if (ld == n && total % 4 == 0 && ((uintptr_t)x | (uintptr_t)y) % 16 == 0) {
+    const size_t n4 = total / 4;
+    const size_t want = (n4 + 255) / 256;
+    const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+    OM_CUDA_OK(launch_pdl(normalize_flat_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream,
+                          reinterpret_cast<const float4*>(x), stats, n4, reinterpret_cast<float4*>(y)));
+    OM_LAUNCHED();
+    return 0;
+  }
   int gx = ceil_div(n, 256);
   if (gx > 592) gx = 592;
   dim3 grid(gx, rows);
