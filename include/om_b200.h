@@ -43,9 +43,13 @@ int om_abi_version(void);
 /* number of kernels launched by this library since load / since om_reset_launch_count() */
 long long om_launch_count(void);
 void om_reset_launch_count(void);
-/* Tuning / test hook: force a kernel variant ("play_chunk", "h1_split", "a3_split", "serial_scan", "disc_vail2",
- * "disc_pg2"; -1 / 0 = automatic).  The same knobs are initialised ONCE, when the library is loaded, from the OM_PLAY_CHUNK,
- * OM_H1_SPLIT, ... environment variables; no launch path calls getenv. */
+/* Tuning / test hook: force a kernel variant ("play_chunk", "h1_split", "a3_split", "a3_feat_minb", "serial_scan",
+ * "disc_vail2", "disc_pg2"; -1 / 0 = automatic).  The same knobs are initialised ONCE, when the library is loaded, from the
+ * OM_PLAY_CHUNK, OM_H1_SPLIT, ... environment variables; no launch path calls getenv.
+ * "disc_vail2" selects the VAIL discriminator kernel: -1 / 4 disc_vail4_kernel (one CTA per SM, A operand in tensor
+ * memory: the default), 6 / 5 / 7 its variants (layer-1 blocks released head by head / rotating accumulator blocks /
+ * alternating producer warpgroups), 1 disc_vail2_kernel (two CTAs per SM, shared-memory operands), 3 disc_vail3_kernel
+ * (two CTAs per SM, A in tensor memory), 0 the kernels that also serve GAIL ("disc_pg2" 0: one producer warpgroup). */
 int om_debug_set(const char* knob, int value);
 
 /* ------------------------------------------------------------------------------------------------
