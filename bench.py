@@ -225,6 +225,8 @@ def compact(d):
               "eager_python_loop_ms_per_step", "envs_per_gpu", "scaling", "net"):
         if k in d:
             keep[k] = round(d[k], 5) if isinstance(d[k], float) and abs(d[k]) < 1e6 else d[k]
+    if "timing" in d:                                   # how the device time was taken: "eager" launches or "graph" replay
+        keep["timing"] = "graph" if d["timing"].startswith("CUDA-graph") else "eager"
     r = d.get("roofline")
     if r:
         for k in ("frac", "frac_executed", "frac_dram", "peak", "bound"):
