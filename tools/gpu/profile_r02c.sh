@@ -10,7 +10,7 @@ ncu --set full --import-source on --clock-control none -k regex:play_h1_tp_kerne
 ncu --set full --clock-control none -k regex:"play_moments_kernel|play_snapshot_kernel|affine_scan_kernel|normalize_kernel|moments_kernel" -s 20 -c 5 -o gpurun_out/r02_step_tail -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-other-configs > /dev/null 2>&1
 ncu --set full --clock-control none -k regex:"a3_feat_kernel|a3_walk_kernel|a3_post_kernel" -s 6 -c 3 -o gpurun_out/r02_a3_replay -f python tools/bench_a3.py --steps 3 --warmup 1 > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum,sm__cycles_elapsed.max,smsp__inst_executed.sum --cache-control none --clock-control none -k regex:"a3_|affine_scan" -s 12 -c 12 --csv --log-file gpurun_out/r02_a3_inflow.csv python tools/bench_a3.py --steps 6 --warmup 3 > /dev/null 2>&1
-ncu --set full --clock-control none -k regex:"disc_vail4_kernel|disc_reward_pg2_kernel" -s 4 -c 2 -o gpurun_out/r02_disc -f python tools/bench_disc.py --steps 2 --warmup 2 > /dev/null 2>&1
+ncu --set full --clock-control none -k regex:"disc_vail4_kernel|disc_reward_pg2_kernel" -s 3 -c 2 -o gpurun_out/r02_disc -f python tools/bench_disc.py --steps 2 --warmup 2 > /dev/null 2>&1
 ncu --set full --clock-control none -k regex:"disc_vail4_kernel" -s 2 -c 1 -o gpurun_out/r02_disc_vail4_1m -f python tools/bench_disc.py --envs 1048576 --steps 2 --warmup 2 > /dev/null 2>&1
 ncu --set full --clock-control none -k regex:"h1_live_step_kernel" -s 6 -c 1 -o gpurun_out/r02_h1_live_step -f python tools/bench_h1_step.py --steps 5 > /dev/null 2>&1
 tools/micro/umma_rate > gpurun_out/r02_umma_rate.txt 2>&1
