@@ -70,7 +70,7 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clocks / throttle reasons sampled DURING the timed region (NVML in-process; nvidia-smi if NVML is unavailable)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -79,15 +79,36 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
 
+    def _nvml_row(self):
+        """The same fields through NVML in this process: a query costs well under a millisecond, where every nvidia-smi
+        spawn initialises the driver API again and was seen to stall the end-to-end leg's copies for tens of ms."""
+        import pynvml as nv
+        if not hasattr(self, "_h"):
+            nv.nvmlInit()
+            self._h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        h = self._h
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = int(get_reasons(h))
+        flag = lambda m: "Active" if bits & m else "Not Active"
+        return [str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)),
+                str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0), flag(0x8), flag(0x40), flag(0x20), flag(0x4)]
+
     def run(self):
+        use_nvml = True
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
+                if use_nvml:
+                    try:
+                        self.rows.append(self._nvml_row())
+                    except Exception:
+                        use_nvml = False
+                if not use_nvml:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    self.rows.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.05)
+            self._stop_evt.wait(0.05 if not use_nvml else 0.01)
 
     def stop(self):
         self._stop_evt.set()
