@@ -149,11 +149,13 @@ __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w
   const float* vp = a.qvel + (size_t)t * A3_NV * ld + e;
   const float* cp = a.contact + (size_t)t * 4 * ld + e;
 #pragma unroll
-  for (int k = 0; k < A3_NQ; ++k) q[k] = *row(qp, k, lu);
+  // inputs are read once and the observations written once: streaming accesses (evict-first), so that the 64 MB of
+  // records this pass leaves for the post pass have a chance to stay in the 126 MB L2
+  for (int k = 0; k < A3_NQ; ++k) q[k] = __ldcs(row(qp, k, lu));
 #pragma unroll
-  for (int k = 0; k < A3_NV; ++k) qd[k] = *row(vp, k, lu);
+  for (int k = 0; k < A3_NV; ++k) qd[k] = __ldcs(row(vp, k, lu));
 #pragma unroll
-  for (int k = 0; k < 4; ++k) con[k] = *row(cp, k, lu);
+  for (int k = 0; k < 4; ++k) con[k] = __ldcs(row(cp, k, lu));
   int phase = a.ints[A3I_PHASE * ld + e] + (t + 1) % a.C.period;            // walking_task.py:248-250, t + 1 increments;
   if (phase >= a.C.period) phase -= a.C.period;                            // the modulo is warp-uniform, the wrap a select
   const int mode = a.ints[A3I_MODE * ld + e];
@@ -198,11 +200,11 @@ __device__ __forceinline__ void a3_feat_item(const A3Args& a, const A3Scratch& w
   if (a.o.obs) {
     float* ob = a.o.obs + (size_t)t * A3_NOBS * ld + e;
 #pragma unroll
-    for (int k = 0; k < 33; ++k) *row(ob, k, lu) = obs[k];
+    for (int k = 0; k < 33; ++k) __stcs(row(ob, k, lu), obs[k]);
   }
   if (a.o.terms) {
     float* tp = a.o.terms + (size_t)t * 6 * ld + e;
-    tp[0] = terms[0]; *row(tp, 1, lu) = terms[1]; *row(tp, 3, lu) = terms[3]; *row(tp, 5, lu) = terms[5];
+    __stcs(tp, terms[0]); __stcs(row(tp, 1, lu), terms[1]); __stcs(row(tp, 3, lu), terms[3]); __stcs(row(tp, 5, lu), terms[5]);
   }
   if (a.o.done) a.o.done[(size_t)t * ld + e] = done ? 1 : 0;
 }
@@ -354,12 +356,12 @@ __global__ void __launch_bounds__(BLOCK) a3_post_kernel(A3Args a, A3Scratch w) {
   if (a.o.obs) {
     float* ob = a.o.obs + ((size_t)t * A3_NOBS + 33) * ld + e;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) *row(ob, k, lu) = goal[k];
+    for (int k = 0; k < 8; ++k) __stcs(row(ob, k, lu), goal[k]);
   }
   if (a.o.terms) {
     float* tp = a.o.terms + (size_t)t * 6 * ld + e;
-    *row(tp, 2, lu) = tm2;
-    *row(tp, 4, lu) = tm4;
+    __stcs(row(tp, 2, lu), tm2);
+    __stcs(row(tp, 4, lu), tm4);
   }
   if (a.o.reward) a.o.reward[(size_t)t * ld + e] = total;
 }

@@ -351,13 +351,21 @@ OM_HD void a3_rec_store(const A3Rec& r, float* b, unsigned ld) {
   b[10u * ld] = r.rsite.x; b[11u * ld] = r.rsite.y; b[12u * ld] = r.rsite.z;
   b[13u * ld] = r.t01; b[14u * ld] = r.t3; b[15u * ld] = r.t5;
 }
+// (read once: streaming loads on the device, the line may leave L2 first)
+OM_HD float a3_ld_once(const float* p) {
+#ifdef __CUDA_ARCH__
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
 OM_HD A3Rec a3_rec_load(const float* b, unsigned ld) {
   A3Rec r;
-  r.root_p = V3{b[0], b[ld], b[2u * ld]};
-  r.root_q = Q4{b[3u * ld], b[4u * ld], b[5u * ld], b[6u * ld]};
-  r.lsite = V3{b[7u * ld], b[8u * ld], b[9u * ld]};
-  r.rsite = V3{b[10u * ld], b[11u * ld], b[12u * ld]};
-  r.t01 = b[13u * ld]; r.t3 = b[14u * ld]; r.t5 = b[15u * ld];
+  r.root_p = V3{a3_ld_once(b), a3_ld_once(b + ld), a3_ld_once(b + 2u * ld)};
+  r.root_q = Q4{a3_ld_once(b + 3u * ld), a3_ld_once(b + 4u * ld), a3_ld_once(b + 5u * ld), a3_ld_once(b + 6u * ld)};
+  r.lsite = V3{a3_ld_once(b + 7u * ld), a3_ld_once(b + 8u * ld), a3_ld_once(b + 9u * ld)};
+  r.rsite = V3{a3_ld_once(b + 10u * ld), a3_ld_once(b + 11u * ld), a3_ld_once(b + 12u * ld)};
+  r.t01 = a3_ld_once(b + 13u * ld); r.t3 = a3_ld_once(b + 14u * ld); r.t5 = a3_ld_once(b + 15u * ld);
   return r;
 }
 
