@@ -529,9 +529,12 @@ static int a3_step_impl(const OmModel* m, const OmA3Task* task, const float* qpo
       w.tp = (len + 15) / 16 * 16;
       OM_REQUIRE(len <= 65535, "om_a3_task_step: at most 65535 steps per call");
       const int ncand = a3_num_cand_host(len, task->C.delay_frames);
+      // 64-thread CTAs, ten per SM (the same 20 warps as 128 x 5, finer-grained: 0.5 % / 1.5 % faster at 16384 / 262144
+      // envs); knob values 4 / 5 / 6: 128-thread CTAs compiled for that many per SM (tuning)
       if (g_knobs.a3_feat_minb == 6) a3_feat_kernel<FB, 6><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
+      else if (g_knobs.a3_feat_minb == 5) a3_feat_kernel<FB, 5><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
       else if (g_knobs.a3_feat_minb == 4) a3_feat_kernel<FB, 4><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
-      else a3_feat_kernel<FB, 5><<<dim3(env_blocks, len), FB, 0, st>>>(sub, w, ncand);
+      else a3_feat_kernel<64, 10><<<dim3(ceil_div(n, 64), len), 64, 0, st>>>(sub, w, ncand);
       OM_LAUNCHED();
       OM_CUDA_OK(launch_pdl(a3_walk_kernel, dim3(ceil_div(n, 64)), dim3(64), 0, st, sub, w, ncand));
       OM_LAUNCHED();

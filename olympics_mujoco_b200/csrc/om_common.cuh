@@ -31,7 +31,7 @@ struct Knobs {
   int disc_vail2 = -1;    // OM_DISC_VAIL2   VAIL kernel: -1 / 4 one CTA per SM with the A operand in TMEM (default), 1 two CTAs per SM
                           //                 (shared-memory operands), 3 two CTAs per SM with A in TMEM, 0 the kernels that also serve GAIL
   int disc_pg2 = -1;      // OM_DISC_PG2     1 / 0: two producer warpgroups
-  int a3_feat_minb = 5;   // OM_A3_FEAT_MINB 4 / 5 / 6: resident CTAs per SM the A3 replay kernel is compiled for (tuning)
+  int a3_feat_minb = 0;   // OM_A3_FEAT_MINB 0: 64-thread CTAs, ten per SM (default); 4 / 5 / 6: 128-thread CTAs, that many per SM (tuning)
 };
 extern Knobs g_knobs;
 

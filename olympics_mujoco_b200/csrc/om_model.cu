@@ -36,7 +36,7 @@ Knobs g_knobs = [] {
   k.serial_scan = env_int("OM_SERIAL_SCAN", 0);
   k.disc_vail2 = env_int("OM_DISC_VAIL2", -1);
   k.disc_pg2 = env_int("OM_DISC_PG2", -1);
-  k.a3_feat_minb = env_int("OM_A3_FEAT_MINB", 5);
+  k.a3_feat_minb = env_int("OM_A3_FEAT_MINB", 0);
   return k;
 }();
 
