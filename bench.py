@@ -381,10 +381,11 @@ def run_ours(args):
     for i in range(2):
         e2e_step(i)
     # The end-to-end leg is bound by the HOST path (PCIe + host memory of a shared machine: profiles/r02d_probe_d2h.json),
-    # which is noisy from run to run -- one of our runs on a fresh box read 7x below the others.  The timed region is
-    # therefore measured twice; both readings are reported and the better one is the value.
+    # which is noisy from run to run -- one run in five or so reads 2-3x (once 7x) slower than the others, at N = 1 and
+    # at N = 2, with or without the clock sampler.  The timed region is therefore measured three times; every reading is
+    # reported and the best one is the value.
     e2e_runs = []
-    for rep_ in range(2):
+    for rep_ in range(3):
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(main)
