@@ -180,6 +180,9 @@ __global__ void __launch_bounds__(1024) affine_scan_kernel(AffineIn in, int T, i
   }
 }
 
+// (Measured and rejected for 256 < T <= 512: the time axis cut in two, a cluster of two 512-thread CTAs per 32 envs, the
+// earlier half taking its carry-in out of the later half's shared memory behind one cluster barrier -- twice the CTAs,
+// two per SM, all 148 SMs busy at 4096 envs, and no faster: 0.5003 against 0.4980 ms for the whole 4096 x 500 step.)
 static int launch_affine_scan(const AffineIn& in, int T, int n, int ld, float* o0, float* o1, cudaStream_t st) {
   // L steps per warp, W = ceil(T / L) warps per CTA: short horizons take 8 steps per warp (T = 64: 8 warps, 7 segment
   // folds and 4x more CTAs than 32 warps of 2 steps), long ones fill the 32 warps

@@ -36,7 +36,7 @@ def test_ppo_returns_vs_reference_buffer():
 
 
 @pytest.mark.parametrize("serial", [False, True])
-@pytest.mark.parametrize("T,n", [(64, 1000), (1, 5), (37, 1), (500, 45)])
+@pytest.mark.parametrize("T,n", [(64, 1000), (1, 5), (37, 1), (500, 45), (257, 33), (512, 64), (400, 4100)])
 def test_ppo_returns_segmented(T, n, serial, om_knob):
     from olympics_mujoco_b200 import kernels as Kn
     if serial:
@@ -55,7 +55,7 @@ def test_ppo_returns_segmented(T, n, serial, om_knob):
 
 
 @pytest.mark.parametrize("serial", [False, True])                 # affine-scan kernel / one-thread-per-env kernel
-@pytest.mark.parametrize("T,n", [(64, 513), (1000, 3), (500, 70), (1, 1), (1500, 33)])
+@pytest.mark.parametrize("T,n", [(64, 513), (1000, 3), (500, 70), (1, 1), (1500, 33), (258, 31), (511, 97), (384, 4096)])
 def test_gae_vs_mushroom_restatement(T, n, serial, om_knob):
     from olympics_mujoco_b200 import kernels as Kn
     if serial:
