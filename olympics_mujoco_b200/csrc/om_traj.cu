@@ -80,7 +80,8 @@ struct PlayArgs {
   uint32_t env_id0;
   double dt;
   float target;
-  int use_absorbing, n_steps, end_reset, n, ld;
+  int n_steps, end_reset, n, ld;      // (no use_absorbing: the playback loops call _has_fallen whatever the MDP setting,
+                                      //  loco_env_base.py:422,541)
   int forced;         // 1 = play_trajectory (the model is forced to each sample), 0 = play_trajectory_from_velocity
   OmPlayState s;      // live carried state (written by the thread that runs the last step)
   OmPlayState snap;   // episode-start snapshot read by every chunk of the time-parallel kernel
@@ -706,7 +707,7 @@ static int play_impl(const OmModel* m, const OmH1Spec* spec, const OmTraj* t, ui
                  state->pending && state->prev_x_vel, "om_h1_play_from_velocity: incomplete state");
   PlayArgs a;
   a.t = t->d; a.seed = seed; a.env_id0 = env_id0; a.dt = dt; a.target = spec->target_velocity;
-  a.use_absorbing = spec->use_absorbing_states; a.n_steps = n_steps; a.end_reset = end_episode_reset & 1;
+  a.n_steps = n_steps; a.end_reset = end_episode_reset & 1;
   const bool start_reset = (end_episode_reset & 2) != 0;          // OM_PLAY_START_RESET
   a.n = n; a.ld = ld; a.s = *state; a.snap = *state; a.o = *out; a.forced = forced;
   a.obs_moments = out->obs_moments;

@@ -56,6 +56,37 @@ def test_h1_step_parity(h1_model, h1_states, threads_per_env, om_knob):
     assert_close(o["cvel"].T.reshape(n, 21, 6), ref["cvel"], "cvel")
 
 
+def test_h1_split_kernel_is_deterministic_under_repetition(h1_model, om_knob):
+    """h1_step_split_kernel exchanges subtree results between its three threads per env through shared memory (VERDICT
+    W12: compute-sanitizer's racecheck is closed on this pool).  A missing barrier there shows up as run-to-run
+    differences under load: 40 back-to-back launches on 32768 envs, two streams in flight, every output bit-identical to
+    the first launch -- and, within fp32 rounding, equal to the one-thread-per-env kernel."""
+    import torch
+    from olympics_mujoco_b200 import kernels as Kn
+    n = 32768
+    rng = np.random.default_rng(5)
+    qpos, qvel = rng.normal(0, 0.4, (n, 17)), rng.normal(0, 2.0, (n, 17))
+    dm = Kn.DeviceModel(h1_model)
+    spec = _spec(h1_model)
+    q, qd = Kn.to_soa(qpos), Kn.to_soa(qvel)
+    pxv = torch.zeros(n, device="cuda")
+    om_knob("h1_split", 1)
+    first = {k: v.clone() for k, v in Kn.h1_step(dm, spec, q, qd, pxv).items()}
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    for it in range(40):
+        with torch.cuda.stream(side if it % 2 else torch.cuda.current_stream()):
+            out = Kn.h1_step(dm, spec, q, qd, pxv)
+            for k in ("xpos", "xquat", "cvel", "site_xpos", "obs"):
+                assert torch.equal(out[k], first[k]), f"{k} differs on launch {it}"
+    torch.cuda.synchronize()
+    om_knob("h1_split", 0)
+    one = Kn.h1_step(dm, spec, q, qd, pxv)
+    torch.cuda.synchronize()
+    for k in ("xpos", "xquat", "cvel"):
+        assert_close(first[k].cpu().numpy(), one[k].cpu().numpy(), k, rtol=2e-5, atol=2e-5)
+
+
 def test_h1_step_absorbing_disabled(h1_model, h1_states):
     import torch
     from olympics_mujoco_b200 import kernels as Kn
