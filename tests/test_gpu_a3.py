@@ -324,3 +324,40 @@ def test_a3_rollout_with_fused_returns_equals_step_then_ppo_returns(a3_model, T,
                 R = float(r[t, e]) + 0.99 * R
                 want[t] = R
         assert_close(v[:, e], want, "returns vs finish_path", rtol=2e-5, atol=2e-5)
+
+
+def test_a3_replay_is_deterministic_under_repetition(a3_model):
+    """The post pass of the replay starts while the walk pass runs and each of its threads waits for bit 7 of its own
+    per-step byte (om_a3.cu: a3_walk_kernel / a3_post_kernel).  A hole in that hand-over -- a post thread reading a
+    candidate byte as a state code, or a stale byte of the previous call -- shows as run-to-run differences: 30
+    back-to-back rollouts of 4096 envs x 64 steps from the same task state, every output bit-identical to the first,
+    with a smaller and a longer call in between so that stale bytes of other shapes lie in the scratch."""
+    import torch
+    from olympics_mujoco_b200 import kernels as Kn
+    n, T = 4096, 64
+    g = torch.Generator(device="cuda").manual_seed(9)
+    task = _task(a3_model, n, seed=11)
+    q0, v0 = Kn.soa(25, n), Kn.soa(24, n)
+    task.reset(q0, v0, iteration_count=5000.0)
+    qpos = q0[None] + 0.01 * torch.randn((T + 40, 25, n), device="cuda", generator=g).cumsum(0)
+    qvel = torch.randn((T + 40, 24, n), device="cuda", generator=g)
+    con = torch.stack([torch.rand((T + 40, n), device="cuda", generator=g) * 400, torch.rand((T + 40, n), device="cuda", generator=g) * 400,
+                       (torch.rand((T + 40, n), device="cuda", generator=g) - 0.5) * 0.02,
+                       (torch.rand((T + 40, n), device="cuda", generator=g) < 0.7).float()], dim=1).contiguous()
+    ints0 = task.ints.clone()
+    first = None
+    for it in range(30):
+        task.ints.copy_(ints0)
+        steps = T if it % 5 else (T + 40 if it % 2 else 7)           # every fifth call has another length
+        out = task.step(qpos[:steps], qvel[:steps], con[:steps])
+        if steps != T:
+            continue
+        cur = {k: v.clone() for k, v in out.items()}
+        cur["ints"] = task.ints.clone()
+        if first is None:
+            first = cur
+        else:
+            for k, v in cur.items():
+                assert torch.equal(v, first[k]), f"{k} differs on rollout {it}"
+    torch.cuda.synchronize()
+    assert first is not None
