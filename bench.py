@@ -108,7 +108,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.05 if not use_nvml else 0.01)
+            self._stop_evt.wait(0.1)       # NOT faster: at 100 Hz per rank the NVML queries of 4 ranks cost the step 9 % (driver lock)
 
     def stop(self):
         self._stop_evt.set()
