@@ -416,3 +416,20 @@ def test_host_philox_matches_the_contract():
         want = [int(x) for x in OP.draw(seed, np.uint32(env), np.uint32(cnt), stream)]
         assert list(HP.philox4x32_10((env, cnt, stream, 0), (seed & 0xFFFFFFFF, seed >> 32))) == want
         assert HP.philox_randint(seed, env, cnt, stream, 4) == int(OP.to_int(np.uint32(want[0]), 4))
+
+
+def test_bench_helpers_without_a_gpu():
+    """bench.py's clock sampler degrades to "no samples" when neither NVML nor nvidia-smi answers (this container), and
+    compact() keeps the few numbers of a side measurement, including how its device time was taken."""
+    import time
+    import bench
+    s = bench.ClockSampler(0)
+    s.start()
+    time.sleep(0.25)
+    c = s.stop()
+    assert set(c) == {"sm_mhz", "sm_max_mhz", "reasons", "samples"} and c["reasons"] == [] or c["samples"] > 0
+    d = bench.compact({"value": 2.0, "ms_per_step": 0.1234567, "timing": "CUDA-graph replay of the same launches",
+                       "roofline": {"frac": 0.70123, "bound": "hbm", "peak": 6454.6}, "noise": [1, 2, 3]})
+    assert d == {"value": 2.0, "ms_per_step": 0.12346, "timing": "graph", "frac": 0.7012, "bound": "hbm", "peak": 6454.6}
+    assert bench.compact([{"value": 1.0, "timing": "eager launches"}]) == [{"value": 1.0, "timing": "eager"}]
+    assert bench.compact({"error": "x"}) == {"error": "x"}
